@@ -1,0 +1,155 @@
+"""ctypes binding of oracle/liboracle.so (the CPU oracle -- test infrastructure only)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "liboracle.so")
+
+U64MAX = (1 << 64) - 1
+
+
+class SeqDB(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("offsets", C.c_void_p), ("lens", C.c_void_p), ("keys", C.c_void_p),
+                ("n", C.c_uint64), ("dbtype", C.c_int)]
+
+
+class KmParams(C.Structure):
+    _fields_ = [("kmer_size", C.c_int), ("alph_size", C.c_int), ("kmers_per_seq", C.c_int),
+                ("kmers_per_seq_scale", C.c_float), ("hash_shift", C.c_int), ("include_only_extendable", C.c_int),
+                ("ignore_multi_kmer", C.c_int), ("cov_mode", C.c_int), ("cov_thr", C.c_float),
+                ("hash_start", C.c_uint64), ("hash_end", C.c_uint64)]
+
+
+class RsParams(C.Structure):
+    _fields_ = [("rescore_mode", C.c_int), ("seq_id_thr", C.c_float), ("eval_thr", C.c_double), ("cov_mode", C.c_int),
+                ("cov_thr", C.c_float), ("aln_len_thr", C.c_int), ("seq_id_mode", C.c_int)]
+
+
+class ExParams(C.Structure):
+    _fields_ = [("seq_id_thr", C.c_float), ("max_seq_len", C.c_int), ("keep_target", C.c_int), ("rescore_mode", C.c_int)]
+
+
+KMER_REC = np.dtype([("kmer", "<u8"), ("id", "<u4"), ("seq_len", "<i4"), ("pos", "<i4")], align=True)
+HIT = np.dtype([("rep", "<u4"), ("target", "<u4"), ("score", "<i4"), ("diag", "<i4")], align=True)
+ALN = np.dtype([("query", "<u4"), ("target", "<u4"), ("bits", "<i4"), ("seq_id", "<f4"), ("evalue", "<f8"),
+                ("q_start", "<i4"), ("q_end", "<i4"), ("q_len", "<i4"),
+                ("db_start", "<i4"), ("db_end", "<i4"), ("db_len", "<i4")], align=True)
+assert KMER_REC.itemsize == 24 and HIT.itemsize == 16 and ALN.itemsize == 48
+
+
+def build():
+    src = os.path.join(ORACLE_DIR, "oracle.cpp")
+    deps = [src, os.path.join(ORACLE_DIR, "oracle.h"), os.path.join(ORACLE_DIR, "oracle_tables.h")]
+    if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", LIB_PATH, src], check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.or_hash_u64.restype = C.c_uint64
+        _lib.or_hash_u64.argtypes = [C.c_uint64, C.c_uint64]
+        for f in ("or_evalue", "or_bitscore", "or_raw_from_bits"):
+            getattr(_lib, f).restype = C.c_double
+        _lib.or_evalue.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
+        _lib.or_bitscore.argtypes = [C.c_int, C.c_double]
+        _lib.or_raw_from_bits.argtypes = [C.c_int, C.c_double]
+        _lib.or_free.argtypes = [C.c_void_p]
+    return _lib
+
+
+def seqdb_struct(db):
+    """db: plass_b200.mmseqsdb.DB (arrays must stay alive while the struct is used)."""
+    s = SeqDB()
+    s.data = db.data.ctypes.data
+    s.offsets = db.offsets.ctypes.data
+    s.lens = db.lens.ctypes.data
+    s.keys = db.keys.ctypes.data
+    s.n = db.n
+    s.dbtype = db.dbtype
+    return s
+
+
+def _take(ptr, n, dtype):
+    if n == 0:
+        out = np.zeros(0, dtype=dtype)
+    else:
+        buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr.value)
+        out = np.frombuffer(buf, dtype=dtype).copy()
+    lib().or_free(ptr)
+    return out
+
+
+def extract_kmers(db, kp):
+    out, n = C.c_void_p(), C.c_uint64()
+    s = seqdb_struct(db)
+    rc = lib().or_extract_kmers(C.byref(s), C.byref(kp), C.byref(out), C.byref(n))
+    assert rc == 0
+    return _take(out, n.value, KMER_REC)
+
+
+def kmermatch(db, kp):
+    out, n = C.c_void_p(), C.c_uint64()
+    s = seqdb_struct(db)
+    rc = lib().or_kmermatch(C.byref(s), C.byref(kp), C.byref(out), C.byref(n))
+    assert rc == 0
+    return _take(out, n.value, HIT)
+
+
+def rescore(db, hits, rp):
+    out, n = C.c_void_p(), C.c_uint64()
+    s = seqdb_struct(db)
+    hits = np.ascontiguousarray(hits)
+    rc = lib().or_rescore(C.byref(s), C.c_void_p(hits.ctypes.data), C.c_uint64(len(hits)), C.byref(rp), C.byref(out), C.byref(n))
+    assert rc == 0, rc
+    return _take(out, n.value, ALN)
+
+
+def extend(db, alns, ep):
+    from plass_b200.mmseqsdb import DB
+    od, oo, ol, ok, ex = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    on, ob = C.c_uint64(), C.c_uint64()
+    s = seqdb_struct(db)
+    alns = np.ascontiguousarray(alns)
+    rc = lib().or_extend(C.byref(s), C.c_void_p(alns.ctypes.data), C.c_uint64(len(alns)), C.byref(ep),
+                         C.byref(od), C.byref(oo), C.byref(ol), C.byref(ok), C.byref(ex), C.byref(on), C.byref(ob))
+    assert rc == 0, rc
+    n = on.value
+    data = _take(od, ob.value, np.dtype("u1"))
+    offs = _take(oo, n, np.dtype("<u8"))
+    lens = _take(ol, n, np.dtype("<u4"))
+    keys = _take(ok, n, np.dtype("<u4"))
+    ext = _take(ex, n, np.dtype("u1"))
+    return DB(data, keys, offs, lens, db.dbtype), ext
+
+
+def format_hits_by_rep(db_keys, hits):
+    """Logical content of a prefilter DB: {key: entry bytes} (self line + hit lines)."""
+    buf = C.create_string_buffer(128)
+    out = {int(k): bytearray(b"%d\t0\t0\n" % int(k)) for k in db_keys}
+    L = lib()
+    for h in hits:
+        n = L.or_format_hit(buf, C.c_uint32(int(h["target"])), C.c_int32(int(h["score"])), C.c_int32(int(h["diag"])))
+        out[int(h["rep"])] += buf.raw[:n]
+    return {k: bytes(v) for k, v in out.items()}
+
+
+def format_alns_by_query(db_keys, alns):
+    buf = C.create_string_buffer(256)
+    out = {int(k): bytearray() for k in db_keys}
+    L = lib()
+    alns = np.ascontiguousarray(alns)
+    base = alns.ctypes.data
+    for i in range(len(alns)):
+        n = L.or_format_aln(buf, C.c_void_p(base + i * ALN.itemsize))
+        out[int(alns[i]["query"])] += buf.raw[:n]
+    return {k: bytes(v) for k, v in out.items()}

@@ -1,0 +1,114 @@
+"""Pins the CPU oracle (oracle/oracle.cpp) against outputs of the UNMODIFIED reference binary.
+
+Fixtures: tests/golden/<case>.tar.xz, produced by tests/golden/make_golden.py running
+oracle/_ref/bin/{plass,penguin} (built from /root/reference by oracle/ref_build.mk).  Every hot-path
+step of every iteration is checked independently: the step's golden input DBs go through the oracle
+and the result must equal the golden output DB entry by entry (key -> bytes), i.e. bit-exact text.
+"""
+import os
+import numpy as np
+import pytest
+
+from common import golden_case, parse_pref_entry
+from plass_b200 import mmseqsdb
+import oracle_binding as ob
+import params
+
+CASES = ["example_aa", "synth_aa", "synth_nt"]
+
+
+def _steps(case, golden_root, cmd):
+    d, man = golden_case(case, golden_root)
+    return d, [s for s in man["steps"] if s["cmd"] in cmd]
+
+
+def hits_from_pref(pref):
+    rows = []
+    for i, k in enumerate(pref.keys):
+        for (t, s, dg) in parse_pref_entry(int(k), pref.entry(i)):
+            rows.append((int(k), t, s, dg))
+    return np.array(rows, dtype=ob.HIT) if rows else np.zeros(0, dtype=ob.HIT)
+
+
+def alns_from_db(aln):
+    rows = []
+    for i, k in enumerate(aln.keys):
+        for ln in aln.entry(i).decode().splitlines():
+            c = ln.split("\t")
+            rows.append((int(k), int(c[0]), int(c[1]), np.float32(float(c[2])), float(c[3]),
+                         int(c[4]), int(c[5]), int(c[6]), int(c[7]), int(c[8]), int(c[9])))
+    return np.array(rows, dtype=ob.ALN) if rows else np.zeros(0, dtype=ob.ALN)
+
+
+def assert_same_entries(got, want, what):
+    assert set(got) == set(want), what + ": key sets differ"
+    bad = [k for k in want if got[k] != want[k]]
+    assert not bad, "%s: %d of %d entries differ, first key %d:\n got  %r\n want %r" % (
+        what, len(bad), len(want), bad[0], got[bad[0]][:300], want[bad[0]][:300])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_kmermatcher(case, golden_root):
+    d, steps = _steps(case, golden_root, ("kmermatcher",))
+    assert steps
+    for s in steps:
+        seq = mmseqsdb.read_db(os.path.join(d, s["dbs"][0]))
+        want = mmseqsdb.read_db(os.path.join(d, s["dbs"][1]))
+        hits = ob.kmermatch(seq, params.oracle_km(s["args"], seq.dbtype == 1))
+        got = ob.format_hits_by_rep(seq.keys, hits)
+        assert want.dbtype == (14 if seq.dbtype == 1 else 7)
+        assert_same_entries(got, want.entries_by_key(), "%s/%s" % (case, s["dbs"][1]))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_rescorediagonal(case, golden_root):
+    d, steps = _steps(case, golden_root, ("rescorediagonal",))
+    assert steps
+    for s in steps:
+        seq = mmseqsdb.read_db(os.path.join(d, s["dbs"][0]))
+        pref = mmseqsdb.read_db(os.path.join(d, s["dbs"][2]))
+        want = mmseqsdb.read_db(os.path.join(d, s["dbs"][3]))
+        alns = ob.rescore(seq, hits_from_pref(pref), params.oracle_rs(s["args"]))
+        got = ob.format_alns_by_query(seq.keys, alns)
+        assert_same_entries(got, want.entries_by_key(), "%s/%s" % (case, s["dbs"][3]))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_assembleresults(case, golden_root):
+    d, steps = _steps(case, golden_root, ("assembleresults", "nuclassembleresults"))
+    assert steps
+    for s in steps:
+        seq = mmseqsdb.read_db(os.path.join(d, s["dbs"][0]))
+        aln = mmseqsdb.read_db(os.path.join(d, s["dbs"][1]))
+        want = mmseqsdb.read_db(os.path.join(d, s["dbs"][2]))
+        alns = alns_from_db(aln)
+        # the float parsed from the 3-decimal text must print back to the same text
+        assert_same_entries(ob.format_alns_by_query(seq.keys, alns), aln.entries_by_key(), "aln text round trip")
+        out, ext = ob.extend(seq, alns, params.oracle_ex(s["args"]))
+        assert out.dbtype == want.dbtype
+        assert_same_entries(out.entries_by_key(), want.entries_by_key(), "%s/%s" % (case, s["dbs"][2]))
+        assert ext.sum() > 0
+
+
+def test_xxh64_known_answers():
+    # SURVEY.md A.1 KATs (vendored xxhash.h, XXH64(le64(v), seed))
+    kats = [(67, 0, 0x694b701bc9e44ec7), (67, 1, 0x65d8542382d84f46), (67, 0x0123456789ABCDEF, 0x05ba4c1df800d008),
+            (67, 12 ** 14 - 1, 0xae465f8955fd9423), (67, 2 ** 44 - 1, 0xff6d4ee59ddc5537),
+            (68, 0, 0xaaa171741b9abdd1), (68, 1, 0x610900b3b71600dc), (68, 0x0123456789ABCDEF, 0x42c4b3605484fb17)]
+    for seed, v, h in kats:
+        assert ob.lib().or_hash_u64(v, seed) == h
+
+
+def test_evalue_known_answers():
+    import json
+    from common import GOLDEN
+    t = json.load(open(os.path.join(GOLDEN, "tables.json")))
+    L = ob.lib()
+    assert L.or_bitscore(0, 255.0) == t["aa_kat_bits255"]
+    assert L.or_raw_from_bits(0, 121.0) == t["aa_kat_raw121"]
+    assert L.or_evalue(0, 1e8, 255.0, 50.0) == t["aa_kat_eval_255_50_1e8"]
+    assert L.or_evalue(0, 1e8, 67.0, 50.0) == t["aa_kat_eval_67_50_1e8"]
+    assert L.or_evalue(0, 1e8, 30.0, 21.0) == t["aa_kat_eval_30_21_1e8"]
+    assert L.or_bitscore(1, 300.0) == t["nt_kat_bits300"]
+    assert L.or_evalue(1, 1.5e8, 300.0, 150.0) == t["nt_kat_eval_300_150_1.5e8"]
+    assert L.or_evalue(1, 1.5e8, 98.0, 150.0) == t["nt_kat_eval_98_150_1.5e8"]
