@@ -1,0 +1,150 @@
+/* plassgpu.h -- C ABI of the B200-native assemble-iteration hot path (libplassgpu.so).
+ *
+ * Drop-in boundary: these entry points are what the reference's four hot-path commands bind to when
+ * the CPU implementations are swapped out (see INTEGRATION.md for the Command-table stub):
+ *
+ *   pg_kmermatch   replaces  kmermatcherInner<T>           lib/mmseqs/src/linclust/kmermatcher.cpp:589-733
+ *                            (fillKmerPositionArray :77-385, SORT_PARALLEL :408-412,427-431,
+ *                             assignGroup :450-559, writeKmerMatcherResult :809-924)
+ *   pg_rescore     replaces  doRescorediagonal             lib/mmseqs/src/alignment/rescorediagonal.cpp:45-379
+ *   pg_extend      replaces  doassembly / doNuclAssembly   src/assembler/assembleresult.cpp:110-356,
+ *                                                          src/assembler/nuclassembleresult.cpp:144-398
+ *   pg_seqdb_*     replaces  DBReader<unsigned int>::getData/getSeqLen/getDbKey views
+ *                                                          lib/mmseqs/src/commons/DBReader.h:151-236
+ *
+ * Plain C: pointers + sizes, no C++ or torch types.  All functions return 0 on success, non-zero on
+ * error (pg_last_error() gives the message).  There is no CPU fallback: without a CUDA device every
+ * compute entry point fails.  Arrays returned through `**out` parameters are pinned host memory owned
+ * by the caller, released with pg_free_host().
+ */
+#ifndef PLASSGPU_H
+#define PLASSGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_DBTYPE_AMINO_ACIDS 0   /* Parameters::DBTYPE_AMINO_ACIDS  (lib/mmseqs/src/commons/Parameters.h:65-79) */
+#define PG_DBTYPE_NUCLEOTIDES 1   /* Parameters::DBTYPE_NUCLEOTIDES */
+
+typedef struct pg_context pg_context; /* one per process/GPU: device, stream, workspace, (optional) NCCL comm */
+typedef struct pg_seqdb pg_seqdb;     /* a sequence DB resident in HBM */
+
+/* Host view of a sequence DB exactly as DBReader exposes it: entry i = data[offsets[i] .. +lens[i]) =
+ * residues + '\n' + '\0' (getSeqLen = lens[i]-2, DBReader.h:192-213); keys ascending (index order). */
+typedef struct {
+    const char *data;
+    uint64_t data_bytes;
+    const uint64_t *offsets;
+    const uint32_t *lens;
+    const uint32_t *keys;
+    uint64_t n;
+    int dbtype;
+} pg_seqdb_view;
+
+/* kmermatcher flags that reach the kernels (Parameters.cpp:871-892).  Unsupported settings
+ * (--mask 1, --spaced-kmer-mode 1, --adjust-kmer-len 1, custom --sub-mat) are rejected by the caller. */
+typedef struct {
+    int kmer_size;               /* -k */
+    int alph_size;               /* --alph-size (aa: 13 reduced / 21 full; nt: 5) */
+    int kmers_per_seq;           /* --kmer-per-seq */
+    float kmers_per_seq_scale;   /* --kmer-per-seq-scale */
+    int hash_shift;              /* --hash-shift */
+    int include_only_extendable; /* --include-only-extendable */
+    int ignore_multi_kmer;       /* --ignore-multi-kmer */
+    int cov_mode;                /* --cov-mode */
+    float cov_thr;               /* -c */
+    uint32_t hash_start;         /* inclusive 16-bit hash range of this shard (setupKmerSplits, kmermatcher.cpp:736-778) */
+    uint32_t hash_end;           /* 0..65535 = everything */
+} pg_km_params;
+
+/* One prefilter hit line of the block of `rep`: "target \t score \t diag" (QueryMatcher.h:35-51,114-126).
+ * score < 0 <=> reverse strand (nt, DBTYPE_PREFILTER_REV_RES). Ordered by (rep, target). */
+typedef struct {
+    uint32_t rep;
+    uint32_t target;
+    int32_t score;
+    int32_t diag; /* (short) of the 16-bit diagonal, as printed */
+} pg_hit;
+
+typedef struct {          /* Parameters.cpp:422-439 */
+    int rescore_mode;     /* --rescore-mode, only 3 (END_TO_END) */
+    float seq_id_thr;     /* --min-seq-id */
+    double eval_thr;      /* -e */
+    int cov_mode;         /* --cov-mode */
+    float cov_thr;        /* -c */
+    int aln_len_thr;      /* --min-aln-len */
+    int seq_id_mode;      /* --seq-id-mode */
+} pg_rs_params;
+
+/* One accepted alignment = the printed fields of Matcher::result_t (Matcher.h:32-91, Matcher.cpp:323-370).
+ * Ordered by (query, prefilter order); the self alignment of every query comes first. */
+typedef struct {
+    uint32_t query;
+    uint32_t target;
+    int32_t bits;
+    float seq_id;
+    double evalue;
+    int32_t q_start, q_end, q_len;
+    int32_t db_start, db_end, db_len;
+} pg_aln;
+
+typedef struct {          /* src/commons/LocalParameters.h:96-102 */
+    float seq_id_thr;     /* --min-seq-id */
+    int max_seq_len;      /* --max-seq-len */
+    int keep_target;      /* --keep-target */
+    int rescore_mode;     /* --rescore-mode, only 3 */
+} pg_ex_params;
+
+/* Device time (CUDA events on the library's stream) of the stages of the last call, in ms. */
+typedef struct {
+    float extract_ms, sort1_ms, group_ms, sort2_ms, reduce_ms;   /* kmermatcher */
+    float rescore_ms, extend_ms, exchange_ms, total_ms;
+    uint64_t n_kmer_records;   /* records entering sort #1 (Sum m) */
+    uint64_t n_pair_records;   /* records entering sort #2 */
+    uint64_t n_hits;           /* prefilter hit lines (h) */
+    uint64_t n_alns;           /* accepted alignments */
+    uint64_t n_extended;       /* sequences that became contigs */
+    uint64_t kernel_launches;  /* kernels launched by the last call */
+    uint64_t sort1_bytes;      /* algorithmic bytes of sort #1: one read + one write of every record */
+} pg_timings;
+
+const char *pg_last_error(void);
+int pg_device_count(void);
+int pg_init(int device, pg_context **ctx);
+void pg_destroy(pg_context *ctx);
+int pg_get_timings(const pg_context *ctx, pg_timings *out);
+
+int pg_seqdb_upload(pg_context *ctx, const pg_seqdb_view *view, pg_seqdb **db);
+/* Copies a device-resident DB back: all four arrays are pinned host buffers (pg_free_host). */
+int pg_seqdb_download(pg_context *ctx, const pg_seqdb *db, char **data, uint64_t *data_bytes, uint64_t **offsets,
+                      uint32_t **lens, uint32_t **keys, uint64_t *n);
+uint64_t pg_seqdb_size(const pg_seqdb *db);
+void pg_seqdb_free(pg_context *ctx, pg_seqdb *db);
+
+/* The three steps with HOST inputs/outputs (what the command shims call). */
+int pg_kmermatch(pg_context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **hits, uint64_t *n_hits);
+int pg_rescore(pg_context *ctx, const pg_seqdb *db, const pg_hit *hits, uint64_t n_hits, const pg_rs_params *p,
+               pg_aln **alns, uint64_t *n_alns);
+int pg_extend(pg_context *ctx, const pg_seqdb *db, const pg_aln *alns, uint64_t n_alns, const pg_ex_params *p,
+              pg_seqdb **out_db, uint8_t **extended);
+
+/* One whole assemble iteration kept in HBM: kmermatcher -> rescorediagonal -> (nucl)assembleresults.
+ * `out_db` is the next iteration's input.  If hits/alns pointers are non-NULL the intermediate
+ * results are also copied to pinned host arrays (for writing pref_N / aln_N). */
+int pg_assemble_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, const pg_rs_params *rp,
+                          const pg_ex_params *ep, pg_seqdb **out_db,
+                          pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns);
+
+/* Multi-GPU (one process per GPU): attach an NCCL communicator created by the caller
+ * (ncclComm_t passed as void*).  With a communicator attached, pg_kmermatch / pg_assemble_iteration
+ * shard the k-mer hash space over the ranks and exchange candidate pairs with one all-to-all. */
+int pg_set_comm(pg_context *ctx, void *nccl_comm, int rank, int world);
+
+void pg_free_host(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

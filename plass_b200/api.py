@@ -1,0 +1,235 @@
+"""ctypes binding of libplassgpu.so -- the host-side mirror of the C ABI in include/plassgpu.h.
+
+Function names and argument meaning follow the reference's three hot-path commands
+(kmermatcher / rescorediagonal / assembleresults); see INTEGRATION.md.  There is no CPU fallback:
+loading works without a GPU (so that the symbol table can be checked), every compute call fails
+loudly when no CUDA device is present.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from . import mmseqsdb
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libplassgpu.so")
+
+# symbols include/plassgpu.h declares
+EXPORTS = ["pg_last_error", "pg_device_count", "pg_init", "pg_destroy", "pg_get_timings", "pg_seqdb_upload",
+           "pg_seqdb_download", "pg_seqdb_size", "pg_seqdb_free", "pg_kmermatch", "pg_rescore", "pg_extend",
+           "pg_assemble_iteration", "pg_free_host",
+           ]
+
+
+class SeqDBView(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("data_bytes", C.c_uint64), ("offsets", C.c_void_p), ("lens", C.c_void_p),
+                ("keys", C.c_void_p), ("n", C.c_uint64), ("dbtype", C.c_int)]
+
+
+class KmParams(C.Structure):
+    _fields_ = [("kmer_size", C.c_int), ("alph_size", C.c_int), ("kmers_per_seq", C.c_int),
+                ("kmers_per_seq_scale", C.c_float), ("hash_shift", C.c_int), ("include_only_extendable", C.c_int),
+                ("ignore_multi_kmer", C.c_int), ("cov_mode", C.c_int), ("cov_thr", C.c_float),
+                ("hash_start", C.c_uint32), ("hash_end", C.c_uint32)]
+
+
+class RsParams(C.Structure):
+    _fields_ = [("rescore_mode", C.c_int), ("seq_id_thr", C.c_float), ("eval_thr", C.c_double), ("cov_mode", C.c_int),
+                ("cov_thr", C.c_float), ("aln_len_thr", C.c_int), ("seq_id_mode", C.c_int)]
+
+
+class ExParams(C.Structure):
+    _fields_ = [("seq_id_thr", C.c_float), ("max_seq_len", C.c_int), ("keep_target", C.c_int), ("rescore_mode", C.c_int)]
+
+
+class Timings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("extract_ms", "sort1_ms", "group_ms", "sort2_ms", "reduce_ms", "rescore_ms",
+                                         "extend_ms", "exchange_ms", "total_ms")] + \
+               [(n, C.c_uint64) for n in ("n_kmer_records", "n_pair_records", "n_hits", "n_alns", "n_extended",
+                                          "kernel_launches", "sort1_bytes")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+HIT = np.dtype([("rep", "<u4"), ("target", "<u4"), ("score", "<i4"), ("diag", "<i4")], align=True)
+ALN = np.dtype([("query", "<u4"), ("target", "<u4"), ("bits", "<i4"), ("seq_id", "<f4"), ("evalue", "<f8"),
+                ("q_start", "<i4"), ("q_end", "<i4"), ("q_len", "<i4"),
+                ("db_start", "<i4"), ("db_end", "<i4"), ("db_len", "<i4")], align=True)
+
+
+def default_km_params(nucl=False, **kw):
+    """Workflow defaults: Assembler.cpp:10-27 (aa) / Nuclassembler.cpp:10-32 (nt)."""
+    p = KmParams(kmer_size=22 if nucl else 14, alph_size=5 if nucl else 13, kmers_per_seq=60,
+                 kmers_per_seq_scale=0.1 if nucl else 0.0, hash_shift=67, include_only_extendable=1 if nucl else 0,
+                 ignore_multi_kmer=1, cov_mode=0, cov_thr=0.0, hash_start=0, hash_end=65535)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def default_rs_params(nucl=False, **kw):
+    p = RsParams(rescore_mode=3, seq_id_thr=0.99 if nucl else 0.9, eval_thr=1e-5, cov_mode=0, cov_thr=0.0, aln_len_thr=0, seq_id_mode=0)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def default_ex_params(nucl=False, **kw):
+    p = ExParams(seq_id_thr=0.99 if nucl else 0.9, max_seq_len=200000 if nucl else 65535, keep_target=1, rescore_mode=3)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library.  Raises if it has not been built (python -m plass_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libplassgpu.so is missing -- build it with `python -m plass_b200.build`; there is no CPU fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.pg_last_error.restype = C.c_char_p
+        _lib.pg_seqdb_size.restype = C.c_uint64
+        _lib.pg_seqdb_size.argtypes = [C.c_void_p]
+        _lib.pg_free_host.argtypes = [C.c_void_p]
+        _lib.pg_destroy.argtypes = [C.c_void_p]
+        _lib.pg_seqdb_free.argtypes = [C.c_void_p, C.c_void_p]
+    return _lib
+
+
+class PlassGpuError(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise PlassGpuError("%s failed: %s" % (what, load_library().pg_last_error().decode()))
+
+
+def _take(ptr, n, dtype):
+    lib = load_library()
+    if n == 0:
+        out = np.zeros(0, dtype=dtype)
+    else:
+        out = np.frombuffer((C.c_char * (n * dtype.itemsize)).from_address(ptr.value), dtype=dtype).copy()
+    if ptr.value:
+        lib.pg_free_host(ptr)
+    return out
+
+
+class DeviceSeqDB:
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self.handle = handle
+
+    @property
+    def n(self):
+        return int(load_library().pg_seqdb_size(self.handle))
+
+    def download(self):
+        lib = load_library()
+        d, o, l, k = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nb, n = C.c_uint64(), C.c_uint64()
+        _check(lib.pg_seqdb_download(self.ctx.handle, self.handle, C.byref(d), C.byref(nb), C.byref(o), C.byref(l), C.byref(k), C.byref(n)), "pg_seqdb_download")
+        return mmseqsdb.DB(_take(d, nb.value, np.dtype("u1")), _take(k, n.value, np.dtype("<u4")),
+                           _take(o, n.value, np.dtype("<u8")), _take(l, n.value, np.dtype("<u4")), self.dbtype)
+
+    def free(self):
+        if self.handle:
+            load_library().pg_seqdb_free(self.ctx.handle, self.handle)
+            self.handle = None
+
+
+class Context:
+    """One GPU.  Methods mirror the reference commands they replace."""
+
+    def __init__(self, device=0):
+        lib = load_library()
+        h = C.c_void_p()
+        _check(lib.pg_init(C.c_int(device), C.byref(h)), "pg_init")
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if self.handle:
+            load_library().pg_destroy(self.handle)
+            self.handle = None
+
+    def timings(self):
+        t = Timings()
+        _check(load_library().pg_get_timings(self.handle, C.byref(t)), "pg_get_timings")
+        return t.as_dict()
+
+    def upload(self, db):
+        """db: mmseqsdb.DB (host).  Returns a DeviceSeqDB resident in HBM."""
+        v = SeqDBView()
+        data = np.ascontiguousarray(db.data)
+        offs = np.ascontiguousarray(db.offsets, dtype=np.uint64)
+        lens = np.ascontiguousarray(db.lens, dtype=np.uint32)
+        keys = np.ascontiguousarray(db.keys, dtype=np.uint32)
+        v.data, v.data_bytes = data.ctypes.data, data.nbytes
+        v.offsets, v.lens, v.keys, v.n, v.dbtype = offs.ctypes.data, lens.ctypes.data, keys.ctypes.data, db.n, db.dbtype
+        h = C.c_void_p()
+        _check(load_library().pg_seqdb_upload(self.handle, C.byref(v), C.byref(h)), "pg_seqdb_upload")
+        d = DeviceSeqDB(self, h)
+        d.dbtype = db.dbtype
+        return d
+
+    # kmermatcher (lib/mmseqs/src/linclust/kmermatcher.cpp:780)
+    def kmermatcher(self, ddb, kp):
+        out, n = C.c_void_p(), C.c_uint64()
+        _check(load_library().pg_kmermatch(self.handle, ddb.handle, C.byref(kp), C.byref(out), C.byref(n)), "pg_kmermatch")
+        return _take(out, n.value, HIT)
+
+    # rescorediagonal (lib/mmseqs/src/alignment/rescorediagonal.cpp:381)
+    def rescorediagonal(self, ddb, hits, rp):
+        hits = np.ascontiguousarray(hits, dtype=HIT)
+        out, n = C.c_void_p(), C.c_uint64()
+        _check(load_library().pg_rescore(self.handle, ddb.handle, C.c_void_p(hits.ctypes.data), C.c_uint64(len(hits)),
+                                         C.byref(rp), C.byref(out), C.byref(n)), "pg_rescore")
+        return _take(out, n.value, ALN)
+
+    # assembleresults / nuclassembleresults (src/assembler/assembleresult.cpp:358, nuclassembleresult.cpp:400)
+    def assembleresults(self, ddb, alns, ep):
+        alns = np.ascontiguousarray(alns, dtype=ALN)
+        h, ext = C.c_void_p(), C.c_void_p()
+        _check(load_library().pg_extend(self.handle, ddb.handle, C.c_void_p(alns.ctypes.data), C.c_uint64(len(alns)),
+                                        C.byref(ep), C.byref(h), C.byref(ext)), "pg_extend")
+        out = DeviceSeqDB(self, h)
+        out.dbtype = ddb.dbtype
+        return out, _take(ext, out.n, np.dtype("u1"))
+
+    def assemble_iteration(self, ddb, kp, rp, ep, want_intermediates=False):
+        """One fused iteration in HBM.  Returns (next DeviceSeqDB, hits or None, alns or None)."""
+        h = C.c_void_p()
+        if want_intermediates:
+            ho, hn, ao, an = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+            _check(load_library().pg_assemble_iteration(self.handle, ddb.handle, C.byref(kp), C.byref(rp), C.byref(ep), C.byref(h),
+                                                        C.byref(ho), C.byref(hn), C.byref(ao), C.byref(an)), "pg_assemble_iteration")
+            hits, alns = _take(ho, hn.value, HIT), _take(ao, an.value, ALN)
+        else:
+            _check(load_library().pg_assemble_iteration(self.handle, ddb.handle, C.byref(kp), C.byref(rp), C.byref(ep), C.byref(h),
+                                                        None, None, None, None), "pg_assemble_iteration")
+            hits = alns = None
+        out = DeviceSeqDB(self, h)
+        out.dbtype = ddb.dbtype
+        return out, hits, alns
+
+    # diagnostics
+    def debug_extract(self, ddb, kp):
+        out, n = C.c_void_p(), C.c_uint64()
+        _check(load_library().pg_debug_extract(self.handle, ddb.handle, C.byref(kp), C.byref(out), C.byref(n)), "pg_debug_extract")
+        return _take(out, n.value, np.dtype([("w0", "<u8"), ("w1", "<u8")]))
+
+    def debug_radix_sort(self, recs, ranges):
+        """recs: (n,2) uint64; ranges: list of (word, lo, hi) least-significant first."""
+        recs = np.ascontiguousarray(recs, dtype=np.uint64)
+        w = (C.c_int * len(ranges))(*[r[0] for r in ranges])
+        lo = (C.c_int * len(ranges))(*[r[1] for r in ranges])
+        hi = (C.c_int * len(ranges))(*[r[2] for r in ranges])
+        _check(load_library().pg_debug_radix_sort(self.handle, C.c_void_p(recs.ctypes.data), C.c_uint64(len(recs)), w, lo, hi, len(ranges)), "pg_debug_radix_sort")
+        return recs

@@ -1,0 +1,275 @@
+// pg_api.cu -- the C ABI of libplassgpu.so (declared in include/plassgpu.h).
+#include "pg_internal.cuh"
+
+#include <mutex>
+#include <vector>
+
+namespace pg {
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+
+void seqdb_release(pg_seqdb *db) {
+    if (!db) return;
+    if (db->data) cudaFree(db->data);
+    if (db->offsets) cudaFree(db->offsets);
+    if (db->lens) cudaFree(db->lens);
+    if (db->keys) cudaFree(db->keys);
+    delete db;
+}
+
+// max length, residue count, max key, key density -- one small reduction kernel
+__global__ void seqdb_stats_kernel(const unsigned *__restrict__ lens, const unsigned *__restrict__ keys, unsigned long long n,
+                                   unsigned long long *__restrict__ out /* [0] sum(len), [1] maxLen, [2] maxKey, [3] nonDense */) {
+    unsigned long long sum = 0, mx = 0, mk = 0, nd = 0;
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
+        const unsigned l = lens[i], k = keys[i];
+        sum += l; mx = max(mx, (unsigned long long) l); mk = max(mk, (unsigned long long) k); nd += (k != (unsigned) i);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        nd += __shfl_xor_sync(0xFFFFFFFFu, nd, o);
+        mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        mk = max(mk, __shfl_xor_sync(0xFFFFFFFFu, mk, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], sum); atomicMax(&out[1], mx); atomicMax(&out[2], mk); atomicAdd(&out[3], nd); }
+}
+
+int seqdb_finalize(Context *ctx, pg_seqdb *db) {
+    PG_TRY(ctx->small.reserve(4096));
+    unsigned long long *d = ctx->small.as<unsigned long long>() + 16;
+    PG_CUDA(cudaMemsetAsync(d, 0, 32, ctx->stream));
+    if (db->n) seqdb_stats_kernel<<<NUM_SMS * 2, 256, 0, ctx->stream>>>(db->lens, db->keys, db->n, d);
+    unsigned long long h[4];
+    PG_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    db->residues = (double) h[0] - 2.0 * (double) db->n;        // DBReader::getAminoAcidDBSize (DBReader.cpp:537-546)
+    db->max_seq_len = h[1] >= 2 ? (unsigned) (h[1] - 2) : 0;
+    db->max_key = (unsigned) h[2];
+    db->dense_keys = (h[3] == 0);
+    return 0;
+}
+
+template <class T>
+static int to_host(cudaStream_t s, const T *d, uint64_t n, T **out) {
+    T *h = nullptr;
+    PG_CUDA(cudaMallocHost(&h, sizeof(T) * (n + 1)));
+    if (n) PG_CUDA(cudaMemcpyAsync(h, d, sizeof(T) * n, cudaMemcpyDeviceToHost, s));
+    PG_CUDA(cudaStreamSynchronize(s));
+    *out = h;
+    return 0;
+}
+
+static void collect_timings(Context *ctx) {
+    pg_timings &t = ctx->timings;
+    auto el = [&](int a, int b) { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]) != cudaSuccess) { ms = 0; cudaGetLastError(); } return ms; };
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->kmRan) {
+        t.extract_ms = el(EV_KM_BEGIN, EV_EXTRACT_END);
+        t.sort1_ms = el(EV_SORT1_BEGIN, EV_SORT1_END);
+        t.group_ms = el(EV_SORT1_END, EV_GROUP_END);
+        t.sort2_ms = el(EV_GROUP_END, EV_SORT2_END);
+        t.reduce_ms = el(EV_SORT2_END, EV_REDUCE_END);
+    }
+    if (ctx->rsRan) t.rescore_ms = el(EV_RS_BEGIN, EV_RS_END);
+    if (ctx->exRan) t.extend_ms = el(EV_EX_BEGIN, EV_EX_END);
+    t.total_ms = el(EV_TOTAL_BEGIN, EV_TOTAL_END);
+    t.kernel_launches = ctx->launches;
+}
+
+static void begin_call(Context *ctx) {
+    cudaSetDevice(ctx->device);
+    ctx->kmRan = ctx->rsRan = ctx->exRan = false;
+    ctx->launches = 0;
+    memset(&ctx->timings, 0, sizeof(ctx->timings));
+    cudaEventRecord(ctx->ev[EV_TOTAL_BEGIN], ctx->stream);
+}
+static void end_call(Context *ctx) {
+    cudaEventRecord(ctx->ev[EV_TOTAL_END], ctx->stream);
+    collect_timings(ctx);
+}
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" {
+
+const char *pg_last_error(void) { return g_error.c_str(); }
+
+int pg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pg_init(int device, pg_context **out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error(std::string("pg_init: no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+        cudaGetLastError();
+        return 1;
+    }
+    PG_CHECK(device >= 0 && device < n, "pg_init: device index out of range");
+    PG_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PG_CUDA(cudaGetDeviceProperties(&prop, device));
+    PG_CHECK(prop.major == 10, "pg_init: this build targets sm_100a (B200) only");
+    pg_context *ctx = new pg_context();
+    ctx->device = device;
+    PG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < EV_COUNT; i++) PG_CUDA(cudaEventCreate(&ctx->ev[i]));
+    memset(&ctx->timings, 0, sizeof(ctx->timings));
+    *out = ctx;
+    return 0;
+}
+
+void pg_destroy(pg_context *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->small, &ctx->lists, &ctx->recA, &ctx->recB, &ctx->radixWs, &ctx->scratch, &ctx->blockCounts, &ctx->hits,
+                      &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta};
+    for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int pg_get_timings(const pg_context *ctx, pg_timings *out) {
+    PG_CHECK(ctx && out, "pg_get_timings: null argument");
+    *out = ctx->timings;
+    return 0;
+}
+
+int pg_seqdb_upload(pg_context *ctx, const pg_seqdb_view *v, pg_seqdb **out) {
+    PG_CHECK(ctx && v && out, "pg_seqdb_upload: null argument");
+    PG_CHECK(v->dbtype == PG_DBTYPE_AMINO_ACIDS || v->dbtype == PG_DBTYPE_NUCLEOTIDES, "pg_seqdb_upload: dbtype must be amino acids (0) or nucleotides (1)");
+    PG_CHECK(v->n < 0xFFFFFFF0ull, "pg_seqdb_upload: more than 2^32 sequences");
+    cudaSetDevice(ctx->device);
+    pg_seqdb *db = new pg_seqdb();
+    db->n = v->n; db->data_bytes = v->data_bytes; db->dbtype = v->dbtype;
+    PG_CUDA(cudaMalloc(&db->data, v->data_bytes + 16));
+    PG_CUDA(cudaMalloc(&db->offsets, sizeof(unsigned long long) * (v->n + 1)));
+    PG_CUDA(cudaMalloc(&db->lens, sizeof(unsigned) * (v->n + 1)));
+    PG_CUDA(cudaMalloc(&db->keys, sizeof(unsigned) * (v->n + 1)));
+    PG_CUDA(cudaMemcpyAsync(db->data, v->data, v->data_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(db->offsets, v->offsets, sizeof(unsigned long long) * v->n, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(db->lens, v->lens, sizeof(unsigned) * v->n, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(cudaMemcpyAsync(db->keys, v->keys, sizeof(unsigned) * v->n, cudaMemcpyHostToDevice, ctx->stream));
+    PG_TRY(seqdb_finalize(ctx, db));
+    for (uint64_t i = 1; i < v->n; i++)
+        if (v->keys[i] <= v->keys[i - 1]) { seqdb_release(db); set_error("pg_seqdb_upload: keys must be strictly ascending (index order of a sequence DB)"); return 1; }
+    *out = db;
+    return 0;
+}
+
+int pg_seqdb_download(pg_context *ctx, const pg_seqdb *db, char **data, uint64_t *data_bytes, uint64_t **offsets,
+                      uint32_t **lens, uint32_t **keys, uint64_t *n) {
+    PG_CHECK(ctx && db, "pg_seqdb_download: null argument");
+    cudaSetDevice(ctx->device);
+    PG_TRY(to_host(ctx->stream, db->data, db->data_bytes, data));
+    PG_TRY(to_host(ctx->stream, (const uint64_t *) db->offsets, db->n, offsets));
+    PG_TRY(to_host(ctx->stream, db->lens, db->n, lens));
+    PG_TRY(to_host(ctx->stream, db->keys, db->n, keys));
+    *data_bytes = db->data_bytes; *n = db->n;
+    return 0;
+}
+
+uint64_t pg_seqdb_size(const pg_seqdb *db) { return db ? db->n : 0; }
+
+void pg_seqdb_free(pg_context *ctx, pg_seqdb *db) {
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    seqdb_release(db);
+}
+
+int pg_kmermatch(pg_context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **hits, uint64_t *n_hits) {
+    PG_CHECK(ctx && db && p && hits && n_hits, "pg_kmermatch: null argument");
+    begin_call(ctx);
+    pg_hit *d = nullptr; uint64_t n = 0;
+    PG_TRY(km_run(ctx, db, p, &d, &n));
+    PG_TRY(to_host(ctx->stream, d, n, hits));
+    *n_hits = n;
+    end_call(ctx);
+    return 0;
+}
+
+int pg_rescore(pg_context *ctx, const pg_seqdb *db, const pg_hit *hits, uint64_t n_hits, const pg_rs_params *p,
+               pg_aln **alns, uint64_t *n_alns) {
+    PG_CHECK(ctx && db && p && alns && n_alns && (hits || n_hits == 0), "pg_rescore: null argument");
+    begin_call(ctx);
+    PG_TRY(ctx->hits.reserve(sizeof(pg_hit) * (n_hits + 1)));
+    if (n_hits) PG_CUDA(cudaMemcpyAsync(ctx->hits.p, hits, sizeof(pg_hit) * n_hits, cudaMemcpyHostToDevice, ctx->stream));
+    for (uint64_t i = 1; i < n_hits; i++)
+        PG_CHECK(hits[i - 1].rep <= hits[i].rep, "pg_rescore: hits must be ordered by rep (prefilter DB order)");
+    pg_aln *d = nullptr; uint64_t n = 0;
+    PG_TRY(rs_run(ctx, db, ctx->hits.as<pg_hit>(), n_hits, p, &d, &n));
+    PG_TRY(to_host(ctx->stream, d, n, alns));
+    *n_alns = n;
+    end_call(ctx);
+    return 0;
+}
+
+int pg_extend(pg_context *ctx, const pg_seqdb *db, const pg_aln *alns, uint64_t n_alns, const pg_ex_params *p,
+              pg_seqdb **out_db, uint8_t **extended) {
+    PG_CHECK(ctx && db && p && out_db && (alns || n_alns == 0), "pg_extend: null argument");
+    begin_call(ctx);
+    PG_TRY(ctx->alns.reserve(sizeof(pg_aln) * (n_alns + 1)));
+    if (n_alns) PG_CUDA(cudaMemcpyAsync(ctx->alns.p, alns, sizeof(pg_aln) * n_alns, cudaMemcpyHostToDevice, ctx->stream));
+    for (uint64_t i = 1; i < n_alns; i++)
+        PG_CHECK(alns[i - 1].query <= alns[i].query, "pg_extend: alignments must be ordered by query");
+    unsigned char *dExt = nullptr;
+    PG_TRY(ex_run(ctx, db, ctx->alns.as<pg_aln>(), n_alns, p, out_db, &dExt));
+    if (extended) PG_TRY(to_host(ctx->stream, dExt, (*out_db)->n, extended));
+    cudaFree(dExt);
+    end_call(ctx);
+    return 0;
+}
+
+int pg_assemble_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, const pg_rs_params *rp,
+                          const pg_ex_params *ep, pg_seqdb **out_db,
+                          pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns) {
+    PG_CHECK(ctx && db && kp && rp && ep && out_db, "pg_assemble_iteration: null argument");
+    begin_call(ctx);
+    pg_hit *dHits = nullptr; uint64_t nH = 0;
+    PG_TRY(km_run(ctx, db, kp, &dHits, &nH));
+    pg_aln *dAlns = nullptr; uint64_t nA = 0;
+    PG_TRY(rs_run(ctx, db, dHits, nH, rp, &dAlns, &nA));
+    unsigned char *dExt = nullptr;
+    PG_TRY(ex_run(ctx, db, dAlns, nA, ep, out_db, &dExt));
+    {   // number of new contigs, for the statistics
+        std::vector<unsigned char> h((*out_db)->n + 1);
+        PG_CUDA(cudaMemcpyAsync(h.data(), dExt, (*out_db)->n, cudaMemcpyDeviceToHost, ctx->stream));
+        PG_CUDA(cudaStreamSynchronize(ctx->stream));
+        uint64_t c = 0;
+        for (uint64_t i = 0; i < (*out_db)->n; i++) c += h[i];
+        ctx->timings.n_extended = c;
+    }
+    cudaFree(dExt);
+    end_call(ctx);
+    if (hits && n_hits) { PG_TRY(to_host(ctx->stream, dHits, nH, hits)); *n_hits = nH; }
+    if (alns && n_alns) { PG_TRY(to_host(ctx->stream, dAlns, nA, alns)); *n_alns = nA; }
+    return 0;
+}
+
+void pg_free_host(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- diagnostics used by the tests (not part of the drop-in surface) --------------------------------
+int pg_debug_radix_sort(pg_context *ctx, uint64_t *recs /* n x 2 u64, in place */, uint64_t n, const int *word, const int *lo, const int *hi, int nRanges) {
+    PG_CHECK(ctx && recs, "pg_debug_radix_sort: null argument");
+    cudaSetDevice(ctx->device);
+    RadixPlan plan; plan.npasses = 0;
+    for (int i = 0; i < nRanges; i++) plan_add_bits(plan, word[i], lo[i], hi[i]);
+    PG_TRY(ctx->recA.reserve(sizeof(Rec) * (n + 1)));
+    PG_TRY(ctx->recB.reserve(sizeof(Rec) * (n + 1)));
+    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(n)));
+    PG_CUDA(cudaMemcpyAsync(ctx->recA.p, recs, sizeof(Rec) * n, cudaMemcpyHostToDevice, ctx->stream));
+    Rec *sorted = nullptr;
+    uint64_t launches = 0;
+    PG_TRY(radix_sort(ctx->recA.as<Rec>(), ctx->recB.as<Rec>(), n, plan, ctx->radixWs.p, ctx->radixWs.cap, ctx->stream, &sorted, &launches));
+    PG_CUDA(cudaMemcpyAsync(recs, sorted, sizeof(Rec) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,446 @@
+// pg_extend.cu -- GPU greedy contig extension (assembleresults / nuclassembleresults).
+//
+// Replaces doassembly (reference src/assembler/assembleresult.cpp:110-356) and doNuclAssembly
+// (src/assembler/nuclassembleresult.cpp:144-398):
+//   pass A  extend_kernel       one thread per query: the priority queue of the reference is replayed
+//                               exactly (libstdc++ push_heap/pop_heap sequence, so that the nucleotide
+//                               comparator -- not a strict weak ordering -- pops in the same order),
+//                               the growing contig is kept as a rope of (source sequence, offset, length,
+//                               reversed) segments, parked alignments are re-scored against the rope;
+//   scan                        output offsets from the contig lengths;
+//   pass B  materialize_kernel  one warp per output sequence copies the rope segments / the original.
+#include "pg_internal.cuh"
+#include "pg_scan.cuh"
+#include "pg_tables.h"
+
+namespace pg {
+
+struct ExConst {
+    int nt;
+    int alph;
+    float seqIdThr;
+    int maxSeqLen;
+    int keepTarget;
+    double lambda, logK;   // computeRawScoreFromBitScore (EvalueComputation.h:22-24)
+};
+
+__constant__ unsigned char c_ex_a2n[256];
+__constant__ signed char c_ex_mat[21 * 21];
+__constant__ unsigned char c_ex_revN[256];   // nt letter -> reverse-complement letter with X -> N (getRevFragment)
+
+struct __align__(4) ExRes {      // Matcher::result_t subset + the per-target useReverse flag
+    unsigned dbKey;
+    int score;
+    float seqId;
+    unsigned alnLength;
+    int qStartPos, qEndPos;
+    unsigned qLen;
+    int dbStartPos, dbEndPos;
+    unsigned dbLen;
+    unsigned rev;
+};
+
+struct ExSeg {                   // one rope segment: bytes [start, start+len) of sequence `src`, optionally
+    unsigned src;                // reverse-complemented (the reversed fragment of that range)
+    unsigned start;
+    unsigned len;
+    unsigned rev;
+};
+
+// CompareResultByScore (assembleresult.cpp:19-36)
+__device__ __forceinline__ bool cmp_aa(const ExRes &r1, const ExRes &r2) {
+    if (r1.score < r2.score) return true;
+    if (r2.score < r1.score) return false;
+    if (r1.alnLength < r2.alnLength) return true;
+    if (r2.alnLength < r1.alnLength) return false;
+    if (r1.dbKey > r2.dbKey) return true;
+    if (r2.dbKey > r1.dbKey) return false;
+    return false;
+}
+// CompareNuclResultByScore (nuclassembleresult.cpp:36-70)
+__device__ bool cmp_nt(const ExRes &r1, const ExRes &r2) {
+    const unsigned mm1 = (unsigned) ((double) ((1.0f - r1.seqId) * (float) r1.alnLength) + 0.5);
+    const unsigned mm2 = (unsigned) ((double) ((1.0f - r2.seqId) * (float) r2.alnLength) + 0.5);
+    const unsigned alpha1 = mm1 + 1, alpha2 = mm2 + 1;
+    const unsigned beta1 = r1.alnLength - mm1 + 1, beta2 = r2.alnLength - mm2 + 1;
+    const double log_c = (lgamma((double) (beta1 + beta2)) + lgamma((double) (alpha1 + beta1))) -
+                         (lgamma((double) (alpha1 + beta1 + beta2)) + lgamma((double) beta1));
+    double log_r = 0.0, p = 0.0;
+    for (unsigned long long idx = 0; idx < alpha2; idx++) {
+        p += exp(log_r + log_c);
+        log_r = log((double) (alpha1 + idx)) + log((double) (beta2 + idx)) - (log((double) (idx + 1)) + log((double) (idx + alpha1 + beta1 + beta2))) + log_r;
+    }
+    if (p < 0.45) return true;
+    if (p > 0.55) return false;
+    if (r1.dbLen - r1.alnLength < r2.dbLen - r2.alnLength) return true;
+    if (r1.dbLen - r1.alnLength > r2.dbLen - r2.alnLength) return false;
+    return true;
+}
+__device__ __forceinline__ bool cmp_res(const ExRes &a, const ExRes &b, int nt) { return nt ? cmp_nt(a, b) : cmp_aa(a, b); }
+
+// libstdc++ std::__push_heap / std::__adjust_heap (bits/stl_heap.h), which std::priority_queue uses.
+__device__ void heap_push_hole(ExRes *first, long hole, long top, const ExRes &value, int nt) {
+    long parent = (hole - 1) / 2;
+    while (hole > top && cmp_res(first[parent], value, nt)) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+__device__ void heap_push(ExRes *first, long &size, const ExRes &value, int nt) {   // push_back + push_heap
+    first[size] = value;
+    size++;
+    heap_push_hole(first, size - 1, 0, value, nt);
+}
+__device__ void heap_pop(ExRes *first, long &size, int nt) {                        // pop_heap + pop_back
+    if (size > 1) {
+        const long len = size - 1;
+        const ExRes value = first[len];
+        first[len] = first[0];
+        long hole = 0, second = 0;
+        while (second < (len - 1) / 2) {
+            second = 2 * (second + 1);
+            if (cmp_res(first[second], first[second - 1], nt)) second--;
+            first[hole] = first[second];
+            hole = second;
+        }
+        if ((len & 1) == 0 && second == (len - 2) / 2) {
+            second = 2 * (second + 1);
+            first[hole] = first[second - 1];
+            hole = second - 1;
+        }
+        heap_push_hole(first, hole, 0, value, nt);
+    }
+    size--;
+}
+
+struct Rope {
+    ExSeg *segs;
+    int n;
+    unsigned len;
+    const pg_seqdb *db;
+    __device__ unsigned char at(unsigned i) const {
+        int s = 0;
+        while (i >= segs[s].len) { i -= segs[s].len; s++; }
+        const ExSeg g = segs[s];
+        const char *base = db->data + db->offsets[g.src];
+        if (!g.rev) return (unsigned char) base[g.start + i];
+        return c_ex_revN[(unsigned char) base[g.start + g.len - 1 - i]];
+    }
+};
+
+// a target as it is compared during re-scoring: forward, or its full reverse complement (X -> N)
+__device__ __forceinline__ unsigned char target_at(const char *t, unsigned tLen, unsigned rev, unsigned i) {
+    return rev ? c_ex_revN[(unsigned char) t[tLen - 1 - i]] : (unsigned char) t[i];
+}
+
+// ungappedAlignmentByDiagonal (mode 3) + updateAlignment (assembleresult.cpp:70-108) against the rope
+__device__ void rescore_parked(ExRes &r, const Rope &q, const char *t, unsigned tLen, unsigned tRev, int diag, int alph) {
+    const unsigned qLen = q.len;
+    const unsigned dist = (unsigned) abs(diag);
+    int start = -1, end = -1; unsigned score = 0, diagLen = 0;
+    unsigned qOff = 0, tOff = 0, len = 0; bool valid = false;
+    if (diag >= 0 && dist < qLen) { len = min(tLen, qLen - dist); qOff = dist; valid = true; }
+    else if (diag < 0 && dist < tLen) { len = min(tLen - dist, qLen); tOff = dist; valid = true; }
+    if (valid && len > 0) {
+        diagLen = len;
+        const unsigned first = (q.at(qOff) == '*' || target_at(t, tLen, tRev, tOff) == '*') ? 1u : 0u;
+        unsigned last = len - 1;
+        if (last > 0 && (q.at(qOff + len - 1) == '*' || target_at(t, tLen, tRev, tOff + len - 1) == '*')) last--;
+        long long sum = 0;
+        for (unsigned pos = first; pos <= last; pos++)
+            sum += c_ex_mat[c_ex_a2n[q.at(qOff + pos)] * alph + c_ex_a2n[target_at(t, tLen, tRev, tOff + pos)]];
+        if (sum < 0) sum = 0;
+        start = (int) first; end = (int) last; score = (unsigned) sum;
+    }
+    const int d2 = max(abs(diag), 0);
+    int qS, qE, dS, dE;
+    if (diag >= 0) { qS = start + d2; qE = end + d2; dS = start; dE = end; }
+    else { qS = start; qE = end; dS = start + d2; dE = end + d2; }
+    int idCnt = 0;
+    for (int i = qS; i < qE; i++) idCnt += (q.at((unsigned) i) == target_at(t, tLen, tRev, (unsigned) (dS + (i - qS)))) ? 1 : 0;
+    r.seqId = __fdiv_rn((float) idCnt, __fsub_rn((float) qE, (float) qS));
+    r.qLen = qLen; r.dbLen = tLen;
+    r.alnLength = diagLen;
+    const float scorePerCol = __fdiv_rn((float) score, (float) ((double) r.alnLength + 0.5));
+    r.score = (int) __fmul_rn(scorePerCol, 100.0f);
+    r.qStartPos = qS; r.qEndPos = qE; r.dbStartPos = dS; r.dbEndPos = dE;
+}
+
+// (float) strtod(text of Util::fastSeqIdToBuffer(seqId)): the value the assembler parses back from aln_N
+__device__ __forceinline__ float seqid_text_roundtrip(float seqId) {
+    if (seqId == 1.0f) return 1.0f;
+    const int n = (int) __fmul_rn(seqId, 1000.0f);
+    return (float) ((double) n / 1000.0);
+}
+
+__global__ void aln_ranges_kernel(const pg_seqdb db, const pg_aln *__restrict__ alns, unsigned long long nAlns,
+                                  unsigned long long *__restrict__ alnStart, unsigned *__restrict__ alnCount) {
+    const unsigned long long j = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nAlns) return;
+    const unsigned qk = alns[j].query;
+    if (j > 0 && alns[j - 1].query == qk) return;
+    unsigned long long k = j;
+    while (k < nAlns && alns[k].query == qk) k++;
+    const unsigned qi = find_id(db.keys, (unsigned) db.n, qk);
+    alnStart[qi] = j;
+    alnCount[qi] = (unsigned) (k - j);
+}
+
+__global__ void __launch_bounds__(128) extend_kernel(const pg_seqdb db, const pg_aln *__restrict__ alns,
+                                                     const unsigned long long *__restrict__ alnStart, const unsigned *__restrict__ alnCount,
+                                                     const ExConst c, ExRes *__restrict__ heapBuf, ExRes *__restrict__ parkBuf,
+                                                     ExSeg *__restrict__ segBuf, unsigned *__restrict__ segCount,
+                                                     unsigned *__restrict__ outLen /* entry length incl. "\n\0" */,
+                                                     unsigned char *__restrict__ extended, unsigned char *__restrict__ used) {
+    const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= db.n) return;
+    const unsigned nAl = alnCount[qi];
+    const unsigned entryLen = db.lens[qi];
+    outLen[qi] = entryLen;
+    extended[qi] = 0;
+    segCount[qi] = 0;
+    if (nAl < 2) return;                 // only the self alignment: nothing can be popped for extension
+    const unsigned long long a0 = alnStart[qi];
+    ExRes *heap = heapBuf + a0;
+    ExRes *park = parkBuf + a0;
+    ExSeg *segs = segBuf + a0 + qi;      // capacity nAl + 1
+    const unsigned queryKey = db.keys[qi];
+    unsigned querySeqLen = entryLen - 2;
+    Rope rope; rope.segs = segs; rope.db = &db;
+    segs[0].src = qi; segs[0].start = 0; segs[0].len = querySeqLen; segs[0].rev = 0;
+    rope.n = 1; rope.len = querySeqLen;
+    bool couldExtend = false;
+    long hsize = 0;
+    // fill the queue (assembleresult.cpp:159-188 / nuclassembleresult.cpp:197-226)
+    for (unsigned i = 0; i < nAl; i++) {
+        const pg_aln a = alns[a0 + i];
+        ExRes r;
+        r.dbKey = a.target;
+        r.seqId = seqid_text_roundtrip(a.seq_id);
+        r.qStartPos = a.q_start; r.qEndPos = a.q_end; r.qLen = (unsigned) a.q_len;
+        r.dbStartPos = a.db_start; r.dbEndPos = a.db_end; r.dbLen = (unsigned) a.db_len;
+        const int adjQ = (r.qStartPos == -1) ? 0 : r.qStartPos;
+        const int adjD = (r.dbStartPos == -1) ? 0 : r.dbStartPos;
+        r.alnLength = (unsigned) (max(abs(r.qEndPos - adjQ), abs(r.dbEndPos - adjD)) + 1);   // Matcher.cpp:201-203
+        const int rawScore = (int) (((c.logK + (double) a.bits * log(2.0)) / c.lambda) + 0.5);
+        const float scorePerCol = __fdiv_rn((float) rawScore, (float) ((double) r.alnLength + 0.5));
+        if (!c.nt) {
+            const float alnLen = (float) r.alnLength;
+            const float ids = __fmul_rn(r.seqId, alnLen);
+            r.seqId = (float) ((double) ids / ((double) alnLen + 0.5));
+        }
+        r.score = (int) __fmul_rn(scorePerCol, 100.0f);
+        r.rev = 0;
+        if (c.nt) {
+            if (r.qStartPos > r.qEndPos) {
+                r.rev = 1;
+                const int t = r.qStartPos; r.qStartPos = r.qEndPos; r.qEndPos = t;
+                const unsigned dbStartPos = (unsigned) r.dbStartPos;
+                r.dbStartPos = (int) (r.dbLen - (unsigned) r.dbEndPos - 1u);
+                r.dbEndPos = (int) (r.dbLen - dbStartPos - 1u);
+            }
+        }
+        heap_push(heap, hsize, r, c.nt);
+    }
+    while (hsize > 0) {
+        unsigned leftOff = 0, rightOff = 0;
+        int nPark = 0;
+        bool brokeOut = false;
+        while (true) {
+            // selectFragmentToExtend (assembleresult.cpp:40-57)
+            bool got = false;
+            ExRes best;
+            while (hsize > 0) {
+                const ExRes res = heap[0];
+                heap_pop(heap, hsize, c.nt);
+                const bool notRightStartAndLeftStart = !(res.dbStartPos == 0 && res.qStartPos == 0);
+                const bool rightStart = res.dbStartPos == 0 && (res.dbEndPos != (int) res.dbLen - 1);
+                const bool leftStart = res.qStartPos == 0 && (res.qEndPos != (int) res.qLen - 1);
+                const bool isNotIdentity = (res.dbKey != queryKey);
+                if ((rightStart || leftStart) && notRightStartAndLeftStart && isNotIdentity) { best = res; got = true; break; }
+            }
+            if (!got) break;
+            const unsigned targetId = find_id(db.keys, (unsigned) db.n, best.dbKey);
+            const unsigned targetSeqLen = db.lens[targetId] - 2;
+            if (best.dbStartPos == 0) {
+                if ((targetSeqLen - (unsigned) (best.dbEndPos + 1)) <= rightOff) continue;
+            } else if (best.qStartPos == 0) {
+                if (best.dbStartPos <= (int) leftOff) continue;
+            }
+            const unsigned dbStartPos = (unsigned) best.dbStartPos, dbEndPos = (unsigned) best.dbEndPos;
+            const unsigned qStartPos = (unsigned) best.qStartPos, qEndPos = (unsigned) best.qEndPos;
+            if (dbStartPos == 0 && qEndPos == (querySeqLen - 1)) {            // right extension
+                if (rightOff > 0) { park[nPark++] = best; continue; }
+                const unsigned fragLen = targetSeqLen - (dbEndPos + 1);
+                if (c.nt && (unsigned long long) rope.len + fragLen >= (unsigned long long) c.maxSeqLen) { brokeOut = true; break; }
+                ExSeg g; g.src = targetId; g.len = fragLen; g.rev = best.rev;
+                g.start = best.rev ? 0u : dbEndPos + 1;                       // reversed: rev(target[0, fragLen))
+                segs[rope.n++] = g;
+                rope.len += fragLen;
+                rightOff += fragLen;
+                used[targetId] = 1;
+            } else if (qStartPos == 0 && dbEndPos == (targetSeqLen - 1)) {    // left extension
+                if (leftOff > 0) { park[nPark++] = best; continue; }
+                const unsigned fragLen = dbStartPos;
+                if ((unsigned long long) rope.len + fragLen >= (unsigned long long) c.maxSeqLen) { brokeOut = true; break; }
+                ExSeg g; g.src = targetId; g.len = fragLen; g.rev = best.rev;
+                g.start = best.rev ? (targetSeqLen - dbStartPos) : 0u;        // reversed: rev(target[tLen-dbStart, tLen))
+                for (int s = rope.n; s > 0; s--) segs[s] = segs[s - 1];
+                segs[0] = g;
+                rope.n++;
+                rope.len += fragLen;
+                leftOff += fragLen;
+                used[targetId] = 1;
+            }
+        }
+        (void) brokeOut;
+        if (leftOff > 0 || rightOff > 0) couldExtend = true;
+        if (hsize > 0) break;
+        querySeqLen = rope.len;
+        for (int ai = 0; ai < nPark; ai++) {
+            ExRes r = park[ai];
+            const unsigned tId = find_id(db.keys, (unsigned) db.n, r.dbKey);
+            const unsigned tSeqLen = db.lens[tId] - 2;
+            const char *tSeq = db.data + db.offsets[tId];
+            const int diag = (int) ((unsigned) r.qStartPos + leftOff) - r.dbStartPos;
+            rescore_parked(r, rope, tSeq, tSeqLen, r.rev, diag, c.alph);
+            if (r.seqId >= c.seqIdThr) heap_push(heap, hsize, r, c.nt);
+        }
+    }
+    if (couldExtend) {
+        extended[qi] = 1;
+        outLen[qi] = rope.len + 2;
+        segCount[qi] = (unsigned) rope.n;
+    }
+}
+
+// keep[i] = 1 if sequence i is written to the output DB (assembleresult.cpp:316-342)
+__global__ void keep_kernel(unsigned long long n, int keepTarget, const unsigned char *__restrict__ extended,
+                            const unsigned char *__restrict__ used, unsigned *__restrict__ keep, unsigned *__restrict__ outLen) {
+    const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool k = extended[i] || keepTarget || !used[i];
+    keep[i] = k ? 1u : 0u;
+    if (!k) outLen[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) materialize_kernel(const pg_seqdb db, const unsigned long long *__restrict__ alnStart,
+                                                          const ExSeg *__restrict__ segBuf, const unsigned *__restrict__ segCount,
+                                                          const unsigned *__restrict__ outLen, const unsigned long long *__restrict__ outOff,
+                                                          const unsigned *__restrict__ keep, const unsigned long long *__restrict__ keepIdx,
+                                                          const unsigned char *__restrict__ extended,
+                                                          char *__restrict__ outData, unsigned long long *__restrict__ outOffsets,
+                                                          unsigned *__restrict__ outLens, unsigned *__restrict__ outKeys,
+                                                          unsigned char *__restrict__ outExtended) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long warpsTotal = (unsigned long long) gridDim.x * (blockDim.x >> 5);
+    for (unsigned long long qi = (unsigned long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); qi < db.n; qi += warpsTotal) {
+        if (!keep[qi]) continue;
+        const unsigned long long o = outOff[qi];
+        const unsigned len = outLen[qi];
+        const unsigned long long slot = keepIdx[qi];
+        char *dst = outData + o;
+        if (lane == 0) { outOffsets[slot] = o; outLens[slot] = len; outKeys[slot] = db.keys[qi]; outExtended[slot] = extended[qi]; }
+        const unsigned nseg = segCount[qi];
+        if (nseg == 0) {
+            const char *src = db.data + db.offsets[qi];
+            for (unsigned i = lane; i < len; i += 32) dst[i] = src[i];
+        } else {
+            const ExSeg *segs = segBuf + alnStart[qi] + qi;
+            unsigned w = 0;
+            for (unsigned s = 0; s < nseg; s++) {
+                const ExSeg g = segs[s];
+                const char *src = db.data + db.offsets[g.src];
+                for (unsigned i = lane; i < g.len; i += 32)
+                    dst[w + i] = g.rev ? (char) c_ex_revN[(unsigned char) src[g.start + g.len - 1 - i]] : src[g.start + i];
+                w += g.len;
+            }
+            if (lane == 0) { dst[w] = '\n'; dst[w + 1] = '\0'; }
+        }
+    }
+}
+
+int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAlns, const pg_ex_params *p, pg_seqdb **outDb, unsigned char **d_extended) {
+    cudaStream_t s = ctx->stream;
+    PG_CHECK(p->rescore_mode == 3, "assembleresults: only --rescore-mode 3 (END_TO_END) is implemented on the GPU path");
+    const bool nt = db->dbtype == PG_DBTYPE_NUCLEOTIDES;
+    ExConst c;
+    c.nt = nt; c.alph = nt ? 5 : 21; c.seqIdThr = p->seq_id_thr; c.maxSeqLen = p->max_seq_len; c.keepTarget = p->keep_target;
+    const double *a = nt ? PG_NT_ALP : PG_AA_ALP;
+    c.lambda = a[0]; c.logK = log(a[1]);
+    unsigned char revN[256];
+    for (int i = 0; i < 256; i++) { unsigned char r = PG_NT_NUM2AA[PG_NT_REVERSE[PG_NT_AA2NUM[i]]]; revN[i] = (r == 'X') ? 'N' : r; }
+    signed char mat[21 * 21] = {0};
+    if (nt) { for (int i = 0; i < 25; i++) mat[i] = PG_NT_SUBMAT[i]; } else { for (int i = 0; i < 441; i++) mat[i] = PG_AA_SUBMAT[i]; }
+    PG_CUDA(cudaMemcpyToSymbolAsync(c_ex_a2n, nt ? PG_NT_AA2NUM : PG_AA_AA2NUM, 256, 0, cudaMemcpyHostToDevice, s));
+    PG_CUDA(cudaMemcpyToSymbolAsync(c_ex_revN, revN, 256, 0, cudaMemcpyHostToDevice, s));
+    PG_CUDA(cudaMemcpyToSymbolAsync(c_ex_mat, mat, sizeof(mat), 0, cudaMemcpyHostToDevice, s));
+    PG_CUDA(cudaStreamSynchronize(s));
+
+    cudaEventRecord(ctx->ev[EV_EX_BEGIN], s);
+    const uint64_t n = db->n;
+    // meta arrays (per sequence)
+    const size_t a16 = 15;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + a16) & ~a16; return r; };
+    const size_t oAlnStart = take(sizeof(unsigned long long) * (n + 1));
+    const size_t oAlnCount = take(sizeof(unsigned) * (n + 1));
+    const size_t oSegCount = take(sizeof(unsigned) * (n + 1));
+    const size_t oOutLen = take(sizeof(unsigned) * (n + 1));
+    const size_t oKeep = take(sizeof(unsigned) * (n + 1));
+    const size_t oOutOff = take(sizeof(unsigned long long) * (n + 2));
+    const size_t oKeepIdx = take(sizeof(unsigned long long) * (n + 2));
+    const size_t oExt = take(n + 1);
+    const size_t oUsed = take(n + 1);
+    const size_t oScan = take(scan_workspace_bytes(n));
+    PG_TRY(ctx->exMeta.reserve(o));
+    unsigned char *m = ctx->exMeta.as<unsigned char>();
+    unsigned long long *alnStart = (unsigned long long *) (m + oAlnStart);
+    unsigned *alnCount = (unsigned *) (m + oAlnCount);
+    unsigned *segCount = (unsigned *) (m + oSegCount);
+    unsigned *outLen = (unsigned *) (m + oOutLen);
+    unsigned *keep = (unsigned *) (m + oKeep);
+    unsigned long long *outOff = (unsigned long long *) (m + oOutOff);
+    unsigned long long *keepIdx = (unsigned long long *) (m + oKeepIdx);
+    unsigned char *ext = m + oExt, *used = m + oUsed;
+    void *scanWs = m + oScan;
+    PG_CUDA(cudaMemsetAsync(m, 0, o, s));
+    PG_TRY(ctx->exWork.reserve(sizeof(ExRes) * 2 * (nAlns + 1)));
+    PG_TRY(ctx->exSegs.reserve(sizeof(ExSeg) * (nAlns + n + 1)));
+    ExRes *heapBuf = ctx->exWork.as<ExRes>();
+    ExRes *parkBuf = heapBuf + (nAlns + 1);
+    if (nAlns) aln_ranges_kernel<<<(unsigned) ((nAlns + 255) / 256), 256, 0, s>>>(*db, d_alns, nAlns, alnStart, alnCount);
+    extend_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(*db, d_alns, alnStart, alnCount, c, heapBuf, parkBuf,
+                                                              ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
+    keep_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(n, c.keepTarget, ext, used, keep, outLen);
+    ctx->launches += 3;
+    unsigned long long *d_tot = ctx->small.as<unsigned long long>() + 5;   // [5] bytes, [6] kept
+    PG_TRY(exclusive_scan_u32(outLen, outOff, n, d_tot, scanWs, scan_workspace_bytes(n), s, &ctx->launches));
+    PG_TRY(exclusive_scan_u32(keep, keepIdx, n, d_tot + 1, scanWs, scan_workspace_bytes(n), s, &ctx->launches));
+    unsigned long long h[2] = {0, 0};
+    PG_CUDA(cudaMemcpyAsync(h, d_tot, sizeof(h), cudaMemcpyDeviceToHost, s));
+    PG_CUDA(cudaStreamSynchronize(s));
+    PG_CUDA(cudaGetLastError());
+    pg_seqdb *out = new pg_seqdb();
+    out->n = h[1]; out->data_bytes = h[0]; out->dbtype = db->dbtype;
+    PG_CUDA(cudaMalloc(&out->data, h[0] + 16));
+    PG_CUDA(cudaMalloc(&out->offsets, sizeof(unsigned long long) * (h[1] + 1)));
+    PG_CUDA(cudaMalloc(&out->lens, sizeof(unsigned) * (h[1] + 1)));
+    PG_CUDA(cudaMalloc(&out->keys, sizeof(unsigned) * (h[1] + 1)));
+    unsigned char *outExt = nullptr;
+    PG_CUDA(cudaMalloc(&outExt, h[1] + 1));
+    materialize_kernel<<<NUM_SMS * 16, 256, 0, s>>>(*db, alnStart, ctx->exSegs.as<ExSeg>(), segCount, outLen, outOff, keep, keepIdx, ext,
+                                                    out->data, out->offsets, out->lens, out->keys, outExt);
+    ctx->launches++;
+    cudaEventRecord(ctx->ev[EV_EX_END], s);
+    PG_CUDA(cudaGetLastError());
+    PG_TRY(seqdb_finalize(ctx, out));
+    *outDb = out;
+    *d_extended = outExt;
+    ctx->exRan = true;
+    return 0;
+}
+
+}  // namespace pg

@@ -1,0 +1,40 @@
+// pg_internal.cuh -- library-internal state shared by the stage implementations.
+#pragma once
+#include "pg_common.cuh"
+#include "pg_radix.cuh"
+
+namespace pg {
+
+enum {
+    EV_KM_BEGIN = 0, EV_EXTRACT_END, EV_SORT1_BEGIN, EV_SORT1_END, EV_GROUP_END, EV_SORT2_END, EV_REDUCE_END,
+    EV_RS_BEGIN, EV_RS_END, EV_EX_BEGIN, EV_EX_END, EV_TOTAL_BEGIN, EV_TOTAL_END, EV_COUNT
+};
+
+}  // namespace pg
+
+// One per process / GPU.
+struct pg_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[pg::EV_COUNT];
+    pg::DevBuf small, lists, recA, recB, radixWs, scratch, blockCounts, hits, alnAll, alns, flags, exWork, exSegs, exMeta;
+    bool pairsInA = false;
+    bool kmRan = false, rsRan = false, exRan = false;
+    uint64_t launches = 0;
+    pg_timings timings;
+    uint64_t nHits = 0, nAlns = 0;
+};
+
+namespace pg {
+typedef pg_context Context;
+
+struct KmConst;
+// kmermatcher stages (pg_kmermatch.cu)
+int km_run(Context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **d_hits, uint64_t *nHits);
+// rescorediagonal (pg_rescore.cu): d_hits sorted by (rep,target); result device array in ctx->alns
+int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHits, const pg_rs_params *p, pg_aln **d_alns, uint64_t *nAlns);
+// extension (pg_extend.cu): d_alns sorted by query; produces a new device DB
+int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAlns, const pg_ex_params *p, pg_seqdb **out, unsigned char **d_extended);
+int seqdb_finalize(Context *ctx, pg_seqdb *db);   // computes max_seq_len / residues / dense_keys on the device
+void seqdb_release(pg_seqdb *db);
+}  // namespace pg

@@ -1,0 +1,923 @@
+// pg_kmermatch.cu -- GPU kmermatcher: k-mer extraction + bottom-m selection, group/join, best diagonal.
+//
+// Replaces (reference lib/mmseqs/src/linclust/kmermatcher.cpp):
+//   fillKmerPositionArray :77-385   -> classify_kernel + extract_warp_kernel<NMAX> + extract_block_kernel
+//   SORT_PARALLEL #1      :408-412  -> pg::radix_sort on the k-mer word
+//   assignGroup           :450-559  -> group_kernel (rep = min by (seqLen desc, id, pos), diagonal, filter)
+//   SORT_PARALLEL #2      :427-431  -> pg::radix_sort on (rep, target, diagonal)
+//   writeKmerMatcherResult:809-924  -> reduce_count_kernel / reduce_emit_kernel (best diagonal per rep,target)
+// Bit-exactness notes refer to SURVEY.md Appendix A.1-A.4.
+#include "pg_internal.cuh"
+#include "pg_tables.h"
+
+namespace pg {
+
+__constant__ unsigned char c_aa2num[256];   // ASCII -> code of the active k-mer alphabet
+struct KmConst {
+    int k;
+    int nt;               // 1 = nucleotides
+    int xCode;            // code of X (12 reduced / 20 full / 4 nt)
+    unsigned base;        // aa index base = alphabetSize-1 (kmermatcher.cpp:113)
+    unsigned long long seed;
+    int kmersPerSeq;
+    float scale;
+    int ignoreMulti;
+    unsigned hashStart, hashEnd;
+    int includeOnlyExtendable;
+    int covMode;
+    float covThr;
+};
+
+// One k-mer of a sequence while it is being selected (SequencePosition, kmermatcher.h:10-46).
+struct __align__(16) Cand {
+    unsigned long long kmer;   // as stored (nt: strand flag in bit 63)
+    unsigned score;            // 16-bit hash; 0xFFFFFFFF = padding
+    unsigned pos;
+};
+
+__device__ __forceinline__ unsigned long long cmp_kmer(unsigned long long k, int nt) { return nt ? (k | (1ULL << 63)) : k; }
+
+// (score, kmer[|bit63], pos) lexicographic -- SequencePosition::compareByScore[Reverse]
+__device__ __forceinline__ bool cand_less(const Cand &a, const Cand &b, int nt) {
+    if (a.score != b.score) return a.score < b.score;
+    const unsigned long long ka = cmp_kmer(a.kmer, nt), kb = cmp_kmer(b.kmer, nt);
+    if (ka != kb) return ka < kb;
+    return a.pos < b.pos;
+}
+
+// k-mer index + score at position pos of the code array; returns false if the window holds X
+// (Sequence::kmerContainsX) or is a reverse-complement palindrome (kmermatcher.cpp:156-158).
+__device__ __forceinline__ bool make_kmer(const unsigned char *codes, int pos, int L, const KmConst &c, Cand &out) {
+    bool hasX = false;
+    if (c.nt) {
+        unsigned long long idx = 0;
+        for (int j = 0; j < c.k; j++) { const unsigned v = codes[pos + j]; hasX |= (v == (unsigned) c.xCode); idx = (idx << 2) | (v & 3u); }
+        if (hasX) return false;
+        unsigned long long rev = 0, t = idx;     // Util::revComplement (Util.cpp:601-638)
+        for (int j = 0; j < c.k; j++) { rev = (rev << 2) | ((t & 3ULL) ^ 2ULL); t >>= 2; }
+        if (rev == idx) return false;
+        const bool pickRev = rev < idx;
+        idx = pickRev ? rev : idx;
+        out.score = (unsigned) (xxh64_u64(idx, c.seed) & 0xFFFFULL);
+        out.kmer = pickRev ? (idx & ~(1ULL << 63)) : (idx | (1ULL << 63));
+        out.pos = pickRev ? (unsigned) (L - pos - c.k) : (unsigned) pos;
+    } else {
+        unsigned long long idx = 0, pw = 1;      // Indexer::int2index (Indexer.h:20-83)
+        for (int j = 0; j < c.k; j++) { const unsigned v = codes[pos + j]; hasX |= (v == (unsigned) c.xCode); idx += (unsigned long long) v * pw; pw *= c.base; }
+        if (hasX) return false;
+        out.kmer = idx;
+        out.pos = (unsigned) pos;
+        out.score = (unsigned) (xxh64_u64(idx, c.seed) & 0xFFFFULL);
+    }
+    return true;
+}
+
+// The selection loop of kmermatcher.cpp:274-347 over candidates sorted by cand_less, run by ONE thread.
+// sorted[0..cnt) holds all k-mers of the sequence (or at least every k-mer with score <= t);
+// emits into outRecs (capacity >= kmerConsidered), returns the number emitted.
+__device__ int select_sequential(const Cand *sorted, int cnt, unsigned long long kmerConsidered, unsigned threshold, int tooMuch,
+                                 const KmConst &c, unsigned id, unsigned seqLen, Rec *outRecs) {
+    int nOut = 0;
+    unsigned long long selected = 0;
+    for (int i = 0; i < cnt && selected < kmerConsidered; i++) {
+        if (c.ignoreMulti) {
+            const unsigned long long kmer = cmp_kmer(sorted[i].kmer, c.nt);
+            if (i + 1 < cnt) {
+                unsigned long long next = cmp_kmer(sorted[i + 1].kmer, c.nt);
+                if (kmer == next) {
+                    while (kmer == next && i < cnt) {
+                        i++;
+                        if (i >= cnt) break;
+                        next = cmp_kmer(sorted[i].kmer, c.nt);
+                    }
+                }
+            }
+            if (i >= cnt) break;
+        }
+        const unsigned sc = sorted[i].score;
+        if (sc < threshold) {
+            if (sc == (threshold - 1) && tooMuch) {
+                tooMuch--;
+                threshold -= (tooMuch == 0) ? 1 : 0;
+            }
+            selected++;
+            if (sc >= c.hashStart && sc <= c.hashEnd) {
+                Rec r;
+                r.w0 = sorted[i].kmer;
+                r.w1 = ((unsigned long long) id << 32) | ((unsigned long long) (seqLen & 0xFFFFu) << 16) | (sorted[i].pos & 0xFFFFu);
+                outRecs[nOut++] = r;
+            }
+        }
+    }
+    return nOut;
+}
+
+// ------------------------------------------------------------------------------------------------
+// classify: bin sequences by the number of k-mer windows so that each class runs in a kernel whose
+// shared-memory tile fits it.  class 0: <=64, 1: <=256, 2: <=1024, 3: larger (block kernel).
+// ------------------------------------------------------------------------------------------------
+__global__ void classify_kernel(const unsigned *__restrict__ lens, unsigned n, int k, unsigned *__restrict__ lists /*4 x n*/,
+                                unsigned *__restrict__ counts /*4*/) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    int cls = -1;
+    if (i < n) {
+        const int L = (int) lens[i] - 2;
+        const int nk = L - k + 1;
+        cls = nk <= 64 ? 0 : (nk <= 256 ? 1 : (nk <= 1024 ? 2 : 3));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, cls == q);
+        if (m) {
+            unsigned base = 0;
+            const int leader = __ffs(m) - 1;
+            if ((int) lane_id() == leader) base = atomicAdd(&counts[q], __popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (cls == q) lists[(size_t) q * n + base + __popc(m & ((1u << lane_id()) - 1u))] = i;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// extract: one warp per sequence, at most NMAX k-mer windows.
+// ------------------------------------------------------------------------------------------------
+template <int NMAX>
+__global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, const unsigned *__restrict__ list,
+                                                           const unsigned *__restrict__ listCount, const KmConst c,
+                                                           Rec *__restrict__ out, unsigned long long *__restrict__ outCount,
+                                                           unsigned long long outCap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int WARPS = 4;
+    constexpr int CODES = NMAX + 40;   // k <= 32
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Cand *cand = reinterpret_cast<Cand *>(smem_raw) + (size_t) w * NMAX;
+    Rec *outRecs = reinterpret_cast<Rec *>(smem_raw + (size_t) WARPS * NMAX * sizeof(Cand)) + (size_t) w * (NMAX + 1);
+    unsigned char *codes = smem_raw + (size_t) WARPS * NMAX * sizeof(Cand) + (size_t) WARPS * (NMAX + 1) * sizeof(Rec) + (size_t) w * CODES;
+
+    const unsigned nList = *listCount;
+    for (unsigned li = blockIdx.x * WARPS + w; li < nList; li += gridDim.x * WARPS) {
+        const unsigned si = list[li];
+        const char *seq = db.data + db.offsets[si];
+        const int entryLen = (int) db.lens[si] - 2;
+        // Sequence::mapSequence (Sequence.cpp:476-489): map until '\n' / '\0'
+        int L = entryLen;
+        for (int i = lane; i < entryLen; i += 32) {
+            const unsigned char ch = (unsigned char) seq[i];
+            codes[i] = c_aa2num[ch];
+            if (ch == '\n' || ch == 0) L = min(L, i);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) L = min(L, __shfl_xor_sync(0xFFFFFFFFu, L, o));
+        __syncwarp();
+        const unsigned id = db.keys[si];
+        // whole-sequence hash: Util::hash (poly 31) then XXH64 (kmermatcher.cpp:133-138)
+        unsigned long long seqHash;
+        {
+            const int chunk = (L + 31) / 32;
+            const int b = lane * chunk, e = min(L, b + chunk);
+            unsigned long long h = 0, pw = 1;
+            for (int i = b; i < e; i++) { h = h * 31ULL + codes[i]; pw *= 31ULL; }
+            unsigned long long acc = 0;
+            for (int l = 0; l < 32; l++) {
+                const unsigned long long hl = __shfl_sync(0xFFFFFFFFu, h, l);
+                const unsigned long long pl = __shfl_sync(0xFFFFFFFFu, pw, l);
+                acc = acc * pl + hl;
+            }
+            seqHash = xxh64_u64(acc, c.seed);
+        }
+        // all k-mer windows, compacted in position order
+        int cnt = 0;
+        const int nWin = L - c.k + 1;
+        for (int p0 = 0; p0 < nWin; p0 += 32) {
+            const int pos = p0 + lane;
+            Cand cd;
+            const bool ok = (pos < nWin) && make_kmer(codes, pos, L, c, cd);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+            if (ok) cand[cnt + __popc(m & ((1u << lane) - 1u))] = cd;
+            cnt += __popc(m);
+        }
+        int n2 = 1;
+        while (n2 < cnt) n2 <<= 1;
+        for (int i = cnt + lane; i < n2; i += 32) { cand[i].score = 0xFFFFFFFFu; cand[i].kmer = ~0ULL; cand[i].pos = 0xFFFFFFFFu; }
+        __syncwarp();
+        // bitonic sort by (score, kmer, pos)   [std::sort at kmermatcher.cpp:266-272; total order => same result]
+        if (c.ignoreMulti) {
+            for (int kk = 2; kk <= n2; kk <<= 1) {
+                for (int j = kk >> 1; j > 0; j >>= 1) {
+                    for (int t = lane; t < (n2 >> 1); t += 32) {
+                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        const int ix = i | j;
+                        const bool up = ((i & kk) == 0);
+                        const Cand a = cand[i], b = cand[ix];
+                        if (cand_less(b, a, c.nt) == up) { cand[i] = b; cand[ix] = a; }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        // threshold of the bottom-m sketch (kmermatcher.cpp:223-238)
+        const unsigned long long want = (unsigned long long) ((float) (c.kmersPerSeq - 1) + (c.scale * (float) L));
+        const unsigned long long kmerConsidered = min(want, (unsigned long long) cnt);
+        int nOut = 0;
+        if (lane == 0) {
+            // sequence-identity record first (:241-246)
+            const unsigned sh16 = (unsigned) (seqHash & 0xFFFFULL);
+            if (sh16 >= c.hashStart && sh16 <= c.hashEnd) {
+                Rec r; r.w0 = seqHash; r.w1 = ((unsigned long long) id << 32) | ((unsigned long long) (L & 0xFFFF) << 16);
+                outRecs[nOut++] = r;
+            }
+            if (cnt > 0 && kmerConsidered > 0) {
+                unsigned threshold; int tooMuch;
+                if (c.ignoreMulti) {
+                    const unsigned t = cand[kmerConsidered - 1].score;
+                    int inBins = (int) kmerConsidered;
+                    while (inBins < cnt && cand[inBins].score == t) inBins++;
+                    threshold = t + 1;
+                    tooMuch = inBins - (int) kmerConsidered;
+                } else {
+                    // positional order kept: find the kmerConsidered-th smallest score by counting
+                    unsigned lo = 0, hi = 65535;
+                    while (lo < hi) {
+                        const unsigned mid = (lo + hi) >> 1;
+                        int le = 0;
+                        for (int i = 0; i < cnt; i++) le += (cand[i].score <= mid);
+                        if ((unsigned long long) le >= kmerConsidered) hi = mid; else lo = mid + 1;
+                    }
+                    int le = 0;
+                    for (int i = 0; i < cnt; i++) le += (cand[i].score <= lo);
+                    threshold = lo + 1;
+                    tooMuch = le - (int) kmerConsidered;
+                }
+                nOut += select_sequential(cand, cnt, kmerConsidered, threshold, tooMuch, c, id, (unsigned) L, outRecs + nOut);
+            }
+        }
+        nOut = __shfl_sync(0xFFFFFFFFu, nOut, 0);
+        __syncwarp();
+        unsigned long long base = 0;
+        if (lane == 0 && nOut) base = atomicAdd(outCount, (unsigned long long) nOut);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base + nOut <= outCap)
+            for (int i = lane; i < nOut; i += 32) out[base + i] = outRecs[i];
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// extract: one block per long sequence (more than 1024 windows); candidates live in global scratch.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) extract_block_kernel(const pg_seqdb db, const unsigned *__restrict__ list,
+                                                            const unsigned *__restrict__ listCount, const KmConst c,
+                                                            Rec *__restrict__ out, unsigned long long *__restrict__ outCount,
+                                                            unsigned long long outCap, unsigned char *__restrict__ scratch,
+                                                            size_t scratchPerBlock) {
+    __shared__ unsigned hier[128];
+    __shared__ unsigned fine[512];
+    __shared__ unsigned sCnt;
+    __shared__ unsigned long long sPart[256], sPow[256];
+    __shared__ unsigned sThreshold, sCoarse;
+    __shared__ int sTooMuch, sInBins, sNOut;
+    __shared__ unsigned long long sBase;
+    const int tid = threadIdx.x;
+    const unsigned nList = *listCount;
+    unsigned char *myScratch = scratch + (size_t) blockIdx.x * scratchPerBlock;
+    for (unsigned li = blockIdx.x; li < nList; li += gridDim.x) {
+        const unsigned si = list[li];
+        const char *seq = db.data + db.offsets[si];
+        const int entryLen = (int) db.lens[si] - 2;
+        // scratch layout: codes[entryLen+1 rounded to 16] | Cand cand[n2] | Rec outRecs[...]
+        unsigned char *codes = myScratch;
+        const size_t codesBytes = ((size_t) entryLen + 16) & ~(size_t) 15;
+        Cand *cand = reinterpret_cast<Cand *>(myScratch + codesBytes);
+        __shared__ int sL;
+        if (tid == 0) sL = entryLen;
+        __syncthreads();
+        for (int i = tid; i < entryLen; i += 256) {
+            const unsigned char ch = (unsigned char) seq[i];
+            codes[i] = c_aa2num[ch];
+            if (ch == '\n' || ch == 0) atomicMin(&sL, i);
+        }
+        __syncthreads();
+        const int L = sL;
+        const unsigned id = db.keys[si];
+        // sequence hash, chunked polynomial
+        {
+            const int chunk = (L + 255) / 256;
+            const int b = min(L, tid * chunk), e = min(L, b + chunk);
+            unsigned long long h = 0, pw = 1;
+            for (int i = b; i < e; i++) { h = h * 31ULL + codes[i]; pw *= 31ULL; }
+            sPart[tid] = h; sPow[tid] = pw;
+        }
+        for (int i = tid; i < 128; i += 256) hier[i] = 0;
+        for (int i = tid; i < 512; i += 256) fine[i] = 0;
+        if (tid == 0) sCnt = 0;
+        __syncthreads();
+        const int nWin = L - c.k + 1;
+        // pass 1: coarse histogram + count
+        for (int pos = tid; pos < nWin; pos += 256) {
+            Cand cd;
+            if (make_kmer(codes, pos, L, c, cd)) { atomicAdd(&hier[cd.score >> 9], 1u); atomicAdd(&sCnt, 1u); }
+        }
+        __syncthreads();
+        const int cnt = (int) sCnt;
+        const unsigned long long want = (unsigned long long) ((float) (c.kmersPerSeq - 1) + (c.scale * (float) L));
+        const unsigned long long kmerConsidered = min(want, (unsigned long long) cnt);
+        if (tid == 0) {
+            unsigned long long acc = 0;
+            for (int l = 0; l < 256; l++) acc = acc * sPow[l] + sPart[l];
+            const unsigned long long seqHash = xxh64_u64(acc, c.seed);
+            sNOut = 0;
+            Rec *outRecs = reinterpret_cast<Rec *>(cand);   // reused later; identity record kept in registers instead
+            (void) outRecs;
+            const unsigned sh16 = (unsigned) (seqHash & 0xFFFFULL);
+            sBase = seqHash;
+            sInBins = (sh16 >= c.hashStart && sh16 <= c.hashEnd) ? 1 : 0;   // temporarily: "emit identity record"
+            // coarse walk (kmermatcher.cpp:227-232)
+            unsigned long long inBins = 0; unsigned ht = 0;
+            if (cnt > 0) {
+                for (ht = 0; ht < 128 && inBins < kmerConsidered; ht++) inBins += hier[ht];
+                ht -= (ht > 0) ? 1 : 0;
+            }
+            sCoarse = ht;
+        }
+        __syncthreads();
+        const bool emitIdentity = sInBins != 0;
+        const unsigned long long seqHash = sBase;
+        const unsigned coarse = sCoarse;
+        __syncthreads();
+        // pass 2: fine histogram of the coarse bin that holds the threshold
+        for (int pos = tid; pos < nWin; pos += 256) {
+            Cand cd;
+            if (make_kmer(codes, pos, L, c, cd) && (cd.score >> 9) == coarse) atomicAdd(&fine[cd.score & 511u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long inBins = 0;
+            for (unsigned h = 0; h < coarse; h++) inBins += hier[h];
+            unsigned threshold = coarse * 512;
+            if (cnt > 0 && kmerConsidered > 0) {
+                for (; threshold <= 65535u && inBins < kmerConsidered; threshold++) inBins += fine[threshold - coarse * 512];
+            } else {
+                threshold = 0; inBins = kmerConsidered;
+            }
+            sThreshold = threshold;
+            sInBins = (int) inBins;
+            sTooMuch = (int) (inBins - kmerConsidered);
+            sCnt = 0;
+        }
+        __syncthreads();
+        const unsigned threshold = sThreshold;
+        const int inBins = sInBins;
+        // pass 3: gather candidates (score < threshold; without ignoreMulti positional order is needed,
+        // which this block path does not provide -> handled by requiring ignoreMulti, checked on the host)
+        for (int pos = tid; pos < nWin; pos += 256) {
+            Cand cd;
+            if (make_kmer(codes, pos, L, c, cd) && cd.score < threshold) cand[atomicAdd(&sCnt, 1u)] = cd;
+        }
+        __syncthreads();
+        int n2 = 1;
+        while (n2 < inBins) n2 <<= 1;
+        for (int i = inBins + tid; i < n2; i += 256) { cand[i].score = 0xFFFFFFFFu; cand[i].kmer = ~0ULL; cand[i].pos = 0xFFFFFFFFu; }
+        __syncthreads();
+        for (int kk = 2; kk <= n2; kk <<= 1) {
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (n2 >> 1); t += 256) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int ix = i | j;
+                    const bool up = ((i & kk) == 0);
+                    const Cand a = cand[i], b = cand[ix];
+                    if (cand_less(b, a, c.nt) == up) { cand[i] = b; cand[ix] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        Rec *outRecs = reinterpret_cast<Rec *>(cand + n2);
+        if (tid == 0) {
+            int nOut = 0;
+            if (emitIdentity) {
+                Rec r; r.w0 = seqHash; r.w1 = ((unsigned long long) id << 32) | ((unsigned long long) (L & 0xFFFF) << 16);
+                outRecs[nOut++] = r;
+            }
+            if (cnt > 0 && kmerConsidered > 0)
+                nOut += select_sequential(cand, inBins, kmerConsidered, threshold, sTooMuch, c, id, (unsigned) L, outRecs + nOut);
+            sNOut = nOut;
+            sBase = nOut ? atomicAdd(outCount, (unsigned long long) nOut) : 0ULL;
+        }
+        __syncthreads();
+        const int nOut = sNOut;
+        const unsigned long long base = sBase;
+        if (base + nOut <= outCap)
+            for (int i = tid; i < nOut; i += 256) out[base + i] = outRecs[i];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// group: assignGroup (kmermatcher.cpp:450-559) on records sorted by k-mer.
+// ------------------------------------------------------------------------------------------------
+constexpr int GROUP_THREADS = 256;
+constexpr int GROUP_ITEMS = 4;
+constexpr int GROUP_TILE = GROUP_THREADS * GROUP_ITEMS;   // 1024 records (static shared memory stays below 48 KiB)
+
+struct GroupAcc {            // partial reduction of one k-mer group
+    unsigned long long key;  // min of rep_key(w1)
+    unsigned strand;         // bit 63 of the k-mer word of the record holding `key`
+    unsigned count;
+};
+__device__ __forceinline__ unsigned long long rep_key(unsigned long long w1) {
+    // order (seqLen desc, id asc, pos asc) -- compareRepSequenceAndIdAndPos (kmermatcher.h:56-96)
+    const unsigned long long id = w1 >> 32, len = (w1 >> 16) & 0xFFFFULL, pos = w1 & 0xFFFFULL;
+    return ((0xFFFFULL ^ len) << 48) | (id << 16) | pos;
+}
+__device__ __forceinline__ void acc_add(GroupAcc &a, unsigned long long key, unsigned strand, unsigned count) {
+    if (count == 0) return;
+    if (a.count == 0 || key < a.key || (key == a.key && strand < a.strand)) { a.key = key; a.strand = strand; }
+    a.count += count;
+}
+
+// Util::canBeCovered (Util.cpp:533-551)
+__device__ __forceinline__ bool can_be_covered(float covThr, int covMode, float q, float t) {
+    switch (covMode) {
+        case 0: return (q / t >= covThr) && (t / q >= covThr);
+        case 1: return (t / q) >= covThr;
+        case 2: return (q / t) >= covThr;
+        case 3: return (t / q) >= covThr && (t / q) <= 1.0f;
+        case 4: return (q / t) >= covThr && (q / t) <= 1.0f;
+        case 5: return (fminf(t, q) / fmaxf(t, q)) >= covThr;
+        default: return true;
+    }
+}
+
+__global__ void __launch_bounds__(GROUP_THREADS) group_kernel(const Rec *__restrict__ in, unsigned long long n, const KmConst c,
+                                                              Rec *__restrict__ out, unsigned long long *__restrict__ outCount) {
+    __shared__ Rec tile[GROUP_TILE];
+    __shared__ int headIdx[GROUP_TILE];       // index (in tile) of the first record of the group of record i
+    __shared__ GroupAcc gacc[GROUP_TILE];     // valid at head indices: reduction of the whole group
+    __shared__ GroupAcc sBack, sFwd;
+    __shared__ int sBackAtZero;
+    __shared__ unsigned sWarpOut[GROUP_THREADS / 32];
+    __shared__ unsigned long long sOutBase;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int nt = c.nt;
+    const unsigned long long tileBase = (unsigned long long) blockIdx.x * GROUP_TILE;
+    const int count = (int) min((unsigned long long) GROUP_TILE, n - tileBase);
+    for (int i = tid; i < count; i += GROUP_THREADS) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(in + tileBase) + i);
+        Rec r; r.w0 = ((unsigned long long) raw.y << 32) | raw.x; r.w1 = ((unsigned long long) raw.w << 32) | raw.z;
+        tile[i] = r;
+    }
+    __syncthreads();
+    // warp 0 walks backwards from the tile start, warp 1 forwards from the tile end, over the
+    // records of the groups cut by the tile boundary.
+    if (w == 0) {
+        GroupAcc a; a.key = 0; a.strand = 0; a.count = 0;
+        const unsigned long long k0 = cmp_kmer(tile[0].w0, nt);
+        long long p = (long long) tileBase - 1 - lane;
+        int atZero = (tileBase == 0);
+        bool go = true;
+        while (go) {
+            bool same = false; unsigned long long key = 0; unsigned st = 0;
+            if (p >= 0) {
+                const Rec r = in[p];
+                same = cmp_kmer(r.w0, nt) == k0;
+                key = rep_key(r.w1); st = (unsigned) (r.w0 >> 63);
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, same);
+            // records are contiguous: count matches from lane 0 upwards until the first mismatch
+            const unsigned firstMiss = __ffs(~m);     // 1-based lane of first non-match, 0 if all match
+            const int take = firstMiss ? (int) firstMiss - 1 : 32;
+            for (int l = 0; l < take; l++) {
+                const unsigned long long kl = __shfl_sync(0xFFFFFFFFu, key, l);
+                const unsigned sl = __shfl_sync(0xFFFFFFFFu, st, l);
+                acc_add(a, kl, sl, 1);
+            }
+            if (take == 32) {
+                p -= 32;
+                if (__shfl_sync(0xFFFFFFFFu, p, 0) < 0) { go = false; atZero = 1; }
+            } else {
+                go = false;
+                // group start is global index 0 iff we ran off the front
+                const long long lastTaken = __shfl_sync(0xFFFFFFFFu, p, 0) - (take - 1);
+                atZero = (take > 0) ? (lastTaken == 0) : (tileBase == 0);
+            }
+        }
+        if (lane == 0) { sBack = a; sBackAtZero = atZero; }
+    } else if (w == 1) {
+        GroupAcc a; a.key = 0; a.strand = 0; a.count = 0;
+        const unsigned long long k1 = cmp_kmer(tile[count - 1].w0, nt);
+        unsigned long long p = tileBase + count + lane;
+        bool go = true;
+        while (go) {
+            bool same = false; unsigned long long key = 0; unsigned st = 0;
+            if (p < n) {
+                const Rec r = in[p];
+                same = cmp_kmer(r.w0, nt) == k1;
+                key = rep_key(r.w1); st = (unsigned) (r.w0 >> 63);
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, same);
+            const unsigned firstMiss = __ffs(~m);
+            const int take = firstMiss ? (int) firstMiss - 1 : 32;
+            for (int l = 0; l < take; l++) {
+                const unsigned long long kl = __shfl_sync(0xFFFFFFFFu, key, l);
+                const unsigned sl = __shfl_sync(0xFFFFFFFFu, st, l);
+                acc_add(a, kl, sl, 1);
+            }
+            if (take == 32) p += 32; else go = false;
+        }
+        if (lane == 0) sFwd = a;
+    }
+    // head flags -> head index by a running max inside each thread's contiguous chunk + block scan
+    {
+        const int b = tid * GROUP_ITEMS;
+        int last = -1;
+        for (int i = b; i < b + GROUP_ITEMS && i < count; i++) {
+            const bool head = (i == 0) || cmp_kmer(tile[i].w0, nt) != cmp_kmer(tile[i - 1].w0, nt);
+            if (head) last = i;
+            headIdx[i] = last;   // -1 = group started in an earlier chunk
+        }
+        // block inclusive max-scan of `last`
+        int v = last;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int nb = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= o) v = max(v, nb); }
+        __shared__ int sWarpMax[GROUP_THREADS / 32];
+        if (lane == 31) sWarpMax[w] = v;
+        __syncthreads();
+        int carry = -1;
+        for (int ww = 0; ww < w; ww++) carry = max(carry, sWarpMax[ww]);
+        const int prevThreads = __shfl_up_sync(0xFFFFFFFFu, v, 1);
+        const int before = max(carry, lane > 0 ? prevThreads : -1);   // max head index of all earlier chunks
+        for (int i = b; i < b + GROUP_ITEMS && i < count; i++)
+            if (headIdx[i] < 0) headIdx[i] = before;
+    }
+    __syncthreads();
+    // each head reduces its in-tile group (groups are short; heavy hitters loop)
+    for (int i = tid; i < count; i += GROUP_THREADS) {
+        if (headIdx[i] == i) {
+            GroupAcc a; a.key = 0; a.strand = 0; a.count = 0;
+            const unsigned long long km = cmp_kmer(tile[i].w0, nt);
+            int j = i;
+            while (j < count && cmp_kmer(tile[j].w0, nt) == km) {
+                acc_add(a, rep_key(tile[j].w1), (unsigned) (tile[j].w0 >> 63), 1);
+                j++;
+            }
+            if (i == 0) acc_add(a, sBack.key, sBack.strand, sBack.count);
+            if (j == count) acc_add(a, sFwd.key, sFwd.strand, sFwd.count);
+            gacc[i] = a;
+        }
+    }
+    __syncthreads();
+    // emit
+    unsigned long long outBase = 0;
+    Rec outRec[GROUP_ITEMS];
+    unsigned keepMask = 0;
+#pragma unroll
+    for (int it = 0; it < GROUP_ITEMS; it++) {
+        const int i = it * GROUP_THREADS + tid;
+        bool keep = false;
+        if (i < count) {
+            const int h = headIdx[i];
+            const GroupAcc a = gacc[h];
+            if (a.count >= 2) {
+                const Rec r = tile[i];
+                const unsigned repId = (unsigned) ((a.key >> 16) & 0xFFFFFFFFULL);
+                const int queryLen = (int) (0xFFFFULL ^ (a.key >> 48));
+                const int repPos = (int) (short) (a.key & 0xFFFFULL);
+                const unsigned tId = (unsigned) (r.w1 >> 32);
+                const int tLen = (int) (short) ((r.w1 >> 16) & 0xFFFFULL);
+                const int tPos = (int) (short) (r.w1 & 0xFFFFULL);
+                int diagonal = repPos - tPos;
+                unsigned qRev = 0;
+                if (nt) {
+                    // the reference initialises repIsReverse = false for the very first group (kmermatcher.cpp:463)
+                    const bool firstGroup = (h == 0) && sBackAtZero;
+                    const bool repIsReverse = firstGroup ? false : (a.strand == 0);
+                    const bool targetIsReverse = ((r.w0 >> 63) == 0);
+                    int queryPos, targetPos;
+                    if (repIsReverse && !targetIsReverse) { queryPos = repPos; targetPos = tPos; qRev = 1; }
+                    else if (repIsReverse && targetIsReverse) { queryPos = (short) ((queryLen - 1) - repPos); targetPos = (short) ((tLen - 1) - tPos); qRev = 0; }
+                    else if (!repIsReverse && targetIsReverse) { queryPos = (short) ((queryLen - 1) - repPos); targetPos = (short) ((tLen - 1) - tPos); qRev = 1; }
+                    else { queryPos = repPos; targetPos = tPos; qRev = 0; }
+                    diagonal = queryPos - targetPos;
+                }
+                const bool canBeExtended = diagonal < 0 || (diagonal > (queryLen - tLen));
+                const bool covered = can_be_covered(c.covThr, c.covMode, (float) queryLen, (float) tLen);
+                keep = (c.includeOnlyExtendable == 0 && covered) || (canBeExtended && c.includeOnlyExtendable != 0);
+                if (keep) {
+                    outRec[it].w0 = ((unsigned long long) repId << 32) | tId;
+                    const unsigned biased = (unsigned) (((int) (short) diagonal) + 32768) & 0xFFFFu;
+                    outRec[it].w1 = ((unsigned long long) qRev << 16) | biased;
+                }
+            }
+        }
+        if (keep) keepMask |= 1u << it;
+    }
+    // block compaction (order inside the output is irrelevant: sort #2 follows)
+    const unsigned mine = __popc(keepMask);
+    unsigned v = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= o) v += nb; }
+    if (lane == 31) sWarpOut[w] = v;
+    __syncthreads();
+    unsigned woff = 0, total = 0;
+    for (int ww = 0; ww < GROUP_THREADS / 32; ww++) { if (ww < w) woff += sWarpOut[ww]; total += sWarpOut[ww]; }
+    if (tid == 0) sOutBase = total ? atomicAdd(outCount, (unsigned long long) total) : 0ULL;
+    __syncthreads();
+    outBase = sOutBase + woff + v - mine;
+#pragma unroll
+    for (int it = 0; it < GROUP_ITEMS; it++)
+        if (keepMask & (1u << it)) {
+            uint4 raw;
+            raw.x = (unsigned) outRec[it].w0; raw.y = (unsigned) (outRec[it].w0 >> 32);
+            raw.z = (unsigned) outRec[it].w1; raw.w = (unsigned) (outRec[it].w1 >> 32);
+            reinterpret_cast<uint4 *>(out)[outBase++] = raw;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reduce: writeKmerMatcherResult (kmermatcher.cpp:809-924) on pairs sorted by (rep, target, diagonal).
+// A run starts where rep or target changes; the scan over the run continues while the TARGET id stays
+// the same even across a rep boundary (the reference's while-loop at :880 only tests the id).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool reduce_one(const Rec *__restrict__ in, unsigned long long n, unsigned long long i, pg_hit &h) {
+    const Rec r = in[i];
+    if (i > 0 && in[i - 1].w0 == r.w0) return false;            // not the first record of (rep, target)
+    const unsigned rep = (unsigned) (r.w0 >> 32), target = (unsigned) r.w0;
+    unsigned diagB = (unsigned) (r.w1 & 0xFFFFu), prevDiag = diagB;
+    unsigned best = diagB, bestRev = (unsigned) ((r.w1 >> 16) & 1u);
+    unsigned maxDiag = 0, diagCnt = 0, top = 0;
+    unsigned long long j = i;
+    while (j < n) {
+        const Rec q = in[j];
+        if ((unsigned) q.w0 != target) break;
+        const unsigned d = (unsigned) (q.w1 & 0xFFFFu);
+        diagCnt = (prevDiag == d) ? diagCnt + 1 : 1;
+        if (diagCnt >= maxDiag) { best = d; maxDiag = diagCnt; bestRev = (unsigned) ((q.w1 >> 16) & 1u); }
+        prevDiag = d;
+        j++; top++;
+    }
+    if (target == rep) return false;                             // :899-904
+    h.rep = rep; h.target = target;
+    h.score = bestRev ? -(int) top : (int) top;
+    h.diag = (int) (short) (unsigned short) (best - 32768u);
+    return true;
+}
+
+__global__ void __launch_bounds__(256) reduce_count_kernel(const Rec *__restrict__ in, unsigned long long n, unsigned *__restrict__ blockCounts) {
+    const unsigned long long i = (unsigned long long) blockIdx.x * 256 + threadIdx.x;
+    pg_hit h;
+    const bool emit = (i < n) && reduce_one(in, n, i, h);
+    const unsigned c = __syncthreads_count(emit);
+    if (threadIdx.x == 0) blockCounts[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(256) reduce_emit_kernel(const Rec *__restrict__ in, unsigned long long n,
+                                                          const unsigned long long *__restrict__ blockOffsets, pg_hit *__restrict__ hits) {
+    __shared__ unsigned sWarp[8];
+    const unsigned long long i = (unsigned long long) blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    pg_hit h;
+    const bool emit = (i < n) && reduce_one(in, n, i, h);
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, emit);
+    if (lane == 0) sWarp[w] = __popc(m);
+    __syncthreads();
+    unsigned off = 0;
+    for (int ww = 0; ww < w; ww++) off += sWarp[ww];
+    if (emit) hits[blockOffsets[blockIdx.x] + off + __popc(m & ((1u << lane) - 1u))] = h;
+}
+
+// exclusive scan of per-block counts (single block, sequential chunks; counts <= 2^24 blocks)
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const unsigned *__restrict__ counts, unsigned long long nBlocks,
+                                                           unsigned long long *__restrict__ offsets, unsigned long long *__restrict__ total) {
+    __shared__ unsigned long long sWarp[32];
+    __shared__ unsigned long long sCarry;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) sCarry = 0;
+    __syncthreads();
+    for (unsigned long long b = 0; b < nBlocks; b += 1024) {
+        const unsigned long long i = b + tid;
+        const unsigned long long c = (i < nBlocks) ? counts[i] : 0ULL;
+        unsigned long long v = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long nb = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= o) v += nb; }
+        if (lane == 31) sWarp[w] = v;
+        __syncthreads();
+        unsigned long long woff = 0;
+        for (int ww = 0; ww < w; ww++) woff += sWarp[ww];
+        const unsigned long long carry = sCarry;
+        if (i < nBlocks) offsets[i] = carry + woff + v - c;
+        __syncthreads();
+        if (tid == 1023) sCarry = carry + woff + v;
+        __syncthreads();
+    }
+    if (tid == 0) *total = sCarry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------
+static int bits_for(unsigned maxValue) {
+    int b = 1;
+    while (b < 32 && (maxValue >> b) != 0) b++;
+    return b;
+}
+
+int km_setup_constants(const pg_seqdb *db, const pg_km_params *p, KmConst &c, cudaStream_t stream) {
+    const bool nt = db->dbtype == PG_DBTYPE_NUCLEOTIDES;
+    PG_CHECK(p->kmer_size >= 2 && p->kmer_size <= (nt ? 31 : 14), "kmermatcher: unsupported k (aa: 2..14 in base-(alph-1) < 2^63, nt: 2..31)");
+    PG_CHECK(nt || p->alph_size == 13 || p->alph_size == 21, "kmermatcher: --alph-size must be 13 or 21 for amino acids");
+    PG_CHECK(db->max_seq_len < 32767, "kmermatcher: sequences >= 32767 residues need the wide (T=int) record layout, which is not built yet");
+    const unsigned char *tab = nt ? PG_NT_AA2NUM : (p->alph_size == 21 ? PG_AA_AA2NUM : PG_RED_AA2NUM);
+    PG_CUDA(cudaMemcpyToSymbolAsync(c_aa2num, tab, 256, 0, cudaMemcpyHostToDevice, stream));
+    c.k = p->kmer_size; c.nt = nt ? 1 : 0;
+    c.xCode = nt ? 4 : p->alph_size - 1;
+    c.base = nt ? 4u : (unsigned) (p->alph_size - 1);
+    c.seed = (unsigned long long) p->hash_shift;
+    c.kmersPerSeq = p->kmers_per_seq; c.scale = p->kmers_per_seq_scale;
+    c.ignoreMulti = p->ignore_multi_kmer;
+    c.hashStart = p->hash_start; c.hashEnd = p->hash_end;
+    c.includeOnlyExtendable = p->include_only_extendable;
+    c.covMode = p->cov_mode; c.covThr = p->cov_thr;
+    return 0;
+}
+
+// computeKmerCount (kmermatcher.cpp:576-585): upper bound on emitted records
+static __global__ void kmer_count_kernel(const unsigned *__restrict__ lens, unsigned n, int k, int kps, float scale,
+                                         unsigned long long *__restrict__ total) {
+    unsigned long long mine = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int seqLen = (int) lens[i] - 2;
+        const int adj = max(1, seqLen - k + 2);
+        mine += (unsigned long long) min(adj, (int) ((float) kps + (scale * (float) seqLen)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(total, mine);
+}
+
+template <int NMAX>
+static int launch_extract_warp(const pg_seqdb &db, const unsigned *list, const unsigned *listCount, unsigned hostCount, const KmConst &c,
+                               Rec *out, unsigned long long *outCount, unsigned long long outCap, cudaStream_t stream, uint64_t *launches) {
+    if (hostCount == 0) return 0;
+    const size_t smem = 4 * ((size_t) NMAX * sizeof(Cand) + (size_t) (NMAX + 1) * sizeof(Rec) + (NMAX + 40));
+    PG_CUDA(cudaFuncSetAttribute(extract_warp_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    unsigned blocks = (hostCount + 3) / 4;
+    const unsigned maxBlocks = NUM_SMS * 32;
+    if (blocks > maxBlocks) blocks = maxBlocks;
+    extract_warp_kernel<NMAX><<<blocks, 128, smem, stream>>>(db, list, listCount, c, out, outCount, outCap);
+    if (launches) (*launches)++;
+    return 0;
+}
+
+// Stage 1: extraction.  Leaves the records in ws.recA, returns their count.
+int km_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const KmConst &c, uint64_t *nRecords) {
+    cudaStream_t s = ctx->stream;
+    const unsigned n = (unsigned) db->n;
+    PG_CHECK(c.ignoreMulti || db->max_seq_len - c.k + 1 <= 1024, "kmermatcher: --ignore-multi-kmer 0 with sequences of more than 1024 k-mers is not supported");
+    PG_TRY(ctx->small.reserve(4096));
+    unsigned long long *d_total = ctx->small.as<unsigned long long>();        // [0] capacity estimate
+    unsigned long long *d_outCount = d_total + 1;                             // [1] emitted records
+    unsigned *d_clsCount = (unsigned *) (d_total + 8);                        // [8..] 4 class counters
+    PG_CUDA(cudaMemsetAsync(d_total, 0, 256, s));
+    kmer_count_kernel<<<NUM_SMS * 4, 256, 0, s>>>(db->lens, n, c.k, c.kmersPerSeq, c.scale, d_total);
+    PG_TRY(ctx->lists.reserve(sizeof(unsigned) * 4 * (size_t) n + 16));
+    unsigned *lists = ctx->lists.as<unsigned>();
+    classify_kernel<<<(n + 255) / 256, 256, 0, s>>>(db->lens, n, c.k, lists, d_clsCount);
+    ctx->launches += 2;
+    unsigned long long h_total = 0; unsigned h_cls[4];
+    PG_CUDA(cudaMemcpyAsync(&h_total, d_total, sizeof(h_total), cudaMemcpyDeviceToHost, s));
+    PG_CUDA(cudaMemcpyAsync(h_cls, d_clsCount, sizeof(h_cls), cudaMemcpyDeviceToHost, s));
+    PG_CUDA(cudaStreamSynchronize(s));
+    const unsigned long long cap = h_total + 1;
+    PG_TRY(ctx->recA.reserve(sizeof(Rec) * cap));
+    PG_TRY(ctx->recB.reserve(sizeof(Rec) * cap));
+    Rec *out = ctx->recA.as<Rec>();
+    PG_TRY(launch_extract_warp<64>(*db, lists + 0 * (size_t) n, d_clsCount + 0, h_cls[0], c, out, d_outCount, cap, s, &ctx->launches));
+    PG_TRY(launch_extract_warp<256>(*db, lists + 1 * (size_t) n, d_clsCount + 1, h_cls[1], c, out, d_outCount, cap, s, &ctx->launches));
+    PG_TRY(launch_extract_warp<1024>(*db, lists + 2 * (size_t) n, d_clsCount + 2, h_cls[2], c, out, d_outCount, cap, s, &ctx->launches));
+    if (h_cls[3]) {
+        const unsigned maxL = db->max_seq_len;
+        size_t n2 = 1;
+        const size_t maxCand = (size_t) maxL + 1;   // worst case: every window shares one score (low-complexity sequence)
+        while (n2 < maxCand) n2 <<= 1;
+        const size_t perBlock = (((size_t) maxL + 32) & ~(size_t) 15) + n2 * sizeof(Cand) + (maxCand + 2) * sizeof(Rec);
+        unsigned blocks = h_cls[3] < (unsigned) NUM_SMS * 2 ? h_cls[3] : NUM_SMS * 2;
+        PG_TRY(ctx->scratch.reserve(perBlock * blocks));
+        extract_block_kernel<<<blocks, 256, 0, s>>>(*db, lists + 3 * (size_t) n, d_clsCount + 3, c, out, d_outCount, cap,
+                                                    ctx->scratch.as<unsigned char>(), perBlock);
+        ctx->launches++;
+    }
+    unsigned long long h_out = 0;
+    PG_CUDA(cudaMemcpyAsync(&h_out, d_outCount, sizeof(h_out), cudaMemcpyDeviceToHost, s));
+    PG_CUDA(cudaStreamSynchronize(s));
+    PG_CUDA(cudaGetLastError());
+    PG_CHECK(h_out <= cap, "kmermatcher: k-mer array overflow");
+    *nRecords = h_out;
+    (void) p;
+    return 0;
+}
+
+// Stage 2: sort #1 + group.  Input records in recA (n), output pair records in recA (count returned).
+int km_group(Context *ctx, const pg_seqdb *db, const KmConst &c, uint64_t nRecords, uint64_t *nPairs) {
+    cudaStream_t s = ctx->stream;
+    *nPairs = 0;
+    if (nRecords == 0) return 0;
+    RadixPlan plan; plan.npasses = 0;
+    plan_add_bits(plan, 0, 0, c.nt ? 63 : 64);   // nt: bit 63 is the strand flag, not part of the key (kmermatcher.h:77-96)
+    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nRecords)));
+    Rec *sorted = nullptr;
+    cudaEventRecord(ctx->ev[EV_SORT1_BEGIN], s);
+    PG_TRY(radix_sort(ctx->recA.as<Rec>(), ctx->recB.as<Rec>(), nRecords, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches));
+    cudaEventRecord(ctx->ev[EV_SORT1_END], s);
+    Rec *outBuf = (sorted == ctx->recA.as<Rec>()) ? ctx->recB.as<Rec>() : ctx->recA.as<Rec>();
+    unsigned long long *d_cnt = ctx->small.as<unsigned long long>() + 2;
+    PG_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
+    const unsigned blocks = (unsigned) ((nRecords + GROUP_TILE - 1) / GROUP_TILE);
+    group_kernel<<<blocks, GROUP_THREADS, 0, s>>>(sorted, nRecords, c, outBuf, d_cnt);
+    ctx->launches++;
+    cudaEventRecord(ctx->ev[EV_GROUP_END], s);
+    unsigned long long h = 0;
+    PG_CUDA(cudaMemcpyAsync(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, s));
+    PG_CUDA(cudaStreamSynchronize(s));
+    PG_CUDA(cudaGetLastError());
+    *nPairs = h;
+    ctx->pairsInA = (outBuf == ctx->recA.as<Rec>());
+    (void) db;
+    return 0;
+}
+
+// Stage 3: sort #2 + best-diagonal reduction.  Pairs are in `pairs` (device), scratch in `tmp`.
+int km_reduce(Context *ctx, const pg_seqdb *db, Rec *pairs, Rec *tmp, uint64_t nPairs, pg_hit **d_hits, uint64_t *nHits) {
+    cudaStream_t s = ctx->stream;
+    *nHits = 0; *d_hits = nullptr;
+    if (nPairs == 0) return 0;
+    const int keyBits = bits_for(db->max_key);
+    RadixPlan plan; plan.npasses = 0;
+    plan_add_bits(plan, 1, 0, 16);                 // diagonal (biased so that the signed order is kept)
+    plan_add_bits(plan, 0, 0, keyBits);            // target id
+    plan_add_bits(plan, 0, 32, 32 + keyBits);      // representative
+    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nPairs)));
+    Rec *sorted = nullptr;
+    PG_TRY(radix_sort(pairs, tmp, nPairs, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches));
+    cudaEventRecord(ctx->ev[EV_SORT2_END], s);
+    const unsigned long long blocks = (nPairs + 255) / 256;
+    PG_TRY(ctx->blockCounts.reserve(sizeof(unsigned) * blocks + sizeof(unsigned long long) * (blocks + 2)));
+    unsigned *d_counts = ctx->blockCounts.as<unsigned>();
+    unsigned long long *d_offsets = (unsigned long long *) (ctx->blockCounts.as<unsigned char>() + ((sizeof(unsigned) * blocks + 15) & ~(size_t) 15));
+    unsigned long long *d_total = ctx->small.as<unsigned long long>() + 3;
+    reduce_count_kernel<<<(unsigned) blocks, 256, 0, s>>>(sorted, nPairs, d_counts);
+    scan_counts_kernel<<<1, 1024, 0, s>>>(d_counts, blocks, d_offsets, d_total);
+    unsigned long long h = 0;
+    PG_CUDA(cudaMemcpyAsync(&h, d_total, sizeof(h), cudaMemcpyDeviceToHost, s));
+    PG_CUDA(cudaStreamSynchronize(s));
+    PG_TRY(ctx->hits.reserve(sizeof(pg_hit) * (h + 1)));
+    reduce_emit_kernel<<<(unsigned) blocks, 256, 0, s>>>(sorted, nPairs, d_offsets, ctx->hits.as<pg_hit>());
+    ctx->launches += 3;
+    cudaEventRecord(ctx->ev[EV_REDUCE_END], s);
+    PG_CUDA(cudaGetLastError());
+    *d_hits = ctx->hits.as<pg_hit>();
+    *nHits = h;
+    return 0;
+}
+
+// Whole kmermatcher on one GPU; hits stay on the device (ctx->hits).
+int km_run(Context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **d_hits, uint64_t *nHits) {
+    KmConst c;
+    cudaStream_t s = ctx->stream;
+    PG_TRY(km_setup_constants(db, p, c, s));
+    cudaEventRecord(ctx->ev[EV_KM_BEGIN], s);
+    uint64_t nRec = 0, nPairs = 0;
+    PG_TRY(km_extract(ctx, db, p, c, &nRec));
+    cudaEventRecord(ctx->ev[EV_EXTRACT_END], s);
+    PG_TRY(km_group(ctx, db, c, nRec, &nPairs));
+    Rec *pairs = ctx->pairsInA ? ctx->recA.as<Rec>() : ctx->recB.as<Rec>();
+    Rec *tmp = ctx->pairsInA ? ctx->recB.as<Rec>() : ctx->recA.as<Rec>();
+    if (nRec == 0) {
+        cudaEventRecord(ctx->ev[EV_SORT1_BEGIN], s); cudaEventRecord(ctx->ev[EV_SORT1_END], s); cudaEventRecord(ctx->ev[EV_GROUP_END], s);
+    }
+    if (nPairs == 0) { cudaEventRecord(ctx->ev[EV_SORT2_END], s); cudaEventRecord(ctx->ev[EV_REDUCE_END], s); }
+    PG_TRY(km_reduce(ctx, db, pairs, tmp, nPairs, d_hits, nHits));
+    ctx->timings.n_kmer_records = nRec;
+    ctx->timings.n_pair_records = nPairs;
+    ctx->timings.n_hits = *nHits;
+    ctx->timings.sort1_bytes = (uint64_t) nRec * sizeof(Rec) * 2;
+    ctx->kmRan = true;
+    return 0;
+}
+
+}  // namespace pg
+
+// diagnostic used by the tests: the k-mer records of stage 1 (order unspecified), n x {w0, w1}
+extern "C" int pg_debug_extract(pg_context *ctx, const pg_seqdb *db, const pg_km_params *p, uint64_t **recs, uint64_t *n) {
+    using namespace pg;
+    PG_CHECK(ctx && db && p && recs && n, "pg_debug_extract: null argument");
+    cudaSetDevice(ctx->device);
+    KmConst c;
+    PG_TRY(km_setup_constants(db, p, c, ctx->stream));
+    uint64_t nRec = 0;
+    PG_TRY(km_extract(ctx, db, p, c, &nRec));
+    uint64_t *h = nullptr;
+    PG_CUDA(cudaMallocHost(&h, sizeof(Rec) * (nRec + 1)));
+    PG_CUDA(cudaMemcpyAsync(h, ctx->recA.p, sizeof(Rec) * nRec, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    *recs = h; *n = nRec;
+    return 0;
+}

@@ -1,0 +1,252 @@
+// pg_radix.cu -- see pg_radix.cuh.
+#include "pg_radix.cuh"
+
+namespace pg {
+
+namespace {
+
+__device__ __forceinline__ unsigned digit_of(const Rec &r, const DigitPass p) {
+    unsigned long long w = p.word ? r.w1 : r.w0;
+    return (unsigned) (w >> p.shift) & p.mask;
+}
+
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(unsigned *p, unsigned v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- histograms of all passes in one read -------------------------------------------------------
+__global__ void __launch_bounds__(512) radix_hist_kernel(const Rec *__restrict__ in, unsigned long long n, RadixPlan plan,
+                                                         unsigned long long *__restrict__ ghist) {
+    __shared__ unsigned sh[RADIX_MAX_PASSES * 256];
+    const int np = plan.npasses;
+    for (int i = threadIdx.x; i < np * 256; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(in) + i);
+        Rec r;
+        r.w0 = ((unsigned long long) raw.y << 32) | raw.x;
+        r.w1 = ((unsigned long long) raw.w << 32) | raw.z;
+#pragma unroll 4
+        for (int p = 0; p < np; p++) atomicAdd(&sh[p * 256 + digit_of(r, plan.pass[p])], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < np * 256; i += blockDim.x)
+        if (sh[i]) atomicAdd(&ghist[i], (unsigned long long) sh[i]);
+}
+
+// exclusive scan of each pass's 256 bins -> bases[p][portion 0][256]
+__global__ void radix_scan_kernel(const unsigned long long *__restrict__ ghist, unsigned long long *__restrict__ bases,
+                                  int portionsPlus1) {
+    __shared__ unsigned long long s[256];
+    const int p = blockIdx.x, t = threadIdx.x;
+    s[t] = ghist[p * 256 + t];
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < 256; i++) { unsigned long long c = s[i]; s[i] = run; run += c; }
+    }
+    __syncthreads();
+    bases[((size_t) p * portionsPlus1) * 256 + t] = s[t];
+}
+
+// ---- one pass over one portion ------------------------------------------------------------------
+constexpr unsigned FLAG_AGG = 1u, FLAG_INC = 2u;
+
+__global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(
+    const Rec *__restrict__ in, Rec *__restrict__ out, unsigned long long portionStart, unsigned long long portionEnd,
+    DigitPass dp, const unsigned long long *__restrict__ gbase, unsigned long long *__restrict__ gbaseNext,
+    unsigned *status, unsigned *ticket, unsigned numTiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Rec *tileRecs = reinterpret_cast<Rec *>(smem_raw);
+    __shared__ unsigned short warpCnt[RADIX_THREADS / 32][256];
+    __shared__ unsigned digitStart[256];
+    __shared__ long long goff[256];
+    __shared__ unsigned warpTotals[RADIX_THREADS / 32];
+    __shared__ unsigned sTile;
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) sTile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < (RADIX_THREADS / 32) * 256; i += RADIX_THREADS) (&warpCnt[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned tile = sTile;
+    const unsigned long long tileBase = portionStart + (unsigned long long) tile * RADIX_TILE;
+    const unsigned count = (unsigned) min((unsigned long long) RADIX_TILE, portionEnd - tileBase);
+
+    // load: warp w owns items [w*512, (w+1)*512), round r covers 32 consecutive records
+    Rec rec[RADIX_ITEMS];
+    unsigned short rank[RADIX_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RADIX_ITEMS; r++) {
+        const unsigned idx = w * (RADIX_ITEMS * 32) + r * 32 + lane;
+        if (idx < count) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(in + tileBase) + idx);
+            rec[r].w0 = ((unsigned long long) raw.y << 32) | raw.x;
+            rec[r].w1 = ((unsigned long long) raw.w << 32) | raw.z;
+        } else {
+            rec[r].w0 = 0; rec[r].w1 = 0;
+        }
+    }
+    // rank: warp-private counters + match_any
+    const unsigned ltMask = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RADIX_ITEMS; r++) {
+        const unsigned idx = w * (RADIX_ITEMS * 32) + r * 32 + lane;
+        const bool valid = idx < count;
+        const unsigned d = valid ? digit_of(rec[r], dp) : 256u;
+        const unsigned m = __match_any_sync(0xFFFFFFFFu, d);
+        unsigned c = 0;
+        if (valid) c = warpCnt[w][d];
+        rank[r] = (unsigned short) (c + __popc(m & ltMask));
+        __syncwarp();
+        if (valid && (m & ltMask) == 0) warpCnt[w][d] = (unsigned short) (c + __popc(m));
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit: exclusive prefix over warps, total count
+    unsigned cnt;
+    {
+        unsigned run = 0;
+#pragma unroll
+        for (int ww = 0; ww < RADIX_THREADS / 32; ww++) {
+            const unsigned c = warpCnt[ww][tid];
+            warpCnt[ww][tid] = (unsigned short) run;
+            run += c;
+        }
+        cnt = run;
+    }
+    // publish the aggregate early so successors can look back while we keep working
+    if (tile == 0) st_volatile_u32(&status[tid], (cnt << 2) | FLAG_INC);
+    else st_volatile_u32(&status[(size_t) tile * 256 + tid], (cnt << 2) | FLAG_AGG);
+    // block exclusive scan of cnt over the 256 digits
+    {
+        unsigned v = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, v, o);
+            if (lane >= o) v += nb;
+        }
+        if (lane == 31) warpTotals[w] = v;
+        __syncthreads();
+        unsigned woff = 0;
+#pragma unroll
+        for (int ww = 0; ww < RADIX_THREADS / 32; ww++) woff += (ww < w) ? warpTotals[ww] : 0u;
+        digitStart[tid] = woff + v - cnt;
+    }
+    __syncthreads();
+    // reorder through shared memory
+#pragma unroll
+    for (int r = 0; r < RADIX_ITEMS; r++) {
+        const unsigned idx = w * (RADIX_ITEMS * 32) + r * 32 + lane;
+        if (idx < count) {
+            const unsigned d = digit_of(rec[r], dp);
+            const unsigned pos = digitStart[d] + warpCnt[w][d] + rank[r];
+            tileRecs[pos] = rec[r];
+        }
+    }
+    // decoupled look-back: exclusive prefix of this digit over all earlier tiles of the portion
+    {
+        unsigned long long prev = 0;
+        if (tile > 0) {
+            long long ll = (long long) tile - 1;
+            while (true) {
+                const unsigned v = ld_volatile_u32(&status[(size_t) ll * 256 + tid]);
+                const unsigned f = v & 3u;
+                if (f == FLAG_INC) { prev += v >> 2; break; }
+                if (f == FLAG_AGG) { prev += v >> 2; ll--; }
+            }
+            st_volatile_u32(&status[(size_t) tile * 256 + tid], ((unsigned) (prev + cnt) << 2) | FLAG_INC);
+        }
+        const unsigned long long base = gbase[tid];
+        goff[tid] = (long long) (base + prev) - (long long) digitStart[tid];
+        if (tile == numTiles - 1) gbaseNext[tid] = base + prev + cnt;
+    }
+    __syncthreads();
+    for (unsigned j = tid; j < count; j += RADIX_THREADS) {
+        const Rec r = tileRecs[j];
+        const unsigned d = digit_of(r, dp);
+        uint4 raw;
+        raw.x = (unsigned) r.w0; raw.y = (unsigned) (r.w0 >> 32); raw.z = (unsigned) r.w1; raw.w = (unsigned) (r.w1 >> 32);
+        reinterpret_cast<uint4 *>(out)[goff[d] + (long long) j] = raw;
+    }
+}
+
+constexpr unsigned long long PORTION_RECORDS = ((1ull << 30) / RADIX_TILE - 1) * RADIX_TILE;   // look-back prefix < 2^30
+
+inline unsigned long long num_portions(uint64_t n) { return n == 0 ? 1 : (n + PORTION_RECORDS - 1) / PORTION_RECORDS; }
+inline unsigned long long max_tiles(uint64_t n) {
+    const unsigned long long per = n < PORTION_RECORDS ? n : PORTION_RECORDS;
+    return (per + RADIX_TILE - 1) / RADIX_TILE + 1;
+}
+
+}  // namespace
+
+void plan_add_bits(RadixPlan &plan, int word, int lo, int hi) {
+    for (int b = lo; b < hi; b += 8) {
+        const int bits = (hi - b) < 8 ? (hi - b) : 8;
+        DigitPass &p = plan.pass[plan.npasses++];
+        p.word = word; p.shift = b; p.mask = (1u << bits) - 1u;
+    }
+}
+
+size_t radix_workspace_bytes(uint64_t n) {
+    const size_t hist = sizeof(unsigned long long) * RADIX_MAX_PASSES * 256;
+    const size_t bases = sizeof(unsigned long long) * RADIX_MAX_PASSES * (num_portions(n) + 1) * 256;
+    const size_t status = sizeof(unsigned) * (max_tiles(n) * 256 + 64);
+    return hist + bases + status + 1024;
+}
+
+int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspace, size_t workspace_bytes,
+               cudaStream_t stream, Rec **sorted, uint64_t *launches) {
+    *sorted = a;
+    if (n == 0 || plan.npasses == 0) return 0;
+    PG_CHECK(plan.npasses <= RADIX_MAX_PASSES, "radix_sort: too many passes");
+    PG_CHECK(workspace_bytes >= radix_workspace_bytes(n), "radix_sort: workspace too small");
+    static bool attrSet = false;
+    const int dynSmem = RADIX_TILE * sizeof(Rec);
+    if (!attrSet) {
+        PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dynSmem));
+        attrSet = true;
+    }
+    const unsigned long long portions = num_portions(n);
+    unsigned char *ws = (unsigned char *) workspace;
+    unsigned long long *ghist = (unsigned long long *) ws;
+    unsigned long long *bases = ghist + RADIX_MAX_PASSES * 256;
+    unsigned *status = (unsigned *) (bases + (size_t) RADIX_MAX_PASSES * (portions + 1) * 256);
+    const size_t statusWords = max_tiles(n) * 256 + 64;
+
+    PG_CUDA(cudaMemsetAsync(ghist, 0, sizeof(unsigned long long) * RADIX_MAX_PASSES * 256, stream));
+    int histBlocks = (int) ((n + 512ull * 16 - 1) / (512ull * 16));
+    if (histBlocks > NUM_SMS * 4) histBlocks = NUM_SMS * 4;
+    if (histBlocks < 1) histBlocks = 1;
+    radix_hist_kernel<<<histBlocks, 512, 0, stream>>>(a, n, plan, ghist);
+    radix_scan_kernel<<<plan.npasses, 256, 0, stream>>>(ghist, bases, (int) (portions + 1));
+    if (launches) *launches += 2;
+
+    Rec *src = a, *dst = b;
+    for (int p = 0; p < plan.npasses; p++) {
+        for (unsigned long long q = 0; q < portions; q++) {
+            const unsigned long long ps = q * PORTION_RECORDS;
+            const unsigned long long pe = (ps + PORTION_RECORDS < n) ? ps + PORTION_RECORDS : n;
+            const unsigned tiles = (unsigned) ((pe - ps + RADIX_TILE - 1) / RADIX_TILE);
+            PG_CUDA(cudaMemsetAsync(status, 0, sizeof(unsigned) * ((size_t) tiles * 256 + 64), stream));
+            unsigned *ticket = status + statusWords - 32;
+            PG_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), stream));
+            unsigned long long *gb = bases + ((size_t) p * (portions + 1) + q) * 256;
+            radix_scatter_kernel<<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + 256,
+                                                                          status, ticket, tiles);
+            if (launches) *launches += 1;
+        }
+        Rec *t = src; src = dst; dst = t;
+    }
+    PG_CUDA(cudaGetLastError());
+    *sorted = src;
+    return 0;
+}
+
+}  // namespace pg

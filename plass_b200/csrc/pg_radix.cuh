@@ -1,0 +1,45 @@
+// pg_radix.cuh -- hand-written least-significant-digit radix sort for 16-byte records (sm_100a).
+//
+// Replaces the reference's SORT_PARALLEL (ips4o / omptl) calls, lib/mmseqs/src/commons/FastSort.h:1-24,
+// used at kmermatcher.cpp:408-412 (sort #1) and :427-431 (sort #2).
+//
+// Design (HBM-bound: every pass is one coalesced read + one coalesced write of the records):
+//   * one histogram kernel computes the 256-bin histograms of ALL passes in a single read,
+//   * per pass one "onesweep" kernel: a tile of 4096 records is ranked in registers with
+//     warp match_any + warp-private counters, reordered through shared memory so that every digit
+//     run leaves the SM as contiguous 16-byte stores, and the tile's global offsets come from a
+//     decoupled look-back over per-tile status words (single pass, no second read of the data),
+//   * stable, so passes compose into a multi-word key sort.
+#pragma once
+#include "pg_common.cuh"
+
+namespace pg {
+
+struct DigitPass {
+    int word;            // 0 -> Rec::w0, 1 -> Rec::w1
+    int shift;           // digit = (w >> shift) & mask
+    unsigned mask;       // <= 255
+};
+
+constexpr int RADIX_MAX_PASSES = 12;
+constexpr int RADIX_THREADS = 256;
+constexpr int RADIX_ITEMS = 16;
+constexpr int RADIX_TILE = RADIX_THREADS * RADIX_ITEMS;   // 4096 records = 64 KiB
+
+struct RadixPlan {
+    DigitPass pass[RADIX_MAX_PASSES];
+    int npasses;
+};
+
+// Workspace owned by the caller (sized by radix_workspace_bytes).
+size_t radix_workspace_bytes(uint64_t n);
+
+// Sorts n records by the digits of plan (pass[0] least significant).  `a` holds the input, `b` is a
+// scratch buffer of the same size; *sorted points to whichever of the two holds the result.
+int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspace, size_t workspace_bytes,
+               cudaStream_t stream, Rec **sorted, uint64_t *launches);
+
+// Helper to build a plan over bit ranges: appends 8-bit digits covering bits [lo, hi) of word w.
+void plan_add_bits(RadixPlan &plan, int word, int lo, int hi);
+
+}  // namespace pg

@@ -1,0 +1,311 @@
+// pg_rescore.cu -- GPU rescorediagonal, --rescore-mode 3 (END_TO_END).
+//
+// Replaces doRescorediagonal (reference lib/mmseqs/src/alignment/rescorediagonal.cpp:45-379) with
+//   DistanceCalculator::computeUngappedAlignment / ungappedAlignmentByDiagonal /
+//   computeGlobalSubstitutionStartEndDistance   (alignment/DistanceCalculator.h:94-113,115-175,204-220)
+//   EvalueComputation::computeEvalue/computeBitScore (alignment/EvalueComputation.h:18-40) + ALP area
+//   (lib/alp/sls_pvalues.cpp:366-525, sls_basic.hpp:195-198)
+// One warp scores one prefilter line: the substitution table (21x21 or 5x5 int8) and the ASCII->code
+// table are staged in shared memory, lanes stride over the diagonal, warp shuffles reduce.
+// Compiled with -fmad=false so the double-precision E-value follows the CPU's operation order.
+#include "pg_internal.cuh"
+#include "pg_scan.cuh"
+#include "pg_tables.h"
+
+namespace pg {
+
+struct RsConst {
+    int nt;
+    int alph;                 // 21 or 5
+    float seqIdThr;
+    double evalThr;
+    int covMode;
+    float covThr;
+    int alnLenThr;
+    int seqIdMode;
+    double dbRes;             // getAminoAcidDBSize of the target DB
+    // ALP (Gumbel + finite size correction) parameters
+    double lambda, K, a_I, b_I, a_J, b_J, alpha_I, beta_I, alpha_J, beta_J, sigma, tau, vi_thr, vj_thr, c_thr, logK;
+};
+
+__constant__ unsigned char c_rs_a2n[256];
+__constant__ signed char c_rs_mat[21 * 21];
+__constant__ unsigned char c_rs_rev[256];     // nt: letter -> reverse-complement letter (num2aa[reverse[aa2num]])
+
+__device__ __forceinline__ double normal_probability(double x) { return 0.5 * erfc(-sqrt(0.5) * x); }
+
+// pvalues::get_appr_tail_prob_with_cov_without_errors, area only (sls_pvalues.cpp:366-525);
+// AlignmentEvaluer::area(score, seqlen1 = query, seqlen2 = db) passes (m_, n_) = (seqlen2, seqlen1).
+__device__ double alp_area(const RsConst &p, double y, double seqlen1, double seqlen2) {
+    const double const_val = 1.0 / sqrt(2.0 * 3.1415926535897932384626433832795);
+    const double m_ = seqlen2, n_ = seqlen1;
+    const double m_li_y = m_ - (p.a_I * y + p.b_I);
+    const double vi_y = fmax(p.vi_thr, p.alpha_I * y + p.beta_I);
+    const double sqrt_vi_y = sqrt(vi_y);
+    const double m_F = (sqrt_vi_y == 0.0) ? 1e100 : m_li_y / sqrt_vi_y;
+    const double P_m_F = normal_probability(m_F);
+    const double E_m_F = -const_val * exp(-0.5 * m_F * m_F);
+    const double p1 = m_li_y * P_m_F - sqrt_vi_y * E_m_F;
+    const double n_lj_y = n_ - (p.a_J * y + p.b_J);
+    const double vj_y = fmax(p.vj_thr, p.alpha_J * y + p.beta_J);
+    const double sqrt_vj_y = sqrt(vj_y);
+    const double n_F = (sqrt_vj_y == 0.0) ? 1e100 : n_lj_y / sqrt_vj_y;
+    const double P_n_F = normal_probability(n_F);
+    const double E_n_F = -const_val * exp(-0.5 * n_F * n_F);
+    const double p2 = n_lj_y * P_n_F - sqrt_vj_y * E_n_F;
+    const double c_y = fmax(p.c_thr, p.sigma * y + p.tau);
+    return p1 * p2 + c_y * (P_m_F * P_n_F);
+}
+
+// SmithWaterman::computeCov (StripedSmithWaterman.cpp:1055-1057), unsigned arithmetic
+__device__ __forceinline__ float compute_cov(unsigned s, unsigned e, unsigned len) {
+    return (float) (min(len, max(s, e)) - min(s, e) + 1u) / (float) len;
+}
+
+__device__ __forceinline__ bool has_coverage(float covThr, int covMode, float qc, float tc) {   // Util.cpp:553-567
+    switch (covMode) {
+        case 0: return qc >= covThr && tc >= covThr;
+        case 1: return qc >= covThr;
+        case 2: return tc >= covThr;
+        default: return true;
+    }
+}
+__device__ __forceinline__ bool rs_can_be_covered(float covThr, int covMode, float q, float t) {   // Util.cpp:533-551
+    switch (covMode) {
+        case 0: return (q / t >= covThr) && (t / q >= covThr);
+        case 1: return (t / q) >= covThr;
+        case 2: return (q / t) >= covThr;
+        case 3: return (t / q) >= covThr && (t / q) <= 1.0f;
+        case 4: return (q / t) >= covThr && (q / t) <= 1.0f;
+        case 5: return (fminf(t, q) / fmaxf(t, q)) >= covThr;
+        default: return true;
+    }
+}
+
+struct QView {             // the query as it is aligned: forward, or the full reverse complement
+    const char *s;
+    int len;
+    bool rev;
+    __device__ __forceinline__ unsigned char at(int i, const unsigned char *sRev) const {
+        return rev ? sRev[(unsigned char) s[len - 1 - i]] : (unsigned char) s[i];
+    }
+};
+
+struct DiagAln { int start, end; unsigned score, diagLen, dist; int diagonal; };
+
+// ungappedAlignmentByDiagonal + computeGlobalSubstitutionStartEndDistance for one candidate diagonal;
+// executed by a full warp, result valid in all lanes.
+__device__ DiagAln align_by_diagonal(const QView &q, const char *t, unsigned tLen, int diagonal, int alph,
+                                     const unsigned char *sA2n, const signed char *sMat, const unsigned char *sRev) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned qLen = (unsigned) q.len;
+    const unsigned dist = (unsigned) abs(diagonal);
+    DiagAln r; r.start = -1; r.end = -1; r.score = 0; r.diagLen = 0; r.dist = dist; r.diagonal = diagonal;
+    unsigned qOff, tOff, len;
+    if (diagonal >= 0 && dist < qLen) { len = min(tLen, qLen - dist); qOff = dist; tOff = 0; }
+    else if (diagonal < 0 && dist < tLen) { len = min(tLen - dist, qLen); qOff = 0; tOff = dist; }
+    else return r;
+    r.diagLen = len;
+    const unsigned char q0 = q.at(qOff, sRev), t0 = (unsigned char) t[tOff];
+    const unsigned char qE = q.at(qOff + len - 1, sRev), tE = (unsigned char) t[tOff + len - 1];
+    const unsigned first = (q0 == '*' || t0 == '*') ? 1u : 0u;
+    unsigned last = len - 1;
+    if (last > 0 && (qE == '*' || tE == '*')) last--;
+    long long sum = 0;
+    for (unsigned pos = first + lane; pos <= last && last != 0xFFFFFFFFu; pos += 32) {
+        const unsigned a = sA2n[q.at(qOff + pos, sRev)], b = sA2n[(unsigned char) t[tOff + pos]];
+        sum += sMat[a * alph + b];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if (sum < 0) sum = 0;
+    r.start = (int) first; r.end = (int) last; r.score = (unsigned) sum;
+    return r;
+}
+
+// items [0, nHits): prefilter hit j;  items [nHits, nHits + n): the "key\t0\t0" self line of query (item - nHits)
+__global__ void __launch_bounds__(256) rescore_kernel(const pg_seqdb db, const pg_hit *__restrict__ hits, unsigned long long nHits,
+                                                      const RsConst c, pg_aln *__restrict__ res, unsigned char *__restrict__ acc) {
+    __shared__ unsigned char sA2n[256];
+    __shared__ unsigned char sRev[256];
+    __shared__ signed char sMat[21 * 21];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { sA2n[i] = c_rs_a2n[i]; sRev[i] = c_rs_rev[i]; }
+    for (int i = threadIdx.x; i < 21 * 21; i += blockDim.x) sMat[i] = c_rs_mat[i];
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long nItems = nHits + db.n;
+    const unsigned long long warpsTotal = (unsigned long long) gridDim.x * (blockDim.x >> 5);
+    for (unsigned long long item = (unsigned long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < nItems; item += warpsTotal) {
+        unsigned qKey, tKey, qi, ti; int prefScore; unsigned short diag16;
+        if (item < nHits) {
+            const pg_hit h = hits[item];
+            qKey = h.rep; tKey = h.target; prefScore = h.score; diag16 = (unsigned short) (short) h.diag;
+            qi = find_id(db.keys, (unsigned) db.n, qKey);
+            ti = find_id(db.keys, (unsigned) db.n, tKey);
+        } else {
+            qi = ti = (unsigned) (item - nHits);
+            qKey = tKey = db.keys[qi]; prefScore = 0; diag16 = 0;
+        }
+        const bool isIdentity = (qi == ti);                 // same DB on both sides (rescorediagonal.cpp:205)
+        QView q; q.s = db.data + db.offsets[qi]; q.len = (int) db.lens[qi] - 2; q.rev = (c.nt && prefScore < 0);
+        const char *t = db.data + db.offsets[ti];
+        const int dbLen = (int) db.lens[ti] - 2;
+        const int qLen = q.len;
+        bool accepted = false;
+        pg_aln out;
+        out.query = qKey; out.target = tKey;
+        if (rs_can_be_covered(c.covThr, c.covMode, (float) qLen, (float) dbLen)) {
+            // computeUngappedAlignment: try every diagonal congruent to diag16 modulo 65536
+            DiagAln best; best.start = -1; best.end = -1; best.score = 0; best.diagLen = 0; best.dist = 0; best.diagonal = 0;
+            const unsigned tl = (unsigned) dbLen;
+            for (unsigned d = 1; d <= 1 + tl / 32768; d++) {
+                const int real = (int) (0u - d * 65536u + (unsigned) diag16);
+                const DiagAln tmp = align_by_diagonal(q, t, tl, real, c.alph, sA2n, sMat, sRev);
+                if (tmp.score > best.score) best = tmp;
+            }
+            for (unsigned d = 0; d <= (unsigned) qLen / 65536; d++) {
+                const int real = (int) (d * 65536u + (unsigned) diag16);
+                const DiagAln tmp = align_by_diagonal(q, t, tl, real, c.alph, sA2n, sMat, sRev);
+                if (tmp.score > best.score) best = tmp;
+            }
+            const int distance = (int) best.score;
+            const double epa = c.K * exp(-c.lambda * (double) distance);
+            const double evalue = epa * alp_area(c, (double) distance, (double) qLen, c.dbRes);
+            const int bitScore = (int) (((c.lambda * (double) distance - c.logK) / log(2.0)) + 0.5);
+            const int alnLen = (best.end - best.start) + 1;
+            int qS, qE, dS, dE;
+            if (best.diagonal >= 0) { qS = best.start + (int) best.dist; qE = best.end + (int) best.dist; dS = best.start; dE = best.end; }
+            else { qS = best.start; qE = best.end; dS = best.start + (int) best.dist; dE = best.end + (int) best.dist; }
+            float seqIdF = 0.0f;
+            if (evalue <= c.evalThr || isIdentity) {
+                int idCnt = 0;
+                if (qS < 0) {
+                    idCnt = (lane == 0) ? 1 : 0;   // zero-score identity hit: the reference compares the byte before both sequences
+                } else {
+                    for (int i = qS + (int) lane; i <= qE; i += 32) {
+                        const unsigned char ql = q.at(i, sRev) & (unsigned char) ~0x20;
+                        const unsigned char tl2 = (unsigned char) t[dS + (i - qS)] & (unsigned char) ~0x20;
+                        idCnt += (ql == tl2) ? 1 : 0;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) idCnt += __shfl_xor_sync(0xFFFFFFFFu, idCnt, o);
+                if (c.seqIdMode == 1) seqIdF = __fdiv_rn((float) idCnt, (float) min(qLen, dbLen));
+                else if (c.seqIdMode == 2) seqIdF = __fdiv_rn((float) idCnt, (float) max(qLen, dbLen));
+                else seqIdF = __fdiv_rn((float) idCnt, (float) alnLen);
+            }
+            const double seqId = (double) seqIdF;
+            const float queryCov = compute_cov((unsigned) qS, (unsigned) qE, (unsigned) qLen);
+            const float targetCov = compute_cov((unsigned) dS, (unsigned) dE, (unsigned) dbLen);
+            if (q.rev) { qS = qLen - qS - 1; qE = qLen - qE - 1; }
+            const bool hasCov = has_coverage(c.covThr, c.covMode, queryCov, targetCov);
+            const bool hasSeqId = seqId >= (double) (c.seqIdThr - 1.1920928955078125e-07f);   // FLT_EPSILON, float subtraction
+            const bool hasEvalue = evalue <= c.evalThr;
+            const bool hasAlnLen = alnLen >= c.alnLenThr;
+            accepted = isIdentity || (hasAlnLen && hasCov && hasSeqId && hasEvalue);
+            out.bits = bitScore; out.seq_id = seqIdF; out.evalue = evalue;
+            out.q_start = qS; out.q_end = qE; out.q_len = qLen; out.db_start = dS; out.db_end = dE; out.db_len = dbLen;
+        }
+        if (lane == 0) {
+            if (accepted) res[item] = out;
+            acc[item] = accepted ? 1 : 0;
+        }
+    }
+}
+
+// number of alignment lines of every query: 1 (self) + accepted hits of its block
+__global__ void count_per_query_kernel(const pg_seqdb db, const pg_hit *__restrict__ hits, unsigned long long nHits,
+                                       const unsigned char *__restrict__ acc, unsigned *__restrict__ cnt) {
+    const unsigned long long j = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nHits) return;
+    const unsigned rep = hits[j].rep;
+    if (j > 0 && hits[j - 1].rep == rep) return;
+    unsigned c = 1;
+    for (unsigned long long k = j; k < nHits && hits[k].rep == rep; k++) c += acc[k];
+    cnt[find_id(db.keys, (unsigned) db.n, rep)] = c;
+}
+
+__global__ void fill_u32_kernel(unsigned *p, unsigned long long n, unsigned v) {
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) p[i] = v;
+}
+
+__global__ void gather_self_kernel(const pg_aln *__restrict__ res, unsigned long long nHits, unsigned long long n,
+                                   const unsigned long long *__restrict__ off, pg_aln *__restrict__ out) {
+    const unsigned long long qi = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi < n) out[off[qi]] = res[nHits + qi];
+}
+
+__global__ void gather_hits_kernel(const pg_seqdb db, const pg_hit *__restrict__ hits, unsigned long long nHits,
+                                   const unsigned char *__restrict__ acc, const pg_aln *__restrict__ res,
+                                   const unsigned long long *__restrict__ off, pg_aln *__restrict__ out) {
+    const unsigned long long j = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nHits) return;
+    const unsigned rep = hits[j].rep;
+    if (j > 0 && hits[j - 1].rep == rep) return;
+    unsigned long long w = off[find_id(db.keys, (unsigned) db.n, rep)] + 1;
+    for (unsigned long long k = j; k < nHits && hits[k].rep == rep; k++)
+        if (acc[k]) out[w++] = res[k];
+}
+
+int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHits, const pg_rs_params *p, pg_aln **d_alns, uint64_t *nAlns) {
+    cudaStream_t s = ctx->stream;
+    PG_CHECK(p->rescore_mode == 3, "rescorediagonal: only --rescore-mode 3 (END_TO_END) is implemented on the GPU path");
+    const bool nt = db->dbtype == PG_DBTYPE_NUCLEOTIDES;
+    RsConst c;
+    c.nt = nt; c.alph = nt ? 5 : 21;
+    c.seqIdThr = p->seq_id_thr; c.evalThr = p->eval_thr; c.covMode = p->cov_mode; c.covThr = p->cov_thr;
+    c.alnLenThr = p->aln_len_thr; c.seqIdMode = p->seq_id_mode; c.dbRes = db->residues;
+    const double *a = nt ? PG_NT_ALP : PG_AA_ALP;
+    c.lambda = a[0]; c.K = a[1]; c.a_I = a[2]; c.b_I = a[3]; c.a_J = a[4]; c.b_J = a[5];
+    c.alpha_I = a[6]; c.beta_I = a[7]; c.alpha_J = a[8]; c.beta_J = a[9]; c.sigma = a[10]; c.tau = a[11];
+    // pvalues::compute_tmp_values (sls_pvalues.cpp:342-364)
+    c.vi_thr = std::max(2.0 * c.alpha_I / c.lambda, 0.0);
+    c.vj_thr = std::max(2.0 * c.alpha_J / c.lambda, 0.0);
+    c.c_thr = std::max(2.0 * c.sigma / c.lambda, 0.0);
+    c.logK = log(c.K);
+    unsigned char rev[256];
+    for (int i = 0; i < 256; i++) rev[i] = PG_NT_NUM2AA[PG_NT_REVERSE[PG_NT_AA2NUM[i]]];
+    signed char mat[21 * 21] = {0};
+    if (nt) { for (int i = 0; i < 25; i++) mat[i] = PG_NT_SUBMAT[i]; } else { for (int i = 0; i < 441; i++) mat[i] = PG_AA_SUBMAT[i]; }
+    PG_CUDA(cudaMemcpyToSymbolAsync(c_rs_a2n, nt ? PG_NT_AA2NUM : PG_AA_AA2NUM, 256, 0, cudaMemcpyHostToDevice, s));
+    PG_CUDA(cudaMemcpyToSymbolAsync(c_rs_rev, rev, 256, 0, cudaMemcpyHostToDevice, s));
+    PG_CUDA(cudaMemcpyToSymbolAsync(c_rs_mat, mat, sizeof(mat), 0, cudaMemcpyHostToDevice, s));
+    PG_CUDA(cudaStreamSynchronize(s));   // host staging arrays above are stack memory
+
+    cudaEventRecord(ctx->ev[EV_RS_BEGIN], s);
+    const uint64_t n = db->n, nItems = nHits + n;
+    PG_TRY(ctx->alnAll.reserve(sizeof(pg_aln) * (nItems + 1)));
+    PG_TRY(ctx->flags.reserve(nItems + 16 + sizeof(unsigned) * (n + 1) + sizeof(unsigned long long) * (n + 2) + scan_workspace_bytes(n) + 64));
+    pg_aln *res = ctx->alnAll.as<pg_aln>();
+    unsigned char *acc = ctx->flags.as<unsigned char>();
+    size_t o = (nItems + 15) & ~(size_t) 15;
+    unsigned *cnt = (unsigned *) (acc + o); o += (sizeof(unsigned) * (n + 1) + 15) & ~(size_t) 15;
+    unsigned long long *off = (unsigned long long *) (acc + o); o += sizeof(unsigned long long) * (n + 2);
+    void *scanWs = acc + o;
+    unsigned long long *d_total = ctx->small.as<unsigned long long>() + 4;
+
+    unsigned long long warps = nItems;
+    unsigned blocks = (unsigned) std::min<unsigned long long>((warps + 7) / 8, (unsigned long long) NUM_SMS * 64);
+    if (blocks == 0) blocks = 1;
+    rescore_kernel<<<blocks, 256, 0, s>>>(*db, d_hits, nHits, c, res, acc);
+    fill_u32_kernel<<<NUM_SMS * 4, 256, 0, s>>>(cnt, n, 1u);
+    if (nHits) count_per_query_kernel<<<(unsigned) ((nHits + 255) / 256), 256, 0, s>>>(*db, d_hits, nHits, acc, cnt);
+    ctx->launches += 3;
+    PG_TRY(exclusive_scan_u32(cnt, off, n, d_total, scanWs, scan_workspace_bytes(n), s, &ctx->launches));
+    unsigned long long h = 0;
+    PG_CUDA(cudaMemcpyAsync(&h, d_total, sizeof(h), cudaMemcpyDeviceToHost, s));
+    PG_CUDA(cudaStreamSynchronize(s));
+    PG_TRY(ctx->alns.reserve(sizeof(pg_aln) * (h + 1)));
+    pg_aln *out = ctx->alns.as<pg_aln>();
+    if (n) gather_self_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(res, nHits, n, off, out);
+    if (nHits) gather_hits_kernel<<<(unsigned) ((nHits + 255) / 256), 256, 0, s>>>(*db, d_hits, nHits, acc, res, off, out);
+    ctx->launches += 2;
+    cudaEventRecord(ctx->ev[EV_RS_END], s);
+    PG_CUDA(cudaGetLastError());
+    *d_alns = out; *nAlns = h;
+    ctx->timings.n_alns = h;
+    ctx->rsRan = true;
+    return 0;
+}
+
+}  // namespace pg

@@ -1,0 +1,148 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (libplassgpu.so), against the CPU
+oracle on the same inputs and against the committed golden fixtures of the reference binary.
+Bar: bit-exact for every integer field; seq.id exact as float; E-value within 1e-6 relative
+(BASELINE.json north_star), and the printed 10-column alignment text must match where the E-value
+prints identically."""
+import os
+import numpy as np
+import pytest
+
+from common import golden_case
+from plass_b200 import mmseqsdb, api
+import oracle_binding as ob
+import params
+from test_oracle_vs_reference import hits_from_pref, alns_from_db, assert_same_entries
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["example_aa", "synth_aa", "synth_nt"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def gpu_km(args, nucl):
+    return api.KmParams(hash_start=0, hash_end=65535, **params.km_fields(args, nucl))
+
+
+def test_radix_sort_matches_numpy(ctx):
+    rng = np.random.default_rng(5)
+    for n in (1, 31, 4096, 4097, 100003, 1 << 20):
+        recs = rng.integers(0, 1 << 63, size=(n, 2), dtype=np.uint64)
+        recs[:, 0] &= np.uint64((1 << 40) - 1)
+        recs[: n // 2, 0] &= np.uint64(0xFF)          # heavy duplicates exercise stability
+        got = ctx.debug_radix_sort(recs.copy(), [(0, 0, 40)])
+        order = np.argsort(recs[:, 0], kind="stable")
+        assert np.array_equal(got, recs[order]), n
+    # two-word key: (w0 bits 0..20 major, w1 bits 0..16 minor)
+    recs = rng.integers(0, 1 << 63, size=(300000, 2), dtype=np.uint64)
+    got = ctx.debug_radix_sort(recs.copy(), [(1, 0, 16), (0, 0, 20)])
+    key = ((recs[:, 0] & np.uint64((1 << 20) - 1)) << np.uint64(16)) | (recs[:, 1] & np.uint64(0xFFFF))
+    assert np.array_equal(got, recs[np.argsort(key, kind="stable")])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_extract_matches_oracle(case, golden_root, ctx):
+    d, man = golden_case(case, golden_root)
+    for s in [s for s in man["steps"] if s["cmd"] == "kmermatcher"]:
+        seq = mmseqsdb.read_db(os.path.join(d, s["dbs"][0]))
+        nucl = seq.dbtype == 1
+        want = ob.extract_kmers(seq, params.oracle_km(s["args"], nucl))
+        ddb = ctx.upload(seq)
+        got = ctx.debug_extract(ddb, gpu_km(s["args"], nucl))
+        ddb.free()
+        w = np.zeros(len(want), dtype=got.dtype)
+        w["w0"] = want["kmer"]
+        w["w1"] = (want["id"].astype(np.uint64) << np.uint64(32)) | ((want["seq_len"].astype(np.uint64) & np.uint64(0xFFFF)) << np.uint64(16)) | (want["pos"].astype(np.uint64) & np.uint64(0xFFFF))
+        assert len(got) == len(w), (case, s["dbs"][0])
+        assert np.array_equal(np.sort(got, order=["w0", "w1"]), np.sort(w, order=["w0", "w1"])), (case, s["dbs"][0])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_kmermatcher_matches_oracle_and_golden(case, golden_root, ctx):
+    d, man = golden_case(case, golden_root)
+    for s in [s for s in man["steps"] if s["cmd"] == "kmermatcher"]:
+        seq = mmseqsdb.read_db(os.path.join(d, s["dbs"][0]))
+        nucl = seq.dbtype == 1
+        ddb = ctx.upload(seq)
+        got = ctx.kmermatcher(ddb, gpu_km(s["args"], nucl))
+        ddb.free()
+        want = ob.kmermatch(seq, params.oracle_km(s["args"], nucl))
+        assert len(got) == len(want), (case, s["dbs"][1], len(got), len(want))
+        for f in ("rep", "target", "score", "diag"):
+            assert np.array_equal(got[f], want[f]), (case, s["dbs"][1], f)
+        golden = mmseqsdb.read_db(os.path.join(d, s["dbs"][1]))
+        assert_same_entries(ob.format_hits_by_rep(seq.keys, got), golden.entries_by_key(), "%s/%s" % (case, s["dbs"][1]))
+
+
+def check_alns(got, want, what):
+    assert len(got) == len(want), (what, len(got), len(want))
+    for f in ("query", "target", "bits", "q_start", "q_end", "q_len", "db_start", "db_end", "db_len"):
+        assert np.array_equal(got[f], want[f]), (what, f)
+    assert np.array_equal(got["seq_id"], want["seq_id"]), (what, "seq_id")          # float32, exact
+    rel = np.abs(got["evalue"] - want["evalue"]) / np.maximum(np.abs(want["evalue"]), 1e-300)
+    assert rel.max() <= 1e-6, (what, "evalue", rel.max())                             # north_star tolerance
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_rescorediagonal_matches_oracle_and_golden(case, golden_root, ctx):
+    d, man = golden_case(case, golden_root)
+    for s in [s for s in man["steps"] if s["cmd"] == "rescorediagonal"]:
+        seq = mmseqsdb.read_db(os.path.join(d, s["dbs"][0]))
+        hits = hits_from_pref(mmseqsdb.read_db(os.path.join(d, s["dbs"][2])))
+        ddb = ctx.upload(seq)
+        got = ctx.rescorediagonal(ddb, hits, api.RsParams(**params.rs_fields(s["args"])))
+        ddb.free()
+        want = ob.rescore(seq, hits, params.oracle_rs(s["args"]))
+        check_alns(got, want, "%s/%s" % (case, s["dbs"][3]))
+        golden = mmseqsdb.read_db(os.path.join(d, s["dbs"][3])).entries_by_key()
+        text = ob.format_alns_by_query(seq.keys, got.astype(ob.ALN))
+        bad = [k for k in golden if text[k] != golden[k]]
+        # the text can only differ where a last-ulp E-value difference flips the 4th significant digit
+        assert len(bad) <= max(1, len(golden) // 10000), (case, s["dbs"][3], len(bad), text[bad[0]], golden[bad[0]])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_assembleresults_matches_oracle_and_golden(case, golden_root, ctx):
+    d, man = golden_case(case, golden_root)
+    for s in [s for s in man["steps"] if s["cmd"] in ("assembleresults", "nuclassembleresults")]:
+        seq = mmseqsdb.read_db(os.path.join(d, s["dbs"][0]))
+        alns = alns_from_db(mmseqsdb.read_db(os.path.join(d, s["dbs"][1])))
+        ddb = ctx.upload(seq)
+        out, ext = ctx.assembleresults(ddb, alns, api.ExParams(**params.ex_fields(s["args"])))
+        got = out.download()
+        out.free(); ddb.free()
+        want, wext = ob.extend(seq, alns, params.oracle_ex(s["args"]))
+        assert np.array_equal(ext, wext), (case, s["dbs"][2])
+        assert_same_entries(got.entries_by_key(), want.entries_by_key(), "%s/%s vs oracle" % (case, s["dbs"][2]))
+        golden = mmseqsdb.read_db(os.path.join(d, s["dbs"][2]))
+        assert_same_entries(got.entries_by_key(), golden.entries_by_key(), "%s/%s vs reference" % (case, s["dbs"][2]))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fused_iteration_matches_golden_chain(case, golden_root, ctx):
+    """kmermatcher -> rescorediagonal -> assembleresults without leaving HBM == the reference's three DBs."""
+    d, man = golden_case(case, golden_root)
+    steps = man["steps"]
+    for i, s in enumerate(steps):
+        if s["cmd"] not in ("assembleresults", "nuclassembleresults"):
+            continue
+        km = [x for x in steps[:i] if x["cmd"] == "kmermatcher" and x["dbs"][0] == s["dbs"][0]][-1]
+        rs = [x for x in steps[:i] if x["cmd"] == "rescorediagonal" and x["dbs"][3] == s["dbs"][1]][-1]
+        seq = mmseqsdb.read_db(os.path.join(d, s["dbs"][0]))
+        nucl = seq.dbtype == 1
+        ddb = ctx.upload(seq)
+        out, hits, alns = ctx.assemble_iteration(ddb, gpu_km(km["args"], nucl), api.RsParams(**params.rs_fields(rs["args"])),
+                                                 api.ExParams(**params.ex_fields(s["args"])), want_intermediates=True)
+        got = out.download()
+        out.free(); ddb.free()
+        pref = mmseqsdb.read_db(os.path.join(d, km["dbs"][1]))
+        assert_same_entries(ob.format_hits_by_rep(seq.keys, hits), pref.entries_by_key(), "%s/%s fused" % (case, km["dbs"][1]))
+        golden = mmseqsdb.read_db(os.path.join(d, s["dbs"][2]))
+        assert_same_entries(got.entries_by_key(), golden.entries_by_key(), "%s/%s fused" % (case, s["dbs"][2]))
+        t = ctx.timings()
+        assert t["kernel_launches"] > 0 and t["n_hits"] == len(hits)
