@@ -1,0 +1,347 @@
+#!/usr/bin/env python3
+"""bench.py -- reads/s through one full assemble iteration (kmermatcher + rescorediagonal + assembleresults).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--reads R]
+
+Workload (BASELINE.json configs[1]): R = 5 M synthetic 150 bp protein-coding reads (seed 1, 20x coverage,
+0.5 % substitutions, 50 % reverse-complemented) -> six-frame amino-acid fragments; one `plass assemble`
+iteration with the workflow defaults (k = 14, 13-letter alphabet, --min-seq-id 0.9, -e 1e-5).
+A "step" is one pass of the hot path over that fragment DB.
+
+  value      whole-job reads/s with the fragment DB already resident in HBM (device-resident fused iteration)
+  e2e        the same iteration through the C ABI with HOST buffers: pinned H2D of the DB, D2H of the
+             prefilter hits, the alignments and the new sequence DB inside the timed region
+  roofline   dominant kernel = the radix scatter passes of sort #1; achieved = algorithmic bytes of the sort
+             (one read + one write of every 16-byte record) / summed scatter time
+  cpu_baseline  the UNMODIFIED reference binary (oracle/_ref/bin/plass: kmermatcher, rescorediagonal,
+             assembleresults sub-commands, all host threads) on a bounded sample of the same fragments
+
+--impl reference times only that reference arm (CPU) and prints it as the line's value.
+N > 1 (torchrun): weak scaling -- R reads per GPU; the k-mer hash space is sharded over the ranks and the
+candidate pairs are exchanged with one NCCL all-to-all (torch.distributed), see DESIGN.md §5.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from plass_b200 import api, mmseqsdb, synth  # noqa: E402
+
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin", "plass")
+KM_FLAGS = "--sub-mat nucl:nucleotide.out,aa:blosum62.out --alph-size 13 --min-seq-id 0.9 --kmer-per-seq 60 " \
+           "--spaced-kmer-mode 0 --kmer-per-seq-scale nucl:0.200,aa:0.000 --adjust-kmer-len 0 --mask 0 --mask-lower-case 0 " \
+           "--cov-mode 0 -k 14 -c 0 --max-seq-len 65535 --hash-shift 67 --split-memory-limit 0 --include-only-extendable 0 " \
+           "--ignore-multi-kmer 1 --compressed 0 -v 3"
+RS_FLAGS = "--sub-mat nucl:nucleotide.out,aa:blosum62.out --rescore-mode 3 --wrapped-scoring 0 --filter-hits 0 -e 1e-05 -c 0 -a 0 " \
+           "--cov-mode 0 --min-seq-id 0.9 --min-aln-len 0 --seq-id-mode 0 --add-self-matches 0 --sort-results 0 --db-load-mode 0 " \
+           "--compressed 0 -v 3"
+EX_FLAGS = "--min-seq-id 0.9 --max-seq-len 65535 --keep-target 1 -v 3 --rescore-mode 3"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_fragments(n_reads, seed):
+    cache = os.path.join(tempfile.gettempdir(), "plass_b200_frag_%d_%d.npz" % (n_reads, seed))
+    if os.path.exists(cache):
+        z = np.load(cache)
+        return mmseqsdb.DB(z["data"], z["keys"], z["offsets"], z["lens"], 0)
+    t = time.time()
+    reads = synth.make_reads_fast(n_reads, seed=seed)
+    db = synth.protein_fragments(reads)
+    log("[bench] generated %d reads -> %d aa fragments (mean %.1f aa) in %.1f s" % (n_reads, db.n, float(db.lens.mean()) - 2, time.time() - t))
+    try:
+        np.savez(cache, data=db.data, keys=db.keys, offsets=db.offsets, lens=db.lens)
+    except OSError:
+        pass
+    return db
+
+
+def subsample(db, n_frag):
+    """First n_frag fragments as their own DB (keys renumbered 0..n-1)."""
+    n = min(n_frag, db.n)
+    end = int(db.offsets[n - 1]) + int(db.lens[n - 1])
+    return mmseqsdb.DB(db.data[:end], np.arange(n, dtype=np.uint32), db.offsets[:n].copy(), db.lens[:n].copy(), db.dbtype)
+
+
+def write_db_fast(path, db):
+    db.data.tofile(path)
+    with open(path + ".index", "w") as f:
+        f.write("".join("%d\t%d\t%d\n" % (int(k), int(o), int(l)) for k, o, l in zip(db.keys, db.offsets, db.lens)))
+    np.array([db.dbtype], dtype="<i4").tofile(path + ".dbtype")
+
+
+def run_reference_iteration(db, threads, workdir):
+    """kmermatcher + rescorediagonal + assembleresults of the unmodified reference on `db`; returns seconds."""
+    if os.path.exists(workdir):
+        shutil.rmtree(workdir)
+    os.makedirs(workdir)
+    seq = os.path.join(workdir, "seq")
+    write_db_fast(seq, db)
+    env = dict(os.environ, MMSEQS_NUM_THREADS=str(threads))
+    cmds = [
+        [REF_BIN, "kmermatcher", seq, os.path.join(workdir, "pref")] + KM_FLAGS.split() + ["--threads", str(threads)],
+        [REF_BIN, "rescorediagonal", seq, seq, os.path.join(workdir, "pref"), os.path.join(workdir, "aln")] + RS_FLAGS.split() + ["--threads", str(threads)],
+        [REF_BIN, "assembleresults", seq, os.path.join(workdir, "aln"), os.path.join(workdir, "asm")] + EX_FLAGS.split() + ["--threads", str(threads)],
+    ]
+    total = 0.0
+    per = []
+    for c in cmds:
+        t = time.time()
+        r = subprocess.run(c, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env)
+        dt = time.time() - t
+        if r.returncode != 0:
+            raise RuntimeError("reference step failed: %s\n%s" % (" ".join(c[:2]), r.stdout.decode()[-2000:]))
+        per.append(dt)
+        total += dt
+    return total, per
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_arm(args, db_full, n_reads_total):
+    """--impl reference: the reference's own CPU path, bounded sample, all host threads."""
+    threads = os.cpu_count() or 1
+    # same generator, same 20x coverage, fewer reads (a prefix of the big DB would have lower coverage and
+    # therefore fewer overlaps per read, which would flatter the CPU)
+    sample_reads = min(args.cpu_sample_reads, n_reads_total)
+    sample = make_fragments(sample_reads, args.seed)
+    work = os.path.join(tempfile.gettempdir(), "plass_b200_ref_%d" % os.getpid())
+    times = []
+    try:
+        for i in range(args.warmup + args.steps):
+            t, per = run_reference_iteration(sample, threads, work)
+            log("[bench/reference] step %d: %.2f s (kmermatcher %.2f, rescorediagonal %.2f, assembleresults %.2f)" % (i, t, per[0], per[1], per[2]))
+            if i >= args.warmup:
+                times.append(t)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+    sec = float(np.mean(times))
+    val = sample_reads / sec
+    sample_desc = "%d reads (%d fragments) from the same generator at the same 20x coverage instead of %d reads; %d threads; tmp dir %s" % (
+        sample_reads, sample.n, n_reads_total, threads, tempfile.gettempdir())
+    return {
+        "metric": "reads/sec per assemble iteration (kmermatcher+rescorediagonal+assembleresults)", "value": val, "unit": "reads/s",
+        "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1000.0,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (+f64 E-values)", "data": "synthetic",
+        "config": {"workload": "5M synthetic 150bp coding reads -> aa fragments, k=14, alph 13, 1 iteration (BASELINE configs[1]); bounded sample",
+                   "reads": n_reads_total, "fragments": int(db_full.n)},
+        "cpu_baseline": {"value": val, "unit": "reads/s", "cores": threads, "kind": "reference", "sample": sample_desc},
+        "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=5000000, help="reads per GPU")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cpu-sample-reads", type=int, default=400000, help="reads in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        db = make_fragments(args.reads, args.seed)
+        print(json.dumps(reference_arm(args, db, args.reads)), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(local_rank)
+
+    # weak scaling: every rank contributes `reads` reads; the job's DB is the union (replicated in each HBM)
+    n_reads_total = args.reads * world
+    db = make_fragments(n_reads_total, args.seed)
+    ctx = api.Context(local_rank)
+    kp, rp, ep = api.default_km_params(False), api.default_rs_params(False), api.default_ex_params(False)
+
+    if world > 1:
+        from plass_b200 import sharded
+        runner = sharded.ShardedIteration(ctx, dist, rank, world)
+    else:
+        runner = None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident arm (value) -------------------------------------------------------------
+    ddb = ctx.upload(db)
+    peak, peak_src = load_peaks()
+    tim = []
+    for i in range(args.warmup):
+        out = runner.step(ddb, kp, rp, ep) if runner else ctx.assemble_iteration(ddb, kp, rp, ep)[0]
+        out.free()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        out = runner.step(ddb, kp, rp, ep) if runner else ctx.assemble_iteration(ddb, kp, rp, ep)[0]
+        tim.append(ctx.timings() if runner is None else runner.timings())
+        n_out = out.n
+        out.free()
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    ms_per_step = dt * 1000.0 / args.steps
+    value = n_reads_total / (dt / args.steps)
+
+    # ---- end-to-end arm: host buffers through the C ABI ---------------------------------------------
+    pinned = mmseqsdb.DB(torch.from_numpy(db.data).pin_memory().numpy(), torch.from_numpy(db.keys).pin_memory().numpy(),
+                         torch.from_numpy(db.offsets.view(np.int64)).pin_memory().numpy().view(np.uint64),
+                         torch.from_numpy(db.lens.view(np.int32)).pin_memory().numpy().view(np.uint32), db.dbtype)
+    h2d = int(pinned.data.nbytes + pinned.keys.nbytes + pinned.offsets.nbytes + pinned.lens.nbytes)
+    e2e_times, d2h = [], 0
+    e2e_steps = max(1, min(args.steps, 2))
+    for i in range(1 + e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
+        d_in = ctx.upload(pinned)
+        if runner:
+            out = runner.step(d_in, kp, rp, ep, download=True)
+            d2h = runner.last_d2h_bytes
+        else:
+            out, hits, alns = ctx.assemble_iteration(d_in, kp, rp, ep, want_intermediates=True)
+            host_out = out.download()
+            d2h = int(hits.nbytes + alns.nbytes + host_out.data.nbytes + host_out.offsets.nbytes + host_out.lens.nbytes + host_out.keys.nbytes)
+        out.free(); d_in.free()
+        barrier()
+        if i > 0:
+            e2e_times.append(time.perf_counter() - t0)
+    e2e_dt = float(np.mean(e2e_times))
+    if world > 1:
+        t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_value = n_reads_total / e2e_dt
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------
+    scatter_ms = float(np.mean([t["sort1_scatter_ms"] for t in tim]))
+    passes = int(tim[-1]["sort1_passes"])
+    nrec = int(tim[-1]["n_kmer_records"])
+    alg_bytes = nrec * 16 * 2                      # a sort = one read + one write of every record
+    achieved = alg_bytes / 1e9 / (scatter_ms / 1e3) if scatter_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "radix_scatter_kernel (sort #1, %d launches/step)" % passes,
+                "algorithmic_bytes_per_launch": alg_bytes / max(passes, 1), "launch_ms": scatter_ms / max(passes, 1), "peak_source": peak_src}
+    stage_ms = {k: float(np.mean([t[k] for t in tim])) for k in ("extract_ms", "sort1_ms", "group_ms", "sort2_ms", "reduce_ms", "rescore_ms", "extend_ms", "exchange_ms", "total_ms")}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN):
+        try:
+            threads = os.cpu_count() or 1
+            sample_reads = min(args.cpu_sample_reads, n_reads_total)
+            sample = make_fragments(sample_reads, args.seed)
+            work = os.path.join(tempfile.gettempdir(), "plass_b200_cpu_%d" % os.getpid())
+            t, per = run_reference_iteration(sample, threads, work)
+            shutil.rmtree(work, ignore_errors=True)
+            cpu = {"value": sample_reads / t, "unit": "reads/s", "cores": threads, "kind": "reference",
+                   "sample": "%d reads (%d fragments), same generator and 20x coverage, one iteration, %.1f s (kmermatcher %.1f, rescorediagonal %.1f, assembleresults %.1f)"
+                             % (sample_reads, sample.n, t, per[0], per[1], per[2])}
+        except Exception as e:  # noqa: BLE001
+            cpu = {"value": None, "unit": "reads/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % e}
+
+    if rank == 0:
+        line = {
+            "metric": "reads/sec per assemble iteration (kmermatcher+rescorediagonal+assembleresults)", "value": value, "unit": "reads/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (+f64 E-values)", "data": "synthetic",
+            "config": {"workload": "5M synthetic 150bp coding reads per GPU -> aa fragments, k=14, alph 13, --min-seq-id 0.9, 1 iteration (BASELINE configs[1])",
+                       "reads": n_reads_total, "fragments": int(db.n), "kmer_records": nrec, "pair_records": int(tim[-1]["n_pair_records"]),
+                       "hits": int(tim[-1]["n_hits"]), "alignments": int(tim[-1]["n_alns"]), "output_sequences": int(n_out),
+                       "l2": "inputs_larger_than_l2 (%.1f GB of k-mer records per step)" % (nrec * 16 / 1e9),
+                       "parallelism": "kmer-hash shards x%d, one all-to-all" % world if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_dt * 1000.0},
+            "gpu_launches": int(sum(t["kernel_launches"] for t in tim)),
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "stage_ms": stage_ms,
+        }
+        print(json.dumps(line), flush=True)
+    ddb.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -108,6 +108,8 @@ typedef struct {
     uint64_t n_extended;       /* sequences that became contigs */
     uint64_t kernel_launches;  /* kernels launched by the last call */
     uint64_t sort1_bytes;      /* algorithmic bytes of sort #1: one read + one write of every record */
+    float sort1_scatter_ms;    /* device time of the radix scatter launches of sort #1 (events around them) */
+    uint32_t sort1_passes;     /* number of scatter launches in sort #1 */
 } pg_timings;
 
 const char *pg_last_error(void);

@@ -46,7 +46,8 @@ class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("extract_ms", "sort1_ms", "group_ms", "sort2_ms", "reduce_ms", "rescore_ms",
                                          "extend_ms", "exchange_ms", "total_ms")] + \
                [(n, C.c_uint64) for n in ("n_kmer_records", "n_pair_records", "n_hits", "n_alns", "n_extended",
-                                          "kernel_launches", "sort1_bytes")]
+                                          "kernel_launches", "sort1_bytes")] + \
+               [("sort1_scatter_ms", C.c_float), ("sort1_passes", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

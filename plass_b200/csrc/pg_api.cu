@@ -67,6 +67,7 @@ static void collect_timings(Context *ctx) {
     if (ctx->kmRan) {
         t.extract_ms = el(EV_KM_BEGIN, EV_EXTRACT_END);
         t.sort1_ms = el(EV_SORT1_BEGIN, EV_SORT1_END);
+        t.sort1_scatter_ms = el(EV_SCATTER1_BEGIN, EV_SCATTER1_END);
         t.group_ms = el(EV_SORT1_END, EV_GROUP_END);
         t.sort2_ms = el(EV_GROUP_END, EV_SORT2_END);
         t.reduce_ms = el(EV_SORT2_END, EV_REDUCE_END);
@@ -129,7 +130,7 @@ void pg_destroy(pg_context *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->small, &ctx->lists, &ctx->recA, &ctx->recB, &ctx->radixWs, &ctx->scratch, &ctx->blockCounts, &ctx->hits,
-                      &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta};
+                      &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta, &ctx->ntTab};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);

@@ -13,9 +13,20 @@
 #include "pg_scan.cuh"
 #include "pg_tables.h"
 
+#include <cmath>
+#include <vector>
+
 namespace pg {
 
 struct ExConst {
+    // CompareNuclResultByScore evaluates lgamma()/log() only at small integers.  For perfect-identity
+    // overlaps its p equals beta1/(beta1+beta2) exactly, so the 0.45 / 0.55 cut-offs are hit as exact
+    // rational ties (e.g. overlap lengths 98 vs 120) and the reference's answer then hangs on the last
+    // ulps of the HOST libm.  The host therefore tabulates lgamma(n) and log(n) with its own libm (the
+    // one the reference binary would call on this machine) and the kernel reads those values.
+    const double *lgammaTab;
+    const double *logTab;
+    unsigned tabN;
     int nt;
     int alph;
     float seqIdThr;
@@ -58,17 +69,19 @@ __device__ __forceinline__ bool cmp_aa(const ExRes &r1, const ExRes &r2) {
     return false;
 }
 // CompareNuclResultByScore (nuclassembleresult.cpp:36-70)
-__device__ bool cmp_nt(const ExRes &r1, const ExRes &r2) {
+__device__ __forceinline__ double tab_lgamma(const ExConst &c, unsigned long long n) { return n < c.tabN ? __ldg(c.lgammaTab + n) : lgamma((double) n); }
+__device__ __forceinline__ double tab_log(const ExConst &c, unsigned long long n) { return n < c.tabN ? __ldg(c.logTab + n) : log((double) n); }
+__device__ bool cmp_nt(const ExRes &r1, const ExRes &r2, const ExConst &c) {
     const unsigned mm1 = (unsigned) ((double) ((1.0f - r1.seqId) * (float) r1.alnLength) + 0.5);
     const unsigned mm2 = (unsigned) ((double) ((1.0f - r2.seqId) * (float) r2.alnLength) + 0.5);
     const unsigned alpha1 = mm1 + 1, alpha2 = mm2 + 1;
     const unsigned beta1 = r1.alnLength - mm1 + 1, beta2 = r2.alnLength - mm2 + 1;
-    const double log_c = (lgamma((double) (beta1 + beta2)) + lgamma((double) (alpha1 + beta1))) -
-                         (lgamma((double) (alpha1 + beta1 + beta2)) + lgamma((double) beta1));
+    const double log_c = (tab_lgamma(c, beta1 + beta2) + tab_lgamma(c, alpha1 + beta1)) -
+                         (tab_lgamma(c, alpha1 + beta1 + beta2) + tab_lgamma(c, beta1));
     double log_r = 0.0, p = 0.0;
     for (unsigned long long idx = 0; idx < alpha2; idx++) {
         p += exp(log_r + log_c);
-        log_r = log((double) (alpha1 + idx)) + log((double) (beta2 + idx)) - (log((double) (idx + 1)) + log((double) (idx + alpha1 + beta1 + beta2))) + log_r;
+        log_r = tab_log(c, alpha1 + idx) + tab_log(c, beta2 + idx) - (tab_log(c, idx + 1) + tab_log(c, idx + alpha1 + beta1 + beta2)) + log_r;
     }
     if (p < 0.45) return true;
     if (p > 0.55) return false;
@@ -76,10 +89,10 @@ __device__ bool cmp_nt(const ExRes &r1, const ExRes &r2) {
     if (r1.dbLen - r1.alnLength > r2.dbLen - r2.alnLength) return false;
     return true;
 }
-__device__ __forceinline__ bool cmp_res(const ExRes &a, const ExRes &b, int nt) { return nt ? cmp_nt(a, b) : cmp_aa(a, b); }
+__device__ __forceinline__ bool cmp_res(const ExRes &a, const ExRes &b, const ExConst &c) { return c.nt ? cmp_nt(a, b, c) : cmp_aa(a, b); }
 
 // libstdc++ std::__push_heap / std::__adjust_heap (bits/stl_heap.h), which std::priority_queue uses.
-__device__ void heap_push_hole(ExRes *first, long hole, long top, const ExRes &value, int nt) {
+__device__ void heap_push_hole(ExRes *first, long hole, long top, const ExRes &value, const ExConst &nt) {
     long parent = (hole - 1) / 2;
     while (hole > top && cmp_res(first[parent], value, nt)) {
         first[hole] = first[parent];
@@ -88,12 +101,12 @@ __device__ void heap_push_hole(ExRes *first, long hole, long top, const ExRes &v
     }
     first[hole] = value;
 }
-__device__ void heap_push(ExRes *first, long &size, const ExRes &value, int nt) {   // push_back + push_heap
+__device__ void heap_push(ExRes *first, long &size, const ExRes &value, const ExConst &nt) {   // push_back + push_heap
     first[size] = value;
     size++;
     heap_push_hole(first, size - 1, 0, value, nt);
 }
-__device__ void heap_pop(ExRes *first, long &size, int nt) {                        // pop_heap + pop_back
+__device__ void heap_pop(ExRes *first, long &size, const ExConst &nt) {                        // pop_heap + pop_back
     if (size > 1) {
         const long len = size - 1;
         const ExRes value = first[len];
@@ -242,7 +255,7 @@ __global__ void __launch_bounds__(128) extend_kernel(const pg_seqdb db, const pg
                 r.dbEndPos = (int) (r.dbLen - dbStartPos - 1u);
             }
         }
-        heap_push(heap, hsize, r, c.nt);
+        heap_push(heap, hsize, r, c);
     }
     while (hsize > 0) {
         unsigned leftOff = 0, rightOff = 0;
@@ -254,7 +267,7 @@ __global__ void __launch_bounds__(128) extend_kernel(const pg_seqdb db, const pg
             ExRes best;
             while (hsize > 0) {
                 const ExRes res = heap[0];
-                heap_pop(heap, hsize, c.nt);
+                heap_pop(heap, hsize, c);
                 const bool notRightStartAndLeftStart = !(res.dbStartPos == 0 && res.qStartPos == 0);
                 const bool rightStart = res.dbStartPos == 0 && (res.dbEndPos != (int) res.dbLen - 1);
                 const bool leftStart = res.qStartPos == 0 && (res.qEndPos != (int) res.qLen - 1);
@@ -306,7 +319,7 @@ __global__ void __launch_bounds__(128) extend_kernel(const pg_seqdb db, const pg
             const char *tSeq = db.data + db.offsets[tId];
             const int diag = (int) ((unsigned) r.qStartPos + leftOff) - r.dbStartPos;
             rescore_parked(r, rope, tSeq, tSeqLen, r.rev, diag, c.alph);
-            if (r.seqId >= c.seqIdThr) heap_push(heap, hsize, r, c.nt);
+            if (r.seqId >= c.seqIdThr) heap_push(heap, hsize, r, c);
         }
     }
     if (couldExtend) {
@@ -379,6 +392,22 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     PG_CUDA(cudaMemcpyToSymbolAsync(c_ex_mat, mat, sizeof(mat), 0, cudaMemcpyHostToDevice, s));
     PG_CUDA(cudaStreamSynchronize(s));
 
+    c.lgammaTab = nullptr; c.logTab = nullptr; c.tabN = 0;
+    if (nt) {
+        const unsigned want = (unsigned) std::min<long long>(2LL * std::max(p->max_seq_len, (int) db->max_seq_len) + 64, 1 << 22);
+        if (ctx->ntTabN < want) {
+            std::vector<double> tab(2 * (size_t) want);
+            tab[0] = 0.0; tab[want] = 0.0;
+            for (unsigned i = 1; i < want; i++) { tab[i] = lgamma((double) i); tab[want + i] = log((double) i); }
+            PG_TRY(ctx->ntTab.reserve(sizeof(double) * tab.size()));
+            PG_CUDA(cudaMemcpyAsync(ctx->ntTab.p, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, s));
+            PG_CUDA(cudaStreamSynchronize(s));
+            ctx->ntTabN = want;
+        }
+        c.tabN = ctx->ntTabN;
+        c.lgammaTab = ctx->ntTab.as<double>();
+        c.logTab = ctx->ntTab.as<double>() + ctx->ntTabN;
+    }
     cudaEventRecord(ctx->ev[EV_EX_BEGIN], s);
     const uint64_t n = db->n;
     // meta arrays (per sequence)

@@ -7,7 +7,7 @@ namespace pg {
 
 enum {
     EV_KM_BEGIN = 0, EV_EXTRACT_END, EV_SORT1_BEGIN, EV_SORT1_END, EV_GROUP_END, EV_SORT2_END, EV_REDUCE_END,
-    EV_RS_BEGIN, EV_RS_END, EV_EX_BEGIN, EV_EX_END, EV_TOTAL_BEGIN, EV_TOTAL_END, EV_COUNT
+    EV_SCATTER1_BEGIN, EV_SCATTER1_END, EV_RS_BEGIN, EV_RS_END, EV_EX_BEGIN, EV_EX_END, EV_TOTAL_BEGIN, EV_TOTAL_END, EV_COUNT
 };
 
 }  // namespace pg
@@ -17,7 +17,8 @@ struct pg_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[pg::EV_COUNT];
-    pg::DevBuf small, lists, recA, recB, radixWs, scratch, blockCounts, hits, alnAll, alns, flags, exWork, exSegs, exMeta;
+    pg::DevBuf small, lists, recA, recB, radixWs, scratch, blockCounts, hits, alnAll, alns, flags, exWork, exSegs, exMeta, ntTab;
+    unsigned ntTabN = 0;
     bool pairsInA = false;
     bool kmRan = false, rsRan = false, exRan = false;
     uint64_t launches = 0;

@@ -825,7 +825,9 @@ int km_group(Context *ctx, const pg_seqdb *db, const KmConst &c, uint64_t nRecor
     PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nRecords)));
     Rec *sorted = nullptr;
     cudaEventRecord(ctx->ev[EV_SORT1_BEGIN], s);
-    PG_TRY(radix_sort(ctx->recA.as<Rec>(), ctx->recB.as<Rec>(), nRecords, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches));
+    PG_TRY(radix_sort(ctx->recA.as<Rec>(), ctx->recB.as<Rec>(), nRecords, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches,
+                      ctx->ev[EV_SCATTER1_BEGIN], ctx->ev[EV_SCATTER1_END]));
+    ctx->timings.sort1_passes = (uint32_t) plan.npasses;
     cudaEventRecord(ctx->ev[EV_SORT1_END], s);
     Rec *outBuf = (sorted == ctx->recA.as<Rec>()) ? ctx->recB.as<Rec>() : ctx->recA.as<Rec>();
     unsigned long long *d_cnt = ctx->small.as<unsigned long long>() + 2;
@@ -891,7 +893,7 @@ int km_run(Context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **d_h
     Rec *pairs = ctx->pairsInA ? ctx->recA.as<Rec>() : ctx->recB.as<Rec>();
     Rec *tmp = ctx->pairsInA ? ctx->recB.as<Rec>() : ctx->recA.as<Rec>();
     if (nRec == 0) {
-        cudaEventRecord(ctx->ev[EV_SORT1_BEGIN], s); cudaEventRecord(ctx->ev[EV_SORT1_END], s); cudaEventRecord(ctx->ev[EV_GROUP_END], s);
+        cudaEventRecord(ctx->ev[EV_SORT1_BEGIN], s); cudaEventRecord(ctx->ev[EV_SCATTER1_BEGIN], s); cudaEventRecord(ctx->ev[EV_SCATTER1_END], s); cudaEventRecord(ctx->ev[EV_SORT1_END], s); cudaEventRecord(ctx->ev[EV_GROUP_END], s);
     }
     if (nPairs == 0) { cudaEventRecord(ctx->ev[EV_SORT2_END], s); cudaEventRecord(ctx->ev[EV_REDUCE_END], s); }
     PG_TRY(km_reduce(ctx, db, pairs, tmp, nPairs, d_hits, nHits));

@@ -202,7 +202,7 @@ size_t radix_workspace_bytes(uint64_t n) {
 }
 
 int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspace, size_t workspace_bytes,
-               cudaStream_t stream, Rec **sorted, uint64_t *launches) {
+               cudaStream_t stream, Rec **sorted, uint64_t *launches, cudaEvent_t evScatterBegin, cudaEvent_t evScatterEnd) {
     *sorted = a;
     if (n == 0 || plan.npasses == 0) return 0;
     PG_CHECK(plan.npasses <= RADIX_MAX_PASSES, "radix_sort: too many passes");
@@ -229,6 +229,7 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
     if (launches) *launches += 2;
 
     Rec *src = a, *dst = b;
+    if (evScatterBegin) cudaEventRecord(evScatterBegin, stream);
     for (int p = 0; p < plan.npasses; p++) {
         for (unsigned long long q = 0; q < portions; q++) {
             const unsigned long long ps = q * PORTION_RECORDS;
@@ -244,6 +245,7 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
         }
         Rec *t = src; src = dst; dst = t;
     }
+    if (evScatterEnd) cudaEventRecord(evScatterEnd, stream);
     PG_CUDA(cudaGetLastError());
     *sorted = src;
     return 0;

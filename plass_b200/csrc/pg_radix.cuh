@@ -37,7 +37,8 @@ size_t radix_workspace_bytes(uint64_t n);
 // Sorts n records by the digits of plan (pass[0] least significant).  `a` holds the input, `b` is a
 // scratch buffer of the same size; *sorted points to whichever of the two holds the result.
 int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspace, size_t workspace_bytes,
-               cudaStream_t stream, Rec **sorted, uint64_t *launches);
+               cudaStream_t stream, Rec **sorted, uint64_t *launches,
+               cudaEvent_t evScatterBegin = nullptr, cudaEvent_t evScatterEnd = nullptr);
 
 // Helper to build a plan over bit ranges: appends 8-bit digits covering bits [lo, hi) of word w.
 void plan_add_bits(RadixPlan &plan, int word, int lo, int hi);

@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 from plass_b200 import mmseqsdb  # noqa: E402
-import synth_reads  # noqa: E402
+from plass_b200 import synth as synth_reads  # noqa: E402
 
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
 STEPS = ("kmermatcher", "rescorediagonal", "assembleresults", "nuclassembleresults")
