@@ -139,10 +139,28 @@ int pg_assemble_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_param
                           const pg_ex_params *ep, pg_seqdb **out_db,
                           pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns);
 
-/* Multi-GPU (one process per GPU): attach an NCCL communicator created by the caller
- * (ncclComm_t passed as void*).  With a communicator attached, pg_kmermatch / pg_assemble_iteration
- * shard the k-mer hash space over the ranks and exchange candidate pairs with one all-to-all. */
-int pg_set_comm(pg_context *ctx, void *nccl_comm, int rank, int world);
+/* Multi-GPU, one process per GPU.  The k-mer hash space is sharded over the ranks exactly
+ * like the reference's memory splits (kmermatcher.cpp:736-778: rank r extracts only the k-mers whose 16-bit
+ * hash lies in [kp->hash_start, kp->hash_end]); equal k-mers share a hash, so sort #1 and the group step are
+ * rank-local.  The (rep, target, diagonal) pairs are then routed to the rank that owns the representative
+ * (contiguous key ranges) by ONE all-to-all, which the caller performs on the device buffers (NCCL through
+ * torch.distributed in bench.py / plass_b200/sharded.py); everything downstream is local to the owner.
+ *
+ *   pg_shard_pairs   extraction of this rank's hash range + sort #1 + group; the pair records are left on
+ *                    the device grouped by destination rank; counts[world] (host) = records per destination
+ *   pg_shard_export  copies those records into a caller-supplied DEVICE buffer (the all-to-all send buffer)
+ *   pg_shard_finish  received pairs (DEVICE pointer) -> sort #2 + best diagonal -> rescorediagonal ->
+ *                    (nucl)assembleresults for the queries with key in [own_lo, own_hi); out_db holds only
+ *                    those sequences.  hits / alns (optional) are copied to pinned host arrays.
+ */
+int pg_shard_pairs(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, int world, uint64_t *counts);
+int pg_shard_export(pg_context *ctx, void *device_dst, uint64_t n_records);
+int pg_shard_finish(pg_context *ctx, const pg_seqdb *db, const void *device_pairs, uint64_t n_pairs,
+                    uint32_t own_lo, uint32_t own_hi, const pg_rs_params *rp, const pg_ex_params *ep,
+                    pg_seqdb **out_db, pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns);
+/* Key range [lo, hi) owned by rank r of `world` for a DB whose largest key is max_key. */
+void pg_shard_owner_range(uint32_t max_key, int rank, int world, uint32_t *lo, uint32_t *hi);
+uint32_t pg_seqdb_max_key(const pg_seqdb *db);
 
 void pg_free_host(void *p);
 

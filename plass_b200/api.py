@@ -7,6 +7,7 @@ loudly when no CUDA device is present.
 """
 import ctypes as C
 import os
+import weakref
 import numpy as np
 
 from . import mmseqsdb
@@ -18,7 +19,7 @@ LIB_PATH = os.path.join(HERE, "libplassgpu.so")
 EXPORTS = ["pg_last_error", "pg_device_count", "pg_init", "pg_destroy", "pg_get_timings", "pg_seqdb_upload",
            "pg_seqdb_download", "pg_seqdb_size", "pg_seqdb_free", "pg_kmermatch", "pg_rescore", "pg_extend",
            "pg_assemble_iteration", "pg_free_host",
-           ]
+           "pg_shard_pairs", "pg_shard_export", "pg_shard_finish", "pg_shard_owner_range", "pg_seqdb_max_key"]
 
 
 class SeqDBView(C.Structure):
@@ -112,13 +113,16 @@ def _check(rc, what):
 
 
 def _take(ptr, n, dtype):
+    """Wrap a pinned host array returned by the library as a numpy array WITHOUT copying; the block goes
+    back to the library's pinned pool (pg_free_host) when the array is garbage collected."""
     lib = load_library()
-    if n == 0:
-        out = np.zeros(0, dtype=dtype)
-    else:
-        out = np.frombuffer((C.c_char * (n * dtype.itemsize)).from_address(ptr.value), dtype=dtype).copy()
-    if ptr.value:
-        lib.pg_free_host(ptr)
+    if n == 0 or not ptr.value:
+        if ptr.value:
+            lib.pg_free_host(ptr)
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr.value)
+    out = np.frombuffer(buf, dtype=dtype)
+    weakref.finalize(buf, lib.pg_free_host, C.c_void_p(ptr.value))
     return out
 
 
@@ -138,6 +142,13 @@ class DeviceSeqDB:
         _check(lib.pg_seqdb_download(self.ctx.handle, self.handle, C.byref(d), C.byref(nb), C.byref(o), C.byref(l), C.byref(k), C.byref(n)), "pg_seqdb_download")
         return mmseqsdb.DB(_take(d, nb.value, np.dtype("u1")), _take(k, n.value, np.dtype("<u4")),
                            _take(o, n.value, np.dtype("<u8")), _take(l, n.value, np.dtype("<u4")), self.dbtype)
+
+    @property
+    def max_key(self):
+        lib = load_library()
+        lib.pg_seqdb_max_key.restype = C.c_uint32
+        lib.pg_seqdb_max_key.argtypes = [C.c_void_p]
+        return int(lib.pg_seqdb_max_key(self.handle))
 
     def free(self):
         if self.handle:
@@ -215,6 +226,31 @@ class Context:
         else:
             _check(load_library().pg_assemble_iteration(self.handle, ddb.handle, C.byref(kp), C.byref(rp), C.byref(ep), C.byref(h),
                                                         None, None, None, None), "pg_assemble_iteration")
+            hits = alns = None
+        out = DeviceSeqDB(self, h)
+        out.dbtype = ddb.dbtype
+        return out, hits, alns
+
+    # ---- multi-GPU phases (see plass_b200/sharded.py) ----
+    def shard_pairs(self, ddb, kp, world):
+        counts = (C.c_uint64 * world)()
+        _check(load_library().pg_shard_pairs(self.handle, ddb.handle, C.byref(kp), C.c_int(world), counts), "pg_shard_pairs")
+        return [int(c) for c in counts]
+
+    def shard_export(self, device_ptr, n_records):
+        _check(load_library().pg_shard_export(self.handle, C.c_void_p(device_ptr), C.c_uint64(n_records)), "pg_shard_export")
+
+    def shard_finish(self, ddb, device_ptr, n_pairs, own, rp, ep, want_intermediates=False):
+        h = C.c_void_p()
+        lib = load_library()
+        if want_intermediates:
+            ho, hn, ao, an = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+            _check(lib.pg_shard_finish(self.handle, ddb.handle, C.c_void_p(device_ptr), C.c_uint64(n_pairs), C.c_uint32(own[0]), C.c_uint32(own[1]),
+                                       C.byref(rp), C.byref(ep), C.byref(h), C.byref(ho), C.byref(hn), C.byref(ao), C.byref(an)), "pg_shard_finish")
+            hits, alns = _take(ho, hn.value, HIT), _take(ao, an.value, ALN)
+        else:
+            _check(lib.pg_shard_finish(self.handle, ddb.handle, C.c_void_p(device_ptr), C.c_uint64(n_pairs), C.c_uint32(own[0]), C.c_uint32(own[1]),
+                                       C.byref(rp), C.byref(ep), C.byref(h), None, None, None, None), "pg_shard_finish")
             hits = alns = None
         out = DeviceSeqDB(self, h)
         out.dbtype = ddb.dbtype

@@ -1,0 +1,323 @@
+// commands.cpp -- host side of the drop-in commands: flag parsing, MMseqs DB in/out, text formatting.
+// All arithmetic of the hot path happens behind the C ABI (libplassgpu.so); there is no CPU fallback.
+#include "commands.h"
+#include "mmdb.h"
+#include "plassgpu.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct Flags {
+    std::vector<std::string> positional;
+    std::map<std::string, std::string> kv;
+};
+
+[[noreturn]] void die(const std::string &msg) {
+    fprintf(stderr, "Error: %s\n", msg.c_str());
+    exit(EXIT_FAILURE);
+}
+
+Flags parseFlags(int argc, const char **argv, size_t nPositional, const std::set<std::string> &known) {
+    Flags f;
+    int i = 0;
+    for (; i < argc && f.positional.size() < nPositional; i++) f.positional.push_back(argv[i]);
+    if (f.positional.size() != nPositional) die("too few database arguments");
+    for (; i < argc; i += 2) {
+        const std::string k = argv[i];
+        if (known.find(k) == known.end()) die("unknown parameter " + k);
+        if (i + 1 >= argc) die("missing value for " + k);
+        f.kv[k] = argv[i + 1];
+    }
+    return f;
+}
+
+// MultiParam "nucl:0.200,aa:0.000" (lib/mmseqs/src/commons/MultiParam.cpp)
+std::string multi(const std::string &v, bool nucl) {
+    if (v.find(':') == std::string::npos) return v;
+    size_t p = 0;
+    while (p < v.size()) {
+        size_t c = v.find(',', p);
+        if (c == std::string::npos) c = v.size();
+        const std::string part = v.substr(p, c - p);
+        const size_t col = part.find(':');
+        if (col != std::string::npos) {
+            const std::string name = part.substr(0, col);
+            if ((nucl && name == "nucl") || (!nucl && name == "aa")) return part.substr(col + 1);
+        }
+        p = c + 1;
+    }
+    die("cannot parse multi-parameter " + v);
+}
+
+std::string get(const Flags &f, const std::string &k, const std::string &dflt) {
+    auto it = f.kv.find(k);
+    return it == f.kv.end() ? dflt : it->second;
+}
+int geti(const Flags &f, const std::string &k, int d) { return atoi(get(f, k, std::to_string(d)).c_str()); }
+double getd(const Flags &f, const std::string &k, double d) { auto it = f.kv.find(k); return it == f.kv.end() ? d : strtod(it->second.c_str(), nullptr); }
+
+void requireValue(const Flags &f, const std::string &k, const std::string &allowed, const char *why) {
+    auto it = f.kv.find(k);
+    if (it != f.kv.end() && it->second != allowed) die(k + " " + it->second + " is not supported by the GPU path (" + why + ")");
+}
+
+void checkSubMat(const Flags &f) {
+    auto it = f.kv.find("--sub-mat");
+    if (it == f.kv.end()) return;
+    if (multi(it->second, true) != "nucleotide.out" || multi(it->second, false) != "blosum62.out")
+        die("--sub-mat " + it->second + ": only the built-in nucleotide.out / blosum62.out tables are available on the GPU path");
+}
+
+struct Timer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void report() const {   // same wording as the reference (Application.cpp:38-43)
+        const long long ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+        printf("Time for processing: %lldh %lldm %llds %lldms\n", ms / 3600000, (ms / 60000) % 60, (ms / 1000) % 60, ms % 1000);
+    }
+};
+
+pg_context *gpu() {
+    static pg_context *ctx = nullptr;
+    if (!ctx) {
+        const char *dev = getenv("PLASS_B200_DEVICE");
+        if (pg_init(dev ? atoi(dev) : 0, &ctx) != 0) die(pg_last_error());
+    }
+    return ctx;
+}
+
+pg_seqdb *uploadSeqDb(const mmdb::Reader &r) {
+    if (r.dbtype != mmdb::DBTYPE_AMINO_ACIDS && r.dbtype != mmdb::DBTYPE_NUCLEOTIDES) die("input is not a sequence database");
+    pg_seqdb_view v;
+    v.data = r.data.data(); v.data_bytes = r.data.size();
+    v.offsets = r.offsets.data(); v.lens = r.lens.data(); v.keys = r.keys.data(); v.n = r.size(); v.dbtype = r.dbtype;
+    pg_seqdb *db = nullptr;
+    if (pg_seqdb_upload(gpu(), &v, &db) != 0) die(pg_last_error());
+    return db;
+}
+
+inline char *putU(char *b, unsigned long long v) {
+    char tmp[24]; int n = 0;
+    do { tmp[n++] = (char) ('0' + v % 10); v /= 10; } while (v);
+    while (n) *b++ = tmp[--n];
+    return b;
+}
+inline char *putI(char *b, long long v) {
+    if (v < 0) { *b++ = '-'; return putU(b, (unsigned long long) (-v)); }
+    return putU(b, (unsigned long long) v);
+}
+// Util::fastSeqIdToBuffer (Util.cpp:278-307) as it ends up on disk: "1.00" for exactly 1, else 0.ddd truncated
+inline char *putSeqId(char *b, float seqId) {
+    if (seqId == 1.0) { memcpy(b, "1.00", 4); return b + 4; }
+    *b++ = '0'; *b++ = '.';
+    if (seqId < 0.10) *b++ = '0';
+    if (seqId < 0.01) *b++ = '0';
+    return putI(b, (int) (seqId * 1000));
+}
+
+const std::set<std::string> KM_FLAGS = {"--sub-mat", "--alph-size", "--min-seq-id", "--kmer-per-seq", "--spaced-kmer-mode", "--spaced-kmer-pattern",
+    "--kmer-per-seq-scale", "--adjust-kmer-len", "--mask", "--mask-lower-case", "--cov-mode", "-k", "-c", "--max-seq-len", "--hash-shift",
+    "--split-memory-limit", "--include-only-extendable", "--ignore-multi-kmer", "--threads", "--compressed", "-v"};
+const std::set<std::string> RS_FLAGS = {"--sub-mat", "--rescore-mode", "--wrapped-scoring", "--filter-hits", "-e", "-c", "-a", "--cov-mode",
+    "--min-seq-id", "--min-aln-len", "--seq-id-mode", "--add-self-matches", "--sort-results", "--db-load-mode", "--threads", "--compressed", "-v"};
+const std::set<std::string> EX_FLAGS = {"--min-seq-id", "--max-seq-len", "--keep-target", "--threads", "-v", "--rescore-mode", "--sub-mat", "--db-load-mode", "--compressed"};
+
+int extendCommand(int argc, const char **argv, bool nuclCommand) {
+    Timer timer;
+    const Flags f = parseFlags(argc, argv, 3, EX_FLAGS);
+    requireValue(f, "--compressed", "0", "uncompressed DBs only");
+    checkSubMat(f);
+    std::string err;
+    mmdb::Reader seq, aln;
+    if (!seq.open(f.positional[0], err) || !aln.open(f.positional[1], err)) die(err);
+    const bool nucl = seq.dbtype == mmdb::DBTYPE_NUCLEOTIDES;
+    (void) nuclCommand;   // like the reference, the comparator follows the command, the letters follow the DB type
+    pg_ex_params p;
+    p.seq_id_thr = (float) getd(f, "--min-seq-id", nuclCommand ? 0.99 : 0.9);
+    p.max_seq_len = geti(f, "--max-seq-len", nuclCommand ? 200000 : 65535);
+    p.keep_target = geti(f, "--keep-target", 1);
+    p.rescore_mode = geti(f, "--rescore-mode", 3);
+    if (nuclCommand != nucl) die("sequence DB type does not match the command (assembleresults = amino acids, nuclassembleresults = nucleotides)");
+    // parse the alignment DB (Matcher::parseAlignmentRecord, Matcher.cpp:248-320)
+    std::vector<pg_aln> alns;
+    for (size_t i = 0; i < aln.size(); i++) {
+        const char *s = aln.entry(i);
+        while (*s) {
+            pg_aln a; a.query = aln.keys[i];
+            char *e;
+            a.target = (uint32_t) strtoul(s, &e, 10);
+            a.bits = (int32_t) strtol(e, &e, 10);
+            a.seq_id = (float) strtod(e, &e);
+            a.evalue = strtod(e, &e);
+            a.q_start = (int32_t) strtol(e, &e, 10); a.q_end = (int32_t) strtol(e, &e, 10); a.q_len = (int32_t) strtol(e, &e, 10);
+            a.db_start = (int32_t) strtol(e, &e, 10); a.db_end = (int32_t) strtol(e, &e, 10); a.db_len = (int32_t) strtol(e, &e, 10);
+            alns.push_back(a);
+            while (*e && *e != '\n') e++;
+            s = *e ? e + 1 : e;
+        }
+    }
+    pg_seqdb *db = uploadSeqDb(seq), *out = nullptr;
+    if (pg_extend(gpu(), db, alns.data(), alns.size(), &p, &out, nullptr) != 0) die(pg_last_error());
+    char *data; uint64_t bytes, *offs, n; uint32_t *lens, *keys;
+    if (pg_seqdb_download(gpu(), out, &data, &bytes, &offs, &lens, &keys, &n) != 0) die(pg_last_error());
+    mmdb::Writer w;
+    if (!w.open(f.positional[2], seq.dbtype, err)) die(err);
+    for (uint64_t i = 0; i < n; i++) w.write(keys[i], data + offs[i], lens[i] - 1);
+    if (!w.close()) die("write error");
+    pg_free_host(data); pg_free_host(offs); pg_free_host(lens); pg_free_host(keys);
+    pg_seqdb_free(gpu(), out); pg_seqdb_free(gpu(), db);
+    printf("\nDone.\n");
+    timer.report();
+    return EXIT_SUCCESS;
+}
+
+}  // namespace
+
+int kmermatcher(int argc, const char **argv) {
+    Timer timer;
+    const Flags f = parseFlags(argc, argv, 2, KM_FLAGS);
+    requireValue(f, "--mask", "0", "tantan masking is not on the assemble path");
+    requireValue(f, "--mask-lower-case", "0", "not on the assemble path");
+    requireValue(f, "--spaced-kmer-mode", "0", "spaced k-mers are not on the assemble path");
+    requireValue(f, "--adjust-kmer-len", "0", "Markov k-mer length adjustment is not on the assemble path");
+    requireValue(f, "--compressed", "0", "uncompressed DBs only");
+    checkSubMat(f);
+    std::string err;
+    mmdb::Reader seq;
+    if (!seq.open(f.positional[0], err)) die(err);
+    const bool nucl = seq.dbtype == mmdb::DBTYPE_NUCLEOTIDES;
+    pg_km_params p;
+    p.kmer_size = geti(f, "-k", nucl ? 22 : 14);
+    p.alph_size = atoi(multi(get(f, "--alph-size", nucl ? "5" : "13"), nucl).c_str());
+    p.kmers_per_seq = geti(f, "--kmer-per-seq", 60);
+    p.kmers_per_seq_scale = (float) strtod(multi(get(f, "--kmer-per-seq-scale", nucl ? "0.1" : "0.0"), nucl).c_str(), nullptr);
+    p.hash_shift = geti(f, "--hash-shift", 67);
+    p.include_only_extendable = geti(f, "--include-only-extendable", 0);
+    p.ignore_multi_kmer = geti(f, "--ignore-multi-kmer", 1);
+    p.cov_mode = geti(f, "--cov-mode", 0);
+    p.cov_thr = (float) getd(f, "-c", 0.0);
+    p.hash_start = 0; p.hash_end = 65535;
+    pg_seqdb *db = uploadSeqDb(seq);
+    pg_hit *hits = nullptr; uint64_t nHits = 0;
+    if (pg_kmermatch(gpu(), db, &p, &hits, &nHits) != 0) die(pg_last_error());
+    // prefilter DB: every key gets "key\t0\t0\n" followed by its hit lines (kmermatcher.cpp:809-924, :705-724;
+    // QueryMatcher::prefilterHitToBuffer).  Entries are written in key order.
+    mmdb::Writer w;
+    if (!w.open(f.positional[1], nucl ? mmdb::DBTYPE_PREFILTER_REV_RES : mmdb::DBTYPE_PREFILTER_RES, err)) die(err);
+    std::string buf;
+    uint64_t h = 0;
+    char line[64];
+    for (size_t i = 0; i < seq.size(); i++) {
+        const uint32_t key = seq.keys[i];
+        buf.clear();
+        char *b = putU(line, key); memcpy(b, "\t0\t0\n", 5); buf.append(line, (size_t) (b + 5 - line));
+        while (h < nHits && hits[h].rep < key) h++;
+        while (h < nHits && hits[h].rep == key) {
+            b = putU(line, hits[h].target); *b++ = '\t';
+            b = putI(b, hits[h].score); *b++ = '\t';
+            b = putI(b, (short) hits[h].diag); *b++ = '\n';
+            buf.append(line, (size_t) (b - line));
+            h++;
+        }
+        w.write(key, buf.data(), buf.size());
+    }
+    if (!w.close()) die("write error");
+    pg_free_host(hits);
+    pg_seqdb_free(gpu(), db);
+    timer.report();
+    return EXIT_SUCCESS;
+}
+
+int rescorediagonal(int argc, const char **argv) {
+    Timer timer;
+    const Flags f = parseFlags(argc, argv, 4, RS_FLAGS);
+    requireValue(f, "--rescore-mode", "3", "the assemble workflows use END_TO_END only");
+    requireValue(f, "--wrapped-scoring", "0", "not on the assemble path");
+    requireValue(f, "--filter-hits", "0", "not on the assemble path");
+    requireValue(f, "-a", "0", "backtraces are not produced by ungapped rescoring on the assemble path");
+    requireValue(f, "--sort-results", "0", "the assemble workflows keep prefilter order");
+    requireValue(f, "--add-self-matches", "0", "query DB == target DB already keeps the self match");
+    requireValue(f, "--compressed", "0", "uncompressed DBs only");
+    checkSubMat(f);
+    if (f.positional[0] != f.positional[1]) die("rescorediagonal on the GPU path requires query DB == target DB (as in assemble.sh / nuclassemble.sh)");
+    std::string err;
+    mmdb::Reader seq, pref;
+    if (!seq.open(f.positional[0], err) || !pref.open(f.positional[2], err)) die(err);
+    const bool nucl = seq.dbtype == mmdb::DBTYPE_NUCLEOTIDES;
+    if (pref.dbtype != (nucl ? mmdb::DBTYPE_PREFILTER_REV_RES : mmdb::DBTYPE_PREFILTER_RES)) die("prefilter DB type does not match the sequence DB");
+    if (pref.size() != seq.size() || !std::equal(pref.keys.begin(), pref.keys.end(), seq.keys.begin()))
+        die("prefilter DB must hold one entry per sequence (kmermatcher output)");
+    pg_rs_params p;
+    p.rescore_mode = 3;
+    p.seq_id_thr = (float) getd(f, "--min-seq-id", 0.0);
+    p.eval_thr = getd(f, "-e", 0.001);
+    p.cov_mode = geti(f, "--cov-mode", 0);
+    p.cov_thr = (float) getd(f, "-c", 0.0);
+    p.aln_len_thr = geti(f, "--min-aln-len", 0);
+    p.seq_id_mode = geti(f, "--seq-id-mode", 0);
+    // QueryMatcher::parsePrefilterHits (QueryMatcher.h:81-112); the first line must be the self line
+    std::vector<pg_hit> hits;
+    for (size_t i = 0; i < pref.size(); i++) {
+        const char *s = pref.entry(i);
+        bool first = true;
+        while (*s) {
+            char *e;
+            pg_hit h; h.rep = pref.keys[i];
+            h.target = (uint32_t) strtoul(s, &e, 10);
+            h.score = (int32_t) strtol(e, &e, 10);
+            h.diag = (int32_t) (short) strtol(e, &e, 10);
+            if (first) {
+                if (h.target != h.rep || h.score != 0 || h.diag != 0) die("prefilter entry does not start with its self line (not a kmermatcher result)");
+                first = false;
+            } else {
+                hits.push_back(h);
+            }
+            while (*e && *e != '\n') e++;
+            s = *e ? e + 1 : e;
+        }
+        if (first) die("empty prefilter entry");
+    }
+    pg_seqdb *db = uploadSeqDb(seq);
+    pg_aln *alns = nullptr; uint64_t nAlns = 0;
+    if (pg_rescore(gpu(), db, hits.data(), hits.size(), &p, &alns, &nAlns) != 0) die(pg_last_error());
+    // Matcher::resultToBuffer (Matcher.cpp:323-370): 10 columns
+    mmdb::Writer w;
+    if (!w.open(f.positional[3], mmdb::DBTYPE_ALIGNMENT_RES, err)) die(err);
+    std::string buf;
+    char line[256];
+    uint64_t a = 0;
+    for (size_t i = 0; i < seq.size(); i++) {
+        const uint32_t key = seq.keys[i];
+        buf.clear();
+        while (a < nAlns && alns[a].query < key) a++;
+        while (a < nAlns && alns[a].query == key) {
+            const pg_aln &r = alns[a];
+            char *b = putU(line, r.target); *b++ = '\t';
+            b = putI(b, r.bits); *b++ = '\t';
+            b = putSeqId(b, r.seq_id); *b++ = '\t';
+            b += sprintf(b, "%.3E", r.evalue); *b++ = '\t';
+            b = putI(b, r.q_start); *b++ = '\t'; b = putI(b, r.q_end); *b++ = '\t'; b = putI(b, r.q_len); *b++ = '\t';
+            b = putI(b, r.db_start); *b++ = '\t'; b = putI(b, r.db_end); *b++ = '\t'; b = putI(b, r.db_len); *b++ = '\n';
+            buf.append(line, (size_t) (b - line));
+            a++;
+        }
+        w.write(key, buf.data(), buf.size());
+    }
+    if (!w.close()) die("write error");
+    pg_free_host(alns);
+    pg_seqdb_free(gpu(), db);
+    timer.report();
+    return EXIT_SUCCESS;
+}
+
+int assembleresults(int argc, const char **argv) { return extendCommand(argc, argv, false); }
+int nuclassembleresults(int argc, const char **argv) { return extendCommand(argc, argv, true); }

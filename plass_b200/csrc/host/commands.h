@@ -1,0 +1,8 @@
+// commands.h -- the four drop-in commands.  Same signature as the reference's command functions
+// (lib/mmseqs/src/commons/Command.h:91-102: int fn(int argc, const char **argv, const Command &)),
+// minus the Command descriptor: argv excludes program and command name (Application.cpp:203).
+#pragma once
+int kmermatcher(int argc, const char **argv);            // replaces linclust/kmermatcher.cpp:780
+int rescorediagonal(int argc, const char **argv);        // replaces alignment/rescorediagonal.cpp:381
+int assembleresults(int argc, const char **argv);        // replaces src/assembler/assembleresult.cpp:358
+int nuclassembleresults(int argc, const char **argv);    // replaces src/assembler/nuclassembleresult.cpp:400

@@ -1,6 +1,8 @@
 // pg_api.cu -- the C ABI of libplassgpu.so (declared in include/plassgpu.h).
 #include "pg_internal.cuh"
 
+#include <algorithm>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -50,10 +52,49 @@ int seqdb_finalize(Context *ctx, pg_seqdb *db) {
     return 0;
 }
 
+// Pinned host blocks are expensive to create (cudaMallocHost pins pages, ~0.3 s/GB), so blocks released
+// with pg_free_host() are kept in a small process-wide cache and handed out again.
+static std::mutex g_pinMutex;
+static std::map<void *, size_t> g_pinLive;            // blocks owned by the caller
+static std::multimap<size_t, void *> g_pinCache;      // released blocks, by size
+static size_t g_pinCachedBytes = 0;
+static const size_t PIN_CACHE_LIMIT = 24ull << 30;
+
+int alloc_pinned(size_t bytes, void **out) {
+    if (bytes < 64) bytes = 64;
+    {
+        std::lock_guard<std::mutex> lk(g_pinMutex);
+        auto it = g_pinCache.lower_bound(bytes);
+        if (it != g_pinCache.end() && it->first <= bytes * 2 + (1 << 20)) {
+            *out = it->second;
+            g_pinLive[it->second] = it->first;
+            g_pinCachedBytes -= it->first;
+            g_pinCache.erase(it);
+            return 0;
+        }
+    }
+    void *p = nullptr;
+    const size_t want = bytes + bytes / 8;            // head-room so that slightly larger results reuse the block
+    PG_CUDA(cudaMallocHost(&p, want));
+    std::lock_guard<std::mutex> lk(g_pinMutex);
+    g_pinLive[p] = want;
+    *out = p;
+    return 0;
+}
+static void release_pinned(void *p) {
+    std::lock_guard<std::mutex> lk(g_pinMutex);
+    auto it = g_pinLive.find(p);
+    if (it == g_pinLive.end()) { cudaFreeHost(p); return; }
+    const size_t sz = it->second;
+    g_pinLive.erase(it);
+    if (g_pinCachedBytes + sz <= PIN_CACHE_LIMIT) { g_pinCache.emplace(sz, p); g_pinCachedBytes += sz; }
+    else cudaFreeHost(p);
+}
+
 template <class T>
 static int to_host(cudaStream_t s, const T *d, uint64_t n, T **out) {
     T *h = nullptr;
-    PG_CUDA(cudaMallocHost(&h, sizeof(T) * (n + 1)));
+    PG_TRY(alloc_pinned(sizeof(T) * (n + 1), (void **) &h));
     if (n) PG_CUDA(cudaMemcpyAsync(h, d, sizeof(T) * n, cudaMemcpyDeviceToHost, s));
     PG_CUDA(cudaStreamSynchronize(s));
     *out = h;
@@ -69,6 +110,10 @@ static void collect_timings(Context *ctx) {
         t.sort1_ms = el(EV_SORT1_BEGIN, EV_SORT1_END);
         t.sort1_scatter_ms = el(EV_SCATTER1_BEGIN, EV_SCATTER1_END);
         t.group_ms = el(EV_SORT1_END, EV_GROUP_END);
+        t.sort2_ms = el(EV_GROUP_END, EV_SORT2_END);
+        t.reduce_ms = el(EV_SORT2_END, EV_REDUCE_END);
+    }
+    else if (ctx->rsRan) {   // pg_shard_finish: only sort #2 + reduce ran in this call
         t.sort2_ms = el(EV_GROUP_END, EV_SORT2_END);
         t.reduce_ms = el(EV_SORT2_END, EV_REDUCE_END);
     }
@@ -253,7 +298,59 @@ int pg_assemble_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_param
     return 0;
 }
 
-void pg_free_host(void *p) { if (p) cudaFreeHost(p); }
+void pg_free_host(void *p) { if (p) release_pinned(p); }
+
+uint32_t pg_seqdb_max_key(const pg_seqdb *db) { return db ? db->max_key : 0; }
+
+void pg_shard_owner_range(uint32_t max_key, int rank, int world, uint32_t *lo, uint32_t *hi) {
+    const unsigned long long per = ((unsigned long long) max_key + (unsigned long long) world) / (unsigned long long) world;   // = keysPerRank of tag_owner_kernel
+    *lo = (uint32_t) std::min<unsigned long long>(per * (unsigned long long) rank, 0xFFFFFFFFull);
+    *hi = (rank == world - 1) ? 0xFFFFFFFFu : (uint32_t) std::min<unsigned long long>(per * (unsigned long long) (rank + 1), 0xFFFFFFFFull);
+}
+
+int pg_shard_pairs(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, int world, uint64_t *counts) {
+    PG_CHECK(ctx && db && kp && counts, "pg_shard_pairs: null argument");
+    begin_call(ctx);
+    PG_TRY(km_shard_pairs(ctx, db, kp, world, counts));
+    end_call(ctx);
+    return 0;
+}
+
+int pg_shard_export(pg_context *ctx, void *device_dst, uint64_t n_records) {
+    PG_CHECK(ctx && (device_dst || n_records == 0), "pg_shard_export: null argument");
+    PG_CHECK(n_records == ctx->shardPairCount, "pg_shard_export: record count does not match pg_shard_pairs");
+    cudaSetDevice(ctx->device);
+    if (n_records) PG_CUDA(cudaMemcpyAsync(device_dst, ctx->shardPairs, sizeof(Rec) * n_records, cudaMemcpyDeviceToDevice, ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int pg_shard_finish(pg_context *ctx, const pg_seqdb *db, const void *device_pairs, uint64_t n_pairs,
+                    uint32_t own_lo, uint32_t own_hi, const pg_rs_params *rp, const pg_ex_params *ep,
+                    pg_seqdb **out_db, pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns) {
+    PG_CHECK(ctx && db && rp && ep && out_db && (device_pairs || n_pairs == 0), "pg_shard_finish: null argument");
+    pg_timings keep = ctx->timings;   // phase-1 numbers of this step
+    begin_call(ctx);
+    ctx->timings.n_kmer_records = keep.n_kmer_records; ctx->timings.n_pair_records = keep.n_pair_records; ctx->timings.sort1_bytes = keep.sort1_bytes;
+    ctx->ownLo = own_lo; ctx->ownHi = own_hi;
+    pg_hit *dHits = nullptr; uint64_t nH = 0;
+    int rc = km_shard_reduce(ctx, db, device_pairs, n_pairs, &dHits, &nH);
+    pg_aln *dAlns = nullptr; uint64_t nA = 0;
+    unsigned char *dExt = nullptr;
+    if (rc == 0) rc = rs_run(ctx, db, dHits, nH, rp, &dAlns, &nA);
+    if (rc == 0) rc = ex_run(ctx, db, dAlns, nA, ep, out_db, &dExt);
+    ctx->ownLo = 0; ctx->ownHi = 0xFFFFFFFFu;
+    if (rc != 0) return rc;
+    cudaFree(dExt);
+    end_call(ctx);
+    // the sort-#2 / reduce events of this call are valid, the extract / sort-#1 ones belong to pg_shard_pairs
+    ctx->timings.extract_ms = keep.extract_ms; ctx->timings.sort1_ms = keep.sort1_ms; ctx->timings.sort1_scatter_ms = keep.sort1_scatter_ms;
+    ctx->timings.sort1_passes = keep.sort1_passes; ctx->timings.group_ms = keep.group_ms;
+    ctx->timings.kernel_launches += keep.kernel_launches; ctx->timings.total_ms += keep.total_ms;
+    if (hits && n_hits) { PG_TRY(to_host(ctx->stream, dHits, nH, hits)); *n_hits = nH; }
+    if (alns && n_alns) { PG_TRY(to_host(ctx->stream, dAlns, nA, alns)); *n_alns = nA; }
+    return 0;
+}
 
 // ---- diagnostics used by the tests (not part of the drop-in surface) --------------------------------
 int pg_debug_radix_sort(pg_context *ctx, uint64_t *recs /* n x 2 u64, in place */, uint64_t n, const int *word, const int *lo, const int *hi, int nRanges) {

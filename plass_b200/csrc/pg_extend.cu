@@ -331,10 +331,12 @@ __global__ void __launch_bounds__(128) extend_kernel(const pg_seqdb db, const pg
 
 // keep[i] = 1 if sequence i is written to the output DB (assembleresult.cpp:316-342)
 __global__ void keep_kernel(unsigned long long n, int keepTarget, const unsigned char *__restrict__ extended,
-                            const unsigned char *__restrict__ used, unsigned *__restrict__ keep, unsigned *__restrict__ outLen) {
+                            const unsigned char *__restrict__ used, unsigned *__restrict__ keep, unsigned *__restrict__ outLen,
+                            const unsigned *__restrict__ keys, unsigned ownLo, unsigned ownHi) {
     const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const bool k = extended[i] || keepTarget || !used[i];
+    const unsigned key = keys[i];
+    const bool k = (key >= ownLo && key < ownHi) && (extended[i] || keepTarget || !used[i]);
     keep[i] = k ? 1u : 0u;
     if (!k) outLen[i] = 0;
 }
@@ -443,7 +445,7 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     if (nAlns) aln_ranges_kernel<<<(unsigned) ((nAlns + 255) / 256), 256, 0, s>>>(*db, d_alns, nAlns, alnStart, alnCount);
     extend_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(*db, d_alns, alnStart, alnCount, c, heapBuf, parkBuf,
                                                               ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
-    keep_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(n, c.keepTarget, ext, used, keep, outLen);
+    keep_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(n, c.keepTarget, ext, used, keep, outLen, db->keys, ctx->ownLo, ctx->ownHi);
     ctx->launches += 3;
     unsigned long long *d_tot = ctx->small.as<unsigned long long>() + 5;   // [5] bytes, [6] kept
     PG_TRY(exclusive_scan_u32(outLen, outOff, n, d_tot, scanWs, scan_workspace_bytes(n), s, &ctx->launches));

@@ -24,6 +24,10 @@ struct pg_context {
     uint64_t launches = 0;
     pg_timings timings;
     uint64_t nHits = 0, nAlns = 0;
+    // multi-GPU: this rank owns the queries / representatives with key in [ownLo, ownHi)
+    unsigned ownLo = 0, ownHi = 0xFFFFFFFFu;
+    pg::Rec *shardPairs = nullptr;
+    uint64_t shardPairCount = 0;
 };
 
 namespace pg {
@@ -32,10 +36,13 @@ typedef pg_context Context;
 struct KmConst;
 // kmermatcher stages (pg_kmermatch.cu)
 int km_run(Context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **d_hits, uint64_t *nHits);
+int km_shard_pairs(Context *ctx, const pg_seqdb *db, const pg_km_params *p, int world, uint64_t *counts);
+int km_shard_reduce(Context *ctx, const pg_seqdb *db, const void *d_pairs, uint64_t nPairs, pg_hit **d_hits, uint64_t *nHits);
 // rescorediagonal (pg_rescore.cu): d_hits sorted by (rep,target); result device array in ctx->alns
 int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHits, const pg_rs_params *p, pg_aln **d_alns, uint64_t *nAlns);
 // extension (pg_extend.cu): d_alns sorted by query; produces a new device DB
 int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAlns, const pg_ex_params *p, pg_seqdb **out, unsigned char **d_extended);
 int seqdb_finalize(Context *ctx, pg_seqdb *db);   // computes max_seq_len / residues / dense_keys on the device
 void seqdb_release(pg_seqdb *db);
+int alloc_pinned(size_t bytes, void **out);        // pooled pinned host memory, released with pg_free_host
 }  // namespace pg

@@ -905,6 +905,69 @@ int km_run(Context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **d_h
     return 0;
 }
 
+// ---- multi-GPU: the k-mer hash space is sharded over the ranks (the reference's split mechanism,
+// kmermatcher.cpp:736-778: each split extracts only the k-mers whose 16-bit hash falls in its range), the
+// (rep, target, diagonal) pairs are then routed to the rank that owns the representative (contiguous key
+// ranges) with one all-to-all; sort #2 and everything downstream is local to the owner. -------------------
+__global__ void tag_owner_kernel(Rec *__restrict__ pairs, unsigned long long n, unsigned keysPerRank, unsigned world) {
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
+        const unsigned rep = (unsigned) (pairs[i].w0 >> 32);
+        const unsigned owner = min(world - 1u, rep / keysPerRank);
+        pairs[i].w1 = (pairs[i].w1 & 0xFFFFFFULL) | ((unsigned long long) owner << 24);
+    }
+}
+
+int km_shard_pairs(Context *ctx, const pg_seqdb *db, const pg_km_params *p, int world, uint64_t *counts) {
+    PG_CHECK(world >= 1 && world <= 256, "pg_shard_pairs: world size must be in [1, 256]");
+    KmConst c;
+    cudaStream_t s = ctx->stream;
+    PG_TRY(km_setup_constants(db, p, c, s));
+    cudaEventRecord(ctx->ev[EV_KM_BEGIN], s);
+    uint64_t nRec = 0, nPairs = 0;
+    PG_TRY(km_extract(ctx, db, p, c, &nRec));
+    cudaEventRecord(ctx->ev[EV_EXTRACT_END], s);
+    PG_TRY(km_group(ctx, db, c, nRec, &nPairs));
+    if (nRec == 0) {
+        cudaEventRecord(ctx->ev[EV_SORT1_BEGIN], s); cudaEventRecord(ctx->ev[EV_SCATTER1_BEGIN], s); cudaEventRecord(ctx->ev[EV_SCATTER1_END], s);
+        cudaEventRecord(ctx->ev[EV_SORT1_END], s); cudaEventRecord(ctx->ev[EV_GROUP_END], s);
+    }
+    Rec *pairs = ctx->pairsInA ? ctx->recA.as<Rec>() : ctx->recB.as<Rec>();
+    Rec *tmp = ctx->pairsInA ? ctx->recB.as<Rec>() : ctx->recA.as<Rec>();
+    for (int r = 0; r < world; r++) counts[r] = 0;
+    ctx->shardPairs = pairs; ctx->shardPairCount = nPairs;
+    ctx->timings.n_kmer_records = nRec; ctx->timings.n_pair_records = nPairs;
+    ctx->timings.sort1_bytes = (uint64_t) nRec * sizeof(Rec) * 2;
+    ctx->kmRan = true;
+    cudaEventRecord(ctx->ev[EV_SORT2_END], s); cudaEventRecord(ctx->ev[EV_REDUCE_END], s);
+    if (nPairs == 0) return 0;
+    const unsigned keysPerRank = (unsigned) (((unsigned long long) db->max_key + world) / world);
+    tag_owner_kernel<<<NUM_SMS * 8, 256, 0, s>>>(pairs, nPairs, keysPerRank, (unsigned) world);
+    RadixPlan plan; plan.npasses = 0;
+    plan_add_bits(plan, 1, 24, 32);
+    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nPairs)));
+    Rec *sorted = nullptr;
+    PG_TRY(radix_sort(pairs, tmp, nPairs, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches));
+    ctx->launches++;
+    unsigned long long h[256];
+    PG_CUDA(cudaMemcpyAsync(h, ctx->radixWs.p, sizeof(unsigned long long) * 256, cudaMemcpyDeviceToHost, s));   // digit histogram of the pass
+    PG_CUDA(cudaStreamSynchronize(s));
+    for (int r = 0; r < world; r++) counts[r] = h[r];
+    ctx->shardPairs = sorted;
+    return 0;
+}
+
+int km_shard_reduce(Context *ctx, const pg_seqdb *db, const void *d_pairs, uint64_t nPairs, pg_hit **d_hits, uint64_t *nHits) {
+    cudaStream_t s = ctx->stream;
+    PG_TRY(ctx->recA.reserve(sizeof(Rec) * (nPairs + 1)));
+    PG_TRY(ctx->recB.reserve(sizeof(Rec) * (nPairs + 1)));
+    if (nPairs) PG_CUDA(cudaMemcpyAsync(ctx->recA.p, d_pairs, sizeof(Rec) * nPairs, cudaMemcpyDeviceToDevice, s));
+    cudaEventRecord(ctx->ev[EV_GROUP_END], s);
+    if (nPairs == 0) { cudaEventRecord(ctx->ev[EV_SORT2_END], s); cudaEventRecord(ctx->ev[EV_REDUCE_END], s); }
+    PG_TRY(km_reduce(ctx, db, ctx->recA.as<Rec>(), ctx->recB.as<Rec>(), nPairs, d_hits, nHits));
+    ctx->timings.n_hits = *nHits;
+    return 0;
+}
+
 }  // namespace pg
 
 // diagnostic used by the tests: the k-mer records of stage 1 (order unspecified), n x {w0, w1}
@@ -917,7 +980,7 @@ extern "C" int pg_debug_extract(pg_context *ctx, const pg_seqdb *db, const pg_km
     uint64_t nRec = 0;
     PG_TRY(km_extract(ctx, db, p, c, &nRec));
     uint64_t *h = nullptr;
-    PG_CUDA(cudaMallocHost(&h, sizeof(Rec) * (nRec + 1)));
+    PG_TRY(alloc_pinned(sizeof(Rec) * (nRec + 1), (void **) &h));
     PG_CUDA(cudaMemcpyAsync(h, ctx->recA.p, sizeof(Rec) * nRec, cudaMemcpyDeviceToHost, ctx->stream));
     PG_CUDA(cudaStreamSynchronize(ctx->stream));
     *recs = h; *n = nRec;

@@ -24,6 +24,7 @@ struct RsConst {
     int alnLenThr;
     int seqIdMode;
     double dbRes;             // getAminoAcidDBSize of the target DB
+    unsigned ownLo, ownHi;    // multi-GPU: self lines only for the queries this rank owns
     // ALP (Gumbel + finite size correction) parameters
     double lambda, K, a_I, b_I, a_J, b_J, alpha_I, beta_I, alpha_J, beta_J, sigma, tau, vi_thr, vj_thr, c_thr, logK;
 };
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const pg_seqdb db, const p
         } else {
             qi = ti = (unsigned) (item - nHits);
             qKey = tKey = db.keys[qi]; prefScore = 0; diag16 = 0;
+            if (qKey < c.ownLo || qKey >= c.ownHi) { if (lane == 0) acc[item] = 0; continue; }
         }
         const bool isIdentity = (qi == ti);                 // same DB on both sides (rescorediagonal.cpp:205)
         QView q; q.s = db.data + db.offsets[qi]; q.len = (int) db.lens[qi] - 2; q.rev = (c.nt && prefScore < 0);
@@ -225,14 +227,17 @@ __global__ void count_per_query_kernel(const pg_seqdb db, const pg_hit *__restri
     cnt[find_id(db.keys, (unsigned) db.n, rep)] = c;
 }
 
-__global__ void fill_u32_kernel(unsigned *p, unsigned long long n, unsigned v) {
-    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) p[i] = v;
+__global__ void fill_owned_kernel(const unsigned *__restrict__ keys, unsigned *p, unsigned long long n, unsigned ownLo, unsigned ownHi) {
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
+        const unsigned k = keys[i];
+        p[i] = (k >= ownLo && k < ownHi) ? 1u : 0u;
+    }
 }
 
 __global__ void gather_self_kernel(const pg_aln *__restrict__ res, unsigned long long nHits, unsigned long long n,
-                                   const unsigned long long *__restrict__ off, pg_aln *__restrict__ out) {
+                                   const unsigned long long *__restrict__ off, const unsigned char *__restrict__ acc, pg_aln *__restrict__ out) {
     const unsigned long long qi = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi < n) out[off[qi]] = res[nHits + qi];
+    if (qi < n && acc[nHits + qi]) out[off[qi]] = res[nHits + qi];
 }
 
 __global__ void gather_hits_kernel(const pg_seqdb db, const pg_hit *__restrict__ hits, unsigned long long nHits,
@@ -255,6 +260,7 @@ int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHit
     c.nt = nt; c.alph = nt ? 5 : 21;
     c.seqIdThr = p->seq_id_thr; c.evalThr = p->eval_thr; c.covMode = p->cov_mode; c.covThr = p->cov_thr;
     c.alnLenThr = p->aln_len_thr; c.seqIdMode = p->seq_id_mode; c.dbRes = db->residues;
+    c.ownLo = ctx->ownLo; c.ownHi = ctx->ownHi;
     const double *a = nt ? PG_NT_ALP : PG_AA_ALP;
     c.lambda = a[0]; c.K = a[1]; c.a_I = a[2]; c.b_I = a[3]; c.a_J = a[4]; c.b_J = a[5];
     c.alpha_I = a[6]; c.beta_I = a[7]; c.alpha_J = a[8]; c.beta_J = a[9]; c.sigma = a[10]; c.tau = a[11];
@@ -288,7 +294,7 @@ int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHit
     unsigned blocks = (unsigned) std::min<unsigned long long>((warps + 7) / 8, (unsigned long long) NUM_SMS * 64);
     if (blocks == 0) blocks = 1;
     rescore_kernel<<<blocks, 256, 0, s>>>(*db, d_hits, nHits, c, res, acc);
-    fill_u32_kernel<<<NUM_SMS * 4, 256, 0, s>>>(cnt, n, 1u);
+    fill_owned_kernel<<<NUM_SMS * 4, 256, 0, s>>>(db->keys, cnt, n, c.ownLo, c.ownHi);
     if (nHits) count_per_query_kernel<<<(unsigned) ((nHits + 255) / 256), 256, 0, s>>>(*db, d_hits, nHits, acc, cnt);
     ctx->launches += 3;
     PG_TRY(exclusive_scan_u32(cnt, off, n, d_total, scanWs, scan_workspace_bytes(n), s, &ctx->launches));
@@ -297,7 +303,7 @@ int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHit
     PG_CUDA(cudaStreamSynchronize(s));
     PG_TRY(ctx->alns.reserve(sizeof(pg_aln) * (h + 1)));
     pg_aln *out = ctx->alns.as<pg_aln>();
-    if (n) gather_self_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(res, nHits, n, off, out);
+    if (n) gather_self_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(res, nHits, n, off, acc, out);
     if (nHits) gather_hits_kernel<<<(unsigned) ((nHits + 255) / 256), 256, 0, s>>>(*db, d_hits, nHits, acc, res, off, out);
     ctx->launches += 2;
     cudaEventRecord(ctx->ev[EV_RS_END], s);

@@ -146,3 +146,52 @@ def test_fused_iteration_matches_golden_chain(case, golden_root, ctx):
         assert_same_entries(got.entries_by_key(), golden.entries_by_key(), "%s/%s fused" % (case, s["dbs"][2]))
         t = ctx.timings()
         assert t["kernel_launches"] > 0 and t["n_hits"] == len(hits)
+
+
+@pytest.mark.parametrize("case,world", [("synth_aa", 2), ("synth_aa", 4), ("synth_nt", 2)])
+def test_sharded_iteration_equals_single_gpu(case, world, golden_root, ctx):
+    """The multi-GPU decomposition (k-mer hash shards -> all-to-all of pair records -> owner-local sort #2,
+    rescoring and extension), emulated rank by rank on one GPU: the union of the ranks' results must equal the
+    unsharded run (and therefore the reference)."""
+    import torch
+    from plass_b200 import sharded
+    d, man = golden_case(case, golden_root)
+    s = [x for x in man["steps"] if x["cmd"] == "kmermatcher"][0]
+    rs = [x for x in man["steps"] if x["cmd"] == "rescorediagonal"][0]
+    ex = [x for x in man["steps"] if x["cmd"] in ("assembleresults", "nuclassembleresults")][0]
+    seq = mmseqsdb.read_db(os.path.join(d, s["dbs"][0]))
+    nucl = seq.dbtype == 1
+    kp, rp, ep = gpu_km(s["args"], nucl), api.RsParams(**params.rs_fields(rs["args"])), api.ExParams(**params.ex_fields(ex["args"]))
+    ddb = ctx.upload(seq)
+    ref_out, ref_hits, ref_alns = ctx.assemble_iteration(ddb, kp, rp, ep, want_intermediates=True)
+    ref_db = ref_out.download()
+    ref_out.free()
+    sends, counts = [], []
+    for r in range(world):
+        c = ctx.shard_pairs(ddb, sharded.shard_km_params(kp, r, world), world)
+        t = torch.empty(max(sum(c), 1) * 16, dtype=torch.uint8, device="cuda")
+        ctx.shard_export(t.data_ptr(), sum(c))
+        sends.append(t); counts.append(c)
+    all_hits, all_alns, entries = [], [], {}
+    for dst in range(world):
+        parts = []
+        for src in range(world):
+            off = sum(counts[src][:dst]) * 16
+            parts.append(sends[src][off: off + counts[src][dst] * 16])
+        recv = torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device="cuda")
+        n = recv.numel() // 16
+        if n == 0:
+            recv = torch.empty(16, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        out, hits, alns = ctx.shard_finish(ddb, recv.data_ptr(), n, sharded.owner_range(ddb.max_key, dst, world), rp, ep, want_intermediates=True)
+        got = out.download()
+        out.free()
+        all_hits.append(hits.copy()); all_alns.append(alns.copy())
+        e = got.entries_by_key()
+        assert not (set(e) & set(entries))
+        entries.update(e)
+    ddb.free()
+    hits, alns = np.concatenate(all_hits), np.concatenate(all_alns)
+    assert len(hits) == len(ref_hits) and all(np.array_equal(hits[f], ref_hits[f]) for f in ("rep", "target", "score", "diag"))
+    check_alns(alns, ref_alns, "%s sharded x%d" % (case, world))
+    assert_same_entries(entries, ref_db.entries_by_key(), "%s sharded x%d output DB" % (case, world))
