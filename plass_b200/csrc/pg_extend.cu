@@ -148,22 +148,32 @@ __device__ __forceinline__ unsigned char target_at(const char *t, unsigned tLen,
     return rev ? c_ex_revN[(unsigned char) t[tLen - 1 - i]] : (unsigned char) t[i];
 }
 
-// ungappedAlignmentByDiagonal (mode 3) + updateAlignment (assembleresult.cpp:70-108) against the rope
-__device__ void rescore_parked(ExRes &r, const Rope &q, const char *t, unsigned tLen, unsigned tRev, int diag, int alph) {
+// ungappedAlignmentByDiagonal (mode 3) + updateAlignment (assembleresult.cpp:70-108) against the rope,
+// executed by a full warp for ONE parked alignment (lanes stride the diagonal).
+__device__ void rescore_parked_warp(ExRes &r, const Rope &q, const char *t, unsigned tLen, unsigned tRev, int diag, int alph,
+                                    const unsigned char *sA2n, const signed char *sMat) {
+    const unsigned lane = threadIdx.x & 31;
     const unsigned qLen = q.len;
     const unsigned dist = (unsigned) abs(diag);
     int start = -1, end = -1; unsigned score = 0, diagLen = 0;
     unsigned qOff = 0, tOff = 0, len = 0; bool valid = false;
     if (diag >= 0 && dist < qLen) { len = min(tLen, qLen - dist); qOff = dist; valid = true; }
     else if (diag < 0 && dist < tLen) { len = min(tLen - dist, qLen); tOff = dist; valid = true; }
+    int idCnt = 0;
     if (valid && len > 0) {
         diagLen = len;
         const unsigned first = (q.at(qOff) == '*' || target_at(t, tLen, tRev, tOff) == '*') ? 1u : 0u;
         unsigned last = len - 1;
         if (last > 0 && (q.at(qOff + len - 1) == '*' || target_at(t, tLen, tRev, tOff + len - 1) == '*')) last--;
         long long sum = 0;
-        for (unsigned pos = first; pos <= last; pos++)
-            sum += c_ex_mat[c_ex_a2n[q.at(qOff + pos)] * alph + c_ex_a2n[target_at(t, tLen, tRev, tOff + pos)]];
+        // score over [first, last]; identities over [qS, qE) = positions [first, last)  (updateAlignment's exclusive end)
+        for (unsigned pos = first + lane; pos <= last; pos += 32) {
+            const unsigned char a = q.at(qOff + pos), b = target_at(t, tLen, tRev, tOff + pos);
+            sum += sMat[sA2n[a] * alph + sA2n[b]];
+            if (pos < last) idCnt += (a == b) ? 1 : 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o); idCnt += __shfl_xor_sync(0xFFFFFFFFu, idCnt, o); }
         if (sum < 0) sum = 0;
         start = (int) first; end = (int) last; score = (unsigned) sum;
     }
@@ -171,8 +181,7 @@ __device__ void rescore_parked(ExRes &r, const Rope &q, const char *t, unsigned 
     int qS, qE, dS, dE;
     if (diag >= 0) { qS = start + d2; qE = end + d2; dS = start; dE = end; }
     else { qS = start; qE = end; dS = start + d2; dE = end + d2; }
-    int idCnt = 0;
-    for (int i = qS; i < qE; i++) idCnt += (q.at((unsigned) i) == target_at(t, tLen, tRev, (unsigned) (dS + (i - qS)))) ? 1 : 0;
+    if (!(valid && len > 0)) idCnt = 0;     // start = end = -1: the reference's loop over [qS, qE) is empty
     r.seqId = __fdiv_rn((float) idCnt, __fsub_rn((float) qE, (float) qS));
     r.qLen = qLen; r.dbLen = tLen;
     r.alnLength = diagLen;
@@ -188,8 +197,20 @@ __device__ __forceinline__ float seqid_text_roundtrip(float seqId) {
     return (float) ((double) n / 1000.0);
 }
 
+// per-query state carried between the rounds of the wavefront
+struct ExState {
+    long long hsize;
+    unsigned leftOff, rightOff;     // of the round that just ended (needed to re-score its parked hits)
+    int nPark;
+    int ropeN;
+    unsigned ropeLen;
+    unsigned querySeqLen;
+    unsigned couldExtend;
+};
+
 __global__ void aln_ranges_kernel(const pg_seqdb db, const pg_aln *__restrict__ alns, unsigned long long nAlns,
-                                  unsigned long long *__restrict__ alnStart, unsigned *__restrict__ alnCount) {
+                                  unsigned long long *__restrict__ alnStart, unsigned *__restrict__ alnCount,
+                                  unsigned *__restrict__ activeList, unsigned *__restrict__ activeCount) {
     const unsigned long long j = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nAlns) return;
     const unsigned qk = alns[j].query;
@@ -199,68 +220,91 @@ __global__ void aln_ranges_kernel(const pg_seqdb db, const pg_aln *__restrict__ 
     const unsigned qi = find_id(db.keys, (unsigned) db.n, qk);
     alnStart[qi] = j;
     alnCount[qi] = (unsigned) (k - j);
+    if (k - j >= 2) activeList[atomicAdd(activeCount, 1u)] = qi;   // only the self alignment: nothing can be popped for extension
 }
 
-__global__ void __launch_bounds__(128) extend_kernel(const pg_seqdb db, const pg_aln *__restrict__ alns,
-                                                     const unsigned long long *__restrict__ alnStart, const unsigned *__restrict__ alnCount,
-                                                     const ExConst c, ExRes *__restrict__ heapBuf, ExRes *__restrict__ parkBuf,
-                                                     ExSeg *__restrict__ segBuf, unsigned *__restrict__ segCount,
-                                                     unsigned *__restrict__ outLen /* entry length incl. "\n\0" */,
-                                                     unsigned char *__restrict__ extended, unsigned char *__restrict__ used) {
-    const unsigned qi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi >= db.n) return;
+__global__ void init_out_kernel(const pg_seqdb db, unsigned *__restrict__ outLen) {
+    const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < db.n) outLen[i] = db.lens[i];
+}
+
+// One round of the reference's outer `while (!alnQueue.empty())` loop for every query of `list`:
+// (first round) fill the queue, or (later rounds) push the re-scored parked hits that still pass --min-seq-id;
+// then pop / extend / park until the queue is empty (assembleresult.cpp:193-289).  Queries whose parked hits
+// must be re-scored append them to `work` and themselves to `nextList`; the others are finished.
+__global__ void __launch_bounds__(128) extend_round_kernel(const pg_seqdb db, const pg_aln *__restrict__ alns,
+                                                           const unsigned long long *__restrict__ alnStart, const unsigned *__restrict__ alnCount,
+                                                           const ExConst c, int firstRound,
+                                                           const unsigned *__restrict__ list, const unsigned *__restrict__ listCount,
+                                                           unsigned *__restrict__ nextList, unsigned *__restrict__ nextCount,
+                                                           uint2 *__restrict__ work, unsigned long long *__restrict__ workCount,
+                                                           ExState *__restrict__ states, ExRes *__restrict__ heapBuf, ExRes *__restrict__ parkBuf,
+                                                           ExSeg *__restrict__ segBuf, unsigned *__restrict__ segCount,
+                                                           unsigned *__restrict__ outLen, unsigned char *__restrict__ extended,
+                                                           unsigned char *__restrict__ used) {
+    const unsigned li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= *listCount) return;
+    const unsigned qi = list[li];
     const unsigned nAl = alnCount[qi];
-    const unsigned entryLen = db.lens[qi];
-    outLen[qi] = entryLen;
-    extended[qi] = 0;
-    segCount[qi] = 0;
-    if (nAl < 2) return;                 // only the self alignment: nothing can be popped for extension
     const unsigned long long a0 = alnStart[qi];
     ExRes *heap = heapBuf + a0;
     ExRes *park = parkBuf + a0;
     ExSeg *segs = segBuf + a0 + qi;      // capacity nAl + 1
     const unsigned queryKey = db.keys[qi];
-    unsigned querySeqLen = entryLen - 2;
+    ExState st;
     Rope rope; rope.segs = segs; rope.db = &db;
-    segs[0].src = qi; segs[0].start = 0; segs[0].len = querySeqLen; segs[0].rev = 0;
-    rope.n = 1; rope.len = querySeqLen;
-    bool couldExtend = false;
     long hsize = 0;
-    // fill the queue (assembleresult.cpp:159-188 / nuclassembleresult.cpp:197-226)
-    for (unsigned i = 0; i < nAl; i++) {
-        const pg_aln a = alns[a0 + i];
-        ExRes r;
-        r.dbKey = a.target;
-        r.seqId = seqid_text_roundtrip(a.seq_id);
-        r.qStartPos = a.q_start; r.qEndPos = a.q_end; r.qLen = (unsigned) a.q_len;
-        r.dbStartPos = a.db_start; r.dbEndPos = a.db_end; r.dbLen = (unsigned) a.db_len;
-        const int adjQ = (r.qStartPos == -1) ? 0 : r.qStartPos;
-        const int adjD = (r.dbStartPos == -1) ? 0 : r.dbStartPos;
-        r.alnLength = (unsigned) (max(abs(r.qEndPos - adjQ), abs(r.dbEndPos - adjD)) + 1);   // Matcher.cpp:201-203
-        const int rawScore = (int) (((c.logK + (double) a.bits * log(2.0)) / c.lambda) + 0.5);
-        const float scorePerCol = __fdiv_rn((float) rawScore, (float) ((double) r.alnLength + 0.5));
-        if (!c.nt) {
-            const float alnLen = (float) r.alnLength;
-            const float ids = __fmul_rn(r.seqId, alnLen);
-            r.seqId = (float) ((double) ids / ((double) alnLen + 0.5));
-        }
-        r.score = (int) __fmul_rn(scorePerCol, 100.0f);
-        r.rev = 0;
-        if (c.nt) {
-            if (r.qStartPos > r.qEndPos) {
-                r.rev = 1;
-                const int t = r.qStartPos; r.qStartPos = r.qEndPos; r.qEndPos = t;
-                const unsigned dbStartPos = (unsigned) r.dbStartPos;
-                r.dbStartPos = (int) (r.dbLen - (unsigned) r.dbEndPos - 1u);
-                r.dbEndPos = (int) (r.dbLen - dbStartPos - 1u);
+    if (firstRound) {
+        st.querySeqLen = db.lens[qi] - 2;
+        segs[0].src = qi; segs[0].start = 0; segs[0].len = st.querySeqLen; segs[0].rev = 0;
+        rope.n = 1; rope.len = st.querySeqLen;
+        st.couldExtend = 0;
+        // fill the queue (assembleresult.cpp:159-188 / nuclassembleresult.cpp:197-226)
+        for (unsigned i = 0; i < nAl; i++) {
+            const pg_aln a = alns[a0 + i];
+            ExRes r;
+            r.dbKey = a.target;
+            r.seqId = seqid_text_roundtrip(a.seq_id);
+            r.qStartPos = a.q_start; r.qEndPos = a.q_end; r.qLen = (unsigned) a.q_len;
+            r.dbStartPos = a.db_start; r.dbEndPos = a.db_end; r.dbLen = (unsigned) a.db_len;
+            const int adjQ = (r.qStartPos == -1) ? 0 : r.qStartPos;
+            const int adjD = (r.dbStartPos == -1) ? 0 : r.dbStartPos;
+            r.alnLength = (unsigned) (max(abs(r.qEndPos - adjQ), abs(r.dbEndPos - adjD)) + 1);   // Matcher.cpp:201-203
+            const int rawScore = (int) (((c.logK + (double) a.bits * log(2.0)) / c.lambda) + 0.5);
+            const float scorePerCol = __fdiv_rn((float) rawScore, (float) ((double) r.alnLength + 0.5));
+            if (!c.nt) {
+                const float alnLen = (float) r.alnLength;
+                const float ids = __fmul_rn(r.seqId, alnLen);
+                r.seqId = (float) ((double) ids / ((double) alnLen + 0.5));
             }
+            r.score = (int) __fmul_rn(scorePerCol, 100.0f);
+            r.rev = 0;
+            if (c.nt) {
+                if (r.qStartPos > r.qEndPos) {
+                    r.rev = 1;
+                    const int t = r.qStartPos; r.qStartPos = r.qEndPos; r.qEndPos = t;
+                    const unsigned dbStartPos = (unsigned) r.dbStartPos;
+                    r.dbStartPos = (int) (r.dbLen - (unsigned) r.dbEndPos - 1u);
+                    r.dbEndPos = (int) (r.dbLen - dbStartPos - 1u);
+                }
+            }
+            heap_push(heap, hsize, r, c);
         }
-        heap_push(heap, hsize, r, c);
+    } else {
+        st = states[qi];
+        rope.n = st.ropeN; rope.len = st.ropeLen;
+        st.querySeqLen = rope.len;                               // querySeqLen = query.length() (assembleresult.cpp:291)
+        // refill the queue with the re-scored parked hits (assembleresult.cpp:309-311), in parked order
+        for (int ai = 0; ai < st.nPark; ai++) {
+            const ExRes r = park[ai];
+            if (r.seqId >= c.seqIdThr) heap_push(heap, hsize, r, c);
+        }
     }
-    while (hsize > 0) {
+    const unsigned querySeqLen = st.querySeqLen;
+    bool finished = true;
+    if (hsize > 0) {
         unsigned leftOff = 0, rightOff = 0;
         int nPark = 0;
-        bool brokeOut = false;
         while (true) {
             // selectFragmentToExtend (assembleresult.cpp:40-57)
             bool got = false;
@@ -287,7 +331,7 @@ __global__ void __launch_bounds__(128) extend_kernel(const pg_seqdb db, const pg
             if (dbStartPos == 0 && qEndPos == (querySeqLen - 1)) {            // right extension
                 if (rightOff > 0) { park[nPark++] = best; continue; }
                 const unsigned fragLen = targetSeqLen - (dbEndPos + 1);
-                if (c.nt && (unsigned long long) rope.len + fragLen >= (unsigned long long) c.maxSeqLen) { brokeOut = true; break; }
+                if (c.nt && (unsigned long long) rope.len + fragLen >= (unsigned long long) c.maxSeqLen) break;   // nucl only (:271-275)
                 ExSeg g; g.src = targetId; g.len = fragLen; g.rev = best.rev;
                 g.start = best.rev ? 0u : dbEndPos + 1;                       // reversed: rev(target[0, fragLen))
                 segs[rope.n++] = g;
@@ -297,7 +341,7 @@ __global__ void __launch_bounds__(128) extend_kernel(const pg_seqdb db, const pg
             } else if (qStartPos == 0 && dbEndPos == (targetSeqLen - 1)) {    // left extension
                 if (leftOff > 0) { park[nPark++] = best; continue; }
                 const unsigned fragLen = dbStartPos;
-                if ((unsigned long long) rope.len + fragLen >= (unsigned long long) c.maxSeqLen) { brokeOut = true; break; }
+                if ((unsigned long long) rope.len + fragLen >= (unsigned long long) c.maxSeqLen) break;
                 ExSeg g; g.src = targetId; g.len = fragLen; g.rev = best.rev;
                 g.start = best.rev ? (targetSeqLen - dbStartPos) : 0u;        // reversed: rev(target[tLen-dbStart, tLen))
                 for (int s = rope.n; s > 0; s--) segs[s] = segs[s - 1];
@@ -308,24 +352,52 @@ __global__ void __launch_bounds__(128) extend_kernel(const pg_seqdb db, const pg
                 used[targetId] = 1;
             }
         }
-        (void) brokeOut;
-        if (leftOff > 0 || rightOff > 0) couldExtend = true;
-        if (hsize > 0) break;
-        querySeqLen = rope.len;
-        for (int ai = 0; ai < nPark; ai++) {
-            ExRes r = park[ai];
-            const unsigned tId = find_id(db.keys, (unsigned) db.n, r.dbKey);
-            const unsigned tSeqLen = db.lens[tId] - 2;
-            const char *tSeq = db.data + db.offsets[tId];
-            const int diag = (int) ((unsigned) r.qStartPos + leftOff) - r.dbStartPos;
-            rescore_parked(r, rope, tSeq, tSeqLen, r.rev, diag, c.alph);
-            if (r.seqId >= c.seqIdThr) heap_push(heap, hsize, r, c);
+        if (leftOff > 0 || rightOff > 0) st.couldExtend = 1;
+        // `if (!alnQueue.empty()) break;` ends the query; otherwise the parked hits are re-scored on the new contig
+        if (hsize == 0 && nPark > 0) {
+            finished = false;
+            st.hsize = 0; st.leftOff = leftOff; st.rightOff = rightOff; st.nPark = nPark;
+            st.ropeN = rope.n; st.ropeLen = rope.len;
+            states[qi] = st;
+            const unsigned long long w0 = atomicAdd(workCount, (unsigned long long) nPark);
+            for (int i = 0; i < nPark; i++) work[w0 + i] = make_uint2(qi, (unsigned) i);
+            nextList[atomicAdd(nextCount, 1u)] = qi;
         }
     }
-    if (couldExtend) {
+    if (finished && st.couldExtend) {
         extended[qi] = 1;
         outLen[qi] = rope.len + 2;
         segCount[qi] = (unsigned) rope.n;
+    }
+}
+
+// warp per parked alignment: re-score it on the extended contig (assembleresult.cpp:293-307)
+__global__ void __launch_bounds__(256) extend_rescore_kernel(const pg_seqdb db, const unsigned long long *__restrict__ alnStart,
+                                                             const ExConst c, const uint2 *__restrict__ work,
+                                                             const unsigned long long *__restrict__ workCount,
+                                                             const ExState *__restrict__ states, ExRes *__restrict__ parkBuf,
+                                                             ExSeg *__restrict__ segBuf) {
+    __shared__ unsigned char sA2n[256];
+    __shared__ signed char sMat[21 * 21];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sA2n[i] = c_ex_a2n[i];
+    for (int i = threadIdx.x; i < 21 * 21; i += blockDim.x) sMat[i] = c_ex_mat[i];
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long nWork = *workCount;
+    const unsigned long long warpsTotal = (unsigned long long) gridDim.x * (blockDim.x >> 5);
+    for (unsigned long long wi = (unsigned long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < nWork; wi += warpsTotal) {
+        const uint2 it = work[wi];
+        const unsigned qi = it.x;
+        const unsigned long long a0 = alnStart[qi];
+        const ExState st = states[qi];
+        Rope rope; rope.segs = segBuf + a0 + qi; rope.db = &db; rope.n = st.ropeN; rope.len = st.ropeLen;
+        ExRes r = parkBuf[a0 + it.y];
+        const unsigned tId = find_id(db.keys, (unsigned) db.n, r.dbKey);
+        const unsigned tSeqLen = db.lens[tId] - 2;
+        const char *tSeq = db.data + db.offsets[tId];
+        const int diag = (int) ((unsigned) r.qStartPos + st.leftOff) - r.dbStartPos;
+        rescore_parked_warp(r, rope, tSeq, tSeqLen, r.rev, diag, c.alph, sA2n, sMat);
+        if (lane == 0) parkBuf[a0 + it.y] = r;
     }
 }
 
@@ -442,11 +514,42 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     PG_TRY(ctx->exSegs.reserve(sizeof(ExSeg) * (nAlns + n + 1)));
     ExRes *heapBuf = ctx->exWork.as<ExRes>();
     ExRes *parkBuf = heapBuf + (nAlns + 1);
-    if (nAlns) aln_ranges_kernel<<<(unsigned) ((nAlns + 255) / 256), 256, 0, s>>>(*db, d_alns, nAlns, alnStart, alnCount);
-    extend_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(*db, d_alns, alnStart, alnCount, c, heapBuf, parkBuf,
-                                                              ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
+    // work lists of the wavefront
+    PG_TRY(ctx->exLists.reserve(sizeof(unsigned) * 2 * (n + 1) + sizeof(uint2) * (nAlns + 1) + sizeof(ExState) * (n + 1) + 256));
+    unsigned char *lb = ctx->exLists.as<unsigned char>();
+    ExState *states = (ExState *) lb;
+    uint2 *work = (uint2 *) (lb + ((sizeof(ExState) * (n + 1) + 15) & ~(size_t) 15));
+    unsigned *listA = (unsigned *) ((unsigned char *) work + ((sizeof(uint2) * (nAlns + 1) + 15) & ~(size_t) 15));
+    unsigned *listB = listA + (n + 1);
+    unsigned long long *d_cnt = ctx->small.as<unsigned long long>() + 24;   // [24] work count, [25] list counts (2 x u32)
+    unsigned *d_listCnt = (unsigned *) (d_cnt + 1);
+    PG_CUDA(cudaMemsetAsync(d_cnt, 0, 16, s));
+    init_out_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(*db, outLen);
+    if (nAlns) aln_ranges_kernel<<<(unsigned) ((nAlns + 255) / 256), 256, 0, s>>>(*db, d_alns, nAlns, alnStart, alnCount, listA, d_listCnt);
+    ctx->launches += 2;
+    unsigned hCnt[2] = {0, 0};
+    PG_CUDA(cudaMemcpyAsync(hCnt, d_listCnt, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    PG_CUDA(cudaStreamSynchronize(s));
+    unsigned active = hCnt[0];
+    unsigned *cur = listA, *nxt = listB;
+    int curIdx = 0;
+    for (int round = 0; active > 0; round++) {
+        PG_CHECK(round < 100000, "assembleresults: extension did not converge");
+        PG_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
+        PG_CUDA(cudaMemsetAsync(d_listCnt + (1 - curIdx), 0, sizeof(unsigned), s));
+        extend_round_kernel<<<(active + 127) / 128, 128, 0, s>>>(*db, d_alns, alnStart, alnCount, c, round == 0, cur, d_listCnt + curIdx,
+                                                                nxt, d_listCnt + (1 - curIdx), work, d_cnt, states, heapBuf, parkBuf,
+                                                                ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
+        extend_rescore_kernel<<<NUM_SMS * 8, 256, 0, s>>>(*db, alnStart, c, work, d_cnt, states, parkBuf, ctx->exSegs.as<ExSeg>());
+        ctx->launches += 2;
+        PG_CUDA(cudaMemcpyAsync(hCnt, d_listCnt + (1 - curIdx), sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+        PG_CUDA(cudaStreamSynchronize(s));
+        active = hCnt[0];
+        unsigned *t = cur; cur = nxt; nxt = t;
+        curIdx = 1 - curIdx;
+    }
     keep_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(n, c.keepTarget, ext, used, keep, outLen, db->keys, ctx->ownLo, ctx->ownHi);
-    ctx->launches += 3;
+    ctx->launches += 1;
     unsigned long long *d_tot = ctx->small.as<unsigned long long>() + 5;   // [5] bytes, [6] kept
     PG_TRY(exclusive_scan_u32(outLen, outOff, n, d_tot, scanWs, scan_workspace_bytes(n), s, &ctx->launches));
     PG_TRY(exclusive_scan_u32(keep, keepIdx, n, d_tot + 1, scanWs, scan_workspace_bytes(n), s, &ctx->launches));

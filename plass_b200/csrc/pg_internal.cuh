@@ -17,7 +17,7 @@ struct pg_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[pg::EV_COUNT];
-    pg::DevBuf small, lists, recA, recB, radixWs, scratch, blockCounts, hits, alnAll, alns, flags, exWork, exSegs, exMeta, ntTab;
+    pg::DevBuf small, lists, recA, recB, radixWs, scratch, blockCounts, hits, alnAll, alns, flags, exWork, exSegs, exMeta, exLists, ntTab;
     unsigned ntTabN = 0;
     bool pairsInA = false;
     bool kmRan = false, rsRan = false, exRan = false;

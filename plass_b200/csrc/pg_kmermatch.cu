@@ -141,6 +141,59 @@ __global__ void classify_kernel(const unsigned *__restrict__ lens, unsigned n, i
 // ------------------------------------------------------------------------------------------------
 // extract: one warp per sequence, at most NMAX k-mer windows.
 // ------------------------------------------------------------------------------------------------
+// Sort key of a k-mer inside one sequence, packed so that (hi, lo) lexicographic == (score, k-mer[|bit63], pos)
+// of SequencePosition::compareByScore[Reverse]:  hi = score<<48 | kmer62..15,  lo = kmer14..0<<33 | pos<<1 | strand.
+struct __align__(16) PCand { unsigned long long hi, lo; };
+__device__ __forceinline__ PCand pack_cand(const Cand &c) {
+    const unsigned long long k63 = c.kmer & ~(1ULL << 63);
+    PCand p;
+    p.hi = ((unsigned long long) c.score << 48) | (k63 >> 15);
+    p.lo = ((k63 & 0x7FFFULL) << 33) | ((unsigned long long) c.pos << 1) | (c.kmer >> 63);
+    return p;
+}
+__device__ __forceinline__ unsigned pc_score(const PCand &p) { return (unsigned) (p.hi >> 48); }
+__device__ __forceinline__ unsigned long long pc_kmer63(const PCand &p) { return ((p.hi & 0xFFFFFFFFFFFFULL) << 15) | ((p.lo >> 33) & 0x7FFFULL); }
+__device__ __forceinline__ unsigned long long pc_kmer_stored(const PCand &p, int nt) { return nt ? (pc_kmer63(p) | ((p.lo & 1ULL) << 63)) : pc_kmer63(p); }
+__device__ __forceinline__ unsigned pc_pos(const PCand &p) { return (unsigned) ((p.lo >> 1) & 0xFFFFFFFFULL); }
+__device__ __forceinline__ bool pc_less(const PCand &a, const PCand &b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+__device__ __forceinline__ bool pc_same_kmer(const PCand &a, const PCand &b) { return ((a.hi ^ b.hi) & 0xFFFFFFFFFFFFULL) == 0 && ((a.lo ^ b.lo) >> 33) == 0; }
+
+// The selection loop of kmermatcher.cpp:274-347 over packed candidates (slow path: duplicates present).
+__device__ int select_sequential_packed(const PCand *sorted, int cnt, unsigned long long kmerConsidered, unsigned threshold, int tooMuch,
+                                        const KmConst &c, unsigned id, unsigned seqLen, Rec *outRecs) {
+    int nOut = 0;
+    unsigned long long selected = 0;
+    for (int i = 0; i < cnt && selected < kmerConsidered; i++) {
+        if (c.ignoreMulti) {
+            if (i + 1 < cnt && pc_same_kmer(sorted[i], sorted[i + 1])) {
+                const PCand cur = sorted[i];
+                bool same = true;
+                while (same && i < cnt) {
+                    i++;
+                    if (i >= cnt) break;
+                    same = pc_same_kmer(cur, sorted[i]);
+                }
+            }
+            if (i >= cnt) break;
+        }
+        const unsigned sc = pc_score(sorted[i]);
+        if (sc < threshold) {
+            if (sc == (threshold - 1) && tooMuch) {
+                tooMuch--;
+                threshold -= (tooMuch == 0) ? 1 : 0;
+            }
+            selected++;
+            if (sc >= c.hashStart && sc <= c.hashEnd) {
+                Rec r;
+                r.w0 = pc_kmer_stored(sorted[i], c.nt);
+                r.w1 = ((unsigned long long) id << 32) | ((unsigned long long) (seqLen & 0xFFFFu) << 16) | (pc_pos(sorted[i]) & 0xFFFFu);
+                outRecs[nOut++] = r;
+            }
+        }
+    }
+    return nOut;
+}
+
 template <int NMAX>
 __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, const unsigned *__restrict__ list,
                                                            const unsigned *__restrict__ listCount, const KmConst c,
@@ -150,9 +203,10 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
     constexpr int WARPS = 4;
     constexpr int CODES = NMAX + 40;   // k <= 32
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    Cand *cand = reinterpret_cast<Cand *>(smem_raw) + (size_t) w * NMAX;
-    Rec *outRecs = reinterpret_cast<Rec *>(smem_raw + (size_t) WARPS * NMAX * sizeof(Cand)) + (size_t) w * (NMAX + 1);
-    unsigned char *codes = smem_raw + (size_t) WARPS * NMAX * sizeof(Cand) + (size_t) WARPS * (NMAX + 1) * sizeof(Rec) + (size_t) w * CODES;
+    const unsigned ltMask = (1u << lane) - 1u;
+    PCand *cand = reinterpret_cast<PCand *>(smem_raw) + (size_t) w * NMAX;
+    Rec *outRecs = reinterpret_cast<Rec *>(smem_raw + (size_t) WARPS * NMAX * sizeof(PCand)) + (size_t) w * (NMAX + 1);
+    unsigned char *codes = smem_raw + (size_t) WARPS * NMAX * sizeof(PCand) + (size_t) WARPS * (NMAX + 1) * sizeof(Rec) + (size_t) w * CODES;
 
     const unsigned nList = *listCount;
     for (unsigned li = blockIdx.x * WARPS + w; li < nList; li += gridDim.x * WARPS) {
@@ -170,20 +224,21 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
         for (int o = 16; o > 0; o >>= 1) L = min(L, __shfl_xor_sync(0xFFFFFFFFu, L, o));
         __syncwarp();
         const unsigned id = db.keys[si];
-        // whole-sequence hash: Util::hash (poly 31) then XXH64 (kmermatcher.cpp:133-138)
+        // whole-sequence hash: Util::hash (poly 31) then XXH64 (kmermatcher.cpp:133-138).  Each lane hashes a
+        // chunk; H(AB) = H(A) * 31^|B| + H(B) is associative, so the chunks fold in log2(32) shuffle steps.
         unsigned long long seqHash;
         {
             const int chunk = (L + 31) / 32;
-            const int b = lane * chunk, e = min(L, b + chunk);
+            const int b = min(L, lane * chunk), e = min(L, b + chunk);
             unsigned long long h = 0, pw = 1;
             for (int i = b; i < e; i++) { h = h * 31ULL + codes[i]; pw *= 31ULL; }
-            unsigned long long acc = 0;
-            for (int l = 0; l < 32; l++) {
-                const unsigned long long hl = __shfl_sync(0xFFFFFFFFu, h, l);
-                const unsigned long long pl = __shfl_sync(0xFFFFFFFFu, pw, l);
-                acc = acc * pl + hl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long hr = __shfl_down_sync(0xFFFFFFFFu, h, o);
+                const unsigned long long pr = __shfl_down_sync(0xFFFFFFFFu, pw, o);
+                if ((lane & (2 * o - 1)) == 0) { h = h * pr + hr; pw *= pr; }
             }
-            seqHash = xxh64_u64(acc, c.seed);
+            seqHash = xxh64_u64(__shfl_sync(0xFFFFFFFFu, h, 0), c.seed);
         }
         // all k-mer windows, compacted in position order
         int cnt = 0;
@@ -193,12 +248,12 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
             Cand cd;
             const bool ok = (pos < nWin) && make_kmer(codes, pos, L, c, cd);
             const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
-            if (ok) cand[cnt + __popc(m & ((1u << lane) - 1u))] = cd;
+            if (ok) cand[cnt + __popc(m & ltMask)] = pack_cand(cd);
             cnt += __popc(m);
         }
         int n2 = 1;
         while (n2 < cnt) n2 <<= 1;
-        for (int i = cnt + lane; i < n2; i += 32) { cand[i].score = 0xFFFFFFFFu; cand[i].kmer = ~0ULL; cand[i].pos = 0xFFFFFFFFu; }
+        for (int i = cnt + lane; i < n2; i += 32) { cand[i].hi = ~0ULL; cand[i].lo = ~0ULL; }
         __syncwarp();
         // bitonic sort by (score, kmer, pos)   [std::sort at kmermatcher.cpp:266-272; total order => same result]
         if (c.ignoreMulti) {
@@ -208,8 +263,8 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
                         const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                         const int ix = i | j;
                         const bool up = ((i & kk) == 0);
-                        const Cand a = cand[i], b = cand[ix];
-                        if (cand_less(b, a, c.nt) == up) { cand[i] = b; cand[ix] = a; }
+                        const PCand a = cand[i], b = cand[ix];
+                        if (pc_less(b, a) == up) { cand[i] = b; cand[ix] = a; }
                     }
                     __syncwarp();
                 }
@@ -219,39 +274,69 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
         const unsigned long long want = (unsigned long long) ((float) (c.kmersPerSeq - 1) + (c.scale * (float) L));
         const unsigned long long kmerConsidered = min(want, (unsigned long long) cnt);
         int nOut = 0;
-        if (lane == 0) {
-            // sequence-identity record first (:241-246)
-            const unsigned sh16 = (unsigned) (seqHash & 0xFFFFULL);
-            if (sh16 >= c.hashStart && sh16 <= c.hashEnd) {
-                Rec r; r.w0 = seqHash; r.w1 = ((unsigned long long) id << 32) | ((unsigned long long) (L & 0xFFFF) << 16);
-                outRecs[nOut++] = r;
-            }
-            if (cnt > 0 && kmerConsidered > 0) {
-                unsigned threshold; int tooMuch;
-                if (c.ignoreMulti) {
-                    const unsigned t = cand[kmerConsidered - 1].score;
-                    int inBins = (int) kmerConsidered;
-                    while (inBins < cnt && cand[inBins].score == t) inBins++;
-                    threshold = t + 1;
-                    tooMuch = inBins - (int) kmerConsidered;
+        // sequence-identity record first (:241-246)
+        const unsigned sh16 = (unsigned) (seqHash & 0xFFFFULL);
+        if (sh16 >= c.hashStart && sh16 <= c.hashEnd) {
+            if (lane == 0) { Rec r; r.w0 = seqHash; r.w1 = ((unsigned long long) id << 32) | ((unsigned long long) (L & 0xFFFF) << 16); outRecs[0] = r; }
+            nOut = 1;
+        }
+        if (cnt > 0 && kmerConsidered > 0) {
+            if (c.ignoreMulti) {
+                // t = score of the kmerConsidered-th smallest; candidates = scores <= t; ties of the last bin = tooMuch
+                const unsigned t = pc_score(cand[kmerConsidered - 1]);
+                int below = 0, inBins = 0, dups = 0;
+                for (int p0 = 0; p0 < cnt; p0 += 32) {
+                    const int i = p0 + lane;
+                    const bool in = i < cnt;
+                    const unsigned sc = in ? pc_score(cand[i]) : 0xFFFFFFFFu;
+                    below += __popc(__ballot_sync(0xFFFFFFFFu, in && sc < t));
+                    inBins += __popc(__ballot_sync(0xFFFFFFFFu, in && sc <= t));
+                    dups += __popc(__ballot_sync(0xFFFFFFFFu, in && i + 1 < cnt && pc_same_kmer(cand[i], cand[i + 1])));
+                }
+                const unsigned threshold = t + 1;
+                const int tooMuch = inBins - (int) kmerConsidered;
+                if (dups == 0) {
+                    // no repeated k-mer: every candidate is visited, so the loop selects the elements below the last
+                    // bin and then the first `tooMuch` (all, if tooMuch == 0) of the last bin, capped at kmerConsidered
+                    const int lastBin = inBins - below;
+                    int nSel = below + (tooMuch > 0 ? min(tooMuch, lastBin) : lastBin);
+                    if ((unsigned long long) nSel > kmerConsidered) nSel = (int) kmerConsidered;
+                    for (int p0 = 0; p0 < nSel; p0 += 32) {
+                        const int i = p0 + lane;
+                        bool emit = false; PCand pc; pc.hi = 0; pc.lo = 0;
+                        if (i < nSel) { pc = cand[i]; const unsigned sc = pc_score(pc); emit = sc >= c.hashStart && sc <= c.hashEnd; }
+                        const unsigned m = __ballot_sync(0xFFFFFFFFu, emit);
+                        if (emit) {
+                            Rec r;
+                            r.w0 = pc_kmer_stored(pc, c.nt);
+                            r.w1 = ((unsigned long long) id << 32) | ((unsigned long long) (L & 0xFFFF) << 16) | (pc_pos(pc) & 0xFFFFu);
+                            outRecs[nOut + __popc(m & ltMask)] = r;
+                        }
+                        nOut += __popc(m);
+                    }
                 } else {
-                    // positional order kept: find the kmerConsidered-th smallest score by counting
+                    int add = 0;
+                    if (lane == 0) add = select_sequential_packed(cand, cnt, kmerConsidered, threshold, tooMuch, c, id, (unsigned) L, outRecs + nOut);
+                    nOut += __shfl_sync(0xFFFFFFFFu, add, 0);
+                }
+            } else {
+                // positional order kept (--ignore-multi-kmer 0): the kmerConsidered-th smallest score by counting
+                int add = 0;
+                if (lane == 0) {
                     unsigned lo = 0, hi = 65535;
                     while (lo < hi) {
                         const unsigned mid = (lo + hi) >> 1;
                         int le = 0;
-                        for (int i = 0; i < cnt; i++) le += (cand[i].score <= mid);
+                        for (int i = 0; i < cnt; i++) le += (pc_score(cand[i]) <= mid);
                         if ((unsigned long long) le >= kmerConsidered) hi = mid; else lo = mid + 1;
                     }
                     int le = 0;
-                    for (int i = 0; i < cnt; i++) le += (cand[i].score <= lo);
-                    threshold = lo + 1;
-                    tooMuch = le - (int) kmerConsidered;
+                    for (int i = 0; i < cnt; i++) le += (pc_score(cand[i]) <= lo);
+                    add = select_sequential_packed(cand, cnt, kmerConsidered, lo + 1, le - (int) kmerConsidered, c, id, (unsigned) L, outRecs + nOut);
                 }
-                nOut += select_sequential(cand, cnt, kmerConsidered, threshold, tooMuch, c, id, (unsigned) L, outRecs + nOut);
+                nOut += __shfl_sync(0xFFFFFFFFu, add, 0);
             }
         }
-        nOut = __shfl_sync(0xFFFFFFFFu, nOut, 0);
         __syncwarp();
         unsigned long long base = 0;
         if (lane == 0 && nOut) base = atomicAdd(outCount, (unsigned long long) nOut);
@@ -757,7 +842,7 @@ template <int NMAX>
 static int launch_extract_warp(const pg_seqdb &db, const unsigned *list, const unsigned *listCount, unsigned hostCount, const KmConst &c,
                                Rec *out, unsigned long long *outCount, unsigned long long outCap, cudaStream_t stream, uint64_t *launches) {
     if (hostCount == 0) return 0;
-    const size_t smem = 4 * ((size_t) NMAX * sizeof(Cand) + (size_t) (NMAX + 1) * sizeof(Rec) + (NMAX + 40));
+    const size_t smem = 4 * ((size_t) NMAX * sizeof(PCand) + (size_t) (NMAX + 1) * sizeof(Rec) + (NMAX + 40));
     PG_CUDA(cudaFuncSetAttribute(extract_warp_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     unsigned blocks = (hostCount + 3) / 4;
     const unsigned maxBlocks = NUM_SMS * 32;

@@ -92,39 +92,46 @@ struct QView {             // the query as it is aligned: forward, or the full r
     }
 };
 
-struct DiagAln { int start, end; unsigned score, diagLen, dist; int diagonal; };
+struct DiagAln { int start, end; unsigned score, diagLen, dist; int diagonal; int idCnt; };
 
-// ungappedAlignmentByDiagonal + computeGlobalSubstitutionStartEndDistance for one candidate diagonal;
-// executed by a full warp, result valid in all lanes.
+// ungappedAlignmentByDiagonal + computeGlobalSubstitutionStartEndDistance for one candidate diagonal, plus the
+// identity count over the same columns (rescorediagonal.cpp:277-282, case-folded); executed by a full warp,
+// result valid in all lanes.
 __device__ DiagAln align_by_diagonal(const QView &q, const char *t, unsigned tLen, int diagonal, int alph,
                                      const unsigned char *sA2n, const signed char *sMat, const unsigned char *sRev) {
     const unsigned lane = threadIdx.x & 31;
     const unsigned qLen = (unsigned) q.len;
     const unsigned dist = (unsigned) abs(diagonal);
-    DiagAln r; r.start = -1; r.end = -1; r.score = 0; r.diagLen = 0; r.dist = dist; r.diagonal = diagonal;
+    DiagAln r; r.start = -1; r.end = -1; r.score = 0; r.diagLen = 0; r.dist = dist; r.diagonal = diagonal; r.idCnt = 0;
     unsigned qOff, tOff, len;
     if (diagonal >= 0 && dist < qLen) { len = min(tLen, qLen - dist); qOff = dist; tOff = 0; }
     else if (diagonal < 0 && dist < tLen) { len = min(tLen - dist, qLen); qOff = 0; tOff = dist; }
     else return r;
     r.diagLen = len;
+    if (len == 0) return r;
     const unsigned char q0 = q.at(qOff, sRev), t0 = (unsigned char) t[tOff];
     const unsigned char qE = q.at(qOff + len - 1, sRev), tE = (unsigned char) t[tOff + len - 1];
     const unsigned first = (q0 == '*' || t0 == '*') ? 1u : 0u;
     unsigned last = len - 1;
     if (last > 0 && (qE == '*' || tE == '*')) last--;
-    long long sum = 0;
-    for (unsigned pos = first + lane; pos <= last && last != 0xFFFFFFFFu; pos += 32) {
-        const unsigned a = sA2n[q.at(qOff + pos, sRev)], b = sA2n[(unsigned char) t[tOff + pos]];
-        sum += sMat[a * alph + b];
+    int sum = 0, ids = 0;
+    for (unsigned pos = first + lane; pos <= last; pos += 32) {
+        const unsigned char qc = q.at(qOff + pos, sRev), tc = (unsigned char) t[tOff + pos];
+        sum += sMat[sA2n[qc] * alph + sA2n[tc]];
+        ids += ((qc & (unsigned char) ~0x20) == (tc & (unsigned char) ~0x20)) ? 1 : 0;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o); ids += __shfl_xor_sync(0xFFFFFFFFu, ids, o); }
     if (sum < 0) sum = 0;
-    r.start = (int) first; r.end = (int) last; r.score = (unsigned) sum;
+    r.start = (int) first; r.end = (int) last; r.score = (unsigned) sum; r.idCnt = ids;
     return r;
 }
 
-// items [0, nHits): prefilter hit j;  items [nHits, nHits + n): the "key\t0\t0" self line of query (item - nHits)
+// items [0, nHits): prefilter hit j;  items [nHits, nHits + n): the "key\t0\t0" self line of query (item - nHits).
+// A warp takes 32 items: every lane first fetches the operands of ITS item (so the dependent loads
+// hit -> key -> offset overlap across the lanes), the warp then scores the 32 diagonals one after the other with
+// all lanes striding the columns, and finally every lane does the double-precision E-value / acceptance
+// arithmetic of its own item -- the fp64 exp/erfc sequence is evaluated once per item instead of once per lane.
 __global__ void __launch_bounds__(256) rescore_kernel(const pg_seqdb db, const pg_hit *__restrict__ hits, unsigned long long nHits,
                                                       const RsConst c, pg_aln *__restrict__ res, unsigned char *__restrict__ acc) {
     __shared__ unsigned char sA2n[256];
@@ -135,63 +142,79 @@ __global__ void __launch_bounds__(256) rescore_kernel(const pg_seqdb db, const p
     __syncthreads();
     const unsigned lane = threadIdx.x & 31;
     const unsigned long long nItems = nHits + db.n;
+    const unsigned long long nBatches = (nItems + 31) / 32;
     const unsigned long long warpsTotal = (unsigned long long) gridDim.x * (blockDim.x >> 5);
-    for (unsigned long long item = (unsigned long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < nItems; item += warpsTotal) {
-        unsigned qKey, tKey, qi, ti; int prefScore; unsigned short diag16;
-        if (item < nHits) {
-            const pg_hit h = hits[item];
-            qKey = h.rep; tKey = h.target; prefScore = h.score; diag16 = (unsigned short) (short) h.diag;
-            qi = find_id(db.keys, (unsigned) db.n, qKey);
-            ti = find_id(db.keys, (unsigned) db.n, tKey);
-        } else {
-            qi = ti = (unsigned) (item - nHits);
-            qKey = tKey = db.keys[qi]; prefScore = 0; diag16 = 0;
-            if (qKey < c.ownLo || qKey >= c.ownHi) { if (lane == 0) acc[item] = 0; continue; }
+    for (unsigned long long batch = (unsigned long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); batch < nBatches; batch += warpsTotal) {
+        const unsigned long long item = batch * 32 + lane;
+        // ---- phase 1: operands of my item
+        unsigned qKey = 0, tKey = 0, qi = 0, ti = 0; int prefScore = 0; unsigned short diag16 = 0;
+        bool live = item < nItems;
+        if (live) {
+            if (item < nHits) {
+                const pg_hit h = hits[item];
+                qKey = h.rep; tKey = h.target; prefScore = h.score; diag16 = (unsigned short) (short) h.diag;
+                qi = find_id(db.keys, (unsigned) db.n, qKey);
+                ti = find_id(db.keys, (unsigned) db.n, tKey);
+            } else {
+                qi = ti = (unsigned) (item - nHits);
+                qKey = tKey = db.keys[qi];
+                if (qKey < c.ownLo || qKey >= c.ownHi) { acc[item] = 0; live = false; }
+            }
         }
-        const bool isIdentity = (qi == ti);                 // same DB on both sides (rescorediagonal.cpp:205)
-        QView q; q.s = db.data + db.offsets[qi]; q.len = (int) db.lens[qi] - 2; q.rev = (c.nt && prefScore < 0);
-        const char *t = db.data + db.offsets[ti];
-        const int dbLen = (int) db.lens[ti] - 2;
-        const int qLen = q.len;
-        bool accepted = false;
-        pg_aln out;
-        out.query = qKey; out.target = tKey;
-        if (rs_can_be_covered(c.covThr, c.covMode, (float) qLen, (float) dbLen)) {
-            // computeUngappedAlignment: try every diagonal congruent to diag16 modulo 65536
-            DiagAln best; best.start = -1; best.end = -1; best.score = 0; best.diagLen = 0; best.dist = 0; best.diagonal = 0;
-            const unsigned tl = (unsigned) dbLen;
+        const char *qPtr = nullptr, *tPtr = nullptr; int qLen = 0, dbLen = 0;
+        bool scoreIt = false;
+        if (live) {
+            qPtr = db.data + db.offsets[qi]; qLen = (int) db.lens[qi] - 2;
+            tPtr = db.data + db.offsets[ti]; dbLen = (int) db.lens[ti] - 2;
+            scoreIt = rs_can_be_covered(c.covThr, c.covMode, (float) qLen, (float) dbLen);
+            if (!scoreIt) acc[item] = 0;                       // `continue` at rescorediagonal.cpp:214-216
+        }
+        // ---- phase 2: the warp scores the items one by one
+        DiagAln mine; mine.start = -1; mine.end = -1; mine.score = 0; mine.diagLen = 0; mine.dist = 0; mine.diagonal = 0; mine.idCnt = 0;
+        unsigned todo = __ballot_sync(0xFFFFFFFFu, scoreIt);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            QView q;
+            q.s = (const char *) __shfl_sync(0xFFFFFFFFu, (unsigned long long) qPtr, j);
+            const char *t = (const char *) __shfl_sync(0xFFFFFFFFu, (unsigned long long) tPtr, j);
+            q.len = __shfl_sync(0xFFFFFFFFu, qLen, j);
+            const unsigned tl = (unsigned) __shfl_sync(0xFFFFFFFFu, dbLen, j);
+            const unsigned d16 = (unsigned) __shfl_sync(0xFFFFFFFFu, (int) diag16, j);
+            q.rev = c.nt && (__shfl_sync(0xFFFFFFFFu, prefScore, j) < 0);
+            // computeUngappedAlignment: try every diagonal congruent to diag16 modulo 65536, keep the strictly best
+            DiagAln best; best.start = -1; best.end = -1; best.score = 0; best.diagLen = 0; best.dist = 0; best.diagonal = 0; best.idCnt = 0;
             for (unsigned d = 1; d <= 1 + tl / 32768; d++) {
-                const int real = (int) (0u - d * 65536u + (unsigned) diag16);
+                const int real = (int) (0u - d * 65536u + d16);
+                if (!(real < 0 && (unsigned) (-real) < tl) && !(real >= 0 && (unsigned) real < (unsigned) q.len)) continue;   // score 0, never the best
                 const DiagAln tmp = align_by_diagonal(q, t, tl, real, c.alph, sA2n, sMat, sRev);
                 if (tmp.score > best.score) best = tmp;
             }
-            for (unsigned d = 0; d <= (unsigned) qLen / 65536; d++) {
-                const int real = (int) (d * 65536u + (unsigned) diag16);
+            for (unsigned d = 0; d <= (unsigned) q.len / 65536; d++) {
+                const int real = (int) (d * 65536u + d16);
+                if (!(real < 0 && (unsigned) (-real) < tl) && !(real >= 0 && (unsigned) real < (unsigned) q.len)) continue;
                 const DiagAln tmp = align_by_diagonal(q, t, tl, real, c.alph, sA2n, sMat, sRev);
                 if (tmp.score > best.score) best = tmp;
             }
-            const int distance = (int) best.score;
+            if ((int) lane == j) mine = best;
+        }
+        // ---- phase 3: E-value, identity, coverage, acceptance of my item
+        if (scoreIt) {
+            const bool isIdentity = (qi == ti);                 // same DB on both sides (rescorediagonal.cpp:205)
+            const bool rev = c.nt && prefScore < 0;
+            const int distance = (int) mine.score;
             const double epa = c.K * exp(-c.lambda * (double) distance);
             const double evalue = epa * alp_area(c, (double) distance, (double) qLen, c.dbRes);
             const int bitScore = (int) (((c.lambda * (double) distance - c.logK) / log(2.0)) + 0.5);
-            const int alnLen = (best.end - best.start) + 1;
+            const int alnLen = (mine.end - mine.start) + 1;
             int qS, qE, dS, dE;
-            if (best.diagonal >= 0) { qS = best.start + (int) best.dist; qE = best.end + (int) best.dist; dS = best.start; dE = best.end; }
-            else { qS = best.start; qE = best.end; dS = best.start + (int) best.dist; dE = best.end + (int) best.dist; }
+            if (mine.diagonal >= 0) { qS = mine.start + (int) mine.dist; qE = mine.end + (int) mine.dist; dS = mine.start; dE = mine.end; }
+            else { qS = mine.start; qE = mine.end; dS = mine.start + (int) mine.dist; dE = mine.end + (int) mine.dist; }
             float seqIdF = 0.0f;
             if (evalue <= c.evalThr || isIdentity) {
-                int idCnt = 0;
-                if (qS < 0) {
-                    idCnt = (lane == 0) ? 1 : 0;   // zero-score identity hit: the reference compares the byte before both sequences
-                } else {
-                    for (int i = qS + (int) lane; i <= qE; i += 32) {
-                        const unsigned char ql = q.at(i, sRev) & (unsigned char) ~0x20;
-                        const unsigned char tl2 = (unsigned char) t[dS + (i - qS)] & (unsigned char) ~0x20;
-                        idCnt += (ql == tl2) ? 1 : 0;
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) idCnt += __shfl_xor_sync(0xFFFFFFFFu, idCnt, o);
+                // zero-score hit (start = end = -1): the reference compares the byte before both sequences; for the
+                // identity hit both are the same byte => one identity
+                const int idCnt = (qS < 0) ? 1 : mine.idCnt;
                 if (c.seqIdMode == 1) seqIdF = __fdiv_rn((float) idCnt, (float) min(qLen, dbLen));
                 else if (c.seqIdMode == 2) seqIdF = __fdiv_rn((float) idCnt, (float) max(qLen, dbLen));
                 else seqIdF = __fdiv_rn((float) idCnt, (float) alnLen);
@@ -199,17 +222,19 @@ __global__ void __launch_bounds__(256) rescore_kernel(const pg_seqdb db, const p
             const double seqId = (double) seqIdF;
             const float queryCov = compute_cov((unsigned) qS, (unsigned) qE, (unsigned) qLen);
             const float targetCov = compute_cov((unsigned) dS, (unsigned) dE, (unsigned) dbLen);
-            if (q.rev) { qS = qLen - qS - 1; qE = qLen - qE - 1; }
+            if (rev) { qS = qLen - qS - 1; qE = qLen - qE - 1; }
             const bool hasCov = has_coverage(c.covThr, c.covMode, queryCov, targetCov);
             const bool hasSeqId = seqId >= (double) (c.seqIdThr - 1.1920928955078125e-07f);   // FLT_EPSILON, float subtraction
             const bool hasEvalue = evalue <= c.evalThr;
             const bool hasAlnLen = alnLen >= c.alnLenThr;
-            accepted = isIdentity || (hasAlnLen && hasCov && hasSeqId && hasEvalue);
-            out.bits = bitScore; out.seq_id = seqIdF; out.evalue = evalue;
-            out.q_start = qS; out.q_end = qE; out.q_len = qLen; out.db_start = dS; out.db_end = dE; out.db_len = dbLen;
-        }
-        if (lane == 0) {
-            if (accepted) res[item] = out;
+            const bool accepted = isIdentity || (hasAlnLen && hasCov && hasSeqId && hasEvalue);
+            if (accepted) {
+                pg_aln out;
+                out.query = qKey; out.target = tKey;
+                out.bits = bitScore; out.seq_id = seqIdF; out.evalue = evalue;
+                out.q_start = qS; out.q_end = qE; out.q_len = qLen; out.db_start = dS; out.db_end = dE; out.db_len = dbLen;
+                res[item] = out;
+            }
             acc[item] = accepted ? 1 : 0;
         }
     }
@@ -290,7 +315,7 @@ int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHit
     void *scanWs = acc + o;
     unsigned long long *d_total = ctx->small.as<unsigned long long>() + 4;
 
-    unsigned long long warps = nItems;
+    unsigned long long warps = (nItems + 31) / 32;
     unsigned blocks = (unsigned) std::min<unsigned long long>((warps + 7) / 8, (unsigned long long) NUM_SMS * 64);
     if (blocks == 0) blocks = 1;
     rescore_kernel<<<blocks, 256, 0, s>>>(*db, d_hits, nHits, c, res, acc);
