@@ -63,7 +63,9 @@ def test_workflow_dropin_matches_reference(tool, wf, iters, tmp_path):
         pytest.skip("reference binary oracle/_ref/bin/%s not available on this box" % tool)
     fa = str(tmp_path / "reads.fasta")
     synth.write_fasta(fa, synth.make_reads(3000, seed=21))
-    common = ["--num-iterations", str(iters), "--remove-tmp-files", "0", "--delete-tmp-inc", "0", "--threads", "4"]
+    # --threads 1: the reference's upstream extractorfs hands out new keys with an atomic counter, so with several
+    # threads two runs number the fragments differently; the hot-path steps themselves are thread-independent.
+    common = ["--num-iterations", str(iters), "--remove-tmp-files", "0", "--delete-tmp-inc", "0", "--threads", "1"]
     run([ref_bin, wf, fa, str(tmp_path / "ref.fas"), str(tmp_path / "tmp_ref")] + common)
     env = dict(os.environ, PLASS_REF_BIN=ref_bin)
     log = run([os.path.join(ROOT, "scripts", "plass_gpu"), wf, fa, str(tmp_path / "gpu.fas"), str(tmp_path / "tmp_gpu")] + common, env=env)
