@@ -352,6 +352,35 @@ int pg_shard_finish(pg_context *ctx, const pg_seqdb *db, const void *device_pair
     return 0;
 }
 
+// micro-benchmark of the radix sort on device-resident pseudo-random records: returns ms per scatter pass
+int pg_debug_radix_bench(pg_context *ctx, uint64_t n, int items, int passes, float *ms_per_pass) {
+    PG_CHECK(ctx && ms_per_pass, "pg_debug_radix_bench: null argument");
+    cudaSetDevice(ctx->device);
+    radix_set_items(items);
+    RadixPlan plan; plan.npasses = 0;
+    plan_add_bits(plan, 0, 0, 8 * passes);
+    PG_TRY(ctx->recA.reserve(sizeof(Rec) * (n + 1)));
+    PG_TRY(ctx->recB.reserve(sizeof(Rec) * (n + 1)));
+    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(n)));
+    std::vector<unsigned long long> seed(1 << 20);
+    unsigned long long x = 88172645463325252ull;
+    for (auto &v : seed) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; v = x; }
+    for (uint64_t off = 0; off < n * 2; off += seed.size()) {
+        const uint64_t c = std::min<uint64_t>(seed.size(), n * 2 - off);
+        PG_CUDA(cudaMemcpyAsync((unsigned long long *) ctx->recA.p + off, seed.data(), c * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    Rec *sorted = nullptr; uint64_t launches = 0;
+    for (int rep = 0; rep < 2; rep++)
+        PG_TRY(radix_sort(ctx->recA.as<Rec>(), ctx->recB.as<Rec>(), n, plan, ctx->radixWs.p, ctx->radixWs.cap, ctx->stream, &sorted, &launches,
+                          ctx->ev[EV_SCATTER1_BEGIN], ctx->ev[EV_SCATTER1_END]));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    PG_CUDA(cudaEventElapsedTime(&ms, ctx->ev[EV_SCATTER1_BEGIN], ctx->ev[EV_SCATTER1_END]));
+    *ms_per_pass = ms / passes;
+    radix_set_items(16);
+    return 0;
+}
+
 // ---- diagnostics used by the tests (not part of the drop-in surface) --------------------------------
 int pg_debug_radix_sort(pg_context *ctx, uint64_t *recs /* n x 2 u64, in place */, uint64_t n, const int *word, const int *lo, const int *hi, int nRanges) {
     PG_CHECK(ctx && recs, "pg_debug_radix_sort: null argument");

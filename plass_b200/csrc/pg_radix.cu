@@ -58,7 +58,8 @@ __global__ void radix_scan_kernel(const unsigned long long *__restrict__ ghist, 
 // ---- one pass over one portion ------------------------------------------------------------------
 constexpr unsigned FLAG_AGG = 1u, FLAG_INC = 2u;
 
-__global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(
+template <int ITEMS, int MINBLOCKS>
+__global__ void __launch_bounds__(RADIX_THREADS, MINBLOCKS) radix_scatter_kernel(
     const Rec *__restrict__ in, Rec *__restrict__ out, unsigned long long portionStart, unsigned long long portionEnd,
     DigitPass dp, const unsigned long long *__restrict__ gbase, unsigned long long *__restrict__ gbaseNext,
     unsigned *status, unsigned *ticket, unsigned numTiles) {
@@ -75,15 +76,15 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(
     for (int i = tid; i < (RADIX_THREADS / 32) * 256; i += RADIX_THREADS) (&warpCnt[0][0])[i] = 0;
     __syncthreads();
     const unsigned tile = sTile;
-    const unsigned long long tileBase = portionStart + (unsigned long long) tile * RADIX_TILE;
-    const unsigned count = (unsigned) min((unsigned long long) RADIX_TILE, portionEnd - tileBase);
+    const unsigned long long tileBase = portionStart + (unsigned long long) tile * (RADIX_THREADS * ITEMS);
+    const unsigned count = (unsigned) min((unsigned long long) (RADIX_THREADS * ITEMS), portionEnd - tileBase);
 
     // load: warp w owns items [w*512, (w+1)*512), round r covers 32 consecutive records
-    Rec rec[RADIX_ITEMS];
-    unsigned short rank[RADIX_ITEMS];
+    Rec rec[ITEMS];
+    unsigned short rank[ITEMS];
 #pragma unroll
-    for (int r = 0; r < RADIX_ITEMS; r++) {
-        const unsigned idx = w * (RADIX_ITEMS * 32) + r * 32 + lane;
+    for (int r = 0; r < ITEMS; r++) {
+        const unsigned idx = w * (ITEMS * 32) + r * 32 + lane;
         if (idx < count) {
             const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(in + tileBase) + idx);
             rec[r].w0 = ((unsigned long long) raw.y << 32) | raw.x;
@@ -95,8 +96,8 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(
     // rank: warp-private counters + match_any
     const unsigned ltMask = (1u << lane) - 1u;
 #pragma unroll
-    for (int r = 0; r < RADIX_ITEMS; r++) {
-        const unsigned idx = w * (RADIX_ITEMS * 32) + r * 32 + lane;
+    for (int r = 0; r < ITEMS; r++) {
+        const unsigned idx = w * (ITEMS * 32) + r * 32 + lane;
         const bool valid = idx < count;
         const unsigned d = valid ? digit_of(rec[r], dp) : 256u;
         const unsigned m = __match_any_sync(0xFFFFFFFFu, d);
@@ -141,8 +142,8 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(
     __syncthreads();
     // reorder through shared memory
 #pragma unroll
-    for (int r = 0; r < RADIX_ITEMS; r++) {
-        const unsigned idx = w * (RADIX_ITEMS * 32) + r * 32 + lane;
+    for (int r = 0; r < ITEMS; r++) {
+        const unsigned idx = w * (ITEMS * 32) + r * 32 + lane;
         if (idx < count) {
             const unsigned d = digit_of(rec[r], dp);
             const unsigned pos = digitStart[d] + warpCnt[w][d] + rank[r];
@@ -190,15 +191,19 @@ __global__ void __launch_bounds__(RADIX_THREADS) radix_scatter_kernel(
     }
 }
 
-constexpr unsigned long long PORTION_RECORDS = ((1ull << 30) / RADIX_TILE - 1) * RADIX_TILE;   // look-back prefix < 2^30
+static int g_items = 16;   // records per thread of the scatter kernel (8 / 12 / 16), see radix_set_items
+static inline unsigned long long tile_records() { return (unsigned long long) RADIX_THREADS * g_items; }
+constexpr unsigned long long PORTION_RECORDS = ((1ull << 30) / 12288 - 1) * 12288;   // look-back prefix < 2^30; multiple of every tile size
 
 inline unsigned long long num_portions(uint64_t n) { return n == 0 ? 1 : (n + PORTION_RECORDS - 1) / PORTION_RECORDS; }
 inline unsigned long long max_tiles(uint64_t n) {
     const unsigned long long per = n < PORTION_RECORDS ? n : PORTION_RECORDS;
-    return (per + RADIX_TILE - 1) / RADIX_TILE + 1;
+    return (per + 2048 - 1) / 2048 + 1;                 // sized for the smallest tile
 }
 
 }  // namespace
+
+void radix_set_items(int items) { g_items = (items == 8 || items == 12) ? items : 16; }
 
 void plan_add_bits(RadixPlan &plan, int word, int lo, int hi) {
     for (int b = lo; b < hi; b += 8) {
@@ -222,9 +227,11 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
     PG_CHECK(plan.npasses <= RADIX_MAX_PASSES, "radix_sort: too many passes");
     PG_CHECK(workspace_bytes >= radix_workspace_bytes(n), "radix_sort: workspace too small");
     static bool attrSet = false;
-    const int dynSmem = RADIX_TILE * sizeof(Rec);
+    const int dynSmem = (int) (tile_records() * sizeof(Rec));
     if (!attrSet) {
-        PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dynSmem));
+        PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int) sizeof(Rec)));
+        PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) sizeof(Rec)));
+        PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * (int) sizeof(Rec)));
         attrSet = true;
     }
     const unsigned long long portions = num_portions(n);
@@ -248,13 +255,14 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
         for (unsigned long long q = 0; q < portions; q++) {
             const unsigned long long ps = q * PORTION_RECORDS;
             const unsigned long long pe = (ps + PORTION_RECORDS < n) ? ps + PORTION_RECORDS : n;
-            const unsigned tiles = (unsigned) ((pe - ps + RADIX_TILE - 1) / RADIX_TILE);
+            const unsigned tiles = (unsigned) ((pe - ps + tile_records() - 1) / tile_records());
             PG_CUDA(cudaMemsetAsync(status, 0, sizeof(unsigned) * ((size_t) tiles * 256 + 64), stream));
             unsigned *ticket = status + statusWords - 32;
             PG_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), stream));
             unsigned long long *gb = bases + ((size_t) p * (portions + 1) + q) * 256;
-            radix_scatter_kernel<<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + 256,
-                                                                          status, ticket, tiles);
+            if (g_items == 16) radix_scatter_kernel<16, 2><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + 256, status, ticket, tiles);
+            else if (g_items == 12) radix_scatter_kernel<12, 3><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + 256, status, ticket, tiles);
+            else radix_scatter_kernel<8, 4><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + 256, status, ticket, tiles);
             if (launches) *launches += 1;
         }
         Rec *t = src; src = dst; dst = t;

@@ -23,8 +23,8 @@ struct DigitPass {
 
 constexpr int RADIX_MAX_PASSES = 12;
 constexpr int RADIX_THREADS = 256;
-constexpr int RADIX_ITEMS = 16;
-constexpr int RADIX_TILE = RADIX_THREADS * RADIX_ITEMS;   // 4096 records = 64 KiB
+// records per thread of the scatter kernel: 16 (4096-record tile, 2 CTAs/SM), 12 (3 CTAs/SM) or 8 (4 CTAs/SM)
+void radix_set_items(int items);
 
 struct RadixPlan {
     DigitPass pass[RADIX_MAX_PASSES];
