@@ -377,7 +377,7 @@ int pg_debug_radix_bench(pg_context *ctx, uint64_t n, int items, int passes, flo
     float ms = 0;
     PG_CUDA(cudaEventElapsedTime(&ms, ctx->ev[EV_SCATTER1_BEGIN], ctx->ev[EV_SCATTER1_END]));
     *ms_per_pass = ms / passes;
-    radix_set_items(16);
+    radix_set_items(12);
     return 0;
 }
 

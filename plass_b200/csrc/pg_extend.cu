@@ -148,48 +148,6 @@ __device__ __forceinline__ unsigned char target_at(const char *t, unsigned tLen,
     return rev ? c_ex_revN[(unsigned char) t[tLen - 1 - i]] : (unsigned char) t[i];
 }
 
-// ungappedAlignmentByDiagonal (mode 3) + updateAlignment (assembleresult.cpp:70-108) against the rope,
-// executed by a full warp for ONE parked alignment (lanes stride the diagonal).
-__device__ void rescore_parked_warp(ExRes &r, const Rope &q, const char *t, unsigned tLen, unsigned tRev, int diag, int alph,
-                                    const unsigned char *sA2n, const signed char *sMat) {
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned qLen = q.len;
-    const unsigned dist = (unsigned) abs(diag);
-    int start = -1, end = -1; unsigned score = 0, diagLen = 0;
-    unsigned qOff = 0, tOff = 0, len = 0; bool valid = false;
-    if (diag >= 0 && dist < qLen) { len = min(tLen, qLen - dist); qOff = dist; valid = true; }
-    else if (diag < 0 && dist < tLen) { len = min(tLen - dist, qLen); tOff = dist; valid = true; }
-    int idCnt = 0;
-    if (valid && len > 0) {
-        diagLen = len;
-        const unsigned first = (q.at(qOff) == '*' || target_at(t, tLen, tRev, tOff) == '*') ? 1u : 0u;
-        unsigned last = len - 1;
-        if (last > 0 && (q.at(qOff + len - 1) == '*' || target_at(t, tLen, tRev, tOff + len - 1) == '*')) last--;
-        long long sum = 0;
-        // score over [first, last]; identities over [qS, qE) = positions [first, last)  (updateAlignment's exclusive end)
-        for (unsigned pos = first + lane; pos <= last; pos += 32) {
-            const unsigned char a = q.at(qOff + pos), b = target_at(t, tLen, tRev, tOff + pos);
-            sum += sMat[sA2n[a] * alph + sA2n[b]];
-            if (pos < last) idCnt += (a == b) ? 1 : 0;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o); idCnt += __shfl_xor_sync(0xFFFFFFFFu, idCnt, o); }
-        if (sum < 0) sum = 0;
-        start = (int) first; end = (int) last; score = (unsigned) sum;
-    }
-    const int d2 = max(abs(diag), 0);
-    int qS, qE, dS, dE;
-    if (diag >= 0) { qS = start + d2; qE = end + d2; dS = start; dE = end; }
-    else { qS = start; qE = end; dS = start + d2; dE = end + d2; }
-    if (!(valid && len > 0)) idCnt = 0;     // start = end = -1: the reference's loop over [qS, qE) is empty
-    r.seqId = __fdiv_rn((float) idCnt, __fsub_rn((float) qE, (float) qS));
-    r.qLen = qLen; r.dbLen = tLen;
-    r.alnLength = diagLen;
-    const float scorePerCol = __fdiv_rn((float) score, (float) ((double) r.alnLength + 0.5));
-    r.score = (int) __fmul_rn(scorePerCol, 100.0f);
-    r.qStartPos = qS; r.qEndPos = qE; r.dbStartPos = dS; r.dbEndPos = dE;
-}
-
 // (float) strtod(text of Util::fastSeqIdToBuffer(seqId)): the value the assembler parses back from aln_N
 __device__ __forceinline__ float seqid_text_roundtrip(float seqId) {
     if (seqId == 1.0f) return 1.0f;
@@ -371,7 +329,10 @@ __global__ void __launch_bounds__(128) extend_round_kernel(const pg_seqdb db, co
     }
 }
 
-// warp per parked alignment: re-score it on the extended contig (assembleresult.cpp:293-307)
+// Re-scoring of the parked alignments on the extended contigs (assembleresult.cpp:293-307).  A warp takes 32
+// parked hits: every lane fetches the operands of ITS hit (state, rope, target, overlap geometry -- a chain of
+// dependent loads that now overlaps across the lanes), the warp then sums the 32 diagonals one after the other with
+// all lanes striding the columns, and every lane finishes its own hit (updateAlignment, :70-108).
 __global__ void __launch_bounds__(256) extend_rescore_kernel(const pg_seqdb db, const unsigned long long *__restrict__ alnStart,
                                                              const ExConst c, const uint2 *__restrict__ work,
                                                              const unsigned long long *__restrict__ workCount,
@@ -384,20 +345,87 @@ __global__ void __launch_bounds__(256) extend_rescore_kernel(const pg_seqdb db, 
     __syncthreads();
     const unsigned lane = threadIdx.x & 31;
     const unsigned long long nWork = *workCount;
+    const unsigned long long nBatches = (nWork + 31) / 32;
     const unsigned long long warpsTotal = (unsigned long long) gridDim.x * (blockDim.x >> 5);
-    for (unsigned long long wi = (unsigned long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < nWork; wi += warpsTotal) {
-        const uint2 it = work[wi];
-        const unsigned qi = it.x;
-        const unsigned long long a0 = alnStart[qi];
-        const ExState st = states[qi];
-        Rope rope; rope.segs = segBuf + a0 + qi; rope.db = &db; rope.n = st.ropeN; rope.len = st.ropeLen;
-        ExRes r = parkBuf[a0 + it.y];
-        const unsigned tId = find_id(db.keys, (unsigned) db.n, r.dbKey);
-        const unsigned tSeqLen = db.lens[tId] - 2;
-        const char *tSeq = db.data + db.offsets[tId];
-        const int diag = (int) ((unsigned) r.qStartPos + st.leftOff) - r.dbStartPos;
-        rescore_parked_warp(r, rope, tSeq, tSeqLen, r.rev, diag, c.alph, sA2n, sMat);
-        if (lane == 0) parkBuf[a0 + it.y] = r;
+    for (unsigned long long batch = (unsigned long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); batch < nBatches; batch += warpsTotal) {
+        const unsigned long long wi = batch * 32 + lane;
+        const bool live = wi < nWork;
+        // ---- phase 1: my hit
+        ExRes r; r.dbKey = 0; r.score = 0; r.seqId = 0; r.alnLength = 0; r.qStartPos = r.qEndPos = 0; r.qLen = 0; r.dbStartPos = r.dbEndPos = 0; r.dbLen = 0; r.rev = 0;
+        Rope rope; rope.segs = nullptr; rope.db = &db; rope.n = 0; rope.len = 0;
+        const char *tSeq = nullptr; unsigned tLen = 0;
+        unsigned long long slot = 0;
+        int diag = 0;
+        unsigned qOff = 0, tOff = 0, len = 0, first = 0, last = 0;
+        bool valid = false;
+        if (live) {
+            const uint2 it = work[wi];
+            const unsigned qi = it.x;
+            const unsigned long long a0 = alnStart[qi];
+            const ExState st = states[qi];
+            rope.segs = segBuf + a0 + qi; rope.n = st.ropeN; rope.len = st.ropeLen;
+            slot = a0 + it.y;
+            r = parkBuf[slot];
+            const unsigned tId = find_id(db.keys, (unsigned) db.n, r.dbKey);
+            tLen = db.lens[tId] - 2;
+            tSeq = db.data + db.offsets[tId];
+            diag = (int) ((unsigned) r.qStartPos + st.leftOff) - r.dbStartPos;
+            const unsigned dist = (unsigned) abs(diag);
+            if (diag >= 0 && dist < rope.len) { len = min(tLen, rope.len - dist); qOff = dist; valid = len > 0; }
+            else if (diag < 0 && dist < tLen) { len = min(tLen - dist, rope.len); tOff = dist; valid = len > 0; }
+            if (valid) {
+                first = (rope.at(qOff) == '*' || target_at(tSeq, tLen, r.rev, tOff) == '*') ? 1u : 0u;
+                last = len - 1;
+                if (last > 0 && (rope.at(qOff + len - 1) == '*' || target_at(tSeq, tLen, r.rev, tOff + len - 1) == '*')) last--;
+            }
+        }
+        // ---- phase 2: the warp sums the diagonals one by one
+        long long mySum = 0; int myIds = 0;
+        unsigned todo = __ballot_sync(0xFFFFFFFFu, valid);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            Rope q; q.db = &db;
+            q.segs = (ExSeg *) __shfl_sync(0xFFFFFFFFu, (unsigned long long) rope.segs, j);
+            q.n = __shfl_sync(0xFFFFFFFFu, rope.n, j);
+            q.len = __shfl_sync(0xFFFFFFFFu, rope.len, j);
+            const char *t = (const char *) __shfl_sync(0xFFFFFFFFu, (unsigned long long) tSeq, j);
+            const unsigned tl = __shfl_sync(0xFFFFFFFFu, tLen, j);
+            const unsigned tRev = __shfl_sync(0xFFFFFFFFu, r.rev, j);
+            const unsigned qo = __shfl_sync(0xFFFFFFFFu, qOff, j), to = __shfl_sync(0xFFFFFFFFu, tOff, j);
+            const unsigned f = __shfl_sync(0xFFFFFFFFu, first, j), l = __shfl_sync(0xFFFFFFFFu, last, j);
+            long long sum = 0; int ids = 0;
+            // score over [first, last]; identities over [qS, qE) = columns [first, last)  (exclusive end of updateAlignment)
+            for (unsigned pos = f + lane; pos <= l; pos += 32) {
+                const unsigned char a = q.at(qo + pos), b = target_at(t, tl, tRev, to + pos);
+                sum += sMat[sA2n[a] * c.alph + sA2n[b]];
+                if (pos < l) ids += (a == b) ? 1 : 0;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o); ids += __shfl_xor_sync(0xFFFFFFFFu, ids, o); }
+            if ((int) lane == j) { mySum = sum; myIds = ids; }
+        }
+        // ---- phase 3: updateAlignment of my hit
+        if (live) {
+            int start = -1, end = -1; unsigned score = 0, diagLen = 0; int idCnt = 0;
+            const unsigned dist = (unsigned) abs(diag);
+            if ((diag >= 0 && dist < rope.len) || (diag < 0 && dist < tLen)) diagLen = len;
+            if (valid) {
+                if (mySum < 0) mySum = 0;
+                start = (int) first; end = (int) last; score = (unsigned) mySum; idCnt = myIds;
+            }
+            const int d2 = max(abs(diag), 0);
+            int qS, qE, dS, dE;
+            if (diag >= 0) { qS = start + d2; qE = end + d2; dS = start; dE = end; }
+            else { qS = start; qE = end; dS = start + d2; dE = end + d2; }
+            r.seqId = __fdiv_rn((float) idCnt, __fsub_rn((float) qE, (float) qS));
+            r.qLen = rope.len; r.dbLen = tLen;
+            r.alnLength = diagLen;
+            const float scorePerCol = __fdiv_rn((float) score, (float) ((double) r.alnLength + 0.5));
+            r.score = (int) __fmul_rn(scorePerCol, 100.0f);
+            r.qStartPos = qS; r.qEndPos = qE; r.dbStartPos = dS; r.dbEndPos = dE;
+            parkBuf[slot] = r;
+        }
     }
 }
 

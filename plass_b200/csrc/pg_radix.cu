@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(RADIX_THREADS, MINBLOCKS) radix_scatter_kernel
     }
 }
 
-static int g_items = 16;   // records per thread of the scatter kernel (8 / 12 / 16), see radix_set_items
+static int g_items = 12;   // records per thread of the scatter kernel (8 / 12 / 16), see radix_set_items
 static inline unsigned long long tile_records() { return (unsigned long long) RADIX_THREADS * g_items; }
 constexpr unsigned long long PORTION_RECORDS = ((1ull << 30) / 12288 - 1) * 12288;   // look-back prefix < 2^30; multiple of every tile size
 
@@ -203,7 +203,7 @@ inline unsigned long long max_tiles(uint64_t n) {
 
 }  // namespace
 
-void radix_set_items(int items) { g_items = (items == 8 || items == 12) ? items : 16; }
+void radix_set_items(int items) { g_items = (items == 8 || items == 16) ? items : 12; }
 
 void plan_add_bits(RadixPlan &plan, int word, int lo, int hi) {
     for (int b = lo; b < hi; b += 8) {
