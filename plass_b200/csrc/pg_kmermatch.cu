@@ -728,14 +728,18 @@ __device__ __forceinline__ bool reduce_one(const Rec *__restrict__ in, unsigned 
     const unsigned rep = (unsigned) (r.w0 >> 32), target = (unsigned) r.w0;
     unsigned diagB = (unsigned) (r.w1 & 0xFFFFu), prevDiag = diagB;
     unsigned best = diagB, bestRev = (unsigned) ((r.w1 >> 16) & 1u);
-    unsigned maxDiag = 0, diagCnt = 0, top = 0;
+    unsigned maxDiag = 0, diagCnt = 0, top = 0, anyRev = 0;
     unsigned long long j = i;
     while (j < n) {
         const Rec q = in[j];
         if ((unsigned) q.w0 != target) break;
         const unsigned d = (unsigned) (q.w1 & 0xFFFFu);
-        diagCnt = (prevDiag == d) ? diagCnt + 1 : 1;
-        if (diagCnt >= maxDiag) { best = d; maxDiag = diagCnt; bestRev = (unsigned) ((q.w1 >> 16) & 1u); }
+        const unsigned rv = (unsigned) ((q.w1 >> 16) & 1u);
+        if (prevDiag == d) { diagCnt++; anyRev |= rv; } else { diagCnt = 1; anyRev = rv; }
+        // nt: records that agree on (rep, target, diagonal) but not on the strand have no defined order in the
+        // reference (unstable sort; the last one wins there).  Here the reverse strand wins,
+        // which makes the result independent of the order in which the group kernel emitted the pairs.
+        if (diagCnt >= maxDiag) { best = d; maxDiag = diagCnt; bestRev = anyRev; }
         prevDiag = d;
         j++; top++;
     }
