@@ -175,7 +175,7 @@ void pg_destroy(pg_context *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->small, &ctx->lists, &ctx->recA, &ctx->recB, &ctx->radixWs, &ctx->scratch, &ctx->blockCounts, &ctx->hits,
-                      &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta, &ctx->exLists, &ctx->ntTab};
+                      &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta, &ctx->exLists, &ctx->ntTab, &ctx->buckets};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);
@@ -351,6 +351,9 @@ int pg_shard_finish(pg_context *ctx, const pg_seqdb *db, const void *device_pair
     if (alns && n_alns) { PG_TRY(to_host(ctx->stream, dAlns, nA, alns)); *n_alns = nA; }
     return 0;
 }
+
+// tests: force the full-sort group path (1) or allow the bucketed hash join (0)
+int pg_debug_force_full_sort(pg_context *ctx, int on) { if (!ctx) return 1; ctx->forceFullSort = on != 0; return 0; }
 
 // micro-benchmark of the radix sort on device-resident pseudo-random records: returns ms per scatter pass
 int pg_debug_radix_bench(pg_context *ctx, uint64_t n, int items, int passes, float *ms_per_pass) {

@@ -17,7 +17,8 @@ struct pg_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[pg::EV_COUNT];
-    pg::DevBuf small, lists, recA, recB, radixWs, scratch, blockCounts, hits, alnAll, alns, flags, exWork, exSegs, exMeta, exLists, ntTab;
+    pg::DevBuf small, lists, recA, recB, radixWs, scratch, blockCounts, hits, alnAll, alns, flags, exWork, exSegs, exMeta, exLists, ntTab, buckets;
+    bool forceFullSort = false;   // tests: take the 8-pass sort + group_kernel path instead of the bucketed hash join
     unsigned ntTabN = 0;
     bool pairsInA = false;
     bool kmRan = false, rsRan = false, exRan = false;

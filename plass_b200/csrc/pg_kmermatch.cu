@@ -718,6 +718,159 @@ __global__ void __launch_bounds__(GROUP_THREADS) group_kernel(const Rec *__restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// group, fast path: partial-key partition + shared-memory hash join.
+// Instead of fully sorting the 64-bit k-mers (8 radix passes) the records are partitioned by B bits of a hash
+// of the k-mer (ceil(B/8) passes, B chosen so that a bucket holds ~500 records).  Equal k-mers share a bucket, so
+// one CTA per bucket can build the groups in a shared-memory hash table: per k-mer the minimum of the packed
+// (seqLen desc, id, pos, strand) key = the representative of assignGroup, and the group size.  A second sweep
+// over the bucket (held in registers) emits the (rep, target, diagonal) pairs.  Buckets that do not fit the
+// table raise `overflow` and the caller falls back to the full sort + group_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int HG_THREADS = 128;
+constexpr int HG_ITEMS = 12;
+constexpr int HG_MAX_BUCKET = HG_THREADS * HG_ITEMS;   // 1536 records
+constexpr int HG_TABLE = 2048;                         // slots (load factor <= 0.75)
+
+__global__ void bucket_bounds_kernel(const Rec *__restrict__ in, unsigned long long n, unsigned long long hashMask, unsigned bucketMask,
+                                     unsigned long long *__restrict__ start, unsigned long long *__restrict__ end,
+                                     unsigned long long *__restrict__ minKmer) {
+    unsigned long long localMin = ~0ULL;
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
+        const unsigned long long k = in[i].w0 & hashMask;
+        const unsigned b = (unsigned) mix64(k) & bucketMask;
+        localMin = min(localMin, k);
+        if (i == 0) start[b] = 0;
+        else {
+            const unsigned pb = (unsigned) mix64(in[i - 1].w0 & hashMask) & bucketMask;
+            if (pb != b) { start[b] = i; end[pb] = i; }
+        }
+        if (i == n - 1) end[b] = n;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) localMin = min(localMin, __shfl_xor_sync(0xFFFFFFFFu, localMin, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(minKmer, localMin);
+}
+
+// packed representative key: (seqLen desc, id asc, pos asc, strand asc); seqLen < 32768 (narrow records)
+__device__ __forceinline__ unsigned long long hg_pack(const Rec &r) {
+    const unsigned long long id = r.w1 >> 32, len = (r.w1 >> 16) & 0x7FFFULL, pos = r.w1 & 0xFFFFULL;
+    return ((0x7FFFULL ^ len) << 49) | (id << 17) | (pos << 1) | (r.w0 >> 63);
+}
+
+// pair record of member r in a group whose representative is described by (repId, queryLen, repPos, repStrand)
+__device__ __forceinline__ bool make_pair_record(const Rec &r, unsigned repId, int queryLen, int repPos, unsigned repStrand, bool firstGroup,
+                                                 const KmConst &c, Rec &out) {
+    const unsigned tId = (unsigned) (r.w1 >> 32);
+    const int tLen = (int) (short) ((r.w1 >> 16) & 0xFFFFULL);
+    const int tPos = (int) (short) (r.w1 & 0xFFFFULL);
+    int diagonal = repPos - tPos;
+    unsigned qRev = 0;
+    if (c.nt) {
+        // the reference initialises repIsReverse = false for the very first group (kmermatcher.cpp:463)
+        const bool repIsReverse = firstGroup ? false : (repStrand == 0);
+        const bool targetIsReverse = ((r.w0 >> 63) == 0);
+        int queryPos, targetPos;
+        if (repIsReverse && !targetIsReverse) { queryPos = repPos; targetPos = tPos; qRev = 1; }
+        else if (repIsReverse && targetIsReverse) { queryPos = (short) ((queryLen - 1) - repPos); targetPos = (short) ((tLen - 1) - tPos); qRev = 0; }
+        else if (!repIsReverse && targetIsReverse) { queryPos = (short) ((queryLen - 1) - repPos); targetPos = (short) ((tLen - 1) - tPos); qRev = 1; }
+        else { queryPos = repPos; targetPos = tPos; qRev = 0; }
+        diagonal = queryPos - targetPos;
+    }
+    const bool canBeExtended = diagonal < 0 || (diagonal > (queryLen - tLen));
+    const bool covered = can_be_covered(c.covThr, c.covMode, (float) queryLen, (float) tLen);
+    const bool keep = (c.includeOnlyExtendable == 0 && covered) || (canBeExtended && c.includeOnlyExtendable != 0);
+    if (keep) {
+        out.w0 = ((unsigned long long) repId << 32) | tId;
+        const unsigned biased = (unsigned) (((int) (short) diagonal) + 32768) & 0xFFFFu;
+        out.w1 = ((unsigned long long) qRev << 16) | biased;
+    }
+    return keep;
+}
+
+__global__ void __launch_bounds__(HG_THREADS) hash_group_kernel(const Rec *__restrict__ in, const unsigned long long *__restrict__ start,
+                                                                const unsigned long long *__restrict__ end, unsigned nBuckets,
+                                                                unsigned long long hashMask, const unsigned long long *__restrict__ minKmer,
+                                                                const KmConst c, Rec *__restrict__ out, unsigned long long *__restrict__ outCount,
+                                                                unsigned *__restrict__ overflow) {
+    __shared__ unsigned long long sKey[HG_TABLE];
+    __shared__ unsigned long long sMin[HG_TABLE];
+    __shared__ unsigned sCnt[HG_TABLE];
+    __shared__ unsigned sWarpOut[HG_THREADS / 32];
+    __shared__ unsigned long long sOutBase;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned long long firstKmer = *minKmer;
+    for (unsigned b = blockIdx.x; b < nBuckets; b += gridDim.x) {
+        const unsigned long long s0 = start[b], e0 = end[b];
+        if (e0 <= s0) continue;
+        const unsigned count = (unsigned) (e0 - s0);
+        if (count > HG_MAX_BUCKET) { if (tid == 0) atomicExch(overflow, 1u); continue; }
+        for (int i = tid; i < HG_TABLE; i += HG_THREADS) { sKey[i] = ~0ULL; sMin[i] = ~0ULL; sCnt[i] = 0; }
+        __syncthreads();
+        Rec rec[HG_ITEMS];
+        unsigned slotOf[HG_ITEMS];
+#pragma unroll
+        for (int it = 0; it < HG_ITEMS; it++) {
+            const unsigned i = it * HG_THREADS + tid;
+            slotOf[it] = 0xFFFFFFFFu;
+            if (i < count) {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(in + s0) + i);
+                rec[it].w0 = ((unsigned long long) raw.y << 32) | raw.x;
+                rec[it].w1 = ((unsigned long long) raw.w << 32) | raw.z;
+                const unsigned long long k = rec[it].w0 & hashMask;
+                // aa: the reference drops k-mer == SIZE_T_MAX, its own array sentinel (kmermatcher.cpp:475); ~0 is also the
+                // empty marker of the table.  nt keys have 63 bits and never collide with it.
+                if (!(hashMask == ~0ULL && k == ~0ULL)) {
+                    unsigned slot = (unsigned) (mix64(k) >> 40) & (HG_TABLE - 1);
+                    while (true) {
+                        const unsigned long long old = atomicCAS(&sKey[slot], ~0ULL, k);
+                        if (old == ~0ULL || old == k) break;
+                        slot = (slot + 1) & (HG_TABLE - 1);
+                    }
+                    atomicMin(&sMin[slot], hg_pack(rec[it]));
+                    atomicAdd(&sCnt[slot], 1u);
+                    slotOf[it] = slot;
+                }
+            }
+        }
+        __syncthreads();
+        Rec outRec[HG_ITEMS];
+        unsigned keepMask = 0;
+#pragma unroll
+        for (int it = 0; it < HG_ITEMS; it++) {
+            if (slotOf[it] != 0xFFFFFFFFu && sCnt[slotOf[it]] >= 2) {
+                const unsigned long long m = sMin[slotOf[it]];
+                const unsigned repId = (unsigned) ((m >> 17) & 0xFFFFFFFFULL);
+                const int queryLen = (int) (0x7FFFULL ^ (m >> 49));
+                const int repPos = (int) (short) ((m >> 1) & 0xFFFFULL);
+                const unsigned repStrand = (unsigned) (m & 1ULL);
+                const bool firstGroup = (rec[it].w0 & hashMask) == firstKmer;
+                if (make_pair_record(rec[it], repId, queryLen, repPos, repStrand, firstGroup, c, outRec[it])) keepMask |= 1u << it;
+            }
+        }
+        const unsigned mine = __popc(keepMask);
+        unsigned v = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= o) v += nb; }
+        if (lane == 31) sWarpOut[w] = v;
+        __syncthreads();
+        unsigned woff = 0, total = 0;
+        for (int ww = 0; ww < HG_THREADS / 32; ww++) { if (ww < w) woff += sWarpOut[ww]; total += sWarpOut[ww]; }
+        if (tid == 0) sOutBase = total ? atomicAdd(outCount, (unsigned long long) total) : 0ULL;
+        __syncthreads();
+        unsigned long long ob = sOutBase + woff + v - mine;
+#pragma unroll
+        for (int it = 0; it < HG_ITEMS; it++)
+            if (keepMask & (1u << it)) {
+                uint4 raw;
+                raw.x = (unsigned) outRec[it].w0; raw.y = (unsigned) (outRec[it].w0 >> 32);
+                raw.z = (unsigned) outRec[it].w1; raw.w = (unsigned) (outRec[it].w1 >> 32);
+                reinterpret_cast<uint4 *>(out)[ob++] = raw;
+            }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // reduce: writeKmerMatcherResult (kmermatcher.cpp:809-924) on pairs sorted by (rep, target, diagonal).
 // A run starts where rep or target changes; the scan over the run continues while the TARGET id stays
 // the same even across a rep boundary (the reference's while-loop at :880 only tests the id).
@@ -905,10 +1058,66 @@ int km_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const Km
 }
 
 // Stage 2: sort #1 + group.  Input records in recA (n), output pair records in recA (count returned).
+// fast path of stage 2 (see hash_group_kernel); returns *ok = false if a bucket overflowed the shared-memory table
+static int km_group_bucketed(Context *ctx, const KmConst &c, uint64_t nRecords, uint64_t *nPairs, bool *ok) {
+    cudaStream_t s = ctx->stream;
+    *ok = false;
+    int B = 1;
+    while (B < 24 && (nRecords >> B) > 512) B++;          // ~512 records per bucket on average
+    if ((nRecords >> B) > 700) return 0;                  // more than 2^24 buckets would be needed: use the full sort
+    const unsigned nBuckets = 1u << B;
+    const unsigned long long hashMask = c.nt ? ~(1ULL << 63) : ~0ULL;   // nt: bit 63 is the strand flag (kmermatcher.h:77-96)
+    RadixPlan plan; plan.npasses = 0;
+    plan_add_hash_bits(plan, hashMask, 0, B);
+    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nRecords)));
+    PG_TRY(ctx->buckets.reserve(sizeof(unsigned long long) * 2 * (size_t) nBuckets + 64));
+    unsigned long long *d_start = ctx->buckets.as<unsigned long long>();
+    unsigned long long *d_end = d_start + nBuckets;
+    unsigned long long *d_min = ctx->small.as<unsigned long long>() + 28;     // [28] min k-mer, [29] overflow flag
+    unsigned *d_over = (unsigned *) (d_min + 1);
+    Rec *sorted = nullptr;
+    cudaEventRecord(ctx->ev[EV_SORT1_BEGIN], s);
+    PG_TRY(radix_sort(ctx->recA.as<Rec>(), ctx->recB.as<Rec>(), nRecords, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches,
+                      ctx->ev[EV_SCATTER1_BEGIN], ctx->ev[EV_SCATTER1_END]));
+    ctx->timings.sort1_passes = (uint32_t) plan.npasses;
+    cudaEventRecord(ctx->ev[EV_SORT1_END], s);
+    PG_CUDA(cudaMemsetAsync(d_start, 0, sizeof(unsigned long long) * 2 * (size_t) nBuckets, s));
+    PG_CUDA(cudaMemsetAsync(d_min, 0xFF, sizeof(unsigned long long), s));
+    PG_CUDA(cudaMemsetAsync(d_over, 0, sizeof(unsigned), s));
+    bucket_bounds_kernel<<<NUM_SMS * 16, 256, 0, s>>>(sorted, nRecords, hashMask, nBuckets - 1, d_start, d_end, d_min);
+    Rec *outBuf = (sorted == ctx->recA.as<Rec>()) ? ctx->recB.as<Rec>() : ctx->recA.as<Rec>();
+    unsigned long long *d_cnt = ctx->small.as<unsigned long long>() + 2;
+    PG_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
+    hash_group_kernel<<<std::min<unsigned>(nBuckets, NUM_SMS * 64), HG_THREADS, 0, s>>>(sorted, d_start, d_end, nBuckets, hashMask, d_min, c, outBuf, d_cnt, d_over);
+    ctx->launches += 2;
+    cudaEventRecord(ctx->ev[EV_GROUP_END], s);
+    unsigned long long h = 0; unsigned over = 0;
+    PG_CUDA(cudaMemcpyAsync(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, s));
+    PG_CUDA(cudaMemcpyAsync(&over, d_over, sizeof(over), cudaMemcpyDeviceToHost, s));
+    PG_CUDA(cudaStreamSynchronize(s));
+    PG_CUDA(cudaGetLastError());
+    if (over) {
+        // the records are only permuted (still all in `sorted`); hand them back in recA for the full sort
+        if (sorted != ctx->recA.as<Rec>()) PG_CUDA(cudaMemcpyAsync(ctx->recA.p, sorted, sizeof(Rec) * nRecords, cudaMemcpyDeviceToDevice, s));
+        return 0;
+    }
+    *nPairs = h;
+    ctx->pairsInA = (outBuf == ctx->recA.as<Rec>());
+    *ok = true;
+    return 0;
+}
+
+// Stage 2: group the k-mer records and emit the pair records.  Input records in recA (n), output pair records in
+// recA or recB (ctx->pairsInA).
 int km_group(Context *ctx, const pg_seqdb *db, const KmConst &c, uint64_t nRecords, uint64_t *nPairs) {
     cudaStream_t s = ctx->stream;
     *nPairs = 0;
     if (nRecords == 0) return 0;
+    if (!ctx->forceFullSort) {
+        bool ok = false;
+        PG_TRY(km_group_bucketed(ctx, c, nRecords, nPairs, &ok));
+        if (ok) return 0;
+    }
     RadixPlan plan; plan.npasses = 0;
     plan_add_bits(plan, 0, 0, c.nt ? 63 : 64);   // nt: bit 63 is the strand flag, not part of the key (kmermatcher.h:77-96)
     PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nRecords)));

@@ -7,6 +7,7 @@ namespace {
 
 __device__ __forceinline__ unsigned digit_of(const Rec &r, const DigitPass p) {
     unsigned long long w = p.word ? r.w1 : r.w0;
+    if (p.hashed) w = mix64(w & p.hashMask);
     return (unsigned) (w >> p.shift) & p.mask;
 }
 
@@ -209,7 +210,15 @@ void plan_add_bits(RadixPlan &plan, int word, int lo, int hi) {
     for (int b = lo; b < hi; b += 8) {
         const int bits = (hi - b) < 8 ? (hi - b) : 8;
         DigitPass &p = plan.pass[plan.npasses++];
-        p.word = word; p.shift = b; p.mask = (1u << bits) - 1u;
+        p.word = word; p.shift = b; p.mask = (1u << bits) - 1u; p.hashed = 0; p.hashMask = 0;
+    }
+}
+
+void plan_add_hash_bits(RadixPlan &plan, unsigned long long hashMask, int lo, int hi) {
+    for (int b = lo; b < hi; b += 8) {
+        const int bits = (hi - b) < 8 ? (hi - b) : 8;
+        DigitPass &p = plan.pass[plan.npasses++];
+        p.word = 0; p.shift = b; p.mask = (1u << bits) - 1u; p.hashed = 1; p.hashMask = hashMask;
     }
 }
 

@@ -19,7 +19,15 @@ struct DigitPass {
     int word;            // 0 -> Rec::w0, 1 -> Rec::w1
     int shift;           // digit = (w >> shift) & mask
     unsigned mask;       // <= 255
+    int hashed;          // 1: w is first replaced by mix64(w & hashMask) -- partition by hash bits instead of key bits
+    unsigned long long hashMask;
 };
+
+// murmur3 fmix64: the bucket hash of the partial-key partition (any fixed bijective mixer would do)
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
 
 constexpr int RADIX_MAX_PASSES = 12;
 constexpr int RADIX_THREADS = 256;
@@ -42,5 +50,7 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
 
 // Helper to build a plan over bit ranges: appends 8-bit digits covering bits [lo, hi) of word w.
 void plan_add_bits(RadixPlan &plan, int word, int lo, int hi);
+// same over bits [lo, hi) of mix64(w0 & hashMask)
+void plan_add_hash_bits(RadixPlan &plan, unsigned long long hashMask, int lo, int hi);
 
 }  // namespace pg

@@ -62,8 +62,18 @@ def test_extract_matches_oracle(case, golden_root, ctx):
         assert np.array_equal(np.sort(got, order=["w0", "w1"]), np.sort(w, order=["w0", "w1"])), (case, s["dbs"][0])
 
 
+@pytest.mark.parametrize("full_sort", [0, 1])
 @pytest.mark.parametrize("case", CASES)
-def test_kmermatcher_matches_oracle_and_golden(case, golden_root, ctx):
+def test_kmermatcher_matches_oracle_and_golden(case, full_sort, golden_root, ctx):
+    """full_sort = 0: partial-key partition + shared-memory hash join (default); 1: 8-pass sort + group_kernel (fallback)."""
+    api.load_library().pg_debug_force_full_sort(ctx.handle, full_sort)
+    try:
+        _kmermatcher_case(case, golden_root, ctx)
+    finally:
+        api.load_library().pg_debug_force_full_sort(ctx.handle, 0)
+
+
+def _kmermatcher_case(case, golden_root, ctx):
     d, man = golden_case(case, golden_root)
     for s in [s for s in man["steps"] if s["cmd"] == "kmermatcher"]:
         seq = mmseqsdb.read_db(os.path.join(d, s["dbs"][0]))
