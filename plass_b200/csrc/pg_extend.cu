@@ -132,12 +132,13 @@ struct Rope {
     ExSeg *segs;
     int n;
     unsigned len;
-    const pg_seqdb *db;
+    const char *data;                       // the sequence DB (held by value: no pointer to the kernel parameter block)
+    const unsigned long long *offsets;
     __device__ unsigned char at(unsigned i) const {
         int s = 0;
         while (i >= segs[s].len) { i -= segs[s].len; s++; }
         const ExSeg g = segs[s];
-        const char *base = db->data + db->offsets[g.src];
+        const char *base = data + offsets[g.src];
         if (!g.rev) return (unsigned char) base[g.start + i];
         return c_ex_revN[(unsigned char) base[g.start + g.len - 1 - i]];
     }
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(128) extend_round_kernel(const pg_seqdb db, co
     ExSeg *segs = segBuf + a0 + qi;      // capacity nAl + 1
     const unsigned queryKey = db.keys[qi];
     ExState st;
-    Rope rope; rope.segs = segs; rope.db = &db;
+    Rope rope; rope.segs = segs; rope.data = db.data; rope.offsets = db.offsets;
     long hsize = 0;
     if (firstRound) {
         st.querySeqLen = db.lens[qi] - 2;
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(256) extend_rescore_kernel(const pg_seqdb db, 
         const bool live = wi < nWork;
         // ---- phase 1: my hit
         ExRes r; r.dbKey = 0; r.score = 0; r.seqId = 0; r.alnLength = 0; r.qStartPos = r.qEndPos = 0; r.qLen = 0; r.dbStartPos = r.dbEndPos = 0; r.dbLen = 0; r.rev = 0;
-        Rope rope; rope.segs = nullptr; rope.db = &db; rope.n = 0; rope.len = 0;
+        Rope rope; rope.segs = nullptr; rope.data = db.data; rope.offsets = db.offsets; rope.n = 0; rope.len = 0;
         const char *tSeq = nullptr; unsigned tLen = 0;
         unsigned long long slot = 0;
         int diag = 0;
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(256) extend_rescore_kernel(const pg_seqdb db, 
         while (todo) {
             const int j = __ffs(todo) - 1;
             todo &= todo - 1;
-            Rope q; q.db = &db;
+            Rope q; q.data = db.data; q.offsets = db.offsets;
             q.segs = (ExSeg *) __shfl_sync(0xFFFFFFFFu, (unsigned long long) rope.segs, j);
             q.n = __shfl_sync(0xFFFFFFFFu, rope.n, j);
             q.len = __shfl_sync(0xFFFFFFFFu, rope.len, j);
