@@ -13,6 +13,7 @@
 #include "pg_scan.cuh"
 #include "pg_tables.h"
 
+#include <climits>
 #include <cmath>
 #include <vector>
 
@@ -156,6 +157,8 @@ __device__ __forceinline__ float seqid_text_roundtrip(float seqId) {
     return (float) ((double) n / 1000.0);
 }
 
+constexpr unsigned EX_WARP_MAX_ALNS = 32;   // queries with more alignments take the heap path
+
 // per-query state carried between the rounds of the wavefront
 struct ExState {
     long long hsize;
@@ -205,6 +208,7 @@ __global__ void __launch_bounds__(128) extend_round_kernel(const pg_seqdb db, co
     if (li >= *listCount) return;
     const unsigned qi = list[li];
     const unsigned nAl = alnCount[qi];
+    if (!c.nt && nAl <= EX_WARP_MAX_ALNS) return;           // amino acids: handled by extend_round_warp_kernel
     const unsigned long long a0 = alnStart[qi];
     ExRes *heap = heapBuf + a0;
     ExRes *park = parkBuf + a0;
@@ -327,6 +331,154 @@ __global__ void __launch_bounds__(128) extend_round_kernel(const pg_seqdb db, co
         extended[qi] = 1;
         outLen[qi] = rope.len + 2;
         segCount[qi] = (unsigned) rope.n;
+    }
+}
+
+// Amino-acid fast path of one round: one WARP per query, one lane per alignment (queries with at most 32
+// alignments).  CompareResultByScore is a strict total order (score, alnLength, dbKey are never all equal for two
+// hits of one query), so popping the priority queue == repeatedly taking the maximum of the remaining elements: a
+// 5-step shuffle arg-max over registers instead of a chain of dependent heap loads.  Elements that fail the
+// selectFragmentToExtend predicate would be popped and discarded by the reference, so their lanes simply start dead.
+__global__ void __launch_bounds__(256) extend_round_warp_kernel(const pg_seqdb db, const pg_aln *__restrict__ alns,
+                                                                const unsigned long long *__restrict__ alnStart, const unsigned *__restrict__ alnCount,
+                                                                const ExConst c, int firstRound,
+                                                                const unsigned *__restrict__ list, const unsigned *__restrict__ listCount,
+                                                                unsigned *__restrict__ nextList, unsigned *__restrict__ nextCount,
+                                                                uint2 *__restrict__ work, unsigned long long *__restrict__ workCount,
+                                                                ExState *__restrict__ states, ExRes *__restrict__ parkBuf,
+                                                                ExSeg *__restrict__ segBuf, unsigned *__restrict__ segCount,
+                                                                unsigned *__restrict__ outLen, unsigned char *__restrict__ extended,
+                                                                unsigned char *__restrict__ used) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned nList = *listCount;
+    const unsigned warpsTotal = gridDim.x * (blockDim.x >> 5);
+    for (unsigned li = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); li < nList; li += warpsTotal) {
+        const unsigned qi = list[li];
+        const unsigned nAl = alnCount[qi];
+        if (nAl > EX_WARP_MAX_ALNS) continue;                 // handled by extend_round_kernel
+        const unsigned long long a0 = alnStart[qi];
+        ExRes *park = parkBuf + a0;
+        ExSeg *segs = segBuf + a0 + qi;
+        const unsigned queryKey = db.keys[qi];
+        ExState st;
+        int ropeN; unsigned ropeLen;
+        ExRes r; r.dbKey = 0; r.score = 0; r.seqId = 0; r.alnLength = 0; r.qStartPos = r.qEndPos = 0; r.qLen = 0; r.dbStartPos = r.dbEndPos = 0; r.dbLen = 0; r.rev = 0;
+        bool alive = false;
+        if (firstRound) {
+            st.querySeqLen = db.lens[qi] - 2;
+            if (lane == 0) { segs[0].src = qi; segs[0].start = 0; segs[0].len = st.querySeqLen; segs[0].rev = 0; }
+            ropeN = 1; ropeLen = st.querySeqLen;
+            st.couldExtend = 0;
+            if (lane < nAl) {
+                const pg_aln a = alns[a0 + lane];
+                r.dbKey = a.target;
+                r.seqId = seqid_text_roundtrip(a.seq_id);
+                r.qStartPos = a.q_start; r.qEndPos = a.q_end; r.qLen = (unsigned) a.q_len;
+                r.dbStartPos = a.db_start; r.dbEndPos = a.db_end; r.dbLen = (unsigned) a.db_len;
+                const int adjQ = (r.qStartPos == -1) ? 0 : r.qStartPos;
+                const int adjD = (r.dbStartPos == -1) ? 0 : r.dbStartPos;
+                r.alnLength = (unsigned) (max(abs(r.qEndPos - adjQ), abs(r.dbEndPos - adjD)) + 1);
+                const int rawScore = (int) (((c.logK + (double) a.bits * log(2.0)) / c.lambda) + 0.5);
+                const float scorePerCol = __fdiv_rn((float) rawScore, (float) ((double) r.alnLength + 0.5));
+                const float alnLen = (float) r.alnLength;
+                const float ids = __fmul_rn(r.seqId, alnLen);
+                r.seqId = (float) ((double) ids / ((double) alnLen + 0.5));
+                r.score = (int) __fmul_rn(scorePerCol, 100.0f);
+                alive = true;
+            }
+        } else {
+            st = states[qi];
+            ropeN = st.ropeN; ropeLen = st.ropeLen;
+            st.querySeqLen = ropeLen;
+            if ((int) lane < st.nPark) { r = park[lane]; alive = r.seqId >= c.seqIdThr; }
+        }
+        const unsigned querySeqLen = st.querySeqLen;
+        const bool entered = alive;                           // this element is in the queue of this round
+        // selectFragmentToExtend's predicate (assembleresult.cpp:40-57): failing elements are popped and dropped
+        if (alive) {
+            const bool notRightStartAndLeftStart = !(r.dbStartPos == 0 && r.qStartPos == 0);
+            const bool rightStart = r.dbStartPos == 0 && (r.dbEndPos != (int) r.dbLen - 1);
+            const bool leftStart = r.qStartPos == 0 && (r.qEndPos != (int) r.qLen - 1);
+            alive = (rightStart || leftStart) && notRightStartAndLeftStart && (r.dbKey != queryKey);
+        }
+        unsigned leftOff = 0, rightOff = 0;
+        int nPark = 0;
+        bool queueNotEmpty = false;   // set by the length-limit `break`: the queue keeps its lower-priority elements
+        while (true) {
+            const unsigned aliveMask = __ballot_sync(0xFFFFFFFFu, alive);
+            if (aliveMask == 0) break;
+            // arg-max by (score, alnLength, smaller dbKey)
+            int bs = alive ? r.score : INT_MIN; unsigned bl = r.alnLength, bk = r.dbKey; int bLane = alive ? (int) lane : -1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int os = __shfl_xor_sync(0xFFFFFFFFu, bs, o);
+                const unsigned ol = __shfl_xor_sync(0xFFFFFFFFu, bl, o), ok = __shfl_xor_sync(0xFFFFFFFFu, bk, o);
+                const int oLane = __shfl_xor_sync(0xFFFFFFFFu, bLane, o);
+                const bool take = (oLane >= 0) && (bLane < 0 || os > bs || (os == bs && (ol > bl || (ol == bl && ok < bk))));
+                if (take) { bs = os; bl = ol; bk = ok; bLane = oLane; }
+            }
+            const int wl = bLane;                                  // the same in every lane
+            if ((int) lane == wl) alive = false;                   // popped
+            const int bDbStart = __shfl_sync(0xFFFFFFFFu, r.dbStartPos, wl), bDbEnd = __shfl_sync(0xFFFFFFFFu, r.dbEndPos, wl);
+            const int bQStart = __shfl_sync(0xFFFFFFFFu, r.qStartPos, wl), bQEnd = __shfl_sync(0xFFFFFFFFu, r.qEndPos, wl);
+            const unsigned bKey = __shfl_sync(0xFFFFFFFFu, r.dbKey, wl);
+            const unsigned targetId = find_id(db.keys, (unsigned) db.n, bKey);
+            const unsigned targetSeqLen = db.lens[targetId] - 2;
+            if (bDbStart == 0) {
+                if ((targetSeqLen - (unsigned) (bDbEnd + 1)) <= rightOff) continue;
+            } else if (bQStart == 0) {
+                if (bDbStart <= (int) leftOff) continue;
+            }
+            const unsigned dbStartPos = (unsigned) bDbStart, dbEndPos = (unsigned) bDbEnd;
+            const unsigned qStartPos = (unsigned) bQStart, qEndPos = (unsigned) bQEnd;
+            if (dbStartPos == 0 && qEndPos == (querySeqLen - 1)) {            // right extension
+                if (rightOff > 0) { if ((int) lane == wl) park[nPark] = r; nPark++; continue; }
+                const unsigned fragLen = targetSeqLen - (dbEndPos + 1);
+                if (lane == 0) {
+                    ExSeg g; g.src = targetId; g.len = fragLen; g.rev = 0; g.start = dbEndPos + 1;
+                    segs[ropeN] = g;
+                    used[targetId] = 1;
+                }
+                ropeN++; ropeLen += fragLen; rightOff += fragLen;
+            } else if (qStartPos == 0 && dbEndPos == (targetSeqLen - 1)) {    // left extension
+                if (leftOff > 0) { if ((int) lane == wl) park[nPark] = r; nPark++; continue; }
+                const unsigned fragLen = dbStartPos;
+                if ((unsigned long long) ropeLen + fragLen >= (unsigned long long) c.maxSeqLen) {
+                    // `break` (assembleresult.cpp:258-262): everything with a lower priority than this hit -- selectable
+                    // or not -- is still in the reference's queue, and a non-empty queue ends the query (:287-288)
+                    const bool lower = entered && (int) lane != wl &&
+                                       (r.score < bs || (r.score == bs && (r.alnLength < bl || (r.alnLength == bl && r.dbKey > bk))));
+                    queueNotEmpty = __ballot_sync(0xFFFFFFFFu, lower) != 0;
+                    break;
+                }
+                if (lane == 0) {
+                    ExSeg g; g.src = targetId; g.len = fragLen; g.rev = 0; g.start = 0;
+                    for (int sI = ropeN; sI > 0; sI--) segs[sI] = segs[sI - 1];
+                    segs[0] = g;
+                    used[targetId] = 1;
+                }
+                ropeN++; ropeLen += fragLen; leftOff += fragLen;
+            }
+        }
+        if (leftOff > 0 || rightOff > 0) st.couldExtend = 1;
+        bool finished = true;
+        __syncwarp();
+        if (!queueNotEmpty && nPark > 0) {
+            finished = false;
+            if (lane == 0) {
+                st.hsize = 0; st.leftOff = leftOff; st.rightOff = rightOff; st.nPark = nPark; st.ropeN = ropeN; st.ropeLen = ropeLen;
+                states[qi] = st;
+                const unsigned long long w0 = atomicAdd(workCount, (unsigned long long) nPark);
+                for (int i = 0; i < nPark; i++) work[w0 + i] = make_uint2(qi, (unsigned) i);
+                nextList[atomicAdd(nextCount, 1u)] = qi;
+            }
+        }
+        if (finished && st.couldExtend && lane == 0) {
+            extended[qi] = 1;
+            outLen[qi] = ropeLen + 2;
+            segCount[qi] = (unsigned) ropeN;
+        }
+        __syncwarp();
     }
 }
 
@@ -566,6 +718,14 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
         PG_CHECK(round < 100000, "assembleresults: extension did not converge");
         PG_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
         PG_CUDA(cudaMemsetAsync(d_listCnt + (1 - curIdx), 0, sizeof(unsigned), s));
+        if (!nt) {
+            // amino acids: warp per query for the queries with <= 32 alignments (list half 0), heap replay for the rest
+            // (both kernels read the same list and skip the queries of the other class)
+            extend_round_warp_kernel<<<std::min<unsigned>((active + 7) / 8, NUM_SMS * 32), 256, 0, s>>>(
+                *db, d_alns, alnStart, alnCount, c, round == 0, cur, d_listCnt + curIdx, nxt, d_listCnt + (1 - curIdx), work, d_cnt, states,
+                parkBuf, ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
+            ctx->launches++;
+        }
         extend_round_kernel<<<(active + 127) / 128, 128, 0, s>>>(*db, d_alns, alnStart, alnCount, c, round == 0, cur, d_listCnt + curIdx,
                                                                 nxt, d_listCnt + (1 - curIdx), work, d_cnt, states, heapBuf, parkBuf,
                                                                 ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);

@@ -833,18 +833,15 @@ __global__ void __launch_bounds__(HG_THREADS) hash_group_kernel(const Rec *__res
             }
         }
         __syncthreads();
-        Rec outRec[HG_ITEMS];
+        // sweep 1: which members produce a pair (the record itself is rebuilt in sweep 2 to keep registers low)
         unsigned keepMask = 0;
 #pragma unroll
         for (int it = 0; it < HG_ITEMS; it++) {
             if (slotOf[it] != 0xFFFFFFFFu && sCnt[slotOf[it]] >= 2) {
                 const unsigned long long m = sMin[slotOf[it]];
-                const unsigned repId = (unsigned) ((m >> 17) & 0xFFFFFFFFULL);
-                const int queryLen = (int) (0x7FFFULL ^ (m >> 49));
-                const int repPos = (int) (short) ((m >> 1) & 0xFFFFULL);
-                const unsigned repStrand = (unsigned) (m & 1ULL);
-                const bool firstGroup = (rec[it].w0 & hashMask) == firstKmer;
-                if (make_pair_record(rec[it], repId, queryLen, repPos, repStrand, firstGroup, c, outRec[it])) keepMask |= 1u << it;
+                Rec tmp;
+                if (make_pair_record(rec[it], (unsigned) ((m >> 17) & 0xFFFFFFFFULL), (int) (0x7FFFULL ^ (m >> 49)), (int) (short) ((m >> 1) & 0xFFFFULL),
+                                     (unsigned) (m & 1ULL), (rec[it].w0 & hashMask) == firstKmer, c, tmp)) keepMask |= 1u << it;
             }
         }
         const unsigned mine = __popc(keepMask);
@@ -861,9 +858,12 @@ __global__ void __launch_bounds__(HG_THREADS) hash_group_kernel(const Rec *__res
 #pragma unroll
         for (int it = 0; it < HG_ITEMS; it++)
             if (keepMask & (1u << it)) {
+                const unsigned long long m = sMin[slotOf[it]];
+                Rec o;
+                make_pair_record(rec[it], (unsigned) ((m >> 17) & 0xFFFFFFFFULL), (int) (0x7FFFULL ^ (m >> 49)), (int) (short) ((m >> 1) & 0xFFFFULL),
+                                 (unsigned) (m & 1ULL), (rec[it].w0 & hashMask) == firstKmer, c, o);
                 uint4 raw;
-                raw.x = (unsigned) outRec[it].w0; raw.y = (unsigned) (outRec[it].w0 >> 32);
-                raw.z = (unsigned) outRec[it].w1; raw.w = (unsigned) (outRec[it].w1 >> 32);
+                raw.x = (unsigned) o.w0; raw.y = (unsigned) (o.w0 >> 32); raw.z = (unsigned) o.w1; raw.w = (unsigned) (o.w1 >> 32);
                 reinterpret_cast<uint4 *>(out)[ob++] = raw;
             }
         __syncthreads();
@@ -881,18 +881,20 @@ __device__ __forceinline__ bool reduce_one(const Rec *__restrict__ in, unsigned 
     const unsigned rep = (unsigned) (r.w0 >> 32), target = (unsigned) r.w0;
     unsigned diagB = (unsigned) (r.w1 & 0xFFFFu), prevDiag = diagB;
     unsigned best = diagB, bestRev = (unsigned) ((r.w1 >> 16) & 1u);
-    unsigned maxDiag = 0, diagCnt = 0, top = 0, anyRev = 0;
+    unsigned maxDiag = 0, diagCnt = 0, top = 0, revCnt = 0;
     unsigned long long j = i;
     while (j < n) {
         const Rec q = in[j];
         if ((unsigned) q.w0 != target) break;
         const unsigned d = (unsigned) (q.w1 & 0xFFFFu);
         const unsigned rv = (unsigned) ((q.w1 >> 16) & 1u);
-        if (prevDiag == d) { diagCnt++; anyRev |= rv; } else { diagCnt = 1; anyRev = rv; }
-        // nt: records that agree on (rep, target, diagonal) but not on the strand have no defined order in the
-        // reference (unstable sort; the last one wins there).  Here the reverse strand wins,
-        // which makes the result independent of the order in which the group kernel emitted the pairs.
-        if (diagCnt >= maxDiag) { best = d; maxDiag = diagCnt; bestRev = anyRev; }
+        if (prevDiag == d) { diagCnt++; revCnt += rv; } else { diagCnt = 1; revCnt = rv; }
+        // nt: records that agree on (rep, target, diagonal) but not on the strand flag have no defined order in the
+        // reference (unstable ips4o sort): it reports the flag of whichever record ends up last.
+        // They arise from the first-group quirk of assignGroup (one odd record per target of that group) and from
+        // reverse-palindromic repeats.  Here the majority of the winning diagonal decides (a tie -> forward), which is
+        // independent of the emission order of the pairs and agrees with the reference unless its odd record is last.
+        if (diagCnt >= maxDiag) { best = d; maxDiag = diagCnt; bestRev = (2u * revCnt > diagCnt) ? 1u : 0u; }
         prevDiag = d;
         j++; top++;
     }
