@@ -13,8 +13,10 @@
 #include "pg_scan.cuh"
 #include "pg_tables.h"
 
+#include <chrono>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace pg {
@@ -663,6 +665,15 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
         c.lgammaTab = ctx->ntTab.as<double>();
         c.logTab = ctx->ntTab.as<double>() + ctx->ntTabN;
     }
+    const bool trace = getenv("PG_TRACE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        cudaStreamSynchronize(s);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pg_trace] ex_run %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     cudaEventRecord(ctx->ev[EV_EX_BEGIN], s);
     const uint64_t n = db->n;
     // meta arrays (per sequence)
@@ -705,12 +716,14 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     unsigned long long *d_cnt = ctx->small.as<unsigned long long>() + 24;   // [24] work count, [25] list counts (2 x u32)
     unsigned *d_listCnt = (unsigned *) (d_cnt + 1);
     PG_CUDA(cudaMemsetAsync(d_cnt, 0, 16, s));
+    lap("setup/reserve/memset");
     init_out_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(*db, outLen);
     if (nAlns) aln_ranges_kernel<<<(unsigned) ((nAlns + 255) / 256), 256, 0, s>>>(*db, d_alns, nAlns, alnStart, alnCount, listA, d_listCnt);
     ctx->launches += 2;
     unsigned hCnt[2] = {0, 0};
     PG_CUDA(cudaMemcpyAsync(hCnt, d_listCnt, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     PG_CUDA(cudaStreamSynchronize(s));
+    lap("init_out+aln_ranges");
     unsigned active = hCnt[0];
     unsigned *cur = listA, *nxt = listB;
     int curIdx = 0;
@@ -736,7 +749,9 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
         active = hCnt[0];
         unsigned *t = cur; cur = nxt; nxt = t;
         curIdx = 1 - curIdx;
+        if (trace && round < 3) lap("  round");
     }
+    lap("rounds (rest)");
     keep_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(n, c.keepTarget, ext, used, keep, outLen, db->keys, ctx->ownLo, ctx->ownHi);
     ctx->launches += 1;
     unsigned long long *d_tot = ctx->small.as<unsigned long long>() + 5;   // [5] bytes, [6] kept
@@ -746,6 +761,7 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     PG_CUDA(cudaMemcpyAsync(h, d_tot, sizeof(h), cudaMemcpyDeviceToHost, s));
     PG_CUDA(cudaStreamSynchronize(s));
     PG_CUDA(cudaGetLastError());
+    lap("keep + scans");
     pg_seqdb *out = new pg_seqdb();
     out->n = h[1]; out->data_bytes = h[0]; out->dbtype = db->dbtype;
     PG_CUDA(cudaMalloc(&out->data, h[0] + 16));
@@ -754,12 +770,14 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     PG_CUDA(cudaMalloc(&out->keys, sizeof(unsigned) * (h[1] + 1)));
     unsigned char *outExt = nullptr;
     PG_CUDA(cudaMalloc(&outExt, h[1] + 1));
+    lap("cudaMalloc x5");
     materialize_kernel<<<NUM_SMS * 16, 256, 0, s>>>(*db, alnStart, ctx->exSegs.as<ExSeg>(), segCount, outLen, outOff, keep, keepIdx, ext,
                                                     out->data, out->offsets, out->lens, out->keys, outExt);
     ctx->launches++;
     cudaEventRecord(ctx->ev[EV_EX_END], s);
     PG_CUDA(cudaGetLastError());
     PG_TRY(seqdb_finalize(ctx, out));
+    lap("materialize + finalize");
     *outDb = out;
     *d_extended = outExt;
     ctx->exRan = true;
