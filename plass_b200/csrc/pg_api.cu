@@ -10,12 +10,14 @@ namespace pg {
 static thread_local std::string g_error;
 void set_error(const std::string &msg) { g_error = msg; }
 
-void seqdb_release(pg_seqdb *db) {
+// Device arrays of sequence DBs come from the stream-ordered pool (cudaMallocAsync; the pool keeps its memory,
+// see pg_init), so producing a new DB every iteration does not pay cudaMalloc / cudaFree each time.
+void seqdb_release(pg_seqdb *db, cudaStream_t s) {
     if (!db) return;
-    if (db->data) cudaFree(db->data);
-    if (db->offsets) cudaFree(db->offsets);
-    if (db->lens) cudaFree(db->lens);
-    if (db->keys) cudaFree(db->keys);
+    if (db->data) cudaFreeAsync(db->data, s);
+    if (db->offsets) cudaFreeAsync(db->offsets, s);
+    if (db->lens) cudaFreeAsync(db->lens, s);
+    if (db->keys) cudaFreeAsync(db->keys, s);
     delete db;
 }
 
@@ -164,6 +166,12 @@ int pg_init(int device, pg_context **out) {
     pg_context *ctx = new pg_context();
     ctx->device = device;
     PG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+        cudaMemPool_t pool;
+        PG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;                 // never give memory back to the driver between iterations
+        PG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     for (int i = 0; i < EV_COUNT; i++) PG_CUDA(cudaEventCreate(&ctx->ev[i]));
     memset(&ctx->timings, 0, sizeof(ctx->timings));
     *out = ctx;
@@ -195,17 +203,17 @@ int pg_seqdb_upload(pg_context *ctx, const pg_seqdb_view *v, pg_seqdb **out) {
     cudaSetDevice(ctx->device);
     pg_seqdb *db = new pg_seqdb();
     db->n = v->n; db->data_bytes = v->data_bytes; db->dbtype = v->dbtype;
-    PG_CUDA(cudaMalloc(&db->data, v->data_bytes + 16));
-    PG_CUDA(cudaMalloc(&db->offsets, sizeof(unsigned long long) * (v->n + 1)));
-    PG_CUDA(cudaMalloc(&db->lens, sizeof(unsigned) * (v->n + 1)));
-    PG_CUDA(cudaMalloc(&db->keys, sizeof(unsigned) * (v->n + 1)));
+    PG_CUDA(cudaMallocAsync(&db->data, v->data_bytes + 16, ctx->stream));
+    PG_CUDA(cudaMallocAsync(&db->offsets, sizeof(unsigned long long) * (v->n + 1), ctx->stream));
+    PG_CUDA(cudaMallocAsync(&db->lens, sizeof(unsigned) * (v->n + 1), ctx->stream));
+    PG_CUDA(cudaMallocAsync(&db->keys, sizeof(unsigned) * (v->n + 1), ctx->stream));
     PG_CUDA(cudaMemcpyAsync(db->data, v->data, v->data_bytes, cudaMemcpyHostToDevice, ctx->stream));
     PG_CUDA(cudaMemcpyAsync(db->offsets, v->offsets, sizeof(unsigned long long) * v->n, cudaMemcpyHostToDevice, ctx->stream));
     PG_CUDA(cudaMemcpyAsync(db->lens, v->lens, sizeof(unsigned) * v->n, cudaMemcpyHostToDevice, ctx->stream));
     PG_CUDA(cudaMemcpyAsync(db->keys, v->keys, sizeof(unsigned) * v->n, cudaMemcpyHostToDevice, ctx->stream));
     PG_TRY(seqdb_finalize(ctx, db));
     for (uint64_t i = 1; i < v->n; i++)
-        if (v->keys[i] <= v->keys[i - 1]) { seqdb_release(db); set_error("pg_seqdb_upload: keys must be strictly ascending (index order of a sequence DB)"); return 1; }
+        if (v->keys[i] <= v->keys[i - 1]) { seqdb_release(db, ctx->stream); set_error("pg_seqdb_upload: keys must be strictly ascending (index order of a sequence DB)"); return 1; }
     *out = db;
     return 0;
 }
@@ -225,8 +233,9 @@ int pg_seqdb_download(pg_context *ctx, const pg_seqdb *db, char **data, uint64_t
 uint64_t pg_seqdb_size(const pg_seqdb *db) { return db ? db->n : 0; }
 
 void pg_seqdb_free(pg_context *ctx, pg_seqdb *db) {
-    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-    seqdb_release(db);
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    seqdb_release(db, ctx->stream);
 }
 
 int pg_kmermatch(pg_context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **hits, uint64_t *n_hits) {
@@ -267,7 +276,7 @@ int pg_extend(pg_context *ctx, const pg_seqdb *db, const pg_aln *alns, uint64_t 
     unsigned char *dExt = nullptr;
     PG_TRY(ex_run(ctx, db, ctx->alns.as<pg_aln>(), n_alns, p, out_db, &dExt));
     if (extended) PG_TRY(to_host(ctx->stream, dExt, (*out_db)->n, extended));
-    cudaFree(dExt);
+    cudaFreeAsync(dExt, ctx->stream);
     end_call(ctx);
     return 0;
 }
@@ -291,7 +300,7 @@ int pg_assemble_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_param
         for (uint64_t i = 0; i < (*out_db)->n; i++) c += h[i];
         ctx->timings.n_extended = c;
     }
-    cudaFree(dExt);
+    cudaFreeAsync(dExt, ctx->stream);
     end_call(ctx);
     if (hits && n_hits) { PG_TRY(to_host(ctx->stream, dHits, nH, hits)); *n_hits = nH; }
     if (alns && n_alns) { PG_TRY(to_host(ctx->stream, dAlns, nA, alns)); *n_alns = nA; }
@@ -341,7 +350,7 @@ int pg_shard_finish(pg_context *ctx, const pg_seqdb *db, const void *device_pair
     if (rc == 0) rc = ex_run(ctx, db, dAlns, nA, ep, out_db, &dExt);
     ctx->ownLo = 0; ctx->ownHi = 0xFFFFFFFFu;
     if (rc != 0) return rc;
-    cudaFree(dExt);
+    cudaFreeAsync(dExt, ctx->stream);
     end_call(ctx);
     // the sort-#2 / reduce events of this call are valid, the extract / sort-#1 ones belong to pg_shard_pairs
     ctx->timings.extract_ms = keep.extract_ms; ctx->timings.sort1_ms = keep.sort1_ms; ctx->timings.sort1_scatter_ms = keep.sort1_scatter_ms;

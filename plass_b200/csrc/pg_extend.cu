@@ -764,13 +764,13 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     lap("keep + scans");
     pg_seqdb *out = new pg_seqdb();
     out->n = h[1]; out->data_bytes = h[0]; out->dbtype = db->dbtype;
-    PG_CUDA(cudaMalloc(&out->data, h[0] + 16));
-    PG_CUDA(cudaMalloc(&out->offsets, sizeof(unsigned long long) * (h[1] + 1)));
-    PG_CUDA(cudaMalloc(&out->lens, sizeof(unsigned) * (h[1] + 1)));
-    PG_CUDA(cudaMalloc(&out->keys, sizeof(unsigned) * (h[1] + 1)));
+    PG_CUDA(cudaMallocAsync(&out->data, h[0] + 16, s));
+    PG_CUDA(cudaMallocAsync(&out->offsets, sizeof(unsigned long long) * (h[1] + 1), s));
+    PG_CUDA(cudaMallocAsync(&out->lens, sizeof(unsigned) * (h[1] + 1), s));
+    PG_CUDA(cudaMallocAsync(&out->keys, sizeof(unsigned) * (h[1] + 1), s));
     unsigned char *outExt = nullptr;
-    PG_CUDA(cudaMalloc(&outExt, h[1] + 1));
-    lap("cudaMalloc x5");
+    PG_CUDA(cudaMallocAsync(&outExt, h[1] + 1, s));
+    lap("cudaMallocAsync x5");
     materialize_kernel<<<NUM_SMS * 16, 256, 0, s>>>(*db, alnStart, ctx->exSegs.as<ExSeg>(), segCount, outLen, outOff, keep, keepIdx, ext,
                                                     out->data, out->offsets, out->lens, out->keys, outExt);
     ctx->launches++;

@@ -44,6 +44,6 @@ int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHit
 // extension (pg_extend.cu): d_alns sorted by query; produces a new device DB
 int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAlns, const pg_ex_params *p, pg_seqdb **out, unsigned char **d_extended);
 int seqdb_finalize(Context *ctx, pg_seqdb *db);   // computes max_seq_len / residues / dense_keys on the device
-void seqdb_release(pg_seqdb *db);
+void seqdb_release(pg_seqdb *db, cudaStream_t s);
 int alloc_pinned(size_t bytes, void **out);        // pooled pinned host memory, released with pg_free_host
 }  // namespace pg

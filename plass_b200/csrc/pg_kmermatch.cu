@@ -47,29 +47,40 @@ __device__ __forceinline__ bool cand_less(const Cand &a, const Cand &b, int nt) 
 
 // k-mer index + score at position pos of the code array; returns false if the window holds X
 // (Sequence::kmerContainsX) or is a reverse-complement palindrome (kmermatcher.cpp:156-158).
-__device__ __forceinline__ bool make_kmer(const unsigned char *codes, int pos, int L, const KmConst &c, Cand &out) {
+// KT > 0: k is the compile-time constant KT (loops fully unrolled); KT == 0: k = c.k.  NTM: 1 nucleotides, 0 amino acids,
+// -1 decide at run time from c.nt.
+template <int KT, int NTM>
+__device__ __forceinline__ bool make_kmer_t(const unsigned char *codes, int pos, int L, const KmConst &c, Cand &out) {
+    const int k = KT > 0 ? KT : c.k;
+    const bool nt = NTM < 0 ? (c.nt != 0) : (NTM != 0);
     bool hasX = false;
-    if (c.nt) {
+    if (nt) {
         unsigned long long idx = 0;
-        for (int j = 0; j < c.k; j++) { const unsigned v = codes[pos + j]; hasX |= (v == (unsigned) c.xCode); idx = (idx << 2) | (v & 3u); }
+#pragma unroll
+        for (int j = 0; j < k; j++) { const unsigned v = codes[pos + j]; hasX |= (v == (unsigned) c.xCode); idx = (idx << 2) | (v & 3u); }
         if (hasX) return false;
         unsigned long long rev = 0, t = idx;     // Util::revComplement (Util.cpp:601-638)
-        for (int j = 0; j < c.k; j++) { rev = (rev << 2) | ((t & 3ULL) ^ 2ULL); t >>= 2; }
+#pragma unroll
+        for (int j = 0; j < k; j++) { rev = (rev << 2) | ((t & 3ULL) ^ 2ULL); t >>= 2; }
         if (rev == idx) return false;
         const bool pickRev = rev < idx;
         idx = pickRev ? rev : idx;
         out.score = (unsigned) (xxh64_u64(idx, c.seed) & 0xFFFFULL);
         out.kmer = pickRev ? (idx & ~(1ULL << 63)) : (idx | (1ULL << 63));
-        out.pos = pickRev ? (unsigned) (L - pos - c.k) : (unsigned) pos;
+        out.pos = pickRev ? (unsigned) (L - pos - k) : (unsigned) pos;
     } else {
         unsigned long long idx = 0, pw = 1;      // Indexer::int2index (Indexer.h:20-83)
-        for (int j = 0; j < c.k; j++) { const unsigned v = codes[pos + j]; hasX |= (v == (unsigned) c.xCode); idx += (unsigned long long) v * pw; pw *= c.base; }
+#pragma unroll
+        for (int j = 0; j < k; j++) { const unsigned v = codes[pos + j]; hasX |= (v == (unsigned) c.xCode); idx += (unsigned long long) v * pw; pw *= c.base; }
         if (hasX) return false;
         out.kmer = idx;
         out.pos = (unsigned) pos;
         out.score = (unsigned) (xxh64_u64(idx, c.seed) & 0xFFFFULL);
     }
     return true;
+}
+__device__ __forceinline__ bool make_kmer(const unsigned char *codes, int pos, int L, const KmConst &c, Cand &out) {
+    return make_kmer_t<0, -1>(codes, pos, L, c, out);
 }
 
 // The selection loop of kmermatcher.cpp:274-347 over candidates sorted by cand_less, run by ONE thread.
@@ -194,7 +205,7 @@ __device__ int select_sequential_packed(const PCand *sorted, int cnt, unsigned l
     return nOut;
 }
 
-template <int NMAX>
+template <int NMAX, int KT, int NTM>
 __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, const unsigned *__restrict__ list,
                                                            const unsigned *__restrict__ listCount, const KmConst c,
                                                            Rec *__restrict__ out, unsigned long long *__restrict__ outCount,
@@ -242,11 +253,11 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
         }
         // all k-mer windows, compacted in position order
         int cnt = 0;
-        const int nWin = L - c.k + 1;
+        const int nWin = L - (KT > 0 ? KT : c.k) + 1;
         for (int p0 = 0; p0 < nWin; p0 += 32) {
             const int pos = p0 + lane;
             Cand cd;
-            const bool ok = (pos < nWin) && make_kmer(codes, pos, L, c, cd);
+            const bool ok = (pos < nWin) && make_kmer_t<KT, NTM>(codes, pos, L, c, cd);
             const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
             if (ok) cand[cnt + __popc(m & ltMask)] = pack_cand(cd);
             cnt += __popc(m);
@@ -997,18 +1008,27 @@ static __global__ void kmer_count_kernel(const unsigned *__restrict__ lens, unsi
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(total, mine);
 }
 
+template <int NMAX, int KT, int NTM>
+static int launch_extract_warp_t(const pg_seqdb &db, const unsigned *list, const unsigned *listCount, unsigned hostCount, const KmConst &c,
+                                 Rec *out, unsigned long long *outCount, unsigned long long outCap, cudaStream_t stream, uint64_t *launches) {
+    const size_t smem = 4 * ((size_t) NMAX * sizeof(PCand) + (size_t) (NMAX + 1) * sizeof(Rec) + (NMAX + 40));
+    PG_CUDA(cudaFuncSetAttribute(extract_warp_kernel<NMAX, KT, NTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    unsigned blocks = (hostCount + 3) / 4;
+    const unsigned maxBlocks = NUM_SMS * 32;
+    if (blocks > maxBlocks) blocks = maxBlocks;
+    extract_warp_kernel<NMAX, KT, NTM><<<blocks, 128, smem, stream>>>(db, list, listCount, c, out, outCount, outCap);
+    if (launches) (*launches)++;
+    return 0;
+}
+
+// the workflow defaults (aa k = 14, nt k = 22) get fully unrolled instances, anything else the generic one
 template <int NMAX>
 static int launch_extract_warp(const pg_seqdb &db, const unsigned *list, const unsigned *listCount, unsigned hostCount, const KmConst &c,
                                Rec *out, unsigned long long *outCount, unsigned long long outCap, cudaStream_t stream, uint64_t *launches) {
     if (hostCount == 0) return 0;
-    const size_t smem = 4 * ((size_t) NMAX * sizeof(PCand) + (size_t) (NMAX + 1) * sizeof(Rec) + (NMAX + 40));
-    PG_CUDA(cudaFuncSetAttribute(extract_warp_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    unsigned blocks = (hostCount + 3) / 4;
-    const unsigned maxBlocks = NUM_SMS * 32;
-    if (blocks > maxBlocks) blocks = maxBlocks;
-    extract_warp_kernel<NMAX><<<blocks, 128, smem, stream>>>(db, list, listCount, c, out, outCount, outCap);
-    if (launches) (*launches)++;
-    return 0;
+    if (!c.nt && c.k == 14) return launch_extract_warp_t<NMAX, 14, 0>(db, list, listCount, hostCount, c, out, outCount, outCap, stream, launches);
+    if (c.nt && c.k == 22) return launch_extract_warp_t<NMAX, 22, 1>(db, list, listCount, hostCount, c, out, outCount, outCap, stream, launches);
+    return launch_extract_warp_t<NMAX, 0, -1>(db, list, listCount, hostCount, c, out, outCount, outCap, stream, launches);
 }
 
 // Stage 1: extraction.  Leaves the records in ws.recA, returns their count.

@@ -205,3 +205,38 @@ def test_sharded_iteration_equals_single_gpu(case, world, golden_root, ctx):
     assert len(hits) == len(ref_hits) and all(np.array_equal(hits[f], ref_hits[f]) for f in ("rep", "target", "score", "diag"))
     check_alns(alns, ref_alns, "%s sharded x%d" % (case, world))
     assert_same_entries(entries, ref_db.entries_by_key(), "%s sharded x%d output DB" % (case, world))
+
+
+SWEEP = [
+    # (case, overrides)  -- parameter values outside the workflow defaults exercise the generic kernel instances
+    ("example_aa", dict(kmer_size=10, alph_size=21, kmers_per_seq=20)),
+    ("example_aa", dict(kmer_size=12, kmers_per_seq=8, hash_shift=70, include_only_extendable=1)),
+    ("example_aa", dict(ignore_multi_kmer=0, kmers_per_seq=25)),
+    ("example_aa", dict(cov_mode=1, cov_thr=0.8)),
+    ("synth_nt", dict(kmer_size=15, kmers_per_seq=30, kmers_per_seq_scale=0.2, include_only_extendable=0)),
+    ("synth_nt", dict(kmer_size=27, kmers_per_seq=10, kmers_per_seq_scale=0.0, hash_shift=5)),
+    ("synth_nt", dict(ignore_multi_kmer=0)),
+]
+
+
+@pytest.mark.parametrize("case,over", SWEEP)
+def test_kmermatcher_param_sweep_matches_oracle(case, over, golden_root, ctx):
+    d, man = golden_case(case, golden_root)
+    steps = [s for s in man["steps"] if s["cmd"] == "kmermatcher"]
+    for s in (steps[0], steps[-1]):           # first iteration (reads) and last (contigs of mixed length)
+        seq = mmseqsdb.read_db(os.path.join(d, s["dbs"][0]))
+        nucl = seq.dbtype == 1
+        f = params.km_fields(s["args"], nucl)
+        f.update(over)
+        okp = ob.KmParams(**f)
+        okp.hash_start, okp.hash_end = 0, ob.U64MAX
+        want = ob.kmermatch(seq, okp)
+        ddb = ctx.upload(seq)
+        got = ctx.kmermatcher(ddb, api.KmParams(hash_start=0, hash_end=65535, **f))
+        ddb.free()
+        assert len(got) == len(want), (case, over, len(got), len(want))
+        for fld in ("rep", "target", "diag"):
+            assert np.array_equal(got[fld], want[fld]), (case, over, fld)
+        # the strand sign is only defined up to the documented tie hazard (nt); magnitudes must agree
+        assert np.array_equal(np.abs(got["score"]), np.abs(want["score"])), (case, over)
+        assert (got["score"] != want["score"]).sum() <= max(2, len(want) // 500), (case, over)
