@@ -284,6 +284,9 @@ def main():
             out, hits, alns = ctx.assemble_iteration(d_in, kp, rp, ep, want_intermediates=True)
             host_out = out.download()
             d2h = int(hits.nbytes + alns.nbytes + host_out.data.nbytes + host_out.offsets.nbytes + host_out.lens.nbytes + host_out.keys.nbytes)
+            # the step's results live in pinned blocks of the library's pool: drop them so that the next step reuses
+            # the blocks instead of pinning 2 GB of fresh host memory
+            del hits, alns, host_out
         out.free(); d_in.free()
         barrier()
         if i > 0:

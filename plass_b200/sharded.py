@@ -72,6 +72,7 @@ class ShardedIteration:
         if download:
             host = out.download()
             self.last_d2h_bytes = int(hits.nbytes + alns.nbytes + host.data.nbytes + host.offsets.nbytes + host.lens.nbytes + host.keys.nbytes)
+            del hits, alns, host
         return out
 
     def timings(self):
