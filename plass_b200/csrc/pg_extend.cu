@@ -185,6 +185,7 @@ __global__ void aln_ranges_kernel(const pg_seqdb db, const pg_aln *__restrict__ 
     alnStart[qi] = j;
     alnCount[qi] = (unsigned) (k - j);
     if (k - j >= 2) activeList[atomicAdd(activeCount, 1u)] = qi;   // only the self alignment: nothing can be popped for extension
+    if (k - j > EX_WARP_MAX_ALNS) atomicAdd(activeCount + 2, 1u);  // queries that need the heap path even for amino acids
 }
 
 __global__ void init_out_kernel(const pg_seqdb db, unsigned *__restrict__ outLen) {
@@ -396,6 +397,9 @@ __global__ void __launch_bounds__(256) extend_round_warp_kernel(const pg_seqdb d
         }
         const unsigned querySeqLen = st.querySeqLen;
         const bool entered = alive;                           // this element is in the queue of this round
+        // every lane resolves ITS target once (index + length): the pops below then need no dependent global loads
+        unsigned myTargetId = 0, myTargetLen = 0;
+        if (alive) { myTargetId = find_id(db.keys, (unsigned) db.n, r.dbKey); myTargetLen = db.lens[myTargetId] - 2; }
         // selectFragmentToExtend's predicate (assembleresult.cpp:40-57): failing elements are popped and dropped
         if (alive) {
             const bool notRightStartAndLeftStart = !(r.dbStartPos == 0 && r.qStartPos == 0);
@@ -423,9 +427,8 @@ __global__ void __launch_bounds__(256) extend_round_warp_kernel(const pg_seqdb d
             if ((int) lane == wl) alive = false;                   // popped
             const int bDbStart = __shfl_sync(0xFFFFFFFFu, r.dbStartPos, wl), bDbEnd = __shfl_sync(0xFFFFFFFFu, r.dbEndPos, wl);
             const int bQStart = __shfl_sync(0xFFFFFFFFu, r.qStartPos, wl), bQEnd = __shfl_sync(0xFFFFFFFFu, r.qEndPos, wl);
-            const unsigned bKey = __shfl_sync(0xFFFFFFFFu, r.dbKey, wl);
-            const unsigned targetId = find_id(db.keys, (unsigned) db.n, bKey);
-            const unsigned targetSeqLen = db.lens[targetId] - 2;
+            const unsigned targetId = __shfl_sync(0xFFFFFFFFu, myTargetId, wl);
+            const unsigned targetSeqLen = __shfl_sync(0xFFFFFFFFu, myTargetLen, wl);
             if (bDbStart == 0) {
                 if ((targetSeqLen - (unsigned) (bDbEnd + 1)) <= rightOff) continue;
             } else if (bQStart == 0) {
@@ -714,15 +717,16 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     unsigned *listA = (unsigned *) ((unsigned char *) work + ((sizeof(uint2) * (nAlns + 1) + 15) & ~(size_t) 15));
     unsigned *listB = listA + (n + 1);
     unsigned long long *d_cnt = ctx->small.as<unsigned long long>() + 24;   // [24] work count, [25] list counts (2 x u32)
-    unsigned *d_listCnt = (unsigned *) (d_cnt + 1);
-    PG_CUDA(cudaMemsetAsync(d_cnt, 0, 16, s));
+    unsigned *d_listCnt = (unsigned *) (d_cnt + 1);                          // [0],[1] list counters, [2] number of large queries
+    PG_CUDA(cudaMemsetAsync(d_cnt, 0, 24, s));
     lap("setup/reserve/memset");
     init_out_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(*db, outLen);
     if (nAlns) aln_ranges_kernel<<<(unsigned) ((nAlns + 255) / 256), 256, 0, s>>>(*db, d_alns, nAlns, alnStart, alnCount, listA, d_listCnt);
     ctx->launches += 2;
-    unsigned hCnt[2] = {0, 0};
-    PG_CUDA(cudaMemcpyAsync(hCnt, d_listCnt, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    unsigned hCnt[3] = {0, 0, 0};
+    PG_CUDA(cudaMemcpyAsync(hCnt, d_listCnt, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     PG_CUDA(cudaStreamSynchronize(s));
+    const bool needHeap = nt || hCnt[2] > 0;
     lap("init_out+aln_ranges");
     unsigned active = hCnt[0];
     unsigned *cur = listA, *nxt = listB;
@@ -739,11 +743,14 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
                 parkBuf, ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
             ctx->launches++;
         }
-        extend_round_kernel<<<(active + 127) / 128, 128, 0, s>>>(*db, d_alns, alnStart, alnCount, c, round == 0, cur, d_listCnt + curIdx,
-                                                                nxt, d_listCnt + (1 - curIdx), work, d_cnt, states, heapBuf, parkBuf,
-                                                                ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
+        if (needHeap) {
+            extend_round_kernel<<<(active + 127) / 128, 128, 0, s>>>(*db, d_alns, alnStart, alnCount, c, round == 0, cur, d_listCnt + curIdx,
+                                                                    nxt, d_listCnt + (1 - curIdx), work, d_cnt, states, heapBuf, parkBuf,
+                                                                    ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
+            ctx->launches++;
+        }
         extend_rescore_kernel<<<NUM_SMS * 8, 256, 0, s>>>(*db, alnStart, c, work, d_cnt, states, parkBuf, ctx->exSegs.as<ExSeg>());
-        ctx->launches += 2;
+        ctx->launches += 1;
         PG_CUDA(cudaMemcpyAsync(hCnt, d_listCnt + (1 - curIdx), sizeof(unsigned), cudaMemcpyDeviceToHost, s));
         PG_CUDA(cudaStreamSynchronize(s));
         active = hCnt[0];

@@ -17,7 +17,7 @@ struct pg_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[pg::EV_COUNT];
-    pg::DevBuf small, lists, recA, recB, radixWs, scratch, blockCounts, hits, alnAll, alns, flags, exWork, exSegs, exMeta, exLists, ntTab, buckets;
+    pg::DevBuf small, lists, recA, recB, radixWs, scratch, blockCounts, hits, alnAll, alns, flags, exWork, exSegs, exMeta, exLists, ntTab, buckets, buckets2;
     bool forceFullSort = false;   // tests: take the 8-pass sort + group_kernel path instead of the bucketed hash join
     unsigned ntTabN = 0;
     bool pairsInA = false;
