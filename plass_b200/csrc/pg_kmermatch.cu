@@ -948,7 +948,7 @@ __global__ void __launch_bounds__(256) reduce_emit_kernel(const Rec *__restrict_
 // buckets concatenate into the final (rep, target) order.
 // ------------------------------------------------------------------------------------------------
 constexpr int RB_THREADS = 256;
-constexpr int RB_MAX = 2048;          // pairs per bucket (shared-memory sort capacity)
+constexpr int RB_MAX = 8192;          // pairs per bucket (shared-memory sort capacity, 64 KiB of keys)
 
 struct RunState {                     // the scan state at the end of a bucket whose last run may continue in the next bucket
     unsigned valid;                   // 1: the last (rep, target) run of the bucket touches the bucket end
@@ -984,7 +984,8 @@ __global__ void __launch_bounds__(RB_THREADS) reduce_bucket_kernel(const Rec *__
                                                                    pg_hit *__restrict__ tmpHits, unsigned *__restrict__ hitCount,
                                                                    RunState *__restrict__ states, unsigned long long *__restrict__ firstKey,
                                                                    unsigned *__restrict__ overflow) {
-    __shared__ unsigned long long key[RB_MAX];
+    extern __shared__ __align__(16) unsigned char rb_smem[];
+    unsigned long long *key = reinterpret_cast<unsigned long long *>(rb_smem);
     __shared__ unsigned sWarp[RB_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const unsigned long long tMask = (keyBits >= 32) ? 0xFFFFFFFFULL : ((1ULL << keyBits) - 1ULL);
@@ -1359,10 +1360,10 @@ static int km_reduce_bucketed(Context *ctx, const pg_seqdb *db, Rec **pairsIO, R
     const int keyBits = bits_for(db->max_key);
     const double perRep = (double) nPairs / ((double) db->max_key + 1.0);
     int shift = 0;
-    while (shift < 15 && shift < keyBits && perRep * (double) (2u << shift) <= 512.0) shift++;
+    while (shift < 15 && shift < keyBits && perRep * (double) (2u << shift) <= 256.0) shift++;   // ~256 pairs per bucket on average
     if (keyBits + 17 + shift > 64) return 0;
     const unsigned nBuckets = (db->max_key >> shift) + 1;
-    if ((double) nPairs / nBuckets > 1400.0) return 0;     // representatives too heavy for the shared-memory sort
+    if ((double) nPairs / nBuckets > 2000.0) return 0;     // representatives too heavy for the shared-memory sort
     RadixPlan plan; plan.npasses = 0;
     plan_add_bits(plan, 0, 32 + shift, 32 + keyBits);
     PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nPairs)));
@@ -1390,7 +1391,8 @@ static int km_reduce_bucketed(Context *ctx, const pg_seqdb *db, Rec **pairsIO, R
     pair_bounds_kernel<<<NUM_SMS * 16, 256, 0, s>>>(sorted, nPairs, shift, d_start, d_end);
     // the temporary hits reuse the other record buffer (a hit is 16 bytes like a record, at most one per pair)
     pg_hit *tmpHits = reinterpret_cast<pg_hit *>(other);
-    reduce_bucket_kernel<<<std::min<unsigned>(nBuckets, NUM_SMS * 32), RB_THREADS, 0, s>>>(sorted, d_start, d_end, nBuckets, shift, keyBits, tmpHits, d_hcnt,
+    PG_CUDA(cudaFuncSetAttribute(reduce_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_MAX * (int) sizeof(unsigned long long)));
+    reduce_bucket_kernel<<<std::min<unsigned>(nBuckets, NUM_SMS * 32), RB_THREADS, RB_MAX * sizeof(unsigned long long), s>>>(sorted, d_start, d_end, nBuckets, shift, keyBits, tmpHits, d_hcnt,
                                                                                          d_states, d_first, d_over);
     reduce_fixup_kernel<<<(nBuckets + 255) / 256, 256, 0, s>>>(sorted, d_start, d_end, nBuckets, d_states, d_first, tmpHits, d_over);
     ctx->launches += 3;
