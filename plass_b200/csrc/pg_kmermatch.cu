@@ -947,8 +947,8 @@ __global__ void __launch_bounds__(256) reduce_emit_kernel(const Rec *__restrict_
 // runs the writeKmerMatcherResult scan on it.  Buckets are in representative order, so the hits of consecutive
 // buckets concatenate into the final (rep, target) order.
 // ------------------------------------------------------------------------------------------------
-constexpr int RB_THREADS = 256;
-constexpr int RB_MAX = 8192;          // pairs per bucket (shared-memory sort capacity, 64 KiB of keys)
+constexpr int RB_SMALL = 2048;        // buckets up to this many pairs: 128-thread CTAs with 16 KiB of keys (many CTAs per SM)
+constexpr int RB_MAX = 8192;          // larger buckets: 256-thread CTAs with 64 KiB of keys; beyond that the full sort is used
 
 struct RunState {                     // the scan state at the end of a bucket whose last run may continue in the next bucket
     unsigned valid;                   // 1: the last (rep, target) run of the bucket touches the bucket end
@@ -979,6 +979,7 @@ __device__ __forceinline__ void run_step(unsigned d, unsigned rv, unsigned &prev
     top++;
 }
 
+template <int RB_THREADS, int CAP_LO, int CAP_HI>      // handles the buckets with CAP_LO < count <= CAP_HI
 __global__ void __launch_bounds__(RB_THREADS) reduce_bucket_kernel(const Rec *__restrict__ in, const unsigned long long *__restrict__ start,
                                                                    const unsigned long long *__restrict__ end, unsigned nBuckets, int shift, int keyBits,
                                                                    pg_hit *__restrict__ tmpHits, unsigned *__restrict__ hitCount,
@@ -991,10 +992,12 @@ __global__ void __launch_bounds__(RB_THREADS) reduce_bucket_kernel(const Rec *__
     const unsigned long long tMask = (keyBits >= 32) ? 0xFFFFFFFFULL : ((1ULL << keyBits) - 1ULL);
     for (unsigned b = blockIdx.x; b < nBuckets; b += gridDim.x) {
         const unsigned long long s0 = start[b], e0 = end[b];
+        const unsigned count = (e0 > s0) ? (unsigned) (e0 - s0) : 0u;
+        if (CAP_LO == 0 && count == 0) { if (tid == 0) { hitCount[b] = 0; states[b].valid = 0; firstKey[b] = ~0ULL; } continue; }
+        if (count > RB_MAX) { if (CAP_LO == 0 && tid == 0) { hitCount[b] = 0; states[b].valid = 0; atomicExch(overflow, 1u); } continue; }
+        if (count <= (unsigned) CAP_LO || count > (unsigned) CAP_HI) continue;       // the other instance's bucket
         if (tid == 0) { hitCount[b] = 0; states[b].valid = 0; firstKey[b] = ~0ULL; }
-        if (e0 <= s0) continue;
-        const unsigned count = (unsigned) (e0 - s0);
-        if (count > RB_MAX) { if (tid == 0) atomicExch(overflow, 1u); continue; }
+        __syncthreads();
         int n2 = 1;
         while (n2 < (int) count) n2 <<= 1;
         // packed key: rep-in-bucket | target | biased diagonal | strand
@@ -1360,7 +1363,7 @@ static int km_reduce_bucketed(Context *ctx, const pg_seqdb *db, Rec **pairsIO, R
     const int keyBits = bits_for(db->max_key);
     const double perRep = (double) nPairs / ((double) db->max_key + 1.0);
     int shift = 0;
-    while (shift < 15 && shift < keyBits && perRep * (double) (2u << shift) <= 256.0) shift++;   // ~256 pairs per bucket on average
+    while (shift < 15 && shift < keyBits && perRep * (double) (2u << shift) <= 768.0) shift++;   // 400-768 pairs per bucket on average
     if (keyBits + 17 + shift > 64) return 0;
     const unsigned nBuckets = (db->max_key >> shift) + 1;
     if ((double) nPairs / nBuckets > 2000.0) return 0;     // representatives too heavy for the shared-memory sort
@@ -1391,9 +1394,12 @@ static int km_reduce_bucketed(Context *ctx, const pg_seqdb *db, Rec **pairsIO, R
     pair_bounds_kernel<<<NUM_SMS * 16, 256, 0, s>>>(sorted, nPairs, shift, d_start, d_end);
     // the temporary hits reuse the other record buffer (a hit is 16 bytes like a record, at most one per pair)
     pg_hit *tmpHits = reinterpret_cast<pg_hit *>(other);
-    PG_CUDA(cudaFuncSetAttribute(reduce_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_MAX * (int) sizeof(unsigned long long)));
-    reduce_bucket_kernel<<<std::min<unsigned>(nBuckets, NUM_SMS * 32), RB_THREADS, RB_MAX * sizeof(unsigned long long), s>>>(sorted, d_start, d_end, nBuckets, shift, keyBits, tmpHits, d_hcnt,
-                                                                                         d_states, d_first, d_over);
+    PG_CUDA(cudaFuncSetAttribute(reduce_bucket_kernel<256, RB_SMALL, RB_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_MAX * (int) sizeof(unsigned long long)));
+    reduce_bucket_kernel<128, 0, RB_SMALL><<<std::min<unsigned>(nBuckets, NUM_SMS * 64), 128, RB_SMALL * sizeof(unsigned long long), s>>>(
+        sorted, d_start, d_end, nBuckets, shift, keyBits, tmpHits, d_hcnt, d_states, d_first, d_over);
+    reduce_bucket_kernel<256, RB_SMALL, RB_MAX><<<std::min<unsigned>(nBuckets, NUM_SMS * 16), 256, RB_MAX * sizeof(unsigned long long), s>>>(
+        sorted, d_start, d_end, nBuckets, shift, keyBits, tmpHits, d_hcnt, d_states, d_first, d_over);
+    ctx->launches++;
     reduce_fixup_kernel<<<(nBuckets + 255) / 256, 256, 0, s>>>(sorted, d_start, d_end, nBuckets, d_states, d_first, tmpHits, d_over);
     ctx->launches += 3;
     PG_TRY(exclusive_scan_u32(d_hcnt, d_hoff, nBuckets, d_total, bb + oScan, scan_workspace_bytes(nBuckets), s, &ctx->launches));
