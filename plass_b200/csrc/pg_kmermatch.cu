@@ -263,28 +263,54 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
             if (ok) cand[cnt + __popc(m & ltMask)] = pack_cand(cd);
             cnt += __popc(m);
         }
-        int n2 = 1;
-        while (n2 < cnt) n2 <<= 1;
-        for (int i = cnt + lane; i < n2; i += 32) { cand[i].hi = ~0ULL; cand[i].lo = ~0ULL; }
-        __syncwarp();
-        // bitonic sort by (score, kmer, pos)   [std::sort at kmermatcher.cpp:266-272; total order => same result]
-        if (c.ignoreMulti) {
-            for (int kk = 2; kk <= n2; kk <<= 1) {
-                for (int j = kk >> 1; j > 0; j >>= 1) {
-                    for (int t = lane; t < (n2 >> 1); t += 32) {
-                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                        const int ix = i | j;
-                        const bool up = ((i & kk) == 0);
-                        const PCand a = cand[i], b = cand[ix];
-                        if (pc_less(b, a) == up) { cand[i] = b; cand[ix] = a; }
-                    }
-                    __syncwarp();
-                }
-            }
-        }
         // threshold of the bottom-m sketch (kmermatcher.cpp:223-238)
         const unsigned long long want = (unsigned long long) ((float) (c.kmersPerSeq - 1) + (c.scale * (float) L));
         const unsigned long long kmerConsidered = min(want, (unsigned long long) cnt);
+        // Short-cut for the common case of reads: every k-mer is selected (cnt <= kmerConsidered) and no k-mer occurs
+        // twice in the sequence.  Then the sorted walk of kmermatcher.cpp:274-347 selects all of them and their order is
+        // irrelevant (the records are re-ordered globally afterwards), so neither the sort nor the walk is needed.
+        // Duplicates are detected with a small open-addressing set in shared memory (the output staging area).
+        bool allDistinct = false;
+        if (c.ignoreMulti && cnt > 0 && kmerConsidered >= (unsigned long long) cnt) {
+            unsigned long long *set = reinterpret_cast<unsigned long long *>(outRecs);
+            constexpr unsigned SLOTS = 2 * NMAX;
+            for (int i = lane; i < (int) SLOTS; i += 32) set[i] = ~0ULL;
+            __syncwarp();
+            bool dup = false;
+            for (int i = lane; i < cnt; i += 32) {
+                const unsigned long long k63 = pc_kmer63(cand[i]);
+                unsigned slot = (unsigned) (mix64(k63) >> 32) & (SLOTS - 1);
+                while (true) {
+                    const unsigned long long old = atomicCAS(&set[slot], ~0ULL, k63);
+                    if (old == ~0ULL) break;
+                    if (old == k63) { dup = true; break; }
+                    slot = (slot + 1) & (SLOTS - 1);
+                }
+            }
+            allDistinct = __ballot_sync(0xFFFFFFFFu, dup) == 0;
+            __syncwarp();
+        }
+        if (!allDistinct) {
+            int n2 = 1;
+            while (n2 < cnt) n2 <<= 1;
+            for (int i = cnt + lane; i < n2; i += 32) { cand[i].hi = ~0ULL; cand[i].lo = ~0ULL; }
+            __syncwarp();
+            // bitonic sort by (score, kmer, pos)   [std::sort at kmermatcher.cpp:266-272; total order => same result]
+            if (c.ignoreMulti) {
+                for (int kk = 2; kk <= n2; kk <<= 1) {
+                    for (int j = kk >> 1; j > 0; j >>= 1) {
+                        for (int t = lane; t < (n2 >> 1); t += 32) {
+                            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                            const int ix = i | j;
+                            const bool up = ((i & kk) == 0);
+                            const PCand a = cand[i], b = cand[ix];
+                            if (pc_less(b, a) == up) { cand[i] = b; cand[ix] = a; }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
         int nOut = 0;
         // sequence-identity record first (:241-246)
         const unsigned sh16 = (unsigned) (seqHash & 0xFFFFULL);
@@ -292,7 +318,22 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
             if (lane == 0) { Rec r; r.w0 = seqHash; r.w1 = ((unsigned long long) id << 32) | ((unsigned long long) (L & 0xFFFF) << 16); outRecs[0] = r; }
             nOut = 1;
         }
-        if (cnt > 0 && kmerConsidered > 0) {
+        if (allDistinct) {
+            // all cnt k-mers are selected (unsorted), subject only to the shard's hash range
+            for (int p0 = 0; p0 < cnt; p0 += 32) {
+                const int i = p0 + lane;
+                bool emit = false; PCand pc; pc.hi = 0; pc.lo = 0;
+                if (i < cnt) { pc = cand[i]; const unsigned sc = pc_score(pc); emit = sc >= c.hashStart && sc <= c.hashEnd; }
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, emit);
+                if (emit) {
+                    Rec r;
+                    r.w0 = pc_kmer_stored(pc, c.nt);
+                    r.w1 = ((unsigned long long) id << 32) | ((unsigned long long) (L & 0xFFFF) << 16) | (pc_pos(pc) & 0xFFFFu);
+                    outRecs[nOut + __popc(m & ltMask)] = r;
+                }
+                nOut += __popc(m);
+            }
+        } else if (cnt > 0 && kmerConsidered > 0) {
             if (c.ignoreMulti) {
                 // t = score of the kmerConsidered-th smallest; candidates = scores <= t; ties of the last bin = tooMuch
                 const unsigned t = pc_score(cand[kmerConsidered - 1]);
