@@ -1168,6 +1168,288 @@ __global__ void compact_hits_kernel(const pg_hit *__restrict__ tmpHits, const un
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// reduce, fast path v2: sort the pairs by the representative only (ceil(keyBits/8) radix passes), then one WARP per
+// representative sorts that representative's pairs by (target, diagonal, strand) in registers (bitonic network over
+// warp shuffles, up to 128 pairs) and runs the writeKmerMatcherResult scan on them.  Representatives with more pairs go
+// to a CTA-wide shared-memory sort.  The reference's scan does not stop at a change of representative when the next
+// block starts with the same target id; the warp therefore peeks at the following representative(s).
+// ------------------------------------------------------------------------------------------------
+constexpr int SEG_WARP_MAX = 128;
+constexpr int SEG_BLOCK_MAX = 8192;
+
+__global__ void seg_bounds_kernel(const Rec *__restrict__ in, unsigned long long n, unsigned long long *__restrict__ start,
+                                  unsigned long long *__restrict__ end) {
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
+        const unsigned rep = (unsigned) (in[i].w0 >> 32);
+        if (i == 0) start[rep] = 0;
+        else {
+            const unsigned prev = (unsigned) (in[i - 1].w0 >> 32);
+            if (prev != rep) { start[rep] = i; end[prev] = i; }
+        }
+        if (i == n - 1) end[rep] = n;
+    }
+}
+
+template <int SLOTS>
+__device__ __forceinline__ void warp_bitonic(unsigned long long (&r)[SLOTS], int n2, unsigned lane) {
+    for (int kk = 2; kk <= n2; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int js = j >> 5;
+#pragma unroll
+                for (int sl = 0; sl < SLOTS; sl++) {
+                    if ((sl & js) == 0 && (sl | js) < SLOTS) {
+                        const bool up = (((sl * 32 + (int) lane) & kk) == 0);
+                        const unsigned long long a = r[sl], b = r[sl | js];
+                        if ((b < a) == up) { r[sl] = b; r[sl | js] = a; }
+                    }
+                }
+            } else {
+                const bool lower = ((lane & (unsigned) j) == 0);
+#pragma unroll
+                for (int sl = 0; sl < SLOTS; sl++) {
+                    const unsigned long long p = __shfl_xor_sync(0xFFFFFFFFu, r[sl], j);
+                    const bool up = (((sl * 32 + (int) lane) & kk) == 0);
+                    r[sl] = (lower == up) ? min(r[sl], p) : max(r[sl], p);
+                }
+            }
+        }
+    }
+}
+
+struct ScanState { unsigned prevDiag, diagCnt, revCnt, maxDiag, best, bestRev, top; };
+
+// The reference's scan for (rep A, target X) reached the end of A's block.  If the next representative's smallest
+// target is X too, the scan goes on through that run (kmermatcher.cpp:880 tests only the target id), possibly over
+// several representatives.  Executed by a whole warp; returns the final state in every lane.  *overflow is raised when
+// the continued run is longer than the staging list.
+__device__ ScanState continue_run_warp(const Rec *__restrict__ in, unsigned long long n, const unsigned long long *__restrict__ end,
+                                       unsigned long long nextPos, unsigned X, ScanState st, unsigned *stage /* >= 256 words */,
+                                       unsigned *overflow) {
+    const unsigned lane = threadIdx.x & 31;
+    while (nextPos < n) {
+        const unsigned B = (unsigned) (in[nextPos].w0 >> 32);
+        const unsigned long long be = end[B];
+        unsigned minT = 0xFFFFFFFFu;
+        for (unsigned long long i = nextPos + lane; i < be; i += 32) minT = min(minT, (unsigned) in[i].w0);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) minT = min(minT, __shfl_xor_sync(0xFFFFFFFFu, minT, o));
+        if (minT != X) break;
+        // collect (diagonal, strand) of B's pairs with target X
+        unsigned cnt = 0;
+        for (unsigned long long i0 = nextPos; i0 < be; i0 += 32) {
+            const unsigned long long i = i0 + lane;
+            bool hit = false; unsigned v = 0;
+            if (i < be) { const Rec r = in[i]; hit = (unsigned) r.w0 == X; v = (unsigned) ((r.w1 & 0xFFFFULL) << 1) | (unsigned) ((r.w1 >> 16) & 1ULL); }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+            const unsigned pos = cnt + __popc(m & ((1u << lane) - 1u));
+            if (hit && pos < 256) stage[pos] = v;
+            cnt += __popc(m);
+        }
+        __syncwarp();
+        if (cnt > 256) { if (lane == 0) atomicExch(overflow, 1u); break; }
+        if (lane == 0) {
+            for (unsigned i = 1; i < cnt; i++) { const unsigned v = stage[i]; int j = (int) i - 1; while (j >= 0 && stage[j] > v) { stage[j + 1] = stage[j]; j--; } stage[j + 1] = v; }
+            for (unsigned i = 0; i < cnt; i++) run_step(stage[i] >> 1, stage[i] & 1u, st.prevDiag, st.diagCnt, st.revCnt, st.maxDiag, st.best, st.bestRev, st.top);
+        }
+        st.prevDiag = __shfl_sync(0xFFFFFFFFu, st.prevDiag, 0); st.diagCnt = __shfl_sync(0xFFFFFFFFu, st.diagCnt, 0);
+        st.revCnt = __shfl_sync(0xFFFFFFFFu, st.revCnt, 0); st.maxDiag = __shfl_sync(0xFFFFFFFFu, st.maxDiag, 0);
+        st.best = __shfl_sync(0xFFFFFFFFu, st.best, 0); st.bestRev = __shfl_sync(0xFFFFFFFFu, st.bestRev, 0); st.top = __shfl_sync(0xFFFFFFFFu, st.top, 0);
+        __syncwarp();
+        if ((unsigned long long) cnt != be - nextPos) break;      // B has other targets after X: the scan stops inside B
+        nextPos = be;                                              // B consisted of X only: look at the next representative
+    }
+    return st;
+}
+
+__global__ void __launch_bounds__(256) reduce_rep_warp_kernel(const Rec *__restrict__ in, unsigned long long n,
+                                                              const unsigned long long *__restrict__ start, const unsigned long long *__restrict__ end,
+                                                              unsigned nKeys, pg_hit *__restrict__ tmpHits, unsigned *__restrict__ hitCount,
+                                                              unsigned *__restrict__ bigList, unsigned *__restrict__ bigCount, unsigned *__restrict__ overflow) {
+    __shared__ unsigned long long sKeys[8][SEG_WARP_MAX];
+    __shared__ unsigned sStage[8][256];
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned warpsTotal = gridDim.x * (blockDim.x >> 5);
+    for (unsigned rep = blockIdx.x * (blockDim.x >> 5) + w; rep < nKeys; rep += warpsTotal) {
+        const unsigned long long s0 = start[rep], e0 = end[rep];
+        if (e0 <= s0) continue;
+        const unsigned count = (unsigned) (e0 - s0);
+        if (count > SEG_WARP_MAX) { if (lane == 0) bigList[atomicAdd(bigCount, 1u)] = rep; continue; }
+        int n2 = 32;
+        while (n2 < (int) count) n2 <<= 1;
+        unsigned long long r[4];
+#pragma unroll
+        for (int sl = 0; sl < 4; sl++) {
+            const unsigned e = sl * 32 + lane;
+            r[sl] = ~0ULL;
+            if (e < count) { const Rec p = in[s0 + e]; r[sl] = ((unsigned long long) (unsigned) p.w0 << 17) | ((p.w1 & 0xFFFFULL) << 1) | ((p.w1 >> 16) & 1ULL); }
+        }
+        if (n2 <= 32) { unsigned long long q[1] = {r[0]}; warp_bitonic<1>(q, 32, lane); r[0] = q[0]; }
+        else if (n2 <= 64) { unsigned long long q[2] = {r[0], r[1]}; warp_bitonic<2>(q, 64, lane); r[0] = q[0]; r[1] = q[1]; }
+        else warp_bitonic<4>(r, 128, lane);
+#pragma unroll
+        for (int sl = 0; sl < 4; sl++) sKeys[w][sl * 32 + lane] = r[sl];
+        __syncwarp();
+        const unsigned long long *key = sKeys[w];
+        unsigned nEmitted = 0;
+        // the last run of the block (largest target) is the only one that can reach the block end
+        bool ownsLast = false; ScanState lastSt; lastSt.prevDiag = lastSt.diagCnt = lastSt.revCnt = lastSt.maxDiag = lastSt.best = lastSt.bestRev = lastSt.top = 0;
+        long long lastSlot = -1; unsigned lastTarget = 0;
+        for (int sl = 0; sl * 32 < (int) count; sl++) {
+            const int i = sl * 32 + (int) lane;
+            bool emit = false; pg_hit h; h.rep = rep; h.target = 0; h.score = 0; h.diag = 0;
+            bool reached = false; ScanState st; st.prevDiag = st.diagCnt = st.revCnt = st.maxDiag = st.best = st.bestRev = st.top = 0;
+            if (i < (int) count) {
+                const unsigned long long k = key[i];
+                if (i == 0 || (key[i - 1] >> 17) != (k >> 17)) {
+                    const unsigned target = (unsigned) (k >> 17);
+                    st.prevDiag = (unsigned) ((k >> 1) & 0xFFFFULL); st.best = st.prevDiag; st.bestRev = (unsigned) (k & 1ULL);
+                    int j = i;
+                    while (j < (int) count && (unsigned) (key[j] >> 17) == target) {
+                        run_step((unsigned) ((key[j] >> 1) & 0xFFFFULL), (unsigned) (key[j] & 1ULL), st.prevDiag, st.diagCnt, st.revCnt, st.maxDiag, st.best, st.bestRev, st.top);
+                        j++;
+                    }
+                    emit = target != rep;
+                    h.target = target;
+                    h.score = st.bestRev ? -(int) st.top : (int) st.top;
+                    h.diag = (int) (short) (unsigned short) (st.best - 32768u);
+                    reached = (j == (int) count);
+                }
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, emit);
+            const long long slot = (long long) (s0 + nEmitted + __popc(m & ((1u << lane) - 1u)));
+            if (emit) tmpHits[slot] = h;
+            if (reached) { ownsLast = true; lastSt = st; lastSlot = emit ? slot : -1; lastTarget = h.target; }
+            nEmitted += __popc(m);
+        }
+        // continuation of the last run into the following representative(s)
+        const unsigned ownerMask = __ballot_sync(0xFFFFFFFFu, ownsLast);
+        if (ownerMask && e0 < n) {
+            const int owner = __ffs(ownerMask) - 1;
+            ScanState st;
+            st.prevDiag = __shfl_sync(0xFFFFFFFFu, lastSt.prevDiag, owner); st.diagCnt = __shfl_sync(0xFFFFFFFFu, lastSt.diagCnt, owner);
+            st.revCnt = __shfl_sync(0xFFFFFFFFu, lastSt.revCnt, owner); st.maxDiag = __shfl_sync(0xFFFFFFFFu, lastSt.maxDiag, owner);
+            st.best = __shfl_sync(0xFFFFFFFFu, lastSt.best, owner); st.bestRev = __shfl_sync(0xFFFFFFFFu, lastSt.bestRev, owner);
+            st.top = __shfl_sync(0xFFFFFFFFu, lastSt.top, owner);
+            const unsigned X = __shfl_sync(0xFFFFFFFFu, lastTarget, owner);
+            const long long slot = __shfl_sync(0xFFFFFFFFu, lastSlot, owner);
+            const unsigned topBefore = st.top;
+            st = continue_run_warp(in, n, end, e0, X, st, sStage[w], overflow);
+            if (st.top != topBefore && slot >= 0 && lane == 0) {
+                pg_hit h; h.rep = rep; h.target = X;
+                h.score = st.bestRev ? -(int) st.top : (int) st.top;
+                h.diag = (int) (short) (unsigned short) (st.best - 32768u);
+                tmpHits[slot] = h;
+            }
+        }
+        if (lane == 0) hitCount[rep] = nEmitted;
+        __syncwarp();
+    }
+}
+
+// representatives with more than SEG_WARP_MAX pairs: one CTA each, bitonic sort in shared memory
+__global__ void __launch_bounds__(256) reduce_rep_block_kernel(const Rec *__restrict__ in, unsigned long long n,
+                                                               const unsigned long long *__restrict__ start, const unsigned long long *__restrict__ end,
+                                                               const unsigned *__restrict__ bigList, const unsigned *__restrict__ bigCount,
+                                                               pg_hit *__restrict__ tmpHits, unsigned *__restrict__ hitCount, unsigned *__restrict__ overflow) {
+    extern __shared__ __align__(16) unsigned char rb_smem[];
+    unsigned long long *key = reinterpret_cast<unsigned long long *>(rb_smem);
+    __shared__ unsigned sWarp[8];
+    __shared__ unsigned sStage[256];
+    __shared__ ScanState sLast;
+    __shared__ long long sLastSlot;
+    __shared__ unsigned sLastTarget, sHasLast;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned nBig = *bigCount;
+    for (unsigned bi = blockIdx.x; bi < nBig; bi += gridDim.x) {
+        const unsigned rep = bigList[bi];
+        const unsigned long long s0 = start[rep], e0 = end[rep];
+        const unsigned count = (unsigned) (e0 - s0);
+        if (count > SEG_BLOCK_MAX) { if (tid == 0) { atomicExch(overflow, 1u); hitCount[rep] = 0; } continue; }
+        int n2 = 1;
+        while (n2 < (int) count) n2 <<= 1;
+        for (int i = tid; i < n2; i += 256) {
+            unsigned long long k = ~0ULL;
+            if (i < (int) count) { const Rec p = in[s0 + i]; k = ((unsigned long long) (unsigned) p.w0 << 17) | ((p.w1 & 0xFFFFULL) << 1) | ((p.w1 >> 16) & 1ULL); }
+            key[i] = k;
+        }
+        if (tid == 0) sHasLast = 0;
+        __syncthreads();
+        for (int kk = 2; kk <= n2; kk <<= 1) {
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (n2 >> 1); t += 256) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int ix = i | j;
+                    const bool up = ((i & kk) == 0);
+                    const unsigned long long a = key[i], c2 = key[ix];
+                    if ((c2 < a) == up) { key[i] = c2; key[ix] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        unsigned long long base = 0;
+        for (int i0 = 0; i0 < (int) count; i0 += 256) {
+            const int i = i0 + tid;
+            bool emit = false; pg_hit h; h.rep = rep; h.target = 0; h.score = 0; h.diag = 0;
+            bool reached = false; ScanState st; st.prevDiag = st.diagCnt = st.revCnt = st.maxDiag = st.best = st.bestRev = st.top = 0;
+            if (i < (int) count) {
+                const unsigned long long k = key[i];
+                if (i == 0 || (key[i - 1] >> 17) != (k >> 17)) {
+                    const unsigned target = (unsigned) (k >> 17);
+                    st.prevDiag = (unsigned) ((k >> 1) & 0xFFFFULL); st.best = st.prevDiag; st.bestRev = (unsigned) (k & 1ULL);
+                    int j = i;
+                    while (j < (int) count && (unsigned) (key[j] >> 17) == target) {
+                        run_step((unsigned) ((key[j] >> 1) & 0xFFFFULL), (unsigned) (key[j] & 1ULL), st.prevDiag, st.diagCnt, st.revCnt, st.maxDiag, st.best, st.bestRev, st.top);
+                        j++;
+                    }
+                    emit = target != rep;
+                    h.target = target;
+                    h.score = st.bestRev ? -(int) st.top : (int) st.top;
+                    h.diag = (int) (short) (unsigned short) (st.best - 32768u);
+                    reached = (j == (int) count);
+                }
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, emit);
+            if (lane == 0) sWarp[w] = __popc(m);
+            __syncthreads();
+            unsigned off = 0, total = 0;
+            for (int ww = 0; ww < 8; ww++) { if (ww < w) off += sWarp[ww]; total += sWarp[ww]; }
+            const long long slot = (long long) (s0 + base + off + __popc(m & ((1u << lane) - 1u)));
+            if (emit) tmpHits[slot] = h;
+            if (reached) { sLast = st; sLastSlot = emit ? slot : -1; sLastTarget = h.target; sHasLast = 1; }
+            base += total;
+            __syncthreads();
+        }
+        if (w == 0 && sHasLast && e0 < n) {
+            ScanState st = sLast;
+            const unsigned topBefore = st.top;
+            st = continue_run_warp(in, n, end, e0, sLastTarget, st, sStage, overflow);
+            if (st.top != topBefore && sLastSlot >= 0 && lane == 0) {
+                pg_hit h; h.rep = rep; h.target = sLastTarget;
+                h.score = st.bestRev ? -(int) st.top : (int) st.top;
+                h.diag = (int) (short) (unsigned short) (st.best - 32768u);
+                tmpHits[sLastSlot] = h;
+            }
+        }
+        if (tid == 0) hitCount[rep] = (unsigned) base;
+        __syncthreads();
+    }
+}
+
+__global__ void compact_rep_hits_kernel(const pg_hit *__restrict__ tmpHits, const unsigned long long *__restrict__ start,
+                                        const unsigned *__restrict__ hitCount, const unsigned long long *__restrict__ hitOffset, unsigned nKeys,
+                                        pg_hit *__restrict__ hits) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned warpsTotal = gridDim.x * (blockDim.x >> 5);
+    for (unsigned rep = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rep < nKeys; rep += warpsTotal) {
+        const unsigned c = hitCount[rep];
+        if (c == 0) continue;
+        const unsigned long long s0 = start[rep], o = hitOffset[rep];
+        for (unsigned i = lane; i < c; i += 32) hits[o + i] = tmpHits[s0 + i];
+    }
+}
+
 // exclusive scan of per-block counts (single block, sequential chunks; counts <= 2^24 blocks)
 __global__ void __launch_bounds__(1024) scan_counts_kernel(const unsigned *__restrict__ counts, unsigned long long nBlocks,
                                                            unsigned long long *__restrict__ offsets, unsigned long long *__restrict__ total) {
@@ -1461,6 +1743,60 @@ static int km_reduce_bucketed(Context *ctx, const pg_seqdb *db, Rec **pairsIO, R
     return 0;
 }
 
+// fast path v2 of stage 3 (see reduce_rep_warp_kernel); *ok = false if a representative exceeded the CTA capacity
+static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, Rec **tmpIO, uint64_t nPairs, pg_hit **d_hits, uint64_t *nHits, bool *ok) {
+    cudaStream_t s = ctx->stream;
+    *ok = false;
+    Rec *pairs = *pairsIO, *tmp = *tmpIO;
+    const int keyBits = bits_for(db->max_key);
+    const unsigned nKeys = db->max_key + 1;
+    RadixPlan plan; plan.npasses = 0;
+    plan_add_bits(plan, 0, 32, 32 + keyBits);
+    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nPairs)));
+    Rec *sorted = pairs;
+    PG_TRY(radix_sort(pairs, tmp, nPairs, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches));
+    cudaEventRecord(ctx->ev[EV_SORT2_END], s);
+    Rec *other = (sorted == pairs) ? tmp : pairs;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t) 15; return r; };
+    const size_t oStart = take(sizeof(unsigned long long) * nKeys), oEnd = take(sizeof(unsigned long long) * nKeys);
+    const size_t oCnt = take(sizeof(unsigned) * ((size_t) nKeys + 1));
+    const size_t oOff = take(sizeof(unsigned long long) * ((size_t) nKeys + 2)), oBig = take(sizeof(unsigned) * ((size_t) nKeys + 1));
+    const size_t oScan = take(scan_workspace_bytes(nKeys));
+    PG_TRY(ctx->buckets2.reserve(o));
+    unsigned char *bb = ctx->buckets2.as<unsigned char>();
+    unsigned long long *d_start = (unsigned long long *) (bb + oStart), *d_end = (unsigned long long *) (bb + oEnd);
+    unsigned *d_hcnt = (unsigned *) (bb + oCnt), *d_big = (unsigned *) (bb + oBig);
+    unsigned long long *d_hoff = (unsigned long long *) (bb + oOff);
+    unsigned *d_over = (unsigned *) (ctx->small.as<unsigned long long>() + 30);     // [30] overflow flag + big count, [31] total hits
+    unsigned *d_bigCnt = d_over + 1;
+    unsigned long long *d_total = ctx->small.as<unsigned long long>() + 31;
+    PG_CUDA(cudaMemsetAsync(d_start, 0, oOff, s));   // start, end, hit counts
+    PG_CUDA(cudaMemsetAsync(d_over, 0, 2 * sizeof(unsigned), s));
+    seg_bounds_kernel<<<NUM_SMS * 16, 256, 0, s>>>(sorted, nPairs, d_start, d_end);
+    pg_hit *tmpHits = reinterpret_cast<pg_hit *>(other);   // a hit is 16 bytes like a record, at most one per pair
+    reduce_rep_warp_kernel<<<NUM_SMS * 16, 256, 0, s>>>(sorted, nPairs, d_start, d_end, nKeys, tmpHits, d_hcnt, d_big, d_bigCnt, d_over);
+    PG_CUDA(cudaFuncSetAttribute(reduce_rep_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_BLOCK_MAX * (int) sizeof(unsigned long long)));
+    reduce_rep_block_kernel<<<NUM_SMS * 3, 256, SEG_BLOCK_MAX * sizeof(unsigned long long), s>>>(sorted, nPairs, d_start, d_end, d_big, d_bigCnt, tmpHits, d_hcnt, d_over);
+    ctx->launches += 3;
+    PG_TRY(exclusive_scan_u32(d_hcnt, d_hoff, nKeys, d_total, bb + oScan, scan_workspace_bytes(nKeys), s, &ctx->launches));
+    unsigned long long h = 0; unsigned over = 0;
+    PG_CUDA(cudaMemcpyAsync(&h, d_total, sizeof(h), cudaMemcpyDeviceToHost, s));
+    PG_CUDA(cudaMemcpyAsync(&over, d_over, sizeof(over), cudaMemcpyDeviceToHost, s));
+    PG_CUDA(cudaStreamSynchronize(s));
+    PG_CUDA(cudaGetLastError());
+    if (over) { *pairsIO = sorted; *tmpIO = other; return 0; }
+    PG_TRY(ctx->hits.reserve(sizeof(pg_hit) * (h + 1)));
+    compact_rep_hits_kernel<<<NUM_SMS * 16, 256, 0, s>>>(tmpHits, d_start, d_hcnt, d_hoff, nKeys, ctx->hits.as<pg_hit>());
+    ctx->launches++;
+    cudaEventRecord(ctx->ev[EV_REDUCE_END], s);
+    PG_CUDA(cudaGetLastError());
+    *d_hits = ctx->hits.as<pg_hit>();
+    *nHits = h;
+    *ok = true;
+    return 0;
+}
+
 // Stage 3: sort #2 + best-diagonal reduction.  Pairs are in `pairs` (device), scratch in `tmp`.
 int km_reduce(Context *ctx, const pg_seqdb *db, Rec *pairs, Rec *tmp, uint64_t nPairs, pg_hit **d_hits, uint64_t *nHits) {
     cudaStream_t s = ctx->stream;
@@ -1468,7 +1804,7 @@ int km_reduce(Context *ctx, const pg_seqdb *db, Rec *pairs, Rec *tmp, uint64_t n
     if (nPairs == 0) return 0;
     if (!ctx->forceFullSort) {
         bool ok = false;
-        PG_TRY(km_reduce_bucketed(ctx, db, &pairs, &tmp, nPairs, d_hits, nHits, &ok));
+        PG_TRY(km_reduce_segmented(ctx, db, &pairs, &tmp, nPairs, d_hits, nHits, &ok));
         if (ok) return 0;
     }
     const int keyBits = bits_for(db->max_key);
