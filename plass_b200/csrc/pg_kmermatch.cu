@@ -11,6 +11,8 @@
 #include "pg_scan.cuh"
 #include "pg_tables.h"
 
+#include <type_traits>
+
 namespace pg {
 
 __constant__ unsigned char c_aa2num[256];   // ASCII -> code of the active k-mer alphabet
@@ -1175,7 +1177,7 @@ __global__ void compact_hits_kernel(const pg_hit *__restrict__ tmpHits, const un
 // to a CTA-wide shared-memory sort.  The reference's scan does not stop at a change of representative when the next
 // block starts with the same target id; the warp therefore peeks at the following representative(s).
 // ------------------------------------------------------------------------------------------------
-constexpr int SEG_WARP_MAX = 128;
+constexpr int SEG_WARP_MAX = 512;     // pairs one warp sorts in registers (16 per lane)
 constexpr int SEG_BLOCK_MAX = 8192;
 
 __global__ void seg_bounds_kernel(const Rec *__restrict__ in, unsigned long long n, unsigned long long *__restrict__ start,
@@ -1196,13 +1198,18 @@ __device__ __forceinline__ void warp_bitonic(unsigned long long (&r)[SLOTS], int
     for (int kk = 2; kk <= n2; kk <<= 1) {
         for (int j = kk >> 1; j > 0; j >>= 1) {
             if (j >= 32) {
-                const int js = j >> 5;
+                // partner lives in the same lane, another register: js is resolved at compile time so that r[] stays in registers
 #pragma unroll
-                for (int sl = 0; sl < SLOTS; sl++) {
-                    if ((sl & js) == 0 && (sl | js) < SLOTS) {
-                        const bool up = (((sl * 32 + (int) lane) & kk) == 0);
-                        const unsigned long long a = r[sl], b = r[sl | js];
-                        if ((b < a) == up) { r[sl] = b; r[sl | js] = a; }
+                for (int js = 1; js < SLOTS; js <<= 1) {
+                    if (j == js * 32) {
+#pragma unroll
+                        for (int sl = 0; sl < SLOTS; sl++) {
+                            if ((sl & js) == 0) {
+                                const bool up = (((sl * 32 + (int) lane) & kk) == 0);
+                                const unsigned long long a = r[sl], b = r[sl | js];
+                                if ((b < a) == up) { r[sl] = b; r[sl | js] = a; }
+                            }
+                        }
                     }
                 }
             } else {
@@ -1278,18 +1285,25 @@ __global__ void __launch_bounds__(256) reduce_rep_warp_kernel(const Rec *__restr
         if (count > SEG_WARP_MAX) { if (lane == 0) bigList[atomicAdd(bigCount, 1u)] = rep; continue; }
         int n2 = 32;
         while (n2 < (int) count) n2 <<= 1;
-        unsigned long long r[4];
+        // load + sort + stage in shared memory, with as many registers per lane as this representative needs
+        auto sortSegment = [&](auto slotsTag) {
+            constexpr int SL = decltype(slotsTag)::value;
+            unsigned long long r[SL];
 #pragma unroll
-        for (int sl = 0; sl < 4; sl++) {
-            const unsigned e = sl * 32 + lane;
-            r[sl] = ~0ULL;
-            if (e < count) { const Rec p = in[s0 + e]; r[sl] = ((unsigned long long) (unsigned) p.w0 << 17) | ((p.w1 & 0xFFFFULL) << 1) | ((p.w1 >> 16) & 1ULL); }
-        }
-        if (n2 <= 32) { unsigned long long q[1] = {r[0]}; warp_bitonic<1>(q, 32, lane); r[0] = q[0]; }
-        else if (n2 <= 64) { unsigned long long q[2] = {r[0], r[1]}; warp_bitonic<2>(q, 64, lane); r[0] = q[0]; r[1] = q[1]; }
-        else warp_bitonic<4>(r, 128, lane);
+            for (int sl = 0; sl < SL; sl++) {
+                const unsigned e = sl * 32 + lane;
+                r[sl] = ~0ULL;
+                if (e < count) { const Rec p = in[s0 + e]; r[sl] = ((unsigned long long) (unsigned) p.w0 << 17) | ((p.w1 & 0xFFFFULL) << 1) | ((p.w1 >> 16) & 1ULL); }
+            }
+            warp_bitonic<SL>(r, SL * 32, lane);
 #pragma unroll
-        for (int sl = 0; sl < 4; sl++) sKeys[w][sl * 32 + lane] = r[sl];
+            for (int sl = 0; sl < SL; sl++) sKeys[w][sl * 32 + lane] = r[sl];
+        };
+        if (n2 <= 32) sortSegment(std::integral_constant<int, 1>());
+        else if (n2 <= 64) sortSegment(std::integral_constant<int, 2>());
+        else if (n2 <= 128) sortSegment(std::integral_constant<int, 4>());
+        else if (n2 <= 256) sortSegment(std::integral_constant<int, 8>());
+        else sortSegment(std::integral_constant<int, 16>());
         __syncwarp();
         const unsigned long long *key = sKeys[w];
         unsigned nEmitted = 0;
