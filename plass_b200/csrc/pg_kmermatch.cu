@@ -1181,15 +1181,25 @@ constexpr int SEG_WARP_MAX = 512;     // pairs one warp sorts in registers (16 p
 constexpr int SEG_BLOCK_MAX = 8192;
 
 __global__ void seg_bounds_kernel(const Rec *__restrict__ in, unsigned long long n, unsigned long long *__restrict__ start,
-                                  unsigned long long *__restrict__ end) {
-    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
-        const unsigned rep = (unsigned) (in[i].w0 >> 32);
-        if (i == 0) start[rep] = 0;
-        else {
-            const unsigned prev = (unsigned) (in[i - 1].w0 >> 32);
-            if (prev != rep) { start[rep] = i; end[prev] = i; }
+                                  unsigned long long *__restrict__ end, unsigned *__restrict__ minTarget /* preset to 0xFFFFFFFF */) {
+    const unsigned long long nRound = (n + 31) & ~31ULL;
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < nRound; i += (unsigned long long) gridDim.x * blockDim.x) {
+        const bool live = i < n;
+        unsigned rep = 0xFFFFFFFFu, target = 0xFFFFFFFFu;
+        if (live) {
+            const unsigned long long w0 = in[i].w0;
+            rep = (unsigned) (w0 >> 32); target = (unsigned) w0;
+            if (i == 0) start[rep] = 0;
+            else {
+                const unsigned prev = (unsigned) (in[i - 1].w0 >> 32);
+                if (prev != rep) { start[rep] = i; end[prev] = i; }
+            }
+            if (i == n - 1) end[rep] = n;
         }
-        if (i == n - 1) end[rep] = n;
+        // smallest target of every representative: the lanes that share a representative combine before the atomic
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, rep);
+        const unsigned mt = __reduce_min_sync(peers, target);
+        if (live && (threadIdx.x & 31) == (unsigned) (__ffs(peers) - 1)) atomicMin(&minTarget[rep], mt);
     }
 }
 
@@ -1232,17 +1242,14 @@ struct ScanState { unsigned prevDiag, diagCnt, revCnt, maxDiag, best, bestRev, t
 // several representatives.  Executed by a whole warp; returns the final state in every lane.  *overflow is raised when
 // the continued run is longer than the staging list.
 __device__ ScanState continue_run_warp(const Rec *__restrict__ in, unsigned long long n, const unsigned long long *__restrict__ end,
+                                       const unsigned *__restrict__ minTarget,
                                        unsigned long long nextPos, unsigned X, ScanState st, unsigned *stage /* >= 256 words */,
                                        unsigned *overflow) {
     const unsigned lane = threadIdx.x & 31;
     while (nextPos < n) {
         const unsigned B = (unsigned) (in[nextPos].w0 >> 32);
+        if (minTarget[B] != X) break;                 // the usual case: one load decides
         const unsigned long long be = end[B];
-        unsigned minT = 0xFFFFFFFFu;
-        for (unsigned long long i = nextPos + lane; i < be; i += 32) minT = min(minT, (unsigned) in[i].w0);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) minT = min(minT, __shfl_xor_sync(0xFFFFFFFFu, minT, o));
-        if (minT != X) break;
         // collect (diagonal, strand) of B's pairs with target X
         unsigned cnt = 0;
         for (unsigned long long i0 = nextPos; i0 < be; i0 += 32) {
@@ -1270,19 +1277,30 @@ __device__ ScanState continue_run_warp(const Rec *__restrict__ in, unsigned long
     return st;
 }
 
+// MODE 0: sweep over all keys, handle representatives with <= 128 pairs (4 registers per lane: high occupancy), queue the
+//         medium ones (<= SEG_WARP_MAX) in midList and the large ones in bigList;   MODE 1: process midList.
+template <int MODE>
 __global__ void __launch_bounds__(256) reduce_rep_warp_kernel(const Rec *__restrict__ in, unsigned long long n,
                                                               const unsigned long long *__restrict__ start, const unsigned long long *__restrict__ end,
+                                                              const unsigned *__restrict__ minTarget,
                                                               unsigned nKeys, pg_hit *__restrict__ tmpHits, unsigned *__restrict__ hitCount,
-                                                              unsigned *__restrict__ bigList, unsigned *__restrict__ bigCount, unsigned *__restrict__ overflow) {
-    __shared__ unsigned long long sKeys[8][SEG_WARP_MAX];
+                                                              unsigned *__restrict__ bigList, unsigned *__restrict__ bigCount,
+                                                              unsigned *__restrict__ midList, unsigned *__restrict__ midCount, unsigned *__restrict__ overflow) {
+    constexpr int KEYS = MODE == 0 ? 128 : SEG_WARP_MAX;
+    __shared__ unsigned long long sKeys[8][KEYS];
     __shared__ unsigned sStage[8][256];
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned warpsTotal = gridDim.x * (blockDim.x >> 5);
-    for (unsigned rep = blockIdx.x * (blockDim.x >> 5) + w; rep < nKeys; rep += warpsTotal) {
+    const unsigned nWork = MODE == 0 ? nKeys : *midCount;
+    for (unsigned wi = blockIdx.x * (blockDim.x >> 5) + w; wi < nWork; wi += warpsTotal) {
+        const unsigned rep = MODE == 0 ? wi : midList[wi];
         const unsigned long long s0 = start[rep], e0 = end[rep];
         if (e0 <= s0) continue;
         const unsigned count = (unsigned) (e0 - s0);
-        if (count > SEG_WARP_MAX) { if (lane == 0) bigList[atomicAdd(bigCount, 1u)] = rep; continue; }
+        if (MODE == 0) {
+            if (count > SEG_WARP_MAX) { if (lane == 0) bigList[atomicAdd(bigCount, 1u)] = rep; continue; }
+            if (count > 128) { if (lane == 0) midList[atomicAdd(midCount, 1u)] = rep; continue; }
+        }
         int n2 = 32;
         while (n2 < (int) count) n2 <<= 1;
         // load + sort + stage in shared memory, with as many registers per lane as this representative needs
@@ -1299,44 +1317,55 @@ __global__ void __launch_bounds__(256) reduce_rep_warp_kernel(const Rec *__restr
 #pragma unroll
             for (int sl = 0; sl < SL; sl++) sKeys[w][sl * 32 + lane] = r[sl];
         };
-        if (n2 <= 32) sortSegment(std::integral_constant<int, 1>());
-        else if (n2 <= 64) sortSegment(std::integral_constant<int, 2>());
-        else if (n2 <= 128) sortSegment(std::integral_constant<int, 4>());
-        else if (n2 <= 256) sortSegment(std::integral_constant<int, 8>());
-        else sortSegment(std::integral_constant<int, 16>());
+        if (MODE == 0) {
+            if (n2 <= 32) sortSegment(std::integral_constant<int, 1>());
+            else if (n2 <= 64) sortSegment(std::integral_constant<int, 2>());
+            else sortSegment(std::integral_constant<int, 4>());
+        } else {
+            if (n2 <= 256) sortSegment(std::integral_constant<int, 8>());
+            else sortSegment(std::integral_constant<int, 16>());
+        }
         __syncwarp();
         const unsigned long long *key = sKeys[w];
-        unsigned nEmitted = 0;
-        // the last run of the block (largest target) is the only one that can reach the block end
-        bool ownsLast = false; ScanState lastSt; lastSt.prevDiag = lastSt.diagCnt = lastSt.revCnt = lastSt.maxDiag = lastSt.best = lastSt.bestRev = lastSt.top = 0;
-        long long lastSlot = -1; unsigned lastTarget = 0;
+        // run starts (first element of every target), compacted in order; then one lane per run
+        unsigned short *runStart = reinterpret_cast<unsigned short *>(sStage[w]);     // up to 512 entries
+        unsigned nRuns = 0;
         for (int sl = 0; sl * 32 < (int) count; sl++) {
             const int i = sl * 32 + (int) lane;
+            const bool isStart = (i < (int) count) && (i == 0 || (key[i - 1] >> 17) != (key[i] >> 17));
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, isStart);
+            if (isStart) runStart[nRuns + __popc(m & ((1u << lane) - 1u))] = (unsigned short) i;
+            nRuns += __popc(m);
+        }
+        __syncwarp();
+        unsigned nEmitted = 0;
+        // the last run of the block (largest target) is the only one that reaches the block end
+        bool ownsLast = false; ScanState lastSt; lastSt.prevDiag = lastSt.diagCnt = lastSt.revCnt = lastSt.maxDiag = lastSt.best = lastSt.bestRev = lastSt.top = 0;
+        long long lastSlot = -1; unsigned lastTarget = 0;
+        for (unsigned r0 = 0; r0 < nRuns; r0 += 32) {
+            const unsigned ri = r0 + lane;
             bool emit = false; pg_hit h; h.rep = rep; h.target = 0; h.score = 0; h.diag = 0;
-            bool reached = false; ScanState st; st.prevDiag = st.diagCnt = st.revCnt = st.maxDiag = st.best = st.bestRev = st.top = 0;
-            if (i < (int) count) {
+            ScanState st; st.prevDiag = st.diagCnt = st.revCnt = st.maxDiag = st.best = st.bestRev = st.top = 0;
+            if (ri < nRuns) {
+                const int i = runStart[ri];
+                const int e = (ri + 1 < nRuns) ? (int) runStart[ri + 1] : (int) count;
                 const unsigned long long k = key[i];
-                if (i == 0 || (key[i - 1] >> 17) != (k >> 17)) {
-                    const unsigned target = (unsigned) (k >> 17);
-                    st.prevDiag = (unsigned) ((k >> 1) & 0xFFFFULL); st.best = st.prevDiag; st.bestRev = (unsigned) (k & 1ULL);
-                    int j = i;
-                    while (j < (int) count && (unsigned) (key[j] >> 17) == target) {
-                        run_step((unsigned) ((key[j] >> 1) & 0xFFFFULL), (unsigned) (key[j] & 1ULL), st.prevDiag, st.diagCnt, st.revCnt, st.maxDiag, st.best, st.bestRev, st.top);
-                        j++;
-                    }
-                    emit = target != rep;
-                    h.target = target;
-                    h.score = st.bestRev ? -(int) st.top : (int) st.top;
-                    h.diag = (int) (short) (unsigned short) (st.best - 32768u);
-                    reached = (j == (int) count);
-                }
+                const unsigned target = (unsigned) (k >> 17);
+                st.prevDiag = (unsigned) ((k >> 1) & 0xFFFFULL); st.best = st.prevDiag; st.bestRev = (unsigned) (k & 1ULL);
+                for (int j = i; j < e; j++)
+                    run_step((unsigned) ((key[j] >> 1) & 0xFFFFULL), (unsigned) (key[j] & 1ULL), st.prevDiag, st.diagCnt, st.revCnt, st.maxDiag, st.best, st.bestRev, st.top);
+                emit = target != rep;
+                h.target = target;
+                h.score = st.bestRev ? -(int) st.top : (int) st.top;
+                h.diag = (int) (short) (unsigned short) (st.best - 32768u);
             }
             const unsigned m = __ballot_sync(0xFFFFFFFFu, emit);
             const long long slot = (long long) (s0 + nEmitted + __popc(m & ((1u << lane) - 1u)));
             if (emit) tmpHits[slot] = h;
-            if (reached) { ownsLast = true; lastSt = st; lastSlot = emit ? slot : -1; lastTarget = h.target; }
+            if (ri + 1 == nRuns) { ownsLast = true; lastSt = st; lastSlot = emit ? slot : -1; lastTarget = h.target; }
             nEmitted += __popc(m);
         }
+        __syncwarp();
         // continuation of the last run into the following representative(s)
         const unsigned ownerMask = __ballot_sync(0xFFFFFFFFu, ownsLast);
         if (ownerMask && e0 < n) {
@@ -1349,7 +1378,7 @@ __global__ void __launch_bounds__(256) reduce_rep_warp_kernel(const Rec *__restr
             const unsigned X = __shfl_sync(0xFFFFFFFFu, lastTarget, owner);
             const long long slot = __shfl_sync(0xFFFFFFFFu, lastSlot, owner);
             const unsigned topBefore = st.top;
-            st = continue_run_warp(in, n, end, e0, X, st, sStage[w], overflow);
+            st = continue_run_warp(in, n, end, minTarget, e0, X, st, sStage[w], overflow);
             if (st.top != topBefore && slot >= 0 && lane == 0) {
                 pg_hit h; h.rep = rep; h.target = X;
                 h.score = st.bestRev ? -(int) st.top : (int) st.top;
@@ -1365,6 +1394,7 @@ __global__ void __launch_bounds__(256) reduce_rep_warp_kernel(const Rec *__restr
 // representatives with more than SEG_WARP_MAX pairs: one CTA each, bitonic sort in shared memory
 __global__ void __launch_bounds__(256) reduce_rep_block_kernel(const Rec *__restrict__ in, unsigned long long n,
                                                                const unsigned long long *__restrict__ start, const unsigned long long *__restrict__ end,
+                                                               const unsigned *__restrict__ minTarget,
                                                                const unsigned *__restrict__ bigList, const unsigned *__restrict__ bigCount,
                                                                pg_hit *__restrict__ tmpHits, unsigned *__restrict__ hitCount, unsigned *__restrict__ overflow) {
     extern __shared__ __align__(16) unsigned char rb_smem[];
@@ -1438,7 +1468,7 @@ __global__ void __launch_bounds__(256) reduce_rep_block_kernel(const Rec *__rest
         if (w == 0 && sHasLast && e0 < n) {
             ScanState st = sLast;
             const unsigned topBefore = st.top;
-            st = continue_run_warp(in, n, end, e0, sLastTarget, st, sStage, overflow);
+            st = continue_run_warp(in, n, end, minTarget, e0, sLastTarget, st, sStage, overflow);
             if (st.top != topBefore && sLastSlot >= 0 && lane == 0) {
                 pg_hit h; h.rep = rep; h.target = sLastTarget;
                 h.score = st.bestRev ? -(int) st.top : (int) st.top;
@@ -1776,22 +1806,27 @@ static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, 
     const size_t oStart = take(sizeof(unsigned long long) * nKeys), oEnd = take(sizeof(unsigned long long) * nKeys);
     const size_t oCnt = take(sizeof(unsigned) * ((size_t) nKeys + 1));
     const size_t oOff = take(sizeof(unsigned long long) * ((size_t) nKeys + 2)), oBig = take(sizeof(unsigned) * ((size_t) nKeys + 1));
+    const size_t oMid = take(sizeof(unsigned) * ((size_t) nKeys + 1));
     const size_t oScan = take(scan_workspace_bytes(nKeys));
+    const size_t oMinT = take(sizeof(unsigned) * ((size_t) nKeys + 1));
     PG_TRY(ctx->buckets2.reserve(o));
     unsigned char *bb = ctx->buckets2.as<unsigned char>();
     unsigned long long *d_start = (unsigned long long *) (bb + oStart), *d_end = (unsigned long long *) (bb + oEnd);
-    unsigned *d_hcnt = (unsigned *) (bb + oCnt), *d_big = (unsigned *) (bb + oBig);
+    unsigned *d_hcnt = (unsigned *) (bb + oCnt), *d_big = (unsigned *) (bb + oBig), *d_minT = (unsigned *) (bb + oMinT), *d_mid = (unsigned *) (bb + oMid);
     unsigned long long *d_hoff = (unsigned long long *) (bb + oOff);
-    unsigned *d_over = (unsigned *) (ctx->small.as<unsigned long long>() + 30);     // [30] overflow flag + big count, [31] total hits
-    unsigned *d_bigCnt = d_over + 1;
-    unsigned long long *d_total = ctx->small.as<unsigned long long>() + 31;
+    unsigned *d_over = (unsigned *) (ctx->small.as<unsigned long long>() + 32);     // [32] overflow flag, big count, mid count; [34] total hits
+    unsigned *d_bigCnt = d_over + 1, *d_midCnt = d_over + 2;
+    unsigned long long *d_total = ctx->small.as<unsigned long long>() + 34;
     PG_CUDA(cudaMemsetAsync(d_start, 0, oOff, s));   // start, end, hit counts
-    PG_CUDA(cudaMemsetAsync(d_over, 0, 2 * sizeof(unsigned), s));
-    seg_bounds_kernel<<<NUM_SMS * 16, 256, 0, s>>>(sorted, nPairs, d_start, d_end);
+    PG_CUDA(cudaMemsetAsync(d_over, 0, 4 * sizeof(unsigned), s));
+    PG_CUDA(cudaMemsetAsync(d_minT, 0xFF, sizeof(unsigned) * ((size_t) nKeys + 1), s));
+    seg_bounds_kernel<<<NUM_SMS * 16, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT);
     pg_hit *tmpHits = reinterpret_cast<pg_hit *>(other);   // a hit is 16 bytes like a record, at most one per pair
-    reduce_rep_warp_kernel<<<NUM_SMS * 16, 256, 0, s>>>(sorted, nPairs, d_start, d_end, nKeys, tmpHits, d_hcnt, d_big, d_bigCnt, d_over);
+    reduce_rep_warp_kernel<0><<<NUM_SMS * 32, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT, nKeys, tmpHits, d_hcnt, d_big, d_bigCnt, d_mid, d_midCnt, d_over);
+    reduce_rep_warp_kernel<1><<<NUM_SMS * 8, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT, nKeys, tmpHits, d_hcnt, d_big, d_bigCnt, d_mid, d_midCnt, d_over);
+    ctx->launches++;
     PG_CUDA(cudaFuncSetAttribute(reduce_rep_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_BLOCK_MAX * (int) sizeof(unsigned long long)));
-    reduce_rep_block_kernel<<<NUM_SMS * 3, 256, SEG_BLOCK_MAX * sizeof(unsigned long long), s>>>(sorted, nPairs, d_start, d_end, d_big, d_bigCnt, tmpHits, d_hcnt, d_over);
+    reduce_rep_block_kernel<<<NUM_SMS * 3, 256, SEG_BLOCK_MAX * sizeof(unsigned long long), s>>>(sorted, nPairs, d_start, d_end, d_minT, d_big, d_bigCnt, tmpHits, d_hcnt, d_over);
     ctx->launches += 3;
     PG_TRY(exclusive_scan_u32(d_hcnt, d_hoff, nKeys, d_total, bb + oScan, scan_workspace_bytes(nKeys), s, &ctx->launches));
     unsigned long long h = 0; unsigned over = 0;
