@@ -224,7 +224,14 @@ def main():
 
     # weak scaling: every rank contributes `reads` reads; the job's DB is the union (replicated in each HBM)
     n_reads_total = args.reads * world
-    db = make_fragments(n_reads_total, args.seed)
+    if world > 1:
+        # rank 0 generates (and caches) the job's input, the other ranks load the cached copy
+        db = make_fragments(n_reads_total, args.seed) if rank == 0 else None
+        dist.barrier()
+        if db is None:
+            db = make_fragments(n_reads_total, args.seed)
+    else:
+        db = make_fragments(n_reads_total, args.seed)
     ctx = api.Context(local_rank)
     kp, rp, ep = api.default_km_params(False), api.default_rs_params(False), api.default_ex_params(False)
 

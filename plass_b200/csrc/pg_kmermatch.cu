@@ -983,36 +983,6 @@ __global__ void __launch_bounds__(256) reduce_emit_kernel(const Rec *__restrict_
     if (emit) hits[blockOffsets[blockIdx.x] + off + __popc(m & ((1u << lane) - 1u))] = h;
 }
 
-// ------------------------------------------------------------------------------------------------
-// reduce, fast path: partition the pairs by the high bits of the representative (ceil(bits/8) radix passes instead of
-// the 8 of the full (rep, target, diagonal) sort); a bucket = a contiguous range of representatives holding ~500
-// pairs.  One CTA sorts its bucket in shared memory by the packed key (rep-in-bucket, target, diagonal, strand) and
-// runs the writeKmerMatcherResult scan on it.  Buckets are in representative order, so the hits of consecutive
-// buckets concatenate into the final (rep, target) order.
-// ------------------------------------------------------------------------------------------------
-constexpr int RB_SMALL = 2048;        // buckets up to this many pairs: 128-thread CTAs with 16 KiB of keys (many CTAs per SM)
-constexpr int RB_MAX = 8192;          // larger buckets: 256-thread CTAs with 64 KiB of keys; beyond that the full sort is used
-
-struct RunState {                     // the scan state at the end of a bucket whose last run may continue in the next bucket
-    unsigned valid;                   // 1: the last (rep, target) run of the bucket touches the bucket end
-    unsigned rep, target;
-    long long hitSlot;                // index of its hit in the temporary hit array, -1 if not emitted (target == rep)
-    unsigned prevDiag, diagCnt, revCnt, maxDiag, best, bestRev, top;
-};
-
-__global__ void pair_bounds_kernel(const Rec *__restrict__ in, unsigned long long n, int shift,
-                                   unsigned long long *__restrict__ start, unsigned long long *__restrict__ end) {
-    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
-        const unsigned b = (unsigned) (in[i].w0 >> 32) >> shift;
-        if (i == 0) start[b] = 0;
-        else {
-            const unsigned pb = (unsigned) (in[i - 1].w0 >> 32) >> shift;
-            if (pb != b) { start[b] = i; end[pb] = i; }
-        }
-        if (i == n - 1) end[b] = n;
-    }
-}
-
 // one step of the reference's run scan (kmermatcher.cpp:880-893) with the majority strand rule of reduce_one
 __device__ __forceinline__ void run_step(unsigned d, unsigned rv, unsigned &prevDiag, unsigned &diagCnt, unsigned &revCnt,
                                          unsigned &maxDiag, unsigned &best, unsigned &bestRev, unsigned &top) {
@@ -1022,156 +992,8 @@ __device__ __forceinline__ void run_step(unsigned d, unsigned rv, unsigned &prev
     top++;
 }
 
-template <int RB_THREADS, int CAP_LO, int CAP_HI>      // handles the buckets with CAP_LO < count <= CAP_HI
-__global__ void __launch_bounds__(RB_THREADS) reduce_bucket_kernel(const Rec *__restrict__ in, const unsigned long long *__restrict__ start,
-                                                                   const unsigned long long *__restrict__ end, unsigned nBuckets, int shift, int keyBits,
-                                                                   pg_hit *__restrict__ tmpHits, unsigned *__restrict__ hitCount,
-                                                                   RunState *__restrict__ states, unsigned long long *__restrict__ firstKey,
-                                                                   unsigned *__restrict__ overflow) {
-    extern __shared__ __align__(16) unsigned char rb_smem[];
-    unsigned long long *key = reinterpret_cast<unsigned long long *>(rb_smem);
-    __shared__ unsigned sWarp[RB_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const unsigned long long tMask = (keyBits >= 32) ? 0xFFFFFFFFULL : ((1ULL << keyBits) - 1ULL);
-    for (unsigned b = blockIdx.x; b < nBuckets; b += gridDim.x) {
-        const unsigned long long s0 = start[b], e0 = end[b];
-        const unsigned count = (e0 > s0) ? (unsigned) (e0 - s0) : 0u;
-        if (CAP_LO == 0 && count == 0) { if (tid == 0) { hitCount[b] = 0; states[b].valid = 0; firstKey[b] = ~0ULL; } continue; }
-        if (count > RB_MAX) { if (CAP_LO == 0 && tid == 0) { hitCount[b] = 0; states[b].valid = 0; atomicExch(overflow, 1u); } continue; }
-        if (count <= (unsigned) CAP_LO || count > (unsigned) CAP_HI) continue;       // the other instance's bucket
-        if (tid == 0) { hitCount[b] = 0; states[b].valid = 0; firstKey[b] = ~0ULL; }
-        __syncthreads();
-        int n2 = 1;
-        while (n2 < (int) count) n2 <<= 1;
-        // packed key: rep-in-bucket | target | biased diagonal | strand
-        for (int i = tid; i < n2; i += RB_THREADS) {
-            unsigned long long k = ~0ULL;
-            if (i < (int) count) {
-                const Rec r = in[s0 + i];
-                const unsigned rep = (unsigned) (r.w0 >> 32), target = (unsigned) r.w0;
-                const unsigned repLow = rep & ((1u << shift) - 1u);
-                k = ((unsigned long long) repLow << (keyBits + 17)) | ((unsigned long long) target << 17) | ((r.w1 & 0xFFFFULL) << 1) | ((r.w1 >> 16) & 1ULL);
-            }
-            key[i] = k;
-        }
-        __syncthreads();
-        for (int kk = 2; kk <= n2; kk <<= 1) {
-            for (int j = kk >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < (n2 >> 1); t += RB_THREADS) {
-                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                    const int ix = i | j;
-                    const bool up = ((i & kk) == 0);
-                    const unsigned long long a = key[i], c2 = key[ix];
-                    if ((c2 < a) == up) { key[i] = c2; key[ix] = a; }
-                }
-                __syncthreads();
-            }
-        }
-        const unsigned repBase = b << shift;
-        // run scan: thread i owns element i; run starts emit
-        unsigned long long base = 0;   // hits emitted so far in this bucket (ordered)
-        for (int i0 = 0; i0 < (int) count; i0 += RB_THREADS) {
-            const int i = i0 + tid;
-            bool emit = false; pg_hit h; h.rep = h.target = 0; h.score = h.diag = 0;
-            if (i < (int) count) {
-                const unsigned long long k = key[i];
-                const bool runStart = (i == 0) || ((key[i - 1] >> 17) != (k >> 17));
-                if (runStart) {
-                    const unsigned target = (unsigned) ((k >> 17) & tMask);
-                    const unsigned rep = repBase | (unsigned) (k >> (keyBits + 17));
-                    unsigned prevDiag = (unsigned) ((k >> 1) & 0xFFFFULL), diagCnt = 0, revCnt = 0, maxDiag = 0;
-                    unsigned best = prevDiag, bestRev = (unsigned) (k & 1ULL), top = 0;
-                    int j = i;
-                    while (j < (int) count && (unsigned) ((key[j] >> 17) & tMask) == target) {
-                        run_step((unsigned) ((key[j] >> 1) & 0xFFFFULL), (unsigned) (key[j] & 1ULL), prevDiag, diagCnt, revCnt, maxDiag, best, bestRev, top);
-                        j++;
-                    }
-                    emit = target != rep;
-                    h.rep = rep; h.target = target;
-                    h.score = bestRev ? -(int) top : (int) top;
-                    h.diag = (int) (short) (unsigned short) (best - 32768u);
-                    if (j == (int) count) {
-                        // the scan reached the end of the bucket: it may have to continue in the next bucket
-                        // (the reference's loop does not stop at a change of representative); fixed up later.  Only the
-                        // bucket's last run can be carried; an earlier run that also reaches the end (several
-                        // representatives ending on the same target) sends the whole call to the full sort.
-                        const unsigned long long kl = key[count - 1];
-                        if ((kl >> 17) != (k >> 17)) atomicExch(overflow, 1u);
-                        RunState st; st.valid = 1; st.rep = rep; st.target = target; st.hitSlot = emit ? 0 : -1;
-                        st.prevDiag = prevDiag; st.diagCnt = diagCnt; st.revCnt = revCnt; st.maxDiag = maxDiag; st.best = best; st.bestRev = bestRev; st.top = top;
-                        states[b] = st;   // hitSlot completed below for the emitting case
-                    }
-                }
-                if (i == 0) firstKey[b] = ((unsigned long long) (repBase | (unsigned) (k >> (keyBits + 17))) << 32) | ((k >> 17) & tMask);
-            }
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, emit);
-            if (lane == 0) sWarp[w] = __popc(m);
-            __syncthreads();
-            unsigned off = 0, total = 0;
-            for (int ww = 0; ww < RB_THREADS / 32; ww++) { if (ww < w) off += sWarp[ww]; total += sWarp[ww]; }
-            if (emit) {
-                const unsigned long long slot = s0 + base + off + __popc(m & ((1u << lane) - 1u));
-                tmpHits[slot] = h;
-                // a run that touches the bucket end is by construction the last emitted hit of the bucket
-                if (states[b].valid && states[b].rep == h.rep && states[b].target == h.target) states[b].hitSlot = (long long) slot;
-            }
-            base += total;
-            __syncthreads();
-        }
-        if (tid == 0) hitCount[b] = (unsigned) base;
-        __syncthreads();
-    }
-}
-
-// continuation of a run across a bucket border (rare): the next non-empty bucket's first (rep, target) run has the
-// same target id => the reference's scan would have kept counting through it.
-__global__ void reduce_fixup_kernel(const Rec *__restrict__ in, const unsigned long long *__restrict__ start, const unsigned long long *__restrict__ end,
-                                    unsigned nBuckets, const RunState *__restrict__ states, const unsigned long long *__restrict__ firstKey,
-                                    pg_hit *__restrict__ tmpHits, unsigned *__restrict__ overflow) {
-    const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nBuckets) return;
-    const RunState st = states[b];
-    if (!st.valid) return;
-    unsigned nb = b + 1;
-    while (nb < nBuckets && end[nb] <= start[nb]) nb++;
-    if (nb >= nBuckets) return;
-    const unsigned long long fk = firstKey[nb];
-    if ((unsigned) fk != st.target) return;
-    // collect the diagonals of the next bucket's first run (unsorted in global memory), sort, continue the scan
-    const unsigned CAP = 256;
-    unsigned dv[CAP];
-    unsigned cnt = 0;
-    const unsigned long long s0 = start[nb], e0 = end[nb];
-    for (unsigned long long i = s0; i < e0; i++) {
-        const Rec r = in[i];
-        if (r.w0 == fk) {
-            if (cnt >= CAP) { atomicExch(overflow, 1u); return; }
-            dv[cnt++] = (unsigned) ((r.w1 & 0xFFFFULL) << 1) | (unsigned) ((r.w1 >> 16) & 1ULL);
-        }
-    }
-    if (cnt == (unsigned) (e0 - s0)) { atomicExch(overflow, 1u); return; }   // the run could continue even further: use the full sort
-    for (unsigned i = 1; i < cnt; i++) { const unsigned v = dv[i]; int j = (int) i - 1; while (j >= 0 && dv[j] > v) { dv[j + 1] = dv[j]; j--; } dv[j + 1] = v; }
-    unsigned prevDiag = st.prevDiag, diagCnt = st.diagCnt, revCnt = st.revCnt, maxDiag = st.maxDiag, best = st.best, bestRev = st.bestRev, top = st.top;
-    for (unsigned i = 0; i < cnt; i++) run_step(dv[i] >> 1, dv[i] & 1u, prevDiag, diagCnt, revCnt, maxDiag, best, bestRev, top);
-    if (st.hitSlot >= 0) {
-        pg_hit h; h.rep = st.rep; h.target = st.target;
-        h.score = bestRev ? -(int) top : (int) top;
-        h.diag = (int) (short) (unsigned short) (best - 32768u);
-        tmpHits[st.hitSlot] = h;
-    }
-}
-
-__global__ void compact_hits_kernel(const pg_hit *__restrict__ tmpHits, const unsigned long long *__restrict__ start, const unsigned *__restrict__ hitCount,
-                                    const unsigned long long *__restrict__ hitOffset, unsigned nBuckets, pg_hit *__restrict__ hits) {
-    for (unsigned b = blockIdx.x; b < nBuckets; b += gridDim.x) {
-        const unsigned c = hitCount[b];
-        const unsigned long long s0 = start[b], o = hitOffset[b];
-        for (unsigned i = threadIdx.x; i < c; i += blockDim.x) hits[o + i] = tmpHits[s0 + i];
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
-// reduce, fast path v2: sort the pairs by the representative only (ceil(keyBits/8) radix passes), then one WARP per
+// reduce, fast path: sort the pairs by the representative only (ceil(keyBits/8) radix passes), then one WARP per
 // representative sorts that representative's pairs by (target, diagonal, strand) in registers (bitonic network over
 // warp shuffles, up to 128 pairs) and runs the writeKmerMatcherResult scan on them.  Representatives with more pairs go
 // to a CTA-wide shared-memory sort.  The reference's scan does not stop at a change of representative when the next
@@ -1721,73 +1543,7 @@ int km_group(Context *ctx, const pg_seqdb *db, const KmConst &c, uint64_t nRecor
     return 0;
 }
 
-// fast path of stage 3 (see reduce_bucket_kernel); *ok = false if a bucket overflowed (the pairs are then handed back
-// unchanged up to a permutation for the full sort)
-static int km_reduce_bucketed(Context *ctx, const pg_seqdb *db, Rec **pairsIO, Rec **tmpIO, uint64_t nPairs, pg_hit **d_hits, uint64_t *nHits, bool *ok) {
-    cudaStream_t s = ctx->stream;
-    *ok = false;
-    Rec *pairs = *pairsIO, *tmp = *tmpIO;
-    const int keyBits = bits_for(db->max_key);
-    const double perRep = (double) nPairs / ((double) db->max_key + 1.0);
-    int shift = 0;
-    while (shift < 15 && shift < keyBits && perRep * (double) (2u << shift) <= 768.0) shift++;   // 400-768 pairs per bucket on average
-    if (keyBits + 17 + shift > 64) return 0;
-    const unsigned nBuckets = (db->max_key >> shift) + 1;
-    if ((double) nPairs / nBuckets > 2000.0) return 0;     // representatives too heavy for the shared-memory sort
-    RadixPlan plan; plan.npasses = 0;
-    plan_add_bits(plan, 0, 32 + shift, 32 + keyBits);
-    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nPairs)));
-    Rec *sorted = pairs;
-    if (plan.npasses > 0) PG_TRY(radix_sort(pairs, tmp, nPairs, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches));
-    cudaEventRecord(ctx->ev[EV_SORT2_END], s);
-    Rec *other = (sorted == pairs) ? tmp : pairs;
-    // per-bucket arrays
-    size_t o = 0;
-    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t) 15; return r; };
-    const size_t oStart = take(sizeof(unsigned long long) * nBuckets), oEnd = take(sizeof(unsigned long long) * nBuckets);
-    const size_t oCnt = take(sizeof(unsigned) * (nBuckets + 1)), oOff = take(sizeof(unsigned long long) * (nBuckets + 2));
-    const size_t oFirst = take(sizeof(unsigned long long) * nBuckets), oState = take(sizeof(RunState) * nBuckets);
-    const size_t oScan = take(scan_workspace_bytes(nBuckets));
-    PG_TRY(ctx->buckets2.reserve(o));
-    unsigned char *bb = ctx->buckets2.as<unsigned char>();
-    unsigned long long *d_start = (unsigned long long *) (bb + oStart), *d_end = (unsigned long long *) (bb + oEnd);
-    unsigned *d_hcnt = (unsigned *) (bb + oCnt);
-    unsigned long long *d_hoff = (unsigned long long *) (bb + oOff), *d_first = (unsigned long long *) (bb + oFirst);
-    RunState *d_states = (RunState *) (bb + oState);
-    unsigned *d_over = (unsigned *) (ctx->small.as<unsigned long long>() + 30);     // [30] overflow flag, [31] total hits
-    unsigned long long *d_total = ctx->small.as<unsigned long long>() + 31;
-    PG_CUDA(cudaMemsetAsync(d_start, 0, oCnt, s));   // start + end
-    PG_CUDA(cudaMemsetAsync(d_over, 0, sizeof(unsigned), s));
-    pair_bounds_kernel<<<NUM_SMS * 16, 256, 0, s>>>(sorted, nPairs, shift, d_start, d_end);
-    // the temporary hits reuse the other record buffer (a hit is 16 bytes like a record, at most one per pair)
-    pg_hit *tmpHits = reinterpret_cast<pg_hit *>(other);
-    PG_CUDA(cudaFuncSetAttribute(reduce_bucket_kernel<256, RB_SMALL, RB_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_MAX * (int) sizeof(unsigned long long)));
-    reduce_bucket_kernel<128, 0, RB_SMALL><<<std::min<unsigned>(nBuckets, NUM_SMS * 64), 128, RB_SMALL * sizeof(unsigned long long), s>>>(
-        sorted, d_start, d_end, nBuckets, shift, keyBits, tmpHits, d_hcnt, d_states, d_first, d_over);
-    reduce_bucket_kernel<256, RB_SMALL, RB_MAX><<<std::min<unsigned>(nBuckets, NUM_SMS * 16), 256, RB_MAX * sizeof(unsigned long long), s>>>(
-        sorted, d_start, d_end, nBuckets, shift, keyBits, tmpHits, d_hcnt, d_states, d_first, d_over);
-    ctx->launches++;
-    reduce_fixup_kernel<<<(nBuckets + 255) / 256, 256, 0, s>>>(sorted, d_start, d_end, nBuckets, d_states, d_first, tmpHits, d_over);
-    ctx->launches += 3;
-    PG_TRY(exclusive_scan_u32(d_hcnt, d_hoff, nBuckets, d_total, bb + oScan, scan_workspace_bytes(nBuckets), s, &ctx->launches));
-    unsigned long long h = 0; unsigned over = 0;
-    PG_CUDA(cudaMemcpyAsync(&h, d_total, sizeof(h), cudaMemcpyDeviceToHost, s));
-    PG_CUDA(cudaMemcpyAsync(&over, d_over, sizeof(over), cudaMemcpyDeviceToHost, s));
-    PG_CUDA(cudaStreamSynchronize(s));
-    PG_CUDA(cudaGetLastError());
-    if (over) { *pairsIO = sorted; *tmpIO = other; return 0; }
-    PG_TRY(ctx->hits.reserve(sizeof(pg_hit) * (h + 1)));
-    compact_hits_kernel<<<std::min<unsigned>(nBuckets, NUM_SMS * 32), 128, 0, s>>>(tmpHits, d_start, d_hcnt, d_hoff, nBuckets, ctx->hits.as<pg_hit>());
-    ctx->launches++;
-    cudaEventRecord(ctx->ev[EV_REDUCE_END], s);
-    PG_CUDA(cudaGetLastError());
-    *d_hits = ctx->hits.as<pg_hit>();
-    *nHits = h;
-    *ok = true;
-    return 0;
-}
-
-// fast path v2 of stage 3 (see reduce_rep_warp_kernel); *ok = false if a representative exceeded the CTA capacity
+// fast path of stage 3 (see reduce_rep_warp_kernel); *ok = false if a representative exceeded the CTA capacity
 static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, Rec **tmpIO, uint64_t nPairs, pg_hit **d_hits, uint64_t *nHits, bool *ok) {
     cudaStream_t s = ctx->stream;
     *ok = false;
