@@ -190,7 +190,24 @@ def reference_arm(args, db_full, n_reads_total):
     }
 
 
+_REAL_STDOUT = None
+
+
+def emit_json(line):
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner) also write to fd 1, so
+    fd 1 is pointed at stderr for the whole run and the line goes to the saved descriptor."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -210,7 +227,7 @@ def main():
         if rank != 0:
             return 0
         db = make_fragments(args.reads, args.seed)
-        print(json.dumps(reference_arm(args, db, args.reads)), flush=True)
+        emit_json(reference_arm(args, db, args.reads))
         return 0
 
     import torch
@@ -345,7 +362,7 @@ def main():
             "gpu_launches": int(sum(t["kernel_launches"] for t in tim)),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "stage_ms": stage_ms,
         }
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     ddb.free()
     ctx.close()
     if world > 1:
