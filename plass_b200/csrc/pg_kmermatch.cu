@@ -1105,7 +1105,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) reduce_rep_warp_kernel(const Rec *__restrict__ in, unsigned long long n,
                                                               const unsigned long long *__restrict__ start, const unsigned long long *__restrict__ end,
                                                               const unsigned *__restrict__ minTarget,
-                                                              unsigned nKeys, pg_hit *__restrict__ tmpHits, unsigned *__restrict__ hitCount,
+                                                              unsigned keyLo, unsigned keyHi, pg_hit *__restrict__ tmpHits, unsigned *__restrict__ hitCount,
                                                               unsigned *__restrict__ bigList, unsigned *__restrict__ bigCount,
                                                               unsigned *__restrict__ midList, unsigned *__restrict__ midCount, unsigned *__restrict__ overflow) {
     constexpr int KEYS = MODE == 0 ? 128 : SEG_WARP_MAX;
@@ -1113,9 +1113,10 @@ __global__ void __launch_bounds__(256) reduce_rep_warp_kernel(const Rec *__restr
     __shared__ unsigned sStage[8][256];
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned warpsTotal = gridDim.x * (blockDim.x >> 5);
-    const unsigned nWork = MODE == 0 ? nKeys : *midCount;
+    // MODE 0 sweeps the representatives this rank owns ([keyLo, keyHi); everything on a single GPU)
+    const unsigned nWork = MODE == 0 ? (keyHi - keyLo) : *midCount;
     for (unsigned wi = blockIdx.x * (blockDim.x >> 5) + w; wi < nWork; wi += warpsTotal) {
-        const unsigned rep = MODE == 0 ? wi : midList[wi];
+        const unsigned rep = MODE == 0 ? keyLo + wi : midList[wi];
         const unsigned long long s0 = start[rep], e0 = end[rep];
         if (e0 <= s0) continue;
         const unsigned count = (unsigned) (e0 - s0);
@@ -1304,11 +1305,11 @@ __global__ void __launch_bounds__(256) reduce_rep_block_kernel(const Rec *__rest
 }
 
 __global__ void compact_rep_hits_kernel(const pg_hit *__restrict__ tmpHits, const unsigned long long *__restrict__ start,
-                                        const unsigned *__restrict__ hitCount, const unsigned long long *__restrict__ hitOffset, unsigned nKeys,
-                                        pg_hit *__restrict__ hits) {
+                                        const unsigned *__restrict__ hitCount, const unsigned long long *__restrict__ hitOffset,
+                                        unsigned keyLo, unsigned keyHi, pg_hit *__restrict__ hits) {
     const unsigned lane = threadIdx.x & 31;
     const unsigned warpsTotal = gridDim.x * (blockDim.x >> 5);
-    for (unsigned rep = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rep < nKeys; rep += warpsTotal) {
+    for (unsigned rep = keyLo + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rep < keyHi; rep += warpsTotal) {
         const unsigned c = hitCount[rep];
         if (c == 0) continue;
         const unsigned long long s0 = start[rep], o = hitOffset[rep];
@@ -1550,6 +1551,7 @@ static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, 
     Rec *pairs = *pairsIO, *tmp = *tmpIO;
     const int keyBits = bits_for(db->max_key);
     const unsigned nKeys = db->max_key + 1;
+    const unsigned keyLo = std::min(ctx->ownLo, nKeys), keyHi = std::min(ctx->ownHi, nKeys);   // representatives of this rank
     RadixPlan plan; plan.npasses = 0;
     plan_add_bits(plan, 0, 32, 32 + keyBits);
     PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nPairs)));
@@ -1578,8 +1580,8 @@ static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, 
     PG_CUDA(cudaMemsetAsync(d_minT, 0xFF, sizeof(unsigned) * ((size_t) nKeys + 1), s));
     seg_bounds_kernel<<<NUM_SMS * 16, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT);
     pg_hit *tmpHits = reinterpret_cast<pg_hit *>(other);   // a hit is 16 bytes like a record, at most one per pair
-    reduce_rep_warp_kernel<0><<<NUM_SMS * 32, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT, nKeys, tmpHits, d_hcnt, d_big, d_bigCnt, d_mid, d_midCnt, d_over);
-    reduce_rep_warp_kernel<1><<<NUM_SMS * 8, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT, nKeys, tmpHits, d_hcnt, d_big, d_bigCnt, d_mid, d_midCnt, d_over);
+    reduce_rep_warp_kernel<0><<<NUM_SMS * 32, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT, keyLo, keyHi, tmpHits, d_hcnt, d_big, d_bigCnt, d_mid, d_midCnt, d_over);
+    reduce_rep_warp_kernel<1><<<NUM_SMS * 8, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT, keyLo, keyHi, tmpHits, d_hcnt, d_big, d_bigCnt, d_mid, d_midCnt, d_over);
     ctx->launches++;
     PG_CUDA(cudaFuncSetAttribute(reduce_rep_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_BLOCK_MAX * (int) sizeof(unsigned long long)));
     reduce_rep_block_kernel<<<NUM_SMS * 3, 256, SEG_BLOCK_MAX * sizeof(unsigned long long), s>>>(sorted, nPairs, d_start, d_end, d_minT, d_big, d_bigCnt, tmpHits, d_hcnt, d_over);
@@ -1592,7 +1594,7 @@ static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, 
     PG_CUDA(cudaGetLastError());
     if (over) { *pairsIO = sorted; *tmpIO = other; return 0; }
     PG_TRY(ctx->hits.reserve(sizeof(pg_hit) * (h + 1)));
-    compact_rep_hits_kernel<<<NUM_SMS * 16, 256, 0, s>>>(tmpHits, d_start, d_hcnt, d_hoff, nKeys, ctx->hits.as<pg_hit>());
+    compact_rep_hits_kernel<<<NUM_SMS * 16, 256, 0, s>>>(tmpHits, d_start, d_hcnt, d_hoff, keyLo, keyHi, ctx->hits.as<pg_hit>());
     ctx->launches++;
     cudaEventRecord(ctx->ev[EV_REDUCE_END], s);
     PG_CUDA(cudaGetLastError());

@@ -24,7 +24,8 @@ struct RsConst {
     int alnLenThr;
     int seqIdMode;
     double dbRes;             // getAminoAcidDBSize of the target DB
-    unsigned ownLo, ownHi;    // multi-GPU: self lines only for the queries this rank owns
+    unsigned ownLo, ownHi;    // multi-GPU: self lines only for the queries this rank owns (key range)
+    unsigned selfLo, nSelf;   // ... = the index range [selfLo, selfLo + nSelf) of the key-sorted DB
     // ALP (Gumbel + finite size correction) parameters
     double lambda, K, a_I, b_I, a_J, b_J, alpha_I, beta_I, alpha_J, beta_J, sigma, tau, vi_thr, vj_thr, c_thr, logK;
 };
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const pg_seqdb db, const p
     for (int i = threadIdx.x; i < 21 * 21; i += blockDim.x) sMat[i] = c_rs_mat[i];
     __syncthreads();
     const unsigned lane = threadIdx.x & 31;
-    const unsigned long long nItems = nHits + db.n;
+    const unsigned long long nItems = nHits + c.nSelf;
     const unsigned long long nBatches = (nItems + 31) / 32;
     const unsigned long long warpsTotal = (unsigned long long) gridDim.x * (blockDim.x >> 5);
     for (unsigned long long batch = (unsigned long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); batch < nBatches; batch += warpsTotal) {
@@ -156,9 +157,8 @@ __global__ void __launch_bounds__(256) rescore_kernel(const pg_seqdb db, const p
                 qi = find_id(db.keys, (unsigned) db.n, qKey);
                 ti = find_id(db.keys, (unsigned) db.n, tKey);
             } else {
-                qi = ti = (unsigned) (item - nHits);
+                qi = ti = c.selfLo + (unsigned) (item - nHits);
                 qKey = tKey = db.keys[qi];
-                if (qKey < c.ownLo || qKey >= c.ownHi) { acc[item] = 0; live = false; }
             }
         }
         const char *qPtr = nullptr, *tPtr = nullptr; int qLen = 0, dbLen = 0;
@@ -259,10 +259,20 @@ __global__ void fill_owned_kernel(const unsigned *__restrict__ keys, unsigned *p
     }
 }
 
+// first index with key >= lo / key >= hi in the ascending key array
+__global__ void key_lower_bound_kernel(const unsigned *__restrict__ keys, unsigned n, unsigned lo, unsigned hi, unsigned *__restrict__ out) {
+    if (threadIdx.x < 2) {
+        const unsigned want = threadIdx.x == 0 ? lo : hi;
+        unsigned a = 0, b = n;
+        while (a < b) { const unsigned m = (a + b) >> 1; if (keys[m] < want) a = m + 1; else b = m; }
+        out[threadIdx.x] = a;
+    }
+}
+
 __global__ void gather_self_kernel(const pg_aln *__restrict__ res, unsigned long long nHits, unsigned long long n,
-                                   const unsigned long long *__restrict__ off, const unsigned char *__restrict__ acc, pg_aln *__restrict__ out) {
-    const unsigned long long qi = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi < n && acc[nHits + qi]) out[off[qi]] = res[nHits + qi];
+                                   const unsigned long long *__restrict__ off, const unsigned char *__restrict__ acc, unsigned selfLo, pg_aln *__restrict__ out) {
+    const unsigned long long k = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;     // k-th owned query
+    if (k < n && acc[nHits + k]) out[off[selfLo + k]] = res[nHits + k];
 }
 
 __global__ void gather_hits_kernel(const pg_seqdb db, const pg_hit *__restrict__ hits, unsigned long long nHits,
@@ -303,8 +313,19 @@ int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHit
     PG_CUDA(cudaMemcpyToSymbolAsync(c_rs_mat, mat, sizeof(mat), 0, cudaMemcpyHostToDevice, s));
     PG_CUDA(cudaStreamSynchronize(s));   // host staging arrays above are stack memory
 
+    // index range of the owned keys (keys are ascending): everything on one GPU
+    unsigned selfLo = 0, selfHi = (unsigned) db->n;
+    if (ctx->ownLo != 0 || ctx->ownHi != 0xFFFFFFFFu) {
+        unsigned *d_lb = (unsigned *) (ctx->small.as<unsigned long long>() + 36);
+        key_lower_bound_kernel<<<1, 32, 0, s>>>(db->keys, (unsigned) db->n, ctx->ownLo, ctx->ownHi, d_lb);
+        unsigned h_lb[2] = {0, 0};
+        PG_CUDA(cudaMemcpyAsync(h_lb, d_lb, sizeof(h_lb), cudaMemcpyDeviceToHost, s));
+        PG_CUDA(cudaStreamSynchronize(s));
+        selfLo = h_lb[0]; selfHi = h_lb[1];
+    }
+    c.selfLo = selfLo; c.nSelf = selfHi - selfLo;
     cudaEventRecord(ctx->ev[EV_RS_BEGIN], s);
-    const uint64_t n = db->n, nItems = nHits + n;
+    const uint64_t n = db->n, nItems = nHits + c.nSelf;
     PG_TRY(ctx->alnAll.reserve(sizeof(pg_aln) * (nItems + 1)));
     PG_TRY(ctx->flags.reserve(nItems + 16 + sizeof(unsigned) * (n + 1) + sizeof(unsigned long long) * (n + 2) + scan_workspace_bytes(n) + 64));
     pg_aln *res = ctx->alnAll.as<pg_aln>();
@@ -328,7 +349,7 @@ int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHit
     PG_CUDA(cudaStreamSynchronize(s));
     PG_TRY(ctx->alns.reserve(sizeof(pg_aln) * (h + 1)));
     pg_aln *out = ctx->alns.as<pg_aln>();
-    if (n) gather_self_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(res, nHits, n, off, acc, out);
+    if (c.nSelf) gather_self_kernel<<<(unsigned) ((c.nSelf + 255) / 256), 256, 0, s>>>(res, nHits, c.nSelf, off, acc, selfLo, out);
     if (nHits) gather_hits_kernel<<<(unsigned) ((nHits + 255) / 256), 256, 0, s>>>(*db, d_hits, nHits, acc, res, off, out);
     ctx->launches += 2;
     cudaEventRecord(ctx->ev[EV_RS_END], s);
