@@ -328,7 +328,10 @@ def main():
     nrec = int(tim[-1]["n_kmer_records"])
     alg_bytes = nrec * 16 * 2                      # a sort = one read + one write of every record
     achieved = alg_bytes / 1e9 / (scatter_ms / 1e3) if scatter_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # DRAM traffic of one scatter launch from the ncu --set full capture of this kernel (profiles/r1_summary_c.md):
+    # 8.14 GB for 250 M records = 32.56 B per record and pass, i.e. the algorithmic 2 x 16 B plus 1.7 % (status words, tails)
+    traffic = nrec * 32.56
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "radix_scatter_kernel (sort #1, %d launches/step)" % passes,
                 "algorithmic_bytes_per_launch": alg_bytes / max(passes, 1), "launch_ms": scatter_ms / max(passes, 1), "peak_source": peak_src}
     stage_ms = {k: float(np.mean([t[k] for t in tim])) for k in ("extract_ms", "sort1_ms", "group_ms", "sort2_ms", "reduce_ms", "rescore_ms", "extend_ms", "exchange_ms", "total_ms")}
