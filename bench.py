@@ -17,8 +17,9 @@ A "step" is one pass of the hot path over that fragment DB.
              assembleresults sub-commands, all host threads) on a bounded sample of the same fragments
 
 --impl reference times only that reference arm (CPU) and prints it as the line's value.
-N > 1 (torchrun): weak scaling -- R reads per GPU; the k-mer hash space is sharded over the ranks and the
-candidate pairs are exchanged with one NCCL all-to-all (torch.distributed), see DESIGN.md §5.
+N > 1 (torchrun): weak scaling -- R reads per GPU; extraction is sliced by sequence, the k-mer records go to the
+rank owning the k-mer and the candidate pairs to the rank owning the representative (two NCCL all-to-alls through
+torch.distributed), see DESIGN.md §5.
 """
 import argparse
 import json
@@ -300,11 +301,12 @@ def main():
     for i in range(1 + e2e_steps):
         barrier()
         t0 = time.perf_counter()
-        d_in = ctx.upload(pinned)
         if runner:
+            d_in, h2d_rank = sharded.upload_sliced(ctx, dist, pinned, rank, world)   # PCIe: this rank's slice; NVLink: the rest
             out = runner.step(d_in, kp, rp, ep, download=True)
             d2h = runner.last_d2h_bytes
         else:
+            d_in = ctx.upload(pinned)
             out, hits, alns = ctx.assemble_iteration(d_in, kp, rp, ep, want_intermediates=True)
             host_out = out.download()
             d2h = int(hits.nbytes + alns.nbytes + host_out.data.nbytes + host_out.offsets.nbytes + host_out.lens.nbytes + host_out.keys.nbytes)
@@ -320,6 +322,9 @@ def main():
         t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
+        t = torch.tensor([d2h], dtype=torch.int64, device="cuda")      # bytes of the whole job: sum over the ranks
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        d2h = int(t.item())
     e2e_value = n_reads_total / e2e_dt
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------
@@ -360,7 +365,8 @@ def main():
                        "reads": n_reads_total, "fragments": int(db.n), "kmer_records": nrec, "pair_records": int(tim[-1]["n_pair_records"]),
                        "hits": int(tim[-1]["n_hits"]), "alignments": int(tim[-1]["n_alns"]), "output_sequences": int(n_out),
                        "l2": "inputs_larger_than_l2 (%.1f GB of k-mer records per step)" % (nrec * 16 / 1e9),
-                       "parallelism": "kmer-hash shards x%d, one all-to-all" % world if world > 1 else "single GPU"},
+                       "parallelism": ("%d ranks: sequence-sliced extraction, all-to-all of k-mer records by k-mer owner, all-to-all of pair records by "
+                                       "representative owner; record counts above are rank 0's share" % world) if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_dt * 1000.0},
             "gpu_launches": int(sum(t["kernel_launches"] for t in tim)),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "stage_ms": stage_ms,

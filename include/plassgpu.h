@@ -119,6 +119,10 @@ void pg_destroy(pg_context *ctx);
 int pg_get_timings(const pg_context *ctx, pg_timings *out);
 
 int pg_seqdb_upload(pg_context *ctx, const pg_seqdb_view *view, pg_seqdb **db);
+/* Same, but the view's four arrays are DEVICE pointers owned by the caller (not copied; pg_seqdb_free releases only
+ * the handle; data needs 16 readable bytes past data_bytes).  Multi-GPU: every rank copies its slice of the DB to
+ * its GPU, the slices are all-gathered over NVLink, and the gathered arrays are adopted (plass_b200/sharded.py). */
+int pg_seqdb_adopt(pg_context *ctx, const pg_seqdb_view *device_view, pg_seqdb **db);
 /* Copies a device-resident DB back: all four arrays are pinned host buffers (pg_free_host). */
 int pg_seqdb_download(pg_context *ctx, const pg_seqdb *db, char **data, uint64_t *data_bytes, uint64_t **offsets,
                       uint32_t **lens, uint32_t **keys, uint64_t *n);
@@ -139,20 +143,44 @@ int pg_assemble_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_param
                           const pg_ex_params *ep, pg_seqdb **out_db,
                           pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns);
 
-/* Multi-GPU, one process per GPU.  The k-mer hash space is sharded over the ranks exactly
- * like the reference's memory splits (kmermatcher.cpp:736-778: rank r extracts only the k-mers whose 16-bit
- * hash lies in [kp->hash_start, kp->hash_end]); equal k-mers share a hash, so sort #1 and the group step are
- * rank-local.  The (rep, target, diagonal) pairs are then routed to the rank that owns the representative
- * (contiguous key ranges) by ONE all-to-all, which the caller performs on the device buffers (NCCL through
- * torch.distributed in bench.py / plass_b200/sharded.py); everything downstream is local to the owner.
+/* Multi-GPU, one process per GPU.  The sequence DB is replicated in every HBM; one iteration is
+ * split around its two exchange steps, which the caller performs on the device buffers (NCCL all-to-all through
+ * torch.distributed in bench.py / plass_b200/sharded.py):
  *
- *   pg_shard_pairs   extraction of this rank's hash range + sort #1 + group; the pair records are left on
- *                    the device grouped by destination rank; counts[world] (host) = records per destination
- *   pg_shard_export  copies those records into a caller-supplied DEVICE buffer (the all-to-all send buffer)
- *   pg_shard_finish  received pairs (DEVICE pointer) -> sort #2 + best diagonal -> rescorediagonal ->
- *                    (nucl)assembleresults for the queries with key in [own_lo, own_hi); out_db holds only
- *                    those sequences.  hits / alns (optional) are copied to pinned host arrays.
+ *   pg_shard_extract  k-mer extraction (fillKmerPositionArray, kmermatcher.cpp:77-385) of this rank's slice of the
+ *                     SEQUENCES; the 16-byte k-mer records are left on the device partitioned by the rank that owns
+ *                     the k-mer (a fixed hash of the k-mer; equal k-mers meet on one rank, which is all that sort #1
+ *                     + assignGroup need).  counts[world] (host) = records per destination rank.
+ *   -- all-to-all #1 (k-mer records) --
+ *   pg_shard_group    received records -> sort #1 + assignGroup (kmermatcher.cpp:408-559); the (rep, target,
+ *                     diagonal) pair records stay on the device; rep_hist[PG_SHARD_HIST_BINS] (host) = number of
+ *                     pair records per slice of the representative key space, bin = rep * BINS / (max_key + 1).
+ *   pg_shard_route    representatives are owned in contiguous key ranges, rank r owning [bounds[r], bounds[r+1])
+ *                     (bounds[0] = 0, bounds[world] = 0xFFFFFFFF).  Representatives are the longest / lowest-id
+ *                     members of their groups, so the work per key is heavily skewed towards low ids: the caller
+ *                     sums rep_hist over the ranks and cuts the key space into ranges of equal work
+ *                     (plass_b200/sharded.py:balanced_bounds).  The pair records are partitioned by owner;
+ *                     counts[world] as above.
+ *   -- all-to-all #2 (pair records) --
+ *   pg_shard_finish   received pairs -> sort #2 + best diagonal (kmermatcher.cpp:427-431, :809-924) ->
+ *                     rescorediagonal -> (nucl)assembleresults for the queries with key in [own_lo, own_hi);
+ *                     out_db holds only those sequences.  hits / alns (optional) are copied to pinned host arrays.
+ *   pg_shard_export   copies the records the preceding phase left behind into a caller-supplied DEVICE buffer
+ *                     (the all-to-all send buffer).
+ *
+ *   pg_shard_pairs    single-exchange variant = the reference's memory-split mechanism (kmermatcher.cpp:736-778):
+ *                     every rank extracts from ALL sequences only the k-mers whose 16-bit hash lies in
+ *                     [kp->hash_start, kp->hash_end], groups them and leaves the pair records partitioned by
+ *                     representative owner (equal key ranges, pg_shard_owner_range); followed by all-to-all #2 and pg_shard_finish.  Extraction work is
+ *                     replicated world times, so it is the better choice only for world <= 2.
+ *
+ * pg_get_timings after pg_shard_finish reports the sums over the phases of the step.
  */
+int pg_shard_extract(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, int rank, int world, uint64_t *counts);
+#define PG_SHARD_HIST_BINS 4096
+int pg_shard_group(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, const void *device_records, uint64_t n_records,
+                   uint64_t *rep_hist);
+int pg_shard_route(pg_context *ctx, int world, const uint32_t *bounds, uint64_t *counts);
 int pg_shard_pairs(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, int world, uint64_t *counts);
 int pg_shard_export(pg_context *ctx, void *device_dst, uint64_t n_records);
 int pg_shard_finish(pg_context *ctx, const pg_seqdb *db, const void *device_pairs, uint64_t n_pairs,

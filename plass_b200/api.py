@@ -16,10 +16,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libplassgpu.so")
 
 # symbols include/plassgpu.h declares
-EXPORTS = ["pg_last_error", "pg_device_count", "pg_init", "pg_destroy", "pg_get_timings", "pg_seqdb_upload",
+EXPORTS = ["pg_last_error", "pg_device_count", "pg_init", "pg_destroy", "pg_get_timings", "pg_seqdb_upload", "pg_seqdb_adopt",
            "pg_seqdb_download", "pg_seqdb_size", "pg_seqdb_free", "pg_kmermatch", "pg_rescore", "pg_extend",
            "pg_assemble_iteration", "pg_free_host",
-           "pg_shard_pairs", "pg_shard_export", "pg_shard_finish", "pg_shard_owner_range", "pg_seqdb_max_key"]
+           "pg_shard_pairs", "pg_shard_extract", "pg_shard_group", "pg_shard_route", "pg_shard_export", "pg_shard_finish", "pg_shard_owner_range", "pg_seqdb_max_key"]
+
+
+SHARD_HIST_BINS = 4096   # PG_SHARD_HIST_BINS
 
 
 class SeqDBView(C.Structure):
@@ -130,6 +133,7 @@ class DeviceSeqDB:
     def __init__(self, ctx, handle):
         self.ctx = ctx
         self.handle = handle
+        self.keepalive = None
 
     @property
     def n(self):
@@ -154,6 +158,7 @@ class DeviceSeqDB:
         if self.handle:
             load_library().pg_seqdb_free(self.ctx.handle, self.handle)
             self.handle = None
+            self.keepalive = None
 
 
 class Context:
@@ -189,6 +194,18 @@ class Context:
         _check(load_library().pg_seqdb_upload(self.handle, C.byref(v), C.byref(h)), "pg_seqdb_upload")
         d = DeviceSeqDB(self, h)
         d.dbtype = db.dbtype
+        return d
+
+    def adopt(self, data_ptr, data_bytes, offsets_ptr, lens_ptr, keys_ptr, n, dbtype, keepalive=None):
+        """Wraps caller-owned device arrays (e.g. torch tensors filled by an all-gather) as a DeviceSeqDB."""
+        v = SeqDBView()
+        v.data, v.data_bytes = data_ptr, data_bytes
+        v.offsets, v.lens, v.keys, v.n, v.dbtype = offsets_ptr, lens_ptr, keys_ptr, n, dbtype
+        h = C.c_void_p()
+        _check(load_library().pg_seqdb_adopt(self.handle, C.byref(v), C.byref(h)), "pg_seqdb_adopt")
+        d = DeviceSeqDB(self, h)
+        d.dbtype = dbtype
+        d.keepalive = keepalive
         return d
 
     # kmermatcher (lib/mmseqs/src/linclust/kmermatcher.cpp:780)
@@ -236,6 +253,24 @@ class Context:
         counts = (C.c_uint64 * world)()
         _check(load_library().pg_shard_pairs(self.handle, ddb.handle, C.byref(kp), C.c_int(world), counts), "pg_shard_pairs")
         return [int(c) for c in counts]
+
+    def shard_extract(self, ddb, kp, rank, world):
+        counts = (C.c_uint64 * world)()
+        _check(load_library().pg_shard_extract(self.handle, ddb.handle, C.byref(kp), C.c_int(rank), C.c_int(world), counts), "pg_shard_extract")
+        return [int(x) for x in counts]
+
+    def shard_group(self, ddb, kp, device_ptr, n_records):
+        hist = np.zeros(SHARD_HIST_BINS, dtype=np.uint64)
+        _check(load_library().pg_shard_group(self.handle, ddb.handle, C.byref(kp), C.c_void_p(device_ptr), C.c_uint64(n_records),
+                                             C.c_void_p(hist.ctypes.data)), "pg_shard_group")
+        return hist
+
+    def shard_route(self, bounds):
+        world = len(bounds) - 1
+        b = (C.c_uint32 * (world + 1))(*[int(x) for x in bounds])
+        counts = (C.c_uint64 * world)()
+        _check(load_library().pg_shard_route(self.handle, C.c_int(world), b, counts), "pg_shard_route")
+        return [int(x) for x in counts]
 
     def shard_export(self, device_ptr, n_records):
         _check(load_library().pg_shard_export(self.handle, C.c_void_p(device_ptr), C.c_uint64(n_records)), "pg_shard_export")

@@ -14,6 +14,7 @@ void set_error(const std::string &msg) { g_error = msg; }
 // see pg_init), so producing a new DB every iteration does not pay cudaMalloc / cudaFree each time.
 void seqdb_release(pg_seqdb *db, cudaStream_t s) {
     if (!db) return;
+    if (db->borrowed) { delete db; return; }
     if (db->data) cudaFreeAsync(db->data, s);
     if (db->offsets) cudaFreeAsync(db->offsets, s);
     if (db->lens) cudaFreeAsync(db->lens, s);
@@ -23,34 +24,37 @@ void seqdb_release(pg_seqdb *db, cudaStream_t s) {
 
 // max length, residue count, max key, key density -- one small reduction kernel
 __global__ void seqdb_stats_kernel(const unsigned *__restrict__ lens, const unsigned *__restrict__ keys, unsigned long long n,
-                                   unsigned long long *__restrict__ out /* [0] sum(len), [1] maxLen, [2] maxKey, [3] nonDense */) {
-    unsigned long long sum = 0, mx = 0, mk = 0, nd = 0;
+                                   unsigned long long *__restrict__ out /* [0] sum(len), [1] maxLen, [2] maxKey, [3] nonDense, [4] not ascending */) {
+    unsigned long long sum = 0, mx = 0, mk = 0, nd = 0, na = 0;
     for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
         const unsigned l = lens[i], k = keys[i];
         sum += l; mx = max(mx, (unsigned long long) l); mk = max(mk, (unsigned long long) k); nd += (k != (unsigned) i);
+        if (i > 0 && keys[i - 1] >= k) na++;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
         nd += __shfl_xor_sync(0xFFFFFFFFu, nd, o);
+        na += __shfl_xor_sync(0xFFFFFFFFu, na, o);
         mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
         mk = max(mk, __shfl_xor_sync(0xFFFFFFFFu, mk, o));
     }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], sum); atomicMax(&out[1], mx); atomicMax(&out[2], mk); atomicAdd(&out[3], nd); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], sum); atomicMax(&out[1], mx); atomicMax(&out[2], mk); atomicAdd(&out[3], nd); if (na) atomicAdd(&out[4], na); }
 }
 
 int seqdb_finalize(Context *ctx, pg_seqdb *db) {
     PG_TRY(ctx->small.reserve(4096));
     unsigned long long *d = ctx->small.as<unsigned long long>() + 16;
-    PG_CUDA(cudaMemsetAsync(d, 0, 32, ctx->stream));
+    PG_CUDA(cudaMemsetAsync(d, 0, 40, ctx->stream));
     if (db->n) seqdb_stats_kernel<<<NUM_SMS * 2, 256, 0, ctx->stream>>>(db->lens, db->keys, db->n, d);
-    unsigned long long h[4];
+    unsigned long long h[5];
     PG_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     PG_CUDA(cudaStreamSynchronize(ctx->stream));
     db->residues = (double) h[0] - 2.0 * (double) db->n;        // DBReader::getAminoAcidDBSize (DBReader.cpp:537-546)
     db->max_seq_len = h[1] >= 2 ? (unsigned) (h[1] - 2) : 0;
     db->max_key = (unsigned) h[2];
     db->dense_keys = (h[3] == 0);
+    PG_CHECK(h[4] == 0, "sequence DB: keys must be strictly ascending (index order of a sequence DB)");
     return 0;
 }
 
@@ -107,15 +111,13 @@ static void collect_timings(Context *ctx) {
     pg_timings &t = ctx->timings;
     auto el = [&](int a, int b) { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]) != cudaSuccess) { ms = 0; cudaGetLastError(); } return ms; };
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->kmRan) {
-        t.extract_ms = el(EV_KM_BEGIN, EV_EXTRACT_END);
+    if (ctx->tExtract) t.extract_ms = el(EV_KM_BEGIN, EV_EXTRACT_END);
+    if (ctx->tGroup) {
         t.sort1_ms = el(EV_SORT1_BEGIN, EV_SORT1_END);
         t.sort1_scatter_ms = el(EV_SCATTER1_BEGIN, EV_SCATTER1_END);
         t.group_ms = el(EV_SORT1_END, EV_GROUP_END);
-        t.sort2_ms = el(EV_GROUP_END, EV_SORT2_END);
-        t.reduce_ms = el(EV_SORT2_END, EV_REDUCE_END);
     }
-    else if (ctx->rsRan) {   // pg_shard_finish: only sort #2 + reduce ran in this call
+    if (ctx->tReduce) {
         t.sort2_ms = el(EV_GROUP_END, EV_SORT2_END);
         t.reduce_ms = el(EV_SORT2_END, EV_REDUCE_END);
     }
@@ -127,7 +129,7 @@ static void collect_timings(Context *ctx) {
 
 static void begin_call(Context *ctx) {
     cudaSetDevice(ctx->device);
-    ctx->kmRan = ctx->rsRan = ctx->exRan = false;
+    ctx->tExtract = ctx->tGroup = ctx->tReduce = ctx->rsRan = ctx->exRan = false;
     ctx->launches = 0;
     memset(&ctx->timings, 0, sizeof(ctx->timings));
     cudaEventRecord(ctx->ev[EV_TOTAL_BEGIN], ctx->stream);
@@ -135,6 +137,24 @@ static void begin_call(Context *ctx) {
 static void end_call(Context *ctx) {
     cudaEventRecord(ctx->ev[EV_TOTAL_END], ctx->stream);
     collect_timings(ctx);
+}
+// multi-GPU: one step is several calls; the reported timings are the sums over its phases
+static void end_shard_phase(Context *ctx, bool first) {
+    end_call(ctx);
+    pg_timings &a = ctx->shardAcc;
+    const pg_timings &t = ctx->timings;
+    if (first) memset(&a, 0, sizeof(a));
+    a.extract_ms += t.extract_ms; a.sort1_ms += t.sort1_ms; a.group_ms += t.group_ms; a.sort2_ms += t.sort2_ms; a.reduce_ms += t.reduce_ms;
+    a.rescore_ms += t.rescore_ms; a.extend_ms += t.extend_ms; a.total_ms += t.total_ms; a.sort1_scatter_ms += t.sort1_scatter_ms;
+    a.kernel_launches += t.kernel_launches;
+    if (t.n_kmer_records) a.n_kmer_records = t.n_kmer_records;
+    if (t.n_pair_records) a.n_pair_records = t.n_pair_records;
+    if (t.sort1_bytes) a.sort1_bytes = t.sort1_bytes;
+    if (t.sort1_passes) a.sort1_passes = t.sort1_passes;
+    if (t.n_hits) a.n_hits = t.n_hits;
+    if (t.n_alns) a.n_alns = t.n_alns;
+    if (t.n_extended) a.n_extended = t.n_extended;
+    ctx->timings = a;
 }
 }  // namespace pg
 
@@ -211,9 +231,23 @@ int pg_seqdb_upload(pg_context *ctx, const pg_seqdb_view *v, pg_seqdb **out) {
     PG_CUDA(cudaMemcpyAsync(db->offsets, v->offsets, sizeof(unsigned long long) * v->n, cudaMemcpyHostToDevice, ctx->stream));
     PG_CUDA(cudaMemcpyAsync(db->lens, v->lens, sizeof(unsigned) * v->n, cudaMemcpyHostToDevice, ctx->stream));
     PG_CUDA(cudaMemcpyAsync(db->keys, v->keys, sizeof(unsigned) * v->n, cudaMemcpyHostToDevice, ctx->stream));
-    PG_TRY(seqdb_finalize(ctx, db));
-    for (uint64_t i = 1; i < v->n; i++)
-        if (v->keys[i] <= v->keys[i - 1]) { seqdb_release(db, ctx->stream); set_error("pg_seqdb_upload: keys must be strictly ascending (index order of a sequence DB)"); return 1; }
+    if (seqdb_finalize(ctx, db)) { seqdb_release(db, ctx->stream); return 1; }
+    *out = db;
+    return 0;
+}
+
+int pg_seqdb_adopt(pg_context *ctx, const pg_seqdb_view *v, pg_seqdb **out) {
+    PG_CHECK(ctx && v && out, "pg_seqdb_adopt: null argument");
+    PG_CHECK(v->dbtype == PG_DBTYPE_AMINO_ACIDS || v->dbtype == PG_DBTYPE_NUCLEOTIDES, "pg_seqdb_adopt: dbtype must be amino acids (0) or nucleotides (1)");
+    PG_CHECK(v->n < 0xFFFFFFF0ull, "pg_seqdb_adopt: more than 2^32 sequences");
+    cudaSetDevice(ctx->device);
+    cudaPointerAttributes at;
+    PG_CHECK(cudaPointerGetAttributes(&at, v->data) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device == ctx->device,
+             "pg_seqdb_adopt: the arrays must live in this context's device memory");
+    pg_seqdb *db = new pg_seqdb();
+    db->n = v->n; db->data_bytes = v->data_bytes; db->dbtype = v->dbtype; db->borrowed = true;
+    db->data = (char *) v->data; db->offsets = (unsigned long long *) v->offsets; db->lens = (unsigned *) v->lens; db->keys = (unsigned *) v->keys;
+    if (seqdb_finalize(ctx, db)) { delete db; return 1; }
     *out = db;
     return 0;
 }
@@ -321,13 +355,38 @@ int pg_shard_pairs(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, 
     PG_CHECK(ctx && db && kp && counts, "pg_shard_pairs: null argument");
     begin_call(ctx);
     PG_TRY(km_shard_pairs(ctx, db, kp, world, counts));
-    end_call(ctx);
+    end_shard_phase(ctx, true);
+    return 0;
+}
+
+int pg_shard_extract(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, int rank, int world, uint64_t *counts) {
+    PG_CHECK(ctx && db && kp && counts, "pg_shard_extract: null argument");
+    begin_call(ctx);
+    PG_TRY(km_shard_extract(ctx, db, kp, rank, world, counts));
+    end_shard_phase(ctx, true);
+    return 0;
+}
+
+int pg_shard_group(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, const void *device_records, uint64_t n_records,
+                   uint64_t *rep_hist) {
+    PG_CHECK(ctx && db && kp && rep_hist && (device_records || n_records == 0), "pg_shard_group: null argument");
+    begin_call(ctx);
+    PG_TRY(km_shard_group(ctx, db, kp, device_records, n_records, rep_hist));
+    end_shard_phase(ctx, false);
+    return 0;
+}
+
+int pg_shard_route(pg_context *ctx, int world, const uint32_t *bounds, uint64_t *counts) {
+    PG_CHECK(ctx && bounds && counts, "pg_shard_route: null argument");
+    begin_call(ctx);
+    PG_TRY(km_shard_route(ctx, world, bounds, counts));
+    end_shard_phase(ctx, false);
     return 0;
 }
 
 int pg_shard_export(pg_context *ctx, void *device_dst, uint64_t n_records) {
     PG_CHECK(ctx && (device_dst || n_records == 0), "pg_shard_export: null argument");
-    PG_CHECK(n_records == ctx->shardPairCount, "pg_shard_export: record count does not match pg_shard_pairs");
+    PG_CHECK(n_records == ctx->shardPairCount, "pg_shard_export: record count does not match the preceding phase");
     cudaSetDevice(ctx->device);
     if (n_records) PG_CUDA(cudaMemcpyAsync(device_dst, ctx->shardPairs, sizeof(Rec) * n_records, cudaMemcpyDeviceToDevice, ctx->stream));
     PG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -338,9 +397,7 @@ int pg_shard_finish(pg_context *ctx, const pg_seqdb *db, const void *device_pair
                     uint32_t own_lo, uint32_t own_hi, const pg_rs_params *rp, const pg_ex_params *ep,
                     pg_seqdb **out_db, pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns) {
     PG_CHECK(ctx && db && rp && ep && out_db && (device_pairs || n_pairs == 0), "pg_shard_finish: null argument");
-    pg_timings keep = ctx->timings;   // phase-1 numbers of this step
     begin_call(ctx);
-    ctx->timings.n_kmer_records = keep.n_kmer_records; ctx->timings.n_pair_records = keep.n_pair_records; ctx->timings.sort1_bytes = keep.sort1_bytes;
     ctx->ownLo = own_lo; ctx->ownHi = own_hi;
     pg_hit *dHits = nullptr; uint64_t nH = 0;
     int rc = km_shard_reduce(ctx, db, device_pairs, n_pairs, &dHits, &nH);
@@ -351,11 +408,7 @@ int pg_shard_finish(pg_context *ctx, const pg_seqdb *db, const void *device_pair
     ctx->ownLo = 0; ctx->ownHi = 0xFFFFFFFFu;
     if (rc != 0) return rc;
     cudaFreeAsync(dExt, ctx->stream);
-    end_call(ctx);
-    // the sort-#2 / reduce events of this call are valid, the extract / sort-#1 ones belong to pg_shard_pairs
-    ctx->timings.extract_ms = keep.extract_ms; ctx->timings.sort1_ms = keep.sort1_ms; ctx->timings.sort1_scatter_ms = keep.sort1_scatter_ms;
-    ctx->timings.sort1_passes = keep.sort1_passes; ctx->timings.group_ms = keep.group_ms;
-    ctx->timings.kernel_launches += keep.kernel_launches; ctx->timings.total_ms += keep.total_ms;
+    end_shard_phase(ctx, false);
     if (hits && n_hits) { PG_TRY(to_host(ctx->stream, dHits, nH, hits)); *n_hits = nH; }
     if (alns && n_alns) { PG_TRY(to_host(ctx->stream, dAlns, nA, alns)); *n_alns = nA; }
     return 0;

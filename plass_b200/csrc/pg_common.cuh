@@ -110,4 +110,5 @@ struct pg_seqdb {
     unsigned max_key = 0;
     double residues = 0;                  // getAminoAcidDBSize = sum(len) - 2n
     bool dense_keys = false;
+    bool borrowed = false;                // pg_seqdb_adopt: the arrays belong to the caller
 };

@@ -21,7 +21,9 @@ struct pg_context {
     bool forceFullSort = false;   // tests: take the 8-pass sort + group_kernel path instead of the bucketed hash join
     unsigned ntTabN = 0;
     bool pairsInA = false;
-    bool kmRan = false, rsRan = false, exRan = false;
+    bool tExtract = false, tGroup = false, tReduce = false, rsRan = false, exRan = false;   // which stages recorded their events in this call
+    pg_timings shardAcc;                       // multi-GPU: stage times accumulated over the phases of one step
+    unsigned seqLo = 0, seqHi = 0xFFFFFFFFu;   // multi-GPU: extraction restricted to the sequences with index in [seqLo, seqHi)
     uint64_t launches = 0;
     pg_timings timings;
     uint64_t nHits = 0, nAlns = 0;
@@ -38,6 +40,10 @@ struct KmConst;
 // kmermatcher stages (pg_kmermatch.cu)
 int km_run(Context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **d_hits, uint64_t *nHits);
 int km_shard_pairs(Context *ctx, const pg_seqdb *db, const pg_km_params *p, int world, uint64_t *counts);
+int km_shard_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, int rank, int world, uint64_t *counts);
+int km_shard_group(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const void *d_records, uint64_t nRecords, uint64_t *hist);
+int km_shard_route(Context *ctx, int world, const unsigned *bounds, uint64_t *counts);
+void km_equal_key_bounds(unsigned max_key, int world, unsigned *bounds);
 int km_shard_reduce(Context *ctx, const pg_seqdb *db, const void *d_pairs, uint64_t nPairs, pg_hit **d_hits, uint64_t *nHits);
 // rescorediagonal (pg_rescore.cu): d_hits sorted by (rep,target); result device array in ctx->alns
 int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHits, const pg_rs_params *p, pg_aln **d_alns, uint64_t *nAlns);

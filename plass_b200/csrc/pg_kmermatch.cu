@@ -130,11 +130,11 @@ __device__ int select_sequential(const Cand *sorted, int cnt, unsigned long long
 // classify: bin sequences by the number of k-mer windows so that each class runs in a kernel whose
 // shared-memory tile fits it.  class 0: <=64, 1: <=256, 2: <=1024, 3: larger (block kernel).
 // ------------------------------------------------------------------------------------------------
-__global__ void classify_kernel(const unsigned *__restrict__ lens, unsigned n, int k, unsigned *__restrict__ lists /*4 x n*/,
+__global__ void classify_kernel(const unsigned *__restrict__ lens, unsigned lo, unsigned hi, unsigned n, int k, unsigned *__restrict__ lists /*4 x n*/,
                                 unsigned *__restrict__ counts /*4*/) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = lo + blockIdx.x * blockDim.x + threadIdx.x;   // sequences [lo, hi) of n
     int cls = -1;
-    if (i < n) {
+    if (i < hi) {
         const int L = (int) lens[i] - 2;
         const int nk = L - k + 1;
         cls = nk <= 64 ? 0 : (nk <= 256 ? 1 : (nk <= 1024 ? 2 : 3));
@@ -1373,10 +1373,10 @@ int km_setup_constants(const pg_seqdb *db, const pg_km_params *p, KmConst &c, cu
 }
 
 // computeKmerCount (kmermatcher.cpp:576-585): upper bound on emitted records
-static __global__ void kmer_count_kernel(const unsigned *__restrict__ lens, unsigned n, int k, int kps, float scale,
+static __global__ void kmer_count_kernel(const unsigned *__restrict__ lens, unsigned lo, unsigned n, int k, int kps, float scale,
                                          unsigned long long *__restrict__ total) {
     unsigned long long mine = 0;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (unsigned i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int seqLen = (int) lens[i] - 2;
         const int adj = max(1, seqLen - k + 2);
         mine += (unsigned long long) min(adj, (int) ((float) kps + (scale * (float) seqLen)));
@@ -1419,10 +1419,11 @@ int km_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const Km
     unsigned long long *d_outCount = d_total + 1;                             // [1] emitted records
     unsigned *d_clsCount = (unsigned *) (d_total + 8);                        // [8..] 4 class counters
     PG_CUDA(cudaMemsetAsync(d_total, 0, 256, s));
-    kmer_count_kernel<<<NUM_SMS * 4, 256, 0, s>>>(db->lens, n, c.k, c.kmersPerSeq, c.scale, d_total);
+    const unsigned sLo = std::min(ctx->seqLo, n), sHi = std::min(ctx->seqHi, n);
+    kmer_count_kernel<<<NUM_SMS * 4, 256, 0, s>>>(db->lens, sLo, sHi, c.k, c.kmersPerSeq, c.scale, d_total);
     PG_TRY(ctx->lists.reserve(sizeof(unsigned) * 4 * (size_t) n + 16));
     unsigned *lists = ctx->lists.as<unsigned>();
-    classify_kernel<<<(n + 255) / 256, 256, 0, s>>>(db->lens, n, c.k, lists, d_clsCount);
+    classify_kernel<<<(sHi - sLo + 255) / 256 + 1, 256, 0, s>>>(db->lens, sLo, sHi, n, c.k, lists, d_clsCount);
     ctx->launches += 2;
     unsigned long long h_total = 0; unsigned h_cls[4];
     PG_CUDA(cudaMemcpyAsync(&h_total, d_total, sizeof(h_total), cudaMemcpyDeviceToHost, s));
@@ -1664,7 +1665,7 @@ int km_run(Context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **d_h
     ctx->timings.n_pair_records = nPairs;
     ctx->timings.n_hits = *nHits;
     ctx->timings.sort1_bytes = (uint64_t) nRec * sizeof(Rec) * 2;
-    ctx->kmRan = true;
+    ctx->tExtract = ctx->tGroup = ctx->tReduce = true;
     return 0;
 }
 
@@ -1672,12 +1673,95 @@ int km_run(Context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **d_h
 // kmermatcher.cpp:736-778: each split extracts only the k-mers whose 16-bit hash falls in its range), the
 // (rep, target, diagonal) pairs are then routed to the rank that owns the representative (contiguous key
 // ranges) with one all-to-all; sort #2 and everything downstream is local to the owner. -------------------
-__global__ void tag_owner_kernel(Rec *__restrict__ pairs, unsigned long long n, unsigned keysPerRank, unsigned world) {
+constexpr int SHARD_HIST_BINS = 4096;
+
+// owner of a representative = the interval of bounds[0..world] (ascending keys, bounds[0] = 0) that contains it
+__global__ void tag_owner_kernel(Rec *__restrict__ pairs, unsigned long long n, const unsigned *__restrict__ bounds, unsigned world) {
+    __shared__ unsigned sB[257];
+    for (unsigned i = threadIdx.x; i <= world; i += blockDim.x) sB[i] = bounds[i];
+    __syncthreads();
     for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
         const unsigned rep = (unsigned) (pairs[i].w0 >> 32);
-        const unsigned owner = min(world - 1u, rep / keysPerRank);
-        pairs[i].w1 = (pairs[i].w1 & 0xFFFFFFULL) | ((unsigned long long) owner << 24);
+        unsigned lo = 0, hi = world;              // invariant: sB[lo] <= rep, (hi == world or rep < sB[hi])
+        while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (rep >= sB[mid]) lo = mid; else hi = mid; }
+        pairs[i].w1 = (pairs[i].w1 & 0xFFFFFFULL) | ((unsigned long long) lo << 24);
     }
+}
+
+// pair records per slice of the representative key space: bin = rep * SHARD_HIST_BINS / (max_key + 1)
+__global__ void rep_hist_kernel(const Rec *__restrict__ pairs, unsigned long long n, unsigned long long keySpan, unsigned long long *__restrict__ hist) {
+    __shared__ unsigned sH[SHARD_HIST_BINS];
+    for (int i = threadIdx.x; i < SHARD_HIST_BINS; i += blockDim.x) sH[i] = 0;
+    __syncthreads();
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
+        const unsigned long long rep = pairs[i].w0 >> 32;
+        const unsigned bin = (unsigned) ((rep * SHARD_HIST_BINS) / keySpan);
+        // neighbouring records often share the representative: aggregate per warp before touching shared memory
+        const unsigned peers = __match_any_sync(__activemask(), bin);
+        if ((int) lane_id() == __ffs(peers) - 1) atomicAdd(&sH[bin], __popc(peers));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SHARD_HIST_BINS; i += blockDim.x) if (sH[i]) atomicAdd(&hist[i], (unsigned long long) sH[i]);
+}
+
+// pair records (recA/recB per ctx->pairsInA) -> tagged with the rank that owns the representative and partitioned by it
+int km_shard_route(Context *ctx, int world, const unsigned *bounds, uint64_t *counts) {
+    PG_CHECK(world >= 1 && world <= 256, "pg_shard_route: world size must be in [1, 256]");
+    PG_CHECK(bounds[0] == 0, "pg_shard_route: bounds[0] must be 0");
+    for (int r = 0; r < world; r++) PG_CHECK(bounds[r] <= bounds[r + 1], "pg_shard_route: bounds must be ascending");
+    cudaStream_t s = ctx->stream;
+    const uint64_t nPairs = ctx->shardPairCount;
+    Rec *pairs = ctx->pairsInA ? ctx->recA.as<Rec>() : ctx->recB.as<Rec>();
+    Rec *tmp = ctx->pairsInA ? ctx->recB.as<Rec>() : ctx->recA.as<Rec>();
+    for (int r = 0; r < world; r++) counts[r] = 0;
+    ctx->shardPairs = pairs;
+    if (nPairs == 0) return 0;
+    PG_TRY(ctx->small.reserve(4096));
+    unsigned *d_bounds = (unsigned *) (ctx->small.as<unsigned long long>() + 64);     // [64..] 257 x u32
+    PG_CUDA(cudaMemcpyAsync(d_bounds, bounds, sizeof(unsigned) * (world + 1), cudaMemcpyHostToDevice, s));
+    tag_owner_kernel<<<NUM_SMS * 8, 256, 0, s>>>(pairs, nPairs, d_bounds, (unsigned) world);
+    RadixPlan plan; plan.npasses = 0;
+    plan_add_bits(plan, 1, 24, 32);
+    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nPairs)));
+    Rec *sorted = nullptr;
+    PG_TRY(radix_sort(pairs, tmp, nPairs, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches));
+    ctx->launches++;
+    unsigned long long h[256];
+    PG_CUDA(cudaMemcpyAsync(h, ctx->radixWs.p, sizeof(unsigned long long) * 256, cudaMemcpyDeviceToHost, s));   // digit histogram of the pass
+    PG_CUDA(cudaStreamSynchronize(s));
+    for (int r = 0; r < world; r++) counts[r] = h[r];
+    ctx->shardPairs = sorted;
+    ctx->pairsInA = (sorted == ctx->recA.as<Rec>());
+    return 0;
+}
+
+// after km_group: remember the pairs and histogram them over the representative key space
+static int shard_pairs_ready(Context *ctx, const pg_seqdb *db, uint64_t nPairs, uint64_t *hist) {
+    cudaStream_t s = ctx->stream;
+    ctx->shardPairs = ctx->pairsInA ? ctx->recA.as<Rec>() : ctx->recB.as<Rec>();
+    ctx->shardPairCount = nPairs;
+    if (!hist) return 0;
+    for (int i = 0; i < SHARD_HIST_BINS; i++) hist[i] = 0;
+    if (nPairs == 0) return 0;
+    PG_TRY(ctx->buckets2.reserve(sizeof(unsigned long long) * SHARD_HIST_BINS));
+    unsigned long long *d_hist = ctx->buckets2.as<unsigned long long>();
+    PG_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * SHARD_HIST_BINS, s));
+    rep_hist_kernel<<<NUM_SMS * 4, 512, 0, s>>>(ctx->shardPairs, nPairs, (unsigned long long) db->max_key + 1ull, d_hist);
+    ctx->launches++;
+    PG_CUDA(cudaMemcpyAsync(hist, d_hist, sizeof(unsigned long long) * SHARD_HIST_BINS, cudaMemcpyDeviceToHost, s));
+    PG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+void km_equal_key_bounds(unsigned max_key, int world, unsigned *bounds) {
+    const unsigned long long per = ((unsigned long long) max_key + (unsigned long long) world) / (unsigned long long) world;
+    for (int r = 0; r <= world; r++) bounds[r] = (r == world) ? 0xFFFFFFFFu : (unsigned) std::min<unsigned long long>(per * (unsigned long long) r, 0xFFFFFFFFull);
+}
+
+static void record_empty_group_events(Context *ctx) {
+    cudaStream_t s = ctx->stream;
+    cudaEventRecord(ctx->ev[EV_SORT1_BEGIN], s); cudaEventRecord(ctx->ev[EV_SCATTER1_BEGIN], s); cudaEventRecord(ctx->ev[EV_SCATTER1_END], s);
+    cudaEventRecord(ctx->ev[EV_SORT1_END], s); cudaEventRecord(ctx->ev[EV_GROUP_END], s);
 }
 
 int km_shard_pairs(Context *ctx, const pg_seqdb *db, const pg_km_params *p, int world, uint64_t *counts) {
@@ -1690,33 +1774,66 @@ int km_shard_pairs(Context *ctx, const pg_seqdb *db, const pg_km_params *p, int 
     PG_TRY(km_extract(ctx, db, p, c, &nRec));
     cudaEventRecord(ctx->ev[EV_EXTRACT_END], s);
     PG_TRY(km_group(ctx, db, c, nRec, &nPairs));
-    if (nRec == 0) {
-        cudaEventRecord(ctx->ev[EV_SORT1_BEGIN], s); cudaEventRecord(ctx->ev[EV_SCATTER1_BEGIN], s); cudaEventRecord(ctx->ev[EV_SCATTER1_END], s);
-        cudaEventRecord(ctx->ev[EV_SORT1_END], s); cudaEventRecord(ctx->ev[EV_GROUP_END], s);
-    }
-    Rec *pairs = ctx->pairsInA ? ctx->recA.as<Rec>() : ctx->recB.as<Rec>();
-    Rec *tmp = ctx->pairsInA ? ctx->recB.as<Rec>() : ctx->recA.as<Rec>();
-    for (int r = 0; r < world; r++) counts[r] = 0;
-    ctx->shardPairs = pairs; ctx->shardPairCount = nPairs;
+    if (nRec == 0) record_empty_group_events(ctx);
     ctx->timings.n_kmer_records = nRec; ctx->timings.n_pair_records = nPairs;
     ctx->timings.sort1_bytes = (uint64_t) nRec * sizeof(Rec) * 2;
-    ctx->kmRan = true;
-    cudaEventRecord(ctx->ev[EV_SORT2_END], s); cudaEventRecord(ctx->ev[EV_REDUCE_END], s);
-    if (nPairs == 0) return 0;
-    const unsigned keysPerRank = (unsigned) (((unsigned long long) db->max_key + world) / world);
-    tag_owner_kernel<<<NUM_SMS * 8, 256, 0, s>>>(pairs, nPairs, keysPerRank, (unsigned) world);
+    ctx->tExtract = ctx->tGroup = true;
+    PG_TRY(shard_pairs_ready(ctx, db, nPairs, nullptr));
+    unsigned bounds[257];
+    km_equal_key_bounds(db->max_key, world, bounds);
+    return km_shard_route(ctx, world, bounds, counts);
+}
+
+// Two-exchange decomposition, phase 0: k-mer extraction of this rank's slice of the SEQUENCES (all hash values), the
+// records partitioned by the rank that owns the k-mer: owner = (top 8 bits of mix64(k-mer)) * world / 256.  Any
+// partition under which equal k-mers meet is equivalent; this one is independent of the bucket bits of the hash join.
+int km_shard_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, int rank, int world, uint64_t *counts) {
+    PG_CHECK(world >= 1 && world <= 256 && rank >= 0 && rank < world, "pg_shard_extract: bad rank / world size");
+    KmConst c;
+    cudaStream_t s = ctx->stream;
+    PG_TRY(km_setup_constants(db, p, c, s));
+    cudaEventRecord(ctx->ev[EV_KM_BEGIN], s);
+    uint64_t nRec = 0;
+    ctx->seqLo = (unsigned) ((unsigned long long) db->n * (unsigned) rank / (unsigned) world);
+    ctx->seqHi = (unsigned) ((unsigned long long) db->n * (unsigned) (rank + 1) / (unsigned) world);
+    const int rc = km_extract(ctx, db, p, c, &nRec);
+    ctx->seqLo = 0; ctx->seqHi = 0xFFFFFFFFu;
+    if (rc) return rc;
+    for (int r = 0; r < world; r++) counts[r] = 0;
+    ctx->shardPairs = ctx->recA.as<Rec>(); ctx->shardPairCount = nRec;
+    ctx->timings.n_kmer_records = nRec;
+    ctx->tExtract = true;
+    if (nRec == 0 || world == 1) { counts[0] = nRec; cudaEventRecord(ctx->ev[EV_EXTRACT_END], s); return 0; }
     RadixPlan plan; plan.npasses = 0;
-    plan_add_bits(plan, 1, 24, 32);
-    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nPairs)));
+    plan_add_hash_bits(plan, c.nt ? ~(1ULL << 63) : ~0ULL, 56, 64);
+    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nRec)));
     Rec *sorted = nullptr;
-    PG_TRY(radix_sort(pairs, tmp, nPairs, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches));
-    ctx->launches++;
+    PG_TRY(radix_sort(ctx->recA.as<Rec>(), ctx->recB.as<Rec>(), nRec, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches));
+    cudaEventRecord(ctx->ev[EV_EXTRACT_END], s);
     unsigned long long h[256];
-    PG_CUDA(cudaMemcpyAsync(h, ctx->radixWs.p, sizeof(unsigned long long) * 256, cudaMemcpyDeviceToHost, s));   // digit histogram of the pass
+    PG_CUDA(cudaMemcpyAsync(h, ctx->radixWs.p, sizeof(unsigned long long) * 256, cudaMemcpyDeviceToHost, s));
     PG_CUDA(cudaStreamSynchronize(s));
-    for (int r = 0; r < world; r++) counts[r] = h[r];
+    for (int b = 0; b < 256; b++) counts[(unsigned) b * (unsigned) world / 256u] += h[b];
     ctx->shardPairs = sorted;
     return 0;
+}
+
+// phase 1: the k-mer records this rank received (every record of the k-mers it owns) -> sort #1 + group -> pair
+// records (left on the device for pg_shard_route) and their histogram over the representative key space
+int km_shard_group(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const void *d_records, uint64_t nRec, uint64_t *hist) {
+    KmConst c;
+    cudaStream_t s = ctx->stream;
+    PG_TRY(km_setup_constants(db, p, c, s));
+    PG_TRY(ctx->recA.reserve(sizeof(Rec) * (nRec + 1)));
+    PG_TRY(ctx->recB.reserve(sizeof(Rec) * (nRec + 1)));
+    if (nRec && d_records != ctx->recA.p) PG_CUDA(cudaMemcpyAsync(ctx->recA.p, d_records, sizeof(Rec) * nRec, cudaMemcpyDeviceToDevice, s));
+    uint64_t nPairs = 0;
+    PG_TRY(km_group(ctx, db, c, nRec, &nPairs));
+    if (nRec == 0) record_empty_group_events(ctx);
+    ctx->timings.n_kmer_records = nRec; ctx->timings.n_pair_records = nPairs;
+    ctx->timings.sort1_bytes = (uint64_t) nRec * sizeof(Rec) * 2;
+    ctx->tGroup = true;
+    return shard_pairs_ready(ctx, db, nPairs, hist);
 }
 
 int km_shard_reduce(Context *ctx, const pg_seqdb *db, const void *d_pairs, uint64_t nPairs, pg_hit **d_hits, uint64_t *nHits) {
@@ -1728,6 +1845,7 @@ int km_shard_reduce(Context *ctx, const pg_seqdb *db, const void *d_pairs, uint6
     if (nPairs == 0) { cudaEventRecord(ctx->ev[EV_SORT2_END], s); cudaEventRecord(ctx->ev[EV_REDUCE_END], s); }
     PG_TRY(km_reduce(ctx, db, ctx->recA.as<Rec>(), ctx->recB.as<Rec>(), nPairs, d_hits, nHits));
     ctx->timings.n_hits = *nHits;
+    ctx->tReduce = true;
     return 0;
 }
 

@@ -40,6 +40,35 @@ def main():
         blk = recv[off: off + c * sharded.REC_BYTES]
         assert bool((blk == 16 * src + rank).all())
         off += c * sharded.REC_BYTES
+    # k-mer owner bins: 256 hash bins map monotonically onto the ranks, every rank gets at least one bin (world <= 256)
+    own_bins = [b * world // 256 for b in range(256)]
+    assert own_bins[0] == 0 and own_bins[-1] == world - 1 and all(0 <= own_bins[i + 1] - own_bins[i] <= 1 for i in range(255))
+    # sliced upload: every rank contributes its slice of the DB, the broadcasts reassemble the whole DB everywhere
+    from plass_b200 import synth
+    db = synth.protein_fragments(synth.make_reads(301, seed=5))
+    sb = sharded.slice_bounds(db.n, world)
+    assert sb[0][0] == 0 and sb[-1][1] == db.n and all(sb[i][1] == sb[i + 1][0] for i in range(world - 1))
+    (g_data, g_offs, g_lens, g_keys), h2d = sharded.gather_slices(dist, db, rank, world, torch.device("cpu"))
+    assert np.array_equal(g_data[:-16].numpy(), np.asarray(db.data)) and np.array_equal(g_offs[:-1].numpy().view(np.uint64), np.asarray(db.offsets, dtype=np.uint64))
+    assert np.array_equal(g_lens[:-1].numpy().view(np.uint32), np.asarray(db.lens, dtype=np.uint32)) and np.array_equal(g_keys[:-1].numpy().view(np.uint32), np.asarray(db.keys, dtype=np.uint32))
+    tb = torch.tensor([h2d], dtype=torch.int64)
+    dist.all_reduce(tb)
+    assert int(tb[0]) == db.data.nbytes + 16 * db.n
+    # balanced representative ranges: every rank derives the same bounds from the all-reduced histogram, and the
+    # ranges carry (nearly) equal work although the histogram is heavily skewed towards low keys
+    hist = (np.random.default_rng(7 + rank).random(4096) * 1000 * np.exp(-np.arange(4096) / 500.0)).astype(np.int64)
+    th = torch.from_numpy(hist.copy())
+    dist.all_reduce(th)
+    bounds = sharded.balanced_bounds(th.numpy(), max_key, world, per_key_weight=0.0)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, bounds)
+    assert all(g == bounds for g in gathered)
+    assert bounds[0] == 0 and bounds[-1] == 0xFFFFFFFF and all(bounds[i] <= bounds[i + 1] for i in range(world))
+    span = max_key + 1
+    bin_of = lambda key: min(4095, key * 4096 // span)
+    tot_h = th.numpy().astype(np.float64)
+    share = [tot_h[bin_of(bounds[r]): (bin_of(bounds[r + 1]) if r + 1 < world else 4096)].sum() / tot_h.sum() for r in range(world)]
+    assert all(abs(x - 1.0 / world) < 0.02 for x in share), share
     tot = torch.tensor([sum(counts), sum(rcl)], dtype=torch.int64)
     dist.all_reduce(tot)
     assert int(tot[0]) == int(tot[1])

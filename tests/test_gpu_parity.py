@@ -158,11 +158,38 @@ def test_fused_iteration_matches_golden_chain(case, golden_root, ctx):
         assert t["kernel_launches"] > 0 and t["n_hits"] == len(hits)
 
 
-@pytest.mark.parametrize("case,world", [("synth_aa", 2), ("synth_aa", 4), ("synth_nt", 2)])
-def test_sharded_iteration_equals_single_gpu(case, world, golden_root, ctx):
-    """The multi-GPU decomposition (k-mer hash shards -> all-to-all of pair records -> owner-local sort #2,
-    rescoring and extension), emulated rank by rank on one GPU: the union of the ranks' results must equal the
-    unsharded run (and therefore the reference)."""
+def ctx_n_records(ctx, ddb, kp):
+    recs = ctx.debug_extract(ddb, kp)
+    return len(recs)
+
+
+def ptr_n(recv_n):
+    recv, n = recv_n
+    ptr_n.keep = recv          # keep the tensor alive across the call that consumes its pointer
+    return recv.data_ptr(), n
+
+
+def emulated_all_to_all(sends, counts, dst):
+    import torch
+    parts = []
+    for src in range(len(sends)):
+        off = sum(counts[src][:dst]) * 16
+        parts.append(sends[src][off: off + counts[src][dst] * 16])
+    recv = torch.cat(parts)
+    n = recv.numel() // 16
+    if n == 0:
+        recv = torch.empty(16, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    return recv, n
+
+
+@pytest.mark.parametrize("case,world,mode", [("synth_aa", 2, "two"), ("synth_aa", 4, "two"), ("synth_nt", 2, "two"), ("synth_nt", 3, "two"),
+                                             ("synth_aa", 2, "hash"), ("synth_nt", 2, "hash")])
+def test_sharded_iteration_equals_single_gpu(case, world, mode, golden_root, ctx):
+    """The multi-GPU decompositions, emulated rank by rank on one GPU: the union of the ranks' results must equal
+    the unsharded run (and therefore the reference).  "two": sequence-sliced extraction -> all-to-all of k-mer
+    records -> group -> all-to-all of pair records -> owner-local sort #2, rescoring, extension;  "hash": the
+    reference's hash-range split of the extraction + only the pair exchange."""
     import torch
     from plass_b200 import sharded
     d, man = golden_case(case, golden_root)
@@ -176,24 +203,38 @@ def test_sharded_iteration_equals_single_gpu(case, world, golden_root, ctx):
     ref_out, ref_hits, ref_alns = ctx.assemble_iteration(ddb, kp, rp, ep, want_intermediates=True)
     ref_db = ref_out.download()
     ref_out.free()
-    sends, counts = [], []
-    for r in range(world):
-        c = ctx.shard_pairs(ddb, sharded.shard_km_params(kp, r, world), world)
+    def export(c):
         t = torch.empty(max(sum(c), 1) * 16, dtype=torch.uint8, device="cuda")
         ctx.shard_export(t.data_ptr(), sum(c))
-        sends.append(t); counts.append(c)
+        return t
+
+    sends, counts = [], []
+    if mode == "hash":
+        for r in range(world):
+            c = ctx.shard_pairs(ddb, sharded.shard_km_params(kp, r, world), world)
+            sends.append(export(c)); counts.append(c)
+    else:
+        ksends, kcounts = [], []
+        for r in range(world):
+            c = ctx.shard_extract(ddb, kp, r, world)
+            ksends.append(export(c)); kcounts.append(c)
+        assert sum(sum(c) for c in kcounts) == ctx_n_records(ctx, ddb, kp)
+        # the ranks run one after the other on one context, so the group phase runs twice: once for the summed
+        # histogram (the all-reduce), once more right before each rank's route
+        hist = sum(ctx.shard_group(ddb, kp, *ptr_n(emulated_all_to_all(ksends, kcounts, r))).astype(np.float64) for r in range(world))
+        bounds = sharded.balanced_bounds(hist, ddb.max_key, world)
+        assert bounds[0] == 0 and bounds[-1] == 0xFFFFFFFF and all(bounds[i] <= bounds[i + 1] for i in range(world))
+        for r in range(world):
+            h = ctx.shard_group(ddb, kp, *ptr_n(emulated_all_to_all(ksends, kcounts, r)))
+            c = ctx.shard_route(bounds)
+            assert sum(c) == int(h.sum())
+            sends.append(export(c)); counts.append(c)
+    if mode == "hash":
+        bounds = [sharded.owner_range(ddb.max_key, r, world)[0] for r in range(world)] + [0xFFFFFFFF]
     all_hits, all_alns, entries = [], [], {}
     for dst in range(world):
-        parts = []
-        for src in range(world):
-            off = sum(counts[src][:dst]) * 16
-            parts.append(sends[src][off: off + counts[src][dst] * 16])
-        recv = torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device="cuda")
-        n = recv.numel() // 16
-        if n == 0:
-            recv = torch.empty(16, dtype=torch.uint8, device="cuda")
-        torch.cuda.synchronize()
-        out, hits, alns = ctx.shard_finish(ddb, recv.data_ptr(), n, sharded.owner_range(ddb.max_key, dst, world), rp, ep, want_intermediates=True)
+        recv, n = emulated_all_to_all(sends, counts, dst)
+        out, hits, alns = ctx.shard_finish(ddb, recv.data_ptr(), n, (bounds[dst], bounds[dst + 1]), rp, ep, want_intermediates=True)
         got = out.download()
         out.free()
         all_hits.append(hits.copy()); all_alns.append(alns.copy())
