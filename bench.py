@@ -61,6 +61,12 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def workload_name(reads_per_gpu, per_gpu):
+    cfg = {5000000: " (BASELINE configs[1])", 50000000: " (BASELINE configs[2], one iteration)"}.get(reads_per_gpu, "")
+    return "%gM synthetic 150bp coding reads%s -> aa fragments, k=14, alph 13, --min-seq-id 0.9, 1 iteration%s" % (
+        reads_per_gpu / 1e6, " per GPU" if per_gpu else "", cfg)
+
+
 def make_fragments(n_reads, seed):
     cache = os.path.join(tempfile.gettempdir(), "plass_b200_frag_%d_%d.npz" % (n_reads, seed))
     if os.path.exists(cache):
@@ -68,12 +74,14 @@ def make_fragments(n_reads, seed):
         return mmseqsdb.DB(z["data"], z["keys"], z["offsets"], z["lens"], 0)
     t = time.time()
     reads = synth.make_reads_fast(n_reads, seed=seed)
-    db = synth.protein_fragments(reads)
+    db = synth.protein_fragments(reads, workers=min(16, os.cpu_count() or 1))
+    del reads
     log("[bench] generated %d reads -> %d aa fragments (mean %.1f aa) in %.1f s" % (n_reads, db.n, float(db.lens.mean()) - 2, time.time() - t))
-    try:
-        np.savez(cache, data=db.data, keys=db.keys, offsets=db.offsets, lens=db.lens)
-    except OSError:
-        pass
+    if n_reads <= 12000000:      # the cache only serves the other ranks of a multi-GPU run and repeated small samples
+        try:
+            np.savez(cache, data=db.data, keys=db.keys, offsets=db.offsets, lens=db.lens)
+        except OSError:
+            pass
     return db
 
 
@@ -115,6 +123,23 @@ def run_reference_iteration(db, threads, workdir):
         per.append(dt)
         total += dt
     return total, per
+
+
+def sized_cpu_sample(args, n_reads_total, threads, work):
+    """Bounded sample for the CPU arm: the same generator at the same 20x coverage (a prefix of the big DB would have
+    lower coverage, fewer overlaps per read, and flatter the CPU).  A first run on --cpu-sample-reads reads calibrates;
+    if it took less than ~10 s the sample is enlarged towards ~15 s of CPU work, up to the whole workload."""
+    sample_reads = min(args.cpu_sample_reads, n_reads_total)
+    sample = make_fragments(sample_reads, args.seed)
+    t, per = run_reference_iteration(sample, threads, work)
+    log("[bench/reference] calibration: %d reads in %.2f s" % (sample_reads, t))
+    if t < 10.0 and sample_reads < n_reads_total:
+        want = int(sample_reads * 15.0 / max(t, 0.05))
+        want = min(n_reads_total, max(sample_reads, (want // 100000) * 100000))
+        if want > sample_reads:
+            sample_reads = want
+            sample = make_fragments(sample_reads, args.seed)
+    return sample_reads, sample
 
 
 class ClockSampler:
@@ -163,9 +188,8 @@ def reference_arm(args, db_full, n_reads_total):
     threads = os.cpu_count() or 1
     # same generator, same 20x coverage, fewer reads (a prefix of the big DB would have lower coverage and
     # therefore fewer overlaps per read, which would flatter the CPU)
-    sample_reads = min(args.cpu_sample_reads, n_reads_total)
-    sample = make_fragments(sample_reads, args.seed)
     work = os.path.join(tempfile.gettempdir(), "plass_b200_ref_%d" % os.getpid())
+    sample_reads, sample = sized_cpu_sample(args, n_reads_total, threads, work)
     times = []
     try:
         for i in range(args.warmup + args.steps):
@@ -183,7 +207,7 @@ def reference_arm(args, db_full, n_reads_total):
         "metric": "reads/sec per assemble iteration (kmermatcher+rescorediagonal+assembleresults)", "value": val, "unit": "reads/s",
         "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1000.0,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (+f64 E-values)", "data": "synthetic",
-        "config": {"workload": "5M synthetic 150bp coding reads -> aa fragments, k=14, alph 13, 1 iteration (BASELINE configs[1]); bounded sample",
+        "config": {"workload": workload_name(args.reads, False) + "; bounded sample",
                    "reads": n_reads_total, "fragments": int(db_full.n)},
         "cpu_baseline": {"value": val, "unit": "reads/s", "cores": threads, "kind": "reference", "sample": sample_desc},
         "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -296,7 +320,7 @@ def main():
                          torch.from_numpy(db.offsets.view(np.int64)).pin_memory().numpy().view(np.uint64),
                          torch.from_numpy(db.lens.view(np.int32)).pin_memory().numpy().view(np.uint32), db.dbtype)
     h2d = int(pinned.data.nbytes + pinned.keys.nbytes + pinned.offsets.nbytes + pinned.lens.nbytes)
-    e2e_times, d2h = [], 0
+    e2e_times, d2h, e2e_phases = [], 0, []
     e2e_steps = max(1, min(args.steps, 2))
     for i in range(1 + e2e_steps):
         barrier()
@@ -307,8 +331,12 @@ def main():
             d2h = runner.last_d2h_bytes
         else:
             d_in = ctx.upload(pinned)
+            t1 = time.perf_counter()
             out, hits, alns = ctx.assemble_iteration(d_in, kp, rp, ep, want_intermediates=True)
+            t2 = time.perf_counter()
             host_out = out.download()
+            if i > 0:
+                e2e_phases.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (time.perf_counter() - t2) * 1e3))
             d2h = int(hits.nbytes + alns.nbytes + host_out.data.nbytes + host_out.offsets.nbytes + host_out.lens.nbytes + host_out.keys.nbytes)
             # the step's results live in pinned blocks of the library's pool: drop them so that the next step reuses
             # the blocks instead of pinning 2 GB of fresh host memory
@@ -345,9 +373,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN):
         try:
             threads = os.cpu_count() or 1
-            sample_reads = min(args.cpu_sample_reads, n_reads_total)
-            sample = make_fragments(sample_reads, args.seed)
             work = os.path.join(tempfile.gettempdir(), "plass_b200_cpu_%d" % os.getpid())
+            sample_reads, sample = sized_cpu_sample(args, n_reads_total, threads, work)
             t, per = run_reference_iteration(sample, threads, work)
             shutil.rmtree(work, ignore_errors=True)
             cpu = {"value": sample_reads / t, "unit": "reads/s", "cores": threads, "kind": "reference",
@@ -361,13 +388,15 @@ def main():
             "metric": "reads/sec per assemble iteration (kmermatcher+rescorediagonal+assembleresults)", "value": value, "unit": "reads/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (+f64 E-values)", "data": "synthetic",
-            "config": {"workload": "5M synthetic 150bp coding reads per GPU -> aa fragments, k=14, alph 13, --min-seq-id 0.9, 1 iteration (BASELINE configs[1])",
+            "config": {"workload": workload_name(args.reads, True),
                        "reads": n_reads_total, "fragments": int(db.n), "kmer_records": nrec, "pair_records": int(tim[-1]["n_pair_records"]),
                        "hits": int(tim[-1]["n_hits"]), "alignments": int(tim[-1]["n_alns"]), "output_sequences": int(n_out),
                        "l2": "inputs_larger_than_l2 (%.1f GB of k-mer records per step)" % (nrec * 16 / 1e9),
                        "parallelism": ("%d ranks: sequence-sliced extraction, all-to-all of k-mer records by k-mer owner, all-to-all of pair records by "
                                        "representative owner; record counts above are rank 0's share" % world) if world > 1 else "single GPU"},
-            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_dt * 1000.0},
+            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_dt * 1000.0,
+                    "phases_ms": ({"upload": float(np.mean([p[0] for p in e2e_phases])), "iteration_with_hits_alns_d2h": float(np.mean([p[1] for p in e2e_phases])),
+                                   "download_new_db": float(np.mean([p[2] for p in e2e_phases]))} if e2e_phases else None)},
             "gpu_launches": int(sum(t["kernel_launches"] for t in tim)),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "stage_ms": stage_ms,
         }

@@ -22,6 +22,26 @@ void seqdb_release(pg_seqdb *db, cudaStream_t s) {
     delete db;
 }
 
+__global__ void read_back_kernel(unsigned *__restrict__ hostMapped, const unsigned *__restrict__ dev, unsigned words) {
+    for (unsigned i = threadIdx.x; i < words; i += blockDim.x) hostMapped[i] = dev[i];
+}
+
+int read_back(Context *ctx, void *host, const void *dev, size_t bytes) {
+    PG_CHECK(bytes <= 1024 && (bytes & 3) == 0, "read_back: at most 1024 bytes, multiple of 4");
+    read_back_kernel<<<1, 32, 0, ctx->stream>>>((unsigned *) ctx->hostStage, (const unsigned *) dev, (unsigned) (bytes / 4));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(host, ctx->hostStage, bytes);
+    return 0;
+}
+
+__global__ void count_nonzero_kernel(const unsigned char *__restrict__ v, unsigned long long n, unsigned long long *__restrict__ out) {
+    unsigned long long c = 0;
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) c += v[i] != 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 // max length, residue count, max key, key density -- one small reduction kernel
 __global__ void seqdb_stats_kernel(const unsigned *__restrict__ lens, const unsigned *__restrict__ keys, unsigned long long n,
                                    unsigned long long *__restrict__ out /* [0] sum(len), [1] maxLen, [2] maxKey, [3] nonDense, [4] not ascending */) {
@@ -48,8 +68,7 @@ int seqdb_finalize(Context *ctx, pg_seqdb *db) {
     PG_CUDA(cudaMemsetAsync(d, 0, 40, ctx->stream));
     if (db->n) seqdb_stats_kernel<<<NUM_SMS * 2, 256, 0, ctx->stream>>>(db->lens, db->keys, db->n, d);
     unsigned long long h[5];
-    PG_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    PG_TRY(read_back(ctx, h, d, sizeof(h)));
     db->residues = (double) h[0] - 2.0 * (double) db->n;        // DBReader::getAminoAcidDBSize (DBReader.cpp:537-546)
     db->max_seq_len = h[1] >= 2 ? (unsigned) (h[1] - 2) : 0;
     db->max_key = (unsigned) h[2];
@@ -104,6 +123,21 @@ static int to_host(cudaStream_t s, const T *d, uint64_t n, T **out) {
     if (n) PG_CUDA(cudaMemcpyAsync(h, d, sizeof(T) * n, cudaMemcpyDeviceToHost, s));
     PG_CUDA(cudaStreamSynchronize(s));
     *out = h;
+    return 0;
+}
+
+// Device -> host copy of a finished stage's result on the context's copy stream, so that the transfer runs under the
+// kernels of the following stage (the result buffers ctx->hits / ctx->alns are not written again within the call).
+// The caller synchronises ctx->copyStream before it hands the host array out.
+template <class T>
+static int to_host_overlapped(Context *ctx, const T *d, uint64_t n, T **out) {
+    T *h = nullptr;
+    PG_TRY(alloc_pinned(sizeof(T) * (n + 1), (void **) &h));
+    *out = h;
+    if (n == 0) return 0;
+    PG_CUDA(cudaEventRecord(ctx->evCopyReady, ctx->stream));
+    PG_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evCopyReady, 0));
+    PG_CUDA(cudaMemcpyAsync(h, d, sizeof(T) * n, cudaMemcpyDeviceToHost, ctx->copyStream));
     return 0;
 }
 
@@ -186,6 +220,9 @@ int pg_init(int device, pg_context **out) {
     pg_context *ctx = new pg_context();
     ctx->device = device;
     PG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    PG_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+    PG_CUDA(cudaEventCreateWithFlags(&ctx->evCopyReady, cudaEventDisableTiming));
+    PG_CUDA(cudaHostAlloc((void **) &ctx->hostStage, 1024, cudaHostAllocMapped | cudaHostAllocPortable));
     {
         cudaMemPool_t pool;
         PG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -206,6 +243,10 @@ void pg_destroy(pg_context *ctx) {
                       &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta, &ctx->exLists, &ctx->ntTab, &ctx->buckets, &ctx->buckets2};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamSynchronize(ctx->copyStream);
+    cudaEventDestroy(ctx->evCopyReady);
+    cudaFreeHost(ctx->hostStage);
+    cudaStreamDestroy(ctx->copyStream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -322,22 +363,23 @@ int pg_assemble_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_param
     begin_call(ctx);
     pg_hit *dHits = nullptr; uint64_t nH = 0;
     PG_TRY(km_run(ctx, db, kp, &dHits, &nH));
+    if (hits && n_hits) { PG_TRY(to_host_overlapped(ctx, dHits, nH, hits)); *n_hits = nH; }        // copied while rescorediagonal runs
     pg_aln *dAlns = nullptr; uint64_t nA = 0;
     PG_TRY(rs_run(ctx, db, dHits, nH, rp, &dAlns, &nA));
+    if (alns && n_alns) { PG_TRY(to_host_overlapped(ctx, dAlns, nA, alns)); *n_alns = nA; }        // copied while the extension runs
     unsigned char *dExt = nullptr;
     PG_TRY(ex_run(ctx, db, dAlns, nA, ep, out_db, &dExt));
     {   // number of new contigs, for the statistics
-        std::vector<unsigned char> h((*out_db)->n + 1);
-        PG_CUDA(cudaMemcpyAsync(h.data(), dExt, (*out_db)->n, cudaMemcpyDeviceToHost, ctx->stream));
-        PG_CUDA(cudaStreamSynchronize(ctx->stream));
-        uint64_t c = 0;
-        for (uint64_t i = 0; i < (*out_db)->n; i++) c += h[i];
+        unsigned long long *d = ctx->small.as<unsigned long long>() + 40;
+        PG_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream));
+        if ((*out_db)->n) count_nonzero_kernel<<<NUM_SMS * 2, 256, 0, ctx->stream>>>(dExt, (*out_db)->n, d);
+        unsigned long long c = 0;
+        PG_TRY(read_back(ctx, &c, d, sizeof(c)));
         ctx->timings.n_extended = c;
     }
     cudaFreeAsync(dExt, ctx->stream);
     end_call(ctx);
-    if (hits && n_hits) { PG_TRY(to_host(ctx->stream, dHits, nH, hits)); *n_hits = nH; }
-    if (alns && n_alns) { PG_TRY(to_host(ctx->stream, dAlns, nA, alns)); *n_alns = nA; }
+    PG_CUDA(cudaStreamSynchronize(ctx->copyStream));
     return 0;
 }
 
@@ -401,16 +443,17 @@ int pg_shard_finish(pg_context *ctx, const pg_seqdb *db, const void *device_pair
     ctx->ownLo = own_lo; ctx->ownHi = own_hi;
     pg_hit *dHits = nullptr; uint64_t nH = 0;
     int rc = km_shard_reduce(ctx, db, device_pairs, n_pairs, &dHits, &nH);
+    if (rc == 0 && hits && n_hits) { rc = to_host_overlapped(ctx, dHits, nH, hits); *n_hits = nH; }
     pg_aln *dAlns = nullptr; uint64_t nA = 0;
     unsigned char *dExt = nullptr;
     if (rc == 0) rc = rs_run(ctx, db, dHits, nH, rp, &dAlns, &nA);
+    if (rc == 0 && alns && n_alns) { rc = to_host_overlapped(ctx, dAlns, nA, alns); *n_alns = nA; }
     if (rc == 0) rc = ex_run(ctx, db, dAlns, nA, ep, out_db, &dExt);
     ctx->ownLo = 0; ctx->ownHi = 0xFFFFFFFFu;
-    if (rc != 0) return rc;
+    if (rc != 0) { cudaStreamSynchronize(ctx->copyStream); return rc; }
     cudaFreeAsync(dExt, ctx->stream);
     end_shard_phase(ctx, false);
-    if (hits && n_hits) { PG_TRY(to_host(ctx->stream, dHits, nH, hits)); *n_hits = nH; }
-    if (alns && n_alns) { PG_TRY(to_host(ctx->stream, dAlns, nA, alns)); *n_alns = nA; }
+    PG_CUDA(cudaStreamSynchronize(ctx->copyStream));
     return 0;
 }
 

@@ -487,6 +487,199 @@ __global__ void __launch_bounds__(256) extend_round_warp_kernel(const pg_seqdb d
     }
 }
 
+// Amino acids, queries with at most 32 alignments: the WHOLE query in one warp -- every round of the reference's outer
+// loop (assembleresult.cpp:193-313) without leaving the kernel.  Pop / extend / park exactly as in
+// extend_round_warp_kernel; a parked hit stays in the registers of its lane, and when the queue has drained the
+// same warp re-scores the parked hits on the new contig (lane-parallel operand fetch, then the warp sums the
+// diagonals one after the other, as extend_rescore_kernel does) and starts the next round with them.  No per-round
+// state, work lists or host synchronisation.
+__global__ void __launch_bounds__(256) extend_query_warp_kernel(const pg_seqdb db, const pg_aln *__restrict__ alns,
+                                                                const unsigned long long *__restrict__ alnStart, const unsigned *__restrict__ alnCount,
+                                                                const ExConst c, const unsigned *__restrict__ list, const unsigned *__restrict__ listCount,
+                                                                ExSeg *__restrict__ segBuf, unsigned *__restrict__ segCount,
+                                                                unsigned *__restrict__ outLen, unsigned char *__restrict__ extended,
+                                                                unsigned char *__restrict__ used) {
+    __shared__ unsigned char sA2n[256];
+    __shared__ signed char sMat[21 * 21];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sA2n[i] = c_ex_a2n[i];
+    for (int i = threadIdx.x; i < 21 * 21; i += blockDim.x) sMat[i] = c_ex_mat[i];
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned nList = *listCount;
+    const unsigned warpsTotal = gridDim.x * (blockDim.x >> 5);
+    for (unsigned li = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); li < nList; li += warpsTotal) {
+        const unsigned qi = list[li];
+        const unsigned nAl = alnCount[qi];
+        if (nAl > EX_WARP_MAX_ALNS) continue;                 // handled by the round-based heap path
+        const unsigned long long a0 = alnStart[qi];
+        ExSeg *segs = segBuf + a0 + qi;
+        const unsigned queryKey = db.keys[qi];
+        unsigned querySeqLen = db.lens[qi] - 2;
+        if (lane == 0) { segs[0].src = qi; segs[0].start = 0; segs[0].len = querySeqLen; segs[0].rev = 0; }
+        int ropeN = 1; unsigned ropeLen = querySeqLen;
+        bool couldExtend = false;
+        ExRes r; r.dbKey = 0; r.score = 0; r.seqId = 0; r.alnLength = 0; r.qStartPos = r.qEndPos = 0; r.qLen = 0; r.dbStartPos = r.dbEndPos = 0; r.dbLen = 0; r.rev = 0;
+        bool alive = false;
+        unsigned myTargetId = 0, myTargetLen = 0;
+        if (lane < nAl) {
+            const pg_aln a = alns[a0 + lane];
+            r.dbKey = a.target;
+            r.seqId = seqid_text_roundtrip(a.seq_id);
+            r.qStartPos = a.q_start; r.qEndPos = a.q_end; r.qLen = (unsigned) a.q_len;
+            r.dbStartPos = a.db_start; r.dbEndPos = a.db_end; r.dbLen = (unsigned) a.db_len;
+            const int adjQ = (r.qStartPos == -1) ? 0 : r.qStartPos;
+            const int adjD = (r.dbStartPos == -1) ? 0 : r.dbStartPos;
+            r.alnLength = (unsigned) (max(abs(r.qEndPos - adjQ), abs(r.dbEndPos - adjD)) + 1);
+            const int rawScore = (int) (((c.logK + (double) a.bits * log(2.0)) / c.lambda) + 0.5);
+            const float scorePerCol = __fdiv_rn((float) rawScore, (float) ((double) r.alnLength + 0.5));
+            const float alnLen = (float) r.alnLength;
+            const float ids = __fmul_rn(r.seqId, alnLen);
+            r.seqId = (float) ((double) ids / ((double) alnLen + 0.5));
+            r.score = (int) __fmul_rn(scorePerCol, 100.0f);
+            alive = true;
+            // every lane resolves ITS target once (index, length): the pops below then need no dependent global loads
+            myTargetId = find_id(db.keys, (unsigned) db.n, r.dbKey);
+            myTargetLen = db.lens[myTargetId] - 2;
+        }
+        const char *myTargetSeq = db.data + db.offsets[myTargetId];
+        while (true) {                                        // one iteration = one round of the reference's outer loop
+            const bool entered = alive;                       // this element is in the queue of this round
+            // selectFragmentToExtend's predicate (assembleresult.cpp:40-57): failing elements are popped and dropped
+            if (alive) {
+                const bool notRightStartAndLeftStart = !(r.dbStartPos == 0 && r.qStartPos == 0);
+                const bool rightStart = r.dbStartPos == 0 && (r.dbEndPos != (int) r.dbLen - 1);
+                const bool leftStart = r.qStartPos == 0 && (r.qEndPos != (int) r.qLen - 1);
+                alive = (rightStart || leftStart) && notRightStartAndLeftStart && (r.dbKey != queryKey);
+            }
+            unsigned leftOff = 0, rightOff = 0;
+            bool parked = false;
+            int nPark = 0;
+            bool queueNotEmpty = false;   // set by the length-limit `break`: the queue keeps its lower-priority elements
+            while (true) {
+                const unsigned aliveMask = __ballot_sync(0xFFFFFFFFu, alive);
+                if (aliveMask == 0) break;
+                // arg-max by (score, alnLength, smaller dbKey)
+                int bs = alive ? r.score : INT_MIN; unsigned bl = r.alnLength, bk = r.dbKey; int bLane = alive ? (int) lane : -1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const int os = __shfl_xor_sync(0xFFFFFFFFu, bs, o);
+                    const unsigned ol = __shfl_xor_sync(0xFFFFFFFFu, bl, o), ok = __shfl_xor_sync(0xFFFFFFFFu, bk, o);
+                    const int oLane = __shfl_xor_sync(0xFFFFFFFFu, bLane, o);
+                    const bool take = (oLane >= 0) && (bLane < 0 || os > bs || (os == bs && (ol > bl || (ol == bl && ok < bk))));
+                    if (take) { bs = os; bl = ol; bk = ok; bLane = oLane; }
+                }
+                const int wl = bLane;                                  // the same in every lane
+                if ((int) lane == wl) alive = false;                   // popped
+                const int bDbStart = __shfl_sync(0xFFFFFFFFu, r.dbStartPos, wl), bDbEnd = __shfl_sync(0xFFFFFFFFu, r.dbEndPos, wl);
+                const int bQStart = __shfl_sync(0xFFFFFFFFu, r.qStartPos, wl), bQEnd = __shfl_sync(0xFFFFFFFFu, r.qEndPos, wl);
+                const unsigned targetId = __shfl_sync(0xFFFFFFFFu, myTargetId, wl);
+                const unsigned targetSeqLen = __shfl_sync(0xFFFFFFFFu, myTargetLen, wl);
+                if (bDbStart == 0) {
+                    if ((targetSeqLen - (unsigned) (bDbEnd + 1)) <= rightOff) continue;
+                } else if (bQStart == 0) {
+                    if (bDbStart <= (int) leftOff) continue;
+                }
+                const unsigned dbStartPos = (unsigned) bDbStart, dbEndPos = (unsigned) bDbEnd;
+                const unsigned qStartPos = (unsigned) bQStart, qEndPos = (unsigned) bQEnd;
+                if (dbStartPos == 0 && qEndPos == (querySeqLen - 1)) {            // right extension
+                    if (rightOff > 0) { if ((int) lane == wl) parked = true; nPark++; continue; }
+                    const unsigned fragLen = targetSeqLen - (dbEndPos + 1);
+                    if (lane == 0) {
+                        ExSeg g; g.src = targetId; g.len = fragLen; g.rev = 0; g.start = dbEndPos + 1;
+                        segs[ropeN] = g;
+                        used[targetId] = 1;
+                    }
+                    ropeN++; ropeLen += fragLen; rightOff += fragLen;
+                } else if (qStartPos == 0 && dbEndPos == (targetSeqLen - 1)) {    // left extension
+                    if (leftOff > 0) { if ((int) lane == wl) parked = true; nPark++; continue; }
+                    const unsigned fragLen = dbStartPos;
+                    if ((unsigned long long) ropeLen + fragLen >= (unsigned long long) c.maxSeqLen) {
+                        // `break` (assembleresult.cpp:258-262): everything with a lower priority than this hit -- selectable
+                        // or not -- is still in the reference's queue, and a non-empty queue ends the query (:287-288)
+                        const bool lower = entered && (int) lane != wl &&
+                                           (r.score < bs || (r.score == bs && (r.alnLength < bl || (r.alnLength == bl && r.dbKey > bk))));
+                        queueNotEmpty = __ballot_sync(0xFFFFFFFFu, lower) != 0;
+                        break;
+                    }
+                    if (lane == 0) {
+                        ExSeg g; g.src = targetId; g.len = fragLen; g.rev = 0; g.start = 0;
+                        for (int sI = ropeN; sI > 0; sI--) segs[sI] = segs[sI - 1];
+                        segs[0] = g;
+                        used[targetId] = 1;
+                    }
+                    ropeN++; ropeLen += fragLen; leftOff += fragLen;
+                }
+            }
+            if (leftOff > 0 || rightOff > 0) couldExtend = true;
+            __syncwarp();                                     // lane 0's rope segments are visible to the warp
+            if (queueNotEmpty || nPark == 0) break;
+            // ---- re-score the parked hits on the new contig (assembleresult.cpp:293-307, updateAlignment :70-108)
+            Rope rope; rope.segs = segs; rope.data = db.data; rope.offsets = db.offsets; rope.n = ropeN; rope.len = ropeLen;
+            int diag = 0;
+            unsigned qOff = 0, tOff = 0, len = 0, first = 0, last = 0;
+            bool valid = false;
+            if (parked) {
+                diag = (int) ((unsigned) r.qStartPos + leftOff) - r.dbStartPos;
+                const unsigned dist = (unsigned) abs(diag);
+                if (diag >= 0 && dist < ropeLen) { len = min(myTargetLen, ropeLen - dist); qOff = dist; valid = len > 0; }
+                else if (diag < 0 && dist < myTargetLen) { len = min(myTargetLen - dist, ropeLen); tOff = dist; valid = len > 0; }
+                if (valid) {
+                    first = (rope.at(qOff) == '*' || (unsigned char) myTargetSeq[tOff] == '*') ? 1u : 0u;
+                    last = len - 1;
+                    if (last > 0 && (rope.at(qOff + len - 1) == '*' || (unsigned char) myTargetSeq[tOff + len - 1] == '*')) last--;
+                }
+            }
+            long long mySum = 0; int myIds = 0;
+            unsigned todo = __ballot_sync(0xFFFFFFFFu, valid);
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const char *t = (const char *) __shfl_sync(0xFFFFFFFFu, (unsigned long long) myTargetSeq, j);
+                const unsigned qo = __shfl_sync(0xFFFFFFFFu, qOff, j), to = __shfl_sync(0xFFFFFFFFu, tOff, j);
+                const unsigned f = __shfl_sync(0xFFFFFFFFu, first, j), l = __shfl_sync(0xFFFFFFFFu, last, j);
+                long long sum = 0; int ids = 0;
+                // score over [first, last]; identities over [qS, qE) = columns [first, last)  (exclusive end of updateAlignment)
+                for (unsigned pos = f + lane; pos <= l; pos += 32) {
+                    const unsigned char a = rope.at(qo + pos), b = (unsigned char) t[to + pos];
+                    sum += sMat[sA2n[a] * c.alph + sA2n[b]];
+                    if (pos < l) ids += (a == b) ? 1 : 0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o); ids += __shfl_xor_sync(0xFFFFFFFFu, ids, o); }
+                if ((int) lane == j) { mySum = sum; myIds = ids; }
+            }
+            alive = false;
+            if (parked) {
+                int start = -1, end = -1; unsigned score = 0, diagLen = 0; int idCnt = 0;
+                const unsigned dist = (unsigned) abs(diag);
+                if ((diag >= 0 && dist < ropeLen) || (diag < 0 && dist < myTargetLen)) diagLen = len;
+                if (valid) {
+                    if (mySum < 0) mySum = 0;
+                    start = (int) first; end = (int) last; score = (unsigned) mySum; idCnt = myIds;
+                }
+                const int d2 = max(abs(diag), 0);
+                int qS, qE, dS, dE;
+                if (diag >= 0) { qS = start + d2; qE = end + d2; dS = start; dE = end; }
+                else { qS = start; qE = end; dS = start + d2; dE = end + d2; }
+                r.seqId = __fdiv_rn((float) idCnt, __fsub_rn((float) qE, (float) qS));
+                r.qLen = ropeLen; r.dbLen = myTargetLen;
+                r.alnLength = diagLen;
+                const float scorePerCol = __fdiv_rn((float) score, (float) ((double) r.alnLength + 0.5));
+                r.score = (int) __fmul_rn(scorePerCol, 100.0f);
+                r.qStartPos = qS; r.qEndPos = qE; r.dbStartPos = dS; r.dbEndPos = dE;
+                alive = r.seqId >= c.seqIdThr;                // re-queued only if it still passes --min-seq-id (:309-311)
+            }
+            querySeqLen = ropeLen;                            // querySeqLen = query.length() (assembleresult.cpp:291)
+        }
+        if (couldExtend && lane == 0) {
+            extended[qi] = 1;
+            outLen[qi] = ropeLen + 2;
+            segCount[qi] = (unsigned) ropeN;
+        }
+        __syncwarp();
+    }
+}
+
 // Re-scoring of the parked alignments on the extended contigs (assembleresult.cpp:293-307).  A warp takes 32
 // parked hits: every lane fetches the operands of ITS hit (state, rope, target, overlap geometry -- a chain of
 // dependent loads that now overlaps across the lanes), the warp then sums the 32 diagonals one after the other with
@@ -724,20 +917,29 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     if (nAlns) aln_ranges_kernel<<<(unsigned) ((nAlns + 255) / 256), 256, 0, s>>>(*db, d_alns, nAlns, alnStart, alnCount, listA, d_listCnt);
     ctx->launches += 2;
     unsigned hCnt[3] = {0, 0, 0};
-    PG_CUDA(cudaMemcpyAsync(hCnt, d_listCnt, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
-    PG_CUDA(cudaStreamSynchronize(s));
+    PG_TRY(read_back(ctx, hCnt, d_listCnt, 3 * sizeof(unsigned)));
     const bool needHeap = nt || hCnt[2] > 0;
     lap("init_out+aln_ranges");
     unsigned active = hCnt[0];
     unsigned *cur = listA, *nxt = listB;
     int curIdx = 0;
+    // amino acids: the queries with <= 32 alignments (all of them, usually) run to completion inside one kernel; only
+    // the larger ones go through the rounds below
+    const bool fusedWarp = !nt && getenv("PG_EX_WAVEFRONT") == nullptr;
+    if (fusedWarp && active > 0) {
+        extend_query_warp_kernel<<<std::min<unsigned>((active + 7) / 8, NUM_SMS * 32), 256, 0, s>>>(
+            *db, d_alns, alnStart, alnCount, c, cur, d_listCnt + curIdx, ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
+        ctx->launches++;
+        if (!needHeap) active = 0;
+        lap("extend_query_warp");
+    }
     for (int round = 0; active > 0; round++) {
         PG_CHECK(round < 100000, "assembleresults: extension did not converge");
         PG_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
         PG_CUDA(cudaMemsetAsync(d_listCnt + (1 - curIdx), 0, sizeof(unsigned), s));
-        if (!nt) {
-            // amino acids: warp per query for the queries with <= 32 alignments (list half 0), heap replay for the rest
-            // (both kernels read the same list and skip the queries of the other class)
+        if (!nt && !fusedWarp) {
+            // amino acids, wavefront variant (PG_EX_WAVEFRONT=1): warp per query for the queries with <= 32 alignments,
+            // heap replay for the rest (both kernels read the same list and skip the queries of the other class)
             extend_round_warp_kernel<<<std::min<unsigned>((active + 7) / 8, NUM_SMS * 32), 256, 0, s>>>(
                 *db, d_alns, alnStart, alnCount, c, round == 0, cur, d_listCnt + curIdx, nxt, d_listCnt + (1 - curIdx), work, d_cnt, states,
                 parkBuf, ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
@@ -751,8 +953,7 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
         }
         extend_rescore_kernel<<<NUM_SMS * 8, 256, 0, s>>>(*db, alnStart, c, work, d_cnt, states, parkBuf, ctx->exSegs.as<ExSeg>());
         ctx->launches += 1;
-        PG_CUDA(cudaMemcpyAsync(hCnt, d_listCnt + (1 - curIdx), sizeof(unsigned), cudaMemcpyDeviceToHost, s));
-        PG_CUDA(cudaStreamSynchronize(s));
+        PG_TRY(read_back(ctx, hCnt, d_listCnt + (1 - curIdx), sizeof(unsigned)));
         active = hCnt[0];
         unsigned *t = cur; cur = nxt; nxt = t;
         curIdx = 1 - curIdx;
@@ -765,8 +966,7 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     PG_TRY(exclusive_scan_u32(outLen, outOff, n, d_tot, scanWs, scan_workspace_bytes(n), s, &ctx->launches));
     PG_TRY(exclusive_scan_u32(keep, keepIdx, n, d_tot + 1, scanWs, scan_workspace_bytes(n), s, &ctx->launches));
     unsigned long long h[2] = {0, 0};
-    PG_CUDA(cudaMemcpyAsync(h, d_tot, sizeof(h), cudaMemcpyDeviceToHost, s));
-    PG_CUDA(cudaStreamSynchronize(s));
+    PG_TRY(read_back(ctx, h, d_tot, sizeof(h)));
     PG_CUDA(cudaGetLastError());
     lap("keep + scans");
     pg_seqdb *out = new pg_seqdb();

@@ -16,6 +16,9 @@ enum {
 struct pg_context {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copyStream = nullptr;         // device -> host copies of finished stage results, overlapped with the next stage
+    cudaEvent_t evCopyReady = nullptr;
+    unsigned long long *hostStage = nullptr;   // mapped pinned words: the kernels' small results are read back through here (pg::read_back)
     cudaEvent_t ev[pg::EV_COUNT];
     pg::DevBuf small, lists, recA, recB, radixWs, scratch, blockCounts, hits, alnAll, alns, flags, exWork, exSegs, exMeta, exLists, ntTab, buckets, buckets2;
     bool forceFullSort = false;   // tests: take the 8-pass sort + group_kernel path instead of the bucketed hash join
@@ -51,5 +54,9 @@ int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHit
 int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAlns, const pg_ex_params *p, pg_seqdb **out, unsigned char **d_extended);
 int seqdb_finalize(Context *ctx, pg_seqdb *db);   // computes max_seq_len / residues / dense_keys on the device
 void seqdb_release(pg_seqdb *db, cudaStream_t s);
+// Small device -> host read-back (counters, totals) that does NOT go through the copy engine: a one-warp kernel stores
+// the words into mapped pinned memory and the stream is synchronised.  A cudaMemcpyAsync would queue behind the large
+// result transfers that run on ctx->copyStream underneath the following stage.  bytes <= 1024, multiple of 4.
+int read_back(Context *ctx, void *host, const void *dev, size_t bytes);
 int alloc_pinned(size_t bytes, void **out);        // pooled pinned host memory, released with pg_free_host
 }  // namespace pg

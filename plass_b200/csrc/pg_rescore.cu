@@ -319,8 +319,7 @@ int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHit
         unsigned *d_lb = (unsigned *) (ctx->small.as<unsigned long long>() + 36);
         key_lower_bound_kernel<<<1, 32, 0, s>>>(db->keys, (unsigned) db->n, ctx->ownLo, ctx->ownHi, d_lb);
         unsigned h_lb[2] = {0, 0};
-        PG_CUDA(cudaMemcpyAsync(h_lb, d_lb, sizeof(h_lb), cudaMemcpyDeviceToHost, s));
-        PG_CUDA(cudaStreamSynchronize(s));
+        PG_TRY(read_back(ctx, h_lb, d_lb, sizeof(h_lb)));
         selfLo = h_lb[0]; selfHi = h_lb[1];
     }
     c.selfLo = selfLo; c.nSelf = selfHi - selfLo;
@@ -345,8 +344,7 @@ int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHit
     ctx->launches += 3;
     PG_TRY(exclusive_scan_u32(cnt, off, n, d_total, scanWs, scan_workspace_bytes(n), s, &ctx->launches));
     unsigned long long h = 0;
-    PG_CUDA(cudaMemcpyAsync(&h, d_total, sizeof(h), cudaMemcpyDeviceToHost, s));
-    PG_CUDA(cudaStreamSynchronize(s));
+    PG_TRY(read_back(ctx, &h, d_total, sizeof(h)));
     PG_TRY(ctx->alns.reserve(sizeof(pg_aln) * (h + 1)));
     pg_aln *out = ctx->alns.as<pg_aln>();
     if (c.nSelf) gather_self_kernel<<<(unsigned) ((c.nSelf + 255) / 256), 256, 0, s>>>(res, nHits, c.nSelf, off, acc, selfLo, out);

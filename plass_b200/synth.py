@@ -79,44 +79,72 @@ def _translate(codes):
     return _AA_LUT[(c[:, :, 0] << 4) | (c[:, :, 1] << 2) | c[:, :, 2]]
 
 
-def protein_fragments(reads, min_len=45, chunk=500000):
-    """Six-frame translation + split at stops; returns an in-memory amino-acid sequence DB."""
+def _fragments_of_chunk(r, min_len):
+    """Fragments of one block of reads: (data pieces, length pieces) in strand-major, frame-minor order."""
     datas, lens = [], []
-    for s in range(0, len(reads), chunk):
-        r = reads[s:s + chunk]
-        for strand in (r, _COMP[r[:, ::-1]]):
-            codes = _CODE[strand]
-            for f in range(3):
-                k = (codes.shape[1] - f) // 3
-                aa = _translate(codes[:, f:f + 3 * k])
-                # runs between stops, per row: append a stop column so runs never cross rows
-                stop = np.ones((aa.shape[0], k + 1), dtype=bool)
-                stop[:, :k] = aa == ord("*")
-                flat_stop = stop.reshape(-1)
-                flat = np.concatenate([aa, np.full((aa.shape[0], 1), ord("*"), np.uint8)], axis=1).reshape(-1)
-                ends = np.flatnonzero(flat_stop)
-                starts = np.concatenate([[0], ends[:-1] + 1])
-                ln = ends - starts
-                sel = ln >= min_len
-                st, ln = starts[sel], ln[sel]
-                if len(st) == 0:
-                    continue
-                tot = int(ln.sum()) + 2 * len(ln)
-                out = np.empty(tot, dtype=np.uint8)
-                o = np.zeros(len(ln), dtype=np.int64)
-                o[1:] = np.cumsum(ln[:-1] + 2)
-                # gather residues: index = start[i] + (pos - o[i]) for pos within the fragment
-                idx = np.repeat(st - o, ln + 2) + np.arange(tot)
-                body = np.repeat(np.arange(len(ln)), ln + 2)
-                within = np.arange(tot) - o[body]
-                is_nl = within == ln[body]
-                is_nul = within == ln[body] + 1
-                idx[is_nl | is_nul] = 0
-                out[:] = flat[idx]
-                out[is_nl] = 10
-                out[is_nul] = 0
-                datas.append(out)
-                lens.append((ln + 2).astype(np.uint32))
+    for strand in (r, _COMP[r[:, ::-1]]):
+        codes = _CODE[strand]
+        for f in range(3):
+            k = (codes.shape[1] - f) // 3
+            aa = _translate(codes[:, f:f + 3 * k])
+            # runs between stops, per row: append a stop column so runs never cross rows
+            stop = np.ones((aa.shape[0], k + 1), dtype=bool)
+            stop[:, :k] = aa == ord("*")
+            flat_stop = stop.reshape(-1)
+            flat = np.concatenate([aa, np.full((aa.shape[0], 1), ord("*"), np.uint8)], axis=1).reshape(-1)
+            ends = np.flatnonzero(flat_stop)
+            starts = np.concatenate([[0], ends[:-1] + 1])
+            ln = ends - starts
+            sel = ln >= min_len
+            st, ln = starts[sel], ln[sel]
+            if len(st) == 0:
+                continue
+            tot = int(ln.sum()) + 2 * len(ln)
+            out = np.empty(tot, dtype=np.uint8)
+            o = np.zeros(len(ln), dtype=np.int64)
+            o[1:] = np.cumsum(ln[:-1] + 2)
+            # gather residues: index = start[i] + (pos - o[i]) for pos within the fragment
+            idx = np.repeat(st - o, ln + 2) + np.arange(tot)
+            body = np.repeat(np.arange(len(ln)), ln + 2)
+            within = np.arange(tot) - o[body]
+            is_nl = within == ln[body]
+            is_nul = within == ln[body] + 1
+            idx[is_nl | is_nul] = 0
+            out[:] = flat[idx]
+            out[is_nl] = 10
+            out[is_nul] = 0
+            datas.append(out)
+            lens.append((ln + 2).astype(np.uint32))
+    data = np.concatenate(datas) if datas else np.zeros(0, np.uint8)
+    lens = np.concatenate(lens) if lens else np.zeros(0, np.uint32)
+    return data, lens
+
+
+_POOL_READS = None
+
+
+def _pool_chunk(args):
+    s, e, min_len = args
+    return _fragments_of_chunk(_POOL_READS[s:e], min_len)
+
+
+def protein_fragments(reads, min_len=45, chunk=500000, workers=1):
+    """Six-frame translation + split at stops; returns an in-memory amino-acid sequence DB.
+    workers > 1: the blocks of `chunk` reads are translated by forked worker processes (same result, same order)."""
+    global _POOL_READS
+    spans = [(s, min(len(reads), s + chunk), min_len) for s in range(0, len(reads), chunk)]
+    if workers > 1 and len(spans) > 1:
+        import multiprocessing as mp
+        _POOL_READS = reads
+        try:
+            with mp.get_context("fork").Pool(min(workers, len(spans))) as pool:
+                parts = pool.map(_pool_chunk, spans, chunksize=1)
+        finally:
+            _POOL_READS = None
+    else:
+        parts = [_fragments_of_chunk(reads[s:e], min_len) for s, e, _ in spans]
+    datas = [p[0] for p in parts]
+    lens = [p[1] for p in parts]
     data = np.concatenate(datas) if datas else np.zeros(0, np.uint8)
     lens = np.concatenate(lens) if lens else np.zeros(0, np.uint32)
     offsets = np.zeros(len(lens), dtype=np.uint64)
