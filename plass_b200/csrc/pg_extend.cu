@@ -488,11 +488,27 @@ __global__ void __launch_bounds__(256) extend_round_warp_kernel(const pg_seqdb d
 }
 
 // Amino acids, queries with at most 32 alignments: the WHOLE query in one warp -- every round of the reference's outer
-// loop (assembleresult.cpp:193-313) without leaving the kernel.  Pop / extend / park exactly as in
-// extend_round_warp_kernel; a parked hit stays in the registers of its lane, and when the queue has drained the
-// same warp re-scores the parked hits on the new contig (lane-parallel operand fetch, then the warp sums the
-// diagonals one after the other, as extend_rescore_kernel does) and starts the next round with them.  No per-round
-// state, work lists or host synchronisation.
+// loop (assembleresult.cpp:193-313) without leaving the kernel; one lane per alignment.
+//  * CompareResultByScore is a strict total order (score, alnLength, smaller dbKey; never all equal for two hits of one
+//    query), so popping the priority queue == repeatedly taking the maximum of the remaining elements.  The priority
+//    is packed into two 32-bit words (biased score | alnLength << 5 | rank of the dbKey among the query's hits) and
+//    a pop is two warp REDUX.MAX + one ballot instead of a heap operation.  Elements that fail the
+//    selectFragmentToExtend predicate would be popped and discarded by the reference: their lanes start dead.
+//  * The growing contig (a rope of segments) lives in shared memory while the query is processed and is written to
+//    the segment buffer once at the end.
+//  * A parked hit stays in the registers of its lane; when the queue has drained the same warp re-scores the
+//    parked hits on the new contig (lane-parallel operand fetch, then the warp sums the diagonals one after the
+//    other) and starts the next round with them.  No per-round state, work lists or host synchronisation.
+struct WarpRope {                 // shared-memory rope of one warp (amino acids: never reversed)
+    const char *base[EX_WARP_MAX_ALNS + 1];   // first byte of the segment
+    unsigned len[EX_WARP_MAX_ALNS + 1];
+    __device__ __forceinline__ unsigned char at(unsigned i) const {
+        int s = 0;
+        while (i >= len[s]) { i -= len[s]; s++; }
+        return (unsigned char) base[s][i];
+    }
+};
+
 __global__ void __launch_bounds__(256) extend_query_warp_kernel(const pg_seqdb db, const pg_aln *__restrict__ alns,
                                                                 const unsigned long long *__restrict__ alnStart, const unsigned *__restrict__ alnCount,
                                                                 const ExConst c, const unsigned *__restrict__ list, const unsigned *__restrict__ listCount,
@@ -501,26 +517,31 @@ __global__ void __launch_bounds__(256) extend_query_warp_kernel(const pg_seqdb d
                                                                 unsigned char *__restrict__ used) {
     __shared__ unsigned char sA2n[256];
     __shared__ signed char sMat[21 * 21];
+    __shared__ WarpRope sRope[8];
+    __shared__ ExSeg sSegs[8][EX_WARP_MAX_ALNS + 1];          // the same rope as (source, start, length) for the output
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sA2n[i] = c_ex_a2n[i];
     for (int i = threadIdx.x; i < 21 * 21; i += blockDim.x) sMat[i] = c_ex_mat[i];
     __syncthreads();
-    const unsigned lane = threadIdx.x & 31;
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    WarpRope &rope = sRope[w];
+    ExSeg *segs = sSegs[w];
     const unsigned nList = *listCount;
     const unsigned warpsTotal = gridDim.x * (blockDim.x >> 5);
-    for (unsigned li = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); li < nList; li += warpsTotal) {
+    for (unsigned li = blockIdx.x * (blockDim.x >> 5) + w; li < nList; li += warpsTotal) {
         const unsigned qi = list[li];
         const unsigned nAl = alnCount[qi];
         if (nAl > EX_WARP_MAX_ALNS) continue;                 // handled by the round-based heap path
         const unsigned long long a0 = alnStart[qi];
-        ExSeg *segs = segBuf + a0 + qi;
         const unsigned queryKey = db.keys[qi];
         unsigned querySeqLen = db.lens[qi] - 2;
-        if (lane == 0) { segs[0].src = qi; segs[0].start = 0; segs[0].len = querySeqLen; segs[0].rev = 0; }
+        if (lane == 0) {
+            rope.base[0] = db.data + db.offsets[qi]; rope.len[0] = querySeqLen;
+            segs[0].src = qi; segs[0].start = 0; segs[0].len = querySeqLen; segs[0].rev = 0;
+        }
         int ropeN = 1; unsigned ropeLen = querySeqLen;
         bool couldExtend = false;
         ExRes r; r.dbKey = 0; r.score = 0; r.seqId = 0; r.alnLength = 0; r.qStartPos = r.qEndPos = 0; r.qLen = 0; r.dbStartPos = r.dbEndPos = 0; r.dbLen = 0; r.rev = 0;
         bool alive = false;
-        unsigned myTargetId = 0, myTargetLen = 0;
         if (lane < nAl) {
             const pg_aln a = alns[a0 + lane];
             r.dbKey = a.target;
@@ -537,11 +558,15 @@ __global__ void __launch_bounds__(256) extend_query_warp_kernel(const pg_seqdb d
             r.seqId = (float) ((double) ids / ((double) alnLen + 0.5));
             r.score = (int) __fmul_rn(scorePerCol, 100.0f);
             alive = true;
-            // every lane resolves ITS target once (index, length): the pops below then need no dependent global loads
-            myTargetId = find_id(db.keys, (unsigned) db.n, r.dbKey);
-            myTargetLen = db.lens[myTargetId] - 2;
         }
-        const char *myTargetSeq = db.data + db.offsets[myTargetId];
+        // tie-break of the comparator: the smaller dbKey wins => rank = number of hits of this query with a larger key
+        unsigned keyRank = 0;
+        for (unsigned j = 0; j < nAl; j++) keyRank += (__shfl_sync(0xFFFFFFFFu, r.dbKey, j) > r.dbKey) ? 1u : 0u;
+        // the target of a hit is only touched if the hit can be selected at all: resolved lazily, once
+        // (its length is the alignment record's dbLen: rescorediagonal wrote db_len = sequence length)
+        const unsigned myTargetLen = r.dbLen;
+        unsigned myTargetId = 0xFFFFFFFFu;
+        const char *myTargetSeq = nullptr;
         while (true) {                                        // one iteration = one round of the reference's outer loop
             const bool entered = alive;                       // this element is in the queue of this round
             // selectFragmentToExtend's predicate (assembleresult.cpp:40-57): failing elements are popped and dropped
@@ -551,6 +576,13 @@ __global__ void __launch_bounds__(256) extend_query_warp_kernel(const pg_seqdb d
                 const bool leftStart = r.qStartPos == 0 && (r.qEndPos != (int) r.qLen - 1);
                 alive = (rightStart || leftStart) && notRightStartAndLeftStart && (r.dbKey != queryKey);
             }
+            if (alive && myTargetId == 0xFFFFFFFFu) {
+                myTargetId = find_id(db.keys, (unsigned) db.n, r.dbKey);
+                myTargetSeq = db.data + db.offsets[myTargetId];
+            }
+            // packed priority: (score, alnLength, smaller dbKey)
+            const unsigned prHi = (unsigned) r.score ^ 0x80000000u;
+            const unsigned prLo = (r.alnLength << 5) | keyRank;
             unsigned leftOff = 0, rightOff = 0;
             bool parked = false;
             int nPark = 0;
@@ -558,21 +590,13 @@ __global__ void __launch_bounds__(256) extend_query_warp_kernel(const pg_seqdb d
             while (true) {
                 const unsigned aliveMask = __ballot_sync(0xFFFFFFFFu, alive);
                 if (aliveMask == 0) break;
-                // arg-max by (score, alnLength, smaller dbKey)
-                int bs = alive ? r.score : INT_MIN; unsigned bl = r.alnLength, bk = r.dbKey; int bLane = alive ? (int) lane : -1;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const int os = __shfl_xor_sync(0xFFFFFFFFu, bs, o);
-                    const unsigned ol = __shfl_xor_sync(0xFFFFFFFFu, bl, o), ok = __shfl_xor_sync(0xFFFFFFFFu, bk, o);
-                    const int oLane = __shfl_xor_sync(0xFFFFFFFFu, bLane, o);
-                    const bool take = (oLane >= 0) && (bLane < 0 || os > bs || (os == bs && (ol > bl || (ol == bl && ok < bk))));
-                    if (take) { bs = os; bl = ol; bk = ok; bLane = oLane; }
-                }
-                const int wl = bLane;                                  // the same in every lane
+                const unsigned maxHi = __reduce_max_sync(0xFFFFFFFFu, alive ? prHi : 0u);
+                const bool top = alive && prHi == maxHi;
+                const unsigned maxLo = __reduce_max_sync(0xFFFFFFFFu, top ? prLo : 0u);
+                const int wl = __ffs(__ballot_sync(0xFFFFFFFFu, top && prLo == maxLo)) - 1;   // the same in every lane
                 if ((int) lane == wl) alive = false;                   // popped
                 const int bDbStart = __shfl_sync(0xFFFFFFFFu, r.dbStartPos, wl), bDbEnd = __shfl_sync(0xFFFFFFFFu, r.dbEndPos, wl);
                 const int bQStart = __shfl_sync(0xFFFFFFFFu, r.qStartPos, wl), bQEnd = __shfl_sync(0xFFFFFFFFu, r.qEndPos, wl);
-                const unsigned targetId = __shfl_sync(0xFFFFFFFFu, myTargetId, wl);
                 const unsigned targetSeqLen = __shfl_sync(0xFFFFFFFFu, myTargetLen, wl);
                 if (bDbStart == 0) {
                     if ((targetSeqLen - (unsigned) (bDbEnd + 1)) <= rightOff) continue;
@@ -584,10 +608,11 @@ __global__ void __launch_bounds__(256) extend_query_warp_kernel(const pg_seqdb d
                 if (dbStartPos == 0 && qEndPos == (querySeqLen - 1)) {            // right extension
                     if (rightOff > 0) { if ((int) lane == wl) parked = true; nPark++; continue; }
                     const unsigned fragLen = targetSeqLen - (dbEndPos + 1);
-                    if (lane == 0) {
-                        ExSeg g; g.src = targetId; g.len = fragLen; g.rev = 0; g.start = dbEndPos + 1;
+                    if ((int) lane == wl) {
+                        rope.base[ropeN] = myTargetSeq + dbEndPos + 1; rope.len[ropeN] = fragLen;
+                        ExSeg g; g.src = myTargetId; g.len = fragLen; g.rev = 0; g.start = dbEndPos + 1;
                         segs[ropeN] = g;
-                        used[targetId] = 1;
+                        used[myTargetId] = 1;
                     }
                     ropeN++; ropeLen += fragLen; rightOff += fragLen;
                 } else if (qStartPos == 0 && dbEndPos == (targetSeqLen - 1)) {    // left extension
@@ -596,25 +621,25 @@ __global__ void __launch_bounds__(256) extend_query_warp_kernel(const pg_seqdb d
                     if ((unsigned long long) ropeLen + fragLen >= (unsigned long long) c.maxSeqLen) {
                         // `break` (assembleresult.cpp:258-262): everything with a lower priority than this hit -- selectable
                         // or not -- is still in the reference's queue, and a non-empty queue ends the query (:287-288)
-                        const bool lower = entered && (int) lane != wl &&
-                                           (r.score < bs || (r.score == bs && (r.alnLength < bl || (r.alnLength == bl && r.dbKey > bk))));
+                        const bool lower = entered && (int) lane != wl && (prHi < maxHi || (prHi == maxHi && prLo < maxLo));
                         queueNotEmpty = __ballot_sync(0xFFFFFFFFu, lower) != 0;
                         break;
                     }
-                    if (lane == 0) {
-                        ExSeg g; g.src = targetId; g.len = fragLen; g.rev = 0; g.start = 0;
-                        for (int sI = ropeN; sI > 0; sI--) segs[sI] = segs[sI - 1];
+                    if ((int) lane == wl) {
+                        for (int sI = ropeN; sI > 0; sI--) { rope.base[sI] = rope.base[sI - 1]; rope.len[sI] = rope.len[sI - 1]; segs[sI] = segs[sI - 1]; }
+                        rope.base[0] = myTargetSeq; rope.len[0] = fragLen;
+                        ExSeg g; g.src = myTargetId; g.len = fragLen; g.rev = 0; g.start = 0;
                         segs[0] = g;
-                        used[targetId] = 1;
+                        used[myTargetId] = 1;
                     }
                     ropeN++; ropeLen += fragLen; leftOff += fragLen;
                 }
+                __syncwarp();                                 // the rope is edited by the popped lane, one edit at a time
             }
             if (leftOff > 0 || rightOff > 0) couldExtend = true;
-            __syncwarp();                                     // lane 0's rope segments are visible to the warp
+            __syncwarp();                                     // the rope in shared memory is visible to the warp
             if (queueNotEmpty || nPark == 0) break;
             // ---- re-score the parked hits on the new contig (assembleresult.cpp:293-307, updateAlignment :70-108)
-            Rope rope; rope.segs = segs; rope.data = db.data; rope.offsets = db.offsets; rope.n = ropeN; rope.len = ropeLen;
             int diag = 0;
             unsigned qOff = 0, tOff = 0, len = 0, first = 0, last = 0;
             bool valid = false;
@@ -637,15 +662,14 @@ __global__ void __launch_bounds__(256) extend_query_warp_kernel(const pg_seqdb d
                 const char *t = (const char *) __shfl_sync(0xFFFFFFFFu, (unsigned long long) myTargetSeq, j);
                 const unsigned qo = __shfl_sync(0xFFFFFFFFu, qOff, j), to = __shfl_sync(0xFFFFFFFFu, tOff, j);
                 const unsigned f = __shfl_sync(0xFFFFFFFFu, first, j), l = __shfl_sync(0xFFFFFFFFu, last, j);
-                long long sum = 0; int ids = 0;
+                int sum = 0, ids = 0;
                 // score over [first, last]; identities over [qS, qE) = columns [first, last)  (exclusive end of updateAlignment)
                 for (unsigned pos = f + lane; pos <= l; pos += 32) {
                     const unsigned char a = rope.at(qo + pos), b = (unsigned char) t[to + pos];
                     sum += sMat[sA2n[a] * c.alph + sA2n[b]];
                     if (pos < l) ids += (a == b) ? 1 : 0;
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o); ids += __shfl_xor_sync(0xFFFFFFFFu, ids, o); }
+                sum = __reduce_add_sync(0xFFFFFFFFu, sum); ids = __reduce_add_sync(0xFFFFFFFFu, ids);
                 if ((int) lane == j) { mySum = sum; myIds = ids; }
             }
             alive = false;
@@ -671,10 +695,15 @@ __global__ void __launch_bounds__(256) extend_query_warp_kernel(const pg_seqdb d
             }
             querySeqLen = ropeLen;                            // querySeqLen = query.length() (assembleresult.cpp:291)
         }
-        if (couldExtend && lane == 0) {
-            extended[qi] = 1;
-            outLen[qi] = ropeLen + 2;
-            segCount[qi] = (unsigned) ropeN;
+        if (couldExtend) {
+            ExSeg *gsegs = segBuf + a0 + qi;                  // capacity nAl + 1
+            if ((int) lane < ropeN) gsegs[lane] = segs[lane];
+            if (lane == 0) {
+                if (ropeN > 32) gsegs[32] = segs[32];
+                extended[qi] = 1;
+                outLen[qi] = ropeLen + 2;
+                segCount[qi] = (unsigned) ropeN;
+            }
         }
         __syncwarp();
     }

@@ -257,13 +257,58 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
         // all k-mer windows, compacted in position order
         int cnt = 0;
         const int nWin = L - (KT > 0 ? KT : c.k) + 1;
-        for (int p0 = 0; p0 < nWin; p0 += 32) {
-            const int pos = p0 + lane;
-            Cand cd;
-            const bool ok = (pos < nWin) && make_kmer_t<KT, NTM>(codes, pos, L, c, cd);
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
-            if (ok) cand[cnt + __popc(m & ltMask)] = pack_cand(cd);
-            cnt += __popc(m);
+        if constexpr (KT > 0 && NTM == 0 && (KT & 1) == 0) {
+            // amino acids, even compile-time k: Indexer::int2index (Indexer.h:20-83) is sum(code[pos+j] * base^j).  The two
+            // halves of a window are the half-sums of positions pos and pos + k/2, so every position computes ONE k/2-term
+            // sum in 32-bit arithmetic (base^(k/2) <= 20^7 < 2^32) and a window is half[pos] + half[pos+k/2] * base^(k/2):
+            // ~k/2 narrow multiplies per window instead of k wide ones.  X windows (Sequence::kmerContainsX) are found
+            // from a bit mask of the X positions.  Both arrays alias the output staging area, which is not in use yet.
+            constexpr int H = KT / 2;
+            unsigned *half = reinterpret_cast<unsigned *>(outRecs);
+            unsigned *xmask = half + CODES;
+            unsigned baseH = 1;
+#pragma unroll
+            for (int j = 0; j < H; j++) baseH *= c.base;
+            for (int p0 = 0; p0 < L; p0 += 32) {
+                const int pos = p0 + lane;
+                const bool isX = pos < L && codes[pos] == (unsigned char) c.xCode;
+                const unsigned xm = __ballot_sync(0xFFFFFFFFu, isX);
+                if (lane == 0) xmask[p0 >> 5] = xm;
+                if (pos + H <= L) {
+                    unsigned hs = 0, pw = 1;
+#pragma unroll
+                    for (int j = 0; j < H; j++) { hs += (unsigned) codes[pos + j] * pw; pw *= c.base; }
+                    half[pos] = hs;
+                }
+            }
+            if (lane == 0) xmask[(L + 31) >> 5] = 0;
+            __syncwarp();
+            for (int p0 = 0; p0 < nWin; p0 += 32) {
+                const int pos = p0 + lane;
+                bool ok = pos < nWin;
+                Cand cd; cd.kmer = 0; cd.score = 0; cd.pos = (unsigned) pos;
+                if (ok) {
+                    const unsigned long long xb = ((unsigned long long) xmask[pos >> 5] | ((unsigned long long) xmask[(pos >> 5) + 1] << 32)) >> (pos & 31);
+                    ok = (xb & ((1ULL << KT) - 1ULL)) == 0;
+                }
+                if (ok) {
+                    cd.kmer = (unsigned long long) half[pos] + (unsigned long long) half[pos + H] * (unsigned long long) baseH;
+                    cd.score = (unsigned) (xxh64_u64(cd.kmer, c.seed) & 0xFFFFULL);
+                }
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+                if (ok) cand[cnt + __popc(m & ltMask)] = pack_cand(cd);
+                cnt += __popc(m);
+            }
+            __syncwarp();                                     // half / xmask are dead from here on: the staging area is reused
+        } else {
+            for (int p0 = 0; p0 < nWin; p0 += 32) {
+                const int pos = p0 + lane;
+                Cand cd;
+                const bool ok = (pos < nWin) && make_kmer_t<KT, NTM>(codes, pos, L, c, cd);
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+                if (ok) cand[cnt + __popc(m & ltMask)] = pack_cand(cd);
+                cnt += __popc(m);
+            }
         }
         // threshold of the bottom-m sketch (kmermatcher.cpp:223-238)
         const unsigned long long want = (unsigned long long) ((float) (c.kmersPerSeq - 1) + (c.scale * (float) L));
@@ -782,9 +827,9 @@ __global__ void __launch_bounds__(GROUP_THREADS) group_kernel(const Rec *__restr
 // table raise `overflow` and the caller falls back to the full sort + group_kernel.
 // ------------------------------------------------------------------------------------------------
 constexpr int HG_THREADS = 128;
-constexpr int HG_ITEMS = 12;
-constexpr int HG_MAX_BUCKET = HG_THREADS * HG_ITEMS;   // 1536 records
-constexpr int HG_TABLE = 2048;                         // slots (load factor <= 0.75)
+constexpr int HG_ITEMS_SMALL = 6, HG_TABLE_SMALL = 1024;    // buckets of up to 768 records: 20 KB of shared memory, 8 CTAs per SM
+constexpr int HG_ITEMS_BIG = 12, HG_TABLE_BIG = 2048;       // the rare larger ones (deferred to a second launch)
+constexpr int HG_MAX_BUCKET = HG_THREADS * HG_ITEMS_BIG;    // 1536 records
 
 __global__ void bucket_bounds_kernel(const Rec *__restrict__ in, unsigned long long n, unsigned long long hashMask, unsigned bucketMask,
                                      unsigned long long *__restrict__ start, unsigned long long *__restrict__ end,
@@ -842,44 +887,68 @@ __device__ __forceinline__ bool make_pair_record(const Rec &r, unsigned repId, i
     return keep;
 }
 
+// MODE 0: sweep over all buckets, handle those of up to HG_THREADS * ITEMS records and queue the larger ones in bigList;
+// MODE 1: process bigList.
+template <int TABLE, int ITEMS, int MODE>
 __global__ void __launch_bounds__(HG_THREADS) hash_group_kernel(const Rec *__restrict__ in, const unsigned long long *__restrict__ start,
                                                                 const unsigned long long *__restrict__ end, unsigned nBuckets,
                                                                 unsigned long long hashMask, const unsigned long long *__restrict__ minKmer,
                                                                 const KmConst c, Rec *__restrict__ out, unsigned long long *__restrict__ outCount,
+                                                                unsigned *__restrict__ bigList, unsigned *__restrict__ bigCount,
                                                                 unsigned *__restrict__ overflow) {
-    __shared__ unsigned long long sKey[HG_TABLE];
-    __shared__ unsigned long long sMin[HG_TABLE];
-    __shared__ unsigned sCnt[HG_TABLE];
-    __shared__ unsigned sWarpOut[HG_THREADS / 32];
+    __shared__ unsigned long long sKey[TABLE];
+    __shared__ unsigned long long sMin[TABLE];
+    __shared__ unsigned sCnt[TABLE];
+    __shared__ unsigned sItemWarp[ITEMS][HG_THREADS / 32];   // pairs emitted per (item round, warp), then their exclusive offsets
     __shared__ unsigned long long sOutBase;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned ltMask = (1u << lane) - 1u;
     const unsigned long long firstKmer = *minKmer;
-    for (unsigned b = blockIdx.x; b < nBuckets; b += gridDim.x) {
+    const unsigned nWork = MODE == 0 ? nBuckets : *bigCount;
+    for (unsigned wi = blockIdx.x; wi < nWork; wi += gridDim.x) {
+        const unsigned b = MODE == 0 ? wi : bigList[wi];
         const unsigned long long s0 = start[b], e0 = end[b];
         if (e0 <= s0) continue;
         const unsigned count = (unsigned) (e0 - s0);
-        if (count > HG_MAX_BUCKET) { if (tid == 0) atomicExch(overflow, 1u); continue; }
-        for (int i = tid; i < HG_TABLE; i += HG_THREADS) { sKey[i] = ~0ULL; sMin[i] = ~0ULL; sCnt[i] = 0; }
+        if (count > (unsigned) (HG_THREADS * ITEMS)) {
+            if (tid == 0) {
+                if (MODE == 0 && count <= (unsigned) HG_MAX_BUCKET) bigList[atomicAdd(bigCount, 1u)] = b;
+                else atomicExch(overflow, 1u);
+            }
+            continue;
+        }
+        // table sized to the bucket (load factor <= 0.5, <= 0.75 for the very largest): clearing it is most of the
+        // shared-memory traffic of an average bucket
+        unsigned tsize = 64;
+        while (tsize < 2 * count && tsize < (unsigned) TABLE) tsize <<= 1;
+        const unsigned tmask = tsize - 1;
+        for (unsigned i = tid; i < tsize; i += HG_THREADS) { sKey[i] = ~0ULL; sMin[i] = ~0ULL; sCnt[i] = 0; }
         __syncthreads();
-        Rec rec[HG_ITEMS];
-        unsigned slotOf[HG_ITEMS];
+        Rec rec[ITEMS];
+        unsigned slotOf[ITEMS];
 #pragma unroll
-        for (int it = 0; it < HG_ITEMS; it++) {
+        for (int it = 0; it < ITEMS; it++) {
             const unsigned i = it * HG_THREADS + tid;
             slotOf[it] = 0xFFFFFFFFu;
             if (i < count) {
                 const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(in + s0) + i);
                 rec[it].w0 = ((unsigned long long) raw.y << 32) | raw.x;
                 rec[it].w1 = ((unsigned long long) raw.w << 32) | raw.z;
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            const unsigned i = it * HG_THREADS + tid;
+            if (i < count) {
                 const unsigned long long k = rec[it].w0 & hashMask;
                 // aa: the reference drops k-mer == SIZE_T_MAX, its own array sentinel (kmermatcher.cpp:475); ~0 is also the
                 // empty marker of the table.  nt keys have 63 bits and never collide with it.
                 if (!(hashMask == ~0ULL && k == ~0ULL)) {
-                    unsigned slot = (unsigned) (mix64(k) >> 40) & (HG_TABLE - 1);
+                    unsigned slot = (unsigned) (mix64(k) >> 40) & tmask;
                     while (true) {
                         const unsigned long long old = atomicCAS(&sKey[slot], ~0ULL, k);
                         if (old == ~0ULL || old == k) break;
-                        slot = (slot + 1) & (HG_TABLE - 1);
+                        slot = (slot + 1) & tmask;
                     }
                     atomicMin(&sMin[slot], hg_pack(rec[it]));
                     atomicAdd(&sCnt[slot], 1u);
@@ -891,36 +960,44 @@ __global__ void __launch_bounds__(HG_THREADS) hash_group_kernel(const Rec *__res
         // sweep 1: which members produce a pair (the record itself is rebuilt in sweep 2 to keep registers low)
         unsigned keepMask = 0;
 #pragma unroll
-        for (int it = 0; it < HG_ITEMS; it++) {
+        for (int it = 0; it < ITEMS; it++) {
+            bool keep = false;
             if (slotOf[it] != 0xFFFFFFFFu && sCnt[slotOf[it]] >= 2) {
                 const unsigned long long m = sMin[slotOf[it]];
                 Rec tmp;
-                if (make_pair_record(rec[it], (unsigned) ((m >> 17) & 0xFFFFFFFFULL), (int) (0x7FFFULL ^ (m >> 49)), (int) (short) ((m >> 1) & 0xFFFFULL),
-                                     (unsigned) (m & 1ULL), (rec[it].w0 & hashMask) == firstKmer, c, tmp)) keepMask |= 1u << it;
+                keep = make_pair_record(rec[it], (unsigned) ((m >> 17) & 0xFFFFFFFFULL), (int) (0x7FFFULL ^ (m >> 49)), (int) (short) ((m >> 1) & 0xFFFFULL),
+                                        (unsigned) (m & 1ULL), (rec[it].w0 & hashMask) == firstKmer, c, tmp);
             }
+            if (keep) keepMask |= 1u << it;
+            const unsigned bm = __ballot_sync(0xFFFFFFFFu, keep);
+            if (lane == 0) sItemWarp[it][w] = __popc(bm);
         }
-        const unsigned mine = __popc(keepMask);
-        unsigned v = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= o) v += nb; }
-        if (lane == 31) sWarpOut[w] = v;
         __syncthreads();
-        unsigned woff = 0, total = 0;
-        for (int ww = 0; ww < HG_THREADS / 32; ww++) { if (ww < w) woff += sWarpOut[ww]; total += sWarpOut[ww]; }
-        if (tid == 0) sOutBase = total ? atomicAdd(outCount, (unsigned long long) total) : 0ULL;
-        __syncthreads();
-        unsigned long long ob = sOutBase + woff + v - mine;
+        // output positions in (item round, warp, lane) order: the 32 records a warp writes per round are contiguous
+        if (tid == 0) {
+            unsigned run = 0;
 #pragma unroll
-        for (int it = 0; it < HG_ITEMS; it++)
-            if (keepMask & (1u << it)) {
+            for (int it = 0; it < ITEMS; it++)
+#pragma unroll
+                for (int ww = 0; ww < HG_THREADS / 32; ww++) { const unsigned v = sItemWarp[it][ww]; sItemWarp[it][ww] = run; run += v; }
+            sOutBase = run ? atomicAdd(outCount, (unsigned long long) run) : 0ULL;
+        }
+        __syncthreads();
+        const unsigned long long ob = sOutBase;
+#pragma unroll
+        for (int it = 0; it < ITEMS; it++) {
+            const bool keep = (keepMask >> it) & 1u;
+            const unsigned bm = __ballot_sync(0xFFFFFFFFu, keep);
+            if (keep) {
                 const unsigned long long m = sMin[slotOf[it]];
                 Rec o;
                 make_pair_record(rec[it], (unsigned) ((m >> 17) & 0xFFFFFFFFULL), (int) (0x7FFFULL ^ (m >> 49)), (int) (short) ((m >> 1) & 0xFFFFULL),
                                  (unsigned) (m & 1ULL), (rec[it].w0 & hashMask) == firstKmer, c, o);
                 uint4 raw;
                 raw.x = (unsigned) o.w0; raw.y = (unsigned) (o.w0 >> 32); raw.z = (unsigned) o.w1; raw.w = (unsigned) (o.w1 >> 32);
-                reinterpret_cast<uint4 *>(out)[ob++] = raw;
+                reinterpret_cast<uint4 *>(out)[ob + sItemWarp[it][w] + __popc(bm & ltMask)] = raw;
             }
+        }
         __syncthreads();
     }
 }
@@ -1489,8 +1566,16 @@ static int km_group_bucketed(Context *ctx, const KmConst &c, uint64_t nRecords, 
     Rec *outBuf = (sorted == ctx->recA.as<Rec>()) ? ctx->recB.as<Rec>() : ctx->recA.as<Rec>();
     unsigned long long *d_cnt = ctx->small.as<unsigned long long>() + 2;
     PG_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
-    hash_group_kernel<<<std::min<unsigned>(nBuckets, NUM_SMS * 64), HG_THREADS, 0, s>>>(sorted, d_start, d_end, nBuckets, hashMask, d_min, c, outBuf, d_cnt, d_over);
-    ctx->launches += 2;
+    // buckets above the small instance's capacity are listed (after the d_end array's alignment slack: reuse blockCounts)
+    PG_TRY(ctx->blockCounts.reserve(sizeof(unsigned) * ((size_t) nBuckets + 4)));
+    unsigned *d_bigList = ctx->blockCounts.as<unsigned>() + 4;
+    unsigned *d_bigCnt = ctx->blockCounts.as<unsigned>();
+    PG_CUDA(cudaMemsetAsync(d_bigCnt, 0, sizeof(unsigned), s));
+    hash_group_kernel<HG_TABLE_SMALL, HG_ITEMS_SMALL, 0><<<std::min<unsigned>(nBuckets, NUM_SMS * 64), HG_THREADS, 0, s>>>(
+        sorted, d_start, d_end, nBuckets, hashMask, d_min, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_over);
+    hash_group_kernel<HG_TABLE_BIG, HG_ITEMS_BIG, 1><<<NUM_SMS * 4, HG_THREADS, 0, s>>>(
+        sorted, d_start, d_end, nBuckets, hashMask, d_min, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_over);
+    ctx->launches += 3;
     cudaEventRecord(ctx->ev[EV_GROUP_END], s);
     unsigned long long h = 0; unsigned over = 0;
     PG_CUDA(cudaMemcpyAsync(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, s));

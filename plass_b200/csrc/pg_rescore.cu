@@ -128,6 +128,52 @@ __device__ DiagAln align_by_diagonal(const QView &q, const char *t, unsigned tLe
     return r;
 }
 
+// The same for ONE THREAD and a forward query: used for batches of short sequences (amino-acid fragments), where a
+// warp striding ~50 columns is mostly idle.  Both sequences are streamed as aligned 32-bit words (funnel-shifted
+// to the byte offset), four columns per pair of loads.  Integer sums: the result equals the warp version's.
+__device__ DiagAln align_by_diagonal_thread(const char *qs, unsigned qLen, const char *t, unsigned tLen, int diagonal, int alph,
+                                            const unsigned char *sA2n, const signed char *sMat) {
+    const unsigned dist = (unsigned) abs(diagonal);
+    DiagAln r; r.start = -1; r.end = -1; r.score = 0; r.diagLen = 0; r.dist = dist; r.diagonal = diagonal; r.idCnt = 0;
+    unsigned qOff, tOff, len;
+    if (diagonal >= 0 && dist < qLen) { len = min(tLen, qLen - dist); qOff = dist; tOff = 0; }
+    else if (diagonal < 0 && dist < tLen) { len = min(tLen - dist, qLen); qOff = 0; tOff = dist; }
+    else return r;
+    r.diagLen = len;
+    if (len == 0) return r;
+    const unsigned char q0 = (unsigned char) qs[qOff], t0 = (unsigned char) t[tOff];
+    const unsigned char qE = (unsigned char) qs[qOff + len - 1], tE = (unsigned char) t[tOff + len - 1];
+    const unsigned first = (q0 == '*' || t0 == '*') ? 1u : 0u;
+    unsigned last = len - 1;
+    if (last > 0 && (qE == '*' || tE == '*')) last--;
+    int sum = 0, ids = 0;
+    if (last >= first) {
+        const unsigned n = last - first + 1;
+        const unsigned long long qa0 = (unsigned long long) (qs + qOff + first), ta0 = (unsigned long long) (t + tOff + first);
+        const unsigned *qw = reinterpret_cast<const unsigned *>(qa0 & ~3ULL), *tw = reinterpret_cast<const unsigned *>(ta0 & ~3ULL);
+        const unsigned qsh = (unsigned) (qa0 & 3ULL) * 8u, tsh = (unsigned) (ta0 & 3ULL) * 8u;
+        unsigned qPrev = __ldg(qw), tPrev = __ldg(tw);
+        for (unsigned i = 0; i < n; i += 4) {
+            const unsigned qNext = __ldg(qw + (i >> 2) + 1), tNext = __ldg(tw + (i >> 2) + 1);   // at most 7 bytes past the column range: inside the DB's tail slack
+            const unsigned q4 = __funnelshift_r(qPrev, qNext, qsh), t4 = __funnelshift_r(tPrev, tNext, tsh);
+            qPrev = qNext; tPrev = tNext;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                if (i + b < n) {
+                    const unsigned qc = (q4 >> (8 * b)) & 0xFFu, tc = (t4 >> (8 * b)) & 0xFFu;
+                    sum += sMat[sA2n[qc] * alph + sA2n[tc]];
+                    ids += ((qc & 0xDFu) == (tc & 0xDFu)) ? 1 : 0;
+                }
+            }
+        }
+    }
+    if (sum < 0) sum = 0;
+    r.start = (int) first; r.end = (int) last; r.score = (unsigned) sum; r.idCnt = ids;
+    return r;
+}
+
+constexpr int RS_THREAD_MAX_LEN = 512;   // batches whose sequences are all at most this long are scored one item per thread
+
 // items [0, nHits): prefilter hit j;  items [nHits, nHits + n): the "key\t0\t0" self line of query (item - nHits).
 // A warp takes 32 items: every lane first fetches the operands of ITS item (so the dependent loads
 // hit -> key -> offset overlap across the lanes), the warp then scores the 32 diagonals one after the other with
@@ -172,6 +218,27 @@ __global__ void __launch_bounds__(256) rescore_kernel(const pg_seqdb db, const p
         // ---- phase 2: the warp scores the items one by one
         DiagAln mine; mine.start = -1; mine.end = -1; mine.score = 0; mine.diagLen = 0; mine.dist = 0; mine.diagonal = 0; mine.idCnt = 0;
         unsigned todo = __ballot_sync(0xFFFFFFFFu, scoreIt);
+        // short forward sequences (amino-acid fragments): every lane scores its own item
+        const bool threadPath = !c.nt && __all_sync(0xFFFFFFFFu, !scoreIt || (qLen <= RS_THREAD_MAX_LEN && dbLen <= RS_THREAD_MAX_LEN));
+        if (threadPath) {
+            todo = 0;
+            if (scoreIt) {
+                // computeUngappedAlignment: every diagonal congruent to diag16 modulo 65536, the strictly best one wins
+                const unsigned tl = (unsigned) dbLen;
+                for (unsigned d = 1; d <= 1 + tl / 32768; d++) {
+                    const int real = (int) (0u - d * 65536u + diag16);
+                    if (!(real < 0 && (unsigned) (-real) < tl) && !(real >= 0 && (unsigned) real < (unsigned) qLen)) continue;
+                    const DiagAln tmp = align_by_diagonal_thread(qPtr, (unsigned) qLen, tPtr, tl, real, c.alph, sA2n, sMat);
+                    if (tmp.score > mine.score) mine = tmp;
+                }
+                for (unsigned d = 0; d <= (unsigned) qLen / 65536; d++) {
+                    const int real = (int) (d * 65536u + diag16);
+                    if (!(real < 0 && (unsigned) (-real) < tl) && !(real >= 0 && (unsigned) real < (unsigned) qLen)) continue;
+                    const DiagAln tmp = align_by_diagonal_thread(qPtr, (unsigned) qLen, tPtr, tl, real, c.alph, sA2n, sMat);
+                    if (tmp.score > mine.score) mine = tmp;
+                }
+            }
+        }
         while (todo) {
             const int j = __ffs(todo) - 1;
             todo &= todo - 1;
