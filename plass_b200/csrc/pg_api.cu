@@ -165,6 +165,7 @@ static void begin_call(Context *ctx) {
     cudaSetDevice(ctx->device);
     ctx->tExtract = ctx->tGroup = ctx->tReduce = ctx->rsRan = ctx->exRan = false;
     ctx->launches = 0;
+    ctx->rsOut = nullptr; ctx->rsCnt = nullptr; ctx->rsOff = nullptr;
     memset(&ctx->timings, 0, sizeof(ctx->timings));
     cudaEventRecord(ctx->ev[EV_TOTAL_BEGIN], ctx->stream);
 }

@@ -188,6 +188,20 @@ __global__ void aln_ranges_kernel(const pg_seqdb db, const pg_aln *__restrict__ 
     if (k - j > EX_WARP_MAX_ALNS) atomicAdd(activeCount + 2, 1u);  // queries that need the heap path even for amino acids
 }
 
+// the same from the per-sequence alignment counts rescorediagonal left behind (fused iteration): only the work lists
+__global__ void active_from_counts_kernel(const unsigned *__restrict__ alnCount, unsigned long long n,
+                                          unsigned *__restrict__ activeList, unsigned *__restrict__ activeCount) {
+    const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned c = i < n ? alnCount[i] : 0u;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, c >= 2), big = __ballot_sync(0xFFFFFFFFu, c > EX_WARP_MAX_ALNS);
+    unsigned base = 0;
+    if (lane == 0 && m) base = atomicAdd(activeCount, (unsigned) __popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (c >= 2) activeList[base + __popc(m & ((1u << lane) - 1u))] = (unsigned) i;
+    if (lane == 0 && big) atomicAdd(activeCount + 2, (unsigned) __popc(big));
+}
+
 __global__ void init_out_kernel(const pg_seqdb db, unsigned *__restrict__ outLen) {
     const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < db.n) outLen[i] = db.lens[i];
@@ -821,6 +835,9 @@ __global__ void keep_kernel(unsigned long long n, int keepTarget, const unsigned
     if (!k) outLen[i] = 0;
 }
 
+// Output DB: a warp takes 32 consecutive sequences.  Every lane fetches the metadata of ITS sequence (coalesced loads,
+// the dependent chain keep -> offset -> length overlaps across the lanes) and writes its index entry; the warp then
+// copies the kept sequences one after the other: the original bytes, or the rope segments of a new contig.
 __global__ void __launch_bounds__(256) materialize_kernel(const pg_seqdb db, const unsigned long long *__restrict__ alnStart,
                                                           const ExSeg *__restrict__ segBuf, const unsigned *__restrict__ segCount,
                                                           const unsigned *__restrict__ outLen, const unsigned long long *__restrict__ outOff,
@@ -831,28 +848,41 @@ __global__ void __launch_bounds__(256) materialize_kernel(const pg_seqdb db, con
                                                           unsigned char *__restrict__ outExtended) {
     const unsigned lane = threadIdx.x & 31;
     const unsigned long long warpsTotal = (unsigned long long) gridDim.x * (blockDim.x >> 5);
-    for (unsigned long long qi = (unsigned long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); qi < db.n; qi += warpsTotal) {
-        if (!keep[qi]) continue;
-        const unsigned long long o = outOff[qi];
-        const unsigned len = outLen[qi];
-        const unsigned long long slot = keepIdx[qi];
-        char *dst = outData + o;
-        if (lane == 0) { outOffsets[slot] = o; outLens[slot] = len; outKeys[slot] = db.keys[qi]; outExtended[slot] = extended[qi]; }
-        const unsigned nseg = segCount[qi];
-        if (nseg == 0) {
-            const char *src = db.data + db.offsets[qi];
-            for (unsigned i = lane; i < len; i += 32) dst[i] = src[i];
-        } else {
-            const ExSeg *segs = segBuf + alnStart[qi] + qi;
-            unsigned w = 0;
-            for (unsigned s = 0; s < nseg; s++) {
-                const ExSeg g = segs[s];
-                const char *src = db.data + db.offsets[g.src];
-                for (unsigned i = lane; i < g.len; i += 32)
-                    dst[w + i] = g.rev ? (char) c_ex_revN[(unsigned char) src[g.start + g.len - 1 - i]] : src[g.start + i];
-                w += g.len;
+    const unsigned long long nBatches = (db.n + 31) / 32;
+    for (unsigned long long batch = (unsigned long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); batch < nBatches; batch += warpsTotal) {
+        const unsigned long long qi = batch * 32 + lane;
+        const bool live = qi < db.n && keep[qi] != 0;
+        unsigned long long o = 0; unsigned len = 0, nseg = 0;
+        const char *src = nullptr; const ExSeg *segs = nullptr;
+        if (live) {
+            o = outOff[qi]; len = outLen[qi]; nseg = segCount[qi];
+            const unsigned long long slot = keepIdx[qi];
+            outOffsets[slot] = o; outLens[slot] = len; outKeys[slot] = db.keys[qi]; outExtended[slot] = extended[qi];
+            if (nseg == 0) src = db.data + db.offsets[qi];
+            else segs = segBuf + alnStart[qi] + qi;
+        }
+        unsigned todo = __ballot_sync(0xFFFFFFFFu, live);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            char *dst = outData + __shfl_sync(0xFFFFFFFFu, o, j);
+            const unsigned ns = __shfl_sync(0xFFFFFFFFu, nseg, j);
+            if (ns == 0) {
+                const char *sp = (const char *) __shfl_sync(0xFFFFFFFFu, (unsigned long long) src, j);
+                const unsigned l = __shfl_sync(0xFFFFFFFFu, len, j);
+                for (unsigned i = lane; i < l; i += 32) dst[i] = sp[i];
+            } else {
+                const ExSeg *sg = (const ExSeg *) __shfl_sync(0xFFFFFFFFu, (unsigned long long) segs, j);
+                unsigned w = 0;
+                for (unsigned s = 0; s < ns; s++) {
+                    const ExSeg g = sg[s];
+                    const char *sp = db.data + db.offsets[g.src];
+                    for (unsigned i = lane; i < g.len; i += 32)
+                        dst[w + i] = g.rev ? (char) c_ex_revN[(unsigned char) sp[g.start + g.len - 1 - i]] : sp[g.start + i];
+                    w += g.len;
+                }
+                if (lane == 0) { dst[w] = '\n'; dst[w + 1] = '\0'; }
             }
-            if (lane == 0) { dst[w] = '\n'; dst[w + 1] = '\0'; }
         }
     }
 }
@@ -943,7 +973,11 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     PG_CUDA(cudaMemsetAsync(d_cnt, 0, 24, s));
     lap("setup/reserve/memset");
     init_out_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(*db, outLen);
-    if (nAlns) aln_ranges_kernel<<<(unsigned) ((nAlns + 255) / 256), 256, 0, s>>>(*db, d_alns, nAlns, alnStart, alnCount, listA, d_listCnt);
+    if (nAlns && d_alns == ctx->rsOut && ctx->rsCnt) {
+        alnStart = const_cast<unsigned long long *>(ctx->rsOff);      // read-only from here on
+        alnCount = const_cast<unsigned *>(ctx->rsCnt);
+        active_from_counts_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(alnCount, n, listA, d_listCnt);
+    } else if (nAlns) aln_ranges_kernel<<<(unsigned) ((nAlns + 255) / 256), 256, 0, s>>>(*db, d_alns, nAlns, alnStart, alnCount, listA, d_listCnt);
     ctx->launches += 2;
     unsigned hCnt[3] = {0, 0, 0};
     PG_TRY(read_back(ctx, hCnt, d_listCnt, 3 * sizeof(unsigned)));

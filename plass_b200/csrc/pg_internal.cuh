@@ -30,6 +30,11 @@ struct pg_context {
     uint64_t launches = 0;
     pg_timings timings;
     uint64_t nHits = 0, nAlns = 0;
+    // rescorediagonal leaves, per sequence index, the number of alignment lines and their first position in its output;
+    // the extension of the same call reuses them instead of re-deriving the ranges from the alignment array
+    const pg_aln *rsOut = nullptr;
+    const unsigned *rsCnt = nullptr;
+    const unsigned long long *rsOff = nullptr;
     // multi-GPU: this rank owns the queries / representatives with key in [ownLo, ownHi)
     unsigned ownLo = 0, ownHi = 0xFFFFFFFFu;
     pg::Rec *shardPairs = nullptr;

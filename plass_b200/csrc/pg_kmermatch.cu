@@ -1291,6 +1291,226 @@ __global__ void __launch_bounds__(256) reduce_rep_warp_kernel(const Rec *__restr
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// reduce, representatives with more than 128 pairs: aggregate before sorting.  A representative with c pairs has only
+// D ~ c/8 distinct (target, diagonal) combinations (a pair per shared k-mer), so the pairs are first counted in a
+// shared-memory hash table keyed by (target, diagonal) -> (count, reverse-strand count), the D occupied slots are
+// compacted and only those are sorted by (target, diagonal) in registers.  The scan of writeKmerMatcherResult then runs
+// over (diagonal, count) entries: a diagonal's last update of the `>=` rule happens at its last record, when its count
+// is complete, so the aggregated scan selects the same diagonal, strand majority and score.
+//   reduce_rep_hashwarp_kernel   one warp per representative of midList (129 .. RH_WARP_MAX pairs)
+//   reduce_rep_hashcta_kernel    one CTA per representative of bigList (more); representatives whose table or sorted
+//                                list overflows go to hugeList and are done by reduce_rep_block_kernel (full sort)
+// ------------------------------------------------------------------------------------------------
+constexpr int RH_WARP_MAX = SEG_WARP_MAX;       // pairs per representative in the warp kernel (table of 2 * that)
+constexpr int RH_WARP_TABLE = 2 * RH_WARP_MAX;
+constexpr int RH_WARPS = 3;                     // warps per CTA of the warp kernel (39 KB of static shared memory)
+constexpr int RH_CTA_TABLE = 2048;              // only representatives with <= RH_SORT_MAX distinct entries finish here anyway
+constexpr int RH_SORT_MAX = 512;                // aggregated entries one warp sorts in registers
+constexpr int RH_PROBE_MAX = 64;
+
+// entry = target << 32 | diagonal << 16 | table slot
+__device__ __forceinline__ void agg_step(unsigned d, unsigned cnt, unsigned rv, ScanState &st) {
+    st.prevDiag = d; st.diagCnt = cnt; st.revCnt = rv;
+    if (cnt >= st.maxDiag) { st.best = d; st.maxDiag = cnt; st.bestRev = (2u * rv > cnt) ? 1u : 0u; }
+    st.top += cnt;
+}
+
+// insert pairs in[s0 + first], in[s0 + first + step], ... into the table; returns false if a probe sequence gave up
+__device__ __forceinline__ bool rh_insert(const Rec *__restrict__ in, unsigned long long s0, unsigned count, unsigned first, unsigned step,
+                                          unsigned long long *sKey, unsigned *sCnt, unsigned tmask) {
+    bool okAll = true;
+    for (unsigned i = first; i < count; i += step) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(in + s0) + i);
+        const unsigned long long key = ((unsigned long long) raw.x << 16) | (unsigned long long) (raw.z & 0xFFFFu);   // target, biased diagonal
+        const unsigned strand = (raw.z >> 16) & 1u;
+        unsigned slot = (unsigned) (mix64(key) >> 40) & tmask;
+        bool placed = false;
+        for (int probe = 0; probe < RH_PROBE_MAX; probe++) {
+            const unsigned long long old = atomicCAS(&sKey[slot], ~0ULL, key);
+            if (old == ~0ULL || old == key) { placed = true; break; }
+            slot = (slot + 1) & tmask;
+        }
+        if (placed) atomicAdd(&sCnt[slot], 1u + (strand << 16));
+        else okAll = false;
+    }
+    return okAll;
+}
+
+// One warp: sorts the D <= RH_SORT_MAX entries of ent[] (shared memory), scans the (rep, target) runs, writes the hit
+// lines of `rep` to tmpHits[s0 ...] and hitCount[rep]; continues the last run into the following representatives.
+__device__ void rh_sort_scan_emit(const Rec *__restrict__ in, unsigned long long n, const unsigned long long *__restrict__ end,
+                                  const unsigned *__restrict__ minTarget, unsigned rep, unsigned long long s0, unsigned long long e0,
+                                  unsigned long long *ent, unsigned D, const unsigned *sCnt, unsigned *stage /* >= 256 words */,
+                                  pg_hit *__restrict__ tmpHits, unsigned *__restrict__ hitCount, unsigned *overflow) {
+    const unsigned lane = threadIdx.x & 31;
+    int n2 = 32;
+    while (n2 < (int) D) n2 <<= 1;
+    auto sortEntries = [&](auto slotsTag) {
+        constexpr int SL = decltype(slotsTag)::value;
+        unsigned long long r[SL];
+#pragma unroll
+        for (int sl = 0; sl < SL; sl++) { const unsigned e = sl * 32 + lane; r[sl] = e < D ? ent[e] : ~0ULL; }
+        __syncwarp();
+        warp_bitonic<SL>(r, SL * 32, lane);
+#pragma unroll
+        for (int sl = 0; sl < SL; sl++) ent[sl * 32 + lane] = r[sl];
+    };
+    if (n2 <= 32) sortEntries(std::integral_constant<int, 1>());
+    else if (n2 <= 64) sortEntries(std::integral_constant<int, 2>());
+    else if (n2 <= 128) sortEntries(std::integral_constant<int, 4>());
+    else if (n2 <= 256) sortEntries(std::integral_constant<int, 8>());
+    else sortEntries(std::integral_constant<int, 16>());
+    __syncwarp();
+    // run starts (first entry of every target), compacted in order; then one lane per run
+    unsigned short *runStart = reinterpret_cast<unsigned short *>(stage);     // up to 512 entries
+    unsigned nRuns = 0;
+    for (int sl = 0; sl * 32 < (int) D; sl++) {
+        const int i = sl * 32 + (int) lane;
+        const bool isStart = (i < (int) D) && (i == 0 || (ent[i - 1] >> 32) != (ent[i] >> 32));
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, isStart);
+        if (isStart) runStart[nRuns + __popc(m & ((1u << lane) - 1u))] = (unsigned short) i;
+        nRuns += __popc(m);
+    }
+    __syncwarp();
+    unsigned nEmitted = 0;
+    bool ownsLast = false; ScanState lastSt; lastSt.prevDiag = lastSt.diagCnt = lastSt.revCnt = lastSt.maxDiag = lastSt.best = lastSt.bestRev = lastSt.top = 0;
+    long long lastSlot = -1; unsigned lastTarget = 0;
+    for (unsigned r0 = 0; r0 < nRuns; r0 += 32) {
+        const unsigned ri = r0 + lane;
+        bool emit = false; pg_hit h; h.rep = rep; h.target = 0; h.score = 0; h.diag = 0;
+        ScanState st; st.prevDiag = st.diagCnt = st.revCnt = st.maxDiag = st.best = st.bestRev = st.top = 0;
+        if (ri < nRuns) {
+            const int i = runStart[ri];
+            const int e = (ri + 1 < nRuns) ? (int) runStart[ri + 1] : (int) D;
+            const unsigned target = (unsigned) (ent[i] >> 32);
+            for (int j = i; j < e; j++) {
+                const unsigned long long k = ent[j];
+                const unsigned cv = sCnt[(unsigned) (k & 0xFFFFULL)];
+                agg_step((unsigned) ((k >> 16) & 0xFFFFULL), cv & 0xFFFFu, cv >> 16, st);
+            }
+            emit = target != rep;
+            h.target = target;
+            h.score = st.bestRev ? -(int) st.top : (int) st.top;
+            h.diag = (int) (short) (unsigned short) (st.best - 32768u);
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, emit);
+        const long long slot = (long long) (s0 + nEmitted + __popc(m & ((1u << lane) - 1u)));
+        if (emit) tmpHits[slot] = h;
+        if (ri + 1 == nRuns) { ownsLast = true; lastSt = st; lastSlot = emit ? slot : -1; lastTarget = h.target; }
+        nEmitted += __popc(m);
+    }
+    __syncwarp();
+    // continuation of the last run into the following representative(s)
+    const unsigned ownerMask = __ballot_sync(0xFFFFFFFFu, ownsLast);
+    if (ownerMask && e0 < n) {
+        const int owner = __ffs(ownerMask) - 1;
+        ScanState st;
+        st.prevDiag = __shfl_sync(0xFFFFFFFFu, lastSt.prevDiag, owner); st.diagCnt = __shfl_sync(0xFFFFFFFFu, lastSt.diagCnt, owner);
+        st.revCnt = __shfl_sync(0xFFFFFFFFu, lastSt.revCnt, owner); st.maxDiag = __shfl_sync(0xFFFFFFFFu, lastSt.maxDiag, owner);
+        st.best = __shfl_sync(0xFFFFFFFFu, lastSt.best, owner); st.bestRev = __shfl_sync(0xFFFFFFFFu, lastSt.bestRev, owner);
+        st.top = __shfl_sync(0xFFFFFFFFu, lastSt.top, owner);
+        const unsigned X = __shfl_sync(0xFFFFFFFFu, lastTarget, owner);
+        const long long slot = __shfl_sync(0xFFFFFFFFu, lastSlot, owner);
+        const unsigned topBefore = st.top;
+        st = continue_run_warp(in, n, end, minTarget, e0, X, st, stage, overflow);
+        if (st.top != topBefore && slot >= 0 && lane == 0) {
+            pg_hit h; h.rep = rep; h.target = X;
+            h.score = st.bestRev ? -(int) st.top : (int) st.top;
+            h.diag = (int) (short) (unsigned short) (st.best - 32768u);
+            tmpHits[slot] = h;
+        }
+    }
+    if (lane == 0) hitCount[rep] = nEmitted;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(RH_WARPS * 32) reduce_rep_hashwarp_kernel(const Rec *__restrict__ in, unsigned long long n,
+                                                                            const unsigned long long *__restrict__ start, const unsigned long long *__restrict__ end,
+                                                                            const unsigned *__restrict__ minTarget,
+                                                                            const unsigned *__restrict__ midList, const unsigned *__restrict__ midCount,
+                                                                            pg_hit *__restrict__ tmpHits, unsigned *__restrict__ hitCount, unsigned *__restrict__ overflow) {
+    // per warp: table keys (the compacted entries are written over them, in place), counts, staging
+    __shared__ unsigned long long sKey[RH_WARPS][RH_WARP_TABLE];
+    __shared__ unsigned sCnt[RH_WARPS][RH_WARP_TABLE];
+    __shared__ unsigned sStage[RH_WARPS][256];
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const unsigned warpsTotal = gridDim.x * RH_WARPS;
+    const unsigned nWork = *midCount;
+    for (unsigned wi = blockIdx.x * RH_WARPS + w; wi < nWork; wi += warpsTotal) {
+        const unsigned rep = midList[wi];
+        const unsigned long long s0 = start[rep], e0 = end[rep];
+        const unsigned count = (unsigned) (e0 - s0);           // 129 .. RH_WARP_MAX
+        unsigned tsize = 256;
+        while (tsize < 2 * count) tsize <<= 1;                 // load factor <= 0.5: the probes always end
+        for (unsigned i = lane; i < tsize; i += 32) { sKey[w][i] = ~0ULL; sCnt[w][i] = 0; }
+        __syncwarp();
+        rh_insert(in, s0, count, lane, 32, sKey[w], sCnt[w], tsize - 1);
+        __syncwarp();
+        // in-place compaction: an entry moves to an index <= its slot, and every chunk is read before it is written
+        unsigned D = 0;
+        for (unsigned base = 0; base < tsize; base += 32) {
+            const unsigned long long key = sKey[w][base + lane];
+            const bool occ = key != ~0ULL;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, occ);
+            __syncwarp();
+            if (occ) sKey[w][D + __popc(m & ltMask)] = ((key >> 16) << 32) | ((key & 0xFFFFULL) << 16) | (unsigned long long) (base + lane);
+            D += __popc(m);
+            __syncwarp();
+        }
+        rh_sort_scan_emit(in, n, end, minTarget, rep, s0, e0, sKey[w], D, sCnt[w], sStage[w], tmpHits, hitCount, overflow);
+    }
+}
+
+__global__ void __launch_bounds__(256) reduce_rep_hashcta_kernel(const Rec *__restrict__ in, unsigned long long n,
+                                                                 const unsigned long long *__restrict__ start, const unsigned long long *__restrict__ end,
+                                                                 const unsigned *__restrict__ minTarget,
+                                                                 const unsigned *__restrict__ bigList, const unsigned *__restrict__ bigCount,
+                                                                 unsigned *__restrict__ hugeList, unsigned *__restrict__ hugeCount,
+                                                                 pg_hit *__restrict__ tmpHits, unsigned *__restrict__ hitCount, unsigned *__restrict__ overflow) {
+    __shared__ unsigned long long sKey[RH_CTA_TABLE];
+    __shared__ unsigned sCnt[RH_CTA_TABLE];
+    __shared__ unsigned long long sEnt[RH_SORT_MAX];
+    __shared__ unsigned sStage[256];
+    __shared__ unsigned sD, sFail;
+    const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const unsigned nBig = *bigCount;
+    for (unsigned bi = blockIdx.x; bi < nBig; bi += gridDim.x) {
+        const unsigned rep = bigList[bi];
+        const unsigned long long s0 = start[rep], e0 = end[rep];
+        const unsigned long long count64 = e0 - s0;
+        unsigned tsize = 1024;
+        while (tsize < 2 * count64 && tsize < (unsigned) RH_CTA_TABLE) tsize <<= 1;
+        for (unsigned i = tid; i < tsize; i += 256) { sKey[i] = ~0ULL; sCnt[i] = 0; }
+        if (tid == 0) { sD = 0; sFail = count64 > 0xFFFFULL ? 1u : 0u; }     // counts are 16-bit fields
+        __syncthreads();
+        if (!sFail && !rh_insert(in, s0, (unsigned) count64, tid, 256, sKey, sCnt, tsize - 1)) sFail = 1;
+        __syncthreads();
+        if (!sFail) {
+            for (unsigned base = w * 32; base < tsize; base += 256) {
+                const unsigned long long key = sKey[base + lane];
+                const bool occ = key != ~0ULL;
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, occ);
+                unsigned pos0 = 0;
+                if (lane == 0 && m) pos0 = atomicAdd(&sD, (unsigned) __popc(m));
+                pos0 = __shfl_sync(0xFFFFFFFFu, pos0, 0);
+                const unsigned pos = pos0 + __popc(m & ltMask);
+                if (occ && pos < (unsigned) RH_SORT_MAX) sEnt[pos] = ((key >> 16) << 32) | ((key & 0xFFFFULL) << 16) | (unsigned long long) (base + lane);
+            }
+        }
+        __syncthreads();
+        const bool fail = sFail || sD > (unsigned) RH_SORT_MAX;
+        if (fail) {
+            if (tid == 0) hugeList[atomicAdd(hugeCount, 1u)] = rep;
+        } else if (w == 0) {
+            rh_sort_scan_emit(in, n, end, minTarget, rep, s0, e0, sEnt, sD, sCnt, sStage, tmpHits, hitCount, overflow);
+        }
+        __syncthreads();
+    }
+}
+
 // representatives with more than SEG_WARP_MAX pairs: one CTA each, bitonic sort in shared memory
 __global__ void __launch_bounds__(256) reduce_rep_block_kernel(const Rec *__restrict__ in, unsigned long long n,
                                                                const unsigned long long *__restrict__ start, const unsigned long long *__restrict__ end,
@@ -1651,6 +1871,7 @@ static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, 
     const size_t oCnt = take(sizeof(unsigned) * ((size_t) nKeys + 1));
     const size_t oOff = take(sizeof(unsigned long long) * ((size_t) nKeys + 2)), oBig = take(sizeof(unsigned) * ((size_t) nKeys + 1));
     const size_t oMid = take(sizeof(unsigned) * ((size_t) nKeys + 1));
+    const size_t oHuge = take(sizeof(unsigned) * ((size_t) nKeys + 1));
     const size_t oScan = take(scan_workspace_bytes(nKeys));
     const size_t oMinT = take(sizeof(unsigned) * ((size_t) nKeys + 1));
     PG_TRY(ctx->buckets2.reserve(o));
@@ -1659,7 +1880,8 @@ static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, 
     unsigned *d_hcnt = (unsigned *) (bb + oCnt), *d_big = (unsigned *) (bb + oBig), *d_minT = (unsigned *) (bb + oMinT), *d_mid = (unsigned *) (bb + oMid);
     unsigned long long *d_hoff = (unsigned long long *) (bb + oOff);
     unsigned *d_over = (unsigned *) (ctx->small.as<unsigned long long>() + 32);     // [32] overflow flag, big count, mid count; [34] total hits
-    unsigned *d_bigCnt = d_over + 1, *d_midCnt = d_over + 2;
+    unsigned *d_bigCnt = d_over + 1, *d_midCnt = d_over + 2, *d_hugeCnt = d_over + 3;
+    unsigned *d_huge = (unsigned *) (bb + oHuge);
     unsigned long long *d_total = ctx->small.as<unsigned long long>() + 34;
     PG_CUDA(cudaMemsetAsync(d_start, 0, oOff, s));   // start, end, hit counts
     PG_CUDA(cudaMemsetAsync(d_over, 0, 4 * sizeof(unsigned), s));
@@ -1667,11 +1889,13 @@ static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, 
     seg_bounds_kernel<<<NUM_SMS * 16, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT);
     pg_hit *tmpHits = reinterpret_cast<pg_hit *>(other);   // a hit is 16 bytes like a record, at most one per pair
     reduce_rep_warp_kernel<0><<<NUM_SMS * 32, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT, keyLo, keyHi, tmpHits, d_hcnt, d_big, d_bigCnt, d_mid, d_midCnt, d_over);
-    reduce_rep_warp_kernel<1><<<NUM_SMS * 8, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT, keyLo, keyHi, tmpHits, d_hcnt, d_big, d_bigCnt, d_mid, d_midCnt, d_over);
-    ctx->launches++;
+    // 129 .. 512 pairs: warp per representative, > 512: CTA per representative, both aggregating by (target, diagonal)
+    // before they sort; what does not fit their tables is sorted in full by reduce_rep_block_kernel
+    reduce_rep_hashwarp_kernel<<<NUM_SMS * 8, RH_WARPS * 32, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT, d_mid, d_midCnt, tmpHits, d_hcnt, d_over);
+    reduce_rep_hashcta_kernel<<<NUM_SMS * 4, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT, d_big, d_bigCnt, d_huge, d_hugeCnt, tmpHits, d_hcnt, d_over);
     PG_CUDA(cudaFuncSetAttribute(reduce_rep_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_BLOCK_MAX * (int) sizeof(unsigned long long)));
-    reduce_rep_block_kernel<<<NUM_SMS * 3, 256, SEG_BLOCK_MAX * sizeof(unsigned long long), s>>>(sorted, nPairs, d_start, d_end, d_minT, d_big, d_bigCnt, tmpHits, d_hcnt, d_over);
-    ctx->launches += 3;
+    reduce_rep_block_kernel<<<NUM_SMS, 256, SEG_BLOCK_MAX * sizeof(unsigned long long), s>>>(sorted, nPairs, d_start, d_end, d_minT, d_huge, d_hugeCnt, tmpHits, d_hcnt, d_over);
+    ctx->launches += 5;
     PG_TRY(exclusive_scan_u32(d_hcnt, d_hoff, nKeys, d_total, bb + oScan, scan_workspace_bytes(nKeys), s, &ctx->launches));
     unsigned long long h = 0; unsigned over = 0;
     PG_CUDA(cudaMemcpyAsync(&h, d_total, sizeof(h), cudaMemcpyDeviceToHost, s));

@@ -420,6 +420,7 @@ int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHit
     cudaEventRecord(ctx->ev[EV_RS_END], s);
     PG_CUDA(cudaGetLastError());
     *d_alns = out; *nAlns = h;
+    ctx->rsOut = out; ctx->rsCnt = cnt; ctx->rsOff = off;
     ctx->timings.n_alns = h;
     ctx->rsRan = true;
     return 0;

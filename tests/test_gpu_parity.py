@@ -281,3 +281,32 @@ def test_kmermatcher_param_sweep_matches_oracle(case, over, golden_root, ctx):
         # the strand sign is only defined up to the documented tie hazard (nt); magnitudes must agree
         assert np.array_equal(np.abs(got["score"]), np.abs(want["score"])), (case, over)
         assert (got["score"] != want["score"]).sum() <= max(2, len(want) // 500), (case, over)
+
+
+@pytest.mark.parametrize("coverage,n_reads", [(20, 4000), (60, 4000), (120, 4000), (500, 3000), (2500, 2500)])
+def test_whole_iteration_at_high_coverage_matches_oracle(coverage, n_reads, ctx):
+    """Representatives with hundreds to thousands of pair records and queries with more than 32 / 64 alignments:
+    the (target, diagonal) aggregating reduce kernels (warp, CTA, full-sort spill), the wide extension paths and
+    the fall-backs behind them, against the CPU oracle on the same seeded input."""
+    from plass_b200 import synth
+    reads = synth.make_reads(n_reads, coverage=float(coverage), seed=11 + coverage)
+    db = synth.protein_fragments(reads)
+    kp, rp, ep = api.default_km_params(False), api.default_rs_params(False), api.default_ex_params(False)
+    ddb = ctx.upload(db)
+    out, hits, alns = ctx.assemble_iteration(ddb, kp, rp, ep, want_intermediates=True)
+    got = out.download()
+    out.free(); ddb.free()
+    okp = ob.KmParams(**{f: getattr(kp, f) for f, _ in ob.KmParams._fields_ if f not in ("hash_start", "hash_end")})
+    okp.hash_start, okp.hash_end = 0, ob.U64MAX
+    whits = ob.kmermatch(db, okp)
+    assert len(hits) == len(whits), (coverage, len(hits), len(whits))
+    for f in ("rep", "target", "score", "diag"):
+        assert np.array_equal(hits[f], whits[f]), (coverage, f)
+    walns = ob.rescore(db, whits, ob.RsParams(**{f: getattr(rp, f) for f, _ in ob.RsParams._fields_}))
+    check_alns(alns, walns, "coverage %d" % coverage)
+    wout, _ = ob.extend(db, walns, ob.ExParams(**{f: getattr(ep, f) for f, _ in ob.ExParams._fields_}))
+    assert_same_entries(got.entries_by_key(), wout.entries_by_key(), "coverage %d" % coverage)
+    per_rep = np.bincount(whits["rep"]) if len(whits) else np.zeros(1)
+    per_query = np.bincount(walns["query"]) if len(walns) else np.zeros(1)
+    print("coverage %d: %d fragments, %d hits (max %d per representative), max %d alignments per query" % (
+        coverage, db.n, len(whits), per_rep.max(), per_query.max()))
