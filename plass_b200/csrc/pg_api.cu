@@ -26,13 +26,17 @@ __global__ void read_back_kernel(unsigned *__restrict__ hostMapped, const unsign
     for (unsigned i = threadIdx.x; i < words; i += blockDim.x) hostMapped[i] = dev[i];
 }
 
-int read_back(Context *ctx, void *host, const void *dev, size_t bytes) {
+int read_back_on(Context *ctx, cudaStream_t stream, void *host, const void *dev, size_t bytes) {
     PG_CHECK(bytes <= 1024 && (bytes & 3) == 0, "read_back: at most 1024 bytes, multiple of 4");
-    read_back_kernel<<<1, 32, 0, ctx->stream>>>((unsigned *) ctx->hostStage, (const unsigned *) dev, (unsigned) (bytes / 4));
-    PG_CUDA(cudaStreamSynchronize(ctx->stream));
-    memcpy(host, ctx->hostStage, bytes);
+    // the auxiliary stream stages through the second half of the mapped block
+    unsigned *stage = (unsigned *) ctx->hostStage + (stream == ctx->stream ? 0 : 256);
+    read_back_kernel<<<1, 32, 0, stream>>>(stage, (const unsigned *) dev, (unsigned) (bytes / 4));
+    PG_CUDA(cudaStreamSynchronize(stream));
+    memcpy(host, stage, bytes);
     return 0;
 }
+
+int read_back(Context *ctx, void *host, const void *dev, size_t bytes) { return read_back_on(ctx, ctx->stream, host, dev, bytes); }
 
 __global__ void count_nonzero_kernel(const unsigned char *__restrict__ v, unsigned long long n, unsigned long long *__restrict__ out) {
     unsigned long long c = 0;
@@ -223,7 +227,14 @@ int pg_init(int device, pg_context **out) {
     PG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     PG_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
     PG_CUDA(cudaEventCreateWithFlags(&ctx->evCopyReady, cudaEventDisableTiming));
-    PG_CUDA(cudaHostAlloc((void **) &ctx->hostStage, 1024, cudaHostAllocMapped | cudaHostAllocPortable));
+    PG_CUDA(cudaHostAlloc((void **) &ctx->hostStage, 2048, cudaHostAllocMapped | cudaHostAllocPortable));
+    {   // high priority: its small kernels get SM slots as soon as CTAs of the main stream's big kernel retire
+        int lowest = 0, greatest = 0;
+        PG_CUDA(cudaDeviceGetStreamPriorityRange(&lowest, &greatest));
+        PG_CUDA(cudaStreamCreateWithPriority(&ctx->auxStream, cudaStreamNonBlocking, greatest));
+    }
+    PG_CUDA(cudaEventCreateWithFlags(&ctx->evAuxFork, cudaEventDisableTiming));
+    PG_CUDA(cudaEventCreateWithFlags(&ctx->evAuxJoin, cudaEventDisableTiming));
     {
         cudaMemPool_t pool;
         PG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -247,6 +258,9 @@ void pg_destroy(pg_context *ctx) {
     cudaStreamSynchronize(ctx->copyStream);
     cudaEventDestroy(ctx->evCopyReady);
     cudaFreeHost(ctx->hostStage);
+    cudaStreamSynchronize(ctx->auxStream);
+    cudaEventDestroy(ctx->evAuxFork); cudaEventDestroy(ctx->evAuxJoin);
+    cudaStreamDestroy(ctx->auxStream);
     cudaStreamDestroy(ctx->copyStream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

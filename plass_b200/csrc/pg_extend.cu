@@ -989,7 +989,15 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     // amino acids: the queries with <= 32 alignments (all of them, usually) run to completion inside one kernel; only
     // the larger ones go through the rounds below
     const bool fusedWarp = !nt && getenv("PG_EX_WAVEFRONT") == nullptr;
+    cudaStream_t rs = s;                                      // the stream the rounds run on
     if (fusedWarp && active > 0) {
+        if (needHeap) {
+            // the rounds of the large queries run on the auxiliary stream next to the warp kernel: disjoint queries
+            // (`used` is only ever set to 1 by both)
+            rs = ctx->auxStream;
+            PG_CUDA(cudaEventRecord(ctx->evAuxFork, s));
+            PG_CUDA(cudaStreamWaitEvent(rs, ctx->evAuxFork, 0));
+        }
         extend_query_warp_kernel<<<std::min<unsigned>((active + 7) / 8, NUM_SMS * 32), 256, 0, s>>>(
             *db, d_alns, alnStart, alnCount, c, cur, d_listCnt + curIdx, ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
         ctx->launches++;
@@ -998,29 +1006,33 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     }
     for (int round = 0; active > 0; round++) {
         PG_CHECK(round < 100000, "assembleresults: extension did not converge");
-        PG_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
-        PG_CUDA(cudaMemsetAsync(d_listCnt + (1 - curIdx), 0, sizeof(unsigned), s));
+        PG_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), rs));
+        PG_CUDA(cudaMemsetAsync(d_listCnt + (1 - curIdx), 0, sizeof(unsigned), rs));
         if (!nt && !fusedWarp) {
             // amino acids, wavefront variant (PG_EX_WAVEFRONT=1): warp per query for the queries with <= 32 alignments,
             // heap replay for the rest (both kernels read the same list and skip the queries of the other class)
-            extend_round_warp_kernel<<<std::min<unsigned>((active + 7) / 8, NUM_SMS * 32), 256, 0, s>>>(
+            extend_round_warp_kernel<<<std::min<unsigned>((active + 7) / 8, NUM_SMS * 32), 256, 0, rs>>>(
                 *db, d_alns, alnStart, alnCount, c, round == 0, cur, d_listCnt + curIdx, nxt, d_listCnt + (1 - curIdx), work, d_cnt, states,
                 parkBuf, ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
             ctx->launches++;
         }
         if (needHeap) {
-            extend_round_kernel<<<(active + 127) / 128, 128, 0, s>>>(*db, d_alns, alnStart, alnCount, c, round == 0, cur, d_listCnt + curIdx,
-                                                                    nxt, d_listCnt + (1 - curIdx), work, d_cnt, states, heapBuf, parkBuf,
-                                                                    ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
+            extend_round_kernel<<<(active + 127) / 128, 128, 0, rs>>>(*db, d_alns, alnStart, alnCount, c, round == 0, cur, d_listCnt + curIdx,
+                                                                     nxt, d_listCnt + (1 - curIdx), work, d_cnt, states, heapBuf, parkBuf,
+                                                                     ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
             ctx->launches++;
         }
-        extend_rescore_kernel<<<NUM_SMS * 8, 256, 0, s>>>(*db, alnStart, c, work, d_cnt, states, parkBuf, ctx->exSegs.as<ExSeg>());
+        extend_rescore_kernel<<<NUM_SMS * 8, 256, 0, rs>>>(*db, alnStart, c, work, d_cnt, states, parkBuf, ctx->exSegs.as<ExSeg>());
         ctx->launches += 1;
-        PG_TRY(read_back(ctx, hCnt, d_listCnt + (1 - curIdx), sizeof(unsigned)));
+        PG_TRY(read_back_on(ctx, rs, hCnt, d_listCnt + (1 - curIdx), sizeof(unsigned)));
         active = hCnt[0];
         unsigned *t = cur; cur = nxt; nxt = t;
         curIdx = 1 - curIdx;
         if (trace && round < 3) lap("  round");
+    }
+    if (rs != s) {
+        PG_CUDA(cudaEventRecord(ctx->evAuxJoin, rs));
+        PG_CUDA(cudaStreamWaitEvent(s, ctx->evAuxJoin, 0));
     }
     lap("rounds (rest)");
     keep_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(n, c.keepTarget, ext, used, keep, outLen, db->keys, ctx->ownLo, ctx->ownHi);

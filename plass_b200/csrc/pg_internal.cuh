@@ -18,6 +18,8 @@ struct pg_context {
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr;         // device -> host copies of finished stage results, overlapped with the next stage
     cudaEvent_t evCopyReady = nullptr;
+    cudaStream_t auxStream = nullptr;          // independent kernel work that runs next to the main stream (extension: heap rounds)
+    cudaEvent_t evAuxFork = nullptr, evAuxJoin = nullptr;
     unsigned long long *hostStage = nullptr;   // mapped pinned words: the kernels' small results are read back through here (pg::read_back)
     cudaEvent_t ev[pg::EV_COUNT];
     pg::DevBuf small, lists, recA, recB, radixWs, scratch, blockCounts, hits, alnAll, alns, flags, exWork, exSegs, exMeta, exLists, ntTab, buckets, buckets2;
@@ -63,5 +65,6 @@ void seqdb_release(pg_seqdb *db, cudaStream_t s);
 // the words into mapped pinned memory and the stream is synchronised.  A cudaMemcpyAsync would queue behind the large
 // result transfers that run on ctx->copyStream underneath the following stage.  bytes <= 1024, multiple of 4.
 int read_back(Context *ctx, void *host, const void *dev, size_t bytes);
+int read_back_on(Context *ctx, cudaStream_t stream, void *host, const void *dev, size_t bytes);   // same on another stream of the context
 int alloc_pinned(size_t bytes, void **out);        // pooled pinned host memory, released with pg_free_host
 }  // namespace pg
