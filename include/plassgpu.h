@@ -143,6 +143,17 @@ int pg_assemble_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_param
                           const pg_ex_params *ep, pg_seqdb **out_db,
                           pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns);
 
+/* Asynchronous result transfer.  The reference workflow writes pref_N / aln_N / assembly_N to disk while the next
+ * iteration's input already sits in HBM; with pg_set_async_results(ctx, 1) pg_assemble_iteration (hits, alns) and
+ * pg_seqdb_download only ENQUEUE their device->host copies on the context's copy stream and return, so that the
+ * transfers of iteration N run underneath iteration N+1.  The returned host arrays may be read after
+ * pg_results_wait(ctx, t) for a ticket t taken (pg_results_ticket) after the calls that produced them.  A DB whose
+ * download is pending may be released with pg_seqdb_free right away (the release is ordered after the copy).
+ * pg_set_async_results(ctx, 0) drains the copy stream and restores the blocking behaviour. */
+int pg_set_async_results(pg_context *ctx, int on);
+int pg_results_ticket(pg_context *ctx, uint64_t *ticket);
+int pg_results_wait(pg_context *ctx, uint64_t ticket);
+
 /* Multi-GPU, one process per GPU.  The sequence DB is replicated in every HBM; one iteration is
  * split around its two exchange steps, which the caller performs on the device buffers (NCCL all-to-all through
  * torch.distributed in bench.py / plass_b200/sharded.py):

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(HERE, "libplassgpu.so")
 # symbols include/plassgpu.h declares
 EXPORTS = ["pg_last_error", "pg_device_count", "pg_init", "pg_destroy", "pg_get_timings", "pg_seqdb_upload", "pg_seqdb_adopt",
            "pg_seqdb_download", "pg_seqdb_size", "pg_seqdb_free", "pg_kmermatch", "pg_rescore", "pg_extend",
-           "pg_assemble_iteration", "pg_free_host",
+           "pg_assemble_iteration", "pg_free_host", "pg_set_async_results", "pg_results_ticket", "pg_results_wait",
            "pg_shard_pairs", "pg_shard_extract", "pg_shard_group", "pg_shard_route", "pg_shard_export", "pg_shard_finish", "pg_shard_owner_range", "pg_seqdb_max_key"]
 
 
@@ -175,6 +175,19 @@ class Context:
         if self.handle:
             load_library().pg_destroy(self.handle)
             self.handle = None
+
+    # asynchronous results: assemble_iteration(want_intermediates=True) and DeviceSeqDB.download() only enqueue their
+    # device -> host copies; the returned arrays may be read after results_wait(t) for a ticket t taken after the calls
+    def set_async_results(self, on):
+        _check(load_library().pg_set_async_results(self.handle, C.c_int(1 if on else 0)), "pg_set_async_results")
+
+    def results_ticket(self):
+        t = C.c_uint64()
+        _check(load_library().pg_results_ticket(self.handle, C.byref(t)), "pg_results_ticket")
+        return int(t.value)
+
+    def results_wait(self, ticket):
+        _check(load_library().pg_results_wait(self.handle, C.c_uint64(ticket)), "pg_results_wait")
 
     def timings(self):
         t = Timings()

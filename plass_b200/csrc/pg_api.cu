@@ -134,7 +134,7 @@ static int to_host(cudaStream_t s, const T *d, uint64_t n, T **out) {
 // kernels of the following stage (the result buffers ctx->hits / ctx->alns are not written again within the call).
 // The caller synchronises ctx->copyStream before it hands the host array out.
 template <class T>
-static int to_host_overlapped(Context *ctx, const T *d, uint64_t n, T **out) {
+static int to_host_overlapped(Context *ctx, const T *d, uint64_t n, T **out, cudaEvent_t copied = nullptr) {
     T *h = nullptr;
     PG_TRY(alloc_pinned(sizeof(T) * (n + 1), (void **) &h));
     *out = h;
@@ -142,6 +142,7 @@ static int to_host_overlapped(Context *ctx, const T *d, uint64_t n, T **out) {
     PG_CUDA(cudaEventRecord(ctx->evCopyReady, ctx->stream));
     PG_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->evCopyReady, 0));
     PG_CUDA(cudaMemcpyAsync(h, d, sizeof(T) * n, cudaMemcpyDeviceToHost, ctx->copyStream));
+    if (copied) PG_CUDA(cudaEventRecord(copied, ctx->copyStream));
     return 0;
 }
 
@@ -227,6 +228,9 @@ int pg_init(int device, pg_context **out) {
     PG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     PG_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
     PG_CUDA(cudaEventCreateWithFlags(&ctx->evCopyReady, cudaEventDisableTiming));
+    PG_CUDA(cudaEventCreateWithFlags(&ctx->evHitsCopied, cudaEventDisableTiming));
+    PG_CUDA(cudaEventCreateWithFlags(&ctx->evAlnsCopied, cudaEventDisableTiming));
+    for (int i = 0; i < 16; i++) PG_CUDA(cudaEventCreateWithFlags(&ctx->evTicket[i], cudaEventDisableTiming));
     PG_CUDA(cudaHostAlloc((void **) &ctx->hostStage, 2048, cudaHostAllocMapped | cudaHostAllocPortable));
     {   // high priority: its small kernels get SM slots as soon as CTAs of the main stream's big kernel retire
         int lowest = 0, greatest = 0;
@@ -257,6 +261,8 @@ void pg_destroy(pg_context *ctx) {
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
     cudaStreamSynchronize(ctx->copyStream);
     cudaEventDestroy(ctx->evCopyReady);
+    cudaEventDestroy(ctx->evHitsCopied); cudaEventDestroy(ctx->evAlnsCopied);
+    for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->evTicket[i]);
     cudaFreeHost(ctx->hostStage);
     cudaStreamSynchronize(ctx->auxStream);
     cudaEventDestroy(ctx->evAuxFork); cudaEventDestroy(ctx->evAuxJoin);
@@ -312,6 +318,17 @@ int pg_seqdb_download(pg_context *ctx, const pg_seqdb *db, char **data, uint64_t
                       uint32_t **lens, uint32_t **keys, uint64_t *n) {
     PG_CHECK(ctx && db, "pg_seqdb_download: null argument");
     cudaSetDevice(ctx->device);
+    if (ctx->asyncResults) {
+        // enqueue only: the arrays are complete after pg_results_wait on a ticket taken after this call.  The DB's device
+        // arrays are then released on the copy stream (pg_seqdb_free), i.e. after these copies.
+        PG_TRY(to_host_overlapped(ctx, db->data, db->data_bytes, data));
+        PG_TRY(to_host_overlapped(ctx, (const uint64_t *) db->offsets, db->n, offsets));
+        PG_TRY(to_host_overlapped(ctx, db->lens, db->n, lens));
+        PG_TRY(to_host_overlapped(ctx, db->keys, db->n, keys));
+        const_cast<pg_seqdb *>(db)->downloadPending = true;
+        *data_bytes = db->data_bytes; *n = db->n;
+        return 0;
+    }
     PG_TRY(to_host(ctx->stream, db->data, db->data_bytes, data));
     PG_TRY(to_host(ctx->stream, (const uint64_t *) db->offsets, db->n, offsets));
     PG_TRY(to_host(ctx->stream, db->lens, db->n, lens));
@@ -325,7 +342,9 @@ uint64_t pg_seqdb_size(const pg_seqdb *db) { return db ? db->n : 0; }
 void pg_seqdb_free(pg_context *ctx, pg_seqdb *db) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    seqdb_release(db, ctx->stream);
+    // stream-ordered release: after the kernels of the main stream, or after the pending download on the copy stream
+    // (every consumer on the main stream was enqueued before the download)
+    seqdb_release(db, (db && db->downloadPending) ? ctx->copyStream : ctx->stream);
 }
 
 int pg_kmermatch(pg_context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **hits, uint64_t *n_hits) {
@@ -378,10 +397,10 @@ int pg_assemble_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_param
     begin_call(ctx);
     pg_hit *dHits = nullptr; uint64_t nH = 0;
     PG_TRY(km_run(ctx, db, kp, &dHits, &nH));
-    if (hits && n_hits) { PG_TRY(to_host_overlapped(ctx, dHits, nH, hits)); *n_hits = nH; }        // copied while rescorediagonal runs
+    if (hits && n_hits) { PG_TRY(to_host_overlapped(ctx, dHits, nH, hits, ctx->evHitsCopied)); *n_hits = nH; }        // copied while rescorediagonal runs
     pg_aln *dAlns = nullptr; uint64_t nA = 0;
     PG_TRY(rs_run(ctx, db, dHits, nH, rp, &dAlns, &nA));
-    if (alns && n_alns) { PG_TRY(to_host_overlapped(ctx, dAlns, nA, alns)); *n_alns = nA; }        // copied while the extension runs
+    if (alns && n_alns) { PG_TRY(to_host_overlapped(ctx, dAlns, nA, alns, ctx->evAlnsCopied)); *n_alns = nA; }        // copied while the extension runs
     unsigned char *dExt = nullptr;
     PG_TRY(ex_run(ctx, db, dAlns, nA, ep, out_db, &dExt));
     {   // number of new contigs, for the statistics
@@ -394,7 +413,33 @@ int pg_assemble_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_param
     }
     cudaFreeAsync(dExt, ctx->stream);
     end_call(ctx);
-    PG_CUDA(cudaStreamSynchronize(ctx->copyStream));
+    if (!ctx->asyncResults) PG_CUDA(cudaStreamSynchronize(ctx->copyStream));
+    return 0;
+}
+
+int pg_set_async_results(pg_context *ctx, int on) {
+    PG_CHECK(ctx, "pg_set_async_results: null argument");
+    cudaSetDevice(ctx->device);
+    if (!on) PG_CUDA(cudaStreamSynchronize(ctx->copyStream));
+    ctx->asyncResults = on != 0;
+    return 0;
+}
+
+int pg_results_ticket(pg_context *ctx, uint64_t *ticket) {
+    PG_CHECK(ctx && ticket, "pg_results_ticket: null argument");
+    cudaSetDevice(ctx->device);
+    const uint64_t t = ctx->nextTicket++;
+    PG_CUDA(cudaEventRecord(ctx->evTicket[t % 16], ctx->copyStream));
+    *ticket = t;
+    return 0;
+}
+
+int pg_results_wait(pg_context *ctx, uint64_t ticket) {
+    PG_CHECK(ctx, "pg_results_wait: null argument");
+    PG_CHECK(ticket < ctx->nextTicket, "pg_results_wait: unknown ticket");
+    cudaSetDevice(ctx->device);
+    // a slot that was recorded again later marks a later position of the same stream: waiting for it covers the ticket
+    PG_CUDA(cudaEventSynchronize(ctx->evTicket[ticket % 16]));
     return 0;
 }
 

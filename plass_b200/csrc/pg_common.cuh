@@ -111,4 +111,5 @@ struct pg_seqdb {
     double residues = 0;                  // getAminoAcidDBSize = sum(len) - 2n
     bool dense_keys = false;
     bool borrowed = false;                // pg_seqdb_adopt: the arrays belong to the caller
+    bool downloadPending = false;         // an asynchronous pg_seqdb_download is (or was) in flight on the copy stream
 };

@@ -18,6 +18,12 @@ struct pg_context {
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr;         // device -> host copies of finished stage results, overlapped with the next stage
     cudaEvent_t evCopyReady = nullptr;
+    // asynchronous results (pg_set_async_results): the device -> host copies are only enqueued; tickets mark positions
+    // of the copy stream.  evHitsCopied / evAlnsCopied guard the result buffers against the next call's writes.
+    bool asyncResults = false;
+    cudaEvent_t evHitsCopied = nullptr, evAlnsCopied = nullptr;
+    cudaEvent_t evTicket[16];
+    uint64_t nextTicket = 0;
     cudaStream_t auxStream = nullptr;          // independent kernel work that runs next to the main stream (extension: heap rounds)
     cudaEvent_t evAuxFork = nullptr, evAuxJoin = nullptr;
     unsigned long long *hostStage = nullptr;   // mapped pinned words: the kernels' small results are read back through here (pg::read_back)

@@ -1904,6 +1904,7 @@ static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, 
     PG_CUDA(cudaGetLastError());
     if (over) { *pairsIO = sorted; *tmpIO = other; return 0; }
     PG_TRY(ctx->hits.reserve(sizeof(pg_hit) * (h + 1)));
+    PG_CUDA(cudaStreamWaitEvent(s, ctx->evHitsCopied, 0));   // an asynchronous copy of the previous call's hits may still read the buffer
     compact_rep_hits_kernel<<<NUM_SMS * 16, 256, 0, s>>>(tmpHits, d_start, d_hcnt, d_hoff, keyLo, keyHi, ctx->hits.as<pg_hit>());
     ctx->launches++;
     cudaEventRecord(ctx->ev[EV_REDUCE_END], s);
@@ -1944,6 +1945,7 @@ int km_reduce(Context *ctx, const pg_seqdb *db, Rec *pairs, Rec *tmp, uint64_t n
     PG_CUDA(cudaMemcpyAsync(&h, d_total, sizeof(h), cudaMemcpyDeviceToHost, s));
     PG_CUDA(cudaStreamSynchronize(s));
     PG_TRY(ctx->hits.reserve(sizeof(pg_hit) * (h + 1)));
+    PG_CUDA(cudaStreamWaitEvent(s, ctx->evHitsCopied, 0));
     reduce_emit_kernel<<<(unsigned) blocks, 256, 0, s>>>(sorted, nPairs, d_offsets, ctx->hits.as<pg_hit>());
     ctx->launches += 3;
     cudaEventRecord(ctx->ev[EV_REDUCE_END], s);

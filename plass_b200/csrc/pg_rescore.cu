@@ -414,6 +414,7 @@ int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHit
     PG_TRY(read_back(ctx, &h, d_total, sizeof(h)));
     PG_TRY(ctx->alns.reserve(sizeof(pg_aln) * (h + 1)));
     pg_aln *out = ctx->alns.as<pg_aln>();
+    PG_CUDA(cudaStreamWaitEvent(s, ctx->evAlnsCopied, 0));   // an asynchronous copy of the previous call's alignments may still read the buffer
     if (c.nSelf) gather_self_kernel<<<(unsigned) ((c.nSelf + 255) / 256), 256, 0, s>>>(res, nHits, c.nSelf, off, acc, selfLo, out);
     if (nHits) gather_hits_kernel<<<(unsigned) ((nHits + 255) / 256), 256, 0, s>>>(*db, d_hits, nHits, acc, res, off, out);
     ctx->launches += 2;

@@ -12,6 +12,7 @@ import numpy as np
 from . import api
 
 REC_BYTES = 16
+_CONTIGUOUS_OK = set()
 
 
 def hash_range(rank, world):
@@ -77,7 +78,9 @@ def gather_slices(dist, db, rank, world, device):
     lens = np.ascontiguousarray(db.lens, dtype=np.uint32)
     keys = np.ascontiguousarray(db.keys, dtype=np.uint32)
     data = np.ascontiguousarray(db.data)
-    assert n == 0 or (int(offs[0]) == 0 and bool(np.all(offs[1:] == offs[:-1] + lens[:-1]))), "gather_slices: DB data must be contiguous in index order"
+    if id(db) not in _CONTIGUOUS_OK:      # O(n) host check, once per DB object
+        assert n == 0 or (int(offs[0]) == 0 and bool(np.all(offs[1:] == offs[:-1] + lens[:-1]))), "gather_slices: DB data must be contiguous in index order"
+        _CONTIGUOUS_OK.add(id(db))
     d_data = torch.empty(data.nbytes + 16, dtype=torch.uint8, device=device)
     d_offs = torch.empty(n + 1, dtype=torch.int64, device=device)
     d_lens = torch.empty(n + 1, dtype=torch.int32, device=device)

@@ -310,3 +310,31 @@ def test_whole_iteration_at_high_coverage_matches_oracle(coverage, n_reads, ctx)
     per_query = np.bincount(walns["query"]) if len(walns) else np.zeros(1)
     print("coverage %d: %d fragments, %d hits (max %d per representative), max %d alignments per query" % (
         coverage, db.n, len(whits), per_rep.max(), per_query.max()))
+
+
+def test_async_results_equal_blocking(golden_root, ctx):
+    """pg_set_async_results: two iterations in flight, results awaited by ticket, must equal the blocking calls."""
+    from plass_b200 import synth
+    dbs = [synth.protein_fragments(synth.make_reads(3000, seed=s)) for s in (3, 4, 5)]
+    kp, rp, ep = api.default_km_params(False), api.default_rs_params(False), api.default_ex_params(False)
+    want = []
+    for db in dbs:
+        ddb = ctx.upload(db)
+        out, hits, alns = ctx.assemble_iteration(ddb, kp, rp, ep, want_intermediates=True)
+        want.append((hits.copy(), alns.copy(), out.download().entries_by_key()))
+        out.free(); ddb.free()
+    ctx.set_async_results(True)
+    try:
+        inflight = []
+        for db in dbs:
+            ddb = ctx.upload(db)
+            out, hits, alns = ctx.assemble_iteration(ddb, kp, rp, ep, want_intermediates=True)
+            host = out.download()
+            inflight.append((ctx.results_ticket(), hits, alns, host))
+            out.free(); ddb.free()          # released while the copies may still be in flight
+        for (ticket, hits, alns, host), (whits, walns, wout) in zip(inflight, want):
+            ctx.results_wait(ticket)
+            assert np.array_equal(hits, whits) and np.array_equal(alns, walns)
+            assert host.entries_by_key() == wout
+    finally:
+        ctx.set_async_results(False)
