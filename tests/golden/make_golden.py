@@ -34,12 +34,43 @@ CASES = {
     "example_aa": dict(tool="plass", wf="assemble", iters=3, inputs="example"),
     "synth_aa": dict(tool="plass", wf="assemble", iters=3, inputs=dict(n=4000, seed=11)),
     "synth_nt": dict(tool="penguin", wf="nuclassemble", iters=3, inputs=dict(n=2500, seed=12)),
+    # sequences of 32767 residues and more: kmermatcher switches to KmerPosition<int> (kmermatcher.cpp:797-802), diagonals
+    # no longer fit 16 bits (hit_t::diagonal wraps, DistanceCalculator.h:94-113 searches the wrapped diagonals)
+    "long_nt": dict(tool="penguin", wf="nuclassemble", iters=2, inputs=dict(kind="long_nt", seed=13)),
 }
+
+
+def long_nt_fasta(path, seed):
+    """An 80 kb random genome as five long overlapping pieces (45, 50, 70 and 42 kb and a reverse-complemented 40 kb
+    one) plus 1500 nearly error-free 150 nt reads on both strands."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    g = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 80000)]
+    comp = np.zeros(256, dtype=np.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    # g[38000:80000] meets g[0:45000] on diagonal 38000 and g[5000:75000] on 33000: beyond 16 bits
+    seqs = [g[0:45000], g[30000:80000], comp[g[20000:60000][::-1]], g[5000:75000], g[38000:80000]]
+    for _ in range(1500):
+        s = int(rng.integers(0, 80000 - 150))
+        r = g[s:s + 150].copy()
+        sub = rng.random(150) < 0.003
+        r[sub] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(sub.sum()))]
+        seqs.append(comp[r[::-1]] if rng.random() < 0.5 else r)
+    with open(path, "wb") as f:
+        for i, q in enumerate(seqs):
+            f.write(b">s%d\n" % i)
+            f.write(q.tobytes())
+            f.write(b"\n")
 
 
 def run_case(name, spec, work):
     if spec["inputs"] == "example":
         inputs = ["/root/reference/examples/reads_1.fastq.gz", "/root/reference/examples/reads_2.fastq.gz"]
+    elif spec["inputs"].get("kind") == "long_nt":
+        fa = os.path.join(work, "reads.fasta")
+        long_nt_fasta(fa, spec["inputs"]["seed"])
+        inputs = [fa]
     else:
         fa = os.path.join(work, "reads.fasta")
         synth_reads.write_fasta(fa, synth_reads.make_reads(spec["inputs"]["n"], seed=spec["inputs"]["seed"]))

@@ -14,7 +14,7 @@ from plass_b200 import mmseqsdb
 import oracle_binding as ob
 import params
 
-CASES = ["example_aa", "synth_aa", "synth_nt"]
+CASES = ["example_aa", "synth_aa", "synth_nt", "long_nt"]
 
 
 def _steps(case, golden_root, cmd):
