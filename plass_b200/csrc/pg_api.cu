@@ -256,7 +256,7 @@ void pg_destroy(pg_context *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->small, &ctx->lists, &ctx->recA, &ctx->recB, &ctx->radixWs, &ctx->scratch, &ctx->blockCounts, &ctx->hits,
-                      &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta, &ctx->exLists, &ctx->ntTab, &ctx->buckets, &ctx->buckets2};
+                      &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta, &ctx->exLists, &ctx->ntTab, &ctx->buckets, &ctx->buckets2, &ctx->wideTabs};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
     cudaStreamSynchronize(ctx->copyStream);

@@ -29,7 +29,22 @@ struct KmConst {
     int includeOnlyExtendable;
     int covMode;
     float covThr;
+    // wide records (KmerPosition<int>, kmermatcher.cpp:797-802: any sequence of >= SHRT_MAX residues): the 16-byte record
+    // cannot hold id + seqLen + pos at full width, so it carries the sequence's RANK in (seqLen desc, id asc) order --
+    // exactly the part of sort #1's comparator between the k-mer and the position (kmermatcher.h:56-96) -- and a 32-bit
+    // position; id and seqLen are looked up from the rank where assignGroup needs them.
+    int wide;
+    const unsigned *rankOf;   // sequence index -> rank
+    const unsigned *byRank;   // rank -> sequence index
+    const unsigned *keys;     // DB keys / entry lengths by sequence index
+    const unsigned *lens;
 };
+
+// w1 of a k-mer record: narrow id<<32 | seqLen<<16 | pos; wide rank<<32 | pos
+__device__ __forceinline__ unsigned long long kmer_w1(const KmConst &c, unsigned id, unsigned si, unsigned seqLen, unsigned pos) {
+    if (c.wide) return ((unsigned long long) __ldg(c.rankOf + si) << 32) | (unsigned long long) pos;
+    return ((unsigned long long) id << 32) | ((unsigned long long) (seqLen & 0xFFFFu) << 16) | (pos & 0xFFFFu);
+}
 
 // One k-mer of a sequence while it is being selected (SequencePosition, kmermatcher.h:10-46).
 struct __align__(16) Cand {
@@ -90,7 +105,7 @@ __device__ __forceinline__ bool make_kmer(const unsigned char *codes, int pos, i
 // sorted[0..cnt) holds all k-mers of the sequence (or at least every k-mer with score <= t);
 // emits into outRecs (capacity >= kmerConsidered), returns the number emitted.
 __device__ int select_sequential(const Cand *sorted, int cnt, unsigned long long kmerConsidered, unsigned threshold, int tooMuch,
-                                 const KmConst &c, unsigned id, unsigned seqLen, Rec *outRecs) {
+                                 const KmConst &c, unsigned id, unsigned si, unsigned seqLen, Rec *outRecs) {
     int nOut = 0;
     unsigned long long selected = 0;
     for (int i = 0; i < cnt && selected < kmerConsidered; i++) {
@@ -118,7 +133,7 @@ __device__ int select_sequential(const Cand *sorted, int cnt, unsigned long long
             if (sc >= c.hashStart && sc <= c.hashEnd) {
                 Rec r;
                 r.w0 = sorted[i].kmer;
-                r.w1 = ((unsigned long long) id << 32) | ((unsigned long long) (seqLen & 0xFFFFu) << 16) | (sorted[i].pos & 0xFFFFu);
+                r.w1 = kmer_w1(c, id, si, seqLen, sorted[i].pos);
                 outRecs[nOut++] = r;
             }
         }
@@ -174,7 +189,7 @@ __device__ __forceinline__ bool pc_same_kmer(const PCand &a, const PCand &b) { r
 
 // The selection loop of kmermatcher.cpp:274-347 over packed candidates (slow path: duplicates present).
 __device__ int select_sequential_packed(const PCand *sorted, int cnt, unsigned long long kmerConsidered, unsigned threshold, int tooMuch,
-                                        const KmConst &c, unsigned id, unsigned seqLen, Rec *outRecs) {
+                                        const KmConst &c, unsigned id, unsigned si, unsigned seqLen, Rec *outRecs) {
     int nOut = 0;
     unsigned long long selected = 0;
     for (int i = 0; i < cnt && selected < kmerConsidered; i++) {
@@ -200,7 +215,7 @@ __device__ int select_sequential_packed(const PCand *sorted, int cnt, unsigned l
             if (sc >= c.hashStart && sc <= c.hashEnd) {
                 Rec r;
                 r.w0 = pc_kmer_stored(sorted[i], c.nt);
-                r.w1 = ((unsigned long long) id << 32) | ((unsigned long long) (seqLen & 0xFFFFu) << 16) | (pc_pos(sorted[i]) & 0xFFFFu);
+                r.w1 = kmer_w1(c, id, si, seqLen, pc_pos(sorted[i]));
                 outRecs[nOut++] = r;
             }
         }
@@ -362,7 +377,7 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
         // sequence-identity record first (:241-246)
         const unsigned sh16 = (unsigned) (seqHash & 0xFFFFULL);
         if (sh16 >= c.hashStart && sh16 <= c.hashEnd) {
-            if (lane == 0) { Rec r; r.w0 = seqHash; r.w1 = ((unsigned long long) id << 32) | ((unsigned long long) (L & 0xFFFF) << 16); outRecs[0] = r; }
+            if (lane == 0) { Rec r; r.w0 = seqHash; r.w1 = kmer_w1(c, id, si, (unsigned) L, 0u); outRecs[0] = r; }
             nOut = 1;
         }
         if (allDistinct) {
@@ -375,7 +390,7 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
                 if (emit) {
                     Rec r;
                     r.w0 = pc_kmer_stored(pc, c.nt);
-                    r.w1 = ((unsigned long long) id << 32) | ((unsigned long long) (L & 0xFFFF) << 16) | (pc_pos(pc) & 0xFFFFu);
+                    r.w1 = kmer_w1(c, id, si, (unsigned) L, pc_pos(pc));
                     outRecs[nOut + __popc(m & ltMask)] = r;
                 }
                 nOut += __popc(m);
@@ -409,14 +424,14 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
                         if (emit) {
                             Rec r;
                             r.w0 = pc_kmer_stored(pc, c.nt);
-                            r.w1 = ((unsigned long long) id << 32) | ((unsigned long long) (L & 0xFFFF) << 16) | (pc_pos(pc) & 0xFFFFu);
+                            r.w1 = kmer_w1(c, id, si, (unsigned) L, pc_pos(pc));
                             outRecs[nOut + __popc(m & ltMask)] = r;
                         }
                         nOut += __popc(m);
                     }
                 } else {
                     int add = 0;
-                    if (lane == 0) add = select_sequential_packed(cand, cnt, kmerConsidered, threshold, tooMuch, c, id, (unsigned) L, outRecs + nOut);
+                    if (lane == 0) add = select_sequential_packed(cand, cnt, kmerConsidered, threshold, tooMuch, c, id, si, (unsigned) L, outRecs + nOut);
                     nOut += __shfl_sync(0xFFFFFFFFu, add, 0);
                 }
             } else {
@@ -432,7 +447,7 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
                     }
                     int le = 0;
                     for (int i = 0; i < cnt; i++) le += (pc_score(cand[i]) <= lo);
-                    add = select_sequential_packed(cand, cnt, kmerConsidered, lo + 1, le - (int) kmerConsidered, c, id, (unsigned) L, outRecs + nOut);
+                    add = select_sequential_packed(cand, cnt, kmerConsidered, lo + 1, le - (int) kmerConsidered, c, id, si, (unsigned) L, outRecs + nOut);
                 }
                 nOut += __shfl_sync(0xFFFFFFFFu, add, 0);
             }
@@ -579,11 +594,11 @@ __global__ void __launch_bounds__(256) extract_block_kernel(const pg_seqdb db, c
         if (tid == 0) {
             int nOut = 0;
             if (emitIdentity) {
-                Rec r; r.w0 = seqHash; r.w1 = ((unsigned long long) id << 32) | ((unsigned long long) (L & 0xFFFF) << 16);
+                Rec r; r.w0 = seqHash; r.w1 = kmer_w1(c, id, si, (unsigned) L, 0u);
                 outRecs[nOut++] = r;
             }
             if (cnt > 0 && kmerConsidered > 0)
-                nOut += select_sequential(cand, inBins, kmerConsidered, threshold, sTooMuch, c, id, (unsigned) L, outRecs + nOut);
+                nOut += select_sequential(cand, inBins, kmerConsidered, threshold, sTooMuch, c, id, si, (unsigned) L, outRecs + nOut);
             sNOut = nOut;
             sBase = nOut ? atomicAdd(outCount, (unsigned long long) nOut) : 0ULL;
         }
@@ -632,6 +647,12 @@ __device__ __forceinline__ bool can_be_covered(float covThr, int covMode, float 
     }
 }
 
+// WIDE: records carry rank<<32 | pos (see KmConst); w1 itself is then the representative order, ids / lengths come from the
+// rank tables, nothing is truncated to 16 bits and the pair record holds a 32-bit biased diagonal with the strand in bit 32.
+template <bool WIDE>
+__device__ __forceinline__ unsigned long long rep_key_t(unsigned long long w1) { return WIDE ? w1 : rep_key(w1); }
+
+template <bool WIDE>
 __global__ void __launch_bounds__(GROUP_THREADS) group_kernel(const Rec *__restrict__ in, unsigned long long n, const KmConst c,
                                                               Rec *__restrict__ out, unsigned long long *__restrict__ outCount) {
     __shared__ Rec tile[GROUP_TILE];
@@ -664,7 +685,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) group_kernel(const Rec *__restr
             if (p >= 0) {
                 const Rec r = in[p];
                 same = cmp_kmer(r.w0, nt) == k0;
-                key = rep_key(r.w1); st = (unsigned) (r.w0 >> 63);
+                key = rep_key_t<WIDE>(r.w1); st = (unsigned) (r.w0 >> 63);
             }
             const unsigned m = __ballot_sync(0xFFFFFFFFu, same);
             // records are contiguous: count matches from lane 0 upwards until the first mismatch
@@ -696,7 +717,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) group_kernel(const Rec *__restr
             if (p < n) {
                 const Rec r = in[p];
                 same = cmp_kmer(r.w0, nt) == k1;
-                key = rep_key(r.w1); st = (unsigned) (r.w0 >> 63);
+                key = rep_key_t<WIDE>(r.w1); st = (unsigned) (r.w0 >> 63);
             }
             const unsigned m = __ballot_sync(0xFFFFFFFFu, same);
             const unsigned firstMiss = __ffs(~m);
@@ -741,7 +762,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) group_kernel(const Rec *__restr
             const unsigned long long km = cmp_kmer(tile[i].w0, nt);
             int j = i;
             while (j < count && cmp_kmer(tile[j].w0, nt) == km) {
-                acc_add(a, rep_key(tile[j].w1), (unsigned) (tile[j].w0 >> 63), 1);
+                acc_add(a, rep_key_t<WIDE>(tile[j].w1), (unsigned) (tile[j].w0 >> 63), 1);
                 j++;
             }
             if (i == 0) acc_add(a, sBack.key, sBack.strand, sBack.count);
@@ -763,12 +784,19 @@ __global__ void __launch_bounds__(GROUP_THREADS) group_kernel(const Rec *__restr
             const GroupAcc a = gacc[h];
             if (a.count >= 2) {
                 const Rec r = tile[i];
-                const unsigned repId = (unsigned) ((a.key >> 16) & 0xFFFFFFFFULL);
-                const int queryLen = (int) (0xFFFFULL ^ (a.key >> 48));
-                const int repPos = (int) (short) (a.key & 0xFFFFULL);
-                const unsigned tId = (unsigned) (r.w1 >> 32);
-                const int tLen = (int) (short) ((r.w1 >> 16) & 0xFFFFULL);
-                const int tPos = (int) (short) (r.w1 & 0xFFFFULL);
+                unsigned repId, tId; int queryLen, repPos, tLen, tPos;
+                if constexpr (WIDE) {
+                    const unsigned qi = __ldg(c.byRank + (unsigned) (a.key >> 32)), ti = __ldg(c.byRank + (unsigned) (r.w1 >> 32));
+                    repId = __ldg(c.keys + qi); queryLen = (int) __ldg(c.lens + qi) - 2; repPos = (int) (unsigned) (a.key & 0xFFFFFFFFULL);
+                    tId = __ldg(c.keys + ti); tLen = (int) __ldg(c.lens + ti) - 2; tPos = (int) (unsigned) (r.w1 & 0xFFFFFFFFULL);
+                } else {
+                    repId = (unsigned) ((a.key >> 16) & 0xFFFFFFFFULL);
+                    queryLen = (int) (0xFFFFULL ^ (a.key >> 48));
+                    repPos = (int) (short) (a.key & 0xFFFFULL);
+                    tId = (unsigned) (r.w1 >> 32);
+                    tLen = (int) (short) ((r.w1 >> 16) & 0xFFFFULL);
+                    tPos = (int) (short) (r.w1 & 0xFFFFULL);
+                }
                 int diagonal = repPos - tPos;
                 unsigned qRev = 0;
                 if (nt) {
@@ -778,9 +806,10 @@ __global__ void __launch_bounds__(GROUP_THREADS) group_kernel(const Rec *__restr
                     const bool targetIsReverse = ((r.w0 >> 63) == 0);
                     int queryPos, targetPos;
                     if (repIsReverse && !targetIsReverse) { queryPos = repPos; targetPos = tPos; qRev = 1; }
-                    else if (repIsReverse && targetIsReverse) { queryPos = (short) ((queryLen - 1) - repPos); targetPos = (short) ((tLen - 1) - tPos); qRev = 0; }
-                    else if (!repIsReverse && targetIsReverse) { queryPos = (short) ((queryLen - 1) - repPos); targetPos = (short) ((tLen - 1) - tPos); qRev = 1; }
+                    else if (repIsReverse && targetIsReverse) { queryPos = (queryLen - 1) - repPos; targetPos = (tLen - 1) - tPos; qRev = 0; }
+                    else if (!repIsReverse && targetIsReverse) { queryPos = (queryLen - 1) - repPos; targetPos = (tLen - 1) - tPos; qRev = 1; }
                     else { queryPos = repPos; targetPos = tPos; qRev = 0; }
+                    if (!WIDE) { queryPos = (short) queryPos; targetPos = (short) targetPos; }   // T = short arithmetic (a no-op for in-range values)
                     diagonal = queryPos - targetPos;
                 }
                 const bool canBeExtended = diagonal < 0 || (diagonal > (queryLen - tLen));
@@ -788,8 +817,12 @@ __global__ void __launch_bounds__(GROUP_THREADS) group_kernel(const Rec *__restr
                 keep = (c.includeOnlyExtendable == 0 && covered) || (canBeExtended && c.includeOnlyExtendable != 0);
                 if (keep) {
                     outRec[it].w0 = ((unsigned long long) repId << 32) | tId;
-                    const unsigned biased = (unsigned) (((int) (short) diagonal) + 32768) & 0xFFFFu;
-                    outRec[it].w1 = ((unsigned long long) qRev << 16) | biased;
+                    if constexpr (WIDE) {
+                        outRec[it].w1 = ((unsigned long long) qRev << 32) | (unsigned long long) ((unsigned) diagonal + 0x80000000u);
+                    } else {
+                        const unsigned biased = (unsigned) (((int) (short) diagonal) + 32768) & 0xFFFFu;
+                        outRec[it].w1 = ((unsigned long long) qRev << 16) | biased;
+                    }
                 }
             }
         }
@@ -1007,19 +1040,24 @@ __global__ void __launch_bounds__(HG_THREADS) hash_group_kernel(const Rec *__res
 // A run starts where rep or target changes; the scan over the run continues while the TARGET id stays
 // the same even across a rep boundary (the reference's while-loop at :880 only tests the id).
 // ------------------------------------------------------------------------------------------------
+// WIDE pair records: 32-bit biased diagonal in w1 bits 0..31, strand in bit 32 (narrow: 16 bits, strand in bit 16)
+template <bool WIDE> __device__ __forceinline__ unsigned pair_diag(unsigned long long w1) { return WIDE ? (unsigned) w1 : (unsigned) (w1 & 0xFFFFu); }
+template <bool WIDE> __device__ __forceinline__ unsigned pair_rev(unsigned long long w1) { return (unsigned) (w1 >> (WIDE ? 32 : 16)) & 1u; }
+
+template <bool WIDE>
 __device__ __forceinline__ bool reduce_one(const Rec *__restrict__ in, unsigned long long n, unsigned long long i, pg_hit &h) {
     const Rec r = in[i];
     if (i > 0 && in[i - 1].w0 == r.w0) return false;            // not the first record of (rep, target)
     const unsigned rep = (unsigned) (r.w0 >> 32), target = (unsigned) r.w0;
-    unsigned diagB = (unsigned) (r.w1 & 0xFFFFu), prevDiag = diagB;
-    unsigned best = diagB, bestRev = (unsigned) ((r.w1 >> 16) & 1u);
+    unsigned diagB = pair_diag<WIDE>(r.w1), prevDiag = diagB;
+    unsigned best = diagB, bestRev = pair_rev<WIDE>(r.w1);
     unsigned maxDiag = 0, diagCnt = 0, top = 0, revCnt = 0;
     unsigned long long j = i;
     while (j < n) {
         const Rec q = in[j];
         if ((unsigned) q.w0 != target) break;
-        const unsigned d = (unsigned) (q.w1 & 0xFFFFu);
-        const unsigned rv = (unsigned) ((q.w1 >> 16) & 1u);
+        const unsigned d = pair_diag<WIDE>(q.w1);
+        const unsigned rv = pair_rev<WIDE>(q.w1);
         if (prevDiag == d) { diagCnt++; revCnt += rv; } else { diagCnt = 1; revCnt = rv; }
         // nt: records that agree on (rep, target, diagonal) but not on the strand flag have no defined order in the
         // reference (unstable ips4o sort): it reports the flag of whichever record ends up last.
@@ -1033,25 +1071,28 @@ __device__ __forceinline__ bool reduce_one(const Rec *__restrict__ in, unsigned 
     if (target == rep) return false;                             // :899-904
     h.rep = rep; h.target = target;
     h.score = bestRev ? -(int) top : (int) top;
-    h.diag = (int) (short) (unsigned short) (best - 32768u);
+    // hit_t::diagonal is an unsigned short printed as a short (QueryMatcher.h:35-51): the low 16 bits of the diagonal
+    h.diag = (int) (short) (unsigned short) (WIDE ? (best - 0x80000000u) : (best - 32768u));
     return true;
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(256) reduce_count_kernel(const Rec *__restrict__ in, unsigned long long n, unsigned *__restrict__ blockCounts) {
     const unsigned long long i = (unsigned long long) blockIdx.x * 256 + threadIdx.x;
     pg_hit h;
-    const bool emit = (i < n) && reduce_one(in, n, i, h);
+    const bool emit = (i < n) && reduce_one<WIDE>(in, n, i, h);
     const unsigned c = __syncthreads_count(emit);
     if (threadIdx.x == 0) blockCounts[blockIdx.x] = c;
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(256) reduce_emit_kernel(const Rec *__restrict__ in, unsigned long long n,
                                                           const unsigned long long *__restrict__ blockOffsets, pg_hit *__restrict__ hits) {
     __shared__ unsigned sWarp[8];
     const unsigned long long i = (unsigned long long) blockIdx.x * 256 + threadIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     pg_hit h;
-    const bool emit = (i < n) && reduce_one(in, n, i, h);
+    const bool emit = (i < n) && reduce_one<WIDE>(in, n, i, h);
     const unsigned m = __ballot_sync(0xFFFFFFFFu, emit);
     if (lane == 0) sWarp[w] = __popc(m);
     __syncthreads();
@@ -1654,7 +1695,6 @@ int km_setup_constants(const pg_seqdb *db, const pg_km_params *p, KmConst &c, cu
     const bool nt = db->dbtype == PG_DBTYPE_NUCLEOTIDES;
     PG_CHECK(p->kmer_size >= 2 && p->kmer_size <= (nt ? 31 : 14), "kmermatcher: unsupported k (aa: 2..14 in base-(alph-1) < 2^63, nt: 2..31)");
     PG_CHECK(nt || p->alph_size == 13 || p->alph_size == 21, "kmermatcher: --alph-size must be 13 or 21 for amino acids");
-    PG_CHECK(db->max_seq_len < 32767, "kmermatcher: sequences >= 32767 residues need the wide (T=int) record layout, which is not built yet");
     const unsigned char *tab = nt ? PG_NT_AA2NUM : (p->alph_size == 21 ? PG_AA_AA2NUM : PG_RED_AA2NUM);
     PG_CUDA(cudaMemcpyToSymbolAsync(c_aa2num, tab, 256, 0, cudaMemcpyHostToDevice, stream));
     c.k = p->kmer_size; c.nt = nt ? 1 : 0;
@@ -1666,6 +1706,52 @@ int km_setup_constants(const pg_seqdb *db, const pg_km_params *p, KmConst &c, cu
     c.hashStart = p->hash_start; c.hashEnd = p->hash_end;
     c.includeOnlyExtendable = p->include_only_extendable;
     c.covMode = p->cov_mode; c.covThr = p->cov_thr;
+    c.wide = 0; c.rankOf = nullptr; c.byRank = nullptr; c.keys = db->keys; c.lens = db->lens;
+    return 0;
+}
+
+// kmermatcher.cpp:797-802: KmerPosition<short> iff DBReader::getMaxSeqLen() < SHRT_MAX, and getMaxSeqLen is the longest
+// ENTRY (residues + "\n\0", DBReader.cpp:811), i.e. seqLen + 2.
+static bool km_is_wide(const pg_seqdb *db) { return db->max_seq_len + 2 >= 32767u; }
+
+// rank tables of the wide layout: sequences ordered by (seqLen desc, key asc)
+static __global__ void wide_rank_keys_kernel(const unsigned *__restrict__ lens, const unsigned *__restrict__ keys, unsigned n, Rec *__restrict__ out) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Rec r;
+        r.w0 = ((unsigned long long) (0xFFFFFFFFu - (lens[i] - 2u)) << 32) | keys[i];
+        r.w1 = i;
+        out[i] = r;
+    }
+}
+static __global__ void wide_rank_tables_kernel(const Rec *__restrict__ sorted, unsigned n, unsigned *__restrict__ rankOf, unsigned *__restrict__ byRank) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned si = (unsigned) sorted[i].w1;
+        byRank[i] = si;
+        rankOf[si] = i;
+    }
+}
+
+static int km_prepare_wide(Context *ctx, const pg_seqdb *db, KmConst &c) {
+    if (!km_is_wide(db)) return 0;
+    cudaStream_t s = ctx->stream;
+    const unsigned n = (unsigned) db->n;
+    PG_CHECK(ctx->seqLo == 0 && ctx->seqHi >= n && ctx->ownLo == 0 && ctx->ownHi == 0xFFFFFFFFu,
+             "kmermatcher: the wide (T=int) record layout is single-GPU only for now");
+    PG_TRY(ctx->wideTabs.reserve(sizeof(unsigned) * 2 * ((size_t) n + 1)));
+    PG_TRY(ctx->recA.reserve(sizeof(Rec) * ((size_t) n + 1)));
+    PG_TRY(ctx->recB.reserve(sizeof(Rec) * ((size_t) n + 1)));
+    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(n)));
+    unsigned *rankOf = ctx->wideTabs.as<unsigned>(), *byRank = rankOf + n + 1;
+    wide_rank_keys_kernel<<<NUM_SMS * 4, 256, 0, s>>>(db->lens, db->keys, n, ctx->recA.as<Rec>());
+    RadixPlan plan; plan.npasses = 0;
+    plan_add_bits(plan, 0, 0, 64);
+    Rec *sorted = nullptr;
+    PG_TRY(radix_sort(ctx->recA.as<Rec>(), ctx->recB.as<Rec>(), n, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches));
+    wide_rank_tables_kernel<<<NUM_SMS * 4, 256, 0, s>>>(sorted, n, rankOf, byRank);
+    ctx->launches += 2;
+    PG_CUDA(cudaStreamSynchronize(s));      // recA / recB may be re-allocated by the extraction that follows
+    PG_CUDA(cudaGetLastError());
+    c.wide = 1; c.rankOf = rankOf; c.byRank = byRank;
     return 0;
 }
 
@@ -1819,7 +1905,7 @@ int km_group(Context *ctx, const pg_seqdb *db, const KmConst &c, uint64_t nRecor
     cudaStream_t s = ctx->stream;
     *nPairs = 0;
     if (nRecords == 0) return 0;
-    if (!ctx->forceFullSort) {
+    if (!ctx->forceFullSort && !c.wide) {
         bool ok = false;
         PG_TRY(km_group_bucketed(ctx, c, nRecords, nPairs, &ok));
         if (ok) return 0;
@@ -1837,7 +1923,8 @@ int km_group(Context *ctx, const pg_seqdb *db, const KmConst &c, uint64_t nRecor
     unsigned long long *d_cnt = ctx->small.as<unsigned long long>() + 2;
     PG_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
     const unsigned blocks = (unsigned) ((nRecords + GROUP_TILE - 1) / GROUP_TILE);
-    group_kernel<<<blocks, GROUP_THREADS, 0, s>>>(sorted, nRecords, c, outBuf, d_cnt);
+    if (c.wide) group_kernel<true><<<blocks, GROUP_THREADS, 0, s>>>(sorted, nRecords, c, outBuf, d_cnt);
+    else group_kernel<false><<<blocks, GROUP_THREADS, 0, s>>>(sorted, nRecords, c, outBuf, d_cnt);
     ctx->launches++;
     cudaEventRecord(ctx->ev[EV_GROUP_END], s);
     unsigned long long h = 0;
@@ -1920,14 +2007,15 @@ int km_reduce(Context *ctx, const pg_seqdb *db, Rec *pairs, Rec *tmp, uint64_t n
     cudaStream_t s = ctx->stream;
     *nHits = 0; *d_hits = nullptr;
     if (nPairs == 0) return 0;
-    if (!ctx->forceFullSort) {
+    const bool wide = km_is_wide(db);
+    if (!ctx->forceFullSort && !wide) {
         bool ok = false;
         PG_TRY(km_reduce_segmented(ctx, db, &pairs, &tmp, nPairs, d_hits, nHits, &ok));
         if (ok) return 0;
     }
     const int keyBits = bits_for(db->max_key);
     RadixPlan plan; plan.npasses = 0;
-    plan_add_bits(plan, 1, 0, 16);                 // diagonal (biased so that the signed order is kept)
+    plan_add_bits(plan, 1, 0, wide ? 32 : 16);     // diagonal (biased so that the signed order is kept)
     plan_add_bits(plan, 0, 0, keyBits);            // target id
     plan_add_bits(plan, 0, 32, 32 + keyBits);      // representative
     PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nPairs)));
@@ -1939,14 +2027,16 @@ int km_reduce(Context *ctx, const pg_seqdb *db, Rec *pairs, Rec *tmp, uint64_t n
     unsigned *d_counts = ctx->blockCounts.as<unsigned>();
     unsigned long long *d_offsets = (unsigned long long *) (ctx->blockCounts.as<unsigned char>() + ((sizeof(unsigned) * blocks + 15) & ~(size_t) 15));
     unsigned long long *d_total = ctx->small.as<unsigned long long>() + 3;
-    reduce_count_kernel<<<(unsigned) blocks, 256, 0, s>>>(sorted, nPairs, d_counts);
+    if (wide) reduce_count_kernel<true><<<(unsigned) blocks, 256, 0, s>>>(sorted, nPairs, d_counts);
+    else reduce_count_kernel<false><<<(unsigned) blocks, 256, 0, s>>>(sorted, nPairs, d_counts);
     scan_counts_kernel<<<1, 1024, 0, s>>>(d_counts, blocks, d_offsets, d_total);
     unsigned long long h = 0;
     PG_CUDA(cudaMemcpyAsync(&h, d_total, sizeof(h), cudaMemcpyDeviceToHost, s));
     PG_CUDA(cudaStreamSynchronize(s));
     PG_TRY(ctx->hits.reserve(sizeof(pg_hit) * (h + 1)));
     PG_CUDA(cudaStreamWaitEvent(s, ctx->evHitsCopied, 0));
-    reduce_emit_kernel<<<(unsigned) blocks, 256, 0, s>>>(sorted, nPairs, d_offsets, ctx->hits.as<pg_hit>());
+    if (wide) reduce_emit_kernel<true><<<(unsigned) blocks, 256, 0, s>>>(sorted, nPairs, d_offsets, ctx->hits.as<pg_hit>());
+    else reduce_emit_kernel<false><<<(unsigned) blocks, 256, 0, s>>>(sorted, nPairs, d_offsets, ctx->hits.as<pg_hit>());
     ctx->launches += 3;
     cudaEventRecord(ctx->ev[EV_REDUCE_END], s);
     PG_CUDA(cudaGetLastError());
@@ -1962,6 +2052,7 @@ int km_run(Context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **d_h
     PG_TRY(km_setup_constants(db, p, c, s));
     cudaEventRecord(ctx->ev[EV_KM_BEGIN], s);
     uint64_t nRec = 0, nPairs = 0;
+    PG_TRY(km_prepare_wide(ctx, db, c));
     PG_TRY(km_extract(ctx, db, p, c, &nRec));
     cudaEventRecord(ctx->ev[EV_EXTRACT_END], s);
     PG_TRY(km_group(ctx, db, c, nRec, &nPairs));
@@ -2077,6 +2168,7 @@ static void record_empty_group_events(Context *ctx) {
 
 int km_shard_pairs(Context *ctx, const pg_seqdb *db, const pg_km_params *p, int world, uint64_t *counts) {
     PG_CHECK(world >= 1 && world <= 256, "pg_shard_pairs: world size must be in [1, 256]");
+    PG_CHECK(!km_is_wide(db), "multi-GPU kmermatcher: sequences >= 32765 residues (wide T=int records) are single-GPU only for now");
     KmConst c;
     cudaStream_t s = ctx->stream;
     PG_TRY(km_setup_constants(db, p, c, s));
@@ -2100,6 +2192,7 @@ int km_shard_pairs(Context *ctx, const pg_seqdb *db, const pg_km_params *p, int 
 // partition under which equal k-mers meet is equivalent; this one is independent of the bucket bits of the hash join.
 int km_shard_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, int rank, int world, uint64_t *counts) {
     PG_CHECK(world >= 1 && world <= 256 && rank >= 0 && rank < world, "pg_shard_extract: bad rank / world size");
+    PG_CHECK(!km_is_wide(db), "multi-GPU kmermatcher: sequences >= 32765 residues (wide T=int records) are single-GPU only for now");
     KmConst c;
     cudaStream_t s = ctx->stream;
     PG_TRY(km_setup_constants(db, p, c, s));
@@ -2132,6 +2225,7 @@ int km_shard_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, in
 // phase 1: the k-mer records this rank received (every record of the k-mers it owns) -> sort #1 + group -> pair
 // records (left on the device for pg_shard_route) and their histogram over the representative key space
 int km_shard_group(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const void *d_records, uint64_t nRec, uint64_t *hist) {
+    PG_CHECK(!km_is_wide(db), "multi-GPU kmermatcher: sequences >= 32765 residues (wide T=int records) are single-GPU only for now");
     KmConst c;
     cudaStream_t s = ctx->stream;
     PG_TRY(km_setup_constants(db, p, c, s));
