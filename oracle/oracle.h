@@ -124,6 +124,17 @@ double or_evalue(int nt, double db_residues, double score, double q_len);
 double or_bitscore(int nt, double score);
 double or_raw_from_bits(int nt, double bits);
 
+/* ---- components ranked "next" in SURVEY.md section 8(f) (oracle_next.cpp) ---- */
+
+/* findassemblystart (src/assembler/findassemblystart.cpp:35-176): alns = alignment DB of db against itself, ordered by
+ * query.  Output DB in key order; add_stop[i] = position the new '*' precedes in sequence i, or -1. */
+int or_findstart(const or_seqdb *db, const or_aln *alns, uint64_t n_alns,
+                 char **out_data, uint64_t **out_offsets, uint32_t **out_lens, uint32_t **out_keys,
+                 uint64_t *out_n, uint64_t *out_bytes, int32_t **add_stop);
+
+/* cyclecheck (src/assembler/cyclecheck.cpp:71-274): split[i] (caller-allocated, db->n) = splitDiagonal or 0. */
+int or_cyclecheck(const or_seqdb *db, int max_seq_len, int kmer_size, uint32_t *split);
+
 void or_free(void *p);
 
 #ifdef __cplusplus

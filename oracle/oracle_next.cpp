@@ -1,0 +1,245 @@
+/* oracle_next.cpp -- CPU restatement of the components SURVEY.md section 8(f) ranks "next" to the hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle.h).  Scalar, single-threaded, statement-for-statement restatements of
+ *
+ *   or_findstart   findassemblystart        src/assembler/findassemblystart.cpp:35-176
+ *   or_cyclecheck  cyclecheck               src/assembler/cyclecheck.cpp:71-274
+ *
+ * Parity status: PINNED -- tests/test_oracle_vs_reference.py checks both against DBs written by the unmodified
+ * reference binary (tests/golden/{example_aa,synth_aa}: aln_0 -> corrected_seqs; tests/golden/{synth_nt,long_nt}:
+ * assembly_N -> assembly_N_noneCycle / assembly_N_cycle).
+ */
+#include "oracle.h"
+#include "oracle_tables.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+// DBReader::getId (binary search in the key-sorted index); UINT64_MAX if absent
+uint64_t idOfKey(const or_seqdb *db, uint32_t key) {
+    uint64_t lo = 0, hi = db->n;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) / 2;
+        if (db->keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return (lo < db->n && db->keys[lo] == key) ? lo : UINT64_MAX;
+}
+
+// findassemblystart.cpp:12-23
+int findPosOfM(const char *seq) {
+    int pos = 0;
+    while (seq[pos] != '\0') {
+        if (seq[pos] == 'M') return pos;
+        pos++;
+    }
+    return -1;
+}
+
+struct PositionOfM {     // findassemblystart.cpp:25-33
+    uint64_t id;
+    int mPos;
+    bool hasM;
+    bool hasStopM;
+};
+
+void emitDb(const std::vector<std::string> &entries, const or_seqdb *db, char **out_data, uint64_t **out_offsets,
+            uint32_t **out_lens, uint32_t **out_keys, uint64_t *out_n, uint64_t *out_bytes,
+            const std::vector<uint64_t> &ids) {
+    std::string all;
+    const uint64_t n = ids.size();
+    uint64_t *offs = (uint64_t *) malloc(sizeof(uint64_t) * (n + 1));
+    uint32_t *lens = (uint32_t *) malloc(sizeof(uint32_t) * (n + 1));
+    uint32_t *keys = (uint32_t *) malloc(sizeof(uint32_t) * (n + 1));
+    for (uint64_t w = 0; w < n; w++) {
+        offs[w] = all.size();
+        all.append(entries[w]);
+        lens[w] = (uint32_t) entries[w].size();
+        keys[w] = db->keys[ids[w]];
+    }
+    *out_data = (char *) malloc(all.size() + 1);
+    memcpy(*out_data, all.data(), all.size());
+    *out_offsets = offs; *out_lens = lens; *out_keys = keys; *out_n = n; *out_bytes = all.size();
+}
+
+}  // namespace
+
+/* findassemblystart (src/assembler/findassemblystart.cpp:35-176).  alns = the alignment DB of the same sequence DB
+ * (query == target DB), ordered by query key, lines in DB order.  add_stop[i] (by sequence index) = the position the
+ * new '*' is put in front of, or -1.  Output entries: unchanged, or "*" + residues[mPos..] + "\n\0" (:150-160). */
+extern "C" int or_findstart(const or_seqdb *db, const or_aln *alns, uint64_t n_alns,
+                            char **out_data, uint64_t **out_offsets, uint32_t **out_lens, uint32_t **out_keys,
+                            uint64_t *out_n, uint64_t *out_bytes, int32_t **add_stop) {
+    std::vector<int> addStopAtPosition(db->n, -1);
+    const float threshold = 0.2;
+    std::vector<PositionOfM> stopPositions;
+    uint64_t ap = 0;
+    while (ap < n_alns) {
+        const uint32_t queryKey = alns[ap].query;
+        uint64_t ae = ap;
+        while (ae < n_alns && alns[ae].query == queryKey) ae++;
+        const uint64_t qId = idOfKey(db, queryKey);
+        if (qId == UINT64_MAX) return -1;
+        const char *querySeqData = db->data + db->offsets[qId];
+        const int queryPosOfM = findPosOfM(querySeqData);
+        if (queryPosOfM == -1) { ap = ae; continue; }
+        bool qStopM = false;
+        if (queryPosOfM > 0) qStopM = querySeqData[queryPosOfM - 1] == '*';
+        stopPositions.clear();
+        stopPositions.push_back(PositionOfM{qId, queryPosOfM, true, qStopM});
+        for (uint64_t a = ap; a < ae; a++) {
+            const uint64_t edgeId = idOfKey(db, alns[a].target);
+            if (edgeId == UINT64_MAX) return -1;
+            if (edgeId == qId) continue;
+            const or_aln &res = alns[a];
+            const char *dbSeqData = db->data + db->offsets[edgeId];
+            int posOfM = -1;
+            bool hasM = false, hasStopM = false;
+            if (res.q_start >= queryPosOfM && queryPosOfM <= res.q_end) {     // :103 (sic)
+                int queryMoffset = queryPosOfM - res.q_start;
+                int dbMPos = res.db_start + queryMoffset;
+                posOfM = dbMPos;
+                hasM = dbMPos >= 0 && (dbSeqData[dbMPos] == 'M');
+                if (dbMPos > 0 && hasM) hasStopM = dbSeqData[dbMPos - 1] == '*';
+            }
+            stopPositions.push_back(PositionOfM{edgeId, posOfM, hasM, hasStopM});
+        }
+        int stopMCount = 0;
+        for (size_t i = 0; i < stopPositions.size(); i++) stopMCount += stopPositions[i].hasStopM;
+        if (stopPositions.size() > 1) {
+            const float frequency = static_cast<float>(stopMCount) / static_cast<float>(stopPositions.size());
+            if (frequency >= threshold) {
+                for (size_t i = 0; i < stopPositions.size(); i++) {
+                    int &t = addStopAtPosition[stopPositions[i].id];
+                    if (t < stopPositions[i].mPos) t = stopPositions[i].mPos;      // the CAS loop of :125-131 = atomic max
+                }
+            }
+        }
+        ap = ae;
+    }
+    std::vector<std::string> entries(db->n);
+    std::vector<uint64_t> ids(db->n);
+    for (uint64_t id = 0; id < db->n; id++) {
+        ids[id] = id;
+        const char *q = db->data + db->offsets[id];
+        const int mPos = addStopAtPosition[id];
+        if (mPos == -1) {
+            entries[id].assign(q, db->lens[id] - 1);      // getEntryLen - 1 bytes, writeData appends '\0'
+        } else {
+            entries[id] = "*";
+            entries[id].append(q + mPos);                 // up to the entry's '\0': residues + '\n'
+        }
+        entries[id].push_back('\0');
+    }
+    emitDb(entries, db, out_data, out_offsets, out_lens, out_keys, out_n, out_bytes, ids);
+    int32_t *as = (int32_t *) malloc(sizeof(int32_t) * (db->n + 1));
+    for (uint64_t id = 0; id < db->n; id++) as[id] = addStopAtPosition[id];
+    *add_stop = as;
+    return 0;
+}
+
+/* cyclecheck (src/assembler/cyclecheck.cpp:71-274), k = 22 (setCycleCheckDefaults :26-29; -k is not a cyclecheck flag).
+ * split[i] = splitDiagonal of sequence i (0 = not reported).  The output DB holds the reported sequences only:
+ * chop_cycle ? residues[0 .. splitDiagonal) + "\n\0" : the entry unchanged (:249-259). */
+extern "C" int or_cyclecheck(const or_seqdb *db, int max_seq_len, int kmer_size, uint32_t *split) {
+    if (db->dbtype != 1) return -1;
+    // NucleotideMatrix aa2num (mm/commons/NucleotideMatrix.cpp:17-61), dumped from the reference's own object
+    const unsigned char *aa2num = OR_NT_AA2NUM;
+    const size_t kmerSize = (size_t) kmer_size;
+    // Indexer(alphabetSize - 1 = 4, kmerSize): powers[i] = 4^i (mm/prefiltering/Indexer.cpp:4-21)
+    std::vector<uint64_t> powers(kmerSize);
+    { uint64_t pw = 1; for (size_t i = 0; i < kmerSize; i++) { powers[i] = pw; pw *= 4; } }
+    struct kmerSeqPos { uint64_t kmer; unsigned int pos; };
+    auto cmp = [](const kmerSeqPos &a, const kmerSeqPos &b) { if (a.kmer != b.kmer) return a.kmer < b.kmer; return a.pos < b.pos; };
+    std::vector<kmerSeqPos> frontKmers, middleKmers, backKmers;
+    std::vector<unsigned int> diagHits;
+    std::vector<unsigned char> num;
+    for (uint64_t id = 0; id < db->n; id++) {
+        split[id] = 0;
+        const char *nuclSeq = db->data + db->offsets[id];
+        const unsigned int seqLen = db->lens[id] - 2;
+        if (seqLen >= (unsigned int) max_seq_len) continue;                      // :107-112
+        // Sequence::mapSequence (mm/commons/Sequence.cpp:476-489): stops at '\0' / '\n'
+        num.assign(seqLen, 0);
+        unsigned int L = 0;
+        while (L < seqLen && nuclSeq[L] != '\0' && nuclSeq[L] != '\n') { num[L] = aa2num[(unsigned char) nuclSeq[L]]; L++; }
+        frontKmers.clear(); middleKmers.clear(); backKmers.clear();
+        const unsigned int thirdSeqLen = seqLen / 3;
+        // Sequence::hasNextKmer / nextKmer (mm/commons/Sequence.h:98-114): currItPos starts at -1; note that `pos` is read
+        // BEFORE nextKmer advances it (:124), i.e. it is the window position minus one, 0xFFFFFFFF for the first window.
+        int currItPos = -1;
+        while ((size_t) (currItPos + 1) + kmerSize <= (size_t) L) {
+            unsigned int pos = (unsigned int) currItPos;
+            currItPos++;
+            uint64_t kmerIdx = 0;
+            for (size_t i = 0; i < kmerSize; i++) kmerIdx += num[currItPos + i] * powers[i];
+            kmerSeqPos e; e.kmer = kmerIdx; e.pos = (unsigned int) currItPos;
+            if (pos < thirdSeqLen + 1) frontKmers.push_back(e);
+            else if (pos < 2 * thirdSeqLen + 1) middleKmers.push_back(e);
+            else backKmers.push_back(e);
+        }
+        std::sort(frontKmers.begin(), frontKmers.end(), cmp);
+        std::sort(middleKmers.begin(), middleKmers.end(), cmp);
+        std::sort(backKmers.begin(), backKmers.end(), cmp);
+        const unsigned int frontKmersCount = frontKmers.size(), middleKmersCount = middleKmers.size(), backKmersCount = backKmers.size();
+        unsigned int kmermatches = 0;
+        diagHits.assign(2 * (size_t) thirdSeqLen + 1, 0);
+        unsigned int idx = 0, jdx = 0, kdx = 0;
+        while (idx < frontKmersCount && (jdx < backKmersCount || kdx < middleKmersCount)) {      // :150-186
+            uint64_t kmerIdx = frontKmers[idx].kmer;
+            unsigned int pos = frontKmers[idx].pos;
+            while (jdx < backKmersCount && backKmers[jdx].kmer < kmerIdx) jdx++;
+            while (kdx < middleKmersCount && middleKmers[kdx].kmer < kmerIdx) kdx++;
+            while (jdx < backKmersCount && kmerIdx == backKmers[jdx].kmer) {
+                int diag = backKmers[jdx].pos - pos;
+                if (diag >= static_cast<int>(seqLen / 3)) { diagHits[diag - seqLen / 3]++; kmermatches++; }
+                jdx++;
+            }
+            while (kdx < middleKmersCount && kmerIdx == middleKmers[kdx].kmer) {
+                int diag = middleKmers[kdx].pos - pos;
+                if (diag >= static_cast<int>(seqLen / 3)) { diagHits[diag - seqLen / 3]++; kmermatches++; }
+                kdx++;
+            }
+            idx++;
+            while (idx < frontKmersCount && kmerIdx == frontKmers[idx].kmer) idx++;
+        }
+        jdx = 0, kdx = 0;
+        while (kdx < middleKmersCount && jdx < backKmersCount) {                                   // :189-213
+            if (middleKmers[kdx].kmer < backKmers[jdx].kmer) kdx++;
+            else if (middleKmers[kdx].kmer > backKmers[jdx].kmer) jdx++;
+            else {
+                uint64_t kmerIdx = middleKmers[kdx].kmer;
+                unsigned int pos = middleKmers[kdx].pos;
+                while (jdx < backKmersCount && kmerIdx == backKmers[jdx].kmer) {
+                    int diag = backKmers[jdx].pos - pos;
+                    if (diag >= static_cast<int>(seqLen / 3)) { diagHits[diag - seqLen / 3]++; kmermatches++; }
+                    jdx++;
+                }
+                while (kdx < middleKmersCount && kmerIdx == middleKmers[kdx].kmer) kdx++;
+            }
+        }
+        unsigned int splitDiagonal = 0;
+        if (kmermatches > 0) {                                                                     // :238-262
+            for (unsigned int d = 0; d < 2 * thirdSeqLen; d++) {
+                if (diagHits[d] != 0) {
+                    unsigned int diag = d + thirdSeqLen;
+                    unsigned int diaglen = seqLen - diag;
+                    unsigned int gapwindow = diaglen * 0.01;
+                    unsigned int lower = std::max(0, static_cast<int>(d - gapwindow));
+                    unsigned int upper = std::min(d + gapwindow, 2 * thirdSeqLen);
+                    unsigned int diagbandHits = 0;
+                    for (size_t i = lower; i <= upper; i++)
+                        if (diagHits[i] <= diagHits[d]) diagbandHits += diagHits[i];
+                    float diagbandHitRate = static_cast<float>(diagbandHits) / (diaglen - kmerSize + 1);
+                    if (diagbandHitRate > 0.2) { splitDiagonal = diag; break; }
+                }
+            }
+        }
+        split[id] = splitDiagonal;
+    }
+    return 0;
+}

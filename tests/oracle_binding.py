@@ -41,11 +41,11 @@ assert KMER_REC.itemsize == 24 and HIT.itemsize == 16 and ALN.itemsize == 48
 
 
 def build():
-    src = os.path.join(ORACLE_DIR, "oracle.cpp")
-    deps = [src, os.path.join(ORACLE_DIR, "oracle.h"), os.path.join(ORACLE_DIR, "oracle_tables.h")]
+    srcs = [os.path.join(ORACLE_DIR, "oracle.cpp"), os.path.join(ORACLE_DIR, "oracle_next.cpp")]
+    deps = srcs + [os.path.join(ORACLE_DIR, "oracle.h"), os.path.join(ORACLE_DIR, "oracle_tables.h")]
     if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
-    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", LIB_PATH, src], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", LIB_PATH] + srcs, check=True)
     return LIB_PATH
 
 
@@ -130,6 +130,45 @@ def extend(db, alns, ep):
     keys = _take(ok, n, np.dtype("<u4"))
     ext = _take(ex, n, np.dtype("u1"))
     return DB(data, keys, offs, lens, db.dbtype), ext
+
+
+def findstart(db, alns):
+    """findassemblystart: returns (new DB, add_stop[int32 per sequence])."""
+    from plass_b200.mmseqsdb import DB
+    od, oo, ol, ok, st = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    on, ob = C.c_uint64(), C.c_uint64()
+    s = seqdb_struct(db)
+    alns = np.ascontiguousarray(alns)
+    rc = lib().or_findstart(C.byref(s), C.c_void_p(alns.ctypes.data), C.c_uint64(len(alns)),
+                            C.byref(od), C.byref(oo), C.byref(ol), C.byref(ok), C.byref(on), C.byref(ob), C.byref(st))
+    assert rc == 0, rc
+    n = on.value
+    out = DB(_take(od, ob.value, np.dtype("u1")), _take(ok, n, np.dtype("<u4")), _take(oo, n, np.dtype("<u8")),
+             _take(ol, n, np.dtype("<u4")), db.dbtype)
+    return out, _take(st, db.n, np.dtype("<i4"))
+
+
+def cyclecheck(db, max_seq_len, kmer_size=22):
+    """cyclecheck: splitDiagonal per sequence (0 = not circular)."""
+    split = np.zeros(db.n, dtype=np.uint32)
+    s = seqdb_struct(db)
+    rc = lib().or_cyclecheck(C.byref(s), C.c_int(max_seq_len), C.c_int(kmer_size), C.c_void_p(split.ctypes.data))
+    assert rc == 0, rc
+    return split
+
+
+def cycle_db(db, split, chop):
+    """The DB cyclecheck writes for the given split diagonals (cyclecheck.cpp:249-259)."""
+    from plass_b200.mmseqsdb import DB
+    idx = np.nonzero(split)[0]
+    parts, lens = [], []
+    for i in idx:
+        o, l = int(db.offsets[i]), int(db.lens[i])
+        e = (bytes(db.data[o:o + int(split[i])]) + b"\n\0") if chop else bytes(db.data[o:o + l])
+        parts.append(e); lens.append(len(e))
+    lens = np.array(lens, dtype=np.uint32)
+    offs = np.concatenate([[0], np.cumsum(lens[:-1], dtype=np.uint64)]).astype(np.uint64) if len(lens) else np.zeros(0, dtype=np.uint64)
+    return DB(np.frombuffer(b"".join(parts), dtype=np.uint8), db.keys[idx].copy(), offs, lens, db.dbtype)
 
 
 def format_hits_by_rep(db_keys, hits):

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from common import golden_case, parse_pref_entry
+from common import golden_case, parse_flags, parse_pref_entry
 from plass_b200 import mmseqsdb
 import oracle_binding as ob
 import params
@@ -112,3 +112,41 @@ def test_evalue_known_answers():
     assert L.or_bitscore(1, 300.0) == t["nt_kat_bits300"]
     assert L.or_evalue(1, 1.5e8, 300.0, 150.0) == t["nt_kat_eval_300_150_1.5e8"]
     assert L.or_evalue(1, 1.5e8, 98.0, 150.0) == t["nt_kat_eval_98_150_1.5e8"]
+
+
+# ---- components ranked "next" in SURVEY.md section 8(f): oracle_next.cpp ----------------------------------------------
+
+@pytest.mark.parametrize("case", ["example_aa", "synth_aa"])
+def test_findassemblystart(case, golden_root):
+    """aa_6f_start_long + aln_0 -> corrected_seqs (data/assemble.sh:108-117), written by the reference binary."""
+    d, man = golden_case(case, golden_root)
+    seq = mmseqsdb.read_db(os.path.join(d, "aa_6f_start_long"))
+    alns = alns_from_db(mmseqsdb.read_db(os.path.join(d, "aln_0")))
+    want = mmseqsdb.read_db(os.path.join(d, "corrected_seqs"))
+    out, add_stop = ob.findstart(seq, alns)
+    assert out.dbtype == want.dbtype == 0
+    assert_same_entries(out.entries_by_key(), want.entries_by_key(), "%s/corrected_seqs" % case)
+    assert (add_stop >= 0).sum() > 0                      # the fixture does exercise the correction
+
+
+def test_cyclecheck(golden_root):
+    d, man = golden_case("cycle_nt", golden_root)
+    seq = mmseqsdb.read_db(os.path.join(d, "seqs"))
+    for s in man["steps"]:
+        flags = parse_flags(s["args"])
+        split = ob.cyclecheck(seq, int(flags["--max-seq-len"]))
+        want = mmseqsdb.read_db(os.path.join(d, s["dbs"][1]))
+        got = ob.cycle_db(seq, split, int(flags["--chop-cycle"]))
+        assert got.n == want.n > 100
+        assert_same_entries(got.entries_by_key(), want.entries_by_key(), "cycle_nt/%s" % s["dbs"][1])
+
+
+@pytest.mark.parametrize("case", ["synth_nt", "long_nt"])
+def test_cyclecheck_workflow_split(case, golden_root):
+    """nuclassemble.sh:19-60: assembly_N minus the reported sequences = assembly_N_noneCycle (--max-seq-len 200000)."""
+    d, man = golden_case(case, golden_root)
+    for name in sorted(f for f in os.listdir(d) if f.endswith("_noneCycle")):
+        seq = mmseqsdb.read_db(os.path.join(d, name[: -len("_noneCycle")]))
+        none = mmseqsdb.read_db(os.path.join(d, name))
+        split = ob.cyclecheck(seq, 200000)
+        assert sorted(int(k) for k in seq.keys[split == 0]) == sorted(int(k) for k in none.keys), (case, name)
