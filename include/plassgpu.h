@@ -143,6 +143,21 @@ int pg_assemble_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_param
                           const pg_ex_params *ep, pg_seqdb **out_db,
                           pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns);
 
+/* The two per-iteration helpers next to the hot path.
+ *
+ * pg_findassemblystart  replaces findassemblystart, src/assembler/findassemblystart.cpp:35-176 (plass STEP 0 only,
+ *                       data/assemble.sh:108-117): `alns` = the alignment DB of `db` against itself, ordered by query.
+ *                       For every query with an 'M': if >= 20 % of {query, aligned targets} carry "*M" at the projected
+ *                       position, each member's sequence is cut to "*" + residues[M position ..]; out_db holds every
+ *                       sequence (changed or not).  add_stop (optional, pinned, one int32 per sequence) = the cut
+ *                       position or -1.
+ * pg_cyclecheck         replaces cyclecheck, src/assembler/cyclecheck.cpp:71-274 (every penguin iteration,
+ *                       data/nuclassemble.sh:19-60), k = 22: split[i] (pinned, one uint32 per sequence) = the diagonal
+ *                       at which sequence i repeats itself (circular / terminally redundant), 0 = not reported.  The
+ *                       caller writes the reported sequences (--chop-cycle: the first split[i] residues). */
+int pg_findassemblystart(pg_context *ctx, const pg_seqdb *db, const pg_aln *alns, uint64_t n_alns, pg_seqdb **out_db, int32_t **add_stop);
+int pg_cyclecheck(pg_context *ctx, const pg_seqdb *db, int max_seq_len, uint32_t **split);
+
 /* Asynchronous result transfer.  The reference workflow writes pref_N / aln_N / assembly_N to disk while the next
  * iteration's input already sits in HBM; with pg_set_async_results(ctx, 1) pg_assemble_iteration (hits, alns) and
  * pg_seqdb_download only ENQUEUE their device->host copies on the context's copy stream and return, so that the

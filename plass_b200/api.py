@@ -245,6 +245,24 @@ class Context:
         out.dbtype = ddb.dbtype
         return out, _take(ext, out.n, np.dtype("u1"))
 
+    # findassemblystart (src/assembler/findassemblystart.cpp:35-176)
+    def findassemblystart(self, ddb, alns):
+        """Returns (corrected DeviceSeqDB, add_stop int32 per sequence: cut position or -1)."""
+        alns = np.ascontiguousarray(alns, dtype=ALN)
+        h, st = C.c_void_p(), C.c_void_p()
+        _check(load_library().pg_findassemblystart(self.handle, ddb.handle, C.c_void_p(alns.ctypes.data), C.c_uint64(len(alns)),
+                                                   C.byref(h), C.byref(st)), "pg_findassemblystart")
+        out = DeviceSeqDB(self, h)
+        out.dbtype = ddb.dbtype
+        return out, _take(st, ddb.n, np.dtype("<i4"))
+
+    # cyclecheck (src/assembler/cyclecheck.cpp:71-274)
+    def cyclecheck(self, ddb, max_seq_len):
+        """Split diagonal per sequence (uint32, 0 = not circular)."""
+        sp = C.c_void_p()
+        _check(load_library().pg_cyclecheck(self.handle, ddb.handle, C.c_int(int(max_seq_len)), C.byref(sp)), "pg_cyclecheck")
+        return _take(sp, ddb.n, np.dtype("<u4"))
+
     def assemble_iteration(self, ddb, kp, rp, ep, want_intermediates=False):
         """One fused iteration in HBM.  Returns (next DeviceSeqDB, hits or None, alns or None)."""
         h = C.c_void_p()

@@ -28,6 +28,7 @@ CUDA_SOURCES = {
     "pg_kmermatch.cu": [],
     "pg_rescore.cu": ["-fmad=false"],
     "pg_extend.cu": ["-fmad=false"],
+    "pg_next.cu": ["-fmad=false"],
 }
 HOST_SOURCES = ["host/cli.cpp", "host/mmdb.cpp", "host/commands.cpp"]
 

@@ -1,4 +1,4 @@
-// cli.cpp -- `plass_b200_cli <command> <args>`: the four GPU commands behind the reference's own
+// cli.cpp -- `plass_b200_cli <command> <args>`: the GPU commands (the four hot-path steps + findassemblystart, cyclecheck) behind the reference's own
 // command-line contract, so that `$MMSEQS kmermatcher ...` lines of data/assemble.sh / nuclassemble.sh can
 // be pointed at this binary (see INTEGRATION.md for the dispatcher and for the Command-table stub).
 #include "commands.h"
@@ -9,7 +9,7 @@
 
 int main(int argc, const char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "usage: %s <kmermatcher|rescorediagonal|assembleresults|nuclassembleresults> <dbs...> [flags]\n", argv[0]);
+        fprintf(stderr, "usage: %s <kmermatcher|rescorediagonal|assembleresults|nuclassembleresults|findassemblystart|cyclecheck> <dbs...> [flags]\n", argv[0]);
         return EXIT_FAILURE;
     }
     const char *cmd = argv[1];
@@ -17,6 +17,8 @@ int main(int argc, const char **argv) {
     if (!strcmp(cmd, "rescorediagonal")) return rescorediagonal(argc - 2, argv + 2);
     if (!strcmp(cmd, "assembleresults")) return assembleresults(argc - 2, argv + 2);
     if (!strcmp(cmd, "nuclassembleresults")) return nuclassembleresults(argc - 2, argv + 2);
+    if (!strcmp(cmd, "findassemblystart")) return findassemblystart(argc - 2, argv + 2);
+    if (!strcmp(cmd, "cyclecheck")) return cyclecheck(argc - 2, argv + 2);
     fprintf(stderr, "%s: not one of the GPU hot-path commands\n", cmd);
     return EXIT_FAILURE;
 }

@@ -131,23 +131,8 @@ const std::set<std::string> RS_FLAGS = {"--sub-mat", "--rescore-mode", "--wrappe
     "--min-seq-id", "--min-aln-len", "--seq-id-mode", "--add-self-matches", "--sort-results", "--db-load-mode", "--threads", "--compressed", "-v"};
 const std::set<std::string> EX_FLAGS = {"--min-seq-id", "--max-seq-len", "--keep-target", "--threads", "-v", "--rescore-mode", "--sub-mat", "--db-load-mode", "--compressed"};
 
-int extendCommand(int argc, const char **argv, bool nuclCommand) {
-    Timer timer;
-    const Flags f = parseFlags(argc, argv, 3, EX_FLAGS);
-    requireValue(f, "--compressed", "0", "uncompressed DBs only");
-    checkSubMat(f);
-    std::string err;
-    mmdb::Reader seq, aln;
-    if (!seq.open(f.positional[0], err) || !aln.open(f.positional[1], err)) die(err);
-    const bool nucl = seq.dbtype == mmdb::DBTYPE_NUCLEOTIDES;
-    (void) nuclCommand;   // like the reference, the comparator follows the command, the letters follow the DB type
-    pg_ex_params p;
-    p.seq_id_thr = (float) getd(f, "--min-seq-id", nuclCommand ? 0.99 : 0.9);
-    p.max_seq_len = geti(f, "--max-seq-len", nuclCommand ? 200000 : 65535);
-    p.keep_target = geti(f, "--keep-target", 1);
-    p.rescore_mode = geti(f, "--rescore-mode", 3);
-    if (nuclCommand != nucl) die("sequence DB type does not match the command (assembleresults = amino acids, nuclassembleresults = nucleotides)");
-    // parse the alignment DB (Matcher::parseAlignmentRecord, Matcher.cpp:248-320)
+// Matcher::parseAlignmentRecord over a whole alignment DB (Matcher.cpp:190-320), entries in key order
+std::vector<pg_aln> parseAlnDb(const mmdb::Reader &aln) {
     std::vector<pg_aln> alns;
     for (size_t i = 0; i < aln.size(); i++) {
         const char *s = aln.entry(i);
@@ -165,15 +150,43 @@ int extendCommand(int argc, const char **argv, bool nuclCommand) {
             s = *e ? e + 1 : e;
         }
     }
-    pg_seqdb *db = uploadSeqDb(seq), *out = nullptr;
-    if (pg_extend(gpu(), db, alns.data(), alns.size(), &p, &out, nullptr) != 0) die(pg_last_error());
+    return alns;
+}
+
+void writeSeqDb(pg_seqdb *out, const std::string &path, int dbtype) {
     char *data; uint64_t bytes, *offs, n; uint32_t *lens, *keys;
     if (pg_seqdb_download(gpu(), out, &data, &bytes, &offs, &lens, &keys, &n) != 0) die(pg_last_error());
     mmdb::Writer w;
-    if (!w.open(f.positional[2], seq.dbtype, err)) die(err);
+    std::string err;
+    if (!w.open(path, dbtype, err)) die(err);
     for (uint64_t i = 0; i < n; i++) w.write(keys[i], data + offs[i], lens[i] - 1);
     if (!w.close()) die("write error");
     pg_free_host(data); pg_free_host(offs); pg_free_host(lens); pg_free_host(keys);
+}
+
+const std::set<std::string> FS_FLAGS = {"--threads", "-v", "--compressed"};
+const std::set<std::string> CC_FLAGS = {"--max-seq-len", "--chop-cycle", "--threads", "-v", "--compressed"};
+
+int extendCommand(int argc, const char **argv, bool nuclCommand) {
+    Timer timer;
+    const Flags f = parseFlags(argc, argv, 3, EX_FLAGS);
+    requireValue(f, "--compressed", "0", "uncompressed DBs only");
+    checkSubMat(f);
+    std::string err;
+    mmdb::Reader seq, aln;
+    if (!seq.open(f.positional[0], err) || !aln.open(f.positional[1], err)) die(err);
+    const bool nucl = seq.dbtype == mmdb::DBTYPE_NUCLEOTIDES;
+    (void) nuclCommand;   // like the reference, the comparator follows the command, the letters follow the DB type
+    pg_ex_params p;
+    p.seq_id_thr = (float) getd(f, "--min-seq-id", nuclCommand ? 0.99 : 0.9);
+    p.max_seq_len = geti(f, "--max-seq-len", nuclCommand ? 200000 : 65535);
+    p.keep_target = geti(f, "--keep-target", 1);
+    p.rescore_mode = geti(f, "--rescore-mode", 3);
+    if (nuclCommand != nucl) die("sequence DB type does not match the command (assembleresults = amino acids, nuclassembleresults = nucleotides)");
+    const std::vector<pg_aln> alns = parseAlnDb(aln);
+    pg_seqdb *db = uploadSeqDb(seq), *out = nullptr;
+    if (pg_extend(gpu(), db, alns.data(), alns.size(), &p, &out, nullptr) != 0) die(pg_last_error());
+    writeSeqDb(out, f.positional[2], seq.dbtype);
     pg_seqdb_free(gpu(), out); pg_seqdb_free(gpu(), db);
     printf("\nDone.\n");
     timer.report();
@@ -314,6 +327,59 @@ int rescorediagonal(int argc, const char **argv) {
     }
     if (!w.close()) die("write error");
     pg_free_host(alns);
+    pg_seqdb_free(gpu(), db);
+    timer.report();
+    return EXIT_SUCCESS;
+}
+
+// findassemblystart <i:sequenceDB> <i:alnResult> <o:sequenceDB>  (src/assembler/findassemblystart.cpp:35-176)
+int findassemblystart(int argc, const char **argv) {
+    Timer timer;
+    const Flags f = parseFlags(argc, argv, 3, FS_FLAGS);
+    requireValue(f, "--compressed", "0", "uncompressed DBs only");
+    std::string err;
+    mmdb::Reader seq, aln;
+    if (!seq.open(f.positional[0], err) || !aln.open(f.positional[1], err)) die(err);
+    if (seq.dbtype != mmdb::DBTYPE_AMINO_ACIDS) die("findassemblystart expects an amino-acid sequence DB");
+    const std::vector<pg_aln> alns = parseAlnDb(aln);
+    pg_seqdb *db = uploadSeqDb(seq), *out = nullptr;
+    if (pg_findassemblystart(gpu(), db, alns.data(), alns.size(), &out, nullptr) != 0) die(pg_last_error());
+    writeSeqDb(out, f.positional[2], mmdb::DBTYPE_AMINO_ACIDS);
+    pg_seqdb_free(gpu(), out); pg_seqdb_free(gpu(), db);
+    timer.report();
+    return EXIT_SUCCESS;
+}
+
+// cyclecheck <i:sequenceDB> <o:sequenceDBcycle>  (src/assembler/cyclecheck.cpp:31-274): the output holds only the
+// sequences reported as circular, cut at the split diagonal with --chop-cycle 1
+int cyclecheck(int argc, const char **argv) {
+    Timer timer;
+    const Flags f = parseFlags(argc, argv, 2, CC_FLAGS);
+    requireValue(f, "--compressed", "0", "uncompressed DBs only");
+    std::string err;
+    mmdb::Reader seq;
+    if (!seq.open(f.positional[0], err)) die(err);
+    if (seq.dbtype != mmdb::DBTYPE_NUCLEOTIDES) die("Module cyclecheck only supports nucleotide input database");
+    const int maxSeqLen = geti(f, "--max-seq-len", 65535);
+    const bool chop = geti(f, "--chop-cycle", 0) != 0;
+    pg_seqdb *db = uploadSeqDb(seq);
+    uint32_t *split = nullptr;
+    if (pg_cyclecheck(gpu(), db, maxSeqLen, &split) != 0) die(pg_last_error());
+    mmdb::Writer w;
+    if (!w.open(f.positional[1], mmdb::DBTYPE_NUCLEOTIDES, err)) die(err);
+    std::string buf;
+    for (size_t i = 0; i < seq.size(); i++) {
+        if (split[i] == 0) continue;
+        if (chop) {                                    // :251-256
+            buf.assign(seq.entry(i), split[i]);
+            buf.push_back('\n');
+            w.write(seq.keys[i], buf.data(), buf.size());
+        } else {
+            w.write(seq.keys[i], seq.entry(i), seq.lens[i] - 1);
+        }
+    }
+    if (!w.close()) die("write error");
+    pg_free_host(split);
     pg_seqdb_free(gpu(), db);
     timer.report();
     return EXIT_SUCCESS;

@@ -6,3 +6,5 @@ int kmermatcher(int argc, const char **argv);            // replaces linclust/km
 int rescorediagonal(int argc, const char **argv);        // replaces alignment/rescorediagonal.cpp:381
 int assembleresults(int argc, const char **argv);        // replaces src/assembler/assembleresult.cpp:358
 int nuclassembleresults(int argc, const char **argv);    // replaces src/assembler/nuclassembleresult.cpp:400
+int findassemblystart(int argc, const char **argv);      // replaces src/assembler/findassemblystart.cpp:35
+int cyclecheck(int argc, const char **argv);             // replaces src/assembler/cyclecheck.cpp:31

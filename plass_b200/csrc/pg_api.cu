@@ -256,7 +256,7 @@ void pg_destroy(pg_context *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->small, &ctx->lists, &ctx->recA, &ctx->recB, &ctx->radixWs, &ctx->scratch, &ctx->blockCounts, &ctx->hits,
-                      &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta, &ctx->exLists, &ctx->ntTab, &ctx->buckets, &ctx->buckets2, &ctx->wideTabs};
+                      &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta, &ctx->exLists, &ctx->ntTab, &ctx->buckets, &ctx->buckets2, &ctx->wideTabs, &ctx->nextWork};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
     cudaStreamSynchronize(ctx->copyStream);
@@ -414,6 +414,30 @@ int pg_assemble_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_param
     cudaFreeAsync(dExt, ctx->stream);
     end_call(ctx);
     if (!ctx->asyncResults) PG_CUDA(cudaStreamSynchronize(ctx->copyStream));
+    return 0;
+}
+
+int pg_findassemblystart(pg_context *ctx, const pg_seqdb *db, const pg_aln *alns, uint64_t n_alns, pg_seqdb **out_db, int32_t **add_stop) {
+    PG_CHECK(ctx && db && out_db && (alns || n_alns == 0), "pg_findassemblystart: null argument");
+    begin_call(ctx);
+    PG_TRY(ctx->alns.reserve(sizeof(pg_aln) * (n_alns + 1)));
+    if (n_alns) PG_CUDA(cudaMemcpyAsync(ctx->alns.p, alns, sizeof(pg_aln) * n_alns, cudaMemcpyHostToDevice, ctx->stream));
+    for (uint64_t i = 1; i < n_alns; i++)
+        PG_CHECK(alns[i - 1].query <= alns[i].query, "pg_findassemblystart: alignments must be ordered by query");
+    int *dStop = nullptr;
+    PG_TRY(fs_run(ctx, db, ctx->alns.as<pg_aln>(), n_alns, out_db, &dStop));
+    if (add_stop) PG_TRY(to_host(ctx->stream, dStop, db->n, add_stop));
+    end_call(ctx);
+    return 0;
+}
+
+int pg_cyclecheck(pg_context *ctx, const pg_seqdb *db, int max_seq_len, uint32_t **split) {
+    PG_CHECK(ctx && db && split, "pg_cyclecheck: null argument");
+    begin_call(ctx);
+    unsigned *d = nullptr;
+    PG_TRY(cc_run(ctx, db, max_seq_len, 22 /* setCycleCheckDefaults, cyclecheck.cpp:26-29 */, &d));
+    PG_TRY(to_host(ctx->stream, d, db->n, split));
+    end_call(ctx);
     return 0;
 }
 

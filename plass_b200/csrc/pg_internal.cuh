@@ -28,7 +28,7 @@ struct pg_context {
     cudaEvent_t evAuxFork = nullptr, evAuxJoin = nullptr;
     unsigned long long *hostStage = nullptr;   // mapped pinned words: the kernels' small results are read back through here (pg::read_back)
     cudaEvent_t ev[pg::EV_COUNT];
-    pg::DevBuf small, lists, recA, recB, radixWs, scratch, blockCounts, hits, alnAll, alns, flags, exWork, exSegs, exMeta, exLists, ntTab, buckets, buckets2, wideTabs;
+    pg::DevBuf small, lists, recA, recB, radixWs, scratch, blockCounts, hits, alnAll, alns, flags, exWork, exSegs, exMeta, exLists, ntTab, buckets, buckets2, wideTabs, nextWork;
     bool forceFullSort = false;   // tests: take the 8-pass sort + group_kernel path instead of the bucketed hash join
     unsigned ntTabN = 0;
     bool pairsInA = false;
@@ -65,6 +65,9 @@ int km_shard_reduce(Context *ctx, const pg_seqdb *db, const void *d_pairs, uint6
 int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHits, const pg_rs_params *p, pg_aln **d_alns, uint64_t *nAlns);
 // extension (pg_extend.cu): d_alns sorted by query; produces a new device DB
 int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAlns, const pg_ex_params *p, pg_seqdb **out, unsigned char **d_extended);
+// findassemblystart / cyclecheck (pg_next.cu); the returned device arrays live in ctx->nextWork until the next call
+int fs_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAlns, pg_seqdb **out, int **d_addStop);
+int cc_run(Context *ctx, const pg_seqdb *db, int maxSeqLen, int k, unsigned **d_split);
 int seqdb_finalize(Context *ctx, pg_seqdb *db);   // computes max_seq_len / residues / dense_keys on the device
 void seqdb_release(pg_seqdb *db, cudaStream_t s);
 // Small device -> host read-back (counters, totals) that does NOT go through the copy engine: a one-warp kernel stores

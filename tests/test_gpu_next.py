@@ -1,0 +1,123 @@
+"""GPU parity tests (-m gpu) of the two per-iteration helpers next to the hot path:
+findassemblystart and cyclecheck, through the C ABI and through the host CLI, against the CPU oracle (oracle_next.cpp)
+and against DBs written by the unmodified reference binary (tests/golden)."""
+import os
+import subprocess
+import numpy as np
+import pytest
+
+from common import golden_case, parse_flags, ROOT
+from plass_b200 import mmseqsdb, api
+import oracle_binding as ob
+from test_oracle_vs_reference import alns_from_db, assert_same_entries
+
+pytestmark = pytest.mark.gpu
+
+CLI = os.path.join(ROOT, "plass_b200", "plass_b200_cli")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("case", ["example_aa", "synth_aa"])
+def test_findassemblystart_matches_oracle_and_golden(case, golden_root, ctx):
+    d, man = golden_case(case, golden_root)
+    seq = mmseqsdb.read_db(os.path.join(d, "aa_6f_start_long"))
+    alns = alns_from_db(mmseqsdb.read_db(os.path.join(d, "aln_0")))
+    ddb = ctx.upload(seq)
+    out, add_stop = ctx.findassemblystart(ddb, alns)
+    got = out.download()
+    out.free(); ddb.free()
+    want, wstop = ob.findstart(seq, alns)
+    assert np.array_equal(add_stop, wstop), case
+    assert_same_entries(got.entries_by_key(), want.entries_by_key(), "%s/corrected_seqs vs oracle" % case)
+    golden = mmseqsdb.read_db(os.path.join(d, "corrected_seqs"))
+    assert_same_entries(got.entries_by_key(), golden.entries_by_key(), "%s/corrected_seqs vs reference" % case)
+    assert ctx.timings()["kernel_launches"] > 0
+
+
+def test_findassemblystart_without_alignments(ctx):
+    seq = mmseqsdb.from_sequences([b"MKV*MAA", b"AAAA", b"*MKK"], 0, keys=[3, 7, 9])
+    ddb = ctx.upload(seq)
+    out, add_stop = ctx.findassemblystart(ddb, np.zeros(0, dtype=api.ALN))
+    got = out.download()
+    out.free(); ddb.free()
+    assert (add_stop == -1).all()
+    assert got.entries_by_key() == seq.entries_by_key()
+
+
+def test_cyclecheck_matches_oracle_and_golden(golden_root, ctx):
+    d, man = golden_case("cycle_nt", golden_root)
+    seq = mmseqsdb.read_db(os.path.join(d, "seqs"))
+    ddb = ctx.upload(seq)
+    for s in man["steps"]:
+        flags = parse_flags(s["args"])
+        split = ctx.cyclecheck(ddb, int(flags["--max-seq-len"]))
+        want = ob.cyclecheck(seq, int(flags["--max-seq-len"]))
+        assert np.array_equal(split, want), np.nonzero(split != want)[0][:10]
+        golden = mmseqsdb.read_db(os.path.join(d, s["dbs"][1]))
+        assert_same_entries(ob.cycle_db(seq, split, int(flags["--chop-cycle"])).entries_by_key(), golden.entries_by_key(), "cycle_nt/%s" % s["dbs"][1])
+    ddb.free()
+
+
+@pytest.mark.parametrize("case", ["synth_nt", "long_nt"])
+def test_cyclecheck_on_assemblies_matches_oracle(case, golden_root, ctx):
+    """The DBs cyclecheck sees inside the workflow (nuclassemble.sh:19-60), up to 80 000 nt (CTA-per-sequence path)."""
+    d, man = golden_case(case, golden_root)
+    for name in sorted(f for f in os.listdir(d) if f.endswith("_noneCycle")):
+        seq = mmseqsdb.read_db(os.path.join(d, name[: -len("_noneCycle")]))
+        none = mmseqsdb.read_db(os.path.join(d, name))
+        ddb = ctx.upload(seq)
+        split = ctx.cyclecheck(ddb, 200000)
+        ddb.free()
+        assert np.array_equal(split, ob.cyclecheck(seq, 200000)), (case, name)
+        assert sorted(int(k) for k in seq.keys[split == 0]) == sorted(int(k) for k in none.keys), (case, name)
+
+
+def test_cyclecheck_random_lengths_match_oracle(ctx):
+    """Lengths around the boundaries of the three kernel classes (380 / 381, 1532 / 1533), below the k-mer size, with N
+    runs and with every kind of self overlap."""
+    rng = np.random.default_rng(33)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs = []
+    for L in [1, 5, 21, 22, 23, 65, 66, 67, 379, 380, 381, 382, 1531, 1532, 1533, 1534, 3000, 5000] + [int(x) for x in rng.integers(30, 2500, 300)]:
+        g = acgt[rng.integers(0, 4, max(1, int(L * rng.uniform(0.4, 1.0))))]
+        s = np.concatenate([g, g])[:L].copy() if rng.random() < 0.7 else acgt[rng.integers(0, 4, L)]
+        if len(s) < L:
+            s = np.concatenate([s, acgt[rng.integers(0, 4, L - len(s))]])
+        if rng.random() < 0.2 and L > 40:
+            p = int(rng.integers(0, L - 5)); s[p:p + 3] = ord("N")
+        seqs.append(s.tobytes())
+    seq = mmseqsdb.from_sequences(seqs, 1)
+    ddb = ctx.upload(seq)
+    for max_len in (200000, 1000):
+        split = ctx.cyclecheck(ddb, max_len)
+        want = ob.cyclecheck(seq, max_len)
+        assert np.array_equal(split, want), (max_len, np.nonzero(split != want)[0][:10])
+    ddb.free()
+    assert (want > 0).sum() > 20
+
+
+def run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, "%s\n%s" % (" ".join(cmd), r.stdout[-3000:])
+
+
+def test_cli_findassemblystart_and_cyclecheck(golden_root, tmp_path):
+    d, man = golden_case("synth_aa", golden_root)
+    out = str(tmp_path / "corrected_gpu")
+    run([CLI, "findassemblystart", os.path.join(d, "aa_6f_start_long"), os.path.join(d, "aln_0"), out, "--threads", "4", "-v", "3"])
+    got, want = mmseqsdb.read_db(out), mmseqsdb.read_db(os.path.join(d, "corrected_seqs"))
+    assert got.dbtype == want.dbtype
+    assert_same_entries(got.entries_by_key(), want.entries_by_key(), "corrected_seqs via CLI")
+    d, man = golden_case("cycle_nt", golden_root)
+    for s in man["steps"]:
+        out = str(tmp_path / (s["dbs"][1] + "_gpu"))
+        run([CLI, "cyclecheck", os.path.join(d, "seqs"), out] + s["args"])
+        got, want = mmseqsdb.read_db(out), mmseqsdb.read_db(os.path.join(d, s["dbs"][1]))
+        assert got.dbtype == want.dbtype == 1
+        assert_same_entries(got.entries_by_key(), want.entries_by_key(), "%s via CLI" % s["dbs"][1])
