@@ -354,19 +354,32 @@ def main():
         # memory and every result is awaited inside the timed region (the last one after the loop).
         ctx.set_async_results(True)
         try:
+            trace = os.environ.get("PLASS_B200_E2E_TRACE")
+
             def run_pipelined(k):
                 pending = None
                 nbytes = 0
-                for _ in range(k):
-                    d_in = ctx.upload(pinned)
+                # every step copies its own input from pinned host memory; the copy of step i+1's input is enqueued on
+                # the upload stream before step i's kernels are launched, so it travels underneath them
+                nxt = ctx.upload_async(pinned)
+                for i in range(k):
+                    ta = time.perf_counter()
+                    d_in = nxt
+                    nxt = ctx.upload_async(pinned) if i + 1 < k else None
+                    tb = time.perf_counter()
                     out, hits, alns = ctx.assemble_iteration(d_in, kp, rp, ep, want_intermediates=True)
+                    tc = time.perf_counter()
                     host_out = out.download()
                     ticket = ctx.results_ticket()
                     out.free(); d_in.free()
+                    td = time.perf_counter()
                     if pending is not None:
                         ctx.results_wait(pending[0])
                         nbytes = sum(int(a.nbytes) for a in pending[1:])
                     pending = (ticket, hits, alns, host_out.data, host_out.offsets, host_out.lens, host_out.keys)
+                    if trace:
+                        log("[bench/e2e] step %d: enqueue upload %.2f ms, iteration %.2f ms, enqueue download %.2f ms, wait previous results %.2f ms"
+                            % (i, (tb - ta) * 1e3, (tc - tb) * 1e3, (td - tc) * 1e3, (time.perf_counter() - td) * 1e3))
                 ctx.results_wait(pending[0])
                 nbytes = sum(int(a.nbytes) for a in pending[1:])
                 return nbytes
@@ -377,7 +390,8 @@ def main():
             d2h = run_pipelined(k)
             barrier()
             e2e_dt = (time.perf_counter() - t0) / k
-            e2e_mode = "pipelined over %d steps: the device-to-host copies of step i run under the upload and kernels of step i+1; the final drain is inside the timed region" % k
+            e2e_mode = ("pipelined over %d steps: every step's input is copied from pinned host memory (upload stream) while the previous step computes, "
+                        "the device-to-host copies of step i run under the kernels of step i+1; first upload and final drain are inside the timed region" % k)
         finally:
             ctx.set_async_results(False)
     if world > 1:

@@ -119,6 +119,10 @@ void pg_destroy(pg_context *ctx);
 int pg_get_timings(const pg_context *ctx, pg_timings *out);
 
 int pg_seqdb_upload(pg_context *ctx, const pg_seqdb_view *view, pg_seqdb **db);
+/* Same, but only ENQUEUES the copies on the context's upload stream and returns: the transfer of the next input runs
+ * underneath the kernels of the current call.  `view`'s arrays must be pinned host memory and stay alive until the DB
+ * has been used by (or waited for in) a compute call, which orders itself after the copies. */
+int pg_seqdb_upload_async(pg_context *ctx, const pg_seqdb_view *view, pg_seqdb **db);
 /* Same, but the view's four arrays are DEVICE pointers owned by the caller (not copied; pg_seqdb_free releases only
  * the handle; data needs 16 readable bytes past data_bytes).  Multi-GPU: every rank copies its slice of the DB to
  * its GPU, the slices are all-gathered over NVLink, and the gathered arrays are adopted (plass_b200/sharded.py). */

@@ -209,6 +209,24 @@ class Context:
         d.dbtype = db.dbtype
         return d
 
+    def upload_async(self, db):
+        """Like upload(), but only enqueues the host -> device copies (on the context's upload stream) and returns: the
+        transfer runs underneath whatever the GPU is computing.  db's arrays must be pinned and are kept alive by the
+        returned object."""
+        v = SeqDBView()
+        data = np.ascontiguousarray(db.data)
+        offs = np.ascontiguousarray(db.offsets, dtype=np.uint64)
+        lens = np.ascontiguousarray(db.lens, dtype=np.uint32)
+        keys = np.ascontiguousarray(db.keys, dtype=np.uint32)
+        v.data, v.data_bytes = data.ctypes.data, data.nbytes
+        v.offsets, v.lens, v.keys, v.n, v.dbtype = offs.ctypes.data, lens.ctypes.data, keys.ctypes.data, db.n, db.dbtype
+        h = C.c_void_p()
+        _check(load_library().pg_seqdb_upload_async(self.handle, C.byref(v), C.byref(h)), "pg_seqdb_upload_async")
+        d = DeviceSeqDB(self, h)
+        d.dbtype = db.dbtype
+        d.keepalive = (data, offs, lens, keys)
+        return d
+
     def adopt(self, data_ptr, data_bytes, offsets_ptr, lens_ptr, keys_ptr, n, dbtype, keepalive=None):
         """Wraps caller-owned device arrays (e.g. torch tensors filled by an all-gather) as a DeviceSeqDB."""
         v = SeqDBView()

@@ -81,6 +81,19 @@ int seqdb_finalize(Context *ctx, pg_seqdb *db) {
     return 0;
 }
 
+// First use of a DB whose upload was only enqueued (pg_seqdb_upload_async): order the main stream after the copies and
+// compute the statistics every stage relies on.
+int db_ready(Context *ctx, const pg_seqdb *cdb) {
+    pg_seqdb *db = const_cast<pg_seqdb *>(cdb);
+    if (!db || !db->uploadPending) return 0;
+    cudaSetDevice(ctx->device);
+    PG_CUDA(cudaStreamWaitEvent(ctx->stream, db->evReady, 0));
+    db->uploadPending = false;
+    cudaEventDestroy(db->evReady);
+    db->evReady = nullptr;
+    return seqdb_finalize(ctx, db);
+}
+
 // Pinned host blocks are expensive to create (cudaMallocHost pins pages, ~0.3 s/GB), so blocks released
 // with pg_free_host() are kept in a small process-wide cache and handed out again.
 static std::mutex g_pinMutex;
@@ -227,6 +240,7 @@ int pg_init(int device, pg_context **out) {
     ctx->device = device;
     PG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     PG_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+    PG_CUDA(cudaStreamCreateWithFlags(&ctx->h2dStream, cudaStreamNonBlocking));
     PG_CUDA(cudaEventCreateWithFlags(&ctx->evCopyReady, cudaEventDisableTiming));
     PG_CUDA(cudaEventCreateWithFlags(&ctx->evHitsCopied, cudaEventDisableTiming));
     PG_CUDA(cudaEventCreateWithFlags(&ctx->evAlnsCopied, cudaEventDisableTiming));
@@ -268,6 +282,8 @@ void pg_destroy(pg_context *ctx) {
     cudaEventDestroy(ctx->evAuxFork); cudaEventDestroy(ctx->evAuxJoin);
     cudaStreamDestroy(ctx->auxStream);
     cudaStreamDestroy(ctx->copyStream);
+    cudaStreamSynchronize(ctx->h2dStream);
+    cudaStreamDestroy(ctx->h2dStream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -298,6 +314,29 @@ int pg_seqdb_upload(pg_context *ctx, const pg_seqdb_view *v, pg_seqdb **out) {
     return 0;
 }
 
+int pg_seqdb_upload_async(pg_context *ctx, const pg_seqdb_view *v, pg_seqdb **out) {
+    PG_CHECK(ctx && v && out, "pg_seqdb_upload_async: null argument");
+    PG_CHECK(v->dbtype == PG_DBTYPE_AMINO_ACIDS || v->dbtype == PG_DBTYPE_NUCLEOTIDES, "pg_seqdb_upload_async: dbtype must be amino acids (0) or nucleotides (1)");
+    PG_CHECK(v->n < 0xFFFFFFF0ull, "pg_seqdb_upload_async: more than 2^32 sequences");
+    cudaSetDevice(ctx->device);
+    cudaStream_t hs = ctx->h2dStream;
+    pg_seqdb *db = new pg_seqdb();
+    db->n = v->n; db->data_bytes = v->data_bytes; db->dbtype = v->dbtype;
+    PG_CUDA(cudaMallocAsync(&db->data, v->data_bytes + 16, hs));
+    PG_CUDA(cudaMallocAsync(&db->offsets, sizeof(unsigned long long) * (v->n + 1), hs));
+    PG_CUDA(cudaMallocAsync(&db->lens, sizeof(unsigned) * (v->n + 1), hs));
+    PG_CUDA(cudaMallocAsync(&db->keys, sizeof(unsigned) * (v->n + 1), hs));
+    PG_CUDA(cudaMemcpyAsync(db->data, v->data, v->data_bytes, cudaMemcpyHostToDevice, hs));
+    PG_CUDA(cudaMemcpyAsync(db->offsets, v->offsets, sizeof(unsigned long long) * v->n, cudaMemcpyHostToDevice, hs));
+    PG_CUDA(cudaMemcpyAsync(db->lens, v->lens, sizeof(unsigned) * v->n, cudaMemcpyHostToDevice, hs));
+    PG_CUDA(cudaMemcpyAsync(db->keys, v->keys, sizeof(unsigned) * v->n, cudaMemcpyHostToDevice, hs));
+    PG_CUDA(cudaEventCreateWithFlags(&db->evReady, cudaEventDisableTiming));
+    PG_CUDA(cudaEventRecord(db->evReady, hs));
+    db->uploadPending = true;
+    *out = db;
+    return 0;
+}
+
 int pg_seqdb_adopt(pg_context *ctx, const pg_seqdb_view *v, pg_seqdb **out) {
     PG_CHECK(ctx && v && out, "pg_seqdb_adopt: null argument");
     PG_CHECK(v->dbtype == PG_DBTYPE_AMINO_ACIDS || v->dbtype == PG_DBTYPE_NUCLEOTIDES, "pg_seqdb_adopt: dbtype must be amino acids (0) or nucleotides (1)");
@@ -317,6 +356,7 @@ int pg_seqdb_adopt(pg_context *ctx, const pg_seqdb_view *v, pg_seqdb **out) {
 int pg_seqdb_download(pg_context *ctx, const pg_seqdb *db, char **data, uint64_t *data_bytes, uint64_t **offsets,
                       uint32_t **lens, uint32_t **keys, uint64_t *n) {
     PG_CHECK(ctx && db, "pg_seqdb_download: null argument");
+    PG_TRY(db_ready(ctx, db));
     cudaSetDevice(ctx->device);
     if (ctx->asyncResults) {
         // enqueue only: the arrays are complete after pg_results_wait on a ticket taken after this call.  The DB's device
@@ -342,6 +382,11 @@ uint64_t pg_seqdb_size(const pg_seqdb *db) { return db ? db->n : 0; }
 void pg_seqdb_free(pg_context *ctx, pg_seqdb *db) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (db && db->uploadPending) {            // uploaded but never used: release after the copies
+        cudaStreamWaitEvent(ctx->stream, db->evReady, 0);
+        cudaEventDestroy(db->evReady);
+        db->evReady = nullptr; db->uploadPending = false;
+    }
     // stream-ordered release: after the kernels of the main stream, or after the pending download on the copy stream
     // (every consumer on the main stream was enqueued before the download)
     seqdb_release(db, (db && db->downloadPending) ? ctx->copyStream : ctx->stream);
@@ -349,6 +394,7 @@ void pg_seqdb_free(pg_context *ctx, pg_seqdb *db) {
 
 int pg_kmermatch(pg_context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **hits, uint64_t *n_hits) {
     PG_CHECK(ctx && db && p && hits && n_hits, "pg_kmermatch: null argument");
+    PG_TRY(db_ready(ctx, db));
     begin_call(ctx);
     pg_hit *d = nullptr; uint64_t n = 0;
     PG_TRY(km_run(ctx, db, p, &d, &n));
@@ -361,6 +407,7 @@ int pg_kmermatch(pg_context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_
 int pg_rescore(pg_context *ctx, const pg_seqdb *db, const pg_hit *hits, uint64_t n_hits, const pg_rs_params *p,
                pg_aln **alns, uint64_t *n_alns) {
     PG_CHECK(ctx && db && p && alns && n_alns && (hits || n_hits == 0), "pg_rescore: null argument");
+    PG_TRY(db_ready(ctx, db));
     begin_call(ctx);
     PG_TRY(ctx->hits.reserve(sizeof(pg_hit) * (n_hits + 1)));
     if (n_hits) PG_CUDA(cudaMemcpyAsync(ctx->hits.p, hits, sizeof(pg_hit) * n_hits, cudaMemcpyHostToDevice, ctx->stream));
@@ -377,6 +424,7 @@ int pg_rescore(pg_context *ctx, const pg_seqdb *db, const pg_hit *hits, uint64_t
 int pg_extend(pg_context *ctx, const pg_seqdb *db, const pg_aln *alns, uint64_t n_alns, const pg_ex_params *p,
               pg_seqdb **out_db, uint8_t **extended) {
     PG_CHECK(ctx && db && p && out_db && (alns || n_alns == 0), "pg_extend: null argument");
+    PG_TRY(db_ready(ctx, db));
     begin_call(ctx);
     PG_TRY(ctx->alns.reserve(sizeof(pg_aln) * (n_alns + 1)));
     if (n_alns) PG_CUDA(cudaMemcpyAsync(ctx->alns.p, alns, sizeof(pg_aln) * n_alns, cudaMemcpyHostToDevice, ctx->stream));
@@ -394,6 +442,7 @@ int pg_assemble_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_param
                           const pg_ex_params *ep, pg_seqdb **out_db,
                           pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns) {
     PG_CHECK(ctx && db && kp && rp && ep && out_db, "pg_assemble_iteration: null argument");
+    PG_TRY(db_ready(ctx, db));
     begin_call(ctx);
     pg_hit *dHits = nullptr; uint64_t nH = 0;
     PG_TRY(km_run(ctx, db, kp, &dHits, &nH));
@@ -419,6 +468,7 @@ int pg_assemble_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_param
 
 int pg_findassemblystart(pg_context *ctx, const pg_seqdb *db, const pg_aln *alns, uint64_t n_alns, pg_seqdb **out_db, int32_t **add_stop) {
     PG_CHECK(ctx && db && out_db && (alns || n_alns == 0), "pg_findassemblystart: null argument");
+    PG_TRY(db_ready(ctx, db));
     begin_call(ctx);
     PG_TRY(ctx->alns.reserve(sizeof(pg_aln) * (n_alns + 1)));
     if (n_alns) PG_CUDA(cudaMemcpyAsync(ctx->alns.p, alns, sizeof(pg_aln) * n_alns, cudaMemcpyHostToDevice, ctx->stream));
@@ -433,6 +483,7 @@ int pg_findassemblystart(pg_context *ctx, const pg_seqdb *db, const pg_aln *alns
 
 int pg_cyclecheck(pg_context *ctx, const pg_seqdb *db, int max_seq_len, uint32_t **split) {
     PG_CHECK(ctx && db && split, "pg_cyclecheck: null argument");
+    PG_TRY(db_ready(ctx, db));
     begin_call(ctx);
     unsigned *d = nullptr;
     PG_TRY(cc_run(ctx, db, max_seq_len, 22 /* setCycleCheckDefaults, cyclecheck.cpp:26-29 */, &d));
@@ -469,6 +520,7 @@ int pg_results_wait(pg_context *ctx, uint64_t ticket) {
 
 void pg_free_host(void *p) { if (p) release_pinned(p); }
 
+/* for a DB from pg_seqdb_upload_async the key statistics exist after its first use in a compute call */
 uint32_t pg_seqdb_max_key(const pg_seqdb *db) { return db ? db->max_key : 0; }
 
 void pg_shard_owner_range(uint32_t max_key, int rank, int world, uint32_t *lo, uint32_t *hi) {
@@ -479,6 +531,7 @@ void pg_shard_owner_range(uint32_t max_key, int rank, int world, uint32_t *lo, u
 
 int pg_shard_pairs(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, int world, uint64_t *counts) {
     PG_CHECK(ctx && db && kp && counts, "pg_shard_pairs: null argument");
+    PG_TRY(db_ready(ctx, db));
     begin_call(ctx);
     PG_TRY(km_shard_pairs(ctx, db, kp, world, counts));
     end_shard_phase(ctx, true);
@@ -487,6 +540,7 @@ int pg_shard_pairs(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, 
 
 int pg_shard_extract(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, int rank, int world, uint64_t *counts) {
     PG_CHECK(ctx && db && kp && counts, "pg_shard_extract: null argument");
+    PG_TRY(db_ready(ctx, db));
     begin_call(ctx);
     PG_TRY(km_shard_extract(ctx, db, kp, rank, world, counts));
     end_shard_phase(ctx, true);
@@ -496,6 +550,7 @@ int pg_shard_extract(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp
 int pg_shard_group(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, const void *device_records, uint64_t n_records,
                    uint64_t *rep_hist) {
     PG_CHECK(ctx && db && kp && rep_hist && (device_records || n_records == 0), "pg_shard_group: null argument");
+    PG_TRY(db_ready(ctx, db));
     begin_call(ctx);
     PG_TRY(km_shard_group(ctx, db, kp, device_records, n_records, rep_hist));
     end_shard_phase(ctx, false);
@@ -523,6 +578,7 @@ int pg_shard_finish(pg_context *ctx, const pg_seqdb *db, const void *device_pair
                     uint32_t own_lo, uint32_t own_hi, const pg_rs_params *rp, const pg_ex_params *ep,
                     pg_seqdb **out_db, pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns) {
     PG_CHECK(ctx && db && rp && ep && out_db && (device_pairs || n_pairs == 0), "pg_shard_finish: null argument");
+    PG_TRY(db_ready(ctx, db));
     begin_call(ctx);
     ctx->ownLo = own_lo; ctx->ownHi = own_hi;
     pg_hit *dHits = nullptr; uint64_t nH = 0;

@@ -112,4 +112,8 @@ struct pg_seqdb {
     bool dense_keys = false;
     bool borrowed = false;                // pg_seqdb_adopt: the arrays belong to the caller
     bool downloadPending = false;         // an asynchronous pg_seqdb_download is (or was) in flight on the copy stream
+    // pg_seqdb_upload_async: the host -> device copies run on the context's upload stream; evReady marks their end and the
+    // per-DB statistics (max length, residues, ...) are computed at first use (pg::db_ready)
+    cudaEvent_t evReady = nullptr;
+    bool uploadPending = false;
 };

@@ -17,6 +17,7 @@ struct pg_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr;         // device -> host copies of finished stage results, overlapped with the next stage
+    cudaStream_t h2dStream = nullptr;          // pg_seqdb_upload_async: the next input travels while the current iteration computes
     cudaEvent_t evCopyReady = nullptr;
     // asynchronous results (pg_set_async_results): the device -> host copies are only enqueued; tickets mark positions
     // of the copy stream.  evHitsCopied / evAlnsCopied guard the result buffers against the next call's writes.
@@ -68,6 +69,7 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
 // findassemblystart / cyclecheck (pg_next.cu); the returned device arrays live in ctx->nextWork until the next call
 int fs_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAlns, pg_seqdb **out, int **d_addStop);
 int cc_run(Context *ctx, const pg_seqdb *db, int maxSeqLen, int k, unsigned **d_split);
+int db_ready(Context *ctx, const pg_seqdb *db);   // completes a pg_seqdb_upload_async at the DB's first use
 int seqdb_finalize(Context *ctx, pg_seqdb *db);   // computes max_seq_len / residues / dense_keys on the device
 void seqdb_release(pg_seqdb *db, cudaStream_t s);
 // Small device -> host read-back (counters, totals) that does NOT go through the copy engine: a one-warp kernel stores

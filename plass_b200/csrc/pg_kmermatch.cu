@@ -11,6 +11,7 @@
 #include "pg_scan.cuh"
 #include "pg_tables.h"
 
+#include <cstring>
 #include <type_traits>
 
 namespace pg {
@@ -1808,10 +1809,15 @@ int km_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const Km
     unsigned *lists = ctx->lists.as<unsigned>();
     classify_kernel<<<(sHi - sLo + 255) / 256 + 1, 256, 0, s>>>(db->lens, sLo, sHi, n, c.k, lists, d_clsCount);
     ctx->launches += 2;
+    // small read-backs go through mapped pinned memory (pg::read_back), not the copy engine: a cudaMemcpyAsync would
+    // queue behind the previous iteration's result transfers that are still running on the copy stream
     unsigned long long h_total = 0; unsigned h_cls[4];
-    PG_CUDA(cudaMemcpyAsync(&h_total, d_total, sizeof(h_total), cudaMemcpyDeviceToHost, s));
-    PG_CUDA(cudaMemcpyAsync(h_cls, d_clsCount, sizeof(h_cls), cudaMemcpyDeviceToHost, s));
-    PG_CUDA(cudaStreamSynchronize(s));
+    {
+        unsigned long long hb[10];                     // [0] capacity estimate, [8..9] the four class counters
+        PG_TRY(read_back(ctx, hb, d_total, sizeof(hb)));
+        h_total = hb[0];
+        memcpy(h_cls, hb + 8, sizeof(h_cls));
+    }
     const unsigned long long cap = h_total + 1;
     PG_TRY(ctx->recA.reserve(sizeof(Rec) * cap));
     PG_TRY(ctx->recB.reserve(sizeof(Rec) * cap));
@@ -1832,8 +1838,7 @@ int km_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const Km
         ctx->launches++;
     }
     unsigned long long h_out = 0;
-    PG_CUDA(cudaMemcpyAsync(&h_out, d_outCount, sizeof(h_out), cudaMemcpyDeviceToHost, s));
-    PG_CUDA(cudaStreamSynchronize(s));
+    PG_TRY(read_back(ctx, &h_out, d_outCount, sizeof(h_out)));
     PG_CUDA(cudaGetLastError());
     PG_CHECK(h_out <= cap, "kmermatcher: k-mer array overflow");
     *nRecords = h_out;
@@ -1884,9 +1889,8 @@ static int km_group_bucketed(Context *ctx, const KmConst &c, uint64_t nRecords, 
     ctx->launches += 3;
     cudaEventRecord(ctx->ev[EV_GROUP_END], s);
     unsigned long long h = 0; unsigned over = 0;
-    PG_CUDA(cudaMemcpyAsync(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, s));
-    PG_CUDA(cudaMemcpyAsync(&over, d_over, sizeof(over), cudaMemcpyDeviceToHost, s));
-    PG_CUDA(cudaStreamSynchronize(s));
+    PG_TRY(read_back(ctx, &h, d_cnt, sizeof(h)));
+    PG_TRY(read_back(ctx, &over, d_over, sizeof(over)));
     PG_CUDA(cudaGetLastError());
     if (over) {
         // the records are only permuted (still all in `sorted`); hand them back in recA for the full sort
@@ -1928,8 +1932,7 @@ int km_group(Context *ctx, const pg_seqdb *db, const KmConst &c, uint64_t nRecor
     ctx->launches++;
     cudaEventRecord(ctx->ev[EV_GROUP_END], s);
     unsigned long long h = 0;
-    PG_CUDA(cudaMemcpyAsync(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, s));
-    PG_CUDA(cudaStreamSynchronize(s));
+    PG_TRY(read_back(ctx, &h, d_cnt, sizeof(h)));
     PG_CUDA(cudaGetLastError());
     *nPairs = h;
     ctx->pairsInA = (outBuf == ctx->recA.as<Rec>());
@@ -1985,9 +1988,11 @@ static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, 
     ctx->launches += 5;
     PG_TRY(exclusive_scan_u32(d_hcnt, d_hoff, nKeys, d_total, bb + oScan, scan_workspace_bytes(nKeys), s, &ctx->launches));
     unsigned long long h = 0; unsigned over = 0;
-    PG_CUDA(cudaMemcpyAsync(&h, d_total, sizeof(h), cudaMemcpyDeviceToHost, s));
-    PG_CUDA(cudaMemcpyAsync(&over, d_over, sizeof(over), cudaMemcpyDeviceToHost, s));
-    PG_CUDA(cudaStreamSynchronize(s));
+    {
+        unsigned long long hb[3];                      // small[32]: overflow flag (low word) ... small[34]: total hits
+        PG_TRY(read_back(ctx, hb, d_over, sizeof(hb)));
+        over = (unsigned) hb[0]; h = hb[2];
+    }
     PG_CUDA(cudaGetLastError());
     if (over) { *pairsIO = sorted; *tmpIO = other; return 0; }
     PG_TRY(ctx->hits.reserve(sizeof(pg_hit) * (h + 1)));
@@ -2031,8 +2036,7 @@ int km_reduce(Context *ctx, const pg_seqdb *db, Rec *pairs, Rec *tmp, uint64_t n
     else reduce_count_kernel<false><<<(unsigned) blocks, 256, 0, s>>>(sorted, nPairs, d_counts);
     scan_counts_kernel<<<1, 1024, 0, s>>>(d_counts, blocks, d_offsets, d_total);
     unsigned long long h = 0;
-    PG_CUDA(cudaMemcpyAsync(&h, d_total, sizeof(h), cudaMemcpyDeviceToHost, s));
-    PG_CUDA(cudaStreamSynchronize(s));
+    PG_TRY(read_back(ctx, &h, d_total, sizeof(h)));
     PG_TRY(ctx->hits.reserve(sizeof(pg_hit) * (h + 1)));
     PG_CUDA(cudaStreamWaitEvent(s, ctx->evHitsCopied, 0));
     if (wide) reduce_emit_kernel<true><<<(unsigned) blocks, 256, 0, s>>>(sorted, nPairs, d_offsets, ctx->hits.as<pg_hit>());

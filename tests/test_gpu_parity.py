@@ -312,6 +312,29 @@ def test_whole_iteration_at_high_coverage_matches_oracle(coverage, n_reads, ctx)
         coverage, db.n, len(whits), per_rep.max(), per_query.max()))
 
 
+def test_async_upload_equals_blocking(golden_root, ctx):
+    """pg_seqdb_upload_async: the copies are only enqueued (upload stream) and the DB is completed at its first use."""
+    import torch
+    d, man = golden_case("synth_aa", golden_root)
+    s = [x for x in man["steps"] if x["cmd"] == "kmermatcher"][0]
+    seq = mmseqsdb.read_db(os.path.join(d, s["dbs"][0]))
+    pinned = mmseqsdb.DB(torch.from_numpy(seq.data.copy()).pin_memory().numpy(), torch.from_numpy(seq.keys.copy()).pin_memory().numpy(),
+                         torch.from_numpy(seq.offsets.view(np.int64).copy()).pin_memory().numpy().view(np.uint64),
+                         torch.from_numpy(seq.lens.view(np.int32).copy()).pin_memory().numpy().view(np.uint32), seq.dbtype)
+    kp = gpu_km(s["args"], False)
+    a = ctx.upload(seq)
+    want = ctx.kmermatcher(a, kp)
+    a.free()
+    b1, b2, b3 = ctx.upload_async(pinned), ctx.upload_async(pinned), ctx.upload_async(pinned)
+    got1 = ctx.kmermatcher(b1, kp)
+    back = b2.download()                       # first use = a download
+    got2 = ctx.kmermatcher(b2, kp)
+    b1.free(); b2.free(); b3.free()            # b3 is released without ever being used
+    for f in ("rep", "target", "score", "diag"):
+        assert np.array_equal(got1[f], want[f]) and np.array_equal(got2[f], want[f]), f
+    assert back.entries_by_key() == seq.entries_by_key()
+
+
 def test_async_results_equal_blocking(golden_root, ctx):
     """pg_set_async_results: two iterations in flight, results awaited by ticket, must equal the blocking calls."""
     from plass_b200 import synth
