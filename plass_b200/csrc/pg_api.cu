@@ -261,6 +261,8 @@ int pg_init(int device, pg_context **out) {
     }
     for (int i = 0; i < EV_COUNT; i++) PG_CUDA(cudaEventCreate(&ctx->ev[i]));
     memset(&ctx->timings, 0, sizeof(ctx->timings));
+    if (const char *e = getenv("PLASS_B200_BUCKET_TARGET")) { const int b = atoi(e); if (b >= 64 && b <= 1200) ctx->bucketTarget = (unsigned) b; }
+    if (const char *e = getenv("PLASS_B200_DIGIT_BITS")) { const int b = atoi(e); if (b >= 8 && b <= 10) ctx->digitBits = b; }
     *out = ctx;
     return 0;
 }
@@ -600,16 +602,29 @@ int pg_shard_finish(pg_context *ctx, const pg_seqdb *db, const void *device_pair
 // tests: force the full-sort group path (1) or allow the bucketed hash join (0)
 int pg_debug_force_full_sort(pg_context *ctx, int on) { if (!ctx) return 1; ctx->forceFullSort = on != 0; return 0; }
 
+// radix digit width of the fast-path sorts: 8 (256-bin passes), 9 or 10 (wide-digit kernel, fewer passes)
+int pg_debug_set_digit_bits(pg_context *ctx, int bits) {
+    PG_CHECK(ctx && bits >= 8 && bits <= 10, "pg_debug_set_digit_bits: 8, 9 or 10");
+    ctx->digitBits = bits;
+    return 0;
+}
+
 // micro-benchmark of the radix sort on device-resident pseudo-random records: returns ms per scatter pass
+int pg_debug_radix_bench_w(pg_context *ctx, uint64_t n, int items, int passes, int digit_bits, float *ms_per_pass);
 int pg_debug_radix_bench(pg_context *ctx, uint64_t n, int items, int passes, float *ms_per_pass) {
+    return pg_debug_radix_bench_w(ctx, n, items, passes, 8, ms_per_pass);
+}
+int pg_debug_radix_bench_w(pg_context *ctx, uint64_t n, int items, int passes, int digit_bits, float *ms_per_pass) {
     PG_CHECK(ctx && ms_per_pass, "pg_debug_radix_bench: null argument");
+    PG_CHECK(digit_bits >= 8 && digit_bits <= 10, "pg_debug_radix_bench: digit bits must be 8, 9 or 10");
     cudaSetDevice(ctx->device);
     radix_set_items(items);
     RadixPlan plan; plan.npasses = 0;
-    plan_add_bits(plan, 0, 0, 8 * passes);
+    if (digit_bits > 8) plan_add_bits_w(plan, 0, 0, digit_bits * passes, digit_bits);
+    else plan_add_bits(plan, 0, 0, 8 * passes);
     PG_TRY(ctx->recA.reserve(sizeof(Rec) * (n + 1)));
     PG_TRY(ctx->recB.reserve(sizeof(Rec) * (n + 1)));
-    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(n)));
+    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(n, digit_bits)));
     std::vector<unsigned long long> seed(1 << 20);
     unsigned long long x = 88172645463325252ull;
     for (auto &v : seed) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; v = x; }
@@ -634,10 +649,13 @@ int pg_debug_radix_sort(pg_context *ctx, uint64_t *recs /* n x 2 u64, in place *
     PG_CHECK(ctx && recs, "pg_debug_radix_sort: null argument");
     cudaSetDevice(ctx->device);
     RadixPlan plan; plan.npasses = 0;
-    for (int i = 0; i < nRanges; i++) plan_add_bits(plan, word[i], lo[i], hi[i]);
+    for (int i = 0; i < nRanges; i++) {
+        if (ctx->digitBits > 8) plan_add_bits_w(plan, word[i], lo[i], hi[i], ctx->digitBits);
+        else plan_add_bits(plan, word[i], lo[i], hi[i]);
+    }
     PG_TRY(ctx->recA.reserve(sizeof(Rec) * (n + 1)));
     PG_TRY(ctx->recB.reserve(sizeof(Rec) * (n + 1)));
-    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(n)));
+    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(n, ctx->digitBits)));
     PG_CUDA(cudaMemcpyAsync(ctx->recA.p, recs, sizeof(Rec) * n, cudaMemcpyHostToDevice, ctx->stream));
     Rec *sorted = nullptr;
     uint64_t launches = 0;

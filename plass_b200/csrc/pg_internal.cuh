@@ -30,6 +30,8 @@ struct pg_context {
     unsigned long long *hostStage = nullptr;   // mapped pinned words: the kernels' small results are read back through here (pg::read_back)
     cudaEvent_t ev[pg::EV_COUNT];
     pg::DevBuf small, lists, recA, recB, radixWs, scratch, blockCounts, hits, alnAll, alns, flags, exWork, exSegs, exMeta, exLists, ntTab, buckets, buckets2, wideTabs, nextWork;
+    unsigned bucketTarget = 512;  // average records per bucket of the partial-key partition (<= 700: small hash-join instance first)
+    int digitBits = 8;            // radix digit width of the two fast-path sorts (8: 256 bins; 9 / 10: wide-digit kernel)
     bool forceFullSort = false;   // tests: take the 8-pass sort + group_kernel path instead of the bucketed hash join
     unsigned ntTabN = 0;
     bool pairsInA = false;

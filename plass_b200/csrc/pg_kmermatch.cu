@@ -1852,13 +1852,15 @@ static int km_group_bucketed(Context *ctx, const KmConst &c, uint64_t nRecords, 
     cudaStream_t s = ctx->stream;
     *ok = false;
     int B = 1;
-    while (B < 24 && (nRecords >> B) > 512) B++;          // ~512 records per bucket on average
-    if ((nRecords >> B) > 700) return 0;                  // more than 2^24 buckets would be needed: use the full sort
+    while (B < 24 && (nRecords >> B) > ctx->bucketTarget) B++;          // ~512 records per bucket on average
+    if ((nRecords >> B) > ctx->bucketTarget + ctx->bucketTarget / 3) return 0;                  // more than 2^24 buckets would be needed: use the full sort
+    const bool bigFirst = ctx->bucketTarget > 560;        // average bucket beyond the small instance's capacity (768 records)
     const unsigned nBuckets = 1u << B;
     const unsigned long long hashMask = c.nt ? ~(1ULL << 63) : ~0ULL;   // nt: bit 63 is the strand flag (kmermatcher.h:77-96)
     RadixPlan plan; plan.npasses = 0;
-    plan_add_hash_bits(plan, hashMask, 0, B);
-    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nRecords)));
+    if (ctx->digitBits > 8) plan_add_hash_bits_w(plan, hashMask, 0, B, ctx->digitBits);
+    else plan_add_hash_bits(plan, hashMask, 0, B);
+    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nRecords, ctx->digitBits)));
     PG_TRY(ctx->buckets.reserve(sizeof(unsigned long long) * 2 * (size_t) nBuckets + 64));
     unsigned long long *d_start = ctx->buckets.as<unsigned long long>();
     unsigned long long *d_end = d_start + nBuckets;
@@ -1882,10 +1884,15 @@ static int km_group_bucketed(Context *ctx, const KmConst &c, uint64_t nRecords, 
     unsigned *d_bigList = ctx->blockCounts.as<unsigned>() + 4;
     unsigned *d_bigCnt = ctx->blockCounts.as<unsigned>();
     PG_CUDA(cudaMemsetAsync(d_bigCnt, 0, sizeof(unsigned), s));
-    hash_group_kernel<HG_TABLE_SMALL, HG_ITEMS_SMALL, 0><<<std::min<unsigned>(nBuckets, NUM_SMS * 64), HG_THREADS, 0, s>>>(
-        sorted, d_start, d_end, nBuckets, hashMask, d_min, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_over);
-    hash_group_kernel<HG_TABLE_BIG, HG_ITEMS_BIG, 1><<<NUM_SMS * 4, HG_THREADS, 0, s>>>(
-        sorted, d_start, d_end, nBuckets, hashMask, d_min, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_over);
+    if (bigFirst) {
+        hash_group_kernel<HG_TABLE_BIG, HG_ITEMS_BIG, 0><<<std::min<unsigned>(nBuckets, NUM_SMS * 32), HG_THREADS, 0, s>>>(
+            sorted, d_start, d_end, nBuckets, hashMask, d_min, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_over);
+    } else {
+        hash_group_kernel<HG_TABLE_SMALL, HG_ITEMS_SMALL, 0><<<std::min<unsigned>(nBuckets, NUM_SMS * 64), HG_THREADS, 0, s>>>(
+            sorted, d_start, d_end, nBuckets, hashMask, d_min, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_over);
+        hash_group_kernel<HG_TABLE_BIG, HG_ITEMS_BIG, 1><<<NUM_SMS * 4, HG_THREADS, 0, s>>>(
+            sorted, d_start, d_end, nBuckets, hashMask, d_min, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_over);
+    }
     ctx->launches += 3;
     cudaEventRecord(ctx->ev[EV_GROUP_END], s);
     unsigned long long h = 0; unsigned over = 0;
@@ -1949,8 +1956,9 @@ static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, 
     const unsigned nKeys = db->max_key + 1;
     const unsigned keyLo = std::min(ctx->ownLo, nKeys), keyHi = std::min(ctx->ownHi, nKeys);   // representatives of this rank
     RadixPlan plan; plan.npasses = 0;
-    plan_add_bits(plan, 0, 32, 32 + keyBits);
-    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nPairs)));
+    if (ctx->digitBits > 8) plan_add_bits_w(plan, 0, 32, 32 + keyBits, ctx->digitBits);
+    else plan_add_bits(plan, 0, 32, 32 + keyBits);
+    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nPairs, ctx->digitBits)));
     Rec *sorted = pairs;
     PG_TRY(radix_sort(pairs, tmp, nPairs, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches));
     cudaEventRecord(ctx->ev[EV_SORT2_END], s);

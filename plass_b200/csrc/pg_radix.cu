@@ -22,38 +22,38 @@ __device__ __forceinline__ void st_volatile_u32(unsigned *p, unsigned v) {
 
 // ---- histograms of all passes in one read -------------------------------------------------------
 __global__ void __launch_bounds__(512) radix_hist_kernel(const Rec *__restrict__ in, unsigned long long n, RadixPlan plan,
-                                                         unsigned long long *__restrict__ ghist) {
-    __shared__ unsigned sh[RADIX_MAX_PASSES * 256];
+                                                         unsigned long long *__restrict__ ghist, int stride) {
+    extern __shared__ unsigned sh[];          // npasses x stride counters (stride = 256, or 512 / 1024 with wide digits)
     const int np = plan.npasses;
-    for (int i = threadIdx.x; i < np * 256; i += blockDim.x) sh[i] = 0;
+    for (int i = threadIdx.x; i < np * stride; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long gstride = (unsigned long long) gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(in) + i);
         Rec r;
         r.w0 = ((unsigned long long) raw.y << 32) | raw.x;
         r.w1 = ((unsigned long long) raw.w << 32) | raw.z;
 #pragma unroll 4
-        for (int p = 0; p < np; p++) atomicAdd(&sh[p * 256 + digit_of(r, plan.pass[p])], 1u);
+        for (int p = 0; p < np; p++) atomicAdd(&sh[p * stride + digit_of(r, plan.pass[p])], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < np * 256; i += blockDim.x)
+    for (int i = threadIdx.x; i < np * stride; i += blockDim.x)
         if (sh[i]) atomicAdd(&ghist[i], (unsigned long long) sh[i]);
 }
 
-// exclusive scan of each pass's 256 bins -> bases[p][portion 0][256]
+// exclusive scan of each pass's bins -> bases[p][portion 0][stride]
 __global__ void radix_scan_kernel(const unsigned long long *__restrict__ ghist, unsigned long long *__restrict__ bases,
-                                  int portionsPlus1) {
-    __shared__ unsigned long long s[256];
+                                  int portionsPlus1, int stride) {
+    __shared__ unsigned long long s[1024];
     const int p = blockIdx.x, t = threadIdx.x;
-    s[t] = ghist[p * 256 + t];
+    for (int i = t; i < stride; i += blockDim.x) s[i] = ghist[p * stride + i];
     __syncthreads();
     if (t == 0) {
         unsigned long long run = 0;
-        for (int i = 0; i < 256; i++) { unsigned long long c = s[i]; s[i] = run; run += c; }
+        for (int i = 0; i < stride; i++) { unsigned long long c = s[i]; s[i] = run; run += c; }
     }
     __syncthreads();
-    bases[((size_t) p * portionsPlus1) * 256 + t] = s[t];
+    for (int i = t; i < stride; i += blockDim.x) bases[((size_t) p * portionsPlus1) * stride + i] = s[i];
 }
 
 // ---- one pass over one portion ------------------------------------------------------------------
@@ -146,6 +146,8 @@ __global__ void __launch_bounds__(RADIX_THREADS, MINBLOCKS) radix_scatter_kernel
     for (int r = 0; r < ITEMS; r++) {
         const unsigned idx = w * (ITEMS * 32) + r * 32 + lane;
         if (idx < count) {
+            // (keeping the digit from the ranking step in registers / next to the record was measured: no gain, the pass is
+            // bound by the latency of its dependent phases, not by recomputing the hash)
             const unsigned d = digit_of(rec[r], dp);
             const unsigned pos = digitStart[d] + warpCnt[w][d] + rank[r];
             tileRecs[pos] = rec[r];
@@ -192,6 +194,159 @@ __global__ void __launch_bounds__(RADIX_THREADS, MINBLOCKS) radix_scatter_kernel
     }
 }
 
+// Wide-digit instance (BITS = 9 / 10: 512 / 1024 bins, DPT = 2 / 4 digits per thread).  Same structure as the 256-bin
+// kernel above; the per-digit start inside the tile is folded into the warp-private counters (a tile holds < 65536
+// records) so that shared memory stays at 16 B x tile + 2 B x 8 x BINS + 8 B x BINS (72 KB for 1024 bins: 3 CTAs / SM).
+template <int ITEMS, int MINBLOCKS, int BITS>
+__global__ void __launch_bounds__(RADIX_THREADS, MINBLOCKS) radix_scatter_wide_kernel(
+    const Rec *__restrict__ in, Rec *__restrict__ out, unsigned long long portionStart, unsigned long long portionEnd,
+    DigitPass dp, const unsigned long long *__restrict__ gbase, unsigned long long *__restrict__ gbaseNext,
+    unsigned *status, unsigned *ticket, unsigned numTiles) {
+    constexpr int BINS = 1 << BITS, DPT = BINS / RADIX_THREADS, WARPS = RADIX_THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Rec *tileRecs = reinterpret_cast<Rec *>(smem_raw);
+    unsigned short *tileDig = reinterpret_cast<unsigned short *>(smem_raw + (size_t) RADIX_THREADS * ITEMS * sizeof(Rec));
+    __shared__ unsigned short warpCnt[WARPS][BINS];
+    __shared__ long long goff[BINS];
+    __shared__ unsigned warpTotals[WARPS];
+    __shared__ unsigned sTile;
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) sTile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < WARPS * BINS; i += RADIX_THREADS) (&warpCnt[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned tile = sTile;
+    const unsigned long long tileBase = portionStart + (unsigned long long) tile * (RADIX_THREADS * ITEMS);
+    const unsigned count = (unsigned) min((unsigned long long) (RADIX_THREADS * ITEMS), portionEnd - tileBase);
+
+    Rec rec[ITEMS];
+    unsigned short rank[ITEMS];
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        const unsigned idx = w * (ITEMS * 32) + r * 32 + lane;
+        if (idx < count) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(in + tileBase) + idx);
+            rec[r].w0 = ((unsigned long long) raw.y << 32) | raw.x;
+            rec[r].w1 = ((unsigned long long) raw.w << 32) | raw.z;
+        } else {
+            rec[r].w0 = 0; rec[r].w1 = 0;
+        }
+    }
+    const unsigned ltMask = (1u << lane) - 1u;
+    unsigned dpack[(ITEMS + 1) / 2];
+#pragma unroll
+    for (int r = 0; r < (ITEMS + 1) / 2; r++) dpack[r] = 0;
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        const unsigned idx = w * (ITEMS * 32) + r * 32 + lane;
+        const bool valid = idx < count;
+        const unsigned d = valid ? digit_of(rec[r], dp) : (unsigned) BINS;
+        if (valid) dpack[r >> 1] |= d << ((r & 1) * 16);
+        const unsigned m = __match_any_sync(0xFFFFFFFFu, d);
+        unsigned c = 0;
+        if (valid) c = warpCnt[w][d];
+        rank[r] = (unsigned short) (c + __popc(m & ltMask));
+        __syncwarp();
+        if (valid && (m & ltMask) == 0) warpCnt[w][d] = (unsigned short) (c + __popc(m));
+        __syncwarp();
+    }
+    __syncthreads();
+    // thread tid owns the digits j * 256 + tid
+    unsigned cnt[DPT], dStart[DPT];
+#pragma unroll
+    for (int j = 0; j < DPT; j++) {
+        const int d = j * RADIX_THREADS + tid;
+        unsigned run = 0;
+#pragma unroll
+        for (int ww = 0; ww < WARPS; ww++) {
+            const unsigned c = warpCnt[ww][d];
+            warpCnt[ww][d] = (unsigned short) run;
+            run += c;
+        }
+        cnt[j] = run;
+        if (tile == 0) st_volatile_u32(&status[d], (run << 2) | FLAG_INC);
+        else st_volatile_u32(&status[(size_t) tile * BINS + d], (run << 2) | FLAG_AGG);
+    }
+    // exclusive scan over all BINS digits in digit order
+    {
+        unsigned carry = 0;
+#pragma unroll
+        for (int j = 0; j < DPT; j++) {
+            unsigned v = cnt[j];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, v, o);
+                if (lane >= o) v += nb;
+            }
+            if (lane == 31) warpTotals[w] = v;
+            __syncthreads();
+            unsigned woff = 0, total = 0;
+#pragma unroll
+            for (int ww = 0; ww < WARPS; ww++) { const unsigned t = warpTotals[ww]; woff += (ww < w) ? t : 0u; total += t; }
+            dStart[j] = carry + woff + v - cnt[j];
+            carry += total;
+            __syncthreads();
+        }
+    }
+    // fold the digit start into the warp-private prefixes: position in the tile = warpCnt[w][d] + rank
+#pragma unroll
+    for (int j = 0; j < DPT; j++) {
+        const int d = j * RADIX_THREADS + tid;
+#pragma unroll
+        for (int ww = 0; ww < WARPS; ww++) warpCnt[ww][d] = (unsigned short) (warpCnt[ww][d] + dStart[j]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        const unsigned idx = w * (ITEMS * 32) + r * 32 + lane;
+        if (idx < count) {
+            const unsigned d = (dpack[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu;
+            const unsigned pos = (unsigned) warpCnt[w][d] + rank[r];
+            tileRecs[pos] = rec[r];
+            tileDig[pos] = (unsigned short) d;
+        }
+    }
+    // decoupled look-back per owned digit
+#pragma unroll
+    for (int j = 0; j < DPT; j++) {
+        const int d = j * RADIX_THREADS + tid;
+        unsigned long long prev = 0;
+        if (tile > 0) {
+            long long ll = (long long) tile - 1;
+            bool done = false;
+            while (!done) {
+                unsigned v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const long long idx = ll - u;
+                    v[u] = (idx >= 0) ? ld_volatile_u32(&status[(size_t) idx * BINS + d]) : FLAG_INC;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (done) break;
+                    const unsigned f = v[u] & 3u;
+                    if (f == 0u) break;
+                    prev += v[u] >> 2;
+                    ll--;
+                    if (f == FLAG_INC) done = true;
+                }
+            }
+            st_volatile_u32(&status[(size_t) tile * BINS + d], ((unsigned) (prev + cnt[j]) << 2) | FLAG_INC);
+        }
+        const unsigned long long base = gbase[d];
+        goff[d] = (long long) (base + prev) - (long long) dStart[j];
+        if (tile == numTiles - 1) gbaseNext[d] = base + prev + cnt[j];
+    }
+    __syncthreads();
+    for (unsigned j = tid; j < count; j += RADIX_THREADS) {
+        const Rec r = tileRecs[j];
+        const unsigned d = tileDig[j];
+        uint4 raw;
+        raw.x = (unsigned) r.w0; raw.y = (unsigned) (r.w0 >> 32); raw.z = (unsigned) r.w1; raw.w = (unsigned) (r.w1 >> 32);
+        reinterpret_cast<uint4 *>(out)[goff[d] + (long long) j] = raw;
+    }
+}
+
 static int g_items = 12;   // records per thread of the scatter kernel (8 / 12 / 16), see radix_set_items
 static inline unsigned long long tile_records() { return (unsigned long long) RADIX_THREADS * g_items; }
 constexpr unsigned long long PORTION_RECORDS = ((1ull << 30) / 12288 - 1) * 12288;   // look-back prefix < 2^30; multiple of every tile size
@@ -222,10 +377,36 @@ void plan_add_hash_bits(RadixPlan &plan, unsigned long long hashMask, int lo, in
     }
 }
 
-size_t radix_workspace_bytes(uint64_t n) {
-    const size_t hist = sizeof(unsigned long long) * RADIX_MAX_PASSES * 256;
-    const size_t bases = sizeof(unsigned long long) * RADIX_MAX_PASSES * (num_portions(n) + 1) * 256;
-    const size_t status = sizeof(unsigned) * (max_tiles(n) * 256 + 64);
+static int plan_stride(const RadixPlan &plan) {
+    unsigned mx = 255;
+    for (int p = 0; p < plan.npasses; p++) mx = plan.pass[p].mask > mx ? plan.pass[p].mask : mx;
+    return mx > 511 ? 1024 : (mx > 255 ? 512 : 256);
+}
+
+void plan_add_bits_w(RadixPlan &plan, int word, int lo, int hi, int digitBits) {
+    const int total = hi - lo;
+    if (total <= 0) return;
+    const int nd = (total + digitBits - 1) / digitBits;
+    int b = lo;
+    for (int i = 0; i < nd; i++) {
+        const int bits = (total - (b - lo) + (nd - i) - 1) / (nd - i);      // spread the bits evenly over the digits
+        DigitPass &p = plan.pass[plan.npasses++];
+        p.word = word; p.shift = b; p.mask = (1u << bits) - 1u; p.hashed = 0; p.hashMask = 0;
+        b += bits;
+    }
+}
+
+void plan_add_hash_bits_w(RadixPlan &plan, unsigned long long hashMask, int lo, int hi, int digitBits) {
+    const int first = plan.npasses;
+    plan_add_bits_w(plan, 0, lo, hi, digitBits);
+    for (int p = first; p < plan.npasses; p++) { plan.pass[p].hashed = 1; plan.pass[p].hashMask = hashMask; }
+}
+
+size_t radix_workspace_bytes(uint64_t n, int maxDigitBits) {
+    const size_t stride = maxDigitBits > 9 ? 1024 : (maxDigitBits > 8 ? 512 : 256);
+    const size_t hist = sizeof(unsigned long long) * RADIX_MAX_PASSES * stride;
+    const size_t bases = sizeof(unsigned long long) * RADIX_MAX_PASSES * (num_portions(n) + 1) * stride;
+    const size_t status = sizeof(unsigned) * (max_tiles(n) * stride + 64);
     return hist + bases + status + 1024;
 }
 
@@ -234,28 +415,35 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
     *sorted = a;
     if (n == 0 || plan.npasses == 0) return 0;
     PG_CHECK(plan.npasses <= RADIX_MAX_PASSES, "radix_sort: too many passes");
-    PG_CHECK(workspace_bytes >= radix_workspace_bytes(n), "radix_sort: workspace too small");
+    const int stride = plan_stride(plan);
+    PG_CHECK(workspace_bytes >= radix_workspace_bytes(n, stride == 1024 ? 10 : (stride == 512 ? 9 : 8)), "radix_sort: workspace too small");
+    PG_CHECK((size_t) plan.npasses * stride * sizeof(unsigned) <= 48 * 1024, "radix_sort: too many wide passes for one histogram launch");
     static bool attrSet = false;
     const int dynSmem = (int) (tile_records() * sizeof(Rec));
+    const int dynSmemWide = (int) (tile_records() * (sizeof(Rec) + 2));    // wide digits: two bytes
     if (!attrSet) {
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int) sizeof(Rec)));
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) sizeof(Rec)));
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * (int) sizeof(Rec)));
+        PG_CUDA(cudaFuncSetAttribute(radix_scatter_wide_kernel<16, 2, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int) (sizeof(Rec) + 2)));
+        PG_CUDA(cudaFuncSetAttribute(radix_scatter_wide_kernel<12, 3, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) (sizeof(Rec) + 2)));
+        PG_CUDA(cudaFuncSetAttribute(radix_scatter_wide_kernel<16, 2, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int) (sizeof(Rec) + 2)));
+        PG_CUDA(cudaFuncSetAttribute(radix_scatter_wide_kernel<12, 3, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) (sizeof(Rec) + 2)));
         attrSet = true;
     }
     const unsigned long long portions = num_portions(n);
     unsigned char *ws = (unsigned char *) workspace;
     unsigned long long *ghist = (unsigned long long *) ws;
-    unsigned long long *bases = ghist + RADIX_MAX_PASSES * 256;
-    unsigned *status = (unsigned *) (bases + (size_t) RADIX_MAX_PASSES * (portions + 1) * 256);
-    const size_t statusWords = max_tiles(n) * 256 + 64;
+    unsigned long long *bases = ghist + (size_t) RADIX_MAX_PASSES * stride;
+    unsigned *status = (unsigned *) (bases + (size_t) RADIX_MAX_PASSES * (portions + 1) * stride);
+    const size_t statusWords = max_tiles(n) * (size_t) stride + 64;
 
-    PG_CUDA(cudaMemsetAsync(ghist, 0, sizeof(unsigned long long) * RADIX_MAX_PASSES * 256, stream));
+    PG_CUDA(cudaMemsetAsync(ghist, 0, sizeof(unsigned long long) * RADIX_MAX_PASSES * stride, stream));
     int histBlocks = (int) ((n + 512ull * 16 - 1) / (512ull * 16));
     if (histBlocks > NUM_SMS * 4) histBlocks = NUM_SMS * 4;
     if (histBlocks < 1) histBlocks = 1;
-    radix_hist_kernel<<<histBlocks, 512, 0, stream>>>(a, n, plan, ghist);
-    radix_scan_kernel<<<plan.npasses, 256, 0, stream>>>(ghist, bases, (int) (portions + 1));
+    radix_hist_kernel<<<histBlocks, 512, (size_t) plan.npasses * stride * sizeof(unsigned), stream>>>(a, n, plan, ghist, stride);
+    radix_scan_kernel<<<plan.npasses, 256, 0, stream>>>(ghist, bases, (int) (portions + 1), stride);
     if (launches) *launches += 2;
 
     Rec *src = a, *dst = b;
@@ -265,13 +453,20 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
             const unsigned long long ps = q * PORTION_RECORDS;
             const unsigned long long pe = (ps + PORTION_RECORDS < n) ? ps + PORTION_RECORDS : n;
             const unsigned tiles = (unsigned) ((pe - ps + tile_records() - 1) / tile_records());
-            PG_CUDA(cudaMemsetAsync(status, 0, sizeof(unsigned) * ((size_t) tiles * 256 + 64), stream));
+            const int bins = plan.pass[p].mask > 511 ? 1024 : (plan.pass[p].mask > 255 ? 512 : 256);
+            PG_CUDA(cudaMemsetAsync(status, 0, sizeof(unsigned) * ((size_t) tiles * bins + 64), stream));
             unsigned *ticket = status + statusWords - 32;
             PG_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), stream));
-            unsigned long long *gb = bases + ((size_t) p * (portions + 1) + q) * 256;
-            if (g_items == 16) radix_scatter_kernel<16, 2><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + 256, status, ticket, tiles);
-            else if (g_items == 12) radix_scatter_kernel<12, 3><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + 256, status, ticket, tiles);
-            else radix_scatter_kernel<8, 4><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + 256, status, ticket, tiles);
+            unsigned long long *gb = bases + ((size_t) p * (portions + 1) + q) * stride;
+            if (bins == 512) {
+                if (g_items == 16) radix_scatter_wide_kernel<16, 2, 9><<<tiles, RADIX_THREADS, dynSmemWide, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles);
+                else { PG_CHECK(g_items == 12, "radix_sort: wide digits need 12 or 16 records per thread"); radix_scatter_wide_kernel<12, 3, 9><<<tiles, RADIX_THREADS, dynSmemWide, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles); }
+            } else if (bins == 1024) {
+                if (g_items == 16) radix_scatter_wide_kernel<16, 2, 10><<<tiles, RADIX_THREADS, dynSmemWide, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles);
+                else { PG_CHECK(g_items == 12, "radix_sort: wide digits need 12 or 16 records per thread"); radix_scatter_wide_kernel<12, 3, 10><<<tiles, RADIX_THREADS, dynSmemWide, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles); }
+            } else if (g_items == 16) radix_scatter_kernel<16, 2><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles);
+            else if (g_items == 12) radix_scatter_kernel<12, 3><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles);
+            else radix_scatter_kernel<8, 4><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles);
             if (launches) *launches += 1;
         }
         Rec *t = src; src = dst; dst = t;

@@ -18,7 +18,7 @@ namespace pg {
 struct DigitPass {
     int word;            // 0 -> Rec::w0, 1 -> Rec::w1
     int shift;           // digit = (w >> shift) & mask
-    unsigned mask;       // <= 255
+    unsigned mask;       // <= 255 (8-bit digits) or <= 1023 (wide digits: 9 / 10 bits, see plan_add_bits_w)
     int hashed;          // 1: w is first replaced by mix64(w & hashMask) -- partition by hash bits instead of key bits
     unsigned long long hashMask;
 };
@@ -39,8 +39,8 @@ struct RadixPlan {
     int npasses;
 };
 
-// Workspace owned by the caller (sized by radix_workspace_bytes).
-size_t radix_workspace_bytes(uint64_t n);
+// Workspace owned by the caller (sized by radix_workspace_bytes); maxDigitBits = the widest digit of the plan (8..10).
+size_t radix_workspace_bytes(uint64_t n, int maxDigitBits = 8);
 
 // Sorts n records by the digits of plan (pass[0] least significant).  `a` holds the input, `b` is a
 // scratch buffer of the same size; *sorted points to whichever of the two holds the result.
@@ -52,5 +52,10 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
 void plan_add_bits(RadixPlan &plan, int word, int lo, int hi);
 // same over bits [lo, hi) of mix64(w0 & hashMask)
 void plan_add_hash_bits(RadixPlan &plan, unsigned long long hashMask, int lo, int hi);
+// Wide digits: the bit range is cut into ceil((hi-lo)/digitBits) digits of (almost) equal width <= digitBits (8..10).
+// A 512- or 1024-bin pass costs a little more than a 256-bin pass (status words, shorter store runs) but a 20-bit key
+// takes 2 passes instead of 3.
+void plan_add_bits_w(RadixPlan &plan, int word, int lo, int hi, int digitBits);
+void plan_add_hash_bits_w(RadixPlan &plan, unsigned long long hashMask, int lo, int hi, int digitBits);
 
 }  // namespace pg

@@ -45,6 +45,29 @@ def test_radix_sort_matches_numpy(ctx):
     assert np.array_equal(got, recs[np.argsort(key, kind="stable")])
 
 
+@pytest.mark.parametrize("bits", [9, 10])
+def test_wide_digit_radix_and_kmermatcher(bits, golden_root, ctx):
+    """512- / 1024-bin radix passes (radix_scatter_wide_kernel): sort results and the whole kmermatcher stay identical."""
+    lib = api.load_library()
+    assert lib.pg_debug_set_digit_bits(ctx.handle, bits) == 0
+    try:
+        rng = np.random.default_rng(7)
+        for n in (1, 33, 3072, 3073, 100003, 1 << 20):
+            recs = rng.integers(0, 1 << 63, size=(n, 2), dtype=np.uint64)
+            recs[: n // 2, 0] &= np.uint64(0x3FF)          # heavy duplicates exercise stability
+            got = ctx.debug_radix_sort(recs.copy(), [(0, 0, 40)])
+            key = recs[:, 0] & np.uint64((1 << 40) - 1)
+            assert np.array_equal(got, recs[np.argsort(key, kind="stable")]), (bits, n)
+        recs = rng.integers(0, 1 << 63, size=(300000, 2), dtype=np.uint64)
+        got = ctx.debug_radix_sort(recs.copy(), [(1, 0, 16), (0, 32, 55)])
+        key = (((recs[:, 0] >> np.uint64(32)) & np.uint64((1 << 23) - 1)) << np.uint64(16)) | (recs[:, 1] & np.uint64(0xFFFF))
+        assert np.array_equal(got, recs[np.argsort(key, kind="stable")])
+        for case in CASES:
+            _kmermatcher_case(case, golden_root, ctx)
+    finally:
+        lib.pg_debug_set_digit_bits(ctx.handle, 8)
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_extract_matches_oracle(case, golden_root, ctx):
     d, man = golden_case(case, golden_root)
