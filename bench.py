@@ -384,7 +384,7 @@ def main():
                 nbytes = sum(int(a.nbytes) for a in pending[1:])
                 return nbytes
             run_pipelined(2)                                   # warm-up: two sets of pinned result blocks
-            k = max(args.steps, 3)
+            k = max(args.steps, 8)                             # long enough that the first upload and the final drain are amortised
             barrier()
             t0 = time.perf_counter()
             d2h = run_pipelined(k)
