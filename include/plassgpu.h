@@ -160,6 +160,11 @@ int pg_assemble_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_param
  *                       at which sequence i repeats itself (circular / terminally redundant), 0 = not reported.  The
  *                       caller writes the reported sequences (--chop-cycle: the first split[i] residues). */
 int pg_findassemblystart(pg_context *ctx, const pg_seqdb *db, const pg_aln *alns, uint64_t n_alns, pg_seqdb **out_db, int32_t **add_stop);
+/* plass STEP 0 fused (data/assemble.sh:88-151 with STEP = 0): kmermatcher -> rescorediagonal -> findassemblystart ->
+ * kmermatcher -> rescorediagonal -> assembleresults without leaving HBM.  corrected_db (optional) = corrected_seqs,
+ * out_db = assembly_0; hits / alns (optional, pinned) = pref_corrected_0 / aln_corrected_0. */
+int pg_assemble_step0(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, const pg_rs_params *rp, const pg_ex_params *ep,
+                      pg_seqdb **corrected_db, pg_seqdb **out_db, pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns);
 int pg_cyclecheck(pg_context *ctx, const pg_seqdb *db, int max_seq_len, uint32_t **split);
 
 /* Asynchronous result transfer.  The reference workflow writes pref_N / aln_N / assembly_N to disk while the next

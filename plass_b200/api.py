@@ -274,6 +274,23 @@ class Context:
         out.dbtype = ddb.dbtype
         return out, _take(st, ddb.n, np.dtype("<i4"))
 
+    def assemble_step0(self, ddb, kp, rp, ep, want_intermediates=False):
+        """plass STEP 0 fused in HBM.  Returns (corrected DeviceSeqDB, assembly_0 DeviceSeqDB, hits or None, alns or None);
+        hits / alns are those of the corrected pass (pref_corrected_0 / aln_corrected_0)."""
+        hc, ho = C.c_void_p(), C.c_void_p()
+        if want_intermediates:
+            hp, hn, ap, an = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+            _check(load_library().pg_assemble_step0(self.handle, ddb.handle, C.byref(kp), C.byref(rp), C.byref(ep), C.byref(hc), C.byref(ho),
+                                                    C.byref(hp), C.byref(hn), C.byref(ap), C.byref(an)), "pg_assemble_step0")
+            hits, alns = _take(hp, hn.value, HIT), _take(ap, an.value, ALN)
+        else:
+            _check(load_library().pg_assemble_step0(self.handle, ddb.handle, C.byref(kp), C.byref(rp), C.byref(ep), C.byref(hc), C.byref(ho),
+                                                    None, None, None, None), "pg_assemble_step0")
+            hits = alns = None
+        corr, out = DeviceSeqDB(self, hc), DeviceSeqDB(self, ho)
+        corr.dbtype = out.dbtype = ddb.dbtype
+        return corr, out, hits, alns
+
     # cyclecheck (src/assembler/cyclecheck.cpp:71-274)
     def cyclecheck(self, ddb, max_seq_len):
         """Split diagonal per sequence (uint32, 0 = not circular)."""

@@ -468,6 +468,35 @@ int pg_assemble_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_param
     return 0;
 }
 
+// plass STEP 0 in one call (data/assemble.sh:88-151 with STEP = 0): kmermatcher -> rescorediagonal -> findassemblystart ->
+// kmermatcher -> rescorediagonal -> assembleresults, everything between the input DB and assembly_0 stays in HBM.
+int pg_assemble_step0(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, const pg_rs_params *rp, const pg_ex_params *ep,
+                      pg_seqdb **corrected_db, pg_seqdb **out_db, pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns) {
+    PG_CHECK(ctx && db && kp && rp && ep && out_db, "pg_assemble_step0: null argument");
+    PG_TRY(db_ready(ctx, db));
+    begin_call(ctx);
+    pg_hit *dHits = nullptr; uint64_t nH = 0;
+    pg_aln *dAlns = nullptr; uint64_t nA = 0;
+    PG_TRY(km_run(ctx, db, kp, &dHits, &nH));                       // pref_0
+    PG_TRY(rs_run(ctx, db, dHits, nH, rp, &dAlns, &nA));            // aln_0
+    pg_seqdb *corr = nullptr;
+    PG_TRY(fs_run(ctx, db, dAlns, nA, &corr, nullptr));             // corrected_seqs
+    const uint64_t launchesFirst = ctx->launches;
+    int rc = km_run(ctx, corr, kp, &dHits, &nH);                    // pref_corrected_0
+    if (rc == 0 && hits && n_hits) { rc = to_host_overlapped(ctx, dHits, nH, hits, ctx->evHitsCopied); *n_hits = nH; }
+    if (rc == 0) rc = rs_run(ctx, corr, dHits, nH, rp, &dAlns, &nA);    // aln_corrected_0
+    if (rc == 0 && alns && n_alns) { rc = to_host_overlapped(ctx, dAlns, nA, alns, ctx->evAlnsCopied); *n_alns = nA; }
+    unsigned char *dExt = nullptr;
+    if (rc == 0) rc = ex_run(ctx, corr, dAlns, nA, ep, out_db, &dExt);  // assembly_0
+    if (rc != 0) { cudaStreamSynchronize(ctx->copyStream); seqdb_release(corr, ctx->stream); return rc; }
+    cudaFreeAsync(dExt, ctx->stream);
+    (void) launchesFirst;
+    end_call(ctx);
+    if (!ctx->asyncResults) PG_CUDA(cudaStreamSynchronize(ctx->copyStream));
+    if (corrected_db) *corrected_db = corr; else seqdb_release(corr, ctx->stream);
+    return 0;
+}
+
 int pg_findassemblystart(pg_context *ctx, const pg_seqdb *db, const pg_aln *alns, uint64_t n_alns, pg_seqdb **out_db, int32_t **add_stop) {
     PG_CHECK(ctx && db && out_db && (alns || n_alns == 0), "pg_findassemblystart: null argument");
     PG_TRY(db_ready(ctx, db));

@@ -40,6 +40,28 @@ def test_findassemblystart_matches_oracle_and_golden(case, golden_root, ctx):
     assert ctx.timings()["kernel_launches"] > 0
 
 
+@pytest.mark.parametrize("case", ["example_aa", "synth_aa"])
+def test_fused_step0_matches_golden_chain(case, golden_root, ctx):
+    """pg_assemble_step0: aa_6f_start_long -> corrected_seqs -> pref_corrected_0 / aln_corrected_0 -> assembly_0 in HBM."""
+    import params
+    from test_gpu_parity import gpu_km
+    d, man = golden_case(case, golden_root)
+    steps = man["steps"]
+    km = [s for s in steps if s["cmd"] == "kmermatcher" and s["dbs"][0] == "aa_6f_start_long"][0]
+    rs = [s for s in steps if s["cmd"] == "rescorediagonal" and s["dbs"][0] == "aa_6f_start_long"][0]
+    ex = [s for s in steps if s["cmd"] == "assembleresults" and s["dbs"][2] == "assembly_0"][0]
+    seq = mmseqsdb.read_db(os.path.join(d, "aa_6f_start_long"))
+    ddb = ctx.upload(seq)
+    corr, out, hits, alns = ctx.assemble_step0(ddb, gpu_km(km["args"], False), api.RsParams(**params.rs_fields(rs["args"])),
+                                               api.ExParams(**params.ex_fields(ex["args"])), want_intermediates=True)
+    got_corr, got_out = corr.download(), out.download()
+    corr.free(); out.free(); ddb.free()
+    assert_same_entries(got_corr.entries_by_key(), mmseqsdb.read_db(os.path.join(d, "corrected_seqs")).entries_by_key(), "%s/corrected_seqs fused" % case)
+    pref = mmseqsdb.read_db(os.path.join(d, "pref_corrected_0"))
+    assert_same_entries(ob.format_hits_by_rep(got_corr.keys, hits), pref.entries_by_key(), "%s/pref_corrected_0 fused" % case)
+    assert_same_entries(got_out.entries_by_key(), mmseqsdb.read_db(os.path.join(d, "assembly_0")).entries_by_key(), "%s/assembly_0 fused" % case)
+
+
 def test_findassemblystart_without_alignments(ctx):
     seq = mmseqsdb.from_sequences([b"MKV*MAA", b"AAAA", b"*MKK"], 0, keys=[3, 7, 9])
     ddb = ctx.upload(seq)
