@@ -132,6 +132,27 @@ int or_findstart(const or_seqdb *db, const or_aln *alns, uint64_t n_alns,
                  char **out_data, uint64_t **out_offsets, uint32_t **out_lens, uint32_t **out_keys,
                  uint64_t *out_n, uint64_t *out_bytes, int32_t **add_stop);
 
+/* extractorfs flags that reach the ORF finder (mm/commons/Parameters.cpp, extractorfs parameter list). */
+typedef struct {
+    int min_length;            /* --min-length (codons) */
+    int max_length;            /* --max-length */
+    int max_gaps;              /* --max-gaps */
+    int contig_start_mode;     /* --contig-start-mode 0 / 1 / 2 */
+    int contig_end_mode;       /* --contig-end-mode */
+    int orf_start_mode;        /* --orf-start-mode 0 START_TO_STOP / 1 ANY_TO_STOP / 2 LAST_START_TO_STOP */
+    unsigned forward_frames;   /* bit mask: 1 | 2 | 4 for frames 1,2,3 (Orf::getFrames) */
+    unsigned reverse_frames;
+    int translation_table;     /* only 1 */
+    int use_all_table_starts;  /* --use-all-table-starts */
+} or_orf_params;
+
+/* extractorfs (mm/util/extractorfs.cpp:20-159), translate != 0: fused with translatenucs --add-orf-stop 1
+ * (mm/util/translatenucs.cpp:14-128).  Fragments keyed 0..n-1 in (read, emission) order; orf_info = n x {read key,
+ * fromPos, toPos, incompleteStart | incompleteEnd << 1} = the ORF header DB. */
+int or_extractorfs(const or_seqdb *db, const or_orf_params *p, int translate,
+                   char **out_data, uint64_t **out_offsets, uint32_t **out_lens, uint32_t **out_keys,
+                   uint64_t *out_n, uint64_t *out_bytes, uint32_t **orf_info);
+
 /* cyclecheck (src/assembler/cyclecheck.cpp:71-274): split[i] (caller-allocated, db->n) = splitDiagonal or 0. */
 int or_cyclecheck(const or_seqdb *db, int max_seq_len, int kmer_size, uint32_t *split);
 

@@ -148,6 +148,53 @@ def findstart(db, alns):
     return out, _take(st, db.n, np.dtype("<i4"))
 
 
+class OrfParams(C.Structure):
+    _fields_ = [("min_length", C.c_int), ("max_length", C.c_int), ("max_gaps", C.c_int), ("contig_start_mode", C.c_int),
+                ("contig_end_mode", C.c_int), ("orf_start_mode", C.c_int), ("forward_frames", C.c_uint), ("reverse_frames", C.c_uint),
+                ("translation_table", C.c_int), ("use_all_table_starts", C.c_int)]
+
+
+def orf_params_from_flags(flags, cls=None):
+    """extractorfs argv flags (dict) -> OrfParams (or the GPU library's identical struct)."""
+    def frames(s):
+        m = 0
+        for x in s.split(","):
+            m |= {"1": 1, "2": 2, "3": 4}.get(x, 0)
+        return m
+    cls = cls or OrfParams
+    return cls(min_length=int(flags.get("--min-length", 30)), max_length=int(flags.get("--max-length", 32734)),
+               max_gaps=int(flags.get("--max-gaps", 2147483647)), contig_start_mode=int(flags.get("--contig-start-mode", 2)),
+               contig_end_mode=int(flags.get("--contig-end-mode", 2)), orf_start_mode=int(flags.get("--orf-start-mode", 1)),
+               forward_frames=frames(flags.get("--forward-frames", "1,2,3")), reverse_frames=frames(flags.get("--reverse-frames", "1,2,3")),
+               translation_table=int(flags.get("--translation-table", 1)), use_all_table_starts=int(flags.get("--use-all-table-starts", 0)))
+
+
+def extractorfs(db, op, translate):
+    """Returns (fragment DB keyed 0..n-1, orf_info uint32 (n, 4): read key, fromPos, toPos, flags)."""
+    from plass_b200.mmseqsdb import DB
+    od, oo, ol, ok, oi = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    on, ob = C.c_uint64(), C.c_uint64()
+    s = seqdb_struct(db)
+    rc = lib().or_extractorfs(C.byref(s), C.byref(op), C.c_int(1 if translate else 0), C.byref(od), C.byref(oo), C.byref(ol), C.byref(ok),
+                              C.byref(on), C.byref(ob), C.byref(oi))
+    assert rc == 0, rc
+    n = on.value
+    out = DB(_take(od, ob.value, np.dtype("u1")), _take(ok, n, np.dtype("<u4")), _take(oo, n, np.dtype("<u8")),
+             _take(ol, n, np.dtype("<u4")), 0 if translate else 1)
+    return out, _take(oi, 4 * n, np.dtype("<u4")).reshape(n, 4)
+
+
+def orf_header_entries(info):
+    """Orf::writeOrfHeader (mm/commons/Orf.cpp:445-462): {new key: b"readKey\tfrom+len[\tflags]\n"}."""
+    out = {}
+    for k, (key, f, t, fl) in enumerate(info.tolist()):
+        e = "%d\t%d%s%d" % (key, f, "+" if f < t else "-", abs(f - t))
+        if fl:
+            e += "\t%d" % fl
+        out[k] = (e + "\n").encode()
+    return out
+
+
 def cyclecheck(db, max_seq_len, kmer_size=22):
     """cyclecheck: splitDiagonal per sequence (0 = not circular)."""
     split = np.zeros(db.n, dtype=np.uint32)

@@ -150,3 +150,23 @@ def test_cyclecheck_workflow_split(case, golden_root):
         none = mmseqsdb.read_db(os.path.join(d, name))
         split = ob.cyclecheck(seq, 200000)
         assert sorted(int(k) for k in seq.keys[split == 0]) == sorted(int(k) for k in none.keys), (case, name)
+
+
+def test_extractorfs_translatenucs(golden_root):
+    """nucl_reads -> nucl_<run> (+ header DB) -> aa_<run> for five parameter sets, written by the reference's extractorfs and
+    translatenucs --add-orf-stop 1 (reads with N, lower case, IUPAC codes, U, odd lengths, shorter than a codon)."""
+    d, man = golden_case("orf_aa", golden_root)
+    reads = mmseqsdb.read_db(os.path.join(d, "nucl_reads"))
+    runs = [s for s in man["steps"] if s["cmd"] == "extractorfs"]
+    assert len(runs) == 5
+    for s in runs:
+        name = s["dbs"][1]
+        op = ob.orf_params_from_flags(parse_flags(s["args"]))
+        nuc, info = ob.extractorfs(reads, op, False)
+        want = mmseqsdb.read_db(os.path.join(d, name))
+        assert want.dbtype == 1 and nuc.n == want.n > 200, (name, nuc.n, want.n)
+        assert_same_entries(nuc.entries_by_key(), want.entries_by_key(), "orf_aa/" + name)
+        assert_same_entries(ob.orf_header_entries(info), mmseqsdb.read_db(os.path.join(d, name + "_h")).entries_by_key(), "orf_aa/%s_h" % name)
+        aa, info2 = ob.extractorfs(reads, op, True)
+        assert np.array_equal(info, info2)
+        assert_same_entries(aa.entries_by_key(), mmseqsdb.read_db(os.path.join(d, "aa_" + name[len("nucl_"):])).entries_by_key(), "orf_aa/aa_" + name[len("nucl_"):])
