@@ -167,6 +167,36 @@ int pg_assemble_step0(pg_context *ctx, const pg_seqdb *db, const pg_km_params *k
                       pg_seqdb **corrected_db, pg_seqdb **out_db, pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns);
 int pg_cyclecheck(pg_context *ctx, const pg_seqdb *db, int max_seq_len, uint32_t **split);
 
+/* Six-frame ORF extraction of the reads, the step upstream of the first iteration.
+ *
+ * pg_extractorfs   replaces extractorfs, lib/mmseqs/src/util/extractorfs.cpp:20-159 (Orf::findForward,
+ *                  lib/mmseqs/src/commons/Orf.cpp:192-330) and, with translate != 0, the translatenucs --add-orf-stop 1 that
+ *                  follows it in data/assemble.sh:41-66 (lib/mmseqs/src/util/translatenucs.cpp:14-128): out_db holds the
+ *                  fragments (nucleotides, or amino acids framed by '*' where the ORF has a real start / stop) with keys
+ *                  0..n-1 in (read, emission) order, i.e. the renumbered DB the reference writes; orf_info (optional,
+ *                  pinned, 4 words per fragment) = {read key, fromPos, toPos, incompleteStart | incompleteEnd << 1}, the
+ *                  fields of the ORF header DB (Orf::writeOrfHeader, Orf.cpp:445-462).
+ * pg_seqdb_concat  replaces concatdbs without --preserve-keys on two sequence DBs (data/assemble.sh:68-77): a's entries
+ *                  keep the keys 0..a.n-1, b's follow. */
+typedef struct {               /* extractorfs flags (Parameters.cpp, extractorfs list) */
+    int min_length;            /* --min-length (codons) */
+    int max_length;            /* --max-length */
+    int max_gaps;              /* --max-gaps */
+    int contig_start_mode;     /* --contig-start-mode */
+    int contig_end_mode;       /* --contig-end-mode */
+    int orf_start_mode;        /* --orf-start-mode */
+    unsigned forward_frames;   /* bit mask 1 | 2 | 4 = frames 1,2,3 (Orf::getFrames, Orf.h:17-35) */
+    unsigned reverse_frames;
+    int translation_table;     /* --translation-table, only 1 */
+    int use_all_table_starts;  /* --use-all-table-starts */
+} pg_orf_params;
+int pg_extractorfs(pg_context *ctx, const pg_seqdb *db, const pg_orf_params *p, int translate, pg_seqdb **out_db, uint32_t **orf_info);
+int pg_seqdb_concat(pg_context *ctx, const pg_seqdb *a, const pg_seqdb *b, pg_seqdb **out_db);
+/* pg_translatenucs replaces translatenucs (lib/mmseqs/src/util/translatenucs.cpp:14-128) on any nucleotide DB: flags
+ * (optional, host, one byte per sequence) bit 0 = '*' in front, bit 1 = '*' behind unless the last residue is one
+ * (--add-orf-stop 1: from the ORF header of the sequence); entries of fewer than three bytes are dropped, keys are kept. */
+int pg_translatenucs(pg_context *ctx, const pg_seqdb *db, const uint8_t *flags, int translation_table, pg_seqdb **out_db);
+
 /* Asynchronous result transfer.  The reference workflow writes pref_N / aln_N / assembly_N to disk while the next
  * iteration's input already sits in HBM; with pg_set_async_results(ctx, 1) pg_assemble_iteration (hits, alns) and
  * pg_seqdb_download only ENQUEUE their device->host copies on the context's copy stream and return, so that the

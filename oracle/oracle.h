@@ -153,6 +153,12 @@ int or_extractorfs(const or_seqdb *db, const or_orf_params *p, int translate,
                    char **out_data, uint64_t **out_offsets, uint32_t **out_lens, uint32_t **out_keys,
                    uint64_t *out_n, uint64_t *out_bytes, uint32_t **orf_info);
 
+/* translatenucs (mm/util/translatenucs.cpp:14-128) on any nucleotide DB; flags NULL = --add-orf-stop 0, else per sequence
+ * bit 0 = '*' in front, bit 1 = '*' behind.  Keys kept, entries shorter than a codon dropped. */
+int or_translatenucs(const or_seqdb *db, const uint8_t *flags, int max_seq_len,
+                     char **out_data, uint64_t **out_offsets, uint32_t **out_lens, uint32_t **out_keys,
+                     uint64_t *out_n, uint64_t *out_bytes);
+
 /* cyclecheck (src/assembler/cyclecheck.cpp:71-274): split[i] (caller-allocated, db->n) = splitDiagonal or 0. */
 int or_cyclecheck(const or_seqdb *db, int max_seq_len, int kmer_size, uint32_t *split);
 

@@ -427,3 +427,39 @@ extern "C" int or_extractorfs(const or_seqdb *db, const or_orf_params *p, int tr
     *out_n = n; *out_bytes = all.size();
     return 0;
 }
+
+/* translatenucs on any nucleotide DB (mm/util/translatenucs.cpp:14-128).  flags (may be NULL = --add-orf-stop 0): per
+ * sequence bit 0 = addStopAtStart, bit 1 = addStopAtEnd (from the ORF header, :58-63).  Entries shorter than a codon are
+ * dropped; keys are kept. */
+extern "C" int or_translatenucs(const or_seqdb *db, const uint8_t *flags, int max_seq_len,
+                                char **out_data, uint64_t **out_offsets, uint32_t **out_lens, uint32_t **out_keys,
+                                uint64_t *out_n, uint64_t *out_bytes) {
+    static const Translate T;
+    std::vector<std::string> entries;
+    std::vector<uint64_t> ids;
+    std::vector<char> aa;
+    for (uint64_t i = 0; i < db->n; i++) {
+        const char *data = db->data + db->offsets[i];
+        if (*data == '\0') continue;
+        bool addStopAtStart = flags ? (flags[i] & 1) != 0 : false;
+        bool addStopAtEnd = flags ? (flags[i] & 2) != 0 : false;
+        size_t length = db->lens[i] - 1;
+        if ((data[length] != '\n' && length % 3 != 0) && (data[length - 1] == '\n' && (length - 1) % 3 != 0)) length = length - (length % 3);
+        if (length < 3) continue;
+        if (length > (size_t) (3 * max_seq_len)) length = 3 * max_seq_len;
+        aa.assign(length / 3 + 8, 0);
+        char *writeAA = aa.data();
+        if (addStopAtStart) { aa[0] = '*'; writeAA = aa.data() + 1; }
+        // the reference translates ceil(length / 3) codons and then overwrites position length / 3 with the terminator;
+        // the last (partial) codon may read past the entry, its result never survives: translate only the full ones
+        T.translate(writeAA, data, (int) (length / 3) * 3);
+        if (addStopAtEnd && writeAA[(length / 3) - 1] != '*') { writeAA[length / 3] = '*'; writeAA[length / 3 + 1] = '\n'; }
+        else { addStopAtEnd = false; writeAA[length / 3] = '\n'; }
+        std::string e(aa.data(), (length / 3) + 1 + addStopAtStart + addStopAtEnd);
+        e.push_back('\0');
+        entries.push_back(e);
+        ids.push_back(i);
+    }
+    emitDb(entries, db, out_data, out_offsets, out_lens, out_keys, out_n, out_bytes, ids);
+    return 0;
+}

@@ -63,6 +63,25 @@ ALN = np.dtype([("query", "<u4"), ("target", "<u4"), ("bits", "<i4"), ("seq_id",
                 ("db_start", "<i4"), ("db_end", "<i4"), ("db_len", "<i4")], align=True)
 
 
+class OrfParams(C.Structure):
+    """extractorfs flags (include/plassgpu.h pg_orf_params)."""
+    _fields_ = [("min_length", C.c_int), ("max_length", C.c_int), ("max_gaps", C.c_int), ("contig_start_mode", C.c_int),
+                ("contig_end_mode", C.c_int), ("orf_start_mode", C.c_int), ("forward_frames", C.c_uint), ("reverse_frames", C.c_uint),
+                ("translation_table", C.c_int), ("use_all_table_starts", C.c_int)]
+
+
+def orf_params_long(min_length=45):
+    """EXTRACTORFS_LONG_PAR of the assemble workflow (Assembler.cpp:114-118)."""
+    return OrfParams(min_length=min_length, max_length=32734, max_gaps=0, contig_start_mode=2, contig_end_mode=2, orf_start_mode=0,
+                     forward_frames=7, reverse_frames=7, translation_table=1, use_all_table_starts=0)
+
+
+def orf_params_start(min_length=45):
+    """EXTRACTORFS_START_PAR (Assembler.cpp:121-128): fragments that begin at an ATG and run off the read end."""
+    return OrfParams(min_length=min(min_length, 20), max_length=min_length, max_gaps=0, contig_start_mode=1, contig_end_mode=0, orf_start_mode=0,
+                     forward_frames=7, reverse_frames=7, translation_table=1, use_all_table_starts=0)
+
+
 def default_km_params(nucl=False, **kw):
     """Workflow defaults: Assembler.cpp:10-27 (aa) / Nuclassembler.cpp:10-32 (nt)."""
     p = KmParams(kmer_size=22 if nucl else 14, alph_size=5 if nucl else 13, kmers_per_seq=60,
@@ -290,6 +309,41 @@ class Context:
         corr, out = DeviceSeqDB(self, hc), DeviceSeqDB(self, ho)
         corr.dbtype = out.dbtype = ddb.dbtype
         return corr, out, hits, alns
+
+    # extractorfs [+ translatenucs --add-orf-stop 1] (lib/mmseqs/src/util/extractorfs.cpp:20, translatenucs.cpp:14)
+    def extractorfs(self, ddb, op, translate=False):
+        """Returns (fragment DeviceSeqDB keyed 0..n-1, orf_info uint32 (n, 4): read key, fromPos, toPos, flags)."""
+        h, info = C.c_void_p(), C.c_void_p()
+        _check(load_library().pg_extractorfs(self.handle, ddb.handle, C.byref(op), C.c_int(1 if translate else 0), C.byref(h), C.byref(info)), "pg_extractorfs")
+        out = DeviceSeqDB(self, h)
+        out.dbtype = 0 if translate else 1
+        n = out.n
+        return out, _take(info, 4 * n, np.dtype("<u4")).reshape(n, 4)
+
+    def translatenucs(self, ddb, flags=None, translation_table=1):
+        fl = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+        h = C.c_void_p()
+        _check(load_library().pg_translatenucs(self.handle, ddb.handle, None if fl is None else C.c_void_p(fl.ctypes.data), C.c_int(translation_table),
+                                               C.byref(h)), "pg_translatenucs")
+        out = DeviceSeqDB(self, h)
+        out.dbtype = 0
+        return out
+
+    # concatdbs (two sequence DBs, keys renumbered)
+    def concat(self, a, b):
+        h = C.c_void_p()
+        _check(load_library().pg_seqdb_concat(self.handle, a.handle, b.handle, C.byref(h)), "pg_seqdb_concat")
+        out = DeviceSeqDB(self, h)
+        out.dbtype = a.dbtype
+        return out
+
+    def six_frame_fragments(self, reads_ddb, min_length=45):
+        """nucl_reads -> aa_6f_start_long as data/assemble.sh:41-77 builds it: long ORFs first, then the start fragments."""
+        lo, _ = self.extractorfs(reads_ddb, orf_params_long(min_length), translate=True)
+        st, _ = self.extractorfs(reads_ddb, orf_params_start(min_length), translate=True)
+        out = self.concat(lo, st)
+        lo.free(); st.free()
+        return out
 
     # cyclecheck (src/assembler/cyclecheck.cpp:71-274)
     def cyclecheck(self, ddb, max_seq_len):

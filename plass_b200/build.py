@@ -29,6 +29,7 @@ CUDA_SOURCES = {
     "pg_rescore.cu": ["-fmad=false"],
     "pg_extend.cu": ["-fmad=false"],
     "pg_next.cu": ["-fmad=false"],
+    "pg_orf.cu": [],
 }
 HOST_SOURCES = ["host/cli.cpp", "host/mmdb.cpp", "host/commands.cpp"]
 

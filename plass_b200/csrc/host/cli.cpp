@@ -9,7 +9,7 @@
 
 int main(int argc, const char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "usage: %s <kmermatcher|rescorediagonal|assembleresults|nuclassembleresults|findassemblystart|cyclecheck> <dbs...> [flags]\n", argv[0]);
+        fprintf(stderr, "usage: %s <kmermatcher|rescorediagonal|assembleresults|nuclassembleresults|findassemblystart|cyclecheck|extractorfs|translatenucs> <dbs...> [flags]\n", argv[0]);
         return EXIT_FAILURE;
     }
     const char *cmd = argv[1];
@@ -19,6 +19,8 @@ int main(int argc, const char **argv) {
     if (!strcmp(cmd, "nuclassembleresults")) return nuclassembleresults(argc - 2, argv + 2);
     if (!strcmp(cmd, "findassemblystart")) return findassemblystart(argc - 2, argv + 2);
     if (!strcmp(cmd, "cyclecheck")) return cyclecheck(argc - 2, argv + 2);
+    if (!strcmp(cmd, "extractorfs")) return extractorfs(argc - 2, argv + 2);
+    if (!strcmp(cmd, "translatenucs")) return translatenucs(argc - 2, argv + 2);
     fprintf(stderr, "%s: not one of the GPU hot-path commands\n", cmd);
     return EXIT_FAILURE;
 }

@@ -14,8 +14,20 @@
 #include <set>
 #include <string>
 #include <vector>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace {
+
+bool pathExists(const std::string &p) { struct stat st; return lstat(p.c_str(), &st) == 0; }
+
+// DBReader::softlinkDb for one file: out -> basename-relative link to in, if in exists
+void linkIfExists(const std::string &in, const std::string &out) {
+    if (!pathExists(in)) return;
+    if (pathExists(out)) unlink(out.c_str());
+    char *real = realpath(in.c_str(), nullptr);
+    if (real) { if (symlink(real, out.c_str()) != 0) { /* best effort, as the reference */ } free(real); }
+}
 
 struct Flags {
     std::vector<std::string> positional;
@@ -165,6 +177,23 @@ void writeSeqDb(pg_seqdb *out, const std::string &path, int dbtype) {
 }
 
 const std::set<std::string> FS_FLAGS = {"--threads", "-v", "--compressed"};
+const std::set<std::string> ORF_FLAGS = {"--min-length", "--max-length", "--max-gaps", "--contig-start-mode", "--contig-end-mode", "--orf-start-mode",
+    "--forward-frames", "--reverse-frames", "--translation-table", "--translate", "--use-all-table-starts", "--id-offset", "--create-lookup",
+    "--threads", "--compressed", "-v"};
+const std::set<std::string> TN_FLAGS = {"--translation-table", "--add-orf-stop", "-v", "--compressed", "--threads"};
+
+unsigned frameMask(const std::string &s) {      // Orf::getFrames (Orf.h:17-35)
+    unsigned m = 0;
+    size_t p = 0;
+    while (p <= s.size()) {
+        size_t c = s.find(',', p);
+        if (c == std::string::npos) c = s.size();
+        const std::string t = s.substr(p, c - p);
+        if (t == "1") m |= 1u; else if (t == "2") m |= 2u; else if (t == "3") m |= 4u;
+        p = c + 1;
+    }
+    return m;
+}
 const std::set<std::string> CC_FLAGS = {"--max-seq-len", "--chop-cycle", "--threads", "-v", "--compressed"};
 
 int extendCommand(int argc, const char **argv, bool nuclCommand) {
@@ -345,6 +374,99 @@ int findassemblystart(int argc, const char **argv) {
     pg_seqdb *db = uploadSeqDb(seq), *out = nullptr;
     if (pg_findassemblystart(gpu(), db, alns.data(), alns.size(), &out, nullptr) != 0) die(pg_last_error());
     writeSeqDb(out, f.positional[2], mmdb::DBTYPE_AMINO_ACIDS);
+    pg_seqdb_free(gpu(), out); pg_seqdb_free(gpu(), db);
+    timer.report();
+    return EXIT_SUCCESS;
+}
+
+// extractorfs <i:sequenceDB> <o:sequenceDB>  (lib/mmseqs/src/util/extractorfs.cpp:20-159): the ORF fragments (keys 0..n-1
+// in (read, emission) order, as DBWriter::createRenumberedDB leaves them) and their header DB <o>_h
+int extractorfs(int argc, const char **argv) {
+    Timer timer;
+    const Flags f = parseFlags(argc, argv, 2, ORF_FLAGS);
+    requireValue(f, "--compressed", "0", "uncompressed DBs only");
+    requireValue(f, "--create-lookup", "0", "lookup files are not written by the GPU path");
+    requireValue(f, "--id-offset", "0", "not used by the assemble workflow");
+    std::string err;
+    mmdb::Reader seq;
+    if (!seq.open(f.positional[0], err)) die(err);
+    if (seq.dbtype != mmdb::DBTYPE_NUCLEOTIDES) die("extractorfs expects a nucleotide sequence DB");
+    pg_orf_params p;
+    p.min_length = geti(f, "--min-length", 30);
+    p.max_length = geti(f, "--max-length", 32734);
+    p.max_gaps = geti(f, "--max-gaps", 2147483647);
+    p.contig_start_mode = geti(f, "--contig-start-mode", 2);
+    p.contig_end_mode = geti(f, "--contig-end-mode", 2);
+    p.orf_start_mode = geti(f, "--orf-start-mode", 1);
+    p.forward_frames = frameMask(get(f, "--forward-frames", "1,2,3"));
+    p.reverse_frames = frameMask(get(f, "--reverse-frames", "1,2,3"));
+    p.translation_table = geti(f, "--translation-table", 1);
+    p.use_all_table_starts = geti(f, "--use-all-table-starts", 0);
+    const int translate = geti(f, "--translate", 0);
+    pg_seqdb *db = uploadSeqDb(seq), *out = nullptr;
+    uint32_t *info = nullptr;
+    if (pg_extractorfs(gpu(), db, &p, translate, &out, &info) != 0) die(pg_last_error());
+    const uint64_t n = pg_seqdb_size(out);
+    writeSeqDb(out, f.positional[1], translate ? mmdb::DBTYPE_AMINO_ACIDS : mmdb::DBTYPE_NUCLEOTIDES);
+    // header DB: Orf::writeOrfHeader (Orf.cpp:445-462): "readKey \t from (+|-) len [\t flags] \n"
+    mmdb::Writer hw;
+    if (!hw.open(f.positional[1] + "_h", 12 /* DBTYPE_GENERIC_DB */, err)) die(err);
+    char line[96];
+    for (uint64_t i = 0; i < n; i++) {
+        const uint32_t key = info[4 * i], from = info[4 * i + 1], to = info[4 * i + 2], fl = info[4 * i + 3];
+        char *b = putU(line, key); *b++ = '\t';
+        b = putU(b, from); *b++ = (from < to) ? '+' : '-';
+        b = putU(b, from < to ? to - from : from - to);
+        if (fl) { *b++ = '\t'; b = putU(b, fl); }
+        *b++ = '\n';
+        hw.write((uint32_t) i, line, (size_t) (b - line));
+    }
+    if (!hw.close()) die("write error");
+    linkIfExists(f.positional[0] + ".source", f.positional[1] + ".source");
+    pg_free_host(info);
+    pg_seqdb_free(gpu(), out); pg_seqdb_free(gpu(), db);
+    timer.report();
+    return EXIT_SUCCESS;
+}
+
+// translatenucs <i:sequenceDB> <o:sequenceDB>  (lib/mmseqs/src/util/translatenucs.cpp:14-128)
+int translatenucs(int argc, const char **argv) {
+    Timer timer;
+    const Flags f = parseFlags(argc, argv, 2, TN_FLAGS);
+    requireValue(f, "--compressed", "0", "uncompressed DBs only");
+    std::string err;
+    mmdb::Reader seq;
+    if (!seq.open(f.positional[0], err)) die(err);
+    if (seq.dbtype != mmdb::DBTYPE_NUCLEOTIDES) die("translatenucs expects a nucleotide sequence DB");
+    const bool addOrfStop = geti(f, "--add-orf-stop", 0) != 0;
+    std::vector<uint8_t> flags;
+    if (addOrfStop) {
+        // Orf::parseOrfHeader (Orf.cpp:333-443) of the header entry with the same key: third column = incomplete start | end << 1
+        mmdb::Reader hdr;
+        if (!hdr.open(f.positional[0] + "_h", err)) die(err);
+        flags.resize(seq.size());
+        for (size_t i = 0; i < seq.size(); i++) {
+            const auto it = std::lower_bound(hdr.keys.begin(), hdr.keys.end(), seq.keys[i]);
+            if (it == hdr.keys.end() || *it != seq.keys[i]) die("translatenucs --add-orf-stop 1: no ORF header for key " + std::to_string(seq.keys[i]));
+            const char *s = hdr.entry((size_t) (it - hdr.keys.begin()));
+            int col = 0; unsigned long complete = 0;
+            const char *q = s;
+            while (*q && *q != '\n') {
+                while (*q == ' ' || *q == '\t') q++;
+                if (!*q || *q == '\n') break;
+                if (col == 2) complete = strtoul(q, nullptr, 10);
+                col++;
+                while (*q && *q != ' ' && *q != '\t' && *q != '\n') q++;
+            }
+            if (col < 2) die("translatenucs --add-orf-stop 1: header of key " + std::to_string(seq.keys[i]) + " is not an ORF header");
+            flags[i] = (uint8_t) (((complete & 1) ? 0 : 1) | ((complete & 2) ? 0 : 2));
+        }
+    }
+    pg_seqdb *db = uploadSeqDb(seq), *out = nullptr;
+    if (pg_translatenucs(gpu(), db, addOrfStop ? flags.data() : nullptr, geti(f, "--translation-table", 1), &out) != 0) die(pg_last_error());
+    writeSeqDb(out, f.positional[1], mmdb::DBTYPE_AMINO_ACIDS);
+    // DBReader::softlinkDb(db1, db2, SEQUENCE_ANCILLARY): header DB, lookup and source travel with the translated DB
+    for (const char *ext : {"_h", "_h.index", "_h.dbtype", ".lookup", ".source"}) linkIfExists(f.positional[0] + ext, f.positional[1] + ext);
     pg_seqdb_free(gpu(), out); pg_seqdb_free(gpu(), db);
     timer.report();
     return EXIT_SUCCESS;

@@ -8,3 +8,5 @@ int assembleresults(int argc, const char **argv);        // replaces src/assembl
 int nuclassembleresults(int argc, const char **argv);    // replaces src/assembler/nuclassembleresult.cpp:400
 int findassemblystart(int argc, const char **argv);      // replaces src/assembler/findassemblystart.cpp:35
 int cyclecheck(int argc, const char **argv);             // replaces src/assembler/cyclecheck.cpp:31
+int extractorfs(int argc, const char **argv);            // replaces lib/mmseqs/src/util/extractorfs.cpp:20
+int translatenucs(int argc, const char **argv);          // replaces lib/mmseqs/src/util/translatenucs.cpp:14

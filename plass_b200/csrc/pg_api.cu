@@ -272,7 +272,7 @@ void pg_destroy(pg_context *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->small, &ctx->lists, &ctx->recA, &ctx->recB, &ctx->radixWs, &ctx->scratch, &ctx->blockCounts, &ctx->hits,
-                      &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta, &ctx->exLists, &ctx->ntTab, &ctx->buckets, &ctx->buckets2, &ctx->wideTabs, &ctx->nextWork};
+                      &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta, &ctx->exLists, &ctx->ntTab, &ctx->buckets, &ctx->buckets2, &ctx->wideTabs, &ctx->nextWork, &ctx->orfInfo};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
     cudaStreamSynchronize(ctx->copyStream);
@@ -509,6 +509,72 @@ int pg_findassemblystart(pg_context *ctx, const pg_seqdb *db, const pg_aln *alns
     PG_TRY(fs_run(ctx, db, ctx->alns.as<pg_aln>(), n_alns, out_db, &dStop));
     if (add_stop) PG_TRY(to_host(ctx->stream, dStop, db->n, add_stop));
     end_call(ctx);
+    return 0;
+}
+
+int pg_extractorfs(pg_context *ctx, const pg_seqdb *db, const pg_orf_params *p, int translate, pg_seqdb **out_db, uint32_t **orf_info) {
+    PG_CHECK(ctx && db && p && out_db, "pg_extractorfs: null argument");
+    PG_TRY(db_ready(ctx, db));
+    begin_call(ctx);
+    unsigned *dInfo = nullptr;
+    PG_TRY(orf_run(ctx, db, p, translate, out_db, &dInfo));
+    if (orf_info) PG_TRY(to_host(ctx->stream, dInfo, 4 * (*out_db)->n, orf_info));
+    end_call(ctx);
+    return 0;
+}
+
+int pg_translatenucs(pg_context *ctx, const pg_seqdb *db, const uint8_t *flags, int translation_table, pg_seqdb **out_db) {
+    PG_CHECK(ctx && db && out_db, "pg_translatenucs: null argument");
+    PG_TRY(db_ready(ctx, db));
+    begin_call(ctx);
+    unsigned char *dFlags = nullptr;
+    if (flags && db->n) {
+        PG_TRY(ctx->flags.reserve(db->n + 16));
+        dFlags = ctx->flags.as<unsigned char>();
+        PG_CUDA(cudaMemcpyAsync(dFlags, flags, db->n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PG_TRY(tn_run(ctx, db, dFlags, translation_table, out_db));
+    end_call(ctx);
+    return 0;
+}
+
+// concatdbs of two sequence DBs without --preserve-keys (lib/mmseqs/src/util/concatdbs.cpp): a's entries keep their
+// order and get the keys 0..a.n-1, b's follow with a.n..a.n+b.n-1
+__global__ void concat_meta_kernel(const unsigned long long *__restrict__ aOff, const unsigned *__restrict__ aLen, unsigned long long an,
+                                   const unsigned long long *__restrict__ bOff, const unsigned *__restrict__ bLen, unsigned long long bn,
+                                   unsigned long long aBytes, unsigned long long *__restrict__ oOff, unsigned *__restrict__ oLen, unsigned *__restrict__ oKey) {
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < an + bn; i += (unsigned long long) gridDim.x * blockDim.x) {
+        if (i < an) { oOff[i] = aOff[i]; oLen[i] = aLen[i]; }
+        else { oOff[i] = aBytes + bOff[i - an]; oLen[i] = bLen[i - an]; }
+        oKey[i] = (unsigned) i;
+    }
+}
+
+int pg_seqdb_concat(pg_context *ctx, const pg_seqdb *a, const pg_seqdb *b, pg_seqdb **out_db) {
+    PG_CHECK(ctx && a && b && out_db, "pg_seqdb_concat: null argument");
+    PG_CHECK(a->dbtype == b->dbtype, "pg_seqdb_concat: the two DBs must have the same type");
+    PG_TRY(db_ready(ctx, a));
+    PG_TRY(db_ready(ctx, b));
+    begin_call(ctx);
+    cudaStream_t s = ctx->stream;
+    const uint64_t n = a->n + b->n;
+    PG_CHECK(n < 0xFFFFFFF0ull, "pg_seqdb_concat: more than 2^32 sequences");
+    pg_seqdb *out = new pg_seqdb();
+    out->n = n; out->data_bytes = a->data_bytes + b->data_bytes; out->dbtype = a->dbtype;
+    PG_CUDA(cudaMallocAsync(&out->data, out->data_bytes + 16, s));
+    PG_CUDA(cudaMallocAsync(&out->offsets, sizeof(unsigned long long) * (n + 1), s));
+    PG_CUDA(cudaMallocAsync(&out->lens, sizeof(unsigned) * (n + 1), s));
+    PG_CUDA(cudaMallocAsync(&out->keys, sizeof(unsigned) * (n + 1), s));
+    if (a->data_bytes) PG_CUDA(cudaMemcpyAsync(out->data, a->data, a->data_bytes, cudaMemcpyDeviceToDevice, s));
+    if (b->data_bytes) PG_CUDA(cudaMemcpyAsync(out->data + a->data_bytes, b->data, b->data_bytes, cudaMemcpyDeviceToDevice, s));
+    if (n) {
+        concat_meta_kernel<<<NUM_SMS * 4, 256, 0, s>>>(a->offsets, a->lens, a->n, b->offsets, b->lens, b->n, a->data_bytes, out->offsets, out->lens, out->keys);
+        ctx->launches++;
+    }
+    PG_CUDA(cudaGetLastError());
+    PG_TRY(seqdb_finalize(ctx, out));
+    end_call(ctx);
+    *out_db = out;
     return 0;
 }
 

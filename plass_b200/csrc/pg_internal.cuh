@@ -29,7 +29,7 @@ struct pg_context {
     cudaEvent_t evAuxFork = nullptr, evAuxJoin = nullptr;
     unsigned long long *hostStage = nullptr;   // mapped pinned words: the kernels' small results are read back through here (pg::read_back)
     cudaEvent_t ev[pg::EV_COUNT];
-    pg::DevBuf small, lists, recA, recB, radixWs, scratch, blockCounts, hits, alnAll, alns, flags, exWork, exSegs, exMeta, exLists, ntTab, buckets, buckets2, wideTabs, nextWork;
+    pg::DevBuf small, lists, recA, recB, radixWs, scratch, blockCounts, hits, alnAll, alns, flags, exWork, exSegs, exMeta, exLists, ntTab, buckets, buckets2, wideTabs, nextWork, orfInfo;
     unsigned bucketTarget = 512;  // average records per bucket of the partial-key partition (<= 700: small hash-join instance first)
     int digitBits = 8;            // radix digit width of the two fast-path sorts (8: 256 bins; 9 / 10: wide-digit kernel)
     bool forceFullSort = false;   // tests: take the 8-pass sort + group_kernel path instead of the bucketed hash join
@@ -71,6 +71,9 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
 // findassemblystart / cyclecheck (pg_next.cu); the returned device arrays live in ctx->nextWork until the next call
 int fs_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAlns, pg_seqdb **out, int **d_addStop);
 int cc_run(Context *ctx, const pg_seqdb *db, int maxSeqLen, int k, unsigned **d_split);
+// extractorfs (+ translatenucs --add-orf-stop 1) (pg_orf.cu); d_info (4 words per fragment) lives in ctx->orfInfo
+int orf_run(Context *ctx, const pg_seqdb *db, const pg_orf_params *p, int translate, pg_seqdb **out, unsigned **d_info);
+int tn_run(Context *ctx, const pg_seqdb *db, const unsigned char *d_flags, int translationTable, pg_seqdb **out);
 int db_ready(Context *ctx, const pg_seqdb *db);   // completes a pg_seqdb_upload_async at the DB's first use
 int seqdb_finalize(Context *ctx, pg_seqdb *db);   // computes max_seq_len / residues / dense_keys on the device
 void seqdb_release(pg_seqdb *db, cudaStream_t s);

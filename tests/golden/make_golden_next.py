@@ -164,6 +164,13 @@ def make_orf_case():
             steps.append(dict(cmd="extractorfs", dbs=["nucl_reads", "nucl_" + name], args=args + ORF_COMMON))
             steps.append(dict(cmd="translatenucs", dbs=["nucl_" + name, "aa_" + name], args=["--translation-table", "1", "--add-orf-stop", "1"]))
             print("orf_aa/%s: %d fragments" % (name, mmseqsdb.read_db(os.path.join(pack, "aa_" + name)).n))
+        # translatenucs on the raw reads (lengths of every residue class mod 3, reads shorter than a codon), no ORF stops
+        aa = os.path.join(work, "aa_reads")
+        subprocess.run([plass, "translatenucs", src, aa, "--translation-table", "1", "--add-orf-stop", "0", "-v", "3", "--compressed", "0", "--threads", "1"],
+                       check=True, stdout=subprocess.DEVNULL)
+        mmseqsdb.canonicalize(aa, os.path.join(pack, "aa_reads"))
+        steps.append(dict(cmd="translatenucs", dbs=["nucl_reads", "aa_reads"], args=["--translation-table", "1", "--add-orf-stop", "0"]))
+        print("orf_aa/aa_reads: %d of %d reads translated" % (mmseqsdb.read_db(os.path.join(pack, "aa_reads")).n, len(seqs)))
         with open(os.path.join(HERE, "orf_aa.json"), "w") as f:
             json.dump(dict(case="orf_aa", command="plass extractorfs / translatenucs", steps=steps), f, indent=1)
         with tarfile.open(os.path.join(HERE, "orf_aa.tar.xz"), "w:xz") as tf:

@@ -184,6 +184,30 @@ def extractorfs(db, op, translate):
     return out, _take(oi, 4 * n, np.dtype("<u4")).reshape(n, 4)
 
 
+def translatenucs(db, flags=None, max_seq_len=65535):
+    from plass_b200.mmseqsdb import DB
+    od, oo, ol, ok = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    on, ob = C.c_uint64(), C.c_uint64()
+    s = seqdb_struct(db)
+    fl = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+    rc = lib().or_translatenucs(C.byref(s), None if fl is None else C.c_void_p(fl.ctypes.data), C.c_int(max_seq_len),
+                                C.byref(od), C.byref(oo), C.byref(ol), C.byref(ok), C.byref(on), C.byref(ob))
+    assert rc == 0, rc
+    n = on.value
+    return DB(_take(od, ob.value, np.dtype("u1")), _take(ok, n, np.dtype("<u4")), _take(oo, n, np.dtype("<u8")), _take(ol, n, np.dtype("<u4")), 0)
+
+
+def orf_flags_from_headers(hdr_db, keys):
+    """translatenucs.cpp:58-63: addStopAtStart = !incompleteStart, addStopAtEnd = !incompleteEnd from the ORF header of each key."""
+    h = hdr_db.entries_by_key()
+    out = np.zeros(len(keys), dtype=np.uint8)
+    for i, k in enumerate(keys):
+        cols = h[int(k)].decode().split()
+        complete = int(cols[2]) if len(cols) >= 3 else 0
+        out[i] = (0 if (complete & 1) else 1) | (0 if (complete & 2) else 2)
+    return out
+
+
 def orf_header_entries(info):
     """Orf::writeOrfHeader (mm/commons/Orf.cpp:445-462): {new key: b"readKey\tfrom+len[\tflags]\n"}."""
     out = {}

@@ -143,3 +143,91 @@ def test_cli_findassemblystart_and_cyclecheck(golden_root, tmp_path):
         got, want = mmseqsdb.read_db(out), mmseqsdb.read_db(os.path.join(d, s["dbs"][1]))
         assert got.dbtype == want.dbtype == 1
         assert_same_entries(got.entries_by_key(), want.entries_by_key(), "%s via CLI" % s["dbs"][1])
+
+
+# ---- extractorfs / translatenucs / concatdbs ------------------------------------------------
+
+def test_extractorfs_translatenucs_match_oracle_and_golden(golden_root, ctx):
+    d, man = golden_case("orf_aa", golden_root)
+    reads = mmseqsdb.read_db(os.path.join(d, "nucl_reads"))
+    ddb = ctx.upload(reads)
+    for s in [s for s in man["steps"] if s["cmd"] == "extractorfs"]:
+        name = s["dbs"][1]
+        flags = parse_flags(s["args"])
+        op = ob.orf_params_from_flags(flags, api.OrfParams)
+        wnuc, winfo = ob.extractorfs(reads, ob.orf_params_from_flags(flags), False)
+        # nucleotide fragments + ORF header fields
+        out, info = ctx.extractorfs(ddb, op, translate=False)
+        got = out.download()
+        assert np.array_equal(info, winfo), name
+        assert_same_entries(got.entries_by_key(), wnuc.entries_by_key(), "orf_aa/%s vs oracle" % name)
+        golden = mmseqsdb.read_db(os.path.join(d, name))
+        assert_same_entries(got.entries_by_key(), golden.entries_by_key(), "orf_aa/%s vs reference" % name)
+        assert_same_entries(ob.orf_header_entries(info), mmseqsdb.read_db(os.path.join(d, name + "_h")).entries_by_key(), "orf_aa/%s_h" % name)
+        # translatenucs --add-orf-stop 1 on that DB (device resident), flags from the header fields
+        tflags = ((info[:, 3] & 1) == 0).astype(np.uint8) | (((info[:, 3] & 2) == 0).astype(np.uint8) << 1)
+        aa = ctx.translatenucs(out, tflags)
+        gaa = aa.download()
+        aa.free(); out.free()
+        want_aa = mmseqsdb.read_db(os.path.join(d, "aa_" + name[len("nucl_"):]))
+        assert_same_entries(gaa.entries_by_key(), want_aa.entries_by_key(), "orf_aa/translatenucs %s" % name)
+        # the fused form
+        out, info2 = ctx.extractorfs(ddb, op, translate=True)
+        got = out.download()
+        out.free()
+        assert np.array_equal(info2, winfo)
+        assert_same_entries(got.entries_by_key(), want_aa.entries_by_key(), "orf_aa/fused %s" % name)
+    # translatenucs on the raw reads: all length classes mod 3, entries shorter than a codon are dropped
+    aa = ctx.translatenucs(ddb)
+    got = aa.download()
+    aa.free(); ddb.free()
+    assert_same_entries(got.entries_by_key(), mmseqsdb.read_db(os.path.join(d, "aa_reads")).entries_by_key(), "orf_aa/aa_reads")
+    assert_same_entries(got.entries_by_key(), ob.translatenucs(reads).entries_by_key(), "orf_aa/aa_reads vs oracle")
+
+
+def test_six_frame_fragments_equal_workflow_input(golden_root, ctx):
+    """aa_6f_start_long = concatdbs(aa_6f_long, aa_6f_start) (data/assemble.sh:41-77) from the reads in one go."""
+    d, man = golden_case("orf_aa", golden_root)
+    reads = mmseqsdb.read_db(os.path.join(d, "nucl_reads"))
+    ddb = ctx.upload(reads)
+    out = ctx.six_frame_fragments(ddb)
+    got = out.download()
+    out.free(); ddb.free()
+    lo, st = mmseqsdb.read_db(os.path.join(d, "aa_long")), mmseqsdb.read_db(os.path.join(d, "aa_start"))
+    want = {int(k): lo.entry(i) for i, k in enumerate(lo.keys)}
+    want.update({lo.n + int(k): st.entry(i) for i, k in enumerate(st.keys)})
+    assert got.n == lo.n + st.n
+    assert_same_entries(got.entries_by_key(), want, "aa_6f_start_long")
+
+
+def test_extractorfs_empty_and_tiny(ctx):
+    seq = mmseqsdb.from_sequences([b"A", b"AC", b"ATG", b"ATGAAATAG", b"NNNNNNNNNNNN"], 1, keys=[2, 5, 6, 9, 11])
+    ddb = ctx.upload(seq)
+    op = api.OrfParams(min_length=1, max_length=32734, max_gaps=2147483647, contig_start_mode=2, contig_end_mode=2, orf_start_mode=1,
+                       forward_frames=7, reverse_frames=7, translation_table=1, use_all_table_starts=0)
+    for tr in (False, True):
+        out, info = ctx.extractorfs(ddb, op, translate=tr)
+        got = out.download()
+        out.free()
+        want, winfo = ob.extractorfs(seq, ob.OrfParams(**{f: getattr(op, f) for f, _ in ob.OrfParams._fields_}), tr)
+        assert np.array_equal(info, winfo)
+        assert got.entries_by_key() == want.entries_by_key()
+    ddb.free()
+
+
+def test_cli_extractorfs_and_translatenucs(golden_root, tmp_path):
+    d, man = golden_case("orf_aa", golden_root)
+    for s in man["steps"]:
+        if s["cmd"] == "extractorfs" and s["dbs"][1] in ("nucl_start", "nucl_long"):
+            out = str(tmp_path / (s["dbs"][1] + "_gpu"))
+            run([CLI, "extractorfs", os.path.join(d, "nucl_reads"), out] + s["args"])
+            for ext in ("", "_h"):
+                got, want = mmseqsdb.read_db(out + ext), mmseqsdb.read_db(os.path.join(d, s["dbs"][1] + ext))
+                assert got.dbtype == want.dbtype
+                assert_same_entries(got.entries_by_key(), want.entries_by_key(), "%s%s via CLI" % (s["dbs"][1], ext))
+            aa = str(tmp_path / ("aa_" + s["dbs"][1] + "_gpu"))
+            run([CLI, "translatenucs", out, aa, "--translation-table", "1", "--add-orf-stop", "1", "-v", "3", "--compressed", "0", "--threads", "1"])
+            got, want = mmseqsdb.read_db(aa), mmseqsdb.read_db(os.path.join(d, "aa_" + s["dbs"][1][len("nucl_"):]))
+            assert got.dbtype == want.dbtype == 0
+            assert_same_entries(got.entries_by_key(), want.entries_by_key(), "aa_%s via CLI" % s["dbs"][1])
+            assert os.path.exists(aa + "_h.index")          # the header DB travels with the translated DB (softlinkDb)

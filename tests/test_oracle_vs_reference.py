@@ -159,6 +159,10 @@ def test_extractorfs_translatenucs(golden_root):
     reads = mmseqsdb.read_db(os.path.join(d, "nucl_reads"))
     runs = [s for s in man["steps"] if s["cmd"] == "extractorfs"]
     assert len(runs) == 5
+    # raw reads, --add-orf-stop 0: every length class mod 3, reads shorter than a codon are dropped
+    raw = mmseqsdb.read_db(os.path.join(d, "aa_reads"))
+    assert raw.n < reads.n
+    assert_same_entries(ob.translatenucs(reads).entries_by_key(), raw.entries_by_key(), "orf_aa/aa_reads")
     for s in runs:
         name = s["dbs"][1]
         op = ob.orf_params_from_flags(parse_flags(s["args"]))
@@ -167,6 +171,10 @@ def test_extractorfs_translatenucs(golden_root):
         assert want.dbtype == 1 and nuc.n == want.n > 200, (name, nuc.n, want.n)
         assert_same_entries(nuc.entries_by_key(), want.entries_by_key(), "orf_aa/" + name)
         assert_same_entries(ob.orf_header_entries(info), mmseqsdb.read_db(os.path.join(d, name + "_h")).entries_by_key(), "orf_aa/%s_h" % name)
+        # translatenucs on the reference's own ORF DB, flags from its header DB
+        flags = ob.orf_flags_from_headers(mmseqsdb.read_db(os.path.join(d, name + "_h")), want.keys)
+        assert_same_entries(ob.translatenucs(want, flags).entries_by_key(),
+                            mmseqsdb.read_db(os.path.join(d, "aa_" + name[len("nucl_"):])).entries_by_key(), "orf_aa/translatenucs " + name)
         aa, info2 = ob.extractorfs(reads, op, True)
         assert np.array_equal(info, info2)
         assert_same_entries(aa.entries_by_key(), mmseqsdb.read_db(os.path.join(d, "aa_" + name[len("nucl_"):])).entries_by_key(), "orf_aa/aa_" + name[len("nucl_"):])
