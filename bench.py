@@ -242,6 +242,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-sample-reads", type=int, default=400000, help="reads in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the (untimed-for-the-metric) measurements of the neighbouring steps")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -431,6 +432,36 @@ def main():
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": "reads/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % e}
 
+    # ---- neighbouring steps of the iteration, measured for the record; not part of the metric ----------
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            extras = {}
+            # plass STEP 0 fused: two kmermatcher + rescorediagonal passes around findassemblystart, then assembleresults
+            for _ in range(2):
+                corr, out0, _, _ = ctx.assemble_step0(ddb, kp, rp, ep)
+                t0 = ctx.timings()
+                corr.free(); out0.free()
+            extras["step0_fused_ms"] = t0["total_ms"]
+            # reads -> aa_6f_start_long on the GPU (extractorfs x 2 + translatenucs x 2 + concatdbs, data/assemble.sh:41-77)
+            reads = synth.make_reads_fast(min(args.reads, 5000000), seed=args.seed)
+            dn = ctx.upload(synth.nucleotide_db(reads))
+            n_reads_orf = int(reads.shape[0])
+            del reads
+            ms = 0.0
+            for rep_i in range(2):
+                ms = 0.0
+                lo, _ = ctx.extractorfs(dn, api.orf_params_long(), translate=True, want_info=False); ms += ctx.timings()["total_ms"]
+                st, _ = ctx.extractorfs(dn, api.orf_params_start(), translate=True, want_info=False); ms += ctx.timings()["total_ms"]
+                cat = ctx.concat(lo, st); ms += ctx.timings()["total_ms"]
+                n_frag = cat.n
+                lo.free(); st.free(); cat.free()
+            dn.free()
+            extras["six_frame_fragments_ms"] = ms
+            extras["six_frame_fragments"] = {"reads": n_reads_orf, "fragments": int(n_frag), "reads_per_s": n_reads_orf / (ms / 1e3)}
+        except Exception as e:  # noqa: BLE001
+            extras = {"failed": str(e)}
+
     if rank == 0:
         line = {
             "metric": "reads/sec per assemble iteration (kmermatcher+rescorediagonal+assembleresults)", "value": value, "unit": "reads/s",
@@ -447,7 +478,7 @@ def main():
                     "phases_ms": ({"upload": float(np.mean([p[0] for p in e2e_phases])), "iteration_with_hits_alns_d2h": float(np.mean([p[1] for p in e2e_phases])),
                                    "download_new_db": float(np.mean([p[2] for p in e2e_phases]))} if e2e_phases else None)},
             "gpu_launches": int(sum(t["kernel_launches"] for t in tim)),
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "stage_ms": stage_ms,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "stage_ms": stage_ms, "extras": extras,
         }
         emit_json(line)
     ddb.free()

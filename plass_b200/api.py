@@ -311,14 +311,15 @@ class Context:
         return corr, out, hits, alns
 
     # extractorfs [+ translatenucs --add-orf-stop 1] (lib/mmseqs/src/util/extractorfs.cpp:20, translatenucs.cpp:14)
-    def extractorfs(self, ddb, op, translate=False):
-        """Returns (fragment DeviceSeqDB keyed 0..n-1, orf_info uint32 (n, 4): read key, fromPos, toPos, flags)."""
+    def extractorfs(self, ddb, op, translate=False, want_info=True):
+        """Returns (fragment DeviceSeqDB keyed 0..n-1, orf_info uint32 (n, 4): read key, fromPos, toPos, flags -- or None)."""
         h, info = C.c_void_p(), C.c_void_p()
-        _check(load_library().pg_extractorfs(self.handle, ddb.handle, C.byref(op), C.c_int(1 if translate else 0), C.byref(h), C.byref(info)), "pg_extractorfs")
+        _check(load_library().pg_extractorfs(self.handle, ddb.handle, C.byref(op), C.c_int(1 if translate else 0), C.byref(h),
+                                             C.byref(info) if want_info else None), "pg_extractorfs")
         out = DeviceSeqDB(self, h)
         out.dbtype = 0 if translate else 1
         n = out.n
-        return out, _take(info, 4 * n, np.dtype("<u4")).reshape(n, 4)
+        return out, (_take(info, 4 * n, np.dtype("<u4")).reshape(n, 4) if want_info else None)
 
     def translatenucs(self, ddb, flags=None, translation_table=1):
         fl = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
@@ -339,8 +340,8 @@ class Context:
 
     def six_frame_fragments(self, reads_ddb, min_length=45):
         """nucl_reads -> aa_6f_start_long as data/assemble.sh:41-77 builds it: long ORFs first, then the start fragments."""
-        lo, _ = self.extractorfs(reads_ddb, orf_params_long(min_length), translate=True)
-        st, _ = self.extractorfs(reads_ddb, orf_params_start(min_length), translate=True)
+        lo, _ = self.extractorfs(reads_ddb, orf_params_long(min_length), translate=True, want_info=False)
+        st, _ = self.extractorfs(reads_ddb, orf_params_start(min_length), translate=True, want_info=False)
         out = self.concat(lo, st)
         lo.free(); st.free()
         return out
