@@ -32,16 +32,20 @@ constexpr char ORF_PAD = 127;                // CHAR_MAX: the padding behind the
 
 // character p of the strand: forward = the read ('u' -> 't' only: the 'U' branch of Orf::setSequence is overwritten,
 // Orf.cpp:144-147), reverse = complement of the read backwards with '.' -> 'N' (:149-155)
-__device__ __forceinline__ char orf_char(const char *__restrict__ seq, unsigned L, unsigned p, bool reverse) {
+// The two 256-byte tables are read with a different index in every lane: the kernels copy them from constant to shared
+// memory (the constant cache serialises divergent addresses).
+struct OrfLut { const char *rc; const unsigned char *b2i; };
+
+__device__ __forceinline__ char orf_char(const char *__restrict__ seq, unsigned L, unsigned p, bool reverse, const OrfLut &lut) {
     if (p >= L) return ORF_PAD;
     char ch = seq[reverse ? (L - 1 - p) : p];
     if (ch == 'u') ch = 't';
-    if (reverse) { ch = c_orf_rc[(unsigned char) ch]; if (ch == '.') ch = 'N'; }
+    if (reverse) { ch = lut.rc[(unsigned char) ch]; if (ch == '.') ch = 'N'; }
     return ch;
 }
 __device__ __forceinline__ char orf_upper(char ch) { return ch == ORF_PAD ? ORF_PAD : (char) (ch & (char) ~0x20); }
 __device__ __forceinline__ bool orf_is(char a, char b, char c, char x, char y, char z) { return a == x && b == y && c == z; }
-__device__ __forceinline__ bool orf_gap(char ch) { return ch == 'N' || c_orf_rc[(unsigned char) ch] == '.'; }
+__device__ __forceinline__ bool orf_gap(char ch, const OrfLut &lut) { return ch == 'N' || lut.rc[(unsigned char) ch] == '.'; }
 
 struct OrfEmit {
     char *data;                        // output data file
@@ -55,18 +59,18 @@ struct OrfEmit {
 
 template <bool EMIT>
 __device__ void orf_scan_strand(const char *__restrict__ seq, unsigned L, bool reverse, unsigned frames, const OrfConst &c,
-                                const char *__restrict__ aminoAcid, unsigned &nOrf, unsigned long long &nBytes, OrfEmit &e) {
+                                const char *__restrict__ aminoAcid, const OrfLut &lut, unsigned &nOrf, unsigned long long &nBytes, OrfEmit &e) {
     // Orf::findForward: per-frame state, initially inside an ORF that starts at the frame offset (:207-218)
     bool inside[3] = {true, true, true}, hasStart[3] = {false, false, false};
     unsigned gaps[3] = {0, 0, 0}, len[3] = {0, 0, 0}, from[3] = {0, 1, 2};
     const unsigned nPos = ((L - 2 + 2) / 3) * 3;                 // positions visited: i = 0, 3, ... < L - 2, position = i .. i + 2
-    char r0 = orf_char(seq, L, 0, reverse), r1 = orf_char(seq, L, 1, reverse), r2;
+    char r0 = orf_char(seq, L, 0, reverse, lut), r1 = orf_char(seq, L, 1, reverse, lut), r2;
     // nPos is a multiple of three: unrolling by the frame keeps the per-frame state in registers
     for (unsigned pos0 = 0; pos0 < nPos; pos0 += 3) {
 #pragma unroll
       for (int frame = 0; frame < 3; frame++) {
         const unsigned position = pos0 + frame;
-        r2 = orf_char(seq, L, position + 2, reverse);
+        r2 = orf_char(seq, L, position + 2, reverse, lut);
         const char c0 = orf_upper(r0), c1 = orf_upper(r1), c2 = orf_upper(r2);
         r0 = r1; r1 = r2;
         if (!(frames & (1u << frame))) continue;
@@ -81,7 +85,7 @@ __device__ void orf_scan_strand(const char *__restrict__ seq, unsigned L, bool r
         const bool stop = orf_is(c0, c1, c2, 'T', 'A', 'A') || orf_is(c0, c1, c2, 'T', 'A', 'G') || orf_is(c0, c1, c2, 'T', 'G', 'A');
         if (inside[frame]) {
             if (!stop) len[frame]++;
-            if (orf_gap(c0) || orf_gap(c1) || orf_gap(c2)) gaps[frame]++;
+            if (orf_gap(c0, lut) || orf_gap(c1, lut) || orf_gap(c2, lut)) gaps[frame]++;
         }
         if (inside[frame] && (stop || isLast)) {
             inside[frame] = false;
@@ -102,8 +106,8 @@ __device__ void orf_scan_strand(const char *__restrict__ seq, unsigned L, bool r
                 // residue already is one (ambiguity codes such as TAR translate to '*' without being a stop codon)
                 addStart = !incStart; addEnd = !incEnd;
                 if (addEnd) {
-                    const unsigned i0 = c_orf_b2i[(unsigned char) orf_char(seq, L, to - 2, reverse)], i1 = c_orf_b2i[(unsigned char) orf_char(seq, L, to - 1, reverse)],
-                                   i2 = c_orf_b2i[(unsigned char) orf_char(seq, L, to, reverse)];
+                    const unsigned i0 = lut.b2i[(unsigned char) orf_char(seq, L, to - 2, reverse, lut)], i1 = lut.b2i[(unsigned char) orf_char(seq, L, to - 1, reverse, lut)],
+                                   i2 = lut.b2i[(unsigned char) orf_char(seq, L, to, reverse, lut)];
                     if (aminoAcid[256 * i0 + 16 * i1 + i2 + 1] == '*') addEnd = false;
                 }
                 entryLen = nt / 3 + 1 + (addStart ? 1u : 0u) + (addEnd ? 1u : 0u) + 1;
@@ -111,15 +115,15 @@ __device__ void orf_scan_strand(const char *__restrict__ seq, unsigned L, bool r
             if (EMIT) {
                 char *w = e.data + e.byteOff;
                 if (!c.translate) {
-                    for (unsigned k = 0; k < nt; k++) w[k] = orf_char(seq, L, f + k, reverse);
+                    for (unsigned k = 0; k < nt; k++) w[k] = orf_char(seq, L, f + k, reverse, lut);
                     w[nt] = '\n'; w[nt + 1] = '\0';
                 } else {
                     unsigned o = 0;
                     if (addStart) w[o++] = '*';
                     for (unsigned k = 0; k < nt; k += 3) {
-                        const char a = orf_char(seq, L, f + k, reverse), b = orf_char(seq, L, f + k + 1, reverse), d = orf_char(seq, L, f + k + 2, reverse);
+                        const char a = orf_char(seq, L, f + k, reverse, lut), b = orf_char(seq, L, f + k + 1, reverse, lut), d = orf_char(seq, L, f + k + 2, reverse, lut);
                         const bool lower = (a >= 'a' && a <= 'z') || (b >= 'a' && b <= 'z') || (d >= 'a' && d <= 'z');
-                        char res = aminoAcid[256 * c_orf_b2i[(unsigned char) a] + 16 * c_orf_b2i[(unsigned char) b] + c_orf_b2i[(unsigned char) d] + 1];
+                        char res = aminoAcid[256 * lut.b2i[(unsigned char) a] + 16 * lut.b2i[(unsigned char) b] + lut.b2i[(unsigned char) d] + 1];
                         if (lower && res >= 'A' && res <= 'Z') res = (char) (res + 32);
                         w[o++] = res;
                     }
@@ -143,15 +147,23 @@ __device__ void orf_scan_strand(const char *__restrict__ seq, unsigned L, bool r
     }
 }
 
+// (Copying every read into a per-thread slot of shared memory before walking it was measured: 41 ms instead of 35 ms for
+// 5 M reads -- the 46 KB of slots cut the occupancy to 16 warps / SM, which costs more than the byte-wise global reads.)
+
 template <bool EMIT>
 __global__ void __launch_bounds__(128) orf_kernel(const pg_seqdb db, const OrfConst c, const char *__restrict__ aminoAcidG,
                                                   unsigned *__restrict__ cnt, unsigned *__restrict__ bytes,
                                                   const unsigned long long *__restrict__ cntOff, const unsigned long long *__restrict__ byteOff,
                                                   char *__restrict__ oData, unsigned long long *__restrict__ oOffsets, unsigned *__restrict__ oLens,
                                                   unsigned *__restrict__ oKeys, unsigned *__restrict__ oInfo) {
-    __shared__ char sAmino[4112];
+    extern __shared__ __align__(16) unsigned char orf_smem[];
+    char *sAmino = reinterpret_cast<char *>(orf_smem);                    // 4112 bytes
+    char *sRc = sAmino + 4112;                                            // 256
+    unsigned char *sB2i = reinterpret_cast<unsigned char *>(sRc + 256);   // 256
     for (int i = threadIdx.x; i < 4097; i += blockDim.x) sAmino[i] = aminoAcidG[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { sRc[i] = c_orf_rc[i]; sB2i[i] = c_orf_b2i[i]; }
     __syncthreads();
+    OrfLut lut; lut.rc = sRc; lut.b2i = sB2i;
     const unsigned n = (unsigned) db.n;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const unsigned L = db.lens[i] - 2;
@@ -164,8 +176,8 @@ __global__ void __launch_bounds__(128) orf_kernel(const pg_seqdb db, const OrfCo
         }
         if (L >= 3) {                                                                      // Orf::setSequence (Orf.cpp:127-131)
             const char *seq = db.data + db.offsets[i];
-            if (c.forwardFrames) orf_scan_strand<EMIT>(seq, L, false, c.forwardFrames, c, sAmino, nOrf, nBytes, e);
-            if (c.reverseFrames) orf_scan_strand<EMIT>(seq, L, true, c.reverseFrames, c, sAmino, nOrf, nBytes, e);
+            if (c.forwardFrames) orf_scan_strand<EMIT>(seq, L, false, c.forwardFrames, c, sAmino, lut, nOrf, nBytes, e);
+            if (c.reverseFrames) orf_scan_strand<EMIT>(seq, L, true, c.reverseFrames, c, sAmino, lut, nOrf, nBytes, e);
         }
         if (!EMIT) { cnt[i] = nOrf; bytes[i] = (unsigned) nBytes; }
     }
@@ -191,7 +203,9 @@ __global__ void __launch_bounds__(128) tn_kernel(const pg_seqdb db, const unsign
                                                  const unsigned long long *__restrict__ keepIdx, const unsigned long long *__restrict__ outOff,
                                                  char *__restrict__ oData, unsigned long long *__restrict__ oOffsets, unsigned *__restrict__ oLens, unsigned *__restrict__ oKeys) {
     __shared__ char sAmino[4112];
+    __shared__ unsigned char sB2i[256];
     for (int i = threadIdx.x; i < 4097; i += blockDim.x) sAmino[i] = aminoAcidG[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sB2i[i] = c_orf_b2i[i];
     __syncthreads();
     const unsigned n = (unsigned) db.n;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -205,7 +219,7 @@ __global__ void __launch_bounds__(128) tn_kernel(const pg_seqdb db, const unsign
         auto residue = [&](unsigned k) {                     // codon k; bytes beyond the residues are the entry's own "\n\0"
             const char a = seq[3 * k], b = seq[3 * k + 1], d = seq[3 * k + 2];
             const bool lower = (a >= 'a' && a <= 'z') || (b >= 'a' && b <= 'z') || (d >= 'a' && d <= 'z');
-            char res = sAmino[256 * c_orf_b2i[(unsigned char) a] + 16 * c_orf_b2i[(unsigned char) b] + c_orf_b2i[(unsigned char) d] + 1];
+            char res = sAmino[256 * sB2i[(unsigned char) a] + 16 * sB2i[(unsigned char) b] + sB2i[(unsigned char) d] + 1];
             if (lower && res >= 'A' && res <= 'Z') res = (char) (res + 32);
             return res;
         };
@@ -344,8 +358,17 @@ int orf_run(Context *ctx, const pg_seqdb *db, const pg_orf_params *p, int transl
     unsigned long long *cntOff = (unsigned long long *) (bb + oCntOff), *byteOff = (unsigned long long *) (bb + oByteOff);
     unsigned long long totals[2] = {0, 0};
     const unsigned blocks = std::max(1u, std::min<unsigned>((n + 127) / 128, NUM_SMS * 16));
+    constexpr size_t ORF_SMEM_BYTES = 4112 + 512;
+    {
+        static bool attr = false;
+        if (!attr) {
+            PG_CUDA(cudaFuncSetAttribute(orf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ORF_SMEM_BYTES));
+            PG_CUDA(cudaFuncSetAttribute(orf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ORF_SMEM_BYTES));
+            attr = true;
+        }
+    }
     if (n) {
-        orf_kernel<false><<<blocks, 128, 0, s>>>(*db, c, dAmino, cnt, bytes, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        orf_kernel<false><<<blocks, 128, ORF_SMEM_BYTES, s>>>(*db, c, dAmino, cnt, bytes, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
         ctx->launches++;
         unsigned long long *d_tot = ctx->small.as<unsigned long long>() + 46;
         PG_TRY(exclusive_scan_u32(cnt, cntOff, n, d_tot, bb + oScan, scan_workspace_bytes(n), s, &ctx->launches));
@@ -362,7 +385,7 @@ int orf_run(Context *ctx, const pg_seqdb *db, const pg_orf_params *p, int transl
     PG_CUDA(cudaMallocAsync(&out->keys, sizeof(unsigned) * (nFrag + 1), s));
     PG_TRY(ctx->orfInfo.reserve(sizeof(unsigned) * 4 * (nFrag + 1)));
     if (nFrag) {
-        orf_kernel<true><<<blocks, 128, 0, s>>>(*db, c, dAmino, cnt, bytes, cntOff, byteOff, out->data, out->offsets, out->lens, out->keys, ctx->orfInfo.as<unsigned>());
+        orf_kernel<true><<<blocks, 128, ORF_SMEM_BYTES, s>>>(*db, c, dAmino, cnt, bytes, cntOff, byteOff, out->data, out->offsets, out->lens, out->keys, ctx->orfInfo.as<unsigned>());
         ctx->launches++;
     }
     PG_CUDA(cudaGetLastError());
