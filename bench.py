@@ -459,8 +459,27 @@ def main():
             dn.free()
             extras["six_frame_fragments_ms"] = ms
             extras["six_frame_fragments"] = {"reads": n_reads_orf, "fragments": int(n_frag), "reads_per_s": n_reads_orf / (ms / 1e3)}
+            # the nucleotide path (penguin nuclassemble, k = 22): one iteration + cyclecheck on the same reads
+            nreads = synth.make_reads_fast(min(args.reads, 5000000), seed=args.seed + 100)
+            dn = ctx.upload(synth.nucleotide_db(nreads))
+            del nreads
+            nkp, nrp, nep = api.default_km_params(True), api.default_rs_params(True), api.default_ex_params(True)
+            for _ in range(2):
+                nout = ctx.assemble_iteration(dn, nkp, nrp, nep)[0]
+                tn = ctx.timings()
+                n_nt_out = nout.n
+                for _c in range(2):
+                    split = ctx.cyclecheck(nout, 200000)
+                    tc = ctx.timings()
+                nout.free()
+            dn.free()
+            extras["nucl_iteration"] = {"reads": int(min(args.reads, 5000000)), "ms": tn["total_ms"],
+                                        "stage_ms": {k: tn[k] for k in ("extract_ms", "sort1_ms", "group_ms", "sort2_ms", "reduce_ms", "rescore_ms", "extend_ms")},
+                                        "kmer_records": int(tn["n_kmer_records"]), "hits": int(tn["n_hits"]), "alignments": int(tn["n_alns"]),
+                                        "output_sequences": int(n_nt_out)}
+            extras["cyclecheck"] = {"sequences": int(n_nt_out), "ms": tc["total_ms"], "reported": int((split > 0).sum())}
         except Exception as e:  # noqa: BLE001
-            extras = {"failed": str(e)}
+            extras = dict(extras or {}, failed=str(e))
 
     if rank == 0:
         line = {

@@ -333,8 +333,8 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
         // twice in the sequence.  Then the sorted walk of kmermatcher.cpp:274-347 selects all of them and their order is
         // irrelevant (the records are re-ordered globally afterwards), so neither the sort nor the walk is needed.
         // Duplicates are detected with a small open-addressing set in shared memory (the output staging area).
-        bool allDistinct = false;
-        if (c.ignoreMulti && cnt > 0 && kmerConsidered >= (unsigned long long) cnt) {
+        bool noDup = false;
+        if (c.ignoreMulti && cnt > 0) {
             unsigned long long *set = reinterpret_cast<unsigned long long *>(outRecs);
             constexpr unsigned SLOTS = 2 * NMAX;
             for (int i = lane; i < (int) SLOTS; i += 32) set[i] = ~0ULL;
@@ -350,10 +350,63 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
                     slot = (slot + 1) & (SLOTS - 1);
                 }
             }
-            allDistinct = __ballot_sync(0xFFFFFFFFu, dup) == 0;
+            noDup = __ballot_sync(0xFFFFFFFFu, dup) == 0;
             __syncwarp();
         }
-        if (!allDistinct) {
+        const bool allDistinct = noDup && kmerConsidered >= (unsigned long long) cnt;
+        // Sort-free selection when only a part of the (distinct) k-mers is taken -- the nucleotide workflow keeps
+        // 59 + 0.1 L of the L - 21 k-mers of a read.  The sorted walk of kmermatcher.cpp:274-347 then selects every k-mer
+        // whose score lies below the score t of the kmerConsidered-th smallest, plus the first `tooMuch` (all, if
+        // tooMuch == 0) of the k-mers with score t in (k-mer, position) order, capped at kmerConsidered.  t comes from a
+        // 16-step radix select over the scores; only the (usually one or two) k-mers of the last bin need an order.
+        bool quick = false, keepMine = false;
+        unsigned qT = 0;
+        PCand mine; mine.hi = 0; mine.lo = 0;
+        if (noDup && !allDistinct && kmerConsidered > 0) {
+            const int k = (int) kmerConsidered;
+            unsigned t = 0;
+            for (int bit = 15; bit >= 0; bit--) {
+                const unsigned trial = t | (1u << bit);
+                int below = 0;
+                for (int p0 = 0; p0 < cnt; p0 += 32) {
+                    const int i = p0 + lane;
+                    below += __popc(__ballot_sync(0xFFFFFFFFu, i < cnt && pc_score(cand[i]) < trial));
+                }
+                if (below < k) t = trial;                    // the k-th smallest score is >= trial
+            }
+            int below = 0, inBins = 0;
+            for (int p0 = 0; p0 < cnt; p0 += 32) {
+                const int i = p0 + lane;
+                const unsigned sc = i < cnt ? pc_score(cand[i]) : 0xFFFFFFFFu;
+                below += __popc(__ballot_sync(0xFFFFFFFFu, sc < t));
+                inBins += __popc(__ballot_sync(0xFFFFFFFFu, sc <= t));
+            }
+            const int lastBin = inBins - below, tooMuch = inBins - k;
+            if (lastBin <= 32) {
+                quick = true;
+                qT = t;
+                int nLast = tooMuch > 0 ? min(tooMuch, lastBin) : lastBin;
+                nLast = min(nLast, k - below);
+                PCand *lastList = reinterpret_cast<PCand *>(outRecs);     // the set is dead, the staging area not yet in use
+                int base = 0;
+                for (int p0 = 0; p0 < cnt; p0 += 32) {
+                    const int i = p0 + lane;
+                    const bool is = i < cnt && pc_score(cand[i]) == t;
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, is);
+                    if (is) lastList[base + __popc(m & ltMask)] = cand[i];
+                    base += __popc(m);
+                }
+                __syncwarp();
+                if (lane < lastBin) {
+                    mine = lastList[lane];
+                    int rank = 0;
+                    for (int j = 0; j < lastBin; j++) rank += pc_less(lastList[j], mine) ? 1 : 0;
+                    keepMine = rank < nLast;
+                }
+                __syncwarp();
+            }
+        }
+        if (!allDistinct && !quick) {
             int n2 = 1;
             while (n2 < cnt) n2 <<= 1;
             for (int i = cnt + lane; i < n2; i += 32) { cand[i].hi = ~0ULL; cand[i].lo = ~0ULL; }
@@ -392,6 +445,31 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
                     Rec r;
                     r.w0 = pc_kmer_stored(pc, c.nt);
                     r.w1 = kmer_w1(c, id, si, (unsigned) L, pc_pos(pc));
+                    outRecs[nOut + __popc(m & ltMask)] = r;
+                }
+                nOut += __popc(m);
+            }
+        } else if (quick) {
+            for (int p0 = 0; p0 < cnt; p0 += 32) {
+                const int i = p0 + lane;
+                bool emit = false; PCand pc; pc.hi = 0; pc.lo = 0;
+                if (i < cnt) { pc = cand[i]; const unsigned sc = pc_score(pc); emit = sc < qT && sc >= c.hashStart && sc <= c.hashEnd; }
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, emit);
+                if (emit) {
+                    Rec r;
+                    r.w0 = pc_kmer_stored(pc, c.nt);
+                    r.w1 = kmer_w1(c, id, si, (unsigned) L, pc_pos(pc));
+                    outRecs[nOut + __popc(m & ltMask)] = r;
+                }
+                nOut += __popc(m);
+            }
+            {
+                const bool emit = keepMine && qT >= c.hashStart && qT <= c.hashEnd;
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, emit);
+                if (emit) {
+                    Rec r;
+                    r.w0 = pc_kmer_stored(mine, c.nt);
+                    r.w1 = kmer_w1(c, id, si, (unsigned) L, pc_pos(mine));
                     outRecs[nOut + __popc(m & ltMask)] = r;
                 }
                 nOut += __popc(m);
