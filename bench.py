@@ -77,7 +77,7 @@ def make_fragments(n_reads, seed):
     db = synth.protein_fragments(reads, workers=min(16, os.cpu_count() or 1))
     del reads
     log("[bench] generated %d reads -> %d aa fragments (mean %.1f aa) in %.1f s" % (n_reads, db.n, float(db.lens.mean()) - 2, time.time() - t))
-    if n_reads <= 12000000:      # the cache only serves the other ranks of a multi-GPU run and repeated small samples
+    if n_reads <= 45000000:      # the cache only serves the other ranks of a multi-GPU run (up to 8 x 5 M reads) and repeated small samples
         try:
             np.savez(cache, data=db.data, keys=db.keys, offsets=db.offsets, lens=db.lens)
         except OSError:
