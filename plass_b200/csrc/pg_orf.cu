@@ -27,6 +27,14 @@ struct OrfConst {
 
 __constant__ char c_orf_rc[256];             // Orf::iupacReverseComplementTable (Orf.cpp:48-52)
 __constant__ unsigned char c_orf_b2i[256];   // TranslateNucl::sm_BaseToIdx
+// Codon tests of Orf::findForward as integer compares: every character is mapped ONCE to a 3-bit class -- 0..3 = A C G T
+// (after the upper-casing of :226-229), 4 = any other IUPAC letter, 5 = 'N' or a character whose complement is '.'
+// (isGapOrN, :181-185), 7 = the CHAR_MAX padding -- by one table for the forward strand and one for the reverse strand
+// (class of the complemented character, '.' -> 'N').  A codon is c0 * 64 + c1 * 8 + c2.
+__constant__ unsigned char c_orf_clsF[256];
+__constant__ unsigned char c_orf_clsR[256];
+constexpr unsigned ORF_ATG = 0 * 64 + 3 * 8 + 2, ORF_TTG = 3 * 64 + 3 * 8 + 2, ORF_CTG = 1 * 64 + 3 * 8 + 2;
+constexpr unsigned ORF_TAA = 3 * 64 + 0 * 8 + 0, ORF_TAG = 3 * 64 + 0 * 8 + 2, ORF_TGA = 3 * 64 + 2 * 8 + 0;
 
 constexpr char ORF_PAD = 127;                // CHAR_MAX: the padding behind the sequence (Orf.cpp:158-161)
 
@@ -34,7 +42,12 @@ constexpr char ORF_PAD = 127;                // CHAR_MAX: the padding behind the
 // Orf.cpp:144-147), reverse = complement of the read backwards with '.' -> 'N' (:149-155)
 // The two 256-byte tables are read with a different index in every lane: the kernels copy them from constant to shared
 // memory (the constant cache serialises divergent addresses).
-struct OrfLut { const char *rc; const unsigned char *b2i; };
+struct OrfLut { const char *rc; const unsigned char *b2i; const unsigned char *clsF, *clsR; };
+
+__device__ __forceinline__ unsigned orf_class(const char *__restrict__ seq, unsigned L, unsigned p, bool reverse, const OrfLut &lut) {
+    if (p >= L) return 7u;
+    return reverse ? lut.clsR[(unsigned char) seq[L - 1 - p]] : lut.clsF[(unsigned char) seq[p]];
+}
 
 __device__ __forceinline__ char orf_char(const char *__restrict__ seq, unsigned L, unsigned p, bool reverse, const OrfLut &lut) {
     if (p >= L) return ORF_PAD;
@@ -64,28 +77,29 @@ __device__ void orf_scan_strand(const char *__restrict__ seq, unsigned L, bool r
     bool inside[3] = {true, true, true}, hasStart[3] = {false, false, false};
     unsigned gaps[3] = {0, 0, 0}, len[3] = {0, 0, 0}, from[3] = {0, 1, 2};
     const unsigned nPos = ((L - 2 + 2) / 3) * 3;                 // positions visited: i = 0, 3, ... < L - 2, position = i .. i + 2
-    char r0 = orf_char(seq, L, 0, reverse, lut), r1 = orf_char(seq, L, 1, reverse, lut), r2;
+    unsigned c0 = orf_class(seq, L, 0, reverse, lut), c1 = orf_class(seq, L, 1, reverse, lut), c2 = 7u;
     // nPos is a multiple of three: unrolling by the frame keeps the per-frame state in registers
     for (unsigned pos0 = 0; pos0 < nPos; pos0 += 3) {
 #pragma unroll
       for (int frame = 0; frame < 3; frame++) {
         const unsigned position = pos0 + frame;
-        r2 = orf_char(seq, L, position + 2, reverse, lut);
-        const char c0 = orf_upper(r0), c1 = orf_upper(r1), c2 = orf_upper(r2);
-        r0 = r1; r1 = r2;
+        if (position > 0) { c0 = c1; c1 = c2; }
+        c2 = orf_class(seq, L, position + 2, reverse, lut);
         if (!(frames & (1u << frame))) continue;
-        const bool thisIncomplete = c0 == ORF_PAD || c1 == ORF_PAD || c2 == ORF_PAD;
+        const unsigned codon = c0 * 64u + c1 * 8u + c2;
+        const bool thisIncomplete = c0 == 7u || c1 == 7u || c2 == 7u;
         const bool isLast = !thisIncomplete && (position + 5 >= L);                       // the next codon of the frame runs into the padding
-        const bool start = orf_is(c0, c1, c2, 'A', 'T', 'G') || (c.allStarts && (orf_is(c0, c1, c2, 'T', 'T', 'G') || orf_is(c0, c1, c2, 'C', 'T', 'G')));
+        const bool start = codon == ORF_ATG || (c.allStarts && (codon == ORF_TTG || codon == ORF_CTG));
         bool shouldStart;
         if (c.startMode == 0) shouldStart = !inside[frame] && start;
         else if (c.startMode == 1) shouldStart = !inside[frame];
         else shouldStart = start;
         if (shouldStart) { inside[frame] = true; hasStart[frame] = true; from[frame] = position; gaps[frame] = 0; len[frame] = 0; }
-        const bool stop = orf_is(c0, c1, c2, 'T', 'A', 'A') || orf_is(c0, c1, c2, 'T', 'A', 'G') || orf_is(c0, c1, c2, 'T', 'G', 'A');
+        const bool stop = codon == ORF_TAA || codon == ORF_TAG || codon == ORF_TGA;
         if (inside[frame]) {
             if (!stop) len[frame]++;
-            if (orf_gap(c0, lut) || orf_gap(c1, lut) || orf_gap(c2, lut)) gaps[frame]++;
+            // the padding counts as a gap as well: its complement is '.' (isGapOrN on CHAR_MAX)
+            if (c0 == 5u || c1 == 5u || c2 == 5u || thisIncomplete) gaps[frame]++;
         }
         if (inside[frame] && (stop || isLast)) {
             inside[frame] = false;
@@ -160,10 +174,11 @@ __global__ void __launch_bounds__(128) orf_kernel(const pg_seqdb db, const OrfCo
     char *sAmino = reinterpret_cast<char *>(orf_smem);                    // 4112 bytes
     char *sRc = sAmino + 4112;                                            // 256
     unsigned char *sB2i = reinterpret_cast<unsigned char *>(sRc + 256);   // 256
+    unsigned char *sClsF = sB2i + 256, *sClsR = sB2i + 512;               // 2 x 256
     for (int i = threadIdx.x; i < 4097; i += blockDim.x) sAmino[i] = aminoAcidG[i];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) { sRc[i] = c_orf_rc[i]; sB2i[i] = c_orf_b2i[i]; }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { sRc[i] = c_orf_rc[i]; sB2i[i] = c_orf_b2i[i]; sClsF[i] = c_orf_clsF[i]; sClsR[i] = c_orf_clsR[i]; }
     __syncthreads();
-    OrfLut lut; lut.rc = sRc; lut.b2i = sB2i;
+    OrfLut lut; lut.rc = sRc; lut.b2i = sB2i; lut.clsF = sClsF; lut.clsR = sClsR;
     const unsigned n = (unsigned) db.n;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const unsigned L = db.lens[i] - 2;
@@ -282,6 +297,21 @@ static int orf_upload_tables(Context *ctx, char **dAmino, unsigned char *workspa
     static unsigned char b2i[256];
     static char amino[4100];
     orf_build_tables(b2i, amino);
+    static unsigned char clsF[256], clsR[256];
+    for (int ch = 0; ch < 256; ch++) {
+        auto classify = [&](unsigned char u) -> unsigned char {          // u: already upper-cased (& ~0x20)
+            if (u == 'A') return 0; if (u == 'C') return 1; if (u == 'G') return 2; if (u == 'T') return 3;
+            if (u == 'N' || rcTable[u] == '.') return 5;
+            return 4;
+        };
+        const unsigned char f = (ch == 'u') ? (unsigned char) 't' : (unsigned char) ch;       // Orf::setSequence (Orf.cpp:144-147)
+        clsF[ch] = (f == 127) ? 7 : classify((unsigned char) (f & 0xDF));
+        char r = rcTable[f];
+        if (r == '.') r = 'N';
+        clsR[ch] = classify((unsigned char) ((unsigned char) r & 0xDF));
+    }
+    PG_CUDA(cudaMemcpyToSymbolAsync(c_orf_clsF, clsF, 256, 0, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(cudaMemcpyToSymbolAsync(c_orf_clsR, clsR, 256, 0, cudaMemcpyHostToDevice, ctx->stream));
     PG_CUDA(cudaMemcpyToSymbolAsync(c_orf_rc, rcTable, 256, 0, cudaMemcpyHostToDevice, ctx->stream));
     PG_CUDA(cudaMemcpyToSymbolAsync(c_orf_b2i, b2i, 256, 0, cudaMemcpyHostToDevice, ctx->stream));
     PG_CUDA(cudaMemcpyAsync(workspace, amino, 4097, cudaMemcpyHostToDevice, ctx->stream));
@@ -358,7 +388,7 @@ int orf_run(Context *ctx, const pg_seqdb *db, const pg_orf_params *p, int transl
     unsigned long long *cntOff = (unsigned long long *) (bb + oCntOff), *byteOff = (unsigned long long *) (bb + oByteOff);
     unsigned long long totals[2] = {0, 0};
     const unsigned blocks = std::max(1u, std::min<unsigned>((n + 127) / 128, NUM_SMS * 16));
-    constexpr size_t ORF_SMEM_BYTES = 4112 + 512;
+    constexpr size_t ORF_SMEM_BYTES = 4112 + 1024;
     {
         static bool attr = false;
         if (!attr) {
