@@ -154,7 +154,7 @@ class ClockSampler:
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -294,12 +294,15 @@ def main():
     ddb = ctx.upload(db)
     peak, peak_src = load_peaks()
     tim = []
+    # the clock sampler (nvidia-smi, one line every 50 ms) is started before the warm-up steps: the tool needs ~0.1 s
+    # before its first line, and the timed region of a few 50 ms steps would otherwise see a single sample.  Warm-up and
+    # timed steps run the same kernels, so every sample is taken under the load that is being measured.
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(args.warmup):
         out = runner.step(ddb, kp, rp, ep) if runner else ctx.assemble_iteration(ddb, kp, rp, ep)[0]
         out.free()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     t0 = time.perf_counter()
     for i in range(args.steps):
         out = runner.step(ddb, kp, rp, ep) if runner else ctx.assemble_iteration(ddb, kp, rp, ep)[0]
