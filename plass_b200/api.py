@@ -19,7 +19,9 @@ LIB_PATH = os.path.join(HERE, "libplassgpu.so")
 EXPORTS = ["pg_last_error", "pg_device_count", "pg_init", "pg_destroy", "pg_get_timings", "pg_seqdb_upload", "pg_seqdb_adopt",
            "pg_seqdb_download", "pg_seqdb_size", "pg_seqdb_free", "pg_kmermatch", "pg_rescore", "pg_extend",
            "pg_assemble_iteration", "pg_free_host", "pg_set_async_results", "pg_results_ticket", "pg_results_wait",
-           "pg_shard_pairs", "pg_shard_extract", "pg_shard_group", "pg_shard_route", "pg_shard_export", "pg_shard_finish", "pg_shard_owner_range", "pg_seqdb_max_key"]
+           "pg_shard_pairs", "pg_shard_extract", "pg_shard_group", "pg_shard_route", "pg_shard_export", "pg_shard_finish", "pg_shard_owner_range", "pg_seqdb_max_key",
+           "pg_seqdb_upload_async", "pg_findassemblystart", "pg_assemble_step0", "pg_cyclecheck", "pg_extractorfs", "pg_translatenucs",
+           "pg_seqdb_concat"]
 
 
 SHARD_HIST_BINS = 4096   # PG_SHARD_HIST_BINS
