@@ -387,6 +387,9 @@ int extractorfs(int argc, const char **argv) {
     requireValue(f, "--compressed", "0", "uncompressed DBs only");
     requireValue(f, "--create-lookup", "0", "lookup files are not written by the GPU path");
     requireValue(f, "--id-offset", "0", "not used by the assemble workflow");
+    // the reference's --translate 1 writes the bare translation; the fused mode of pg_extractorfs is extractorfs +
+    // translatenucs --add-orf-stop 1 ('*' framing), which is a different output: run translatenucs as the workflow does
+    requireValue(f, "--translate", "0", "use translatenucs on the extracted ORFs, as data/assemble.sh does");
     std::string err;
     mmdb::Reader seq;
     if (!seq.open(f.positional[0], err)) die(err);
