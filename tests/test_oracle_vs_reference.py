@@ -178,3 +178,20 @@ def test_extractorfs_translatenucs(golden_root):
         aa, info2 = ob.extractorfs(reads, op, True)
         assert np.array_equal(info, info2)
         assert_same_entries(aa.entries_by_key(), mmseqsdb.read_db(os.path.join(d, "aa_" + name[len("nucl_"):])).entries_by_key(), "orf_aa/aa_" + name[len("nucl_"):])
+
+
+def test_translation_against_an_independent_codon_table():
+    """The IUPAC state-machine table (TranslateNucl.h) restated in the oracle agrees, on plain ACGT input, with the
+    standard genetic code written down independently; ambiguity codes resolve only when every expansion agrees."""
+    aa = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"
+    code = {a + b + c: aa[16 * i + 4 * j + k] for i, a in enumerate("TCAG") for j, b in enumerate("TCAG") for k, c in enumerate("TCAG")}
+    rng = np.random.default_rng(3)
+    seqs = ["".join("ACGT"[x] for x in rng.integers(0, 4, 3 * int(n))) for n in rng.integers(1, 60, 200)]
+    db = mmseqsdb.from_sequences([s.encode() for s in seqs], 1)
+    out = ob.translatenucs(db).entries_by_key()
+    for i, s in enumerate(seqs):
+        want = "".join(code[s[j:j + 3]] for j in range(0, len(s), 3))
+        assert out[i] == (want + "\n").encode(), (s, out[i])
+    # ambiguity: GCN is always Ala, TAR always stop, AAY always Asn, MGR always Arg, NNN unknown, lower case is kept
+    amb = mmseqsdb.from_sequences([b"GCNTARAAYMGRNNNgcaGCa"], 1)
+    assert ob.translatenucs(amb).entries_by_key()[0] == b"A*NRXaa\n"
