@@ -110,6 +110,7 @@ typedef struct {
     uint64_t sort1_bytes;      /* algorithmic bytes of sort #1: one read + one write of every record */
     float sort1_scatter_ms;    /* device time of the radix scatter launches of sort #1 (events around them) */
     uint32_t sort1_passes;     /* number of scatter launches in sort #1 */
+    uint32_t splits;           /* hash-range splits of the kmermatcher stage (1 = everything at once) */
 } pg_timings;
 
 const char *pg_last_error(void);
@@ -139,6 +140,15 @@ int pg_rescore(pg_context *ctx, const pg_seqdb *db, const pg_hit *hits, uint64_t
                pg_aln **alns, uint64_t *n_alns);
 int pg_extend(pg_context *ctx, const pg_seqdb *db, const pg_aln *alns, uint64_t n_alns, const pg_ex_params *p,
               pg_seqdb **out_db, uint8_t **extended);
+
+/* --split-memory-limit (kmermatcherInner, kmermatcher.cpp:608-624: splits = ceil(totalKmers * 16 B / limit);
+ * setupKmerSplits :736-778; merge :926-1104).  `bytes` bounds the two k-mer record buffers of the kmermatcher stage
+ * (0 = 90 % of the device memory that is free when the stage starts).  If the records do not fit, the 16-bit hash space
+ * is cut into 2, 4, 8 ... equal ranges (pg_km_params.hash_start / hash_end per split); every split extracts, sorts and
+ * groups only its k-mers, the (rep, target, diagonal) pair records of all splits are collected and reduced TOGETHER, so
+ * the hits equal the unsplit run's (the reference's own merge pre-aggregates with a saturating 8-bit score and is not
+ * bit-identical to its unsplit path).  pg_timings.splits reports the number used. */
+int pg_set_split_memory_limit(pg_context *ctx, uint64_t bytes);
 
 /* One whole assemble iteration kept in HBM: kmermatcher -> rescorediagonal -> (nucl)assembleresults.
  * `out_db` is the next iteration's input.  If hits/alns pointers are non-NULL the intermediate

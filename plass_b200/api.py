@@ -21,7 +21,7 @@ EXPORTS = ["pg_last_error", "pg_device_count", "pg_init", "pg_destroy", "pg_get_
            "pg_assemble_iteration", "pg_free_host", "pg_set_async_results", "pg_results_ticket", "pg_results_wait",
            "pg_shard_pairs", "pg_shard_extract", "pg_shard_group", "pg_shard_route", "pg_shard_export", "pg_shard_finish", "pg_shard_owner_range", "pg_seqdb_max_key",
            "pg_seqdb_upload_async", "pg_findassemblystart", "pg_assemble_step0", "pg_cyclecheck", "pg_extractorfs", "pg_translatenucs",
-           "pg_seqdb_concat"]
+           "pg_seqdb_concat", "pg_set_split_memory_limit"]
 
 
 SHARD_HIST_BINS = 4096   # PG_SHARD_HIST_BINS
@@ -53,7 +53,7 @@ class Timings(C.Structure):
                                          "extend_ms", "exchange_ms", "total_ms")] + \
                [(n, C.c_uint64) for n in ("n_kmer_records", "n_pair_records", "n_hits", "n_alns", "n_extended",
                                           "kernel_launches", "sort1_bytes")] + \
-               [("sort1_scatter_ms", C.c_float), ("sort1_passes", C.c_uint32)]
+               [("sort1_scatter_ms", C.c_float), ("sort1_passes", C.c_uint32), ("splits", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -209,6 +209,13 @@ class Context:
 
     def results_wait(self, ticket):
         _check(load_library().pg_results_wait(self.handle, C.c_uint64(ticket)), "pg_results_wait")
+
+    def set_split_memory_limit(self, nbytes):
+        """--split-memory-limit: bound on the kmermatcher stage's two record buffers (0 = 90 % of the free device memory)."""
+        _check(load_library().pg_set_split_memory_limit(self.handle, C.c_uint64(int(nbytes))), "pg_set_split_memory_limit")
+
+    def debug_force_splits(self, n):
+        _check(load_library().pg_debug_force_splits(self.handle, C.c_uint(int(n))), "pg_debug_force_splits")
 
     def timings(self):
         t = Timings()

@@ -25,7 +25,7 @@ CUDA_SOURCES = {
     "pg_api.cu": [],
     "pg_radix.cu": [],
     "pg_scan.cu": [],
-    "pg_kmermatch.cu": [],
+    "pg_kmermatch.cu": ["-fmad=false"],   # (float) budget kmersPerSeq - 1 + scale * L: product and sum rounded separately (kmermatcher.cpp:223)
     "pg_rescore.cu": ["-fmad=false"],
     "pg_extend.cu": ["-fmad=false"],
     "pg_next.cu": ["-fmad=false"],

@@ -9,7 +9,7 @@
 
 int main(int argc, const char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "usage: %s <kmermatcher|rescorediagonal|assembleresults|nuclassembleresults|findassemblystart|cyclecheck|extractorfs|translatenucs> <dbs...> [flags]\n", argv[0]);
+        fprintf(stderr, "usage: %s <kmermatcher|rescorediagonal|assembleresults|nuclassembleresults|findassemblystart|cyclecheck|extractorfs|translatenucs|assembleiteration|dbdiff> <dbs...> [flags]\n", argv[0]);
         return EXIT_FAILURE;
     }
     const char *cmd = argv[1];
@@ -21,6 +21,8 @@ int main(int argc, const char **argv) {
     if (!strcmp(cmd, "cyclecheck")) return cyclecheck(argc - 2, argv + 2);
     if (!strcmp(cmd, "extractorfs")) return extractorfs(argc - 2, argv + 2);
     if (!strcmp(cmd, "translatenucs")) return translatenucs(argc - 2, argv + 2);
+    if (!strcmp(cmd, "assembleiteration")) return assembleiteration(argc - 2, argv + 2);
+    if (!strcmp(cmd, "dbdiff")) return dbdiff(argc - 2, argv + 2);
     fprintf(stderr, "%s: not one of the GPU hot-path commands\n", cmd);
     return EXIT_FAILURE;
 }

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <omp.h>
 #include <set>
 #include <string>
 #include <vector>
@@ -107,10 +108,16 @@ pg_context *gpu() {
     return ctx;
 }
 
+// --threads N (Parameters.cpp:2124): host threads of the text layer (index parse, entry parse, formatting, pwrite)
+void applyThreads(const Flags &f) {
+    auto it = f.kv.find("--threads");
+    if (it != f.kv.end() && atoi(it->second.c_str()) > 0) mmdb::setHostThreads(atoi(it->second.c_str()));
+}
+
 pg_seqdb *uploadSeqDb(const mmdb::Reader &r) {
     if (r.dbtype != mmdb::DBTYPE_AMINO_ACIDS && r.dbtype != mmdb::DBTYPE_NUCLEOTIDES) die("input is not a sequence database");
     pg_seqdb_view v;
-    v.data = r.data.data(); v.data_bytes = r.data.size();
+    v.data = r.data(); v.data_bytes = r.dataBytes();
     v.offsets = r.offsets.data(); v.lens = r.lens.data(); v.keys = r.keys.data(); v.n = r.size(); v.dbtype = r.dbtype;
     pg_seqdb *db = nullptr;
     if (pg_seqdb_upload(gpu(), &v, &db) != 0) die(pg_last_error());
@@ -143,26 +150,130 @@ const std::set<std::string> RS_FLAGS = {"--sub-mat", "--rescore-mode", "--wrappe
     "--min-seq-id", "--min-aln-len", "--seq-id-mode", "--add-self-matches", "--sort-results", "--db-load-mode", "--threads", "--compressed", "-v"};
 const std::set<std::string> EX_FLAGS = {"--min-seq-id", "--max-seq-len", "--keep-target", "--threads", "-v", "--rescore-mode", "--sub-mat", "--db-load-mode", "--compressed"};
 
+// Entries [0, n) cut into one contiguous range per host thread; fn(thread, lo, hi) fills a per-thread vector, the vectors
+// are concatenated in thread order (= key order).
+template <class T, class Fn>
+std::vector<T> parseParallel(size_t n, Fn fn) {
+    const int nT = mmdb::hostThreads();
+    std::vector<std::vector<T>> part((size_t) nT);
+#pragma omp parallel for num_threads(nT) schedule(static, 1)
+    for (int t = 0; t < nT; t++) fn(part[(size_t) t], n * (size_t) t / (size_t) nT, n * (size_t) (t + 1) / (size_t) nT);
+    std::vector<size_t> at((size_t) nT + 1, 0);
+    for (int t = 0; t < nT; t++) at[(size_t) t + 1] = at[(size_t) t] + part[(size_t) t].size();
+    std::vector<T> all(at[(size_t) nT]);
+#pragma omp parallel for num_threads(nT) schedule(static, 1)
+    for (int t = 0; t < nT; t++)
+        if (!part[(size_t) t].empty()) memcpy(all.data() + at[(size_t) t], part[(size_t) t].data(), sizeof(T) * part[(size_t) t].size());
+    return all;
+}
+
 // Matcher::parseAlignmentRecord over a whole alignment DB (Matcher.cpp:190-320), entries in key order
 std::vector<pg_aln> parseAlnDb(const mmdb::Reader &aln) {
-    std::vector<pg_aln> alns;
-    for (size_t i = 0; i < aln.size(); i++) {
-        const char *s = aln.entry(i);
-        while (*s) {
-            pg_aln a; a.query = aln.keys[i];
-            char *e;
-            a.target = (uint32_t) strtoul(s, &e, 10);
-            a.bits = (int32_t) strtol(e, &e, 10);
-            a.seq_id = (float) strtod(e, &e);
-            a.evalue = strtod(e, &e);
-            a.q_start = (int32_t) strtol(e, &e, 10); a.q_end = (int32_t) strtol(e, &e, 10); a.q_len = (int32_t) strtol(e, &e, 10);
-            a.db_start = (int32_t) strtol(e, &e, 10); a.db_end = (int32_t) strtol(e, &e, 10); a.db_len = (int32_t) strtol(e, &e, 10);
-            alns.push_back(a);
-            while (*e && *e != '\n') e++;
-            s = *e ? e + 1 : e;
+    return parseParallel<pg_aln>(aln.size(), [&](std::vector<pg_aln> &alns, size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            const char *s = aln.entry(i);
+            while (*s) {
+                pg_aln a; a.query = aln.keys[i];
+                char *e;
+                a.target = (uint32_t) strtoul(s, &e, 10);
+                a.bits = (int32_t) strtol(e, &e, 10);
+                a.seq_id = (float) strtod(e, &e);
+                a.evalue = strtod(e, &e);
+                a.q_start = (int32_t) strtol(e, &e, 10); a.q_end = (int32_t) strtol(e, &e, 10); a.q_len = (int32_t) strtol(e, &e, 10);
+                a.db_start = (int32_t) strtol(e, &e, 10); a.db_end = (int32_t) strtol(e, &e, 10); a.db_len = (int32_t) strtol(e, &e, 10);
+                alns.push_back(a);
+                while (*e && *e != '\n') e++;
+                s = *e ? e + 1 : e;
+            }
         }
+    });
+}
+
+// QueryMatcher::parsePrefilterHits (QueryMatcher.h:81-112) over a kmermatcher result; the first line of every entry
+// must be the self line "key\t0\t0"
+std::vector<pg_hit> parsePrefDb(const mmdb::Reader &pref) {
+    return parseParallel<pg_hit>(pref.size(), [&](std::vector<pg_hit> &hits, size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            const char *s = pref.entry(i);
+            bool first = true;
+            while (*s) {
+                char *e;
+                pg_hit h; h.rep = pref.keys[i];
+                h.target = (uint32_t) strtoul(s, &e, 10);
+                h.score = (int32_t) strtol(e, &e, 10);
+                h.diag = (int32_t) (short) strtol(e, &e, 10);
+                if (first) {
+                    if (h.target != h.rep || h.score != 0 || h.diag != 0) die("prefilter entry does not start with its self line (not a kmermatcher result)");
+                    first = false;
+                } else {
+                    hits.push_back(h);
+                }
+                while (*e && *e != '\n') e++;
+                s = *e ? e + 1 : e;
+            }
+            if (first) die("empty prefilter entry");
+        }
+    });
+}
+
+// first index of every key's run in an array ordered by key: start[i] .. start[i + 1] are the records of keys[i]
+template <class T, class KeyOf>
+std::vector<uint64_t> runStarts(const std::vector<uint32_t> &keys, const T *recs, uint64_t n, KeyOf keyOf) {
+    std::vector<uint64_t> start(keys.size() + 1);
+    const int nT = mmdb::hostThreads();
+#pragma omp parallel for num_threads(nT) schedule(static)
+    for (size_t i = 0; i < keys.size(); i++) {
+        uint64_t lo = 0, hi = n;
+        const uint32_t k = keys[i];
+        while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (keyOf(recs[mid]) < k) lo = mid + 1; else hi = mid; }
+        start[i] = lo;
     }
-    return alns;
+    start[keys.size()] = n;
+    return start;
+}
+
+// prefilter DB: every key gets "key\t0\t0\n" followed by its hit lines (kmermatcher.cpp:809-924, :705-724;
+// QueryMatcher::prefilterHitToBuffer, QueryMatcher.h:114-126).  Entries are written in key order.
+void writePrefDb(const std::string &path, bool nucl, const std::vector<uint32_t> &keys, const pg_hit *hits, uint64_t nHits) {
+    std::string err;
+    mmdb::Writer w;
+    if (!w.open(path, nucl ? mmdb::DBTYPE_PREFILTER_REV_RES : mmdb::DBTYPE_PREFILTER_RES, err)) die(err);
+    const std::vector<uint64_t> start = runStarts(keys, hits, nHits, [](const pg_hit &h) { return h.rep; });
+    w.writeAll(keys.size(), [&](size_t i) { return keys[i]; }, [&](size_t i, std::string &buf) {
+        char line[64];
+        const uint32_t key = keys[i];
+        char *b = putU(line, key); memcpy(b, "\t0\t0\n", 5); buf.append(line, (size_t) (b + 5 - line));
+        for (uint64_t h = start[i]; h < start[i + 1] && hits[h].rep == key; h++) {
+            b = putU(line, hits[h].target); *b++ = '\t';
+            b = putI(b, hits[h].score); *b++ = '\t';
+            b = putI(b, (short) hits[h].diag); *b++ = '\n';
+            buf.append(line, (size_t) (b - line));
+        }
+    });
+    if (!w.close()) die("write error");
+}
+
+// alignment DB: Matcher::resultToBuffer (Matcher.cpp:323-370), 10 columns per line
+void writeAlnDb(const std::string &path, const std::vector<uint32_t> &keys, const pg_aln *alns, uint64_t nAlns) {
+    std::string err;
+    mmdb::Writer w;
+    if (!w.open(path, mmdb::DBTYPE_ALIGNMENT_RES, err)) die(err);
+    const std::vector<uint64_t> start = runStarts(keys, alns, nAlns, [](const pg_aln &a) { return a.query; });
+    w.writeAll(keys.size(), [&](size_t i) { return keys[i]; }, [&](size_t i, std::string &buf) {
+        char line[256];
+        const uint32_t key = keys[i];
+        for (uint64_t a = start[i]; a < start[i + 1] && alns[a].query == key; a++) {
+            const pg_aln &r = alns[a];
+            char *b = putU(line, r.target); *b++ = '\t';
+            b = putI(b, r.bits); *b++ = '\t';
+            b = putSeqId(b, r.seq_id); *b++ = '\t';
+            b += sprintf(b, "%.3E", r.evalue); *b++ = '\t';
+            b = putI(b, r.q_start); *b++ = '\t'; b = putI(b, r.q_end); *b++ = '\t'; b = putI(b, r.q_len); *b++ = '\t';
+            b = putI(b, r.db_start); *b++ = '\t'; b = putI(b, r.db_end); *b++ = '\t'; b = putI(b, r.db_len); *b++ = '\n';
+            buf.append(line, (size_t) (b - line));
+        }
+    });
+    if (!w.close()) die("write error");
 }
 
 void writeSeqDb(pg_seqdb *out, const std::string &path, int dbtype) {
@@ -171,7 +282,7 @@ void writeSeqDb(pg_seqdb *out, const std::string &path, int dbtype) {
     mmdb::Writer w;
     std::string err;
     if (!w.open(path, dbtype, err)) die(err);
-    for (uint64_t i = 0; i < n; i++) w.write(keys[i], data + offs[i], lens[i] - 1);
+    w.writeAll(n, [&](size_t i) { return keys[i]; }, [&](size_t i, std::string &buf) { buf.append(data + offs[i], lens[i] - 1); });
     if (!w.close()) die("write error");
     pg_free_host(data); pg_free_host(offs); pg_free_host(lens); pg_free_host(keys);
 }
@@ -196,9 +307,79 @@ unsigned frameMask(const std::string &s) {      // Orf::getFrames (Orf.h:17-35)
 }
 const std::set<std::string> CC_FLAGS = {"--max-seq-len", "--chop-cycle", "--threads", "-v", "--compressed"};
 
+void checkKmFlags(const Flags &f) {
+    requireValue(f, "--mask", "0", "tantan masking is not on the assemble path");
+    requireValue(f, "--mask-lower-case", "0", "not on the assemble path");
+    requireValue(f, "--spaced-kmer-mode", "0", "spaced k-mers are not on the assemble path");
+    requireValue(f, "--adjust-kmer-len", "0", "Markov k-mer length adjustment is not on the assemble path");
+    requireValue(f, "--compressed", "0", "uncompressed DBs only");
+    checkSubMat(f);
+}
+pg_km_params kmParams(const Flags &f, bool nucl) {
+    pg_km_params p;
+    p.kmer_size = geti(f, "-k", nucl ? 22 : 14);
+    p.alph_size = atoi(multi(get(f, "--alph-size", nucl ? "5" : "13"), nucl).c_str());
+    p.kmers_per_seq = geti(f, "--kmer-per-seq", 60);
+    p.kmers_per_seq_scale = (float) strtod(multi(get(f, "--kmer-per-seq-scale", nucl ? "0.1" : "0.0"), nucl).c_str(), nullptr);
+    p.hash_shift = geti(f, "--hash-shift", 67);
+    p.include_only_extendable = geti(f, "--include-only-extendable", 0);
+    p.ignore_multi_kmer = geti(f, "--ignore-multi-kmer", 1);
+    p.cov_mode = geti(f, "--cov-mode", 0);
+    p.cov_thr = (float) getd(f, "-c", 0.0);
+    p.hash_start = 0; p.hash_end = 65535;
+    return p;
+}
+// --split-memory-limit (Parameters.cpp, ByteParser: plain bytes or K / M / G / T suffix; 0 = all of the device memory)
+uint64_t splitMemoryLimit(const Flags &f) {
+    const std::string v = get(f, "--split-memory-limit", "0");
+    char *e = nullptr;
+    const double x = strtod(v.c_str(), &e);
+    if (e == v.c_str() || x < 0) die("cannot parse --split-memory-limit " + v);
+    double mul = 1.0;
+    switch (*e) {
+        case 'k': case 'K': mul = 1024.0; break;
+        case 'm': case 'M': mul = 1024.0 * 1024.0; break;
+        case 'g': case 'G': mul = 1024.0 * 1024.0 * 1024.0; break;
+        case 't': case 'T': mul = 1024.0 * 1024.0 * 1024.0 * 1024.0; break;
+        case 'b': case 'B': case '\0': break;
+        default: die("cannot parse --split-memory-limit " + v);
+    }
+    return (uint64_t) (x * mul);
+}
+void checkRsFlags(const Flags &f) {
+    requireValue(f, "--rescore-mode", "3", "the assemble workflows use END_TO_END only");
+    requireValue(f, "--wrapped-scoring", "0", "not on the assemble path");
+    requireValue(f, "--filter-hits", "0", "not on the assemble path");
+    requireValue(f, "-a", "0", "backtraces are not produced by ungapped rescoring on the assemble path");
+    requireValue(f, "--sort-results", "0", "the assemble workflows keep prefilter order");
+    requireValue(f, "--add-self-matches", "0", "query DB == target DB already keeps the self match");
+    requireValue(f, "--compressed", "0", "uncompressed DBs only");
+    checkSubMat(f);
+}
+pg_rs_params rsParams(const Flags &f) {
+    pg_rs_params p;
+    p.rescore_mode = 3;
+    p.seq_id_thr = (float) getd(f, "--min-seq-id", 0.0);
+    p.eval_thr = getd(f, "-e", 0.001);
+    p.cov_mode = geti(f, "--cov-mode", 0);
+    p.cov_thr = (float) getd(f, "-c", 0.0);
+    p.aln_len_thr = geti(f, "--min-aln-len", 0);
+    p.seq_id_mode = geti(f, "--seq-id-mode", 0);
+    return p;
+}
+pg_ex_params exParams(const Flags &f, bool nuclCommand) {
+    pg_ex_params p;
+    p.seq_id_thr = (float) getd(f, "--min-seq-id", nuclCommand ? 0.99 : 0.9);
+    p.max_seq_len = geti(f, "--max-seq-len", nuclCommand ? 200000 : 65535);
+    p.keep_target = geti(f, "--keep-target", 1);
+    p.rescore_mode = geti(f, "--rescore-mode", 3);
+    return p;
+}
+
 int extendCommand(int argc, const char **argv, bool nuclCommand) {
     Timer timer;
     const Flags f = parseFlags(argc, argv, 3, EX_FLAGS);
+    applyThreads(f);
     requireValue(f, "--compressed", "0", "uncompressed DBs only");
     checkSubMat(f);
     std::string err;
@@ -206,11 +387,7 @@ int extendCommand(int argc, const char **argv, bool nuclCommand) {
     if (!seq.open(f.positional[0], err) || !aln.open(f.positional[1], err)) die(err);
     const bool nucl = seq.dbtype == mmdb::DBTYPE_NUCLEOTIDES;
     (void) nuclCommand;   // like the reference, the comparator follows the command, the letters follow the DB type
-    pg_ex_params p;
-    p.seq_id_thr = (float) getd(f, "--min-seq-id", nuclCommand ? 0.99 : 0.9);
-    p.max_seq_len = geti(f, "--max-seq-len", nuclCommand ? 200000 : 65535);
-    p.keep_target = geti(f, "--keep-target", 1);
-    p.rescore_mode = geti(f, "--rescore-mode", 3);
+    const pg_ex_params p = exParams(f, nuclCommand);
     if (nuclCommand != nucl) die("sequence DB type does not match the command (assembleresults = amino acids, nuclassembleresults = nucleotides)");
     const std::vector<pg_aln> alns = parseAlnDb(aln);
     pg_seqdb *db = uploadSeqDb(seq), *out = nullptr;
@@ -227,52 +404,18 @@ int extendCommand(int argc, const char **argv, bool nuclCommand) {
 int kmermatcher(int argc, const char **argv) {
     Timer timer;
     const Flags f = parseFlags(argc, argv, 2, KM_FLAGS);
-    requireValue(f, "--mask", "0", "tantan masking is not on the assemble path");
-    requireValue(f, "--mask-lower-case", "0", "not on the assemble path");
-    requireValue(f, "--spaced-kmer-mode", "0", "spaced k-mers are not on the assemble path");
-    requireValue(f, "--adjust-kmer-len", "0", "Markov k-mer length adjustment is not on the assemble path");
-    requireValue(f, "--compressed", "0", "uncompressed DBs only");
-    checkSubMat(f);
+    applyThreads(f);
+    checkKmFlags(f);
     std::string err;
     mmdb::Reader seq;
     if (!seq.open(f.positional[0], err)) die(err);
     const bool nucl = seq.dbtype == mmdb::DBTYPE_NUCLEOTIDES;
-    pg_km_params p;
-    p.kmer_size = geti(f, "-k", nucl ? 22 : 14);
-    p.alph_size = atoi(multi(get(f, "--alph-size", nucl ? "5" : "13"), nucl).c_str());
-    p.kmers_per_seq = geti(f, "--kmer-per-seq", 60);
-    p.kmers_per_seq_scale = (float) strtod(multi(get(f, "--kmer-per-seq-scale", nucl ? "0.1" : "0.0"), nucl).c_str(), nullptr);
-    p.hash_shift = geti(f, "--hash-shift", 67);
-    p.include_only_extendable = geti(f, "--include-only-extendable", 0);
-    p.ignore_multi_kmer = geti(f, "--ignore-multi-kmer", 1);
-    p.cov_mode = geti(f, "--cov-mode", 0);
-    p.cov_thr = (float) getd(f, "-c", 0.0);
-    p.hash_start = 0; p.hash_end = 65535;
+    const pg_km_params p = kmParams(f, nucl);
+    if (pg_set_split_memory_limit(gpu(), splitMemoryLimit(f)) != 0) die(pg_last_error());
     pg_seqdb *db = uploadSeqDb(seq);
     pg_hit *hits = nullptr; uint64_t nHits = 0;
     if (pg_kmermatch(gpu(), db, &p, &hits, &nHits) != 0) die(pg_last_error());
-    // prefilter DB: every key gets "key\t0\t0\n" followed by its hit lines (kmermatcher.cpp:809-924, :705-724;
-    // QueryMatcher::prefilterHitToBuffer).  Entries are written in key order.
-    mmdb::Writer w;
-    if (!w.open(f.positional[1], nucl ? mmdb::DBTYPE_PREFILTER_REV_RES : mmdb::DBTYPE_PREFILTER_RES, err)) die(err);
-    std::string buf;
-    uint64_t h = 0;
-    char line[64];
-    for (size_t i = 0; i < seq.size(); i++) {
-        const uint32_t key = seq.keys[i];
-        buf.clear();
-        char *b = putU(line, key); memcpy(b, "\t0\t0\n", 5); buf.append(line, (size_t) (b + 5 - line));
-        while (h < nHits && hits[h].rep < key) h++;
-        while (h < nHits && hits[h].rep == key) {
-            b = putU(line, hits[h].target); *b++ = '\t';
-            b = putI(b, hits[h].score); *b++ = '\t';
-            b = putI(b, (short) hits[h].diag); *b++ = '\n';
-            buf.append(line, (size_t) (b - line));
-            h++;
-        }
-        w.write(key, buf.data(), buf.size());
-    }
-    if (!w.close()) die("write error");
+    writePrefDb(f.positional[1], nucl, seq.keys, hits, nHits);
     pg_free_host(hits);
     pg_seqdb_free(gpu(), db);
     timer.report();
@@ -282,14 +425,8 @@ int kmermatcher(int argc, const char **argv) {
 int rescorediagonal(int argc, const char **argv) {
     Timer timer;
     const Flags f = parseFlags(argc, argv, 4, RS_FLAGS);
-    requireValue(f, "--rescore-mode", "3", "the assemble workflows use END_TO_END only");
-    requireValue(f, "--wrapped-scoring", "0", "not on the assemble path");
-    requireValue(f, "--filter-hits", "0", "not on the assemble path");
-    requireValue(f, "-a", "0", "backtraces are not produced by ungapped rescoring on the assemble path");
-    requireValue(f, "--sort-results", "0", "the assemble workflows keep prefilter order");
-    requireValue(f, "--add-self-matches", "0", "query DB == target DB already keeps the self match");
-    requireValue(f, "--compressed", "0", "uncompressed DBs only");
-    checkSubMat(f);
+    applyThreads(f);
+    checkRsFlags(f);
     if (f.positional[0] != f.positional[1]) die("rescorediagonal on the GPU path requires query DB == target DB (as in assemble.sh / nuclassemble.sh)");
     std::string err;
     mmdb::Reader seq, pref;
@@ -298,63 +435,12 @@ int rescorediagonal(int argc, const char **argv) {
     if (pref.dbtype != (nucl ? mmdb::DBTYPE_PREFILTER_REV_RES : mmdb::DBTYPE_PREFILTER_RES)) die("prefilter DB type does not match the sequence DB");
     if (pref.size() != seq.size() || !std::equal(pref.keys.begin(), pref.keys.end(), seq.keys.begin()))
         die("prefilter DB must hold one entry per sequence (kmermatcher output)");
-    pg_rs_params p;
-    p.rescore_mode = 3;
-    p.seq_id_thr = (float) getd(f, "--min-seq-id", 0.0);
-    p.eval_thr = getd(f, "-e", 0.001);
-    p.cov_mode = geti(f, "--cov-mode", 0);
-    p.cov_thr = (float) getd(f, "-c", 0.0);
-    p.aln_len_thr = geti(f, "--min-aln-len", 0);
-    p.seq_id_mode = geti(f, "--seq-id-mode", 0);
-    // QueryMatcher::parsePrefilterHits (QueryMatcher.h:81-112); the first line must be the self line
-    std::vector<pg_hit> hits;
-    for (size_t i = 0; i < pref.size(); i++) {
-        const char *s = pref.entry(i);
-        bool first = true;
-        while (*s) {
-            char *e;
-            pg_hit h; h.rep = pref.keys[i];
-            h.target = (uint32_t) strtoul(s, &e, 10);
-            h.score = (int32_t) strtol(e, &e, 10);
-            h.diag = (int32_t) (short) strtol(e, &e, 10);
-            if (first) {
-                if (h.target != h.rep || h.score != 0 || h.diag != 0) die("prefilter entry does not start with its self line (not a kmermatcher result)");
-                first = false;
-            } else {
-                hits.push_back(h);
-            }
-            while (*e && *e != '\n') e++;
-            s = *e ? e + 1 : e;
-        }
-        if (first) die("empty prefilter entry");
-    }
+    const pg_rs_params p = rsParams(f);
+    const std::vector<pg_hit> hits = parsePrefDb(pref);
     pg_seqdb *db = uploadSeqDb(seq);
     pg_aln *alns = nullptr; uint64_t nAlns = 0;
     if (pg_rescore(gpu(), db, hits.data(), hits.size(), &p, &alns, &nAlns) != 0) die(pg_last_error());
-    // Matcher::resultToBuffer (Matcher.cpp:323-370): 10 columns
-    mmdb::Writer w;
-    if (!w.open(f.positional[3], mmdb::DBTYPE_ALIGNMENT_RES, err)) die(err);
-    std::string buf;
-    char line[256];
-    uint64_t a = 0;
-    for (size_t i = 0; i < seq.size(); i++) {
-        const uint32_t key = seq.keys[i];
-        buf.clear();
-        while (a < nAlns && alns[a].query < key) a++;
-        while (a < nAlns && alns[a].query == key) {
-            const pg_aln &r = alns[a];
-            char *b = putU(line, r.target); *b++ = '\t';
-            b = putI(b, r.bits); *b++ = '\t';
-            b = putSeqId(b, r.seq_id); *b++ = '\t';
-            b += sprintf(b, "%.3E", r.evalue); *b++ = '\t';
-            b = putI(b, r.q_start); *b++ = '\t'; b = putI(b, r.q_end); *b++ = '\t'; b = putI(b, r.q_len); *b++ = '\t';
-            b = putI(b, r.db_start); *b++ = '\t'; b = putI(b, r.db_end); *b++ = '\t'; b = putI(b, r.db_len); *b++ = '\n';
-            buf.append(line, (size_t) (b - line));
-            a++;
-        }
-        w.write(key, buf.data(), buf.size());
-    }
-    if (!w.close()) die("write error");
+    writeAlnDb(f.positional[3], seq.keys, alns, nAlns);
     pg_free_host(alns);
     pg_seqdb_free(gpu(), db);
     timer.report();
@@ -365,6 +451,7 @@ int rescorediagonal(int argc, const char **argv) {
 int findassemblystart(int argc, const char **argv) {
     Timer timer;
     const Flags f = parseFlags(argc, argv, 3, FS_FLAGS);
+    applyThreads(f);
     requireValue(f, "--compressed", "0", "uncompressed DBs only");
     std::string err;
     mmdb::Reader seq, aln;
@@ -384,6 +471,7 @@ int findassemblystart(int argc, const char **argv) {
 int extractorfs(int argc, const char **argv) {
     Timer timer;
     const Flags f = parseFlags(argc, argv, 2, ORF_FLAGS);
+    applyThreads(f);
     requireValue(f, "--compressed", "0", "uncompressed DBs only");
     requireValue(f, "--create-lookup", "0", "lookup files are not written by the GPU path");
     requireValue(f, "--id-offset", "0", "not used by the assemble workflow");
@@ -436,6 +524,7 @@ int extractorfs(int argc, const char **argv) {
 int translatenucs(int argc, const char **argv) {
     Timer timer;
     const Flags f = parseFlags(argc, argv, 2, TN_FLAGS);
+    applyThreads(f);
     requireValue(f, "--compressed", "0", "uncompressed DBs only");
     std::string err;
     mmdb::Reader seq;
@@ -480,6 +569,7 @@ int translatenucs(int argc, const char **argv) {
 int cyclecheck(int argc, const char **argv) {
     Timer timer;
     const Flags f = parseFlags(argc, argv, 2, CC_FLAGS);
+    applyThreads(f);
     requireValue(f, "--compressed", "0", "uncompressed DBs only");
     std::string err;
     mmdb::Reader seq;
@@ -512,3 +602,123 @@ int cyclecheck(int argc, const char **argv) {
 
 int assembleresults(int argc, const char **argv) { return extendCommand(argc, argv, false); }
 int nuclassembleresults(int argc, const char **argv) { return extendCommand(argc, argv, true); }
+
+// assembleiteration <i:sequenceDB> <o:prefDB> <o:alnDB> <o:sequenceDB> [flags of the three steps]
+// One whole iteration of data/assemble.sh:88-151 / data/nuclassemble.sh:100-128 in ONE process: the sequence DB is
+// uploaded once, kmermatcher -> rescorediagonal -> (nucl)assembleresults stay in HBM (pg_assemble_iteration), and
+// pref_N / aln_N / assembly_N are written as the three separate commands would write them.  Saves two process starts,
+// two CUDA initialisations, two uploads and the parse of pref_N and aln_N.
+int assembleiteration(int argc, const char **argv) {
+    Timer timer;
+    std::set<std::string> known = KM_FLAGS;
+    known.insert(RS_FLAGS.begin(), RS_FLAGS.end());
+    known.insert(EX_FLAGS.begin(), EX_FLAGS.end());
+    const Flags f = parseFlags(argc, argv, 4, known);
+    applyThreads(f);
+    checkKmFlags(f);
+    checkRsFlags(f);
+    std::string err;
+    mmdb::Reader seq;
+    if (!seq.open(f.positional[0], err)) die(err);
+    const bool nucl = seq.dbtype == mmdb::DBTYPE_NUCLEOTIDES;
+    const pg_km_params kp = kmParams(f, nucl);
+    pg_rs_params rp = rsParams(f);
+    const pg_ex_params ep = exParams(f, nucl);
+    if (pg_set_split_memory_limit(gpu(), splitMemoryLimit(f)) != 0) die(pg_last_error());
+    const auto tOpen = std::chrono::steady_clock::now();
+    pg_seqdb *db = uploadSeqDb(seq), *out = nullptr;
+    pg_hit *hits = nullptr; pg_aln *alns = nullptr; uint64_t nHits = 0, nAlns = 0;
+    if (pg_assemble_iteration(gpu(), db, &kp, &rp, &ep, &out, &hits, &nHits, &alns, &nAlns) != 0) die(pg_last_error());
+    const auto tGpu = std::chrono::steady_clock::now();
+    writePrefDb(f.positional[1], nucl, seq.keys, hits, nHits);
+    writeAlnDb(f.positional[2], seq.keys, alns, nAlns);
+    writeSeqDb(out, f.positional[3], seq.dbtype);
+    pg_free_host(hits); pg_free_host(alns);
+    pg_seqdb_free(gpu(), out); pg_seqdb_free(gpu(), db);
+    const auto tEnd = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return (long long) std::chrono::duration_cast<std::chrono::milliseconds>(b - a).count(); };
+    printf("open + index parse %lld ms, upload + GPU iteration + result download %lld ms, format + write %lld ms (%d host threads)\n",
+           ms(timer.t0, tOpen), ms(tOpen, tGpu), ms(tGpu, tEnd), mmdb::hostThreads());
+    timer.report();
+    return EXIT_SUCCESS;
+}
+
+// dbdiff <DB a> <DB b> [--mode exact|aln|pref]: logical comparison key -> entry bytes of two MMseqs DBs (physical
+// offsets and index order are not a contract).  Prints one JSON line; exit status 0 iff nothing
+// mismatches.  --mode aln: an entry whose lines differ only in the E-value column by at most one unit of its last
+// printed digit counts as `tolerated` (north-star tolerance 1e-6 on the value, "%.3E" on disk); --mode pref: entries
+// whose lines differ only in the sign of the score (nucleotide strand flag, DESIGN.md section 4 hazard 6) are `tolerated`.
+int dbdiff(int argc, const char **argv) {
+    const Flags f = parseFlags(argc, argv, 2, {"--mode", "--threads"});
+    applyThreads(f);
+    const std::string mode = get(f, "--mode", "exact");
+    if (mode != "exact" && mode != "aln" && mode != "pref") die("dbdiff --mode must be exact, aln or pref");
+    std::string err;
+    mmdb::Reader a, b;
+    if (!a.open(f.positional[0], err) || !b.open(f.positional[1], err)) die(err);
+    // keys of b looked up in a (both ascending)
+    unsigned long long missing = 0, mismatching = 0, tolerated = 0, toleratedLines = 0, same = 0;
+    long long firstBad = -1;
+    const size_t nb = b.size(), na = a.size();
+    const int nT = mmdb::hostThreads();
+    auto splitCols = [](const char *s, const char *e, const char **col, int maxCols) {
+        int c = 0;
+        const char *p = s;
+        while (c < maxCols) { col[c++] = p; while (p < e && *p != '\t') p++; if (p >= e) break; p++; }
+        col[c] = e + 1;
+        return c;
+    };
+#pragma omp parallel for num_threads(nT) schedule(static) reduction(+ : missing, mismatching, tolerated, toleratedLines, same)
+    for (size_t i = 0; i < nb; i++) {
+        const auto it = std::lower_bound(a.keys.begin(), a.keys.end(), b.keys[i]);
+        if (it == a.keys.end() || *it != b.keys[i]) { missing++; continue; }
+        const size_t j = (size_t) (it - a.keys.begin());
+        const char *ea = a.entry(j), *eb = b.entry(i);
+        const size_t la = a.lens[j], lb = b.lens[i];
+        if (la == lb && memcmp(ea, eb, la) == 0) { same++; continue; }
+        bool ok = mode != "exact";
+        unsigned long long lines = 0;
+        if (ok) {
+            const char *pa = ea, *pb = eb, *enda = ea + (la ? la - 1 : 0), *endb = eb + (lb ? lb - 1 : 0);
+            while (ok && pa < enda && pb < endb) {
+                const char *la_e = (const char *) memchr(pa, '\n', (size_t) (enda - pa)); if (!la_e) la_e = enda;
+                const char *lb_e = (const char *) memchr(pb, '\n', (size_t) (endb - pb)); if (!lb_e) lb_e = endb;
+                if ((la_e - pa) != (lb_e - pb) || memcmp(pa, pb, (size_t) (la_e - pa)) != 0) {
+                    const char *ca[12], *cb[12];
+                    const int nca = splitCols(pa, la_e, ca, 10), ncb = splitCols(pb, lb_e, cb, 10);
+                    if (nca != ncb) { ok = false; break; }
+                    for (int c = 0; c < nca && ok; c++) {
+                        const size_t wa = (size_t) (ca[c + 1] - ca[c] - 1), wb = (size_t) (cb[c + 1] - cb[c] - 1);
+                        if (wa == wb && memcmp(ca[c], cb[c], wa) == 0) continue;
+                        if (mode == "aln" && c == 3) {
+                            const double x = strtod(ca[c], nullptr), y = strtod(cb[c], nullptr);
+                            ok = std::fabs(x - y) <= 1.0005e-3 * std::fabs(y);
+                        } else if (mode == "pref" && c == 1) {
+                            ok = strtol(ca[c], nullptr, 10) == -strtol(cb[c], nullptr, 10);
+                        } else ok = false;
+                    }
+                    lines++;
+                }
+                pa = la_e < enda ? la_e + 1 : enda;
+                pb = lb_e < endb ? lb_e + 1 : endb;
+            }
+            if (ok && (pa < enda || pb < endb)) ok = false;      // different number of lines
+        }
+        if (ok) { tolerated++; toleratedLines += lines; }
+        else {
+            mismatching++;
+#pragma omp critical
+            if (firstBad < 0 || (long long) b.keys[i] < firstBad) firstBad = (long long) b.keys[i];
+        }
+    }
+    unsigned long long onlyA = 0;
+#pragma omp parallel for num_threads(nT) schedule(static) reduction(+ : onlyA)
+    for (size_t j = 0; j < na; j++) {
+        const auto it = std::lower_bound(b.keys.begin(), b.keys.end(), a.keys[j]);
+        if (it == b.keys.end() || *it != a.keys[j]) onlyA++;
+    }
+    printf("{\"entries_a\": %zu, \"entries_b\": %zu, \"identical\": %llu, \"tolerated\": %llu, \"tolerated_lines\": %llu, \"mismatching\": %llu, "
+           "\"only_in_b\": %llu, \"only_in_a\": %llu, \"dbtype_equal\": %s, \"first_mismatching_key\": %lld, \"mode\": \"%s\"}\n",
+           na, nb, same, tolerated, toleratedLines, mismatching, missing, onlyA, a.dbtype == b.dbtype ? "true" : "false", firstBad, mode.c_str());
+    return (mismatching == 0 && missing == 0 && onlyA == 0 && a.dbtype == b.dbtype) ? EXIT_SUCCESS : EXIT_FAILURE;
+}

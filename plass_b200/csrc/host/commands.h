@@ -10,3 +10,5 @@ int findassemblystart(int argc, const char **argv);      // replaces src/assembl
 int cyclecheck(int argc, const char **argv);             // replaces src/assembler/cyclecheck.cpp:31
 int extractorfs(int argc, const char **argv);            // replaces lib/mmseqs/src/util/extractorfs.cpp:20
 int translatenucs(int argc, const char **argv);          // replaces lib/mmseqs/src/util/translatenucs.cpp:14
+int assembleiteration(int argc, const char **argv);      // the three hot-path steps of one iteration fused in one process
+int dbdiff(int argc, const char **argv);                 // logical key -> entry comparison of two DBs (test / bench tool)

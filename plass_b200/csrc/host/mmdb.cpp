@@ -2,11 +2,29 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <fcntl.h>
 #include <numeric>
+#include <omp.h>
+#include <parallel/algorithm>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 namespace mmdb {
+
+static int g_threads = 0;
+
+int hostThreads() {
+    if (g_threads > 0) return g_threads;
+    int n = 0;
+    if (const char *e = getenv("MMSEQS_NUM_THREADS")) n = atoi(e);     // Parameters.cpp:2124
+    if (n <= 0) n = omp_get_num_procs();
+    g_threads = std::max(1, std::min(n, 256));
+    return g_threads;
+}
+void setHostThreads(int n) { if (n > 0) g_threads = std::min(n, 256); }
 
 static bool fileExists(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0; }
 
@@ -22,40 +40,104 @@ static bool slurp(const std::string &p, std::vector<char> &out, size_t at) {
     return got == (size_t) sz;
 }
 
+Reader::~Reader() {
+    if (mapped) munmap(mapped, mappedBytes);
+}
+
 bool Reader::open(const std::string &path, std::string &err) {
-    data.clear();
+    if (mapped) { munmap(mapped, mappedBytes); mapped = nullptr; }
+    owned.clear(); base = nullptr; bytes = 0;
     if (fileExists(path)) {
-        if (!slurp(path, data, 0)) { err = "cannot read " + path; return false; }
+        const int fd = ::open(path.c_str(), O_RDONLY);
+        struct stat st;
+        if (fd < 0 || fstat(fd, &st) != 0) { if (fd >= 0) ::close(fd); err = "cannot read " + path; return false; }
+        bytes = (size_t) st.st_size;
+        if (bytes) {
+            mapped = mmap(nullptr, bytes, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (mapped == MAP_FAILED) { mapped = nullptr; ::close(fd); err = "cannot map " + path; return false; }
+            mappedBytes = bytes;
+            madvise(mapped, bytes, MADV_WILLNEED);
+            base = (const char *) mapped;
+        }
+        ::close(fd);
     } else {
         int i = 0;
         while (fileExists(path + "." + std::to_string(i))) {
-            if (!slurp(path + "." + std::to_string(i), data, data.size())) { err = "cannot read split " + path; return false; }
+            if (!slurp(path + "." + std::to_string(i), owned, owned.size())) { err = "cannot read split " + path; return false; }
             i++;
         }
         if (i == 0) { err = "database " + path + " not found"; return false; }
+        base = owned.data(); bytes = owned.size();
     }
     std::vector<char> idx;
     if (!slurp(path + ".index", idx, 0)) { err = "cannot read " + path + ".index"; return false; }
-    std::vector<uint32_t> k; std::vector<uint64_t> o; std::vector<uint32_t> l;
-    const char *p = idx.data(), *e = idx.data() + idx.size();
-    while (p < e) {
-        uint64_t v[3] = {0, 0, 0};
-        for (int c = 0; c < 3; c++) {
-            while (p < e && (*p < '0' || *p > '9')) { if (*p == '\n') break; p++; }
-            while (p < e && *p >= '0' && *p <= '9') { v[c] = v[c] * 10 + (uint64_t) (*p - '0'); p++; }
+    // index parse by all host threads: the text is cut at line ends, every thread counts its lines, then parses them
+    // into their final positions
+    const int T = hostThreads();
+    const char *ib = idx.data();
+    const size_t isz = idx.size();
+    std::vector<size_t> cut((size_t) T + 1, isz), cnt((size_t) T + 1, 0);
+    cut[0] = 0;
+    for (int t = 1; t < T; t++) {
+        size_t p = std::max(cut[t - 1], isz * (size_t) t / (size_t) T);
+        while (p < isz && p > 0 && ib[p - 1] != '\n') p++;
+        cut[t] = p;
+    }
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+    for (int t = 0; t < T; t++) {
+        size_t c = 0;
+        const char *p = ib + cut[t], *e = ib + cut[t + 1];
+        while (p < e) {
+            const char *nl = (const char *) memchr(p, '\n', (size_t) (e - p));
+            const char *le = nl ? nl : e;
+            if (le > p) c++;                        // blank lines are skipped
+            p = nl ? nl + 1 : e;
         }
-        while (p < e && *p != '\n') p++;
-        if (p < e) p++;
-        k.push_back((uint32_t) v[0]); o.push_back(v[1]); l.push_back((uint32_t) v[2]);
+        cnt[(size_t) t + 1] = c;
     }
-    std::vector<size_t> order(k.size());
-    std::iota(order.begin(), order.end(), 0);
-    if (!std::is_sorted(k.begin(), k.end())) std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return k[a] < k[b]; });
-    keys.resize(k.size()); offsets.resize(k.size()); lens.resize(k.size());
-    for (size_t i = 0; i < order.size(); i++) {
-        keys[i] = k[order[i]]; offsets[i] = o[order[i]]; lens[i] = l[order[i]];
-        if (offsets[i] + lens[i] > data.size()) { err = "index of " + path + " points outside the data file"; return false; }
+    for (int t = 0; t < T; t++) cnt[(size_t) t + 1] += cnt[t];
+    const size_t n = cnt[T];
+    keys.assign(n, 0); offsets.assign(n, 0); lens.assign(n, 0);
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+    for (int t = 0; t < T; t++) {
+        size_t i = cnt[t];
+        const char *p = ib + cut[t], *e = ib + cut[t + 1];
+        while (p < e) {
+            if (*p == '\n') { p++; continue; }
+            uint64_t v[3] = {0, 0, 0};
+            for (int c = 0; c < 3; c++) {
+                while (p < e && (*p < '0' || *p > '9')) { if (*p == '\n') break; p++; }
+                while (p < e && *p >= '0' && *p <= '9') { v[c] = v[c] * 10 + (uint64_t) (*p - '0'); p++; }
+            }
+            while (p < e && *p != '\n') p++;
+            if (p < e) p++;
+            keys[i] = (uint32_t) v[0]; offsets[i] = v[1]; lens[i] = (uint32_t) v[2];
+            i++;
+        }
     }
+    bool sorted = true;
+#pragma omp parallel for num_threads(T) reduction(&& : sorted)
+    for (size_t i = 1; i < n; i++) sorted = sorted && keys[i - 1] <= keys[i];
+    if (!sorted) {
+        // kmermatcher's close(false, false) leaves pref_N.index unsorted (DBReader::open re-sorts by id, DBReader.cpp:238-253)
+        std::vector<uint64_t> order(n);
+#pragma omp parallel for num_threads(T)
+        for (size_t i = 0; i < n; i++) order[i] = ((uint64_t) keys[i] << 32) | (uint64_t) i;
+        // (key, original position) pairs are distinct, so the order equals a stable sort by key
+        __gnu_parallel::sort(order.begin(), order.end());
+        std::vector<uint32_t> k2(n), l2(n);
+        std::vector<uint64_t> o2(n);
+#pragma omp parallel for num_threads(T)
+        for (size_t i = 0; i < n; i++) {
+            const size_t j = (size_t) (order[i] & 0xFFFFFFFFull);
+            k2[i] = keys[j]; o2[i] = offsets[j]; l2[i] = lens[j];
+        }
+        keys.swap(k2); offsets.swap(o2); lens.swap(l2);
+    }
+    bool inside = true;
+#pragma omp parallel for num_threads(T) reduction(&& : inside)
+    for (size_t i = 0; i < n; i++) inside = inside && (offsets[i] + lens[i] <= bytes);
+    if (!inside) { err = "index of " + path + " points outside the data file"; return false; }
     FILE *ft = fopen((path + ".dbtype").c_str(), "rb");
     if (!ft) { err = "cannot read " + path + ".dbtype"; return false; }
     int32_t t = 0;
@@ -68,32 +150,141 @@ bool Reader::open(const std::string &path, std::string &err) {
 
 bool Writer::open(const std::string &p, int dbtype, std::string &err) {
     path = p;
-    fd = fopen(p.c_str(), "wb");
-    fi = fopen((p + ".index").c_str(), "wb");
-    if (!fd || !fi) { err = "cannot open " + p + " for writing"; return false; }
-    setvbuf(fd, nullptr, _IOFBF, 1 << 22);
-    setvbuf(fi, nullptr, _IOFBF, 1 << 22);
+    fd = ::open(p.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    fi = ::open((p + ".index").c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0 || fi < 0) { err = "cannot open " + p + " for writing"; return false; }
     FILE *ft = fopen((p + ".dbtype").c_str(), "wb");
     if (!ft) { err = "cannot write dbtype"; return false; }
     const int32_t t = dbtype;
     fwrite(&t, 4, 1, ft);
     fclose(ft);
-    offset = 0;
+    offset = 0; indexOffset = 0; failed = false;
+    pendData.clear(); pendIndex.clear();
     return true;
 }
 
+static bool pwriteAll(int fd, const char *p, size_t n, uint64_t at) {
+    while (n) {
+        const ssize_t w = pwrite(fd, p, n, (off_t) at);
+        if (w <= 0) return false;
+        p += w; n -= (size_t) w; at += (uint64_t) w;
+    }
+    return true;
+}
+
+static inline char *putU64(char *b, unsigned long long v) {
+    char tmp[24]; int n = 0;
+    do { tmp[n++] = (char) ('0' + v % 10); v /= 10; } while (v);
+    while (n) *b++ = tmp[--n];
+    return b;
+}
+
+static inline void indexLine(std::string &out, uint32_t key, uint64_t off, uint64_t len) {
+    char line[72];
+    char *b = putU64(line, key); *b++ = '\t';
+    b = putU64(b, off); *b++ = '\t';
+    b = putU64(b, len); *b++ = '\n';
+    out.append(line, (size_t) (b - line));
+}
+
+static void flushPending(Writer &w) {
+    if (!w.pendData.empty()) {
+        if (!pwriteAll(w.fd, w.pendData.data(), w.pendData.size(), w.offset - w.pendData.size())) w.failed = true;
+        w.pendData.clear();
+    }
+    if (!w.pendIndex.empty()) {
+        if (!pwriteAll(w.fi, w.pendIndex.data(), w.pendIndex.size(), w.indexOffset)) w.failed = true;
+        w.indexOffset += w.pendIndex.size();
+        w.pendIndex.clear();
+    }
+}
+
 void Writer::write(uint32_t key, const char *bytes, size_t n) {
-    fwrite(bytes, 1, n, fd);
-    fputc('\0', fd);
-    fprintf(fi, "%u\t%llu\t%llu\n", key, (unsigned long long) offset, (unsigned long long) (n + 1));
+    pendData.append(bytes, n);
+    pendData.push_back('\0');
+    indexLine(pendIndex, key, offset, n + 1);
     offset += n + 1;
+    if (pendData.size() > (8u << 20)) flushPending(*this);
+}
+
+void Writer::writeAll(size_t n, const std::function<uint32_t(size_t)> &keyOf, const std::function<void(size_t, std::string &)> &format,
+                      const std::function<bool(size_t)> &skip) {
+    flushPending(*this);
+    if (n == 0) return;
+    const int T = hostThreads();
+    size_t chunk = n / ((size_t) T * 8) + 1;
+    chunk = std::max<size_t>(1024, std::min<size_t>(chunk, 65536));
+    const size_t wave = chunk * (size_t) T;
+    std::vector<std::string> dbuf((size_t) T), ibuf((size_t) T);
+    std::vector<std::vector<uint32_t>> elen((size_t) T);
+    std::vector<uint64_t> dBase((size_t) T + 1), iBase((size_t) T + 1);
+    bool bad = false;
+#pragma omp parallel num_threads(T)
+    {
+        for (size_t w0 = 0; w0 < n; w0 += wave) {
+#pragma omp for schedule(static, 1)
+            for (int c = 0; c < T; c++) {
+                std::string &d = dbuf[(size_t) c];
+                std::vector<uint32_t> &el = elen[(size_t) c];
+                d.clear(); el.clear();
+                const size_t lo = std::min(n, w0 + (size_t) c * chunk), hi = std::min(n, lo + chunk);
+                for (size_t i = lo; i < hi; i++) {
+                    if (skip && skip(i)) { el.push_back(0xFFFFFFFFu); continue; }
+                    const size_t before = d.size();
+                    format(i, d);
+                    d.push_back('\0');
+                    el.push_back((uint32_t) (d.size() - before));
+                }
+            }
+#pragma omp single
+            {
+                uint64_t o = offset;
+                for (int c = 0; c < T; c++) { dBase[(size_t) c] = o; o += dbuf[(size_t) c].size(); }
+                offset = o;
+            }
+#pragma omp for schedule(static, 1)
+            for (int c = 0; c < T; c++) {
+                const std::string &d = dbuf[(size_t) c];
+                if (!d.empty() && !pwriteAll(fd, d.data(), d.size(), dBase[(size_t) c])) {
+#pragma omp atomic write
+                    bad = true;
+                }
+                std::string &ix = ibuf[(size_t) c];
+                ix.clear();
+                const size_t lo = std::min(n, w0 + (size_t) c * chunk);
+                uint64_t o = dBase[(size_t) c];
+                const std::vector<uint32_t> &el = elen[(size_t) c];
+                for (size_t j = 0; j < el.size(); j++) {
+                    if (el[j] == 0xFFFFFFFFu) continue;
+                    indexLine(ix, keyOf(lo + j), o, el[j]);
+                    o += el[j];
+                }
+            }
+#pragma omp single
+            {
+                uint64_t o = indexOffset;
+                for (int c = 0; c < T; c++) { iBase[(size_t) c] = o; o += ibuf[(size_t) c].size(); }
+                indexOffset = o;
+            }
+#pragma omp for schedule(static, 1)
+            for (int c = 0; c < T; c++) {
+                const std::string &ix = ibuf[(size_t) c];
+                if (!ix.empty() && !pwriteAll(fi, ix.data(), ix.size(), iBase[(size_t) c])) {
+#pragma omp atomic write
+                    bad = true;
+                }
+            }
+        }
+    }
+    if (bad) failed = true;
 }
 
 bool Writer::close() {
-    bool ok = true;
-    if (fd) ok &= fclose(fd) == 0;
-    if (fi) ok &= fclose(fi) == 0;
-    fd = fi = nullptr;
+    flushPending(*this);
+    bool ok = !failed;
+    if (fd >= 0) ok &= ::close(fd) == 0;
+    if (fi >= 0) ok &= ::close(fi) == 0;
+    fd = fi = -1;
     return ok;
 }
 

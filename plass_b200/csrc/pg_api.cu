@@ -66,6 +66,34 @@ __global__ void seqdb_stats_kernel(const unsigned *__restrict__ lens, const unsi
     if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], sum); atomicMax(&out[1], mx); atomicMax(&out[2], mk); atomicAdd(&out[3], nd); if (na) atomicAdd(&out[4], na); }
 }
 
+// Host-supplied prefilter hits / alignments name sequences by key: every key must exist in the DB before a kernel uses
+// find_id()'s answer as an index (a prefilter DB of another sequence DB would otherwise read out of bounds).
+template <class T, class KA, class KB>
+__global__ void validate_keys_kernel(const T *__restrict__ items, unsigned long long n, const unsigned *__restrict__ keys, unsigned nKeys,
+                                     KA keyA, KB keyB, unsigned *__restrict__ bad) {
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
+        const T it = items[i];
+        if (find_id(keys, nKeys, keyA(it)) == 0xFFFFFFFFu || find_id(keys, nKeys, keyB(it)) == 0xFFFFFFFFu) atomicAdd(bad, 1u);
+    }
+}
+struct HitRep { __device__ unsigned operator()(const pg_hit &h) const { return h.rep; } };
+struct HitTarget { __device__ unsigned operator()(const pg_hit &h) const { return h.target; } };
+struct AlnQuery { __device__ unsigned operator()(const pg_aln &a) const { return a.query; } };
+struct AlnTarget { __device__ unsigned operator()(const pg_aln &a) const { return a.target; } };
+
+template <class T, class KA, class KB>
+static int validate_keys(Context *ctx, const pg_seqdb *db, const T *d_items, uint64_t n, KA ka, KB kb, const char *what) {
+    if (n == 0) return 0;
+    PG_TRY(ctx->small.reserve(4096));
+    unsigned *d_bad = (unsigned *) (ctx->small.as<unsigned long long>() + 48);
+    PG_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned), ctx->stream));
+    validate_keys_kernel<<<NUM_SMS * 8, 256, 0, ctx->stream>>>(d_items, n, db->keys, (unsigned) db->n, ka, kb, d_bad);
+    unsigned bad = 0;
+    PG_TRY(read_back(ctx, &bad, d_bad, sizeof(bad)));
+    PG_CHECK(bad == 0, std::string(what) + ": " + std::to_string(bad) + " records name a key that is not in the sequence DB");
+    return 0;
+}
+
 int seqdb_finalize(Context *ctx, pg_seqdb *db) {
     PG_TRY(ctx->small.reserve(4096));
     unsigned long long *d = ctx->small.as<unsigned long long>() + 16;
@@ -78,6 +106,7 @@ int seqdb_finalize(Context *ctx, pg_seqdb *db) {
     db->max_key = (unsigned) h[2];
     db->dense_keys = (h[3] == 0);
     PG_CHECK(h[4] == 0, "sequence DB: keys must be strictly ascending (index order of a sequence DB)");
+    PG_CHECK(db->max_key < 0xFFFFFFF0u, "sequence DB: keys >= 2^32 - 16 are reserved");
     return 0;
 }
 
@@ -272,7 +301,7 @@ void pg_destroy(pg_context *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->small, &ctx->lists, &ctx->recA, &ctx->recB, &ctx->radixWs, &ctx->scratch, &ctx->blockCounts, &ctx->hits,
-                      &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta, &ctx->exLists, &ctx->ntTab, &ctx->buckets, &ctx->buckets2, &ctx->wideTabs, &ctx->nextWork, &ctx->orfInfo};
+                      &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta, &ctx->exLists, &ctx->ntTab, &ctx->buckets, &ctx->buckets2, &ctx->wideTabs, &ctx->nextWork, &ctx->orfInfo, &ctx->pairAcc};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
     cudaStreamSynchronize(ctx->copyStream);
@@ -415,6 +444,7 @@ int pg_rescore(pg_context *ctx, const pg_seqdb *db, const pg_hit *hits, uint64_t
     if (n_hits) PG_CUDA(cudaMemcpyAsync(ctx->hits.p, hits, sizeof(pg_hit) * n_hits, cudaMemcpyHostToDevice, ctx->stream));
     for (uint64_t i = 1; i < n_hits; i++)
         PG_CHECK(hits[i - 1].rep <= hits[i].rep, "pg_rescore: hits must be ordered by rep (prefilter DB order)");
+    PG_TRY(validate_keys(ctx, db, ctx->hits.as<pg_hit>(), n_hits, HitRep(), HitTarget(), "pg_rescore"));
     pg_aln *d = nullptr; uint64_t n = 0;
     PG_TRY(rs_run(ctx, db, ctx->hits.as<pg_hit>(), n_hits, p, &d, &n));
     PG_TRY(to_host(ctx->stream, d, n, alns));
@@ -432,6 +462,7 @@ int pg_extend(pg_context *ctx, const pg_seqdb *db, const pg_aln *alns, uint64_t 
     if (n_alns) PG_CUDA(cudaMemcpyAsync(ctx->alns.p, alns, sizeof(pg_aln) * n_alns, cudaMemcpyHostToDevice, ctx->stream));
     for (uint64_t i = 1; i < n_alns; i++)
         PG_CHECK(alns[i - 1].query <= alns[i].query, "pg_extend: alignments must be ordered by query");
+    PG_TRY(validate_keys(ctx, db, ctx->alns.as<pg_aln>(), n_alns, AlnQuery(), AlnTarget(), "pg_extend"));
     unsigned char *dExt = nullptr;
     PG_TRY(ex_run(ctx, db, ctx->alns.as<pg_aln>(), n_alns, p, out_db, &dExt));
     if (extended) PG_TRY(to_host(ctx->stream, dExt, (*out_db)->n, extended));
@@ -505,6 +536,7 @@ int pg_findassemblystart(pg_context *ctx, const pg_seqdb *db, const pg_aln *alns
     if (n_alns) PG_CUDA(cudaMemcpyAsync(ctx->alns.p, alns, sizeof(pg_aln) * n_alns, cudaMemcpyHostToDevice, ctx->stream));
     for (uint64_t i = 1; i < n_alns; i++)
         PG_CHECK(alns[i - 1].query <= alns[i].query, "pg_findassemblystart: alignments must be ordered by query");
+    PG_TRY(validate_keys(ctx, db, ctx->alns.as<pg_aln>(), n_alns, AlnQuery(), AlnTarget(), "pg_findassemblystart"));
     int *dStop = nullptr;
     PG_TRY(fs_run(ctx, db, ctx->alns.as<pg_aln>(), n_alns, out_db, &dStop));
     if (add_stop) PG_TRY(to_host(ctx->stream, dStop, db->n, add_stop));
@@ -693,6 +725,15 @@ int pg_shard_finish(pg_context *ctx, const pg_seqdb *db, const void *device_pair
     PG_CUDA(cudaStreamSynchronize(ctx->copyStream));
     return 0;
 }
+
+int pg_set_split_memory_limit(pg_context *ctx, uint64_t bytes) {
+    PG_CHECK(ctx, "pg_set_split_memory_limit: null argument");
+    ctx->memLimit = bytes;
+    return 0;
+}
+
+// tests: run the kmermatcher stage in exactly n hash-range splits (0 = decide from the memory limit)
+int pg_debug_force_splits(pg_context *ctx, unsigned n) { if (!ctx) return 1; ctx->forceSplits = n; return 0; }
 
 // tests: force the full-sort group path (1) or allow the bucketed hash join (0)
 int pg_debug_force_full_sort(pg_context *ctx, int on) { if (!ctx) return 1; ctx->forceFullSort = on != 0; return 0; }

@@ -33,6 +33,12 @@ struct pg_context {
     unsigned bucketTarget = 512;  // average records per bucket of the partial-key partition (<= 700: small hash-join instance first)
     int digitBits = 8;            // radix digit width of the two fast-path sorts (8: 256 bins; 9 / 10: wide-digit kernel)
     bool forceFullSort = false;   // tests: take the 8-pass sort + group_kernel path instead of the bucketed hash join
+    // --split-memory-limit (pg_set_split_memory_limit): bound on the two k-mer record buffers; splitDiv = number of equal
+    // hash-range splits the running kmermatcher call uses (1 = no split), pairAcc collects the splits' pair records
+    uint64_t memLimit = 0;
+    unsigned splitDiv = 1;
+    unsigned forceSplits = 0;     // tests: use exactly this many splits
+    pg::DevBuf pairAcc;
     unsigned ntTabN = 0;
     bool pairsInA = false;
     bool tExtract = false, tGroup = false, tReduce = false, rsRan = false, exRan = false;   // which stages recorded their events in this call

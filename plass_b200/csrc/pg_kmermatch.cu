@@ -715,6 +715,9 @@ __device__ __forceinline__ void acc_add(GroupAcc &a, unsigned long long key, uns
 
 // Util::canBeCovered (Util.cpp:533-551)
 __device__ __forceinline__ bool can_be_covered(float covThr, int covMode, float q, float t) {
+    // -c 0 (the assemble workflows): every ratio of two positive lengths passes, no division needed.  Modes 3 / 4 also
+    // bound the ratio from above and zero lengths give NaN / inf ratios: those keep the reference's arithmetic.
+    if (covThr <= 0.0f && q > 0.0f && t > 0.0f && covMode != 3 && covMode != 4) return true;
     switch (covMode) {
         case 0: return (q / t >= covThr) && (t / q >= covThr);
         case 1: return (t / q) >= covThr;
@@ -892,8 +895,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) group_kernel(const Rec *__restr
                     diagonal = queryPos - targetPos;
                 }
                 const bool canBeExtended = diagonal < 0 || (diagonal > (queryLen - tLen));
-                const bool covered = can_be_covered(c.covThr, c.covMode, (float) queryLen, (float) tLen);
-                keep = (c.includeOnlyExtendable == 0 && covered) || (canBeExtended && c.includeOnlyExtendable != 0);
+                keep = c.includeOnlyExtendable == 0 ? can_be_covered(c.covThr, c.covMode, (float) queryLen, (float) tLen) : canBeExtended;
                 if (keep) {
                     outRec[it].w0 = ((unsigned long long) repId << 32) | tId;
                     if constexpr (WIDE) {
@@ -989,8 +991,7 @@ __device__ __forceinline__ bool make_pair_record(const Rec &r, unsigned repId, i
         diagonal = queryPos - targetPos;
     }
     const bool canBeExtended = diagonal < 0 || (diagonal > (queryLen - tLen));
-    const bool covered = can_be_covered(c.covThr, c.covMode, (float) queryLen, (float) tLen);
-    const bool keep = (c.includeOnlyExtendable == 0 && covered) || (canBeExtended && c.includeOnlyExtendable != 0);
+    const bool keep = c.includeOnlyExtendable == 0 ? can_be_covered(c.covThr, c.covMode, (float) queryLen, (float) tLen) : canBeExtended;
     if (keep) {
         out.w0 = ((unsigned long long) repId << 32) | tId;
         const unsigned biased = (unsigned) (((int) (short) diagonal) + 32768) & 0xFFFFu;
@@ -1896,7 +1897,9 @@ int km_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const Km
         h_total = hb[0];
         memcpy(h_cls, hb + 8, sizeof(h_cls));
     }
-    const unsigned long long cap = h_total + 1;
+    // a hash-range split holds 1 / splitDiv of the records (XXH64 is uniform) + 12.5 % + slack; if a skewed input
+    // overflows that, the caller doubles the number of splits (rc 2)
+    const unsigned long long cap = ctx->splitDiv > 1 ? h_total / ctx->splitDiv + h_total / (8ull * ctx->splitDiv) + 65536ull : h_total + 1;
     PG_TRY(ctx->recA.reserve(sizeof(Rec) * cap));
     PG_TRY(ctx->recB.reserve(sizeof(Rec) * cap));
     Rec *out = ctx->recA.as<Rec>();
@@ -1918,6 +1921,7 @@ int km_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const Km
     unsigned long long h_out = 0;
     PG_TRY(read_back(ctx, &h_out, d_outCount, sizeof(h_out)));
     PG_CUDA(cudaGetLastError());
+    if (h_out > cap && ctx->splitDiv > 1) { *nRecords = h_out; return 2; }
     PG_CHECK(h_out <= cap, "kmermatcher: k-mer array overflow");
     *nRecords = h_out;
     (void) p;
@@ -2099,7 +2103,10 @@ int km_reduce(Context *ctx, const pg_seqdb *db, Rec *pairs, Rec *tmp, uint64_t n
     *nHits = 0; *d_hits = nullptr;
     if (nPairs == 0) return 0;
     const bool wide = km_is_wide(db);
-    if (!ctx->forceFullSort && !wide) {
+    // the segmented path keeps about ten arrays indexed by representative KEY: only for (nearly) dense key spaces; a DB
+    // with sparse keys (a subset that kept its ids) takes the full sort, which needs no per-key tables
+    const bool sparseKeys = (unsigned long long) db->max_key + 1ull > 4ull * db->n + 1024ull;
+    if (!ctx->forceFullSort && !wide && !sparseKeys) {
         bool ok = false;
         PG_TRY(km_reduce_segmented(ctx, db, &pairs, &tmp, nPairs, d_hits, nHits, &ok));
         if (ok) return 0;
@@ -2135,6 +2142,92 @@ int km_reduce(Context *ctx, const pg_seqdb *db, Rec *pairs, Rec *tmp, uint64_t n
     return 0;
 }
 
+static void record_empty_group_events(Context *ctx) {
+    cudaStream_t s = ctx->stream;
+    cudaEventRecord(ctx->ev[EV_SORT1_BEGIN], s); cudaEventRecord(ctx->ev[EV_SCATTER1_BEGIN], s); cudaEventRecord(ctx->ev[EV_SCATTER1_END], s);
+    cudaEventRecord(ctx->ev[EV_SORT1_END], s); cudaEventRecord(ctx->ev[EV_GROUP_END], s);
+}
+
+// kmermatcherInner's split decision (kmermatcher.cpp:608-624): how many equal hash ranges are needed so that the two
+// record buffers of one split fit the memory limit.  The estimate of the record count is computeKmerCount (:576-585).
+static int km_choose_splits(Context *ctx, const pg_seqdb *db, const pg_km_params *p, unsigned *splits) {
+    *splits = 1;
+    if (ctx->forceSplits) { *splits = ctx->forceSplits; return 0; }
+    cudaStream_t s = ctx->stream;
+    PG_TRY(ctx->small.reserve(4096));
+    unsigned long long *d_total = ctx->small.as<unsigned long long>() + 50;
+    PG_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), s));
+    kmer_count_kernel<<<NUM_SMS * 4, 256, 0, s>>>(db->lens, 0, (unsigned) db->n, p->kmer_size, p->kmers_per_seq, p->kmers_per_seq_scale, d_total);
+    ctx->launches++;
+    unsigned long long total = 0;
+    PG_TRY(read_back(ctx, &total, d_total, sizeof(total)));
+    const unsigned long long need = 2ull * sizeof(Rec) * (total + 1) + radix_workspace_bytes(total);
+    unsigned long long limit = ctx->memLimit;
+    if (limit == 0) {
+        size_t freeB = 0, totalB = 0;
+        PG_CUDA(cudaMemGetInfo(&freeB, &totalB));
+        // what the stage's own buffers already hold is reusable
+        limit = (unsigned long long) (0.9 * (double) (freeB + ctx->recA.cap + ctx->recB.cap + ctx->radixWs.cap));
+    }
+    if (need <= limit) return 0;
+    unsigned sp = 2;
+    while (sp < 65536u && 2ull * sizeof(Rec) * (total / sp + total / (8ull * sp) + 65536ull) + radix_workspace_bytes(total / sp + 65536ull) > limit) sp <<= 1;
+    PG_CHECK(2ull * sizeof(Rec) * (total / sp + total / (8ull * sp) + 65536ull) <= limit || sp < 65536u,
+             "kmermatcher: --split-memory-limit is too small for even one of 65536 hash-range splits");
+    *splits = sp;
+    return 0;
+}
+
+// kmermatcher in hash-range splits (setupKmerSplits, kmermatcher.cpp:736-778): every split extracts, partitions and
+// groups only the k-mers whose 16-bit hash lies in its range; the pair records of all splits are collected in
+// ctx->pairAcc.  Equal k-mers have equal hashes, so the union of the splits' groups is the unsplit run's set of groups.
+static int km_run_splits(Context *ctx, const pg_seqdb *db, const pg_km_params *p, KmConst &c, unsigned splits, uint64_t *nRecTotal, uint64_t *nPairsTotal) {
+    cudaStream_t s = ctx->stream;
+    for (;;) {
+        ctx->splitDiv = splits;
+        uint64_t recTotal = 0, pairTotal = 0;
+        bool overflow = false;
+        for (unsigned sp = 0; sp < splits && !overflow; sp++) {
+            // ranges over the reference's own 16-bit hash (hashStart / hashEnd inclusive), clipped to the caller's range
+            const unsigned lo = (unsigned) ((65536ull * sp) / splits), hi = (unsigned) ((65536ull * (sp + 1)) / splits) - 1u;
+            c.hashStart = std::max(lo, p->hash_start); c.hashEnd = std::min(hi, p->hash_end);
+            if (c.hashStart > c.hashEnd) continue;
+            uint64_t nRec = 0, nPairs = 0;
+            const int rc = km_extract(ctx, db, p, c, &nRec);
+            if (rc == 2) { overflow = true; break; }
+            if (rc) { ctx->splitDiv = 1; return rc; }
+            if (sp == 0) cudaEventRecord(ctx->ev[EV_EXTRACT_END], s);
+            const int rg = km_group(ctx, db, c, nRec, &nPairs);
+            if (rg) { ctx->splitDiv = 1; return rg; }
+            if (nRec == 0) record_empty_group_events(ctx);
+            if (nPairs) {
+                // grow-and-copy accumulation of the pair records
+                const size_t needBytes = sizeof(Rec) * (pairTotal + nPairs + 1);
+                if (needBytes > ctx->pairAcc.cap) {
+                    DevBuf bigger;
+                    if (bigger.reserve(needBytes + needBytes / 2)) { ctx->splitDiv = 1; return 1; }
+                    if (pairTotal) cudaMemcpyAsync(bigger.p, ctx->pairAcc.p, sizeof(Rec) * pairTotal, cudaMemcpyDeviceToDevice, s);
+                    cudaStreamSynchronize(s);
+                    ctx->pairAcc.release();
+                    ctx->pairAcc = bigger;
+                }
+                const Rec *src = ctx->pairsInA ? ctx->recA.as<Rec>() : ctx->recB.as<Rec>();
+                cudaMemcpyAsync(ctx->pairAcc.as<Rec>() + pairTotal, src, sizeof(Rec) * nPairs, cudaMemcpyDeviceToDevice, s);
+            }
+            recTotal += nRec; pairTotal += nPairs;
+        }
+        if (overflow) {
+            PG_CHECK(splits < 65536u, "kmermatcher: a single 16-bit hash value holds more k-mer records than the memory limit allows");
+            splits <<= 1;
+            continue;
+        }
+        ctx->splitDiv = 1;
+        *nRecTotal = recTotal; *nPairsTotal = pairTotal;
+        ctx->timings.splits = splits;
+        return 0;
+    }
+}
+
 // Whole kmermatcher on one GPU; hits stay on the device (ctx->hits).
 int km_run(Context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **d_hits, uint64_t *nHits) {
     KmConst c;
@@ -2143,6 +2236,25 @@ int km_run(Context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **d_h
     cudaEventRecord(ctx->ev[EV_KM_BEGIN], s);
     uint64_t nRec = 0, nPairs = 0;
     PG_TRY(km_prepare_wide(ctx, db, c));
+    unsigned splits = 1;
+    PG_TRY(km_choose_splits(ctx, db, p, &splits));
+    ctx->timings.splits = 1;
+    if (splits > 1) {
+        PG_TRY(km_run_splits(ctx, db, p, c, splits, &nRec, &nPairs));
+        // reduce all splits' pairs together: pairAcc is the input, recA the scratch of sort #2
+        ctx->recB.release();
+        PG_TRY(ctx->recA.reserve(sizeof(Rec) * (nPairs + 1)));
+        if (nPairs == 0) { cudaEventRecord(ctx->ev[EV_SORT2_END], s); cudaEventRecord(ctx->ev[EV_REDUCE_END], s); }
+        PG_TRY(km_reduce(ctx, db, ctx->pairAcc.as<Rec>(), ctx->recA.as<Rec>(), nPairs, d_hits, nHits));
+        PG_CUDA(cudaStreamSynchronize(s));
+        ctx->pairAcc.release();
+        ctx->timings.n_kmer_records = nRec;
+        ctx->timings.n_pair_records = nPairs;
+        ctx->timings.n_hits = *nHits;
+        ctx->timings.sort1_bytes = (uint64_t) nRec * sizeof(Rec) * 2;
+        ctx->tExtract = ctx->tGroup = ctx->tReduce = true;
+        return 0;
+    }
     PG_TRY(km_extract(ctx, db, p, c, &nRec));
     cudaEventRecord(ctx->ev[EV_EXTRACT_END], s);
     PG_TRY(km_group(ctx, db, c, nRec, &nPairs));
@@ -2248,12 +2360,6 @@ static int shard_pairs_ready(Context *ctx, const pg_seqdb *db, uint64_t nPairs, 
 void km_equal_key_bounds(unsigned max_key, int world, unsigned *bounds) {
     const unsigned long long per = ((unsigned long long) max_key + (unsigned long long) world) / (unsigned long long) world;
     for (int r = 0; r <= world; r++) bounds[r] = (r == world) ? 0xFFFFFFFFu : (unsigned) std::min<unsigned long long>(per * (unsigned long long) r, 0xFFFFFFFFull);
-}
-
-static void record_empty_group_events(Context *ctx) {
-    cudaStream_t s = ctx->stream;
-    cudaEventRecord(ctx->ev[EV_SORT1_BEGIN], s); cudaEventRecord(ctx->ev[EV_SCATTER1_BEGIN], s); cudaEventRecord(ctx->ev[EV_SCATTER1_END], s);
-    cudaEventRecord(ctx->ev[EV_SORT1_END], s); cudaEventRecord(ctx->ev[EV_GROUP_END], s);
 }
 
 int km_shard_pairs(Context *ctx, const pg_seqdb *db, const pg_km_params *p, int world, uint64_t *counts) {
