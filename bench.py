@@ -3,23 +3,28 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--reads R]
 
-Workload (BASELINE.json configs[1]): R = 5 M synthetic 150 bp protein-coding reads (seed 1, 20x coverage,
-0.5 % substitutions, 50 % reverse-complemented) -> six-frame amino-acid fragments; one `plass assemble`
-iteration with the workflow defaults (k = 14, 13-letter alphabet, --min-seq-id 0.9, -e 1e-5).
-A "step" is one pass of the hot path over that fragment DB.
+Workload (BASELINE.json configs[2] / [3], the configuration the north-star metric is quoted on): R = 50 M synthetic
+150 bp protein-coding reads (seed 1, 20x coverage, 0.5 % substitutions, 50 % reverse-complemented) -> the six-frame
+fragment DB `aa_6f_start_long` exactly as data/assemble.sh:41-77 builds it (extractorfs x 2 + translatenucs x 2 +
+concatdbs; built here by the repo's own six-frame GPU pipeline, pg_extractorfs) -> one `plass assemble` iteration with
+the workflow defaults (k = 14, 13-letter alphabet, --min-seq-id 0.9, -e 1e-5).  A "step" is one pass of the hot path
+over that fragment DB.  N > 1 (torchrun): STRONG scaling -- the same 50 M reads sharded over the N ranks.
 
-  value      whole-job reads/s with the fragment DB already resident in HBM (device-resident fused iteration)
-  e2e        the same iteration through the C ABI with HOST buffers: pinned H2D of the DB, D2H of the
-             prefilter hits, the alignments and the new sequence DB inside the timed region
-  roofline   dominant kernel = the radix scatter passes of sort #1; achieved = algorithmic bytes of the sort
-             (one read + one write of every 16-byte record) / summed scatter time
-  cpu_baseline  the UNMODIFIED reference binary (oracle/_ref/bin/plass: kmermatcher, rescorediagonal,
-             assembleresults sub-commands, all host threads) on a bounded sample of the same fragments
+  value         whole-job reads/s with the fragment DB already resident in HBM (device-resident fused iteration)
+  e2e           the same iteration through the C ABI with HOST buffers: pinned H2D of the DB, D2H of the prefilter hits,
+                the alignments and the new sequence DB inside the timed region
+  roofline      dominant kernel = the radix scatter passes of sort #1; achieved = algorithmic bytes of the sort
+                (one read + one write of every 16-byte record) / summed scatter time; traffic from the
+                round's ncu capture (profiles/roofline_capture.json)
+  cpu_baseline  the UNMODIFIED reference binary (oracle/_ref/bin/plass: kmermatcher, rescorediagonal, assembleresults
+                sub-commands, all host threads) on a bounded sample of the same workload
+  parity        the sample the reference just processed goes through the GPU drop-in commands (plass_b200_cli) and
+                pref / aln / assembly are compared key -> entry bytes with the reference's files; any mismatch fails
+                the run
+  dropin        wall-clock of the drop-in commands (process start to exit, DB files in and out) next to
+                the reference's on the same DB
 
---impl reference times only that reference arm (CPU) and prints it as the line's value.
-N > 1 (torchrun): weak scaling -- R reads per GPU; extraction is sliced by sequence, the k-mer records go to the
-rank owning the k-mer and the candidate pairs to the rank owning the representative (two NCCL all-to-alls through
-torch.distributed), see DESIGN.md §5.
+--impl reference times only the reference arm (CPU) on the same config and prints it as the line's value.
 """
 import argparse
 import json
@@ -36,9 +41,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from plass_b200 import api, mmseqsdb, synth  # noqa: E402
+from plass_b200 import mmseqsdb, synth  # noqa: E402
 
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "bin", "plass")
+CLI = os.path.join(ROOT, "plass_b200", "plass_b200_cli")
+METRIC = "reads/sec per assemble iteration (kmermatcher+rescorediagonal+assembleresults)"
 KM_FLAGS = "--sub-mat nucl:nucleotide.out,aa:blosum62.out --alph-size 13 --min-seq-id 0.9 --kmer-per-seq 60 " \
            "--spaced-kmer-mode 0 --kmer-per-seq-scale nucl:0.200,aa:0.000 --adjust-kmer-len 0 --mask 0 --mask-lower-case 0 " \
            "--cov-mode 0 -k 14 -c 0 --max-seq-len 65535 --hash-shift 67 --split-memory-limit 0 --include-only-extendable 0 " \
@@ -61,85 +68,162 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def workload_name(reads_per_gpu, per_gpu):
-    cfg = {5000000: " (BASELINE configs[1])", 50000000: " (BASELINE configs[2], one iteration)"}.get(reads_per_gpu, "")
-    return "%gM synthetic 150bp coding reads%s -> aa fragments, k=14, alph 13, --min-seq-id 0.9, 1 iteration%s" % (
-        reads_per_gpu / 1e6, " per GPU" if per_gpu else "", cfg)
+def workload_config(reads):
+    """The line's `config`: identical for both arms (it names the workload, not what a run found in it)."""
+    cfg = {5000000: " (BASELINE.json configs[1])", 50000000: " (BASELINE.json configs[2] / configs[3], one iteration)"}.get(reads, "")
+    return {"workload": "%gM synthetic 150bp coding reads -> six-frame fragment DB aa_6f_start_long (extractorfs x2 + translatenucs x2 + concatdbs), "
+                        "one plass assemble iteration: k=14, alph 13, --min-seq-id 0.9, -e 1e-5%s" % (reads / 1e6, cfg),
+            "reads": reads, "l2": "inputs_larger_than_l2 (GBs of k-mer records per step, 126 MB L2)"}
 
 
-def make_fragments(n_reads, seed):
-    cache = os.path.join(tempfile.gettempdir(), "plass_b200_frag_%d_%d.npz" % (n_reads, seed))
-    if os.path.exists(cache):
-        z = np.load(cache)
-        return mmseqsdb.DB(z["data"], z["keys"], z["offsets"], z["lens"], 0)
-    t = time.time()
-    reads = synth.make_reads_fast(n_reads, seed=seed)
-    db = synth.protein_fragments(reads, workers=min(16, os.cpu_count() or 1))
-    del reads
-    log("[bench] generated %d reads -> %d aa fragments (mean %.1f aa) in %.1f s" % (n_reads, db.n, float(db.lens.mean()) - 2, time.time() - t))
-    if n_reads <= 45000000:      # the cache only serves the other ranks of a multi-GPU run (up to 8 x 5 M reads) and repeated small samples
-        try:
-            np.savez(cache, data=db.data, keys=db.keys, offsets=db.offsets, lens=db.lens)
-        except OSError:
-            pass
-    return db
+# ---- workload ---------------------------------------------------------------------------------------------------
+def concat_dbs(a, b):
+    """concatdbs without --preserve-keys (data/assemble.sh:68-77): a's entries, then b's, keys renumbered."""
+    lens = np.concatenate([a.lens, b.lens])
+    offsets = np.zeros(len(lens), dtype=np.uint64)
+    if len(lens):
+        offsets[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+    return mmseqsdb.DB(np.concatenate([a.data, b.data]), np.arange(len(lens), dtype=np.uint32), offsets, lens, a.dbtype)
 
 
-def subsample(db, n_frag):
-    """First n_frag fragments as their own DB (keys renumbered 0..n-1)."""
-    n = min(n_frag, db.n)
-    end = int(db.offsets[n - 1]) + int(db.lens[n - 1])
-    return mmseqsdb.DB(db.data[:end], np.arange(n, dtype=np.uint32), db.offsets[:n].copy(), db.lens[:n].copy(), db.dbtype)
+_ORACLE_READS = None
+
+
+def _oracle_chunk(span):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    s, e = span
+    db = synth.nucleotide_db(_ORACLE_READS[s:e])
+    long_p = ob.orf_params_from_flags({"--min-length": "45", "--max-length": "32734", "--max-gaps": "0", "--contig-start-mode": "2",
+                                       "--contig-end-mode": "2", "--orf-start-mode": "0"})
+    start_p = ob.orf_params_from_flags({"--min-length": "20", "--max-length": "45", "--max-gaps": "0", "--contig-start-mode": "1",
+                                        "--contig-end-mode": "0", "--orf-start-mode": "0"})
+    lo, _ = ob.extractorfs(db, long_p, True)
+    st, _ = ob.extractorfs(db, start_p, True)
+    return (np.array(lo.data), np.array(lo.lens)), (np.array(st.data), np.array(st.lens))
+
+
+def fragments_cpu(reads, workers):
+    """aa_6f_start_long of `reads` WITHOUT a GPU (reference arm): the oracle's restatement of extractorfs + translatenucs
+    (oracle/oracle_next.cpp, pinned against the reference binary on tests/golden/orf_aa), forked over the host cores.
+    Parameters = EXTRACTORFS_LONG_PAR / EXTRACTORFS_START_PAR of src/workflow/Assembler.cpp:114-128."""
+    global _ORACLE_READS
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    ob.build()
+    chunk = 100000
+    spans = [(s, min(len(reads), s + chunk)) for s in range(0, len(reads), chunk)]
+    _ORACLE_READS = reads
+    try:
+        if workers > 1 and len(spans) > 1:
+            import multiprocessing as mp
+            with mp.get_context("fork").Pool(min(workers, len(spans))) as pool:
+                parts = pool.map(_oracle_chunk, spans, chunksize=1)
+        else:
+            parts = [_oracle_chunk(s) for s in spans]
+    finally:
+        _ORACLE_READS = None
+
+    def join(idx):
+        lens = np.concatenate([p[idx][1] for p in parts]).astype(np.uint32)
+        data = np.concatenate([p[idx][0] for p in parts])
+        offsets = np.zeros(len(lens), dtype=np.uint64)
+        if len(lens):
+            offsets[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+        return mmseqsdb.DB(data, np.arange(len(lens), dtype=np.uint32), offsets, lens, 0)
+    return concat_dbs(join(0), join(1))
+
+
+def fragments_gpu(ctx, reads):
+    """aa_6f_start_long of `reads` on the GPU (pg_extractorfs x 2 + pg_seqdb_concat); returns the device DB."""
+    dn = ctx.upload(synth.nucleotide_db(reads))
+    frag = ctx.six_frame_fragments(dn)
+    dn.free()
+    return frag
 
 
 def write_db_fast(path, db):
-    db.data.tofile(path)
-    with open(path + ".index", "w") as f:
-        f.write("".join("%d\t%d\t%d\n" % (int(k), int(o), int(l)) for k, o, l in zip(db.keys, db.offsets, db.lens)))
+    np.asarray(db.data).tofile(path)
+    k = np.asarray(db.keys, dtype=np.uint64); o = np.asarray(db.offsets, dtype=np.uint64); l = np.asarray(db.lens, dtype=np.uint64)
+    try:
+        import pyarrow as pa
+        import pyarrow.csv as pacsv
+        pacsv.write_csv(pa.table({"k": k, "o": o, "l": l}), path + ".index", pacsv.WriteOptions(include_header=False, delimiter="\t"))
+    except Exception:  # noqa: BLE001
+        np.savetxt(path + ".index", np.stack([k, o, l], axis=1), fmt="%d", delimiter="\t")
     np.array([db.dbtype], dtype="<i4").tofile(path + ".dbtype")
 
 
-def run_reference_iteration(db, threads, workdir):
-    """kmermatcher + rescorediagonal + assembleresults of the unmodified reference on `db`; returns seconds."""
-    if os.path.exists(workdir):
-        shutil.rmtree(workdir)
-    os.makedirs(workdir)
-    seq = os.path.join(workdir, "seq")
-    write_db_fast(seq, db)
+# ---- reference binary ---------------------------------------------------------------------------------------------
+def run_reference_iteration(seq, threads, workdir):
+    """kmermatcher + rescorediagonal + assembleresults of the unmodified reference on DB `seq` (on disk); returns
+    (seconds, per-step seconds); leaves pref / aln / asm in workdir."""
+    for name in ("pref", "aln", "asm"):
+        for f in os.listdir(workdir):
+            if f == name or f.startswith(name + "."):
+                os.unlink(os.path.join(workdir, f))
     env = dict(os.environ, MMSEQS_NUM_THREADS=str(threads))
+    w = lambda x: os.path.join(workdir, x)  # noqa: E731
     cmds = [
-        [REF_BIN, "kmermatcher", seq, os.path.join(workdir, "pref")] + KM_FLAGS.split() + ["--threads", str(threads)],
-        [REF_BIN, "rescorediagonal", seq, seq, os.path.join(workdir, "pref"), os.path.join(workdir, "aln")] + RS_FLAGS.split() + ["--threads", str(threads)],
-        [REF_BIN, "assembleresults", seq, os.path.join(workdir, "aln"), os.path.join(workdir, "asm")] + EX_FLAGS.split() + ["--threads", str(threads)],
+        [REF_BIN, "kmermatcher", seq, w("pref")] + KM_FLAGS.split() + ["--threads", str(threads)],
+        [REF_BIN, "rescorediagonal", seq, seq, w("pref"), w("aln")] + RS_FLAGS.split() + ["--threads", str(threads)],
+        [REF_BIN, "assembleresults", seq, w("aln"), w("asm")] + EX_FLAGS.split() + ["--threads", str(threads)],
     ]
-    total = 0.0
     per = []
     for c in cmds:
         t = time.time()
         r = subprocess.run(c, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env)
-        dt = time.time() - t
         if r.returncode != 0:
             raise RuntimeError("reference step failed: %s\n%s" % (" ".join(c[:2]), r.stdout.decode()[-2000:]))
-        per.append(dt)
-        total += dt
-    return total, per
+        per.append(time.time() - t)
+    return sum(per), per
 
 
-def sized_cpu_sample(args, n_reads_total, threads, work):
-    """Bounded sample for the CPU arm: the same generator at the same 20x coverage (a prefix of the big DB would have
-    lower coverage, fewer overlaps per read, and flatter the CPU).  A first run on --cpu-sample-reads reads calibrates;
-    if it took less than ~10 s the sample is enlarged towards ~15 s of CPU work, up to the whole workload."""
-    sample_reads = min(args.cpu_sample_reads, n_reads_total)
-    sample = make_fragments(sample_reads, args.seed)
-    t, per = run_reference_iteration(sample, threads, work)
-    log("[bench/reference] calibration: %d reads in %.2f s" % (sample_reads, t))
-    if t < 10.0 and sample_reads < n_reads_total:
-        want = int(sample_reads * 15.0 / max(t, 0.05))
-        want = min(n_reads_total, max(sample_reads, (want // 100000) * 100000))
-        if want > sample_reads:
-            sample_reads = want
-            sample = make_fragments(sample_reads, args.seed)
-    return sample_reads, sample
+def run_cli(args, threads):
+    t = time.time()
+    r = subprocess.run([CLI] + args + ["--threads", str(threads)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("plass_b200_cli %s failed:\n%s" % (args[0], r.stdout[-2000:]))
+    return time.time() - t, r.stdout
+
+
+def dbdiff(a, b, mode):
+    r = subprocess.run([CLI, "dbdiff", a, b, "--mode", mode], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    line = [x for x in r.stdout.splitlines() if x.startswith("{")]
+    if not line:
+        raise RuntimeError("dbdiff %s %s failed:\n%s" % (a, b, r.stdout[-2000:]))
+    return json.loads(line[-1])
+
+
+def parity_and_dropin(workdir, seq, threads, ref_per):
+    """The sample DB `seq` (on disk, already processed by the reference into workdir/pref|aln|asm) through the GPU drop-in
+    commands; compares the three result DBs key -> entry bytes and reports the commands' wall-clock."""
+    w = lambda x: os.path.join(workdir, x)  # noqa: E731
+    flags = lambda s: s.split()  # noqa: E731
+    # (a) the three commands as data/assemble.sh calls them, one process each
+    t_km, _ = run_cli(["kmermatcher", seq, w("g_pref")] + flags(KM_FLAGS), threads)
+    t_rs, _ = run_cli(["rescorediagonal", seq, seq, w("g_pref"), w("g_aln")] + flags(RS_FLAGS), threads)
+    t_ex, _ = run_cli(["assembleresults", seq, w("g_aln"), w("g_asm")] + flags(EX_FLAGS), threads)
+    d_pref, d_aln, d_asm = dbdiff(w("g_pref"), w("pref"), "exact"), dbdiff(w("g_aln"), w("aln"), "aln"), dbdiff(w("g_asm"), w("asm"), "exact")
+    # (b) the same iteration fused in one process
+    union = flags(KM_FLAGS) + ["--rescore-mode", "3", "--wrapped-scoring", "0", "--filter-hits", "0", "-e", "1e-05", "-a", "0", "--min-aln-len", "0",
+                               "--seq-id-mode", "0", "--add-self-matches", "0", "--sort-results", "0", "--db-load-mode", "0", "--keep-target", "1"]
+    t_fused, out_fused = run_cli(["assembleiteration", seq, w("f_pref"), w("f_aln"), w("f_asm")] + union, threads)
+    f_pref, f_aln, f_asm = dbdiff(w("f_pref"), w("pref"), "exact"), dbdiff(w("f_aln"), w("aln"), "aln"), dbdiff(w("f_asm"), w("asm"), "exact")
+    mism = sum(d["mismatching"] + d["only_in_a"] + d["only_in_b"] for d in (d_pref, d_aln, d_asm, f_pref, f_aln, f_asm))
+    parity = {"sequences": d_pref["entries_b"], "mismatching_entries": int(mism),
+              "evalue_last_digit_entries": int(d_aln["tolerated"]), "evalue_last_digit_lines": int(d_aln["tolerated_lines"]),
+              "compared": "pref, aln, assembly DBs of plass_b200_cli (three commands and fused assembleiteration) vs oracle/_ref/bin/plass on the same "
+                          "sample DB, key -> entry bytes (plass_b200_cli dbdiff); aln: E-value column may differ by one unit of its last printed digit",
+              "entries": {"pref": d_pref["entries_b"], "aln": d_aln["entries_b"], "assembly": d_asm["entries_b"]}}
+    ref_total = sum(ref_per)
+    dropin = {"definition": "wall-clock of each command as a process (start to exit: CUDA init, DB open / index parse, upload, kernels, download, text "
+                            "formatting, DB write), SURVEY.md 8d; tmp dir %s; %d host threads" % (workdir, threads),
+              "reference_s": {"kmermatcher": ref_per[0], "rescorediagonal": ref_per[1], "assembleresults": ref_per[2], "iteration": ref_total},
+              "gpu_cli_s": {"kmermatcher": t_km, "rescorediagonal": t_rs, "assembleresults": t_ex, "iteration": t_km + t_rs + t_ex},
+              "gpu_cli_fused_s": t_fused, "gpu_cli_fused_phases": [x for x in out_fused.splitlines() if x.startswith("open + index parse")][-1:] or None,
+              "speedup_three_commands": ref_total / (t_km + t_rs + t_ex), "speedup_fused": ref_total / t_fused}
+    return parity, dropin
 
 
 class ClockSampler:
@@ -183,17 +267,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_arm(args, db_full, n_reads_total):
-    """--impl reference: the reference's own CPU path, bounded sample, all host threads."""
+def reference_arm(args):
+    """--impl reference: the reference's own CPU path on a bounded sample of the same workload, all host threads."""
     threads = os.cpu_count() or 1
-    # same generator, same 20x coverage, fewer reads (a prefix of the big DB would have lower coverage and
-    # therefore fewer overlaps per read, which would flatter the CPU)
-    work = os.path.join(tempfile.gettempdir(), "plass_b200_ref_%d" % os.getpid())
-    sample_reads, sample = sized_cpu_sample(args, n_reads_total, threads, work)
-    times = []
+    work = tempfile.mkdtemp(prefix="plass_b200_ref_")
     try:
+        # calibration: the same generator at the same 20x coverage (a prefix of the big DB would have lower coverage,
+        # fewer overlaps per read, and flatter the CPU), enlarged towards ~10 s of CPU work per step
+        sample_reads = min(args.cpu_sample_reads, args.reads)
+        seq = os.path.join(work, "seq")
+        db = fragments_cpu(synth.make_reads_fast(sample_reads, seed=args.seed), threads)
+        write_db_fast(seq, db)
+        t, per = run_reference_iteration(seq, threads, work)
+        log("[bench/reference] calibration: %d reads (%d fragments) in %.2f s" % (sample_reads, db.n, t))
+        if t < 7.0 and sample_reads < args.reads:
+            want = min(args.reads, max(sample_reads, (int(sample_reads * 10.0 / max(t, 0.05)) // 100000) * 100000))
+            if want > sample_reads:
+                sample_reads = want
+                db = fragments_cpu(synth.make_reads_fast(sample_reads, seed=args.seed), threads)
+                write_db_fast(seq, db)
+        times = []
         for i in range(args.warmup + args.steps):
-            t, per = run_reference_iteration(sample, threads, work)
+            t, per = run_reference_iteration(seq, threads, work)
             log("[bench/reference] step %d: %.2f s (kmermatcher %.2f, rescorediagonal %.2f, assembleresults %.2f)" % (i, t, per[0], per[1], per[2]))
             if i >= args.warmup:
                 times.append(t)
@@ -201,14 +296,13 @@ def reference_arm(args, db_full, n_reads_total):
         shutil.rmtree(work, ignore_errors=True)
     sec = float(np.mean(times))
     val = sample_reads / sec
-    sample_desc = "%d reads (%d fragments) from the same generator at the same 20x coverage instead of %d reads; %d threads; tmp dir %s" % (
-        sample_reads, sample.n, n_reads_total, threads, tempfile.gettempdir())
+    sample_desc = "%d reads (%d fragments of aa_6f_start_long) from the same generator at the same 20x coverage instead of %d reads; %d threads; tmp dir %s" % (
+        sample_reads, db.n, args.reads, threads, tempfile.gettempdir())
     return {
-        "metric": "reads/sec per assemble iteration (kmermatcher+rescorediagonal+assembleresults)", "value": val, "unit": "reads/s",
+        "metric": METRIC, "value": val, "unit": "reads/s",
         "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1000.0,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (+f64 E-values)", "data": "synthetic",
-        "config": {"workload": workload_name(args.reads, False) + "; bounded sample",
-                   "reads": n_reads_total, "fragments": int(db_full.n)},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32 (+f64 E-values)", "data": "synthetic",
+        "config": workload_config(args.reads),
         "cpu_baseline": {"value": val, "unit": "reads/s", "cores": threads, "kind": "reference", "sample": sample_desc},
         "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -228,6 +322,25 @@ def emit_json(line):
         os.write(_REAL_STDOUT, data)
 
 
+def pin(db):
+    import torch
+    return mmseqsdb.DB(torch.from_numpy(np.ascontiguousarray(db.data)).pin_memory().numpy(),
+                       torch.from_numpy(np.ascontiguousarray(db.keys)).pin_memory().numpy(),
+                       torch.from_numpy(np.ascontiguousarray(db.offsets).view(np.int64)).pin_memory().numpy().view(np.uint64),
+                       torch.from_numpy(np.ascontiguousarray(db.lens).view(np.int32)).pin_memory().numpy().view(np.uint32), db.dbtype)
+
+
+def roofline_traffic(nrec):
+    """DRAM bytes of one scatter launch from the round's `ncu --set full` capture (profiles/roofline_capture.json:
+    dram__bytes_read.sum + dram__bytes_write.sum and the records of the captured launch), scaled to this run's launch."""
+    p = os.path.join(ROOT, "profiles", "roofline_capture.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p))
+    per_rec = (d["dram_bytes_read"] + d["dram_bytes_write"]) / d["records"]
+    return nrec * per_rec, "%s (%s): %.2f B per record and launch" % (d.get("kernel", "?"), d.get("source", p), per_rec)
+
+
 def main():
     global _REAL_STDOUT
     sys.stdout.flush()
@@ -238,11 +351,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=5000000, help="reads per GPU")
+    ap.add_argument("--reads", type=int, default=50000000, help="reads of the whole job (strong scaling over the ranks)")
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--cpu-sample-reads", type=int, default=400000, help="reads in the bounded CPU-baseline sample")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-reads", type=int, default=1000000, help="reads in the bounded CPU-baseline / parity sample (enlarged towards ~10 s of CPU work)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference binary (also skips the parity gate and the drop-in timing)")
     ap.add_argument("--no-extras", action="store_true", help="skip the (untimed-for-the-metric) measurements of the neighbouring steps")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="pipelined end-to-end steps (default max(steps, 8))")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -252,37 +366,20 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        db = make_fragments(args.reads, args.seed)
-        emit_json(reference_arm(args, db, args.reads))
+        emit_json(reference_arm(args))
         return 0
 
     import torch
     import torch.distributed as dist
+    from plass_b200 import api
+    torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local_rank)
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-    else:
-        torch.cuda.set_device(local_rank)
 
-    # weak scaling: every rank contributes `reads` reads; the job's DB is the union (replicated in each HBM)
-    n_reads_total = args.reads * world
-    if world > 1:
-        # rank 0 generates (and caches) the job's input, the other ranks load the cached copy
-        db = make_fragments(n_reads_total, args.seed) if rank == 0 else None
-        dist.barrier()
-        if db is None:
-            db = make_fragments(n_reads_total, args.seed)
-    else:
-        db = make_fragments(n_reads_total, args.seed)
     ctx = api.Context(local_rank)
     kp, rp, ep = api.default_km_params(False), api.default_rs_params(False), api.default_ex_params(False)
-
-    if world > 1:
-        from plass_b200 import sharded
-        runner = sharded.ShardedIteration(ctx, dist, rank, world)
-    else:
-        runner = None
+    threads = os.cpu_count() or 1
 
     def barrier():
         torch.cuda.synchronize()
@@ -290,13 +387,61 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    # ---- CPU baseline + parity gate + drop-in wall-clock on a bounded sample (rank 0, before the big buffers exist) ----
+    cpu = parity = dropin = None
+    if rank == 0 and not args.no_cpu_baseline and os.path.exists(REF_BIN):
+        work = tempfile.mkdtemp(prefix="plass_b200_cpu_")
+        try:
+            seq = os.path.join(work, "seq")
+
+            def make_sample(n_reads):
+                d = fragments_gpu(ctx, synth.make_reads_fast(n_reads, seed=args.seed))
+                h = d.download()
+                d.free()
+                write_db_fast(seq, h)
+                return h.n
+            sample_reads = min(args.cpu_sample_reads, args.reads)
+            n_frag = make_sample(sample_reads)
+            t, per = run_reference_iteration(seq, threads, work)
+            log("[bench/cpu] calibration: %d reads (%d fragments) in %.2f s" % (sample_reads, n_frag, t))
+            if t < 7.0 and sample_reads < args.reads:
+                want = min(args.reads, max(sample_reads, (int(sample_reads * 10.0 / max(t, 0.05)) // 100000) * 100000))
+                if want > sample_reads:
+                    sample_reads = want
+                    n_frag = make_sample(sample_reads)
+                    t, per = run_reference_iteration(seq, threads, work)
+            cpu = {"value": sample_reads / t, "unit": "reads/s", "cores": threads, "kind": "reference",
+                   "sample": "%d reads (%d fragments of aa_6f_start_long), same generator and 20x coverage, one iteration, %.1f s (kmermatcher %.1f, rescorediagonal %.1f, "
+                             "assembleresults %.1f)" % (sample_reads, n_frag, t, per[0], per[1], per[2])}
+            log("[bench/cpu] reference: %s" % cpu["sample"])
+            parity, dropin = parity_and_dropin(work, seq, threads, per)
+            parity["reads"] = sample_reads
+            log("[bench/parity] %s" % json.dumps(parity))
+            log("[bench/dropin] %s" % json.dumps(dropin))
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+        if parity["mismatching_entries"] != 0:
+            raise SystemExit("PARITY FAILURE: %d entries of the GPU drop-in differ from the reference on the %d-read sample" % (parity["mismatching_entries"], sample_reads))
+
+    # ---- the job's input: rank 0 builds it on its GPU, the other ranks receive it over NVLink ------------------------
+    t_gen = time.time()
+    runner = None
+    if world > 1:
+        from plass_b200 import sharded
+        runner = sharded.ShardedIteration(ctx, dist, rank, world)
+        ddb = runner.build_and_broadcast(lambda: fragments_gpu(ctx, synth.make_reads_fast(args.reads, seed=args.seed)))
+    else:
+        ddb = fragments_gpu(ctx, synth.make_reads_fast(args.reads, seed=args.seed))
+    n_frag_total = ddb.n
+    if rank == 0:
+        log("[bench] %d reads -> %d fragments in HBM in %.1f s" % (args.reads, n_frag_total, time.time() - t_gen))
+
     # ---- device-resident arm (value) -------------------------------------------------------------
-    ddb = ctx.upload(db)
     peak, peak_src = load_peaks()
     tim = []
     # the clock sampler (nvidia-smi, one line every 50 ms) is started before the warm-up steps: the tool needs ~0.1 s
-    # before its first line, and the timed region of a few 50 ms steps would otherwise see a single sample.  Warm-up and
-    # timed steps run the same kernels, so every sample is taken under the load that is being measured.
+    # before its first line.  Warm-up and timed steps run the same kernels, so every sample is taken under the load
+    # that is being measured.
     sampler = ClockSampler(local_rank)
     sampler.start()
     for i in range(args.warmup):
@@ -317,20 +462,31 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     ms_per_step = dt * 1000.0 / args.steps
-    value = n_reads_total / (dt / args.steps)
+    value = args.reads / (dt / args.steps)
+
+    # ---- N > 1: the sharded result must equal the single-GPU result (checksums over hits, alignments, new DB) -------
+    shard_check = None
+    if runner is not None:
+        shard_check = runner.verify_against_single_gpu(ddb, kp, rp, ep)
+        if rank == 0:
+            log("[bench/shard-check] %s" % json.dumps(shard_check))
+            if not shard_check["equal"]:
+                raise SystemExit("SHARDED RESULT DIFFERS from the single-GPU result: %s" % json.dumps(shard_check))
 
     # ---- end-to-end arm: host buffers through the C ABI ---------------------------------------------
-    pinned = mmseqsdb.DB(torch.from_numpy(db.data).pin_memory().numpy(), torch.from_numpy(db.keys).pin_memory().numpy(),
-                         torch.from_numpy(db.offsets.view(np.int64)).pin_memory().numpy().view(np.uint64),
-                         torch.from_numpy(db.lens.view(np.int32)).pin_memory().numpy().view(np.uint32), db.dbtype)
+    if runner is None:
+        host = ddb.download()
+        pinned = pin(host)
+        del host
+    else:
+        pinned = runner.pinned_slice(ddb)                    # this rank's slice of the sequences, in pinned host memory
     h2d = int(pinned.data.nbytes + pinned.keys.nbytes + pinned.offsets.nbytes + pinned.lens.nbytes)
     e2e_times, d2h, e2e_phases = [], 0, []
-    e2e_steps = max(1, min(args.steps, 2))
-    for i in range(1 + e2e_steps):
+    for i in range(3):
         barrier()
         t0 = time.perf_counter()
         if runner:
-            d_in, h2d_rank = sharded.upload_sliced(ctx, dist, pinned, rank, world)   # PCIe: this rank's slice; NVLink: the rest
+            d_in = runner.upload_sliced(pinned)              # PCIe: this rank's slice; NVLink: the rest
             out = runner.step(d_in, kp, rp, ep, download=True)
             d2h = runner.last_d2h_bytes
         else:
@@ -342,8 +498,7 @@ def main():
             if i > 0:
                 e2e_phases.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3, (time.perf_counter() - t2) * 1e3))
             d2h = int(hits.nbytes + alns.nbytes + host_out.data.nbytes + host_out.offsets.nbytes + host_out.lens.nbytes + host_out.keys.nbytes)
-            # the step's results live in pinned blocks of the library's pool: drop them so that the next step reuses
-            # the blocks instead of pinning 2 GB of fresh host memory
+            # the step's results live in pinned blocks of the library's pool: drop them so that the next step reuses them
             del hits, alns, host_out
         out.free(); d_in.free()
         barrier()
@@ -356,6 +511,7 @@ def main():
         # Pipelined steps, the way the assembly workflow runs: the results of step i (prefilter hits, alignments, new DB)
         # travel to the host while step i+1 is uploaded and computed.  Every step still copies its input from pinned host
         # memory and every result is awaited inside the timed region (the last one after the loop).
+        ddb.free(); ddb = None                                # the resident copy is not needed any more: room for two steps in flight
         ctx.set_async_results(True)
         try:
             trace = os.environ.get("PLASS_B200_E2E_TRACE")
@@ -363,8 +519,6 @@ def main():
             def run_pipelined(k):
                 pending = None
                 nbytes = 0
-                # every step copies its own input from pinned host memory; the copy of step i+1's input is enqueued on
-                # the upload stream before step i's kernels are launched, so it travels underneath them
                 nxt = ctx.upload_async(pinned)
                 for i in range(k):
                     ta = time.perf_counter()
@@ -388,7 +542,7 @@ def main():
                 nbytes = sum(int(a.nbytes) for a in pending[1:])
                 return nbytes
             run_pipelined(2)                                   # warm-up: two sets of pinned result blocks
-            k = max(args.steps, 8)                             # long enough that the first upload and the final drain are amortised
+            k = args.e2e_steps or max(args.steps, 8)           # long enough that the first upload and the final drain are amortised
             barrier()
             t0 = time.perf_counter()
             d2h = run_pipelined(k)
@@ -402,54 +556,42 @@ def main():
         t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
-        t = torch.tensor([d2h], dtype=torch.int64, device="cuda")      # bytes of the whole job: sum over the ranks
+        t = torch.tensor([d2h, h2d], dtype=torch.int64, device="cuda")      # bytes of the whole job: sum over the ranks
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        d2h = int(t.item())
-    e2e_value = n_reads_total / e2e_dt
+        d2h, h2d = int(t[0].item()), int(t[1].item())
+    e2e_value = args.reads / e2e_dt
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------
     scatter_ms = float(np.mean([t["sort1_scatter_ms"] for t in tim]))
     passes = int(tim[-1]["sort1_passes"])
     nrec = int(tim[-1]["n_kmer_records"])
-    alg_bytes = nrec * 16 * 2                      # SURVEY §8d: a sort = one read + one write of every record
+    alg_bytes = nrec * 16 * 2                      # SURVEY 8d: a sort = one read + one write of every record
     achieved = alg_bytes / 1e9 / (scatter_ms / 1e3) if scatter_ms > 0 else 0.0
-    # DRAM traffic of one scatter launch from the ncu --set full capture of this kernel (profiles/r1_summary_c.md):
-    # 8.14 GB for 250 M records = 32.56 B per record and pass, i.e. the algorithmic 2 x 16 B plus 1.7 % (status words, tails)
-    traffic = nrec * 32.56
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "radix_scatter_kernel (sort #1, %d launches/step)" % passes,
+    traffic, traffic_src = roofline_traffic(nrec)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "radix scatter (sort #1, %d passes/step)" % passes,
                 "algorithmic_bytes_per_launch": alg_bytes / max(passes, 1), "launch_ms": scatter_ms / max(passes, 1), "peak_source": peak_src}
-    stage_ms = {k: float(np.mean([t[k] for t in tim])) for k in ("extract_ms", "sort1_ms", "group_ms", "sort2_ms", "reduce_ms", "rescore_ms", "extend_ms", "exchange_ms", "total_ms")}
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN):
-        try:
-            threads = os.cpu_count() or 1
-            work = os.path.join(tempfile.gettempdir(), "plass_b200_cpu_%d" % os.getpid())
-            sample_reads, sample = sized_cpu_sample(args, n_reads_total, threads, work)
-            t, per = run_reference_iteration(sample, threads, work)
-            shutil.rmtree(work, ignore_errors=True)
-            cpu = {"value": sample_reads / t, "unit": "reads/s", "cores": threads, "kind": "reference",
-                   "sample": "%d reads (%d fragments), same generator and 20x coverage, one iteration, %.1f s (kmermatcher %.1f, rescorediagonal %.1f, assembleresults %.1f)"
-                             % (sample_reads, sample.n, t, per[0], per[1], per[2])}
-        except Exception as e:  # noqa: BLE001
-            cpu = {"value": None, "unit": "reads/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % e}
+    stage_keys = ("extract_ms", "sort1_ms", "group_ms", "sort2_ms", "reduce_ms", "rescore_ms", "extend_ms", "exchange_ms", "total_ms")
+    stage_ms = {k: float(np.mean([t[k] for t in tim])) for k in stage_keys}
+    # per-stage position against the HBM roofline: algorithmic bytes of DESIGN.md section 3 / stage time / peak
+    npair, nhit, naln = int(tim[-1]["n_pair_records"]), int(tim[-1]["n_hits"]), int(tim[-1]["n_alns"])
+    stage_frac = None
+    if world == 1:
+        L = 48.0
+        alg = {"extract_ms": n_frag_total * (L + 2) + 16.0 * nrec, "sort1_ms": 32.0 * nrec, "group_ms": 16.0 * nrec + 16.0 * npair,
+               "sort2_ms": 32.0 * npair, "reduce_ms": 16.0 * npair + 16.0 * nhit, "rescore_ms": nhit * (L + 26) + n_frag_total * (L + 2),
+               "extend_ms": naln * 24.0 + nhit * (L + 2) + 2 * n_frag_total * (L + 2)}
+        stage_frac = {k: (alg[k] / 1e9 / (stage_ms[k] / 1e3) / peak if stage_ms[k] > 0 else None) for k in alg}
+        stage_frac["iteration"] = sum(alg.values()) / 1e9 / (stage_ms["total_ms"] / 1e3) / peak
 
     # ---- neighbouring steps of the iteration, measured for the record; not part of the metric ----------
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
         try:
             extras = {}
-            # plass STEP 0 fused: two kmermatcher + rescorediagonal passes around findassemblystart, then assembleresults
-            for _ in range(2):
-                corr, out0, _, _ = ctx.assemble_step0(ddb, kp, rp, ep)
-                t0 = ctx.timings()
-                corr.free(); out0.free()
-            extras["step0_fused_ms"] = t0["total_ms"]
-            # reads -> aa_6f_start_long on the GPU (extractorfs x 2 + translatenucs x 2 + concatdbs, data/assemble.sh:41-77)
-            reads = synth.make_reads_fast(min(args.reads, 5000000), seed=args.seed)
+            small = min(args.reads, 5000000)
+            reads = synth.make_reads_fast(small, seed=args.seed)
             dn = ctx.upload(synth.nucleotide_db(reads))
-            n_reads_orf = int(reads.shape[0])
             del reads
             ms = 0.0
             for rep_i in range(2):
@@ -457,15 +599,23 @@ def main():
                 lo, _ = ctx.extractorfs(dn, api.orf_params_long(), translate=True, want_info=False); ms += ctx.timings()["total_ms"]
                 st, _ = ctx.extractorfs(dn, api.orf_params_start(), translate=True, want_info=False); ms += ctx.timings()["total_ms"]
                 cat = ctx.concat(lo, st); ms += ctx.timings()["total_ms"]
-                n_frag = cat.n
-                lo.free(); st.free(); cat.free()
-            dn.free()
-            extras["six_frame_fragments_ms"] = ms
-            extras["six_frame_fragments"] = {"reads": n_reads_orf, "fragments": int(n_frag), "reads_per_s": n_reads_orf / (ms / 1e3)}
+                lo.free(); st.free()
+                if rep_i == 0:
+                    cat.free()
+            extras["six_frame_fragments"] = {"reads": small, "fragments": int(cat.n), "ms": ms, "reads_per_s": small / (ms / 1e3)}
+            # configs[1]: the 5 M-read iteration, and plass STEP 0 fused (two kmermatcher + rescorediagonal passes around findassemblystart)
+            for _ in range(3):
+                o5 = ctx.assemble_iteration(cat, kp, rp, ep)[0]
+                t5 = ctx.timings()
+                o5.free()
+            extras["iteration_5M_reads"] = {"reads": small, "ms": t5["total_ms"], "reads_per_s": small / (t5["total_ms"] / 1e3), "stage_ms": {k: t5[k] for k in stage_keys[:7]}}
+            for _ in range(2):
+                corr, out0, _, _ = ctx.assemble_step0(cat, kp, rp, ep)
+                t0s = ctx.timings()
+                corr.free(); out0.free()
+            extras["step0_fused_ms"] = t0s["total_ms"]
+            cat.free()
             # the nucleotide path (penguin nuclassemble, k = 22): one iteration + cyclecheck on the same reads
-            nreads = synth.make_reads_fast(min(args.reads, 5000000), seed=args.seed + 100)
-            dn = ctx.upload(synth.nucleotide_db(nreads))
-            del nreads
             nkp, nrp, nep = api.default_km_params(True), api.default_rs_params(True), api.default_ex_params(True)
             for _ in range(2):
                 nout = ctx.assemble_iteration(dn, nkp, nrp, nep)[0]
@@ -476,8 +626,8 @@ def main():
                     tc = ctx.timings()
                 nout.free()
             dn.free()
-            extras["nucl_iteration"] = {"reads": int(min(args.reads, 5000000)), "ms": tn["total_ms"],
-                                        "stage_ms": {k: tn[k] for k in ("extract_ms", "sort1_ms", "group_ms", "sort2_ms", "reduce_ms", "rescore_ms", "extend_ms")},
+            extras["nucl_iteration"] = {"reads": small, "ms": tn["total_ms"], "reads_per_s": small / (tn["total_ms"] / 1e3),
+                                        "stage_ms": {k: tn[k] for k in stage_keys[:7]},
                                         "kmer_records": int(tn["n_kmer_records"]), "hits": int(tn["n_hits"]), "alignments": int(tn["n_alns"]),
                                         "output_sequences": int(n_nt_out)}
             extras["cyclecheck"] = {"sequences": int(n_nt_out), "ms": tc["total_ms"], "reported": int((split > 0).sum())}
@@ -486,24 +636,25 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": "reads/sec per assemble iteration (kmermatcher+rescorediagonal+assembleresults)", "value": value, "unit": "reads/s",
+            "metric": METRIC, "value": value, "unit": "reads/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (+f64 E-values)", "data": "synthetic",
-            "config": {"workload": workload_name(args.reads, True),
-                       "reads": n_reads_total, "fragments": int(db.n), "kmer_records": nrec, "pair_records": int(tim[-1]["n_pair_records"]),
-                       "hits": int(tim[-1]["n_hits"]), "alignments": int(tim[-1]["n_alns"]), "output_sequences": int(n_out),
-                       "l2": "inputs_larger_than_l2 (%.1f GB of k-mer records per step)" % (nrec * 16 / 1e9),
-                       "parallelism": ("%d ranks: sequence-sliced extraction, all-to-all of k-mer records by k-mer owner, all-to-all of pair records by "
-                                       "representative owner; record counts above are rank 0's share" % world) if world > 1 else "single GPU"},
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8/int32 (+f64 E-values)", "data": "synthetic",
+            "config": workload_config(args.reads),
+            "workload_stats": {"fragments": int(n_frag_total), "kmer_records": nrec, "pair_records": npair, "hits": nhit, "alignments": naln,
+                               "output_sequences": int(n_out), "kmer_record_bytes_per_step": nrec * 16,
+                               "parallelism": (runner.describe() if runner else "single GPU"),
+                               "counts_are": "rank 0's share" if world > 1 else "the whole job's"},
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_dt * 1000.0,
                     "mode": e2e_mode, "serial_ms_per_step": e2e_serial_ms,
                     "phases_ms": ({"upload": float(np.mean([p[0] for p in e2e_phases])), "iteration_with_hits_alns_d2h": float(np.mean([p[1] for p in e2e_phases])),
-                                   "download_new_db": float(np.mean([p[2] for p in e2e_phases]))} if e2e_phases else None)},
+                                   "download_new_db": float(np.mean([p[2] for p in e2e_phases]))} if e2e_phases else (runner.e2e_phases() if runner else None))},
             "gpu_launches": int(sum(t["kernel_launches"] for t in tim)),
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "stage_ms": stage_ms, "extras": extras,
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "dropin": dropin, "shard_check": shard_check,
+            "clocks": clocks, "stage_ms": stage_ms, "stage_roofline_frac": stage_frac, "extras": extras,
         }
         emit_json(line)
-    ddb.free()
+    if ddb is not None:
+        ddb.free()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

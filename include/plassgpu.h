@@ -261,6 +261,35 @@ int pg_shard_export(pg_context *ctx, void *device_dst, uint64_t n_records);
 int pg_shard_finish(pg_context *ctx, const pg_seqdb *db, const void *device_pairs, uint64_t n_pairs,
                     uint32_t own_lo, uint32_t own_hi, const pg_rs_params *rp, const pg_ex_params *ep,
                     pg_seqdb **out_db, pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns);
+/* The same decomposition driven entirely from C++ over NCCL (one process per GPU; plass_b200/csrc/pg_shard.cu):
+ *
+ *   pg_comm_unique_id / pg_comm_init   ncclGetUniqueId on one rank, the PG_COMM_ID_BYTES bytes reach the others by any means
+ *                                      (a file, MPI, torch.distributed), then ncclCommInitRank on every rank's context.
+ *   pg_shard_broadcast_db              replicates a DB held by `root` in every rank's HBM over NVLink.
+ *   pg_shard_iteration                 extraction of this rank's slice -> exchange #1 (k-mer records to the k-mer owner)
+ *                                      -> sort #1 + assignGroup -> all-reduced work histogram -> equal-work key ranges ->
+ *                                      exchange #2 (candidate pairs to the owner of the representative) -> sort #2 + best
+ *                                      diagonal -> rescorediagonal -> extension of the owned queries.  Exchanges are
+ *                                      grouped ncclSend / ncclRecv between the stages' record buffers; the only host
+ *                                      round trips are the W x W count matrix and the work histogram.  out_slice = the
+ *                                      new entries of the keys in [*own_lo, *own_hi).
+ *   pg_shard_allgather_db              concatenates the ranks' slices (ascending key ranges in rank order) into a replicated
+ *                                      DB: the next iteration's input (data/assemble.sh:153), or the upload of a host DB of
+ *                                      which every rank copied only its slice over PCIe. */
+#define PG_COMM_ID_BYTES 128
+int pg_comm_unique_id(void *id);
+int pg_comm_init(pg_context *ctx, int rank, int world, const void *id);
+int pg_comm_destroy(pg_context *ctx);
+int pg_comm_rank(const pg_context *ctx);
+int pg_comm_world(const pg_context *ctx);
+int pg_shard_broadcast_db(pg_context *ctx, const pg_seqdb *db_on_root, int root, pg_seqdb **out_db);
+int pg_shard_allgather_db(pg_context *ctx, const pg_seqdb *slice, pg_seqdb **out_db);
+int pg_shard_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, const pg_rs_params *rp, const pg_ex_params *ep,
+                       pg_seqdb **out_slice, uint32_t *own_lo, uint32_t *own_hi, pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns);
+int pg_shard_exchange_stats(const pg_context *ctx, float *ms /* [2] */, uint64_t *bytes /* [2] */);
+/* the equal-work cut of the representative key space pg_shard_iteration uses (host arithmetic only) */
+int pg_shard_balanced_bounds(const uint64_t *hist, int bins, uint32_t max_key, int world, double per_key_weight, uint32_t *bounds /* world + 1 */);
+
 /* Key range [lo, hi) owned by rank r of `world` for a DB whose largest key is max_key. */
 void pg_shard_owner_range(uint32_t max_key, int rank, int world, uint32_t *lo, uint32_t *hi);
 uint32_t pg_seqdb_max_key(const pg_seqdb *db);

@@ -21,10 +21,12 @@ EXPORTS = ["pg_last_error", "pg_device_count", "pg_init", "pg_destroy", "pg_get_
            "pg_assemble_iteration", "pg_free_host", "pg_set_async_results", "pg_results_ticket", "pg_results_wait",
            "pg_shard_pairs", "pg_shard_extract", "pg_shard_group", "pg_shard_route", "pg_shard_export", "pg_shard_finish", "pg_shard_owner_range", "pg_seqdb_max_key",
            "pg_seqdb_upload_async", "pg_findassemblystart", "pg_assemble_step0", "pg_cyclecheck", "pg_extractorfs", "pg_translatenucs",
-           "pg_seqdb_concat", "pg_set_split_memory_limit"]
+           "pg_seqdb_concat", "pg_set_split_memory_limit", "pg_comm_unique_id", "pg_comm_init", "pg_comm_destroy", "pg_comm_rank", "pg_comm_world",
+           "pg_shard_broadcast_db", "pg_shard_allgather_db", "pg_shard_iteration", "pg_shard_exchange_stats", "pg_shard_balanced_bounds"]
 
 
 SHARD_HIST_BINS = 4096   # PG_SHARD_HIST_BINS
+COMM_ID_BYTES = 128      # PG_COMM_ID_BYTES
 
 
 class SeqDBView(C.Structure):
@@ -378,7 +380,55 @@ class Context:
         out.dbtype = ddb.dbtype
         return out, hits, alns
 
-    # ---- multi-GPU phases (see plass_b200/sharded.py) ----
+    # ---- multi-GPU data plane in C++ over NCCL (plass_b200/csrc/pg_shard.cu) ----
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        _check(load_library().pg_comm_unique_id(buf), "pg_comm_unique_id")
+        return bytes(buf)
+
+    def comm_init(self, rank, world, comm_id):
+        buf = (C.c_uint8 * COMM_ID_BYTES)(*comm_id)
+        _check(load_library().pg_comm_init(self.handle, C.c_int(rank), C.c_int(world), buf), "pg_comm_init")
+
+    def shard_broadcast_db(self, ddb, root, dbtype=0):
+        h = C.c_void_p()
+        _check(load_library().pg_shard_broadcast_db(self.handle, ddb.handle if ddb is not None else None, C.c_int(root), C.byref(h)), "pg_shard_broadcast_db")
+        out = DeviceSeqDB(self, h)
+        out.dbtype = ddb.dbtype if ddb is not None else dbtype
+        return out
+
+    def shard_allgather_db(self, slice_db):
+        h = C.c_void_p()
+        _check(load_library().pg_shard_allgather_db(self.handle, slice_db.handle, C.byref(h)), "pg_shard_allgather_db")
+        out = DeviceSeqDB(self, h)
+        out.dbtype = slice_db.dbtype
+        return out
+
+    def shard_iteration(self, ddb, kp, rp, ep, want_intermediates=False):
+        """One iteration over all ranks of the communicator.  Returns (DeviceSeqDB of the owned keys, (own_lo, own_hi), hits or
+        None, alns or None) -- this rank's share."""
+        lib = load_library()
+        h, lo, hi = C.c_void_p(), C.c_uint32(), C.c_uint32()
+        if want_intermediates:
+            ho, hn, ao, an = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+            _check(lib.pg_shard_iteration(self.handle, ddb.handle, C.byref(kp), C.byref(rp), C.byref(ep), C.byref(h), C.byref(lo), C.byref(hi),
+                                          C.byref(ho), C.byref(hn), C.byref(ao), C.byref(an)), "pg_shard_iteration")
+            hits, alns = _take(ho, hn.value, HIT), _take(ao, an.value, ALN)
+        else:
+            _check(lib.pg_shard_iteration(self.handle, ddb.handle, C.byref(kp), C.byref(rp), C.byref(ep), C.byref(h), C.byref(lo), C.byref(hi),
+                                          None, None, None, None), "pg_shard_iteration")
+            hits = alns = None
+        out = DeviceSeqDB(self, h)
+        out.dbtype = ddb.dbtype
+        return out, (int(lo.value), int(hi.value)), hits, alns
+
+    def shard_exchange_stats(self):
+        ms, nb = (C.c_float * 2)(), (C.c_uint64 * 2)()
+        _check(load_library().pg_shard_exchange_stats(self.handle, ms, nb), "pg_shard_exchange_stats")
+        return [float(x) for x in ms], [int(x) for x in nb]
+
+    # ---- multi-GPU phases, one call each (the exchanges are the caller's; see tests/test_gpu_parity.py) ----
     def shard_pairs(self, ddb, kp, world):
         counts = (C.c_uint64 * world)()
         _check(load_library().pg_shard_pairs(self.handle, ddb.handle, C.byref(kp), C.c_int(world), counts), "pg_shard_pairs")

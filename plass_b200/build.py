@@ -30,6 +30,7 @@ CUDA_SOURCES = {
     "pg_extend.cu": ["-fmad=false"],
     "pg_next.cu": ["-fmad=false"],
     "pg_orf.cu": [],
+    "pg_shard.cu": [],
 }
 HOST_SOURCES = ["host/cli.cpp", "host/mmdb.cpp", "host/commands.cpp"]
 
@@ -77,7 +78,7 @@ def build(verbose=False):
         for o in outs:
             print(o)
     if _newer(LIB, objs):
-        _run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"], os.path.join(OBJ, "link.log"))
+        _run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"], os.path.join(OBJ, "link.log"))
     host = [os.path.join(CSRC, h) for h in HOST_SOURCES]
     if all(os.path.exists(h) for h in host) and _newer(CLI, host + headers + [LIB]):
         _run(["g++", "-O2", "-std=c++17", "-fopenmp", "-Wall", "-I" + os.path.join(os.path.dirname(HERE), "include"), "-o", CLI] + host +

@@ -208,7 +208,7 @@ static void collect_timings(Context *ctx) {
     t.kernel_launches = ctx->launches;
 }
 
-static void begin_call(Context *ctx) {
+void begin_call(Context *ctx) {
     cudaSetDevice(ctx->device);
     ctx->tExtract = ctx->tGroup = ctx->tReduce = ctx->rsRan = ctx->exRan = false;
     ctx->launches = 0;
@@ -216,19 +216,19 @@ static void begin_call(Context *ctx) {
     memset(&ctx->timings, 0, sizeof(ctx->timings));
     cudaEventRecord(ctx->ev[EV_TOTAL_BEGIN], ctx->stream);
 }
-static void end_call(Context *ctx) {
+void end_call(Context *ctx) {
     cudaEventRecord(ctx->ev[EV_TOTAL_END], ctx->stream);
     collect_timings(ctx);
 }
 // multi-GPU: one step is several calls; the reported timings are the sums over its phases
-static void end_shard_phase(Context *ctx, bool first) {
+void end_shard_phase(Context *ctx, bool first) {
     end_call(ctx);
     pg_timings &a = ctx->shardAcc;
     const pg_timings &t = ctx->timings;
     if (first) memset(&a, 0, sizeof(a));
     a.extract_ms += t.extract_ms; a.sort1_ms += t.sort1_ms; a.group_ms += t.group_ms; a.sort2_ms += t.sort2_ms; a.reduce_ms += t.reduce_ms;
     a.rescore_ms += t.rescore_ms; a.extend_ms += t.extend_ms; a.total_ms += t.total_ms; a.sort1_scatter_ms += t.sort1_scatter_ms;
-    a.kernel_launches += t.kernel_launches;
+    a.kernel_launches += t.kernel_launches; a.exchange_ms += t.exchange_ms;
     if (t.n_kmer_records) a.n_kmer_records = t.n_kmer_records;
     if (t.n_pair_records) a.n_pair_records = t.n_pair_records;
     if (t.sort1_bytes) a.sort1_bytes = t.sort1_bytes;
@@ -238,6 +238,8 @@ static void end_shard_phase(Context *ctx, bool first) {
     if (t.n_extended) a.n_extended = t.n_extended;
     ctx->timings = a;
 }
+int hits_to_host_overlapped(Context *ctx, const pg_hit *d, uint64_t n, pg_hit **out) { return to_host_overlapped(ctx, d, n, out); }
+int alns_to_host_overlapped(Context *ctx, const pg_aln *d, uint64_t n, pg_aln **out) { return to_host_overlapped(ctx, d, n, out); }
 }  // namespace pg
 
 using namespace pg;
@@ -300,6 +302,7 @@ void pg_destroy(pg_context *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) pg_comm_destroy(ctx);
     DevBuf *bufs[] = {&ctx->small, &ctx->lists, &ctx->recA, &ctx->recB, &ctx->radixWs, &ctx->scratch, &ctx->blockCounts, &ctx->hits,
                       &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta, &ctx->exLists, &ctx->ntTab, &ctx->buckets, &ctx->buckets2, &ctx->wideTabs, &ctx->nextWork, &ctx->orfInfo, &ctx->pairAcc};
     for (DevBuf *b : bufs) b->release();

@@ -957,13 +957,21 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     unsigned char *ext = m + oExt, *used = m + oUsed;
     void *scanWs = m + oScan;
     PG_CUDA(cudaMemsetAsync(m, 0, o, s));
-    PG_TRY(ctx->exWork.reserve(sizeof(ExRes) * 2 * (nAlns + 1)));
-    PG_TRY(ctx->exSegs.reserve(sizeof(ExSeg) * (nAlns + n + 1)));
-    ExRes *heapBuf = ctx->exWork.as<ExRes>();
+    // the extension's work arrays (heaps, rope segments, work lists: ~120 B per alignment) live in the kmermatcher's two
+    // record buffers when those are large enough: their records are dead by now, and everything runs on this stream or on
+    // the auxiliary stream forked from it.  30 GB less at 50 M reads.
+    const size_t workBytes = sizeof(ExRes) * 2 * (nAlns + 1);
+    const size_t segBytes = (sizeof(ExSeg) * (nAlns + n + 1) + 255) & ~(size_t) 255;
+    const size_t listBytes = sizeof(unsigned) * 2 * (n + 1) + sizeof(uint2) * (nAlns + 1) + sizeof(ExState) * (n + 1) + 256;
+    const bool workInRecB = ctx->recB.cap >= workBytes;
+    const bool segsInRecA = ctx->recA.cap >= segBytes + listBytes;
+    if (!workInRecB) PG_TRY(ctx->exWork.reserve(workBytes));
+    if (!segsInRecA) { PG_TRY(ctx->exSegs.reserve(segBytes)); PG_TRY(ctx->exLists.reserve(listBytes)); }
+    ExRes *heapBuf = workInRecB ? ctx->recB.as<ExRes>() : ctx->exWork.as<ExRes>();
     ExRes *parkBuf = heapBuf + (nAlns + 1);
+    ExSeg *segBuf = segsInRecA ? ctx->recA.as<ExSeg>() : ctx->exSegs.as<ExSeg>();
     // work lists of the wavefront
-    PG_TRY(ctx->exLists.reserve(sizeof(unsigned) * 2 * (n + 1) + sizeof(uint2) * (nAlns + 1) + sizeof(ExState) * (n + 1) + 256));
-    unsigned char *lb = ctx->exLists.as<unsigned char>();
+    unsigned char *lb = segsInRecA ? ctx->recA.as<unsigned char>() + segBytes : ctx->exLists.as<unsigned char>();
     ExState *states = (ExState *) lb;
     uint2 *work = (uint2 *) (lb + ((sizeof(ExState) * (n + 1) + 15) & ~(size_t) 15));
     unsigned *listA = (unsigned *) ((unsigned char *) work + ((sizeof(uint2) * (nAlns + 1) + 15) & ~(size_t) 15));
@@ -999,7 +1007,7 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
             PG_CUDA(cudaStreamWaitEvent(rs, ctx->evAuxFork, 0));
         }
         extend_query_warp_kernel<<<std::min<unsigned>((active + 7) / 8, NUM_SMS * 32), 256, 0, s>>>(
-            *db, d_alns, alnStart, alnCount, c, cur, d_listCnt + curIdx, ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
+            *db, d_alns, alnStart, alnCount, c, cur, d_listCnt + curIdx, segBuf, segCount, outLen, ext, used);
         ctx->launches++;
         if (!needHeap) active = 0;
         lap("extend_query_warp");
@@ -1013,16 +1021,16 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
             // heap replay for the rest (both kernels read the same list and skip the queries of the other class)
             extend_round_warp_kernel<<<std::min<unsigned>((active + 7) / 8, NUM_SMS * 32), 256, 0, rs>>>(
                 *db, d_alns, alnStart, alnCount, c, round == 0, cur, d_listCnt + curIdx, nxt, d_listCnt + (1 - curIdx), work, d_cnt, states,
-                parkBuf, ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
+                parkBuf, segBuf, segCount, outLen, ext, used);
             ctx->launches++;
         }
         if (needHeap) {
             extend_round_kernel<<<(active + 127) / 128, 128, 0, rs>>>(*db, d_alns, alnStart, alnCount, c, round == 0, cur, d_listCnt + curIdx,
                                                                      nxt, d_listCnt + (1 - curIdx), work, d_cnt, states, heapBuf, parkBuf,
-                                                                     ctx->exSegs.as<ExSeg>(), segCount, outLen, ext, used);
+                                                                     segBuf, segCount, outLen, ext, used);
             ctx->launches++;
         }
-        extend_rescore_kernel<<<NUM_SMS * 8, 256, 0, rs>>>(*db, alnStart, c, work, d_cnt, states, parkBuf, ctx->exSegs.as<ExSeg>());
+        extend_rescore_kernel<<<NUM_SMS * 8, 256, 0, rs>>>(*db, alnStart, c, work, d_cnt, states, parkBuf, segBuf);
         ctx->launches += 1;
         PG_TRY(read_back_on(ctx, rs, hCnt, d_listCnt + (1 - curIdx), sizeof(unsigned)));
         active = hCnt[0];
@@ -1053,7 +1061,7 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     unsigned char *outExt = nullptr;
     PG_CUDA(cudaMallocAsync(&outExt, h[1] + 1, s));
     lap("cudaMallocAsync x5");
-    materialize_kernel<<<NUM_SMS * 16, 256, 0, s>>>(*db, alnStart, ctx->exSegs.as<ExSeg>(), segCount, outLen, outOff, keep, keepIdx, ext,
+    materialize_kernel<<<NUM_SMS * 16, 256, 0, s>>>(*db, alnStart, segBuf, segCount, outLen, outOff, keep, keepIdx, ext,
                                                     out->data, out->offsets, out->lens, out->keys, outExt);
     ctx->launches++;
     cudaEventRecord(ctx->ev[EV_EX_END], s);

@@ -56,6 +56,16 @@ struct pg_context {
     unsigned ownLo = 0, ownHi = 0xFFFFFFFFu;
     pg::Rec *shardPairs = nullptr;
     uint64_t shardPairCount = 0;
+    // multi-GPU data plane (pg_shard.cu): one process per GPU, NCCL communicator over NVLink / NVSwitch
+    void *comm = nullptr;                      // ncclComm_t
+    int rank = 0, world = 1;
+    cudaEvent_t evXchg[4] = {nullptr, nullptr, nullptr, nullptr};   // begin / end of the two exchanges of a step
+    pg::DevBuf commWs;                         // counts matrix, histogram, bounds
+    unsigned long long firstKmerOverride = 0;  // nt: the job-wide smallest k-mer (all-reduced), see hash_group_kernel
+    bool useFirstKmerOverride = false;
+    float lastExchangeMs[2] = {0, 0};
+    uint64_t lastExchangeBytes[2] = {0, 0};
+    uint32_t lastBounds[257];
 };
 
 namespace pg {
@@ -89,4 +99,11 @@ void seqdb_release(pg_seqdb *db, cudaStream_t s);
 int read_back(Context *ctx, void *host, const void *dev, size_t bytes);
 int read_back_on(Context *ctx, cudaStream_t stream, void *host, const void *dev, size_t bytes);   // same on another stream of the context
 int alloc_pinned(size_t bytes, void **out);        // pooled pinned host memory, released with pg_free_host
+// call bracketing shared by pg_api.cu and pg_shard.cu
+void begin_call(Context *ctx);
+void end_call(Context *ctx);
+void end_shard_phase(Context *ctx, bool first);
+int hits_to_host_overlapped(Context *ctx, const pg_hit *d, uint64_t n, pg_hit **out);
+int alns_to_host_overlapped(Context *ctx, const pg_aln *d, uint64_t n, pg_aln **out);
+void km_min_kmer_slot(Context *ctx, unsigned long long **d_min);
 }  // namespace pg

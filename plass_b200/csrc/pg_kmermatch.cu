@@ -1966,14 +1966,17 @@ static int km_group_bucketed(Context *ctx, const KmConst &c, uint64_t nRecords, 
     unsigned *d_bigList = ctx->blockCounts.as<unsigned>() + 4;
     unsigned *d_bigCnt = ctx->blockCounts.as<unsigned>();
     PG_CUDA(cudaMemsetAsync(d_bigCnt, 0, sizeof(unsigned), s));
+    // multi-GPU: the smallest k-mer of the whole job (all-reduced by pg_shard_iteration), not of this rank's share
+    unsigned long long *d_first = d_min;
+    km_min_kmer_slot(ctx, &d_first);
     if (bigFirst) {
         hash_group_kernel<HG_TABLE_BIG, HG_ITEMS_BIG, 0><<<std::min<unsigned>(nBuckets, NUM_SMS * 32), HG_THREADS, 0, s>>>(
-            sorted, d_start, d_end, nBuckets, hashMask, d_min, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_over);
+            sorted, d_start, d_end, nBuckets, hashMask, d_first, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_over);
     } else {
         hash_group_kernel<HG_TABLE_SMALL, HG_ITEMS_SMALL, 0><<<std::min<unsigned>(nBuckets, NUM_SMS * 64), HG_THREADS, 0, s>>>(
-            sorted, d_start, d_end, nBuckets, hashMask, d_min, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_over);
+            sorted, d_start, d_end, nBuckets, hashMask, d_first, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_over);
         hash_group_kernel<HG_TABLE_BIG, HG_ITEMS_BIG, 1><<<NUM_SMS * 4, HG_THREADS, 0, s>>>(
-            sorted, d_start, d_end, nBuckets, hashMask, d_min, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_over);
+            sorted, d_start, d_end, nBuckets, hashMask, d_first, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_over);
     }
     ctx->launches += 3;
     cudaEventRecord(ctx->ev[EV_GROUP_END], s);
@@ -2441,7 +2444,7 @@ int km_shard_reduce(Context *ctx, const pg_seqdb *db, const void *d_pairs, uint6
     cudaStream_t s = ctx->stream;
     PG_TRY(ctx->recA.reserve(sizeof(Rec) * (nPairs + 1)));
     PG_TRY(ctx->recB.reserve(sizeof(Rec) * (nPairs + 1)));
-    if (nPairs) PG_CUDA(cudaMemcpyAsync(ctx->recA.p, d_pairs, sizeof(Rec) * nPairs, cudaMemcpyDeviceToDevice, s));
+    if (nPairs && d_pairs != ctx->recA.p) PG_CUDA(cudaMemcpyAsync(ctx->recA.p, d_pairs, sizeof(Rec) * nPairs, cudaMemcpyDeviceToDevice, s));
     cudaEventRecord(ctx->ev[EV_GROUP_END], s);
     if (nPairs == 0) { cudaEventRecord(ctx->ev[EV_SORT2_END], s); cudaEventRecord(ctx->ev[EV_REDUCE_END], s); }
     PG_TRY(km_reduce(ctx, db, ctx->recA.as<Rec>(), ctx->recB.as<Rec>(), nPairs, d_hits, nHits));

@@ -1,9 +1,11 @@
 """Multi-GPU assemble iteration: one process per GPU, the sequence DB replicated in every HBM.  Each rank
-extracts the k-mers of its slice of the sequences; all-to-all #1 routes the k-mer records to the rank that owns
-the k-mer (hash of the k-mer), which sorts and groups them; all-to-all #2 routes the (rep, target, diagonal) pair
+extracts the k-mers of its slice of the sequences; exchange #1 routes the k-mer records to the rank that owns
+the k-mer (hash of the k-mer), which sorts and groups them; exchange #2 routes the (rep, target, diagonal) pair
 records to the rank that owns the representative, which finishes kmermatcher, rescorediagonal and the extension
-for its queries.  torch.distributed (NCCL over NVLink) is only the transport: the
-records that cross the links are produced and consumed by the CUDA kernels of libplassgpu.so."""
+for its queries.  The data plane is C++ (plass_b200/csrc/pg_shard.cu:
+pg_shard_iteration, grouped ncclSend / ncclRecv between the stages' record buffers, DB broadcast / all-gather);
+this module is the launcher-side glue: it hands the NCCL unique id from rank 0 to the others through
+torch.distributed and keeps the Python mirrors of the host arithmetic for the CPU tests."""
 import ctypes as C
 import time
 
@@ -115,57 +117,120 @@ def upload_sliced(ctx, dist, db, rank, world):
 
 
 class ShardedIteration:
+    """The C++ data plane of one rank (pg_comm_init + pg_shard_iteration)."""
+
     def __init__(self, ctx, dist, rank, world):
+        import torch
         self.ctx, self.dist, self.rank, self.world = ctx, dist, rank, world
         self._t = {}
         self.last_d2h_bytes = 0
-        self.exchange_bytes = 0
+        self._phases = []
+        # the NCCL unique id travels from rank 0 to the others over the launcher's own process group
+        uid = ctx.comm_unique_id() if rank == 0 else bytes(api.COMM_ID_BYTES)
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor(list(uid), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0)
+        ctx.comm_init(rank, world, bytes(t.cpu().numpy().tobytes()))
 
-    def _exchange(self, counts):
-        """All-to-all of the records the preceding phase left on the device; returns (recv buffer, n received)."""
-        import torch
-        ctx, dist = self.ctx, self.dist
-        n_send = sum(counts)
-        send = torch.empty(max(n_send, 1) * REC_BYTES, dtype=torch.uint8, device="cuda")
-        ctx.shard_export(send.data_ptr(), n_send)
-        self._ev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
-        self._ev[-1][0].record()
-        send_counts = torch.tensor(counts, dtype=torch.int64, device="cuda")
-        recv_counts = torch.empty(self.world, dtype=torch.int64, device="cuda")
-        dist.all_to_all_single(recv_counts, send_counts)
-        rc = [int(x) for x in recv_counts.tolist()]
-        n_recv = sum(rc)
-        recv = torch.empty(max(n_recv, 1) * REC_BYTES, dtype=torch.uint8, device="cuda")
-        dist.all_to_all_single(recv[: n_recv * REC_BYTES], send[: n_send * REC_BYTES], split_bytes(rc), split_bytes(counts))
-        self._ev[-1][1].record()
-        torch.cuda.synchronize()
-        self.exchange_bytes += (n_send - counts[self.rank]) * REC_BYTES
-        return recv, n_recv
+    def describe(self):
+        return ("%d ranks, one process per GPU, C++ data plane over NCCL (pg_shard_iteration): sequence-sliced extraction, grouped ncclSend/ncclRecv of "
+                "k-mer records to the k-mer owner, sort #1 + assignGroup, all-reduced work histogram -> equal-work key ranges, grouped ncclSend/ncclRecv "
+                "of candidate pairs to the representative's owner, sort #2 + best diagonal + rescore + extension of the owned queries" % self.world)
+
+    def build_and_broadcast(self, build_fn):
+        """rank 0 builds the job's DB on its GPU (build_fn() -> DeviceSeqDB), every rank gets a replica over NVLink."""
+        src = build_fn() if self.rank == 0 else None
+        out = self.ctx.shard_broadcast_db(src, 0)
+        if src is not None:
+            src.free()
+        return out
 
     def step(self, ddb, kp, rp, ep, download=False):
-        import torch
+        """One iteration; returns this rank's slice of the new DB (DeviceSeqDB)."""
         ctx = self.ctx
-        self._ev, self.exchange_bytes = [], 0
-        counts = ctx.shard_extract(ddb, kp, self.rank, self.world)
-        recv, n_recv = self._exchange(counts)                       # all-to-all #1: k-mer records -> k-mer owner
-        hist = torch.from_numpy(ctx.shard_group(ddb, kp, recv.data_ptr(), n_recv).view(np.int64)).cuda()
-        del recv
-        self.dist.all_reduce(hist)                                   # work per slice of the representative key space
-        bounds = balanced_bounds(hist.cpu().numpy(), ddb.max_key, self.world)
-        counts = ctx.shard_route(bounds)
-        recv, n_recv = self._exchange(counts)                       # all-to-all #2: pair records -> representative owner
-        own = (bounds[self.rank], bounds[self.rank + 1])
-        self.bounds = bounds
-        out, hits, alns = ctx.shard_finish(ddb, recv.data_ptr(), n_recv, own, rp, ep, want_intermediates=download)
-        t2 = ctx.timings()
-        t2["exchange_ms"] = sum(a.elapsed_time(b) for a, b in self._ev)
-        t2["total_ms"] = t2["total_ms"] + t2["exchange_ms"]
-        self._t = t2
+        out, own, hits, alns = ctx.shard_iteration(ddb, kp, rp, ep, want_intermediates=download)
+        self._t = ctx.timings()
+        self.own = own
         if download:
             host = out.download()
             self.last_d2h_bytes = int(hits.nbytes + alns.nbytes + host.data.nbytes + host.offsets.nbytes + host.lens.nbytes + host.keys.nbytes)
-            del hits, alns, host
+            self.last_host = (hits, alns, host)
         return out
 
     def timings(self):
-        return self._t
+        t = dict(self._t)
+        ms, nb = self.ctx.shard_exchange_stats()
+        t["exchange1_ms"], t["exchange2_ms"] = ms
+        t["exchange1_bytes_sent"], t["exchange2_bytes_sent"] = nb
+        return t
+
+    def pinned_slice(self, ddb):
+        """This rank's slice of the sequences of the replicated DB as a host DB in pinned memory (offsets rebased to 0)."""
+        import torch
+        host = ddb.download()
+        lo, hi = slice_bounds(host.n, self.world)[self.rank]
+        b0 = int(host.offsets[lo]) if lo < host.n else int(host.data.nbytes)
+        b1 = int(host.offsets[hi]) if hi < host.n else int(host.data.nbytes)
+
+        def pin(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a).view(dt)).pin_memory().numpy().view(a.dtype)
+        from . import mmseqsdb
+        return mmseqsdb.DB(pin(host.data[b0:b1], np.uint8), pin(host.keys[lo:hi], np.int32),
+                           pin((host.offsets[lo:hi] - np.uint64(b0)).astype(np.uint64), np.int64), pin(host.lens[lo:hi], np.int32), host.dbtype)
+
+    def upload_sliced(self, pinned):
+        """PCIe carries only this rank's slice, NVLink the rest (pg_shard_allgather_db); returns the replicated DeviceSeqDB."""
+        sl = self.ctx.upload(pinned)
+        full = self.ctx.shard_allgather_db(sl)
+        sl.free()
+        return full
+
+    def e2e_phases(self):
+        return None
+
+    def verify_against_single_gpu(self, ddb, kp, rp, ep):
+        """The sharded iteration's results (hits, alignments, all-gathered new DB) against a single-GPU run of the same
+        replicated DB on rank 0.  Counts and order-independent checksums of the hit / alignment records are summed over
+        the ranks; the all-gathered DB (the next iteration's input) must equal the single-GPU output byte for byte."""
+        import torch
+        ctx, dist = self.ctx, self.dist
+        out, own, hits, alns = ctx.shard_iteration(ddb, kp, rp, ep, want_intermediates=True)
+        full = ctx.shard_allgather_db(out)
+        out.free()
+        mine = np.array([len(hits), len(alns), record_checksum(hits), record_checksum(alns)], dtype=np.uint64)
+        t = torch.from_numpy(mine.view(np.int64)).cuda()
+        dist.all_reduce(t)                       # int64 sums wrap like uint64 sums
+        tot = t.cpu().numpy().view(np.uint64)
+        del hits, alns
+        res = None
+        if self.rank == 0:
+            g = full.download()
+            full.free()
+            one, h1, a1 = ctx.assemble_iteration(ddb, kp, rp, ep, want_intermediates=True)
+            o = one.download()
+            one.free()
+            want = np.array([len(h1), len(a1), record_checksum(h1), record_checksum(a1)], dtype=np.uint64)
+            same_db = (np.array_equal(g.keys, o.keys) and np.array_equal(g.lens, o.lens) and np.array_equal(g.offsets, o.offsets)
+                       and np.array_equal(g.data, o.data))
+            res = {"ranks": self.world, "hits": int(tot[0]), "hits_single_gpu": int(want[0]), "alignments": int(tot[1]), "alignments_single_gpu": int(want[1]),
+                   "hit_checksum_equal": bool(tot[2] == want[2]), "alignment_checksum_equal": bool(tot[3] == want[3]),
+                   "gathered_db_equals_single_gpu_db": bool(same_db), "sequences": int(o.n)}
+            res["equal"] = bool(tot[0] == want[0] and tot[1] == want[1] and res["hit_checksum_equal"] and res["alignment_checksum_equal"] and same_db)
+        else:
+            full.free()
+        dist.barrier()
+        return res
+
+
+def record_checksum(recs):
+    """Order-independent checksum of an array of POD records: sum over the records of a mixed hash of their 64-bit words
+    (wrap-around uint64 arithmetic)."""
+    if len(recs) == 0:
+        return np.uint64(0)
+    w = np.ascontiguousarray(recs).view(np.uint64).reshape(len(recs), -1)
+    with np.errstate(over="ignore"):
+        h = np.zeros(len(recs), dtype=np.uint64)
+        for j in range(w.shape[1]):
+            h = (h ^ w[:, j]) * np.uint64(0x9E3779B97F4A7C15)
+            h ^= h >> np.uint64(29)
+        return np.uint64(h.sum(dtype=np.uint64))

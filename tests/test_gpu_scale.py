@@ -1,0 +1,124 @@
+"""Parity at scale (-m gpu): >= 1 M synthetic reads through the GPU drop-in commands against the UNMODIFIED reference
+binaries (oracle/_ref/bin/plass, penguin) run on the same box on the same DB.  The golden fixtures hold a few thousand
+sequences; these inputs exercise what they cannot: multi-tile look-back chains, ~10^5 buckets, bucket spill lists,
+representatives with hundreds of pairs, 10^7-record sorts.
+
+  aa   1 M reads -> aa_6f_start_long (GPU six-frame pipeline) -> kmermatcher / rescorediagonal / assembleresults, two
+       chained iterations (hash shift 67 then 68, --include-only-extendable 0 then 1, as Assembler.cpp:99-110)
+  nt   1 M reads, penguin's k = 22 path, two chained iterations with cyclecheck's input (the assembly) compared too
+
+Comparison = plass_b200_cli dbdiff (key -> entry bytes).  aa: zero mismatching entries (E-value column: last printed digit).
+nt: prefilter lines may differ in the SIGN of the score only for targets of the single k-mer group whose strand the reference
+leaves uninitialised (kmermatcher.cpp:463) -- bounded by a handful of lines; everything downstream of
+those lines is excluded, everything else must be identical."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import ROOT
+from plass_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+CLI = os.path.join(ROOT, "plass_b200", "plass_b200_cli")
+REF = os.path.join(ROOT, "oracle", "_ref", "bin")
+N_READS = int(os.environ.get("PLASS_SCALE_READS", "1000000"))
+THREADS = str(os.cpu_count() or 1)
+
+
+def run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, "%s\n%s" % (" ".join(cmd), r.stdout[-3000:])
+    return r.stdout
+
+
+def dbdiff(a, b, mode):
+    r = subprocess.run([CLI, "dbdiff", a, b, "--mode", mode], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    line = [x for x in r.stdout.splitlines() if x.startswith("{")]
+    assert line, r.stdout[-2000:]
+    return json.loads(line[-1])
+
+
+def write_db(path, db):
+    import bench
+    bench.write_db_fast(path, db)
+
+
+def km_flags(nucl, it):
+    if nucl:
+        return ("--sub-mat nucl:nucleotide.out,aa:blosum62.out --alph-size 5 --min-seq-id 0.99 --kmer-per-seq 60 --spaced-kmer-mode 0 --kmer-per-seq-scale 0.100 "
+                "--adjust-kmer-len 0 --mask 0 --mask-lower-case 0 --cov-mode 0 -k 22 -c 0 --max-seq-len 200000 --hash-shift %d --split-memory-limit 0 "
+                "--include-only-extendable 1 --ignore-multi-kmer 1 --compressed 0 -v 3" % 67).split()      # Nuclassembler.cpp keeps one KMERMATCHER_PAR
+    return ("--sub-mat nucl:nucleotide.out,aa:blosum62.out --alph-size 13 --min-seq-id 0.9 --kmer-per-seq 60 --spaced-kmer-mode 0 --kmer-per-seq-scale nucl:0.200,aa:0.000 "
+            "--adjust-kmer-len 0 --mask 0 --mask-lower-case 0 --cov-mode 0 -k 14 -c 0 --max-seq-len 65535 --hash-shift %d --split-memory-limit 0 "
+            "--include-only-extendable %d --ignore-multi-kmer 1 --compressed 0 -v 3" % (67 + (it + 1) // 2, 1 if it > 0 else 0)).split()
+
+
+def rs_flags(nucl):
+    return ("--sub-mat nucl:nucleotide.out,aa:blosum62.out --rescore-mode 3 --wrapped-scoring 0 --filter-hits 0 -e 1e-05 -c 0 -a 0 --cov-mode 0 --min-seq-id %s "
+            "--min-aln-len 0 --seq-id-mode 0 --add-self-matches 0 --sort-results 0 --db-load-mode 0 --compressed 0 -v 3" % ("0.99" if nucl else "0.9")).split()
+
+
+def ex_flags(nucl):
+    return ("--min-seq-id %s --max-seq-len %s --keep-target 1 -v 3 --rescore-mode 3" % (("0.99", "200000") if nucl else ("0.9", "65535"))).split()
+
+
+@pytest.mark.parametrize("nucl", [False, True], ids=["aa", "nt"])
+def test_million_reads_two_iterations_match_the_reference_binary(nucl, tmp_path):
+    tool = "penguin" if nucl else "plass"
+    ref_bin = os.path.join(REF, tool)
+    if not os.path.exists(ref_bin):
+        pytest.skip("reference binary oracle/_ref/bin/%s not available on this box" % tool)
+    w = lambda x: str(tmp_path / x)  # noqa: E731
+    reads = synth.make_reads_fast(N_READS, seed=11 if nucl else 12)
+    ctx = api.Context(0)
+    try:
+        if nucl:
+            write_db(w("in_0"), synth.nucleotide_db(reads))
+        else:
+            dn = ctx.upload(synth.nucleotide_db(reads))
+            frag = ctx.six_frame_fragments(dn)
+            write_db(w("in_0"), frag.download())
+            frag.free(); dn.free()
+    finally:
+        ctx.close()
+    del reads
+    ex_cmd = "nuclassembleresults" if nucl else "assembleresults"
+    report = {}
+    for it in range(2):
+        seq = w("in_%d" % it)
+        # the reference's three steps
+        run([ref_bin, "kmermatcher", seq, w("r_pref_%d" % it)] + km_flags(nucl, it) + ["--threads", THREADS])
+        run([ref_bin, "rescorediagonal", seq, seq, w("r_pref_%d" % it), w("r_aln_%d" % it)] + rs_flags(nucl) + ["--threads", THREADS])
+        run([ref_bin, ex_cmd, seq, w("r_aln_%d" % it), w("in_%d" % (it + 1))] + ex_flags(nucl) + ["--threads", THREADS])
+        # the GPU drop-in on the same inputs
+        run([CLI, "kmermatcher", seq, w("g_pref_%d" % it)] + km_flags(nucl, it) + ["--threads", THREADS])
+        d_pref = dbdiff(w("g_pref_%d" % it), w("r_pref_%d" % it), "pref" if nucl else "exact")
+        # downstream steps take the REFERENCE's prefilter / alignment DB, so that a tolerated strand sign does not propagate
+        run([CLI, "rescorediagonal", seq, seq, w("r_pref_%d" % it), w("g_aln_%d" % it)] + rs_flags(nucl) + ["--threads", THREADS])
+        d_aln = dbdiff(w("g_aln_%d" % it), w("r_aln_%d" % it), "aln")
+        run([CLI, ex_cmd, seq, w("r_aln_%d" % it), w("g_asm_%d" % it)] + ex_flags(nucl) + ["--threads", THREADS])
+        d_asm = dbdiff(w("g_asm_%d" % it), w("in_%d" % (it + 1)), "exact")
+        report[it] = (d_pref, d_aln, d_asm)
+        print("iteration %d: pref %s\n             aln %s\n             asm %s" % (it, d_pref, d_aln, d_asm))
+        for d in (d_pref, d_aln, d_asm):
+            assert d["mismatching"] == 0 and d["only_in_a"] == 0 and d["only_in_b"] == 0 and d["dbtype_equal"], (it, d)
+        assert d_pref["entries_b"] >= (N_READS if nucl else N_READS * 3 // 2)
+        if nucl:
+            assert d_pref["tolerated_lines"] <= 64, d_pref      # one k-mer group's targets
+        else:
+            assert d_pref["tolerated"] == 0
+        # E-values: the fp64 exp / erfc of CUDA vs glibc may flip the last printed digit of a few values
+        assert d_aln["tolerated_lines"] <= max(10, d_aln["entries_b"] // 10000), d_aln
+    # the fused command on iteration 0's input reproduces all three DBs as well
+    union = km_flags(nucl, 0) + ["--rescore-mode", "3", "--wrapped-scoring", "0", "--filter-hits", "0", "-e", "1e-05", "-a", "0", "--min-aln-len", "0",
+                                  "--seq-id-mode", "0", "--add-self-matches", "0", "--sort-results", "0", "--db-load-mode", "0", "--keep-target", "1"]
+    run([CLI, "assembleiteration", w("in_0"), w("f_pref"), w("f_aln"), w("f_asm")] + union + ["--threads", THREADS])
+    f_pref = dbdiff(w("f_pref"), w("r_pref_0"), "pref" if nucl else "exact")
+    assert f_pref["mismatching"] == 0, f_pref
+    if not nucl:
+        f_aln, f_asm = dbdiff(w("f_aln"), w("r_aln_0"), "aln"), dbdiff(w("f_asm"), w("in_1"), "exact")
+        assert f_aln["mismatching"] == 0 and f_asm["mismatching"] == 0, (f_aln, f_asm)
