@@ -111,6 +111,7 @@ typedef struct {
     float sort1_scatter_ms;    /* device time of the radix scatter launches of sort #1 (events around them) */
     uint32_t sort1_passes;     /* number of scatter launches in sort #1 */
     uint32_t splits;           /* hash-range splits of the kmermatcher stage (1 = everything at once) */
+    uint64_t spilled_records;  /* k-mer records of buckets beyond the shared-memory hash join (sorted and grouped apart) */
 } pg_timings;
 
 const char *pg_last_error(void);

@@ -55,7 +55,7 @@ class Timings(C.Structure):
                                          "extend_ms", "exchange_ms", "total_ms")] + \
                [(n, C.c_uint64) for n in ("n_kmer_records", "n_pair_records", "n_hits", "n_alns", "n_extended",
                                           "kernel_launches", "sort1_bytes")] + \
-               [("sort1_scatter_ms", C.c_float), ("sort1_passes", C.c_uint32), ("splits", C.c_uint32)]
+               [("sort1_scatter_ms", C.c_float), ("sort1_passes", C.c_uint32), ("splits", C.c_uint32), ("spilled_records", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

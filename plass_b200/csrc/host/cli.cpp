@@ -23,6 +23,7 @@ int main(int argc, const char **argv) {
     if (!strcmp(cmd, "translatenucs")) return translatenucs(argc - 2, argv + 2);
     if (!strcmp(cmd, "assembleiteration")) return assembleiteration(argc - 2, argv + 2);
     if (!strcmp(cmd, "dbdiff")) return dbdiff(argc - 2, argv + 2);
+    if (!strcmp(cmd, "iotest")) return iotest(argc - 2, argv + 2);
     fprintf(stderr, "%s: not one of the GPU hot-path commands\n", cmd);
     return EXIT_FAILURE;
 }

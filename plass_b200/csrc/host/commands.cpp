@@ -91,6 +91,20 @@ void checkSubMat(const Flags &f) {
         die("--sub-mat " + it->second + ": only the built-in nucleotide.out / blosum62.out tables are available on the GPU path");
 }
 
+// wall-clock of the phases of a command, printed next to the reference's "Time for processing" line
+struct Phases {
+    std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    std::string text;
+    void lap(const char *name) {
+        const auto now = std::chrono::steady_clock::now();
+        char b[96];
+        snprintf(b, sizeof(b), "%s%s %lld ms", text.empty() ? "" : ", ", name, (long long) std::chrono::duration_cast<std::chrono::milliseconds>(now - last).count());
+        text += b;
+        last = now;
+    }
+    void report() const { printf("Phases: %s (%d host threads)\n", text.c_str(), mmdb::hostThreads()); }
+};
+
 struct Timer {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     void report() const {   // same wording as the reference (Application.cpp:38-43)
@@ -150,69 +164,131 @@ const std::set<std::string> RS_FLAGS = {"--sub-mat", "--rescore-mode", "--wrappe
     "--min-seq-id", "--min-aln-len", "--seq-id-mode", "--add-self-matches", "--sort-results", "--db-load-mode", "--threads", "--compressed", "-v"};
 const std::set<std::string> EX_FLAGS = {"--min-seq-id", "--max-seq-len", "--keep-target", "--threads", "-v", "--rescore-mode", "--sub-mat", "--db-load-mode", "--compressed"};
 
-// Entries [0, n) cut into one contiguous range per host thread; fn(thread, lo, hi) fills a per-thread vector, the vectors
-// are concatenated in thread order (= key order).
+// POD array without value-initialisation: the parsing threads are the first to touch their part of it
+template <class T>
+struct PodArray {
+    T *p = nullptr;
+    size_t n = 0;
+    PodArray() = default;
+    explicit PodArray(size_t count) : p((T *) malloc(sizeof(T) * (count + 1))), n(count) { if (!p) die("out of host memory"); }
+    PodArray(PodArray &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    PodArray(const PodArray &) = delete;
+    PodArray &operator=(const PodArray &) = delete;
+    ~PodArray() { free(p); }
+    const T *data() const { return p; }
+    size_t size() const { return n; }
+};
+
+// Text entries -> records, by all host threads.  The entries are cut into contiguous ranges of (nearly) equal BYTES; a first
+// sweep counts the lines of every range (memchr), so every thread parses straight into its slice of the one result array.
 template <class T, class Fn>
-std::vector<T> parseParallel(size_t n, Fn fn) {
+PodArray<T> parseParallel(const mmdb::Reader &db, size_t skipLinesPerEntry, Fn parseEntry) {
     const int nT = mmdb::hostThreads();
-    std::vector<std::vector<T>> part((size_t) nT);
+    const size_t n = db.size();
+    std::vector<size_t> cut((size_t) nT + 1, n), cnt((size_t) nT + 1, 0);
+    cut[0] = 0;
+    if (n) {
+        // equal BYTES per range (entries in key order are not in file order: cumulate the lengths, not the offsets)
+        const size_t blk = 4096, nBlk = (n + blk - 1) / blk;
+        std::vector<uint64_t> blkBytes(nBlk + 1, 0);
+#pragma omp parallel for num_threads(nT) schedule(static)
+        for (size_t b = 0; b < nBlk; b++) {
+            uint64_t sum = 0;
+            for (size_t i = b * blk; i < std::min(n, (b + 1) * blk); i++) sum += db.lens[i];
+            blkBytes[b + 1] = sum;
+        }
+        for (size_t b = 0; b < nBlk; b++) blkBytes[b + 1] += blkBytes[b];
+        for (int t = 1; t < nT; t++) {
+            const uint64_t want = blkBytes[nBlk] * (uint64_t) t / (uint64_t) nT;
+            const size_t b = (size_t) (std::lower_bound(blkBytes.begin(), blkBytes.end(), want) - blkBytes.begin());
+            cut[(size_t) t] = std::max(cut[(size_t) t - 1], std::min(n, b * blk));
+        }
+    }
 #pragma omp parallel for num_threads(nT) schedule(static, 1)
-    for (int t = 0; t < nT; t++) fn(part[(size_t) t], n * (size_t) t / (size_t) nT, n * (size_t) (t + 1) / (size_t) nT);
-    std::vector<size_t> at((size_t) nT + 1, 0);
-    for (int t = 0; t < nT; t++) at[(size_t) t + 1] = at[(size_t) t] + part[(size_t) t].size();
-    std::vector<T> all(at[(size_t) nT]);
+    for (int t = 0; t < nT; t++) {
+        size_t c = 0;
+        for (size_t i = cut[(size_t) t]; i < cut[(size_t) t + 1]; i++) {
+            const char *p = db.entry(i), *e = p + (db.lens[i] ? db.lens[i] - 1 : 0);
+            size_t lines = 0;
+            while (p < e) { const char *nl = (const char *) memchr(p, '\n', (size_t) (e - p)); lines++; if (!nl) break; p = nl + 1; }
+            c += lines > skipLinesPerEntry ? lines - skipLinesPerEntry : 0;
+        }
+        cnt[(size_t) t + 1] = c;
+    }
+    for (int t = 0; t < nT; t++) cnt[(size_t) t + 1] += cnt[(size_t) t];
+    PodArray<T> all(cnt[(size_t) nT]);
 #pragma omp parallel for num_threads(nT) schedule(static, 1)
-    for (int t = 0; t < nT; t++)
-        if (!part[(size_t) t].empty()) memcpy(all.data() + at[(size_t) t], part[(size_t) t].data(), sizeof(T) * part[(size_t) t].size());
+    for (int t = 0; t < nT; t++) {
+        T *out = all.p + cnt[(size_t) t];
+        for (size_t i = cut[(size_t) t]; i < cut[(size_t) t + 1]; i++) out = parseEntry(i, out);
+        if (out != all.p + cnt[(size_t) t + 1]) die("malformed result DB: a line count changed between the two parse sweeps");
+    }
     return all;
 }
 
+// decimal integer / the fields of a result line; faster than strtol for the well-formed lines the reference writes
+static inline const char *getU(const char *s, uint32_t &v) {
+    while (*s == ' ' || *s == '\t') s++;
+    uint32_t x = 0;
+    while (*s >= '0' && *s <= '9') { x = x * 10 + (uint32_t) (*s - '0'); s++; }
+    v = x;
+    return s;
+}
+static inline const char *getI(const char *s, int32_t &v) {
+    while (*s == ' ' || *s == '\t') s++;
+    const bool neg = *s == '-';
+    if (neg || *s == '+') s++;
+    uint32_t x;
+    s = getU(s, x);
+    v = neg ? -(int32_t) x : (int32_t) x;
+    return s;
+}
+
 // Matcher::parseAlignmentRecord over a whole alignment DB (Matcher.cpp:190-320), entries in key order
-std::vector<pg_aln> parseAlnDb(const mmdb::Reader &aln) {
-    return parseParallel<pg_aln>(aln.size(), [&](std::vector<pg_aln> &alns, size_t lo, size_t hi) {
-        for (size_t i = lo; i < hi; i++) {
-            const char *s = aln.entry(i);
-            while (*s) {
-                pg_aln a; a.query = aln.keys[i];
-                char *e;
-                a.target = (uint32_t) strtoul(s, &e, 10);
-                a.bits = (int32_t) strtol(e, &e, 10);
-                a.seq_id = (float) strtod(e, &e);
-                a.evalue = strtod(e, &e);
-                a.q_start = (int32_t) strtol(e, &e, 10); a.q_end = (int32_t) strtol(e, &e, 10); a.q_len = (int32_t) strtol(e, &e, 10);
-                a.db_start = (int32_t) strtol(e, &e, 10); a.db_end = (int32_t) strtol(e, &e, 10); a.db_len = (int32_t) strtol(e, &e, 10);
-                alns.push_back(a);
-                while (*e && *e != '\n') e++;
-                s = *e ? e + 1 : e;
-            }
+PodArray<pg_aln> parseAlnDb(const mmdb::Reader &aln) {
+    return parseParallel<pg_aln>(aln, 0, [&](size_t i, pg_aln *out) {
+        const char *s = aln.entry(i);
+        while (*s) {
+            pg_aln a; a.query = aln.keys[i];
+            char *e;
+            s = getU(s, a.target);
+            s = getI(s, a.bits);
+            a.seq_id = strtof(s, &e);              // fastSeqIdToBuffer prints at most three decimals: float parsing is exact for them
+            a.evalue = strtod(e, &e);
+            s = getI(e, a.q_start); s = getI(s, a.q_end); s = getI(s, a.q_len);
+            s = getI(s, a.db_start); s = getI(s, a.db_end); s = getI(s, a.db_len);
+            *out++ = a;
+            while (*s && *s != '\n') s++;
+            if (*s) s++;
         }
+        return out;
     });
 }
 
 // QueryMatcher::parsePrefilterHits (QueryMatcher.h:81-112) over a kmermatcher result; the first line of every entry
 // must be the self line "key\t0\t0"
-std::vector<pg_hit> parsePrefDb(const mmdb::Reader &pref) {
-    return parseParallel<pg_hit>(pref.size(), [&](std::vector<pg_hit> &hits, size_t lo, size_t hi) {
-        for (size_t i = lo; i < hi; i++) {
-            const char *s = pref.entry(i);
-            bool first = true;
-            while (*s) {
-                char *e;
-                pg_hit h; h.rep = pref.keys[i];
-                h.target = (uint32_t) strtoul(s, &e, 10);
-                h.score = (int32_t) strtol(e, &e, 10);
-                h.diag = (int32_t) (short) strtol(e, &e, 10);
-                if (first) {
-                    if (h.target != h.rep || h.score != 0 || h.diag != 0) die("prefilter entry does not start with its self line (not a kmermatcher result)");
-                    first = false;
-                } else {
-                    hits.push_back(h);
-                }
-                while (*e && *e != '\n') e++;
-                s = *e ? e + 1 : e;
+PodArray<pg_hit> parsePrefDb(const mmdb::Reader &pref) {
+    return parseParallel<pg_hit>(pref, 1, [&](size_t i, pg_hit *out) {
+        const char *s = pref.entry(i);
+        bool first = true;
+        while (*s) {
+            pg_hit h; h.rep = pref.keys[i];
+            int32_t d;
+            s = getU(s, h.target);
+            s = getI(s, h.score);
+            s = getI(s, d);
+            h.diag = (int32_t) (short) d;
+            if (first) {
+                if (h.target != h.rep || h.score != 0 || h.diag != 0) die("prefilter entry does not start with its self line (not a kmermatcher result)");
+                first = false;
+            } else {
+                *out++ = h;
             }
-            if (first) die("empty prefilter entry");
+            while (*s && *s != '\n') s++;
+            if (*s) s++;
         }
+        if (first) die("empty prefilter entry");
+        return out;
     });
 }
 
@@ -253,6 +329,26 @@ void writePrefDb(const std::string &path, bool nucl, const std::vector<uint32_t>
     if (!w.close()) die("write error");
 }
 
+// "%.3E" of an E-value.  The value depends only on (raw score, query length) and the DB size, so a DB holds few distinct
+// ones: a small per-thread direct-mapped cache in front of sprintf (the exact glibc rounding stays the only formatter).
+struct EvalueText {
+    struct Slot { uint64_t bits; char text[14]; unsigned char len; unsigned char used; };
+    std::vector<Slot> slots;
+    EvalueText() : slots(8192) { for (auto &s : slots) s.used = 0; }
+    inline char *put(char *b, double v) {
+        uint64_t bits;
+        memcpy(&bits, &v, 8);
+        Slot &s = slots[(size_t) ((bits * 0x9E3779B97F4A7C15ull) >> 51)];
+        if (!s.used || s.bits != bits) {
+            const int n = snprintf(s.text, sizeof(s.text), "%.3E", v);
+            if (n <= 0 || n >= (int) sizeof(s.text)) return b + sprintf(b, "%.3E", v);
+            s.bits = bits; s.len = (unsigned char) n; s.used = 1;
+        }
+        memcpy(b, s.text, s.len);
+        return b + s.len;
+    }
+};
+
 // alignment DB: Matcher::resultToBuffer (Matcher.cpp:323-370), 10 columns per line
 void writeAlnDb(const std::string &path, const std::vector<uint32_t> &keys, const pg_aln *alns, uint64_t nAlns) {
     std::string err;
@@ -260,6 +356,7 @@ void writeAlnDb(const std::string &path, const std::vector<uint32_t> &keys, cons
     if (!w.open(path, mmdb::DBTYPE_ALIGNMENT_RES, err)) die(err);
     const std::vector<uint64_t> start = runStarts(keys, alns, nAlns, [](const pg_aln &a) { return a.query; });
     w.writeAll(keys.size(), [&](size_t i) { return keys[i]; }, [&](size_t i, std::string &buf) {
+        static thread_local EvalueText evText;
         char line[256];
         const uint32_t key = keys[i];
         for (uint64_t a = start[i]; a < start[i + 1] && alns[a].query == key; a++) {
@@ -267,7 +364,7 @@ void writeAlnDb(const std::string &path, const std::vector<uint32_t> &keys, cons
             char *b = putU(line, r.target); *b++ = '\t';
             b = putI(b, r.bits); *b++ = '\t';
             b = putSeqId(b, r.seq_id); *b++ = '\t';
-            b += sprintf(b, "%.3E", r.evalue); *b++ = '\t';
+            b = evText.put(b, r.evalue); *b++ = '\t';
             b = putI(b, r.q_start); *b++ = '\t'; b = putI(b, r.q_end); *b++ = '\t'; b = putI(b, r.q_len); *b++ = '\t';
             b = putI(b, r.db_start); *b++ = '\t'; b = putI(b, r.db_end); *b++ = '\t'; b = putI(b, r.db_len); *b++ = '\n';
             buf.append(line, (size_t) (b - line));
@@ -378,6 +475,7 @@ pg_ex_params exParams(const Flags &f, bool nuclCommand) {
 
 int extendCommand(int argc, const char **argv, bool nuclCommand) {
     Timer timer;
+    Phases ph;
     const Flags f = parseFlags(argc, argv, 3, EX_FLAGS);
     applyThreads(f);
     requireValue(f, "--compressed", "0", "uncompressed DBs only");
@@ -389,12 +487,20 @@ int extendCommand(int argc, const char **argv, bool nuclCommand) {
     (void) nuclCommand;   // like the reference, the comparator follows the command, the letters follow the DB type
     const pg_ex_params p = exParams(f, nuclCommand);
     if (nuclCommand != nucl) die("sequence DB type does not match the command (assembleresults = amino acids, nuclassembleresults = nucleotides)");
-    const std::vector<pg_aln> alns = parseAlnDb(aln);
+    ph.lap("open + index parse");
+    const PodArray<pg_aln> alns = parseAlnDb(aln);
+    ph.lap("parse alignments");
+    gpu();
+    ph.lap("CUDA init");
     pg_seqdb *db = uploadSeqDb(seq), *out = nullptr;
+    ph.lap("upload");
     if (pg_extend(gpu(), db, alns.data(), alns.size(), &p, &out, nullptr) != 0) die(pg_last_error());
+    ph.lap("kernels");
     writeSeqDb(out, f.positional[2], seq.dbtype);
+    ph.lap("download + write");
     pg_seqdb_free(gpu(), out); pg_seqdb_free(gpu(), db);
     printf("\nDone.\n");
+    ph.report();
     timer.report();
     return EXIT_SUCCESS;
 }
@@ -403,6 +509,7 @@ int extendCommand(int argc, const char **argv, bool nuclCommand) {
 
 int kmermatcher(int argc, const char **argv) {
     Timer timer;
+    Phases ph;
     const Flags f = parseFlags(argc, argv, 2, KM_FLAGS);
     applyThreads(f);
     checkKmFlags(f);
@@ -411,19 +518,26 @@ int kmermatcher(int argc, const char **argv) {
     if (!seq.open(f.positional[0], err)) die(err);
     const bool nucl = seq.dbtype == mmdb::DBTYPE_NUCLEOTIDES;
     const pg_km_params p = kmParams(f, nucl);
+    ph.lap("open + index parse");
     if (pg_set_split_memory_limit(gpu(), splitMemoryLimit(f)) != 0) die(pg_last_error());
+    ph.lap("CUDA init");
     pg_seqdb *db = uploadSeqDb(seq);
+    ph.lap("upload");
     pg_hit *hits = nullptr; uint64_t nHits = 0;
     if (pg_kmermatch(gpu(), db, &p, &hits, &nHits) != 0) die(pg_last_error());
+    ph.lap("kernels + download");
     writePrefDb(f.positional[1], nucl, seq.keys, hits, nHits);
+    ph.lap("format + write");
     pg_free_host(hits);
     pg_seqdb_free(gpu(), db);
+    ph.report();
     timer.report();
     return EXIT_SUCCESS;
 }
 
 int rescorediagonal(int argc, const char **argv) {
     Timer timer;
+    Phases ph;
     const Flags f = parseFlags(argc, argv, 4, RS_FLAGS);
     applyThreads(f);
     checkRsFlags(f);
@@ -436,13 +550,21 @@ int rescorediagonal(int argc, const char **argv) {
     if (pref.size() != seq.size() || !std::equal(pref.keys.begin(), pref.keys.end(), seq.keys.begin()))
         die("prefilter DB must hold one entry per sequence (kmermatcher output)");
     const pg_rs_params p = rsParams(f);
-    const std::vector<pg_hit> hits = parsePrefDb(pref);
+    ph.lap("open + index parse");
+    const PodArray<pg_hit> hits = parsePrefDb(pref);
+    ph.lap("parse prefilter hits");
+    gpu();
+    ph.lap("CUDA init");
     pg_seqdb *db = uploadSeqDb(seq);
+    ph.lap("upload");
     pg_aln *alns = nullptr; uint64_t nAlns = 0;
     if (pg_rescore(gpu(), db, hits.data(), hits.size(), &p, &alns, &nAlns) != 0) die(pg_last_error());
+    ph.lap("kernels + download");
     writeAlnDb(f.positional[3], seq.keys, alns, nAlns);
+    ph.lap("format + write");
     pg_free_host(alns);
     pg_seqdb_free(gpu(), db);
+    ph.report();
     timer.report();
     return EXIT_SUCCESS;
 }
@@ -457,7 +579,7 @@ int findassemblystart(int argc, const char **argv) {
     mmdb::Reader seq, aln;
     if (!seq.open(f.positional[0], err) || !aln.open(f.positional[1], err)) die(err);
     if (seq.dbtype != mmdb::DBTYPE_AMINO_ACIDS) die("findassemblystart expects an amino-acid sequence DB");
-    const std::vector<pg_aln> alns = parseAlnDb(aln);
+    const PodArray<pg_aln> alns = parseAlnDb(aln);
     pg_seqdb *db = uploadSeqDb(seq), *out = nullptr;
     if (pg_findassemblystart(gpu(), db, alns.data(), alns.size(), &out, nullptr) != 0) die(pg_last_error());
     writeSeqDb(out, f.positional[2], mmdb::DBTYPE_AMINO_ACIDS);
@@ -721,4 +843,31 @@ int dbdiff(int argc, const char **argv) {
            "\"only_in_b\": %llu, \"only_in_a\": %llu, \"dbtype_equal\": %s, \"first_mismatching_key\": %lld, \"mode\": \"%s\"}\n",
            na, nb, same, tolerated, toleratedLines, mismatching, missing, onlyA, a.dbtype == b.dbtype ? "true" : "false", firstBad, mode.c_str());
     return (mismatching == 0 && missing == 0 && onlyA == 0 && a.dbtype == b.dbtype) ? EXIT_SUCCESS : EXIT_FAILURE;
+}
+
+// iotest <pref|aln> <i:DB> <o:DB>: the text layer alone -- parse a prefilter / alignment DB into the records the kernels
+// consume and write them back (no GPU involved).  The round trip must reproduce the input (dbdiff); the printed phase
+// times are the host-side cost of a drop-in step.
+int iotest(int argc, const char **argv) {
+    Timer timer;
+    Phases ph;
+    const Flags f = parseFlags(argc, argv, 3, {"--threads"});
+    applyThreads(f);
+    std::string err;
+    mmdb::Reader in;
+    if (!in.open(f.positional[1], err)) die(err);
+    ph.lap("open + index parse");
+    if (f.positional[0] == "pref") {
+        const PodArray<pg_hit> hits = parsePrefDb(in);
+        ph.lap("parse prefilter hits");
+        writePrefDb(f.positional[2], in.dbtype == mmdb::DBTYPE_PREFILTER_REV_RES, in.keys, hits.data(), hits.size());
+    } else if (f.positional[0] == "aln") {
+        const PodArray<pg_aln> alns = parseAlnDb(in);
+        ph.lap("parse alignments");
+        writeAlnDb(f.positional[2], in.keys, alns.data(), alns.size());
+    } else die("iotest: first argument must be pref or aln");
+    ph.lap("format + write");
+    ph.report();
+    timer.report();
+    return EXIT_SUCCESS;
 }

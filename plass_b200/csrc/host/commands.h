@@ -12,3 +12,4 @@ int extractorfs(int argc, const char **argv);            // replaces lib/mmseqs/
 int translatenucs(int argc, const char **argv);          // replaces lib/mmseqs/src/util/translatenucs.cpp:14
 int assembleiteration(int argc, const char **argv);      // the three hot-path steps of one iteration fused in one process
 int dbdiff(int argc, const char **argv);                 // logical key -> entry comparison of two DBs (test / bench tool)
+int iotest(int argc, const char **argv);                 // text layer round trip without a GPU (CPU tests, host-side timing)

@@ -61,13 +61,43 @@ bool Reader::open(const std::string &path, std::string &err) {
         }
         ::close(fd);
     } else {
-        int i = 0;
-        while (fileExists(path + "." + std::to_string(i))) {
-            if (!slurp(path + "." + std::to_string(i), owned, owned.size())) { err = "cannot read split " + path; return false; }
-            i++;
+        // split data files X.0 .. X.k (DBWriter::close without merge): one anonymous mapping, filled by all host threads
+        std::vector<std::string> files;
+        std::vector<size_t> at(1, 0);
+        while (fileExists(path + "." + std::to_string(files.size()))) {
+            struct stat st;
+            files.push_back(path + "." + std::to_string(files.size()));
+            if (stat(files.back().c_str(), &st) != 0) { err = "cannot read split " + path; return false; }
+            at.push_back(at.back() + (size_t) st.st_size);
         }
-        if (i == 0) { err = "database " + path + " not found"; return false; }
-        base = owned.data(); bytes = owned.size();
+        if (files.empty()) { err = "database " + path + " not found"; return false; }
+        bytes = at.back();
+        if (bytes) {
+            mapped = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+            if (mapped == MAP_FAILED) { mapped = nullptr; err = "cannot allocate " + std::to_string(bytes) + " bytes for " + path; return false; }
+            mappedBytes = bytes;
+            base = (const char *) mapped;
+            // pieces of 8 MB over all files
+            struct Piece { size_t file; size_t off; size_t len; };
+            std::vector<Piece> pieces;
+            for (size_t f = 0; f < files.size(); f++)
+                for (size_t o = 0; o < at[f + 1] - at[f]; o += (8u << 20)) pieces.push_back({f, o, std::min<size_t>(8u << 20, at[f + 1] - at[f] - o)});
+            std::vector<int> fds(files.size());
+            for (size_t f = 0; f < files.size(); f++) fds[f] = ::open(files[f].c_str(), O_RDONLY);
+            bool ok = true;
+#pragma omp parallel for num_threads(hostThreads()) schedule(dynamic, 1)
+            for (size_t k = 0; k < pieces.size(); k++) {
+                const Piece &pc = pieces[k];
+                size_t done = 0;
+                while (done < pc.len) {
+                    const ssize_t r = fds[pc.file] < 0 ? -1 : pread(fds[pc.file], (char *) mapped + at[pc.file] + pc.off + done, pc.len - done, (off_t) (pc.off + done));
+                    if (r <= 0) { ok = false; break; }
+                    done += (size_t) r;
+                }
+            }
+            for (int fd : fds) if (fd >= 0) ::close(fd);
+            if (!ok) { err = "cannot read split " + path; return false; }
+        }
     }
     std::vector<char> idx;
     if (!slurp(path + ".index", idx, 0)) { err = "cannot read " + path + ".index"; return false; }

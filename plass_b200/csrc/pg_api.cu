@@ -129,7 +129,7 @@ static std::mutex g_pinMutex;
 static std::map<void *, size_t> g_pinLive;            // blocks owned by the caller
 static std::multimap<size_t, void *> g_pinCache;      // released blocks, by size
 static size_t g_pinCachedBytes = 0;
-static const size_t PIN_CACHE_LIMIT = 24ull << 30;
+static const size_t PIN_CACHE_LIMIT = 96ull << 30;     // two steps' results in flight at 50 M reads are 2 x 21 GB
 
 int alloc_pinned(size_t bytes, void **out) {
     if (bytes < 64) bytes = 64;
@@ -269,6 +269,7 @@ int pg_init(int device, pg_context **out) {
     PG_CHECK(prop.major == 10, "pg_init: this build targets sm_100a (B200) only");
     pg_context *ctx = new pg_context();
     ctx->device = device;
+    ctx->deviceMemBytes = prop.totalGlobalMem;
     PG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     PG_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
     PG_CUDA(cudaStreamCreateWithFlags(&ctx->h2dStream, cudaStreamNonBlocking));
@@ -304,7 +305,7 @@ void pg_destroy(pg_context *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm) pg_comm_destroy(ctx);
     DevBuf *bufs[] = {&ctx->small, &ctx->lists, &ctx->recA, &ctx->recB, &ctx->radixWs, &ctx->scratch, &ctx->blockCounts, &ctx->hits,
-                      &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta, &ctx->exLists, &ctx->ntTab, &ctx->buckets, &ctx->buckets2, &ctx->wideTabs, &ctx->nextWork, &ctx->orfInfo, &ctx->pairAcc};
+                      &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta, &ctx->exLists, &ctx->ntTab, &ctx->buckets, &ctx->buckets2, &ctx->wideTabs, &ctx->nextWork, &ctx->orfInfo, &ctx->pairAcc, &ctx->spill, &ctx->commWs};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < EV_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
     cudaStreamSynchronize(ctx->copyStream);

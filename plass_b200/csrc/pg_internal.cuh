@@ -36,9 +36,11 @@ struct pg_context {
     // --split-memory-limit (pg_set_split_memory_limit): bound on the two k-mer record buffers; splitDiv = number of equal
     // hash-range splits the running kmermatcher call uses (1 = no split), pairAcc collects the splits' pair records
     uint64_t memLimit = 0;
+    uint64_t deviceMemBytes = 0;  // total device memory (pg_init)
+    uint64_t kmerTotalHint = 0;   // computeKmerCount + 1 of the whole DB, handed from km_choose_splits to km_extract
     unsigned splitDiv = 1;
     unsigned forceSplits = 0;     // tests: use exactly this many splits
-    pg::DevBuf pairAcc;
+    pg::DevBuf pairAcc, spill;
     unsigned ntTabN = 0;
     bool pairsInA = false;
     bool tExtract = false, tGroup = false, tReduce = false, rsRan = false, exRan = false;   // which stages recorded their events in this call

@@ -734,9 +734,12 @@ __device__ __forceinline__ bool can_be_covered(float covThr, int covMode, float 
 template <bool WIDE>
 __device__ __forceinline__ unsigned long long rep_key_t(unsigned long long w1) { return WIDE ? w1 : rep_key(w1); }
 
+// firstKmer (optional): the records are a SUBSET of the job's k-mer records (spill list of the bucketed path); the group of
+// assignGroup's first-group quirk is then named by its k-mer (strand bit cleared) instead of by its position.
 template <bool WIDE>
 __global__ void __launch_bounds__(GROUP_THREADS) group_kernel(const Rec *__restrict__ in, unsigned long long n, const KmConst c,
-                                                              Rec *__restrict__ out, unsigned long long *__restrict__ outCount) {
+                                                              Rec *__restrict__ out, unsigned long long *__restrict__ outCount,
+                                                              const unsigned long long *__restrict__ firstKmer = nullptr) {
     __shared__ Rec tile[GROUP_TILE];
     __shared__ int headIdx[GROUP_TILE];       // index (in tile) of the first record of the group of record i
     __shared__ GroupAcc gacc[GROUP_TILE];     // valid at head indices: reduction of the whole group
@@ -883,7 +886,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) group_kernel(const Rec *__restr
                 unsigned qRev = 0;
                 if (nt) {
                     // the reference initialises repIsReverse = false for the very first group (kmermatcher.cpp:463)
-                    const bool firstGroup = (h == 0) && sBackAtZero;
+                    const bool firstGroup = firstKmer ? ((r.w0 & ~(1ULL << 63)) == *firstKmer) : ((h == 0) && sBackAtZero);
                     const bool repIsReverse = firstGroup ? false : (a.strand == 0);
                     const bool targetIsReverse = ((r.w0 >> 63) == 0);
                     int queryPos, targetPos;
@@ -965,6 +968,27 @@ __global__ void bucket_bounds_kernel(const Rec *__restrict__ in, unsigned long l
     if ((threadIdx.x & 31) == 0) atomicMin(minKmer, localMin);
 }
 
+// spill list of the bucketed path: buckets beyond the largest shared-memory instance (a k-mer that occurs in thousands of
+// sequences, or an unlucky pile-up) are copied out, fully sorted and grouped by group_kernel -- only these buckets, the
+// rest of the iteration keeps the fast path.
+__global__ void huge_offsets_kernel(const unsigned *__restrict__ list, unsigned n, const unsigned long long *__restrict__ start,
+                                    const unsigned long long *__restrict__ end, unsigned long long *__restrict__ off /* n + 1 */) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (unsigned i = 0; i < n; i++) { off[i] = run; run += end[list[i]] - start[list[i]]; }
+        off[n] = run;
+    }
+}
+__global__ void huge_gather_kernel(const Rec *__restrict__ in, const unsigned *__restrict__ list, unsigned n, const unsigned long long *__restrict__ start,
+                                   const unsigned long long *__restrict__ end, const unsigned long long *__restrict__ off, Rec *__restrict__ out) {
+    for (unsigned i = blockIdx.x; i < n; i += gridDim.x) {
+        const unsigned b = list[i];
+        const unsigned long long s0 = start[b], cnt = end[b] - s0, o = off[i];
+        for (unsigned long long j = threadIdx.x; j < cnt; j += blockDim.x)
+            reinterpret_cast<uint4 *>(out)[o + j] = __ldg(reinterpret_cast<const uint4 *>(in) + s0 + j);
+    }
+}
+
 // packed representative key: (seqLen desc, id asc, pos asc, strand asc); seqLen < 32768 (narrow records)
 __device__ __forceinline__ unsigned long long hg_pack(const Rec &r) {
     const unsigned long long id = r.w1 >> 32, len = (r.w1 >> 16) & 0x7FFFULL, pos = r.w1 & 0xFFFFULL;
@@ -1008,7 +1032,7 @@ __global__ void __launch_bounds__(HG_THREADS) hash_group_kernel(const Rec *__res
                                                                 unsigned long long hashMask, const unsigned long long *__restrict__ minKmer,
                                                                 const KmConst c, Rec *__restrict__ out, unsigned long long *__restrict__ outCount,
                                                                 unsigned *__restrict__ bigList, unsigned *__restrict__ bigCount,
-                                                                unsigned *__restrict__ overflow) {
+                                                                unsigned *__restrict__ hugeList, unsigned *__restrict__ hugeCount) {
     __shared__ unsigned long long sKey[TABLE];
     __shared__ unsigned long long sMin[TABLE];
     __shared__ unsigned sCnt[TABLE];
@@ -1024,9 +1048,10 @@ __global__ void __launch_bounds__(HG_THREADS) hash_group_kernel(const Rec *__res
         if (e0 <= s0) continue;
         const unsigned count = (unsigned) (e0 - s0);
         if (count > (unsigned) (HG_THREADS * ITEMS)) {
+            // too large for this instance: the next larger one, or the spill list (sorted and grouped apart, only these buckets)
             if (tid == 0) {
                 if (MODE == 0 && count <= (unsigned) HG_MAX_BUCKET) bigList[atomicAdd(bigCount, 1u)] = b;
-                else atomicExch(overflow, 1u);
+                else hugeList[atomicAdd(hugeCount, 1u)] = b;
             }
             continue;
         }
@@ -1198,7 +1223,7 @@ __device__ __forceinline__ void run_step(unsigned d, unsigned rv, unsigned &prev
 // block starts with the same target id; the warp therefore peeks at the following representative(s).
 // ------------------------------------------------------------------------------------------------
 constexpr int SEG_WARP_MAX = 512;     // pairs one warp sorts in registers (16 per lane)
-constexpr int SEG_BLOCK_MAX = 8192;
+constexpr int SEG_BLOCK_MAX = 16384;   // pairs of one representative sorted by a CTA in shared memory (128 KB)
 
 __global__ void seg_bounds_kernel(const Rec *__restrict__ in, unsigned long long n, unsigned long long *__restrict__ start,
                                   unsigned long long *__restrict__ end, unsigned *__restrict__ minTarget /* preset to 0xFFFFFFFF */) {
@@ -1883,7 +1908,9 @@ int km_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const Km
     unsigned *d_clsCount = (unsigned *) (d_total + 8);                        // [8..] 4 class counters
     PG_CUDA(cudaMemsetAsync(d_total, 0, 256, s));
     const unsigned sLo = std::min(ctx->seqLo, n), sHi = std::min(ctx->seqHi, n);
-    kmer_count_kernel<<<NUM_SMS * 4, 256, 0, s>>>(db->lens, sLo, sHi, c.k, c.kmersPerSeq, c.scale, d_total);
+    const unsigned long long hint = (sLo == 0 && sHi == n) ? ctx->kmerTotalHint : 0;     // km_choose_splits counted already
+    ctx->kmerTotalHint = 0;
+    if (!hint) kmer_count_kernel<<<NUM_SMS * 4, 256, 0, s>>>(db->lens, sLo, sHi, c.k, c.kmersPerSeq, c.scale, d_total);
     PG_TRY(ctx->lists.reserve(sizeof(unsigned) * 4 * (size_t) n + 16));
     unsigned *lists = ctx->lists.as<unsigned>();
     classify_kernel<<<(sHi - sLo + 255) / 256 + 1, 256, 0, s>>>(db->lens, sLo, sHi, n, c.k, lists, d_clsCount);
@@ -1894,7 +1921,7 @@ int km_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const Km
     {
         unsigned long long hb[10];                     // [0] capacity estimate, [8..9] the four class counters
         PG_TRY(read_back(ctx, hb, d_total, sizeof(hb)));
-        h_total = hb[0];
+        h_total = hint ? hint - 1 : hb[0];
         memcpy(h_cls, hb + 8, sizeof(h_cls));
     }
     // a hash-range split holds 1 / splitDiv of the records (XXH64 is uniform) + 12.5 % + slack; if a skewed input
@@ -1950,45 +1977,77 @@ static int km_group_bucketed(Context *ctx, const KmConst &c, uint64_t nRecords, 
     unsigned *d_over = (unsigned *) (d_min + 1);
     Rec *sorted = nullptr;
     cudaEventRecord(ctx->ev[EV_SORT1_BEGIN], s);
-    PG_TRY(radix_sort(ctx->recA.as<Rec>(), ctx->recB.as<Rec>(), nRecords, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches,
-                      ctx->ev[EV_SCATTER1_BEGIN], ctx->ev[EV_SCATTER1_END]));
-    ctx->timings.sort1_passes = (uint32_t) plan.npasses;
-    cudaEventRecord(ctx->ev[EV_SORT1_END], s);
-    PG_CUDA(cudaMemsetAsync(d_start, 0, sizeof(unsigned long long) * 2 * (size_t) nBuckets, s));
+    // the last partition pass knows every record's final position: it also leaves the bucket boundaries and the smallest
+    // k-mer (bulk-copy kernel); otherwise a sweep over the partitioned records finds them
+    const bool fusedBounds = radix_emits_bounds(plan);
+    RadixBounds rb;
+    rb.start = d_start; rb.end = d_end; rb.minKey = d_min; rb.hashMask = hashMask; rb.bucketMask = nBuckets - 1;
     PG_CUDA(cudaMemsetAsync(d_min, 0xFF, sizeof(unsigned long long), s));
     PG_CUDA(cudaMemsetAsync(d_over, 0, sizeof(unsigned), s));
-    bucket_bounds_kernel<<<NUM_SMS * 16, 256, 0, s>>>(sorted, nRecords, hashMask, nBuckets - 1, d_start, d_end, d_min);
+    if (fusedBounds) {
+        PG_CUDA(cudaMemsetAsync(d_start, 0xFF, sizeof(unsigned long long) * (size_t) nBuckets, s));
+        PG_CUDA(cudaMemsetAsync(d_end, 0, sizeof(unsigned long long) * (size_t) nBuckets, s));
+    }
+    PG_TRY(radix_sort(ctx->recA.as<Rec>(), ctx->recB.as<Rec>(), nRecords, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches,
+                      ctx->ev[EV_SCATTER1_BEGIN], ctx->ev[EV_SCATTER1_END], fusedBounds ? &rb : nullptr));
+    ctx->timings.sort1_passes = (uint32_t) plan.npasses;
+    cudaEventRecord(ctx->ev[EV_SORT1_END], s);
+    if (!fusedBounds) {
+        PG_CUDA(cudaMemsetAsync(d_start, 0, sizeof(unsigned long long) * 2 * (size_t) nBuckets, s));
+        bucket_bounds_kernel<<<NUM_SMS * 16, 256, 0, s>>>(sorted, nRecords, hashMask, nBuckets - 1, d_start, d_end, d_min);
+    }
     Rec *outBuf = (sorted == ctx->recA.as<Rec>()) ? ctx->recB.as<Rec>() : ctx->recA.as<Rec>();
     unsigned long long *d_cnt = ctx->small.as<unsigned long long>() + 2;
     PG_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
     // buckets above the small instance's capacity are listed (after the d_end array's alignment slack: reuse blockCounts)
-    PG_TRY(ctx->blockCounts.reserve(sizeof(unsigned) * ((size_t) nBuckets + 4)));
+    PG_TRY(ctx->blockCounts.reserve(sizeof(unsigned) * (2 * (size_t) nBuckets + 8)));
     unsigned *d_bigList = ctx->blockCounts.as<unsigned>() + 4;
     unsigned *d_bigCnt = ctx->blockCounts.as<unsigned>();
+    unsigned *d_hugeList = d_bigList + nBuckets + 4;
+    unsigned *d_hugeCnt = d_over;                 // the former overflow flag: number of buckets on the spill list
     PG_CUDA(cudaMemsetAsync(d_bigCnt, 0, sizeof(unsigned), s));
     // multi-GPU: the smallest k-mer of the whole job (all-reduced by pg_shard_iteration), not of this rank's share
     unsigned long long *d_first = d_min;
     km_min_kmer_slot(ctx, &d_first);
     if (bigFirst) {
         hash_group_kernel<HG_TABLE_BIG, HG_ITEMS_BIG, 0><<<std::min<unsigned>(nBuckets, NUM_SMS * 32), HG_THREADS, 0, s>>>(
-            sorted, d_start, d_end, nBuckets, hashMask, d_first, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_over);
+            sorted, d_start, d_end, nBuckets, hashMask, d_first, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_hugeList, d_hugeCnt);
     } else {
         hash_group_kernel<HG_TABLE_SMALL, HG_ITEMS_SMALL, 0><<<std::min<unsigned>(nBuckets, NUM_SMS * 64), HG_THREADS, 0, s>>>(
-            sorted, d_start, d_end, nBuckets, hashMask, d_first, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_over);
+            sorted, d_start, d_end, nBuckets, hashMask, d_first, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_hugeList, d_hugeCnt);
         hash_group_kernel<HG_TABLE_BIG, HG_ITEMS_BIG, 1><<<NUM_SMS * 4, HG_THREADS, 0, s>>>(
-            sorted, d_start, d_end, nBuckets, hashMask, d_first, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_over);
+            sorted, d_start, d_end, nBuckets, hashMask, d_first, c, outBuf, d_cnt, d_bigList, d_bigCnt, d_hugeList, d_hugeCnt);
     }
     ctx->launches += 3;
-    cudaEventRecord(ctx->ev[EV_GROUP_END], s);
-    unsigned long long h = 0; unsigned over = 0;
-    PG_TRY(read_back(ctx, &h, d_cnt, sizeof(h)));
-    PG_TRY(read_back(ctx, &over, d_over, sizeof(over)));
-    PG_CUDA(cudaGetLastError());
-    if (over) {
-        // the records are only permuted (still all in `sorted`); hand them back in recA for the full sort
-        if (sorted != ctx->recA.as<Rec>()) PG_CUDA(cudaMemcpyAsync(ctx->recA.p, sorted, sizeof(Rec) * nRecords, cudaMemcpyDeviceToDevice, s));
-        return 0;
+    unsigned long long h = 0; unsigned nHuge = 0;
+    PG_TRY(read_back(ctx, &nHuge, d_hugeCnt, sizeof(nHuge)));
+    if (nHuge) {
+        // spill list: copy the listed buckets out, sort them by the full k-mer, group them with the tile kernel; their pairs
+        // are appended to the same output.  If the spill is most of the input the whole input takes that path instead.
+        PG_TRY(ctx->scratch.reserve(sizeof(unsigned long long) * ((size_t) nHuge + 2)));
+        unsigned long long *d_off = ctx->scratch.as<unsigned long long>();
+        huge_offsets_kernel<<<1, 32, 0, s>>>(d_hugeList, nHuge, d_start, d_end, d_off);
+        unsigned long long nSpill = 0;
+        PG_TRY(read_back(ctx, &nSpill, d_off + nHuge, sizeof(nSpill)));
+        if (nSpill > nRecords / 2) {
+            // the records are only permuted (still all in `sorted`); hand them back in recA for the full sort
+            if (sorted != ctx->recA.as<Rec>()) PG_CUDA(cudaMemcpyAsync(ctx->recA.p, sorted, sizeof(Rec) * nRecords, cudaMemcpyDeviceToDevice, s));
+            return 0;
+        }
+        PG_TRY(ctx->spill.reserve(sizeof(Rec) * 2 * (size_t) (nSpill + 1)));
+        Rec *spA = ctx->spill.as<Rec>(), *spB = spA + (nSpill + 1);
+        huge_gather_kernel<<<std::min<unsigned>(nHuge, NUM_SMS * 8), 256, 0, s>>>(sorted, d_hugeList, nHuge, d_start, d_end, d_off, spA);
+        RadixPlan full; full.npasses = 0;
+        plan_add_bits(full, 0, 0, c.nt ? 63 : 64);
+        Rec *spSorted = nullptr;
+        PG_TRY(radix_sort(spA, spB, nSpill, full, ctx->radixWs.p, ctx->radixWs.cap, s, &spSorted, &ctx->launches));
+        group_kernel<false><<<(unsigned) ((nSpill + GROUP_TILE - 1) / GROUP_TILE), GROUP_THREADS, 0, s>>>(spSorted, nSpill, c, outBuf, d_cnt, d_first);
+        ctx->launches += 3;
+        ctx->timings.spilled_records = nSpill;
     }
+    cudaEventRecord(ctx->ev[EV_GROUP_END], s);
+    PG_TRY(read_back(ctx, &h, d_cnt, sizeof(h)));
+    PG_CUDA(cudaGetLastError());
     *nPairs = h;
     ctx->pairsInA = (outBuf == ctx->recA.as<Rec>());
     *ok = true;
@@ -2164,8 +2223,12 @@ static int km_choose_splits(Context *ctx, const pg_seqdb *db, const pg_km_params
     ctx->launches++;
     unsigned long long total = 0;
     PG_TRY(read_back(ctx, &total, d_total, sizeof(total)));
+    ctx->kmerTotalHint = total + 1;             // km_extract does not count again
     const unsigned long long need = 2ull * sizeof(Rec) * (total + 1) + radix_workspace_bytes(total);
     unsigned long long limit = ctx->memLimit;
+    // cudaMemGetInfo waits for the device (it would serialise this call with the previous step's result transfers on the copy
+    // stream): only asked when the stage needs a sizeable part of the device memory
+    if (limit == 0 && (need <= ctx->deviceMemBytes / 4 || need <= ctx->recA.cap + ctx->recB.cap + ctx->radixWs.cap)) return 0;   // small, or the buffers exist already
     if (limit == 0) {
         size_t freeB = 0, totalB = 0;
         PG_CUDA(cudaMemGetInfo(&freeB, &totalB));

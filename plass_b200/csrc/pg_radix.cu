@@ -1,6 +1,9 @@
 // pg_radix.cu -- see pg_radix.cuh.
 #include "pg_radix.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace pg {
 
 namespace {
@@ -347,6 +350,244 @@ __global__ void __launch_bounds__(RADIX_THREADS, MINBLOCKS) radix_scatter_wide_k
     }
 }
 
+
+// ---- persistent bulk-copy (TMA) pass ------------------------------------------------------------------------------
+// One CTA keeps taking tiles (ticket order, so the decoupled look-back never waits on a tile that has not started).  The
+// records of tile i+1 are fetched by ONE bulk asynchronous copy (cp.async.bulk.shared.global, completion counted on an
+// mbarrier) while tile i is ranked, so the load latency that the register-tile kernel exposes once per tile is off the
+// critical path; after the in-place reorder each digit run is one contiguous piece of shared memory AND of the output,
+// and the thread that owns the digit hands it to the copy engine as one bulk shared -> global copy.  STAGES buffers:
+// with 3, the stores of tile i-1 may still be draining while tile i is ranked and tile i+1 is loading.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int ITEMS, int STAGES, bool BOUNDS>
+__global__ void __launch_bounds__(RADIX_THREADS, 2) radix_scatter_tma_kernel(
+    const Rec *__restrict__ in, Rec *__restrict__ out, unsigned long long portionStart, unsigned long long portionEnd,
+    DigitPass dp, const unsigned long long *__restrict__ gbase, unsigned long long *__restrict__ gbaseNext,
+    unsigned *status, unsigned *ticket, unsigned numTiles, RadixBounds bo) {
+    constexpr int TILE = RADIX_THREADS * ITEMS;
+    constexpr int WARPS = RADIX_THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];          // STAGES x TILE records
+    __shared__ unsigned short warpCnt[WARPS][256];
+    __shared__ unsigned digitStart[256];
+    __shared__ unsigned digitCnt[256];
+    __shared__ long long goff[256];
+    __shared__ unsigned warpTotals[WARPS];
+    __shared__ unsigned sTile[STAGES];
+    __shared__ __align__(8) unsigned long long bar[STAGES];
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned ltMask = (1u << lane) - 1u;
+    auto bufOf = [&](int st) { return reinterpret_cast<Rec *>(smem_raw) + (size_t) st * TILE; };
+    auto tileCount = [&](unsigned tile) {
+        const unsigned long long tb = portionStart + (unsigned long long) tile * TILE;
+        return (unsigned) min((unsigned long long) TILE, portionEnd - tb);
+    };
+    // one thread: take the next ticket and start its load into stage st
+    auto fetch = [&](int st) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        sTile[st] = t;
+        if (t < numTiles) {
+            const unsigned bytes = tileCount(t) * (unsigned) sizeof(Rec);
+            fence_async_smem();                                       // generic-proxy accesses to the stage before the async write
+            mbar_expect_tx(&bar[st], bytes);
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(in + portionStart + (unsigned long long) t * TILE);
+            unsigned char *dst = reinterpret_cast<unsigned char *>(bufOf(st));
+            // pieces of at most 16 KB: several copies in flight per tile
+            for (unsigned o = 0; o < bytes; o += 16384u) bulk_g2s(dst + o, src + o, min(16384u, bytes - o), &bar[st]);
+        }
+    };
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; i++) mbar_init(&bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) fetch(0);
+    unsigned long long localMin = ~0ULL;
+    __syncthreads();
+
+    for (unsigned it = 0;; it++) {
+        const int cur = (int) (it % STAGES);
+        const unsigned tile = sTile[cur];
+        if (tile >= numTiles) break;
+        const unsigned count = tileCount(tile);
+        Rec *buf = bufOf(cur);
+        // the stage the next tile goes to was last used by tile it+1-STAGES, whose bulk stores have been waited for
+        if (tid == 0) fetch((int) ((it + 1) % STAGES));
+        for (int i = tid; i < WARPS * 256; i += RADIX_THREADS) (&warpCnt[0][0])[i] = 0;
+        while (!mbar_try_wait(&bar[cur], (it / STAGES) & 1u)) { }
+        __syncthreads();
+
+        // records of this thread: warp w owns [w * ITEMS * 32, ...), round r covers 32 consecutive records
+        Rec rec[ITEMS];
+        unsigned short rank[ITEMS];
+        unsigned dpack[(ITEMS + 3) / 4];
+#pragma unroll
+        for (int r = 0; r < (ITEMS + 3) / 4; r++) dpack[r] = 0;
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) {
+            const unsigned idx = w * (ITEMS * 32) + r * 32 + lane;
+            if (idx < count) {
+                const uint4 raw = *reinterpret_cast<const uint4 *>(buf + idx);
+                rec[r].w0 = ((unsigned long long) raw.y << 32) | raw.x;
+                rec[r].w1 = ((unsigned long long) raw.w << 32) | raw.z;
+            } else {
+                rec[r].w0 = 0; rec[r].w1 = 0;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) {
+            const unsigned idx = w * (ITEMS * 32) + r * 32 + lane;
+            const bool valid = idx < count;
+            const unsigned d = valid ? digit_of(rec[r], dp) : 256u;
+            if (valid) dpack[r >> 2] |= d << ((r & 3) * 8);
+            const unsigned m = __match_any_sync(0xFFFFFFFFu, d);
+            unsigned c = 0;
+            if (valid) c = warpCnt[w][d];
+            rank[r] = (unsigned short) (c + __popc(m & ltMask));
+            __syncwarp();
+            if (valid && (m & ltMask) == 0) warpCnt[w][d] = (unsigned short) (c + __popc(m));
+            __syncwarp();
+        }
+        __syncthreads();
+        // per digit: exclusive prefix over warps, total count
+        unsigned cnt;
+        {
+            unsigned run = 0;
+#pragma unroll
+            for (int ww = 0; ww < WARPS; ww++) {
+                const unsigned c = warpCnt[ww][tid];
+                warpCnt[ww][tid] = (unsigned short) run;
+                run += c;
+            }
+            cnt = run;
+        }
+        if (tile == 0) st_volatile_u32(&status[tid], (cnt << 2) | FLAG_INC);
+        else st_volatile_u32(&status[(size_t) tile * 256 + tid], (cnt << 2) | FLAG_AGG);
+        unsigned myStart;
+        {
+            unsigned v = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, v, o);
+                if (lane >= o) v += nb;
+            }
+            if (lane == 31) warpTotals[w] = v;
+            __syncthreads();
+            unsigned woff = 0;
+#pragma unroll
+            for (int ww = 0; ww < WARPS; ww++) woff += (ww < w) ? warpTotals[ww] : 0u;
+            myStart = woff + v - cnt;
+            digitStart[tid] = myStart;
+            digitCnt[tid] = cnt;
+        }
+        __syncthreads();
+        // in-place reorder: every thread holds its records in registers since before the two barriers above
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) {
+            const unsigned idx = w * (ITEMS * 32) + r * 32 + lane;
+            if (idx < count) {
+                const unsigned d = (dpack[r >> 2] >> ((r & 3) * 8)) & 0xFFu;
+                const unsigned pos = digitStart[d] + warpCnt[w][d] + rank[r];
+                uint4 raw;
+                raw.x = (unsigned) rec[r].w0; raw.y = (unsigned) (rec[r].w0 >> 32); raw.z = (unsigned) rec[r].w1; raw.w = (unsigned) (rec[r].w1 >> 32);
+                *reinterpret_cast<uint4 *>(buf + pos) = raw;
+            }
+        }
+        fence_async_smem();                       // the reordered tile must be visible to the copy engine
+        // decoupled look-back: exclusive prefix of this digit over all earlier tiles of the portion
+        unsigned long long myGlobal;
+        {
+            unsigned long long prev = 0;
+            if (tile > 0) {
+                long long ll = (long long) tile - 1;
+                bool done = false;
+                while (!done) {
+                    unsigned v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const long long idx = ll - u;
+                        v[u] = (idx >= 0) ? ld_volatile_u32(&status[(size_t) idx * 256 + tid]) : FLAG_INC;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        if (done) break;
+                        const unsigned f = v[u] & 3u;
+                        if (f == 0u) break;
+                        prev += v[u] >> 2;
+                        ll--;
+                        if (f == FLAG_INC) done = true;
+                    }
+                }
+                st_volatile_u32(&status[(size_t) tile * 256 + tid], ((unsigned) (prev + cnt) << 2) | FLAG_INC);
+            }
+            const unsigned long long base = gbase[tid];
+            myGlobal = base + prev;
+            if (BOUNDS) goff[tid] = (long long) myGlobal - (long long) myStart;
+            if (tile == numTiles - 1) gbaseNext[tid] = base + prev + cnt;
+        }
+        __syncthreads();
+        // one bulk copy per digit run
+        if (cnt) bulk_s2g(out + myGlobal, buf + myStart, cnt * (unsigned) sizeof(Rec));
+        bulk_commit();
+        if (BOUNDS) {
+            // bucket boundaries + smallest key from the reordered tile (neighbours in the tile are neighbours in the output
+            // as long as they share the digit, and the bucket id contains the digit)
+            for (unsigned j0 = 0; j0 < count; j0 += RADIX_THREADS) {
+                const unsigned j = j0 + tid;
+                const bool valid = j < count;
+                unsigned long long hb = ~0ULL;
+                if (valid) {
+                    const unsigned long long k = buf[j].w0 & bo.hashMask;
+                    localMin = min(localMin, k);
+                    hb = mix64(k) & (unsigned long long) bo.bucketMask;
+                }
+                unsigned long long bp = __shfl_up_sync(0xFFFFFFFFu, hb, 1), bn = __shfl_down_sync(0xFFFFFFFFu, hb, 1);
+                if (valid) {
+                    if (lane == 0) bp = j > 0 ? (mix64(buf[j - 1].w0 & bo.hashMask) & (unsigned long long) bo.bucketMask) : ~0ULL;
+                    if (lane == 31) bn = j + 1 < count ? (mix64(buf[j + 1].w0 & bo.hashMask) & (unsigned long long) bo.bucketMask) : ~0ULL;
+                    if (j + 1 >= count) bn = ~0ULL;
+                    const unsigned d = (unsigned) (hb >> dp.shift) & dp.mask;
+                    const unsigned long long g = (unsigned long long) (goff[d] + (long long) j);
+                    if (bp != hb) atomicMin(&bo.start[(unsigned) hb], g);
+                    if (bn != hb) atomicMax(&bo.end[(unsigned) hb], g + 1ULL);
+                }
+            }
+        }
+        // the stage that the NEXT iteration's fetch targets must have been read out by the copy engine
+        bulk_wait_read<STAGES - 2>();
+        __syncthreads();
+    }
+    bulk_wait_read<0>();
+    if (BOUNDS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) localMin = min(localMin, __shfl_xor_sync(0xFFFFFFFFu, localMin, o));
+        if (lane == 0 && localMin != ~0ULL) atomicMin(bo.minKey, localMin);
+    }
+}
+
 static int g_items = 12;   // records per thread of the scatter kernel (8 / 12 / 16), see radix_set_items
 static inline unsigned long long tile_records() { return (unsigned long long) RADIX_THREADS * g_items; }
 constexpr unsigned long long PORTION_RECORDS = ((1ull << 30) / 12288 - 1) * 12288;   // look-back prefix < 2^30; multiple of every tile size
@@ -360,6 +601,42 @@ inline unsigned long long max_tiles(uint64_t n) {
 }  // namespace
 
 void radix_set_items(int items) { g_items = (items == 8 || items == 16) ? items : 12; }
+
+// 0: register-tile kernel; 1: bulk-copy kernel, 3072-record tiles, 2 stages; 2: bulk-copy kernel, 2048-record tiles, 3 stages
+static int g_mode = -1;
+int radix_get_mode() {
+    if (g_mode < 0) {
+        g_mode = 1;
+        if (const char *e = getenv("PLASS_B200_RADIX_MODE")) { const int m = atoi(e); if (m >= 0 && m <= 2) g_mode = m; }
+    }
+    return g_mode;
+}
+void radix_set_mode(int mode) { g_mode = (mode >= 0 && mode <= 2) ? mode : 1; }
+
+bool radix_emits_bounds(const RadixPlan &plan) {
+    if (radix_get_mode() == 0 || plan.npasses == 0) return false;
+    for (int p = 0; p < plan.npasses; p++) if (plan.pass[p].mask > 255u || !plan.pass[p].hashed) return false;
+    return true;
+}
+
+template <int ITEMS, int STAGES>
+static int launch_tma(const Rec *src, Rec *dst, unsigned long long ps, unsigned long long pe, const DigitPass &dp, const unsigned long long *gb,
+                      unsigned long long *gbNext, unsigned *status, unsigned *ticket, const RadixBounds *bounds, cudaStream_t stream, unsigned *tilesOut) {
+    constexpr int TILE = RADIX_THREADS * ITEMS;
+    const int smem = STAGES * TILE * (int) sizeof(Rec);
+    static bool attr[2] = {false, false};
+    const unsigned tiles = (unsigned) ((pe - ps + TILE - 1) / TILE);
+    *tilesOut = tiles;
+    const unsigned grid = std::min<unsigned>(tiles, (unsigned) NUM_SMS * 2u);
+    if (bounds) {
+        if (!attr[1]) { PG_CUDA(cudaFuncSetAttribute(radix_scatter_tma_kernel<ITEMS, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[1] = true; }
+        radix_scatter_tma_kernel<ITEMS, STAGES, true><<<grid, RADIX_THREADS, smem, stream>>>(src, dst, ps, pe, dp, gb, gbNext, status, ticket, tiles, *bounds);
+    } else {
+        if (!attr[0]) { PG_CUDA(cudaFuncSetAttribute(radix_scatter_tma_kernel<ITEMS, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[0] = true; }
+        radix_scatter_tma_kernel<ITEMS, STAGES, false><<<grid, RADIX_THREADS, smem, stream>>>(src, dst, ps, pe, dp, gb, gbNext, status, ticket, tiles, RadixBounds());
+    }
+    return 0;
+}
 
 void plan_add_bits(RadixPlan &plan, int word, int lo, int hi) {
     for (int b = lo; b < hi; b += 8) {
@@ -411,7 +688,7 @@ size_t radix_workspace_bytes(uint64_t n, int maxDigitBits) {
 }
 
 int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspace, size_t workspace_bytes,
-               cudaStream_t stream, Rec **sorted, uint64_t *launches, cudaEvent_t evScatterBegin, cudaEvent_t evScatterEnd) {
+               cudaStream_t stream, Rec **sorted, uint64_t *launches, cudaEvent_t evScatterBegin, cudaEvent_t evScatterEnd, const RadixBounds *bounds) {
     *sorted = a;
     if (n == 0 || plan.npasses == 0) return 0;
     PG_CHECK(plan.npasses <= RADIX_MAX_PASSES, "radix_sort: too many passes");
@@ -452,13 +729,20 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
         for (unsigned long long q = 0; q < portions; q++) {
             const unsigned long long ps = q * PORTION_RECORDS;
             const unsigned long long pe = (ps + PORTION_RECORDS < n) ? ps + PORTION_RECORDS : n;
-            const unsigned tiles = (unsigned) ((pe - ps + tile_records() - 1) / tile_records());
+            unsigned tiles = (unsigned) ((pe - ps + tile_records() - 1) / tile_records());
             const int bins = plan.pass[p].mask > 511 ? 1024 : (plan.pass[p].mask > 255 ? 512 : 256);
+            const int mode = radix_get_mode();
+            if (bins == 256 && mode != 0) tiles = (unsigned) ((pe - ps + (mode == 2 ? 2048 : 3072) - 1) / (mode == 2 ? 2048 : 3072));
             PG_CUDA(cudaMemsetAsync(status, 0, sizeof(unsigned) * ((size_t) tiles * bins + 64), stream));
             unsigned *ticket = status + statusWords - 32;
             PG_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), stream));
             unsigned long long *gb = bases + ((size_t) p * (portions + 1) + q) * stride;
-            if (bins == 512) {
+            if (bins == 256 && mode != 0) {
+                const RadixBounds *bp = (bounds && p == plan.npasses - 1 && radix_emits_bounds(plan)) ? bounds : nullptr;
+                unsigned t2 = 0;
+                if (mode == 2) PG_TRY((launch_tma<8, 3>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, bp, stream, &t2)));
+                else PG_TRY((launch_tma<12, 2>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, bp, stream, &t2)));
+            } else if (bins == 512) {
                 if (g_items == 16) radix_scatter_wide_kernel<16, 2, 9><<<tiles, RADIX_THREADS, dynSmemWide, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles);
                 else { PG_CHECK(g_items == 12, "radix_sort: wide digits need 12 or 16 records per thread"); radix_scatter_wide_kernel<12, 3, 9><<<tiles, RADIX_THREADS, dynSmemWide, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles); }
             } else if (bins == 1024) {

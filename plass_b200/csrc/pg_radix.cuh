@@ -10,6 +10,9 @@
 //     run leaves the SM as contiguous 16-byte stores, and the tile's global offsets come from a
 //     decoupled look-back over per-tile status words (single pass, no second read of the data),
 //   * stable, so passes compose into a multi-word key sort.
+// Round 2: the 256-bin pass is a PERSISTENT kernel whose tiles arrive by bulk asynchronous copy (cp.async.bulk global ->
+// shared, completion on an mbarrier; SASS UBLKCP.S.G): tile i+1 travels while tile i is ranked, and every digit run leaves
+// the SM as one bulk shared -> global copy (UBLKCP.G.S) issued by the thread that owns the digit.
 #pragma once
 #include "pg_common.cuh"
 
@@ -39,6 +42,19 @@ struct RadixPlan {
     int npasses;
 };
 
+// Optional by-product of the LAST pass of a hashed-bucket partition (sort #1): the first / one-past-last output index of
+// every bucket (bucket = mix64(w0 & hashMask) & bucketMask, all of whose bits the plan sorts by) and the smallest
+// w0 & hashMask of the input.  The last pass knows every record's final position, so the separate sweep over the sorted
+// records that used to find the bucket boundaries (one more read of every record) is not needed.  start[] must be preset
+// to 0xFF.., end[] to 0, *minKey to 0xFF.. by the caller.
+struct RadixBounds {
+    unsigned long long *start = nullptr;
+    unsigned long long *end = nullptr;
+    unsigned long long *minKey = nullptr;
+    unsigned long long hashMask = 0;
+    unsigned bucketMask = 0;
+};
+
 // Workspace owned by the caller (sized by radix_workspace_bytes); maxDigitBits = the widest digit of the plan (8..10).
 size_t radix_workspace_bytes(uint64_t n, int maxDigitBits = 8);
 
@@ -46,7 +62,12 @@ size_t radix_workspace_bytes(uint64_t n, int maxDigitBits = 8);
 // scratch buffer of the same size; *sorted points to whichever of the two holds the result.
 int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspace, size_t workspace_bytes,
                cudaStream_t stream, Rec **sorted, uint64_t *launches,
-               cudaEvent_t evScatterBegin = nullptr, cudaEvent_t evScatterEnd = nullptr);
+               cudaEvent_t evScatterBegin = nullptr, cudaEvent_t evScatterEnd = nullptr, const RadixBounds *bounds = nullptr);
+// true if radix_sort would honour `bounds` for this plan (256-bin digits through the bulk-copy kernel)
+bool radix_emits_bounds(const RadixPlan &plan);
+// 0: register-tile kernel (round 1), 1: persistent bulk-copy (TMA) kernel, 2 records-per-thread / stage variants; see pg_radix.cu
+void radix_set_mode(int mode);
+int radix_get_mode();
 
 // Helper to build a plan over bit ranges: appends 8-bit digits covering bits [lo, hi) of word w.
 void plan_add_bits(RadixPlan &plan, int word, int lo, int hi);
