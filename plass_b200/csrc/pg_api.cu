@@ -742,6 +742,10 @@ int pg_debug_force_splits(pg_context *ctx, unsigned n) { if (!ctx) return 1; ctx
 // tests: force the full-sort group path (1) or allow the bucketed hash join (0)
 int pg_debug_force_full_sort(pg_context *ctx, int on) { if (!ctx) return 1; ctx->forceFullSort = on != 0; return 0; }
 
+// 256-bin radix pass: 0 register-tile kernel, 1 bulk-copy kernel (3072-record tiles, 2 stages), 2 bulk-copy kernel (2048, 3 stages)
+int pg_debug_set_radix_mode(int mode) { radix_set_mode(mode); return 0; }
+int pg_debug_get_radix_mode(void) { return radix_get_mode(); }
+
 // radix digit width of the fast-path sorts: 8 (256-bin passes), 9 or 10 (wide-digit kernel, fewer passes)
 int pg_debug_set_digit_bits(pg_context *ctx, int bits) {
     PG_CHECK(ctx && bits >= 8 && bits <= 10, "pg_debug_set_digit_bits: 8, 9 or 10");

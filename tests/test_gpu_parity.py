@@ -45,6 +45,62 @@ def test_radix_sort_matches_numpy(ctx):
     assert np.array_equal(got, recs[np.argsort(key, kind="stable")])
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_radix_pass_variants(mode, golden_root, ctx):
+    """The three 256-bin pass kernels -- register tile (round 1), persistent bulk-copy (TMA) with 3072-record tiles / 2 stages
+    and with 2048-record tiles / 3 stages -- sort identically (stable), at sizes around the tile and portion edges, and the
+    kmermatcher (whose last partition pass also emits the bucket bounds in the bulk-copy variants) reproduces the golden hits."""
+    lib = api.load_library()
+    before = lib.pg_debug_get_radix_mode()
+    lib.pg_debug_set_radix_mode(mode)
+    try:
+        rng = np.random.default_rng(50 + mode)
+        for n in (1, 17, 2047, 2048, 2049, 3071, 3072, 3073, 6144, 100003, (1 << 21) + 5):
+            recs = rng.integers(0, 1 << 63, size=(n, 2), dtype=np.uint64)
+            recs[: n // 2, 0] &= np.uint64(0xFF)          # heavy duplicates exercise stability
+            got = ctx.debug_radix_sort(recs.copy(), [(0, 0, 24)])
+            key = recs[:, 0] & np.uint64((1 << 24) - 1)
+            assert np.array_equal(got, recs[np.argsort(key, kind="stable")]), (mode, n)
+        recs = rng.integers(0, 1 << 63, size=(700001, 2), dtype=np.uint64)
+        got = ctx.debug_radix_sort(recs.copy(), [(1, 0, 16), (0, 0, 20)])
+        key = ((recs[:, 0] & np.uint64((1 << 20) - 1)) << np.uint64(16)) | (recs[:, 1] & np.uint64(0xFFFF))
+        assert np.array_equal(got, recs[np.argsort(key, kind="stable")])
+        for case in CASES:
+            _kmermatcher_case(case, golden_root, ctx)
+    finally:
+        lib.pg_debug_set_radix_mode(before)
+
+
+def test_spill_list_of_oversized_buckets_matches_oracle(ctx):
+    """A k-mer that occurs in thousands of sequences (here: 1500x coverage of a 300 nt region inside a 20x data set) makes
+    its bucket larger than the shared-memory hash join takes.  Only those buckets go through the spill list (copied out,
+    sorted in full, grouped by the tile kernel); the iteration keeps the fast path and equals the oracle."""
+    from plass_b200 import synth
+    base = synth.make_reads(30000, coverage=20.0, seed=5)
+    rng = np.random.default_rng(6)
+    region = synth.make_genome(330, rng)
+    starts = rng.integers(0, len(region) - 150 + 1, 3000)
+    hot = region[starts[:, None] + np.arange(150)[None, :]]
+    reads = np.concatenate([base, hot])
+    db = synth.protein_fragments(reads)
+    kp, rp, ep = api.default_km_params(False), api.default_rs_params(False), api.default_ex_params(False)
+    ddb = ctx.upload(db)
+    out, hits, alns = ctx.assemble_iteration(ddb, kp, rp, ep, want_intermediates=True)
+    t = ctx.timings()
+    got = out.download()
+    out.free(); ddb.free()
+    assert 0 < t["spilled_records"] < t["n_kmer_records"] // 2, t
+    okp = ob.KmParams(**{f: getattr(kp, f) for f, _ in ob.KmParams._fields_ if f not in ("hash_start", "hash_end")})
+    okp.hash_start, okp.hash_end = 0, ob.U64MAX
+    whits = ob.kmermatch(db, okp)
+    assert len(hits) == len(whits) and all(np.array_equal(hits[f], whits[f]) for f in ("rep", "target", "score", "diag"))
+    walns = ob.rescore(db, whits, ob.RsParams(**{f: getattr(rp, f) for f, _ in ob.RsParams._fields_}))
+    check_alns(alns, walns, "spill list")
+    wout, _ = ob.extend(db, walns, ob.ExParams(**{f: getattr(ep, f) for f, _ in ob.ExParams._fields_}))
+    assert_same_entries(got.entries_by_key(), wout.entries_by_key(), "spill list")
+    print("spill list: %d of %d k-mer records, %d hits" % (t["spilled_records"], t["n_kmer_records"], len(hits)))
+
+
 @pytest.mark.parametrize("bits", [9, 10])
 def test_wide_digit_radix_and_kmermatcher(bits, golden_root, ctx):
     """512- / 1024-bin radix passes (radix_scatter_wide_kernel): sort results and the whole kmermatcher stay identical."""
