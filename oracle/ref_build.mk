@@ -76,6 +76,20 @@ $(OUT)/bin/penguin: $(PENGUIN_OBJ) $(COMMON_OBJ) $(OUT)/libmmseqs-framework.a
 	@mkdir -p $(dir $@)
 	$(CXX) -fopenmp -o $@ $(PENGUIN_OBJ) $(COMMON_OBJ) $(OUT)/libmmseqs-framework.a -lz -latomic -lpthread
 
+# The compiled reference-side binding: the reference's plass tool + three GPU Command rows.
+# Needs plass_b200/libplassgpu.so (python -m plass_b200.build); still test infrastructure, lives beside the reference binaries.
+REPO := $(abspath $(dir $(lastword $(MAKEFILE_LIST)))..)
+SHIM_SRC := $(REPO)/oracle/shim/gpu_commands.cpp
+$(OBJ)/shim/gpu_commands.o: $(SHIM_SRC) $(REPO)/include/plassgpu.h $(GEN)/.stamp
+	@mkdir -p $(dir $@)
+	@echo CXX $< && $(CXX) $(CXXFLAGS) -DPLASS_TOOL_CPP='"$(REF)/src/plass.cpp"' -I$(REPO)/include -c $< -o $@
+
+shim: $(OUT)/bin/plass_gpu_shim
+$(OUT)/bin/plass_gpu_shim: $(OBJ)/shim/gpu_commands.o $(filter-out %/src/plass.cpp.o,$(PLASS_OBJ)) $(COMMON_OBJ) $(OUT)/libmmseqs-framework.a $(REPO)/plass_b200/libplassgpu.so
+	@mkdir -p $(dir $@)
+	$(CXX) -fopenmp -o $@ $(OBJ)/shim/gpu_commands.o $(filter-out %/src/plass.cpp.o,$(PLASS_OBJ)) $(COMMON_OBJ) $(OUT)/libmmseqs-framework.a \
+	    -L$(REPO)/plass_b200 -lplassgpu -Wl,-rpath,'$$ORIGIN/../../../plass_b200' -L/usr/local/cuda/lib64 -Wl,-rpath,/usr/local/cuda/lib64 -lcudart -lz -latomic -lpthread
+
 clean:
 	rm -rf $(OBJ) $(GEN) $(OUT)/bin $(OUT)/libmmseqs-framework.a
-.PHONY: all clean
+.PHONY: all clean shim

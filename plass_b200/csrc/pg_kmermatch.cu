@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
         }
         // all k-mer windows, compacted in position order
         int cnt = 0;
+        bool scoreless = false;
         const int nWin = L - (KT > 0 ? KT : c.k) + 1;
         if constexpr (KT > 0 && NTM == 0 && (KT & 1) == 0) {
             // amino acids, even compile-time k: Indexer::int2index (Indexer.h:20-83) is sum(code[pos+j] * base^j).  The two
@@ -299,6 +300,11 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
             }
             if (lane == 0) xmask[(L + 31) >> 5] = 0;
             __syncwarp();
+            // A read has fewer windows than the bottom-m budget (kmersPerSeq - 1 + scale * L >= number of windows): every k-mer
+            // is taken whatever its score, and with the whole hash range wanted the score is not needed at all -- no XXH64 per
+            // window.  (If the sequence turns out to repeat a k-mer, the scores are computed after all, below.)
+            scoreless = c.ignoreMulti && c.hashStart == 0 && c.hashEnd >= 65535u && nWin > 0 &&
+                        (unsigned long long) ((float) (c.kmersPerSeq - 1) + (c.scale * (float) L)) >= (unsigned long long) nWin;
             for (int p0 = 0; p0 < nWin; p0 += 32) {
                 const int pos = p0 + lane;
                 bool ok = pos < nWin;
@@ -309,7 +315,7 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
                 }
                 if (ok) {
                     cd.kmer = (unsigned long long) half[pos] + (unsigned long long) half[pos + H] * (unsigned long long) baseH;
-                    cd.score = (unsigned) (xxh64_u64(cd.kmer, c.seed) & 0xFFFFULL);
+                    if (!scoreless) cd.score = (unsigned) (xxh64_u64(cd.kmer, c.seed) & 0xFFFFULL);
                 }
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
                 if (ok) cand[cnt + __popc(m & ltMask)] = pack_cand(cd);
@@ -342,7 +348,7 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
             bool dup = false;
             for (int i = lane; i < cnt; i += 32) {
                 const unsigned long long k63 = pc_kmer63(cand[i]);
-                unsigned slot = (unsigned) (mix64(k63) >> 32) & (SLOTS - 1);
+                unsigned slot = (unsigned) ((k63 * 0x9E3779B97F4A7C15ULL) >> 40) & (SLOTS - 1);     // multiplicative hash: the set only has to spread
                 while (true) {
                     const unsigned long long old = atomicCAS(&set[slot], ~0ULL, k63);
                     if (old == ~0ULL) break;
@@ -352,6 +358,16 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
             }
             noDup = __ballot_sync(0xFFFFFFFFu, dup) == 0;
             __syncwarp();
+            if (scoreless && !noDup) {
+                // rare: a repeated k-mer sends the sequence through the sorted walk, which orders by score
+                for (int i = lane; i < cnt; i += 32) {
+                    Cand cd; cd.kmer = pc_kmer_stored(cand[i], c.nt); cd.pos = pc_pos(cand[i]);
+                    cd.score = (unsigned) (xxh64_u64(pc_kmer63(cand[i]), c.seed) & 0xFFFFULL);
+                    cand[i] = pack_cand(cd);
+                }
+                __syncwarp();
+                scoreless = false;
+            }
         }
         const bool allDistinct = noDup && kmerConsidered >= (unsigned long long) cnt;
         // Sort-free selection when only a part of the (distinct) k-mers is taken -- the nucleotide workflow keeps
@@ -2101,6 +2117,7 @@ static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, 
     const unsigned keyLo = std::min(ctx->ownLo, nKeys), keyHi = std::min(ctx->ownHi, nKeys);   // representatives of this rank
     RadixPlan plan; plan.npasses = 0;
     if (ctx->digitBits > 8) plan_add_bits_w(plan, 0, 32, 32 + keyBits, ctx->digitBits);
+    else if (keyLo > 0 || keyHi < nKeys) plan_add_rebased_high_bits(plan, keyLo, bits_for(keyHi > keyLo ? keyHi - 1 - keyLo : 0));   // multi-GPU: only the owned key range
     else plan_add_bits(plan, 0, 32, 32 + keyBits);
     PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nPairs, ctx->digitBits)));
     Rec *sorted = pairs;
@@ -2389,9 +2406,9 @@ int km_shard_route(Context *ctx, int world, const unsigned *bounds, uint64_t *co
     PG_TRY(ctx->small.reserve(4096));
     unsigned *d_bounds = (unsigned *) (ctx->small.as<unsigned long long>() + 64);     // [64..] 257 x u32
     PG_CUDA(cudaMemcpyAsync(d_bounds, bounds, sizeof(unsigned) * (world + 1), cudaMemcpyHostToDevice, s));
-    tag_owner_kernel<<<NUM_SMS * 8, 256, 0, s>>>(pairs, nPairs, d_bounds, (unsigned) world);
+    // one partition pass whose digit is the owner: the interval of bounds[] that holds the representative
     RadixPlan plan; plan.npasses = 0;
-    plan_add_bits(plan, 1, 24, 32);
+    plan_add_interval(plan, d_bounds, (unsigned) world);
     PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nPairs)));
     Rec *sorted = nullptr;
     PG_TRY(radix_sort(pairs, tmp, nPairs, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches));

@@ -10,7 +10,13 @@ namespace {
 
 __device__ __forceinline__ unsigned digit_of(const Rec &r, const DigitPass p) {
     unsigned long long w = p.word ? r.w1 : r.w0;
-    if (p.hashed) w = mix64(w & p.hashMask);
+    if (p.hashed == 1) w = mix64(w & p.hashMask);
+    else if (p.hashed == 2) {
+        const unsigned key = (unsigned) (r.w0 >> 32);
+        unsigned d = 0;
+        for (unsigned i = 1; i < p.auxN; i++) d += (key >= __ldg(p.aux + i)) ? 1u : 0u;
+        return d;
+    } else if (p.hashed == 3) w = (w >> 32) - p.hashMask;
     return (unsigned) (w >> p.shift) & p.mask;
 }
 
@@ -382,23 +388,23 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int ITEMS, int STAGES, bool BOUNDS>
-__global__ void __launch_bounds__(RADIX_THREADS, 2) radix_scatter_tma_kernel(
+template <int THREADS, int MINB, int ITEMS, int STAGES, bool BOUNDS>
+__global__ void __launch_bounds__(THREADS, MINB) radix_scatter_tma_kernel(
     const Rec *__restrict__ in, Rec *__restrict__ out, unsigned long long portionStart, unsigned long long portionEnd,
     DigitPass dp, const unsigned long long *__restrict__ gbase, unsigned long long *__restrict__ gbaseNext,
     unsigned *status, unsigned *ticket, unsigned numTiles, RadixBounds bo) {
-    constexpr int TILE = RADIX_THREADS * ITEMS;
-    constexpr int WARPS = RADIX_THREADS / 32;
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];          // STAGES x TILE records
     __shared__ unsigned short warpCnt[WARPS][256];
     __shared__ unsigned digitStart[256];
-    __shared__ unsigned digitCnt[256];
-    __shared__ long long goff[256];
-    __shared__ unsigned warpTotals[WARPS];
+    __shared__ long long goff[BOUNDS ? 256 : 1];
+    __shared__ unsigned warpTotals[8];
     __shared__ unsigned sTile[STAGES];
     __shared__ __align__(8) unsigned long long bar[STAGES];
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const bool digitThread = tid < 256;                                  // thread d < 256 owns digit d
     const unsigned ltMask = (1u << lane) - 1u;
     auto bufOf = [&](int st) { return reinterpret_cast<Rec *>(smem_raw) + (size_t) st * TILE; };
     auto tileCount = [&](unsigned tile) {
@@ -436,7 +442,7 @@ __global__ void __launch_bounds__(RADIX_THREADS, 2) radix_scatter_tma_kernel(
         Rec *buf = bufOf(cur);
         // the stage the next tile goes to was last used by tile it+1-STAGES, whose bulk stores have been waited for
         if (tid == 0) fetch((int) ((it + 1) % STAGES));
-        for (int i = tid; i < WARPS * 256; i += RADIX_THREADS) (&warpCnt[0][0])[i] = 0;
+        for (int i = tid; i < WARPS * 128; i += THREADS) reinterpret_cast<unsigned *>(&warpCnt[0][0])[i] = 0;
         while (!mbar_try_wait(&bar[cur], (it / STAGES) & 1u)) { }
         __syncthreads();
 
@@ -473,8 +479,8 @@ __global__ void __launch_bounds__(RADIX_THREADS, 2) radix_scatter_tma_kernel(
         }
         __syncthreads();
         // per digit: exclusive prefix over warps, total count
-        unsigned cnt;
-        {
+        unsigned cnt = 0, myStart = 0;
+        if (digitThread) {
             unsigned run = 0;
 #pragma unroll
             for (int ww = 0; ww < WARPS; ww++) {
@@ -483,10 +489,9 @@ __global__ void __launch_bounds__(RADIX_THREADS, 2) radix_scatter_tma_kernel(
                 run += c;
             }
             cnt = run;
+            if (tile == 0) st_volatile_u32(&status[tid], (cnt << 2) | FLAG_INC);
+            else st_volatile_u32(&status[(size_t) tile * 256 + tid], (cnt << 2) | FLAG_AGG);
         }
-        if (tile == 0) st_volatile_u32(&status[tid], (cnt << 2) | FLAG_INC);
-        else st_volatile_u32(&status[(size_t) tile * 256 + tid], (cnt << 2) | FLAG_AGG);
-        unsigned myStart;
         {
             unsigned v = cnt;
 #pragma unroll
@@ -494,14 +499,15 @@ __global__ void __launch_bounds__(RADIX_THREADS, 2) radix_scatter_tma_kernel(
                 const unsigned nb = __shfl_up_sync(0xFFFFFFFFu, v, o);
                 if (lane >= o) v += nb;
             }
-            if (lane == 31) warpTotals[w] = v;
+            if (digitThread && lane == 31) warpTotals[w] = v;
             __syncthreads();
-            unsigned woff = 0;
+            if (digitThread) {
+                unsigned woff = 0;
 #pragma unroll
-            for (int ww = 0; ww < WARPS; ww++) woff += (ww < w) ? warpTotals[ww] : 0u;
-            myStart = woff + v - cnt;
-            digitStart[tid] = myStart;
-            digitCnt[tid] = cnt;
+                for (int ww = 0; ww < 8; ww++) woff += (ww < w) ? warpTotals[ww] : 0u;
+                myStart = woff + v - cnt;
+                digitStart[tid] = myStart;
+            }
         }
         __syncthreads();
         // in-place reorder: every thread holds its records in registers since before the two barriers above
@@ -518,8 +524,8 @@ __global__ void __launch_bounds__(RADIX_THREADS, 2) radix_scatter_tma_kernel(
         }
         fence_async_smem();                       // the reordered tile must be visible to the copy engine
         // decoupled look-back: exclusive prefix of this digit over all earlier tiles of the portion
-        unsigned long long myGlobal;
-        {
+        unsigned long long myGlobal = 0;
+        if (digitThread) {
             unsigned long long prev = 0;
             if (tile > 0) {
                 long long ll = (long long) tile - 1;
@@ -550,12 +556,12 @@ __global__ void __launch_bounds__(RADIX_THREADS, 2) radix_scatter_tma_kernel(
         }
         __syncthreads();
         // one bulk copy per digit run
-        if (cnt) bulk_s2g(out + myGlobal, buf + myStart, cnt * (unsigned) sizeof(Rec));
+        if (digitThread && cnt) bulk_s2g(out + myGlobal, buf + myStart, cnt * (unsigned) sizeof(Rec));
         bulk_commit();
         if (BOUNDS) {
             // bucket boundaries + smallest key from the reordered tile (neighbours in the tile are neighbours in the output
             // as long as they share the digit, and the bucket id contains the digit)
-            for (unsigned j0 = 0; j0 < count; j0 += RADIX_THREADS) {
+            for (unsigned j0 = 0; j0 < count; j0 += THREADS) {
                 const unsigned j = j0 + tid;
                 const bool valid = j < count;
                 unsigned long long hb = ~0ULL;
@@ -602,47 +608,63 @@ inline unsigned long long max_tiles(uint64_t n) {
 
 void radix_set_items(int items) { g_items = (items == 8 || items == 16) ? items : 12; }
 
-// 0: register-tile kernel; 1: bulk-copy kernel, 3072-record tiles, 2 stages; 2: bulk-copy kernel, 2048-record tiles, 3 stages
+// 0: register-tile kernel; 1 / 2 / 3: bulk-copy kernel variants (see tma_tile)
 static int g_mode = -1;
 int radix_get_mode() {
     if (g_mode < 0) {
         g_mode = 1;
-        if (const char *e = getenv("PLASS_B200_RADIX_MODE")) { const int m = atoi(e); if (m >= 0 && m <= 2) g_mode = m; }
+        if (const char *e = getenv("PLASS_B200_RADIX_MODE")) { const int m = atoi(e); if (m >= 0 && m <= 3) g_mode = m; }
     }
     return g_mode;
 }
-void radix_set_mode(int mode) { g_mode = (mode >= 0 && mode <= 2) ? mode : 1; }
+void radix_set_mode(int mode) { g_mode = (mode >= 0 && mode <= 3) ? mode : 1; }
 
 bool radix_emits_bounds(const RadixPlan &plan) {
     if (radix_get_mode() == 0 || plan.npasses == 0) return false;
-    for (int p = 0; p < plan.npasses; p++) if (plan.pass[p].mask > 255u || !plan.pass[p].hashed) return false;
+    for (int p = 0; p < plan.npasses; p++) if (plan.pass[p].mask > 255u || plan.pass[p].hashed != 1) return false;
     return true;
 }
 
-template <int ITEMS, int STAGES>
+template <int THREADS, int MINB, int ITEMS, int STAGES>
 static int launch_tma(const Rec *src, Rec *dst, unsigned long long ps, unsigned long long pe, const DigitPass &dp, const unsigned long long *gb,
-                      unsigned long long *gbNext, unsigned *status, unsigned *ticket, const RadixBounds *bounds, cudaStream_t stream, unsigned *tilesOut) {
-    constexpr int TILE = RADIX_THREADS * ITEMS;
+                      unsigned long long *gbNext, unsigned *status, unsigned *ticket, const RadixBounds *bounds, cudaStream_t stream) {
+    constexpr int TILE = THREADS * ITEMS;
     const int smem = STAGES * TILE * (int) sizeof(Rec);
     static bool attr[2] = {false, false};
     const unsigned tiles = (unsigned) ((pe - ps + TILE - 1) / TILE);
-    *tilesOut = tiles;
-    const unsigned grid = std::min<unsigned>(tiles, (unsigned) NUM_SMS * 2u);
+    const unsigned grid = std::min<unsigned>(tiles, (unsigned) NUM_SMS * (unsigned) MINB);
     if (bounds) {
-        if (!attr[1]) { PG_CUDA(cudaFuncSetAttribute(radix_scatter_tma_kernel<ITEMS, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[1] = true; }
-        radix_scatter_tma_kernel<ITEMS, STAGES, true><<<grid, RADIX_THREADS, smem, stream>>>(src, dst, ps, pe, dp, gb, gbNext, status, ticket, tiles, *bounds);
+        if (!attr[1]) { PG_CUDA(cudaFuncSetAttribute(radix_scatter_tma_kernel<THREADS, MINB, ITEMS, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[1] = true; }
+        radix_scatter_tma_kernel<THREADS, MINB, ITEMS, STAGES, true><<<grid, THREADS, smem, stream>>>(src, dst, ps, pe, dp, gb, gbNext, status, ticket, tiles, *bounds);
     } else {
-        if (!attr[0]) { PG_CUDA(cudaFuncSetAttribute(radix_scatter_tma_kernel<ITEMS, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[0] = true; }
-        radix_scatter_tma_kernel<ITEMS, STAGES, false><<<grid, RADIX_THREADS, smem, stream>>>(src, dst, ps, pe, dp, gb, gbNext, status, ticket, tiles, RadixBounds());
+        if (!attr[0]) { PG_CUDA(cudaFuncSetAttribute(radix_scatter_tma_kernel<THREADS, MINB, ITEMS, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[0] = true; }
+        radix_scatter_tma_kernel<THREADS, MINB, ITEMS, STAGES, false><<<grid, THREADS, smem, stream>>>(src, dst, ps, pe, dp, gb, gbNext, status, ticket, tiles, RadixBounds());
     }
     return 0;
 }
+
+// tile size of the bulk-copy variants: mode 1 = 512 threads x 6 records, 2 stages, 2 CTAs / SM (32 warps);
+// mode 2 = 256 threads x 8 records, 2 stages, 3 CTAs / SM (24 warps); mode 3 = 512 threads x 4 records, 3 stages, 2 CTAs / SM
+static unsigned tma_tile(int mode) { return mode == 1 ? 3072u : 2048u; }
 
 void plan_add_bits(RadixPlan &plan, int word, int lo, int hi) {
     for (int b = lo; b < hi; b += 8) {
         const int bits = (hi - b) < 8 ? (hi - b) : 8;
         DigitPass &p = plan.pass[plan.npasses++];
-        p.word = word; p.shift = b; p.mask = (1u << bits) - 1u; p.hashed = 0; p.hashMask = 0;
+        p.word = word; p.shift = b; p.mask = (1u << bits) - 1u; p.hashed = 0; p.hashMask = 0; p.aux = nullptr; p.auxN = 0;
+    }
+}
+
+void plan_add_interval(RadixPlan &plan, const unsigned *deviceBounds, unsigned n) {
+    DigitPass &p = plan.pass[plan.npasses++];
+    p.word = 0; p.shift = 0; p.mask = 255u; p.hashed = 2; p.hashMask = 0; p.aux = deviceBounds; p.auxN = n;
+}
+
+void plan_add_rebased_high_bits(RadixPlan &plan, unsigned long long sub, int nbits) {
+    for (int b = 0; b < nbits; b += 8) {
+        const int bits = (nbits - b) < 8 ? (nbits - b) : 8;
+        DigitPass &p = plan.pass[plan.npasses++];
+        p.word = 0; p.shift = b; p.mask = (1u << bits) - 1u; p.hashed = 3; p.hashMask = sub; p.aux = nullptr; p.auxN = 0;
     }
 }
 
@@ -650,7 +672,7 @@ void plan_add_hash_bits(RadixPlan &plan, unsigned long long hashMask, int lo, in
     for (int b = lo; b < hi; b += 8) {
         const int bits = (hi - b) < 8 ? (hi - b) : 8;
         DigitPass &p = plan.pass[plan.npasses++];
-        p.word = 0; p.shift = b; p.mask = (1u << bits) - 1u; p.hashed = 1; p.hashMask = hashMask;
+        p.word = 0; p.shift = b; p.mask = (1u << bits) - 1u; p.hashed = 1; p.hashMask = hashMask; p.aux = nullptr; p.auxN = 0;
     }
 }
 
@@ -668,7 +690,7 @@ void plan_add_bits_w(RadixPlan &plan, int word, int lo, int hi, int digitBits) {
     for (int i = 0; i < nd; i++) {
         const int bits = (total - (b - lo) + (nd - i) - 1) / (nd - i);      // spread the bits evenly over the digits
         DigitPass &p = plan.pass[plan.npasses++];
-        p.word = word; p.shift = b; p.mask = (1u << bits) - 1u; p.hashed = 0; p.hashMask = 0;
+        p.word = word; p.shift = b; p.mask = (1u << bits) - 1u; p.hashed = 0; p.hashMask = 0; p.aux = nullptr; p.auxN = 0;
         b += bits;
     }
 }
@@ -732,16 +754,16 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
             unsigned tiles = (unsigned) ((pe - ps + tile_records() - 1) / tile_records());
             const int bins = plan.pass[p].mask > 511 ? 1024 : (plan.pass[p].mask > 255 ? 512 : 256);
             const int mode = radix_get_mode();
-            if (bins == 256 && mode != 0) tiles = (unsigned) ((pe - ps + (mode == 2 ? 2048 : 3072) - 1) / (mode == 2 ? 2048 : 3072));
+            if (bins == 256 && mode != 0) tiles = (unsigned) ((pe - ps + tma_tile(mode) - 1) / tma_tile(mode));
             PG_CUDA(cudaMemsetAsync(status, 0, sizeof(unsigned) * ((size_t) tiles * bins + 64), stream));
             unsigned *ticket = status + statusWords - 32;
             PG_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), stream));
             unsigned long long *gb = bases + ((size_t) p * (portions + 1) + q) * stride;
             if (bins == 256 && mode != 0) {
                 const RadixBounds *bp = (bounds && p == plan.npasses - 1 && radix_emits_bounds(plan)) ? bounds : nullptr;
-                unsigned t2 = 0;
-                if (mode == 2) PG_TRY((launch_tma<8, 3>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, bp, stream, &t2)));
-                else PG_TRY((launch_tma<12, 2>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, bp, stream, &t2)));
+                if (mode == 2) PG_TRY((launch_tma<256, 3, 8, 2>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, bp, stream)));
+                else if (mode == 3) PG_TRY((launch_tma<512, 2, 4, 3>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, bp, stream)));
+                else PG_TRY((launch_tma<512, 2, 6, 2>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, bp, stream)));
             } else if (bins == 512) {
                 if (g_items == 16) radix_scatter_wide_kernel<16, 2, 9><<<tiles, RADIX_THREADS, dynSmemWide, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles);
                 else { PG_CHECK(g_items == 12, "radix_sort: wide digits need 12 or 16 records per thread"); radix_scatter_wide_kernel<12, 3, 9><<<tiles, RADIX_THREADS, dynSmemWide, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles); }

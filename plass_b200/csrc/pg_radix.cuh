@@ -23,7 +23,11 @@ struct DigitPass {
     int shift;           // digit = (w >> shift) & mask
     unsigned mask;       // <= 255 (8-bit digits) or <= 1023 (wide digits: 9 / 10 bits, see plan_add_bits_w)
     int hashed;          // 1: w is first replaced by mix64(w & hashMask) -- partition by hash bits instead of key bits
+                         // 2: digit = index of the interval of aux[0..auxN] (ascending) that holds the high half of w0 (owner rank of a representative)
+                         // 3: w is replaced by (w >> 32) - hashMask (keys of a rank's contiguous range, rebased to 0)
     unsigned long long hashMask;
+    const unsigned *aux; // mode 2: device array of interval bounds, aux[0] = 0
+    unsigned auxN;       // mode 2: number of intervals
 };
 
 // murmur3 fmix64: the bucket hash of the partial-key partition (any fixed bijective mixer would do)
@@ -73,6 +77,10 @@ int radix_get_mode();
 void plan_add_bits(RadixPlan &plan, int word, int lo, int hi);
 // same over bits [lo, hi) of mix64(w0 & hashMask)
 void plan_add_hash_bits(RadixPlan &plan, unsigned long long hashMask, int lo, int hi);
+// one pass whose digit is the interval index of (w0 >> 32) in bounds[0..n) (device array, ascending, bounds[0] = 0), n <= 256
+void plan_add_interval(RadixPlan &plan, const unsigned *deviceBounds, unsigned n);
+// 8-bit digits over bits [0, nbits) of (w0 >> 32) - sub
+void plan_add_rebased_high_bits(RadixPlan &plan, unsigned long long sub, int nbits);
 // Wide digits: the bit range is cut into ceil((hi-lo)/digitBits) digits of (almost) equal width <= digitBits (8..10).
 // A 512- or 1024-bin pass costs a little more than a 256-bin pass (status words, shorter store runs) but a 20-bit key
 // takes 2 passes instead of 3.

@@ -112,3 +112,27 @@ def test_workflow_dropin_matches_reference(tool, wf, iters, tmp_path):
             else:
                 bad = [k for k in w if g[k] != w[k] and k not in affected]
                 assert not bad, (name, bad[:5])
+
+
+def test_compiled_reference_plugin_runs_the_workflow(tmp_path):
+    """INTEGRATION.md section 3 as code: oracle/_ref/bin/plass_gpu_shim is the reference's own plass tool (src/plass.cpp compiled
+    from where it lies) with three Command rows in front of its table that bind kmermatcher / rescorediagonal / assembleresults
+    to libplassgpu.so through the reference's Parameters, DBReader and DBWriter (oracle/shim/gpu_commands.cpp).  The unmodified
+    data/assemble.sh, run by that binary, must give the DBs and the FASTA of the unmodified reference."""
+    ref_bin, shim = os.path.join(REF, "plass"), os.path.join(REF, "plass_gpu_shim")
+    if not (os.path.exists(ref_bin) and os.path.exists(shim)):
+        pytest.skip("oracle/_ref/bin/plass_gpu_shim not built (needs the reference sources: python __graft_entry__.py)")
+    fa = str(tmp_path / "reads.fasta")
+    synth.write_fasta(fa, synth.make_reads(3000, seed=33))
+    common = ["--num-iterations", "2", "--remove-tmp-files", "0", "--delete-tmp-inc", "0", "--threads", "1"]
+    run([ref_bin, "assemble", fa, str(tmp_path / "ref.fas"), str(tmp_path / "tmp_ref")] + common)
+    log = run([shim, "assemble", fa, str(tmp_path / "gpu.fas"), str(tmp_path / "tmp_gpu")] + common)
+    assert "B200" in log or "kmermatcher" in log
+    tr, tg = str(tmp_path / "tmp_ref" / "latest"), str(tmp_path / "tmp_gpu" / "latest")
+    for i in range(2):
+        for name in ("pref_%d" % i, "assembly_%d" % i):
+            assert_same_entries(mmseqsdb.read_db(os.path.join(tg, name)).entries_by_key(),
+                                mmseqsdb.read_db(os.path.join(tr, name)).entries_by_key(), "shim %s" % name)
+        aln_entries_close(mmseqsdb.read_db(os.path.join(tg, "aln_%d" % i)).entries_by_key(),
+                          mmseqsdb.read_db(os.path.join(tr, "aln_%d" % i)).entries_by_key())
+    assert open(str(tmp_path / "gpu.fas"), "rb").read() == open(str(tmp_path / "ref.fas"), "rb").read()

@@ -45,10 +45,10 @@ def test_radix_sort_matches_numpy(ctx):
     assert np.array_equal(got, recs[np.argsort(key, kind="stable")])
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_radix_pass_variants(mode, golden_root, ctx):
-    """The three 256-bin pass kernels -- register tile (round 1), persistent bulk-copy (TMA) with 3072-record tiles / 2 stages
-    and with 2048-record tiles / 3 stages -- sort identically (stable), at sizes around the tile and portion edges, and the
+    """The 256-bin pass kernels -- register tile (round 1) and the persistent bulk-copy (TMA) variants (512 threads x 6 records /
+    2 stages, 256 x 8 / 2 stages at 3 CTAs per SM, 512 x 4 / 3 stages) -- sort identically (stable), at sizes around the tile edges, and the
     kmermatcher (whose last partition pass also emits the bucket bounds in the bulk-copy variants) reproduces the golden hits."""
     lib = api.load_library()
     before = lib.pg_debug_get_radix_mode()
