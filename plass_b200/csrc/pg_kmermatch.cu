@@ -238,6 +238,12 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
     Rec *outRecs = reinterpret_cast<Rec *>(smem_raw + (size_t) WARPS * NMAX * sizeof(PCand)) + (size_t) w * (NMAX + 1);
     unsigned char *codes = smem_raw + (size_t) WARPS * NMAX * sizeof(PCand) + (size_t) WARPS * (NMAX + 1) * sizeof(Rec) + (size_t) w * CODES;
 
+    // powers of 31 for the whole-sequence hash of short sequences (Util::hash: h = h * 31 + code), one table per CTA
+    __shared__ unsigned long long sPow31[NMAX <= 64 ? 128 : 1];
+    if (NMAX <= 64) {
+        if (threadIdx.x < 128) { unsigned long long pw = 1; for (int j = 0; j < (int) threadIdx.x; j++) pw *= 31ULL; sPow31[threadIdx.x] = pw; }
+        __syncthreads();
+    }
     const unsigned nList = *listCount;
     for (unsigned li = blockIdx.x * WARPS + w; li < nList; li += gridDim.x * WARPS) {
         const unsigned si = list[li];
@@ -257,7 +263,14 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
         // whole-sequence hash: Util::hash (poly 31) then XXH64 (kmermatcher.cpp:133-138).  Each lane hashes a
         // chunk; H(AB) = H(A) * 31^|B| + H(B) is associative, so the chunks fold in log2(32) shuffle steps.
         unsigned long long seqHash;
-        {
+        if (NMAX <= 64 && L <= 128) {
+            // sum(code[i] * 31^(L-1-i)) == the Horner form, modulo 2^64: every lane takes the positions lane, lane + 32, ...
+            unsigned long long h = 0;
+            for (int i = lane; i < L; i += 32) h += (unsigned long long) codes[i] * sPow31[L - 1 - i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xFFFFFFFFu, h, o);
+            seqHash = xxh64_u64(h, c.seed);
+        } else {
             const int chunk = (L + 31) / 32;
             const int b = min(L, lane * chunk), e = min(L, b + chunk);
             unsigned long long h = 0, pw = 1;
@@ -305,6 +318,73 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
             // window.  (If the sequence turns out to repeat a k-mer, the scores are computed after all, below.)
             scoreless = c.ignoreMulti && c.hashStart == 0 && c.hashEnd >= 65535u && nWin > 0 &&
                         (unsigned long long) ((float) (c.kmersPerSeq - 1) + (c.scale * (float) L)) >= (unsigned long long) nWin;
+            if (NMAX <= 64 && scoreless) {
+                // Fused path of a read: window -> k-mer -> duplicate check -> record, no candidate list, no score.  At most two
+                // windows per lane (NMAX = 64), held in registers while the half sums (which alias the staging area) are alive.
+                unsigned long long km[2]; bool okk[2];
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const int pos = r * 32 + lane;
+                    bool ok = pos < nWin;
+                    if (ok) {
+                        const unsigned long long xb = ((unsigned long long) xmask[pos >> 5] | ((unsigned long long) xmask[(pos >> 5) + 1] << 32)) >> (pos & 31);
+                        ok = (xb & ((1ULL << KT) - 1ULL)) == 0;
+                    }
+                    km[r] = ok ? (unsigned long long) half[pos] + (unsigned long long) half[pos + H] * (unsigned long long) baseH : 0ULL;
+                    okk[r] = ok;
+                }
+                __syncwarp();                                 // half / xmask are dead: the staging area takes the records
+                unsigned long long *set = reinterpret_cast<unsigned long long *>(cand);        // 2 * NMAX slots in the (unused) candidate area
+                constexpr unsigned SLOTS = 2 * NMAX;
+                for (int i = lane; i < (int) SLOTS; i += 32) set[i] = ~0ULL;
+                __syncwarp();
+                bool dup = false;
+                int n = 0;
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, okk[r]);
+                    if (okk[r]) {
+                        unsigned slot = (unsigned) ((km[r] * 0x9E3779B97F4A7C15ULL) >> 40) & (SLOTS - 1);
+                        while (true) {
+                            const unsigned long long old = atomicCAS(&set[slot], ~0ULL, km[r]);
+                            if (old == ~0ULL) break;
+                            if (old == km[r]) { dup = true; break; }
+                            slot = (slot + 1) & (SLOTS - 1);
+                        }
+                        Rec rr; rr.w0 = km[r]; rr.w1 = kmer_w1(c, id, si, (unsigned) L, (unsigned) (r * 32 + lane));
+                        outRecs[1 + n + __popc(m & ltMask)] = rr;
+                    }
+                    n += __popc(m);
+                }
+                if (__ballot_sync(0xFFFFFFFFu, dup) == 0) {
+                    // every k-mer is taken (kmermatcher.cpp:274-347 with kmerConsidered >= the number of k-mers, all distinct);
+                    // the sequence-identity record goes first (:241-246)
+                    if (lane == 0) { Rec r0; r0.w0 = seqHash; r0.w1 = kmer_w1(c, id, si, (unsigned) L, 0u); outRecs[0] = r0; }
+                    const int nOutF = n + 1;
+                    __syncwarp();
+                    unsigned long long baseF = 0;
+                    if (lane == 0) baseF = atomicAdd(outCount, (unsigned long long) nOutF);
+                    baseF = __shfl_sync(0xFFFFFFFFu, baseF, 0);
+                    if (baseF + nOutF <= outCap)
+                        for (int i = lane; i < nOutF; i += 32) out[baseF + i] = outRecs[i];
+                    __syncwarp();
+                    continue;
+                }
+                // a repeated k-mer (rare): the sorted walk decides, with scores, from the candidate list
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, okk[r]);
+                    if (okk[r]) {
+                        Cand cd; cd.kmer = km[r]; cd.pos = (unsigned) (r * 32 + lane);
+                        cd.score = (unsigned) (xxh64_u64(km[r], c.seed) & 0xFFFFULL);
+                        cand[cnt + __popc(m & ltMask)] = pack_cand(cd);
+                    }
+                    cnt += __popc(m);
+                }
+                scoreless = false;
+                __syncwarp();
+            } else
             for (int p0 = 0; p0 < nWin; p0 += 32) {
                 const int pos = p0 + lane;
                 bool ok = pos < nWin;

@@ -392,7 +392,7 @@ template <int THREADS, int MINB, int ITEMS, int STAGES, bool BOUNDS>
 __global__ void __launch_bounds__(THREADS, MINB) radix_scatter_tma_kernel(
     const Rec *__restrict__ in, Rec *__restrict__ out, unsigned long long portionStart, unsigned long long portionEnd,
     DigitPass dp, const unsigned long long *__restrict__ gbase, unsigned long long *__restrict__ gbaseNext,
-    unsigned *status, unsigned *ticket, unsigned numTiles, RadixBounds bo) {
+    unsigned *status, unsigned *ticket, unsigned numTiles, RadixBounds bo, unsigned staggerCycles) {
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];          // STAGES x TILE records
@@ -430,7 +430,16 @@ __global__ void __launch_bounds__(THREADS, MINB) radix_scatter_tma_kernel(
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) fetch(0);
+    // All CTAs of a persistent grid start together; left alone they would run in lockstep, every tile's look-back would find
+    // the ~300 tiles in flight all in the "aggregate only" state and walk back over a whole wave of status words.  Spreading
+    // the first tickets over one tile period keeps the tiles in flight at evenly spread phases (as a grid of short-lived
+    // CTAs is by itself), so a look-back finds an inclusive prefix within a few tiles.
+    if (tid == 0) {
+        const long long wait = (long long) ((unsigned long long) staggerCycles * blockIdx.x / gridDim.x);
+        const long long t0 = clock64();
+        while (clock64() - t0 < wait) { }
+        fetch(0);
+    }
     unsigned long long localMin = ~0ULL;
     __syncthreads();
 
@@ -633,12 +642,16 @@ static int launch_tma(const Rec *src, Rec *dst, unsigned long long ps, unsigned 
     static bool attr[2] = {false, false};
     const unsigned tiles = (unsigned) ((pe - ps + TILE - 1) / TILE);
     const unsigned grid = std::min<unsigned>(tiles, (unsigned) NUM_SMS * (unsigned) MINB);
+    // one tile period: 2 x TILE x 16 B per CTA at this SM's share of ~5 TB/s (read + write), in SM cycles at ~1.9 GHz
+    static int stagger = -1;
+    if (stagger < 0) { stagger = 11000; if (const char *e = getenv("PLASS_B200_RADIX_STAGGER")) stagger = std::max(0, atoi(e)); }
+    const unsigned staggerCycles = tiles > grid ? (unsigned) stagger : 0u;
     if (bounds) {
         if (!attr[1]) { PG_CUDA(cudaFuncSetAttribute(radix_scatter_tma_kernel<THREADS, MINB, ITEMS, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[1] = true; }
-        radix_scatter_tma_kernel<THREADS, MINB, ITEMS, STAGES, true><<<grid, THREADS, smem, stream>>>(src, dst, ps, pe, dp, gb, gbNext, status, ticket, tiles, *bounds);
+        radix_scatter_tma_kernel<THREADS, MINB, ITEMS, STAGES, true><<<grid, THREADS, smem, stream>>>(src, dst, ps, pe, dp, gb, gbNext, status, ticket, tiles, *bounds, staggerCycles);
     } else {
         if (!attr[0]) { PG_CUDA(cudaFuncSetAttribute(radix_scatter_tma_kernel<THREADS, MINB, ITEMS, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[0] = true; }
-        radix_scatter_tma_kernel<THREADS, MINB, ITEMS, STAGES, false><<<grid, THREADS, smem, stream>>>(src, dst, ps, pe, dp, gb, gbNext, status, ticket, tiles, RadixBounds());
+        radix_scatter_tma_kernel<THREADS, MINB, ITEMS, STAGES, false><<<grid, THREADS, smem, stream>>>(src, dst, ps, pe, dp, gb, gbNext, status, ticket, tiles, RadixBounds(), staggerCycles);
     }
     return 0;
 }
