@@ -201,9 +201,10 @@ def parity_and_dropin(workdir, seq, threads, ref_per):
     w = lambda x: os.path.join(workdir, x)  # noqa: E731
     flags = lambda s: s.split()  # noqa: E731
     # (a) the three commands as data/assemble.sh calls them, one process each
-    t_km, _ = run_cli(["kmermatcher", seq, w("g_pref")] + flags(KM_FLAGS), threads)
-    t_rs, _ = run_cli(["rescorediagonal", seq, seq, w("g_pref"), w("g_aln")] + flags(RS_FLAGS), threads)
-    t_ex, _ = run_cli(["assembleresults", seq, w("g_aln"), w("g_asm")] + flags(EX_FLAGS), threads)
+    t_km, o_km = run_cli(["kmermatcher", seq, w("g_pref")] + flags(KM_FLAGS), threads)
+    t_rs, o_rs = run_cli(["rescorediagonal", seq, seq, w("g_pref"), w("g_aln")] + flags(RS_FLAGS), threads)
+    t_ex, o_ex = run_cli(["assembleresults", seq, w("g_aln"), w("g_asm")] + flags(EX_FLAGS), threads)
+    phases = {n: ([x for x in o.splitlines() if x.startswith("Phases:")] or [None])[-1] for n, o in (("kmermatcher", o_km), ("rescorediagonal", o_rs), ("assembleresults", o_ex))}
     d_pref, d_aln, d_asm = dbdiff(w("g_pref"), w("pref"), "exact"), dbdiff(w("g_aln"), w("aln"), "aln"), dbdiff(w("g_asm"), w("asm"), "exact")
     # (b) the same iteration fused in one process
     union = flags(KM_FLAGS) + ["--rescore-mode", "3", "--wrapped-scoring", "0", "--filter-hits", "0", "-e", "1e-05", "-a", "0", "--min-aln-len", "0",
@@ -221,6 +222,7 @@ def parity_and_dropin(workdir, seq, threads, ref_per):
                             "formatting, DB write), SURVEY.md 8d; tmp dir %s; %d host threads" % (workdir, threads),
               "reference_s": {"kmermatcher": ref_per[0], "rescorediagonal": ref_per[1], "assembleresults": ref_per[2], "iteration": ref_total},
               "gpu_cli_s": {"kmermatcher": t_km, "rescorediagonal": t_rs, "assembleresults": t_ex, "iteration": t_km + t_rs + t_ex},
+              "gpu_cli_phases": phases,
               "gpu_cli_fused_s": t_fused, "gpu_cli_fused_phases": [x for x in out_fused.splitlines() if x.startswith("open + index parse")][-1:] or None,
               "speedup_three_commands": ref_total / (t_km + t_rs + t_ex), "speedup_fused": ref_total / t_fused}
     return parity, dropin

@@ -14,6 +14,7 @@
 #include <omp.h>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -113,14 +114,32 @@ struct Timer {
     }
 };
 
-pg_context *gpu() {
-    static pg_context *ctx = nullptr;
-    if (!ctx) {
-        const char *dev = getenv("PLASS_B200_DEVICE");
-        if (pg_init(dev ? atoi(dev) : 0, &ctx) != 0) die(pg_last_error());
+// The CUDA context (driver start-up, module load: a few hundred ms) is created by a helper thread while the main thread
+// opens the DBs and parses their indices; gpu() joins it at the first use.
+struct GpuInit {
+    std::thread worker;
+    pg_context *ctx = nullptr;
+    std::string error;
+    bool started = false;
+    void start() {
+        if (started) return;
+        started = true;
+        worker = std::thread([this] {
+            const char *dev = getenv("PLASS_B200_DEVICE");
+            if (pg_init(dev ? atoi(dev) : 0, &ctx) != 0) error = pg_last_error();
+        });
     }
-    return ctx;
-}
+    pg_context *get() {
+        start();
+        if (worker.joinable()) worker.join();
+        if (!ctx) die(error.empty() ? "pg_init failed" : error);
+        return ctx;
+    }
+};
+GpuInit g_gpuInit;
+pg_context *gpu() { return g_gpuInit.get(); }
+void gpuWarmUp() { g_gpuInit.start(); }
+
 
 // --threads N (Parameters.cpp:2124): host threads of the text layer (index parse, entry parse, formatting, pwrite)
 void applyThreads(const Flags &f) {
@@ -478,6 +497,7 @@ int extendCommand(int argc, const char **argv, bool nuclCommand) {
     Phases ph;
     const Flags f = parseFlags(argc, argv, 3, EX_FLAGS);
     applyThreads(f);
+    gpuWarmUp();
     requireValue(f, "--compressed", "0", "uncompressed DBs only");
     checkSubMat(f);
     std::string err;
@@ -512,6 +532,7 @@ int kmermatcher(int argc, const char **argv) {
     Phases ph;
     const Flags f = parseFlags(argc, argv, 2, KM_FLAGS);
     applyThreads(f);
+    gpuWarmUp();
     checkKmFlags(f);
     std::string err;
     mmdb::Reader seq;
@@ -540,6 +561,7 @@ int rescorediagonal(int argc, const char **argv) {
     Phases ph;
     const Flags f = parseFlags(argc, argv, 4, RS_FLAGS);
     applyThreads(f);
+    gpuWarmUp();
     checkRsFlags(f);
     if (f.positional[0] != f.positional[1]) die("rescorediagonal on the GPU path requires query DB == target DB (as in assemble.sh / nuclassemble.sh)");
     std::string err;
@@ -574,6 +596,7 @@ int findassemblystart(int argc, const char **argv) {
     Timer timer;
     const Flags f = parseFlags(argc, argv, 3, FS_FLAGS);
     applyThreads(f);
+    gpuWarmUp();
     requireValue(f, "--compressed", "0", "uncompressed DBs only");
     std::string err;
     mmdb::Reader seq, aln;
@@ -594,6 +617,7 @@ int extractorfs(int argc, const char **argv) {
     Timer timer;
     const Flags f = parseFlags(argc, argv, 2, ORF_FLAGS);
     applyThreads(f);
+    gpuWarmUp();
     requireValue(f, "--compressed", "0", "uncompressed DBs only");
     requireValue(f, "--create-lookup", "0", "lookup files are not written by the GPU path");
     requireValue(f, "--id-offset", "0", "not used by the assemble workflow");
@@ -647,6 +671,7 @@ int translatenucs(int argc, const char **argv) {
     Timer timer;
     const Flags f = parseFlags(argc, argv, 2, TN_FLAGS);
     applyThreads(f);
+    gpuWarmUp();
     requireValue(f, "--compressed", "0", "uncompressed DBs only");
     std::string err;
     mmdb::Reader seq;
@@ -692,6 +717,7 @@ int cyclecheck(int argc, const char **argv) {
     Timer timer;
     const Flags f = parseFlags(argc, argv, 2, CC_FLAGS);
     applyThreads(f);
+    gpuWarmUp();
     requireValue(f, "--compressed", "0", "uncompressed DBs only");
     std::string err;
     mmdb::Reader seq;
@@ -737,6 +763,7 @@ int assembleiteration(int argc, const char **argv) {
     known.insert(EX_FLAGS.begin(), EX_FLAGS.end());
     const Flags f = parseFlags(argc, argv, 4, known);
     applyThreads(f);
+    gpuWarmUp();
     checkKmFlags(f);
     checkRsFlags(f);
     std::string err;

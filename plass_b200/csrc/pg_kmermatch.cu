@@ -1562,19 +1562,31 @@ __device__ __forceinline__ void agg_step(unsigned d, unsigned cnt, unsigned rv, 
 __device__ __forceinline__ bool rh_insert(const Rec *__restrict__ in, unsigned long long s0, unsigned count, unsigned first, unsigned step,
                                           unsigned long long *sKey, unsigned *sCnt, unsigned tmask) {
     bool okAll = true;
-    for (unsigned i = first; i < count; i += step) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(in + s0) + i);
-        const unsigned long long key = ((unsigned long long) raw.x << 16) | (unsigned long long) (raw.z & 0xFFFFu);   // target, biased diagonal
-        const unsigned strand = (raw.z >> 16) & 1u;
-        unsigned slot = (unsigned) (mix64(key) >> 40) & tmask;
-        bool placed = false;
-        for (int probe = 0; probe < RH_PROBE_MAX; probe++) {
-            const unsigned long long old = atomicCAS(&sKey[slot], ~0ULL, key);
-            if (old == ~0ULL || old == key) { placed = true; break; }
-            slot = (slot + 1) & tmask;
+    // four independent loads in flight per lane: the insert loop is otherwise one exposed DRAM latency per record
+    for (unsigned i0 = first; i0 < count; i0 += 4 * step) {
+        uint4 raws[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned i = i0 + u * step;
+            if (i < count) raws[u] = __ldg(reinterpret_cast<const uint4 *>(in + s0) + i);
         }
-        if (placed) atomicAdd(&sCnt[slot], 1u + (strand << 16));
-        else okAll = false;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned i = i0 + u * step;
+            if (i >= count) break;
+            const uint4 raw = raws[u];
+            const unsigned long long key = ((unsigned long long) raw.x << 16) | (unsigned long long) (raw.z & 0xFFFFu);   // target, biased diagonal
+            const unsigned strand = (raw.z >> 16) & 1u;
+            unsigned slot = (unsigned) (mix64(key) >> 40) & tmask;
+            bool placed = false;
+            for (int probe = 0; probe < RH_PROBE_MAX; probe++) {
+                const unsigned long long old = atomicCAS(&sKey[slot], ~0ULL, key);
+                if (old == ~0ULL || old == key) { placed = true; break; }
+                slot = (slot + 1) & tmask;
+            }
+            if (placed) atomicAdd(&sCnt[slot], 1u + (strand << 16));
+            else okAll = false;
+        }
     }
     return okAll;
 }

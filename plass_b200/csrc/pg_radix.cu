@@ -8,17 +8,24 @@ namespace pg {
 
 namespace {
 
-__device__ __forceinline__ unsigned digit_of(const Rec &r, const DigitPass p) {
+// EXT = false: the two digit kinds of the single-GPU path (plain bits, bits of mix64); EXT = true adds the two kinds of
+// the multi-GPU path (owner interval, rebased key).  Separate instances: the extra cases cost the hot kernels ~12 %.
+template <bool EXT>
+__device__ __forceinline__ unsigned digit_of_t(const Rec &r, const DigitPass p) {
     unsigned long long w = p.word ? r.w1 : r.w0;
-    if (p.hashed == 1) w = mix64(w & p.hashMask);
-    else if (p.hashed == 2) {
-        const unsigned key = (unsigned) (r.w0 >> 32);
-        unsigned d = 0;
-        for (unsigned i = 1; i < p.auxN; i++) d += (key >= __ldg(p.aux + i)) ? 1u : 0u;
-        return d;
-    } else if (p.hashed == 3) w = (w >> 32) - p.hashMask;
+    if (EXT) {
+        if (p.hashed == 2) {
+            const unsigned key = (unsigned) (r.w0 >> 32);
+            unsigned d = 0;
+            for (unsigned i = 1; i < p.auxN; i++) d += (key >= __ldg(p.aux + i)) ? 1u : 0u;
+            return d;
+        }
+        if (p.hashed == 3) { w = (w >> 32) - p.hashMask; return (unsigned) (w >> p.shift) & p.mask; }
+    }
+    if (p.hashed) w = mix64(w & p.hashMask);
     return (unsigned) (w >> p.shift) & p.mask;
 }
+__device__ __forceinline__ unsigned digit_of(const Rec &r, const DigitPass p) { return digit_of_t<true>(r, p); }
 
 __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
     unsigned v;
@@ -30,6 +37,7 @@ __device__ __forceinline__ void st_volatile_u32(unsigned *p, unsigned v) {
 }
 
 // ---- histograms of all passes in one read -------------------------------------------------------
+template <bool EXT>
 __global__ void __launch_bounds__(512) radix_hist_kernel(const Rec *__restrict__ in, unsigned long long n, RadixPlan plan,
                                                          unsigned long long *__restrict__ ghist, int stride) {
     extern __shared__ unsigned sh[];          // npasses x stride counters (stride = 256, or 512 / 1024 with wide digits)
@@ -43,7 +51,7 @@ __global__ void __launch_bounds__(512) radix_hist_kernel(const Rec *__restrict__
         r.w0 = ((unsigned long long) raw.y << 32) | raw.x;
         r.w1 = ((unsigned long long) raw.w << 32) | raw.z;
 #pragma unroll 4
-        for (int p = 0; p < np; p++) atomicAdd(&sh[p * stride + digit_of(r, plan.pass[p])], 1u);
+        for (int p = 0; p < np; p++) atomicAdd(&sh[p * stride + digit_of_t<EXT>(r, plan.pass[p])], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < np * stride; i += blockDim.x)
@@ -68,11 +76,11 @@ __global__ void radix_scan_kernel(const unsigned long long *__restrict__ ghist, 
 // ---- one pass over one portion ------------------------------------------------------------------
 constexpr unsigned FLAG_AGG = 1u, FLAG_INC = 2u;
 
-template <int ITEMS, int MINBLOCKS>
+template <int ITEMS, int MINBLOCKS, bool EXT, bool BOUNDS>
 __global__ void __launch_bounds__(RADIX_THREADS, MINBLOCKS) radix_scatter_kernel(
     const Rec *__restrict__ in, Rec *__restrict__ out, unsigned long long portionStart, unsigned long long portionEnd,
     DigitPass dp, const unsigned long long *__restrict__ gbase, unsigned long long *__restrict__ gbaseNext,
-    unsigned *status, unsigned *ticket, unsigned numTiles) {
+    unsigned *status, unsigned *ticket, unsigned numTiles, RadixBounds bo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Rec *tileRecs = reinterpret_cast<Rec *>(smem_raw);
     __shared__ unsigned short warpCnt[RADIX_THREADS / 32][256];
@@ -109,7 +117,7 @@ __global__ void __launch_bounds__(RADIX_THREADS, MINBLOCKS) radix_scatter_kernel
     for (int r = 0; r < ITEMS; r++) {
         const unsigned idx = w * (ITEMS * 32) + r * 32 + lane;
         const bool valid = idx < count;
-        const unsigned d = valid ? digit_of(rec[r], dp) : 256u;
+        const unsigned d = valid ? digit_of_t<EXT>(rec[r], dp) : 256u;
         const unsigned m = __match_any_sync(0xFFFFFFFFu, d);
         unsigned c = 0;
         if (valid) c = warpCnt[w][d];
@@ -157,7 +165,7 @@ __global__ void __launch_bounds__(RADIX_THREADS, MINBLOCKS) radix_scatter_kernel
         if (idx < count) {
             // (keeping the digit from the ranking step in registers / next to the record was measured: no gain, the pass is
             // bound by the latency of its dependent phases, not by recomputing the hash)
-            const unsigned d = digit_of(rec[r], dp);
+            const unsigned d = digit_of_t<EXT>(rec[r], dp);
             const unsigned pos = digitStart[d] + warpCnt[w][d] + rank[r];
             tileRecs[pos] = rec[r];
         }
@@ -194,12 +202,49 @@ __global__ void __launch_bounds__(RADIX_THREADS, MINBLOCKS) radix_scatter_kernel
         if (tile == numTiles - 1) gbaseNext[tid] = base + prev + cnt;
     }
     __syncthreads();
-    for (unsigned j = tid; j < count; j += RADIX_THREADS) {
-        const Rec r = tileRecs[j];
-        const unsigned d = digit_of(r, dp);
-        uint4 raw;
-        raw.x = (unsigned) r.w0; raw.y = (unsigned) (r.w0 >> 32); raw.z = (unsigned) r.w1; raw.w = (unsigned) (r.w1 >> 32);
-        reinterpret_cast<uint4 *>(out)[goff[d] + (long long) j] = raw;
+    if (!BOUNDS) {
+        for (unsigned j = tid; j < count; j += RADIX_THREADS) {
+            const Rec r = tileRecs[j];
+            const unsigned d = digit_of_t<EXT>(r, dp);
+            uint4 raw;
+            raw.x = (unsigned) r.w0; raw.y = (unsigned) (r.w0 >> 32); raw.z = (unsigned) r.w1; raw.w = (unsigned) (r.w1 >> 32);
+            reinterpret_cast<uint4 *>(out)[goff[d] + (long long) j] = raw;
+        }
+    } else {
+        // last pass of a hashed-bucket partition: the store loop hashes every record anyway (its digit is a slice of
+        // mix64), so the bucket id -- all sorted bits of the same hash -- is free, and so are the bucket boundaries:
+        // neighbours in the reordered tile are neighbours in the output as long as they share the digit, and the bucket id
+        // contains the digit.
+        const int lane = tid & 31;
+        unsigned long long localMin = ~0ULL;
+        for (unsigned j0 = 0; j0 < count; j0 += RADIX_THREADS) {
+            const unsigned j = j0 + tid;
+            const bool valid = j < count;
+            unsigned long long hb = ~0ULL;
+            Rec r; r.w0 = 0; r.w1 = 0;
+            if (valid) {
+                r = tileRecs[j];
+                const unsigned long long k = r.w0 & bo.hashMask;
+                localMin = min(localMin, k);
+                hb = mix64(k) & (unsigned long long) bo.bucketMask;
+            }
+            unsigned long long bp = __shfl_up_sync(0xFFFFFFFFu, hb, 1), bn = __shfl_down_sync(0xFFFFFFFFu, hb, 1);
+            if (valid) {
+                if (lane == 0) bp = j > 0 ? (mix64(tileRecs[j - 1].w0 & bo.hashMask) & (unsigned long long) bo.bucketMask) : ~0ULL;
+                if (lane == 31) bn = j + 1 < count ? (mix64(tileRecs[j + 1].w0 & bo.hashMask) & (unsigned long long) bo.bucketMask) : ~0ULL;
+                if (j + 1 >= count) bn = ~0ULL;
+                const unsigned d = (unsigned) (hb >> dp.shift) & dp.mask;
+                const unsigned long long g = (unsigned long long) (goff[d] + (long long) j);
+                uint4 raw;
+                raw.x = (unsigned) r.w0; raw.y = (unsigned) (r.w0 >> 32); raw.z = (unsigned) r.w1; raw.w = (unsigned) (r.w1 >> 32);
+                reinterpret_cast<uint4 *>(out)[g] = raw;
+                if (bp != hb) atomicMin(&bo.start[(unsigned) hb], g);
+                if (bn != hb) atomicMax(&bo.end[(unsigned) hb], g + 1ULL);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) localMin = min(localMin, __shfl_xor_sync(0xFFFFFFFFu, localMin, o));
+        if (lane == 0 && localMin != ~0ULL) atomicMin(bo.minKey, localMin);
     }
 }
 
@@ -621,15 +666,15 @@ void radix_set_items(int items) { g_items = (items == 8 || items == 16) ? items 
 static int g_mode = -1;
 int radix_get_mode() {
     if (g_mode < 0) {
-        g_mode = 1;
+        g_mode = 0;      // measured: the register-tile kernel is still the fastest on the real record streams (profiles/r2_summary_a.md)
         if (const char *e = getenv("PLASS_B200_RADIX_MODE")) { const int m = atoi(e); if (m >= 0 && m <= 3) g_mode = m; }
     }
     return g_mode;
 }
-void radix_set_mode(int mode) { g_mode = (mode >= 0 && mode <= 3) ? mode : 1; }
+void radix_set_mode(int mode) { g_mode = (mode >= 0 && mode <= 3) ? mode : 0; }
 
 bool radix_emits_bounds(const RadixPlan &plan) {
-    if (radix_get_mode() == 0 || plan.npasses == 0) return false;
+    if (plan.npasses == 0 || (radix_get_mode() == 0 && g_items != 12)) return false;
     for (int p = 0; p < plan.npasses; p++) if (plan.pass[p].mask > 255u || plan.pass[p].hashed != 1) return false;
     return true;
 }
@@ -734,9 +779,11 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
     const int dynSmem = (int) (tile_records() * sizeof(Rec));
     const int dynSmemWide = (int) (tile_records() * (sizeof(Rec) + 2));    // wide digits: two bytes
     if (!attrSet) {
-        PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int) sizeof(Rec)));
-        PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) sizeof(Rec)));
-        PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * (int) sizeof(Rec)));
+        PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<16, 2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int) sizeof(Rec)));
+        PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<12, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) sizeof(Rec)));
+        PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<12, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) sizeof(Rec)));
+        PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<12, 3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) sizeof(Rec)));
+        PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<8, 4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * (int) sizeof(Rec)));
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_wide_kernel<16, 2, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int) (sizeof(Rec) + 2)));
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_wide_kernel<12, 3, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) (sizeof(Rec) + 2)));
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_wide_kernel<16, 2, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int) (sizeof(Rec) + 2)));
@@ -754,7 +801,10 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
     int histBlocks = (int) ((n + 512ull * 16 - 1) / (512ull * 16));
     if (histBlocks > NUM_SMS * 4) histBlocks = NUM_SMS * 4;
     if (histBlocks < 1) histBlocks = 1;
-    radix_hist_kernel<<<histBlocks, 512, (size_t) plan.npasses * stride * sizeof(unsigned), stream>>>(a, n, plan, ghist, stride);
+    bool ext = false;
+    for (int p = 0; p < plan.npasses; p++) ext = ext || plan.pass[p].hashed >= 2;
+    if (ext) radix_hist_kernel<true><<<histBlocks, 512, (size_t) plan.npasses * stride * sizeof(unsigned), stream>>>(a, n, plan, ghist, stride);
+    else radix_hist_kernel<false><<<histBlocks, 512, (size_t) plan.npasses * stride * sizeof(unsigned), stream>>>(a, n, plan, ghist, stride);
     radix_scan_kernel<<<plan.npasses, 256, 0, stream>>>(ghist, bases, (int) (portions + 1), stride);
     if (launches) *launches += 2;
 
@@ -783,9 +833,14 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
             } else if (bins == 1024) {
                 if (g_items == 16) radix_scatter_wide_kernel<16, 2, 10><<<tiles, RADIX_THREADS, dynSmemWide, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles);
                 else { PG_CHECK(g_items == 12, "radix_sort: wide digits need 12 or 16 records per thread"); radix_scatter_wide_kernel<12, 3, 10><<<tiles, RADIX_THREADS, dynSmemWide, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles); }
-            } else if (g_items == 16) radix_scatter_kernel<16, 2><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles);
-            else if (g_items == 12) radix_scatter_kernel<12, 3><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles);
-            else radix_scatter_kernel<8, 4><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles);
+            } else if (plan.pass[p].hashed >= 2) {
+                PG_CHECK(g_items == 12, "radix_sort: interval / rebased digits need 12 records per thread");
+                radix_scatter_kernel<12, 3, true, false><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles, RadixBounds());
+            } else if (bounds && p == plan.npasses - 1 && radix_emits_bounds(plan) && g_items == 12) {
+                radix_scatter_kernel<12, 3, false, true><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles, *bounds);
+            } else if (g_items == 16) radix_scatter_kernel<16, 2, false, false><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles, RadixBounds());
+            else if (g_items == 12) radix_scatter_kernel<12, 3, false, false><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles, RadixBounds());
+            else radix_scatter_kernel<8, 4, false, false><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles, RadixBounds());
             if (launches) *launches += 1;
         }
         Rec *t = src; src = dst; dst = t;
