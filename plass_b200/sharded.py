@@ -210,11 +210,28 @@ class ShardedIteration:
             o = one.download()
             one.free()
             want = np.array([len(h1), len(a1), record_checksum(h1), record_checksum(a1)], dtype=np.uint64)
-            same_db = (np.array_equal(g.keys, o.keys) and np.array_equal(g.lens, o.lens) and np.array_equal(g.offsets, o.offsets)
-                       and np.array_equal(g.data, o.data))
+            eq = {f: bool(np.array_equal(getattr(g, f), getattr(o, f))) for f in ("keys", "lens", "offsets", "data")}
+            same_db = all(eq.values())
+            detail = None
+            if not same_db:
+                detail = {"arrays_equal": eq, "n": [int(g.n), int(o.n)], "data_bytes": [int(g.data.nbytes), int(o.data.nbytes)]}
+                if g.n == o.n:
+                    bad_len = np.flatnonzero(np.asarray(g.lens) != np.asarray(o.lens))
+                    detail["entries_with_other_length"] = int(len(bad_len))
+                    if eq["lens"] and eq["offsets"] and g.data.nbytes == o.data.nbytes:
+                        diff = np.flatnonzero(np.asarray(g.data) != np.asarray(o.data))
+                        detail["differing_bytes"] = int(len(diff))
+                        if len(diff):
+                            ent = np.unique(np.searchsorted(np.asarray(o.offsets), diff, side="right") - 1)
+                            detail["differing_entries"] = int(len(ent))
+                            detail["first_entries"] = [{"index": int(i), "key": int(o.keys[i]), "sharded": g.entry(int(i)).decode("latin1")[:120],
+                                                        "single": o.entry(int(i)).decode("latin1")[:120]} for i in ent[:4]]
+                    elif len(bad_len):
+                        detail["first_entries"] = [{"index": int(i), "key": int(o.keys[i]), "sharded": g.entry(int(i)).decode("latin1")[:120],
+                                                    "single": o.entry(int(i)).decode("latin1")[:120]} for i in bad_len[:4]]
             res = {"ranks": self.world, "hits": int(tot[0]), "hits_single_gpu": int(want[0]), "alignments": int(tot[1]), "alignments_single_gpu": int(want[1]),
                    "hit_checksum_equal": bool(tot[2] == want[2]), "alignment_checksum_equal": bool(tot[3] == want[3]),
-                   "gathered_db_equals_single_gpu_db": bool(same_db), "sequences": int(o.n)}
+                   "gathered_db_equals_single_gpu_db": bool(same_db), "sequences": int(o.n), "detail": detail}
             res["equal"] = bool(tot[0] == want[0] and tot[1] == want[1] and res["hit_checksum_equal"] and res["alignment_checksum_equal"] and same_db)
         else:
             full.free()
