@@ -563,6 +563,40 @@ def main():
                         "the device-to-host copies of step i run under the kernels of step i+1; first upload and final drain are inside the timed region" % k)
         finally:
             ctx.set_async_results(False)
+    else:
+        # the same pipeline on every rank: this rank's slice of the next input travels over PCIe while the current step
+        # computes; the slices are all-gathered over NVLink; this rank's share of the results goes back under the next step
+        ctx.set_async_results(True)
+        try:
+            def run_pipelined_sharded(k):
+                pending, nbytes = None, 0
+                nxt = ctx.upload_async(pinned)
+                for i in range(k):
+                    sl_in = nxt
+                    nxt = ctx.upload_async(pinned) if i + 1 < k else None
+                    d_in = ctx.shard_allgather_db(sl_in)
+                    sl_in.free()
+                    out, _, hits, alns = ctx.shard_iteration(d_in, kp, rp, ep, want_intermediates=True)
+                    host_out = out.download()
+                    ticket = ctx.results_ticket()
+                    out.free(); d_in.free()
+                    if pending is not None:
+                        ctx.results_wait(pending[0])
+                        nbytes = sum(int(a.nbytes) for a in pending[1:])
+                    pending = (ticket, hits, alns, host_out.data, host_out.offsets, host_out.lens, host_out.keys)
+                ctx.results_wait(pending[0])
+                return sum(int(a.nbytes) for a in pending[1:])
+            run_pipelined_sharded(2)
+            k = args.e2e_steps or max(args.steps, 8)
+            barrier()
+            t0 = time.perf_counter()
+            d2h = run_pipelined_sharded(k)
+            barrier()
+            e2e_dt = (time.perf_counter() - t0) / k
+            e2e_mode = ("pipelined over %d steps on every rank: the rank's slice of the next input is copied from pinned host memory while the current step computes, "
+                        "the slices are all-gathered over NVLink, the rank's share of hits / alignments / new DB returns under the next step" % k)
+        finally:
+            ctx.set_async_results(False)
     if world > 1:
         t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -238,8 +238,9 @@ void end_shard_phase(Context *ctx, bool first) {
     if (t.n_extended) a.n_extended = t.n_extended;
     ctx->timings = a;
 }
-int hits_to_host_overlapped(Context *ctx, const pg_hit *d, uint64_t n, pg_hit **out) { return to_host_overlapped(ctx, d, n, out); }
-int alns_to_host_overlapped(Context *ctx, const pg_aln *d, uint64_t n, pg_aln **out) { return to_host_overlapped(ctx, d, n, out); }
+// (the events guard the device buffers against the next call's writes while an asynchronous copy still reads them)
+int hits_to_host_overlapped(Context *ctx, const pg_hit *d, uint64_t n, pg_hit **out) { return to_host_overlapped(ctx, d, n, out, ctx->evHitsCopied); }
+int alns_to_host_overlapped(Context *ctx, const pg_aln *d, uint64_t n, pg_aln **out) { return to_host_overlapped(ctx, d, n, out, ctx->evAlnsCopied); }
 }  // namespace pg
 
 using namespace pg;
@@ -293,6 +294,7 @@ int pg_init(int device, pg_context **out) {
     }
     for (int i = 0; i < EV_COUNT; i++) PG_CUDA(cudaEventCreate(&ctx->ev[i]));
     memset(&ctx->timings, 0, sizeof(ctx->timings));
+    if (const char *e = getenv("PLASS_B200_NO_SCRATCH_ALIAS")) ctx->noScratchAlias = atoi(e) != 0;
     if (const char *e = getenv("PLASS_B200_BUCKET_TARGET")) { const int b = atoi(e); if (b >= 64 && b <= 1200) ctx->bucketTarget = (unsigned) b; }
     if (const char *e = getenv("PLASS_B200_DIGIT_BITS")) { const int b = atoi(e); if (b >= 8 && b <= 10) ctx->digitBits = b; }
     *out = ctx;
@@ -735,6 +737,8 @@ int pg_set_split_memory_limit(pg_context *ctx, uint64_t bytes) {
     ctx->memLimit = bytes;
     return 0;
 }
+
+int pg_debug_no_scratch_alias(pg_context *ctx, int on) { if (!ctx) return 1; ctx->noScratchAlias = on != 0; return 0; }
 
 // tests: run the kmermatcher stage in exactly n hash-range splits (0 = decide from the memory limit)
 int pg_debug_force_splits(pg_context *ctx, unsigned n) { if (!ctx) return 1; ctx->forceSplits = n; return 0; }

@@ -963,8 +963,8 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     const size_t workBytes = sizeof(ExRes) * 2 * (nAlns + 1);
     const size_t segBytes = (sizeof(ExSeg) * (nAlns + n + 1) + 255) & ~(size_t) 255;
     const size_t listBytes = sizeof(unsigned) * 2 * (n + 1) + sizeof(uint2) * (nAlns + 1) + sizeof(ExState) * (n + 1) + 256;
-    const bool workInRecB = ctx->recB.cap >= workBytes;
-    const bool segsInRecA = ctx->recA.cap >= segBytes + listBytes;
+    const bool workInRecB = !ctx->noScratchAlias && ctx->recB.cap >= workBytes;
+    const bool segsInRecA = !ctx->noScratchAlias && ctx->recA.cap >= segBytes + listBytes;
     if (!workInRecB) PG_TRY(ctx->exWork.reserve(workBytes));
     if (!segsInRecA) { PG_TRY(ctx->exSegs.reserve(segBytes)); PG_TRY(ctx->exLists.reserve(listBytes)); }
     ExRes *heapBuf = workInRecB ? ctx->recB.as<ExRes>() : ctx->exWork.as<ExRes>();

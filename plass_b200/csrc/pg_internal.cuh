@@ -35,6 +35,7 @@ struct pg_context {
     bool forceFullSort = false;   // tests: take the 8-pass sort + group_kernel path instead of the bucketed hash join
     // --split-memory-limit (pg_set_split_memory_limit): bound on the two k-mer record buffers; splitDiv = number of equal
     // hash-range splits the running kmermatcher call uses (1 = no split), pairAcc collects the splits' pair records
+    bool noScratchAlias = false;  // diagnostics: keep the later stages' scratch out of the record buffers
     uint64_t memLimit = 0;
     uint64_t deviceMemBytes = 0;  // total device memory (pg_init)
     uint64_t kmerTotalHint = 0;   // computeKmerCount + 1 of the whole DB, handed from km_choose_splits to km_extract

@@ -394,7 +394,7 @@ int rs_run(Context *ctx, const pg_seqdb *db, const pg_hit *d_hits, uint64_t nHit
     const uint64_t n = db->n, nItems = nHits + c.nSelf;
     // the staging array of all scored lines lives in the kmermatcher's first record buffer when that is large enough (its
     // records are dead once the hits exist; same stream, so the reuse is ordered): 12 GB less at 50 M reads
-    const bool stageInRecA = ctx->recA.cap >= sizeof(pg_aln) * (nItems + 1);
+    const bool stageInRecA = !ctx->noScratchAlias && ctx->recA.cap >= sizeof(pg_aln) * (nItems + 1);
     if (!stageInRecA) PG_TRY(ctx->alnAll.reserve(sizeof(pg_aln) * (nItems + 1)));
     PG_TRY(ctx->flags.reserve(nItems + 16 + sizeof(unsigned) * (n + 1) + sizeof(unsigned long long) * (n + 2) + scan_workspace_bytes(n) + 64));
     pg_aln *res = stageInRecA ? ctx->recA.as<pg_aln>() : ctx->alnAll.as<pg_aln>();

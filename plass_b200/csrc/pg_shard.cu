@@ -375,7 +375,7 @@ int pg_shard_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_params *
             else cudaGetLastError();
         }
     }
-    PG_CUDA(cudaStreamSynchronize(ctx->copyStream));
+    if (!ctx->asyncResults) PG_CUDA(cudaStreamSynchronize(ctx->copyStream));   // pg_set_async_results: the caller waits on a ticket
     if (own_lo) *own_lo = lo;
     if (own_hi) *own_hi = hi;
     return 0;
