@@ -962,7 +962,7 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     // the auxiliary stream forked from it.  30 GB less at 50 M reads.
     const size_t workBytes = sizeof(ExRes) * 2 * (nAlns + 1);
     const size_t segBytes = (sizeof(ExSeg) * (nAlns + n + 1) + 255) & ~(size_t) 255;
-    const size_t listBytes = sizeof(unsigned) * 2 * (n + 1) + sizeof(uint2) * (nAlns + 1) + sizeof(ExState) * (n + 1) + 256;
+    const size_t listBytes = sizeof(unsigned) * 3 * (n + 1) + sizeof(uint2) * (nAlns + 1) + sizeof(ExState) * (n + 1) + 256;
     const bool workInRecB = !ctx->noScratchAlias && ctx->recB.cap >= workBytes;
     const bool segsInRecA = !ctx->noScratchAlias && ctx->recA.cap >= segBytes + listBytes;
     if (!workInRecB) PG_TRY(ctx->exWork.reserve(workBytes));
@@ -976,6 +976,7 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     uint2 *work = (uint2 *) (lb + ((sizeof(ExState) * (n + 1) + 15) & ~(size_t) 15));
     unsigned *listA = (unsigned *) ((unsigned char *) work + ((sizeof(uint2) * (nAlns + 1) + 15) & ~(size_t) 15));
     unsigned *listB = listA + (n + 1);
+    unsigned *listC = listB + (n + 1);
     unsigned long long *d_cnt = ctx->small.as<unsigned long long>() + 24;   // [24] work count, [25] list counts (2 x u32)
     unsigned *d_listCnt = (unsigned *) (d_cnt + 1);                          // [0],[1] list counters, [2] number of large queries
     PG_CUDA(cudaMemsetAsync(d_cnt, 0, 24, s));
@@ -992,8 +993,14 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     const bool needHeap = nt || hCnt[2] > 0;
     lap("init_out+aln_ranges");
     unsigned active = hCnt[0];
+    // listA (count d_listCnt[0]) is the list of all active queries.  The one-kernel warp path reads it for its whole run, while
+    // the rounds of the large queries proceed next to it on the auxiliary stream: the rounds therefore never write listA or
+    // its count again -- they read it in round 0 and ping-pong between listB (count [1]) and listC (count [3]) afterwards.
+    // (Round 1 used to recycle listA and zero its count: CTAs of the warp kernel that started after that point found an empty
+    // list and silently skipped their queries -- only visible once the warp kernel runs in several waves AND a large query
+    // needs a second round, i.e. from a few million reads on.)
     unsigned *cur = listA, *nxt = listB;
-    int curIdx = 0;
+    int curIdx = 0, nxtIdx = 1;
     // amino acids: the queries with <= 32 alignments (all of them, usually) run to completion inside one kernel; only
     // the larger ones go through the rounds below
     const bool fusedWarp = !nt && getenv("PG_EX_WAVEFRONT") == nullptr;
@@ -1015,27 +1022,27 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     for (int round = 0; active > 0; round++) {
         PG_CHECK(round < 100000, "assembleresults: extension did not converge");
         PG_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), rs));
-        PG_CUDA(cudaMemsetAsync(d_listCnt + (1 - curIdx), 0, sizeof(unsigned), rs));
+        PG_CUDA(cudaMemsetAsync(d_listCnt + nxtIdx, 0, sizeof(unsigned), rs));
         if (!nt && !fusedWarp) {
             // amino acids, wavefront variant (PG_EX_WAVEFRONT=1): warp per query for the queries with <= 32 alignments,
             // heap replay for the rest (both kernels read the same list and skip the queries of the other class)
             extend_round_warp_kernel<<<std::min<unsigned>((active + 7) / 8, NUM_SMS * 32), 256, 0, rs>>>(
-                *db, d_alns, alnStart, alnCount, c, round == 0, cur, d_listCnt + curIdx, nxt, d_listCnt + (1 - curIdx), work, d_cnt, states,
+                *db, d_alns, alnStart, alnCount, c, round == 0, cur, d_listCnt + curIdx, nxt, d_listCnt + nxtIdx, work, d_cnt, states,
                 parkBuf, segBuf, segCount, outLen, ext, used);
             ctx->launches++;
         }
         if (needHeap) {
             extend_round_kernel<<<(active + 127) / 128, 128, 0, rs>>>(*db, d_alns, alnStart, alnCount, c, round == 0, cur, d_listCnt + curIdx,
-                                                                     nxt, d_listCnt + (1 - curIdx), work, d_cnt, states, heapBuf, parkBuf,
+                                                                     nxt, d_listCnt + nxtIdx, work, d_cnt, states, heapBuf, parkBuf,
                                                                      segBuf, segCount, outLen, ext, used);
             ctx->launches++;
         }
         extend_rescore_kernel<<<NUM_SMS * 8, 256, 0, rs>>>(*db, alnStart, c, work, d_cnt, states, parkBuf, segBuf);
         ctx->launches += 1;
-        PG_TRY(read_back_on(ctx, rs, hCnt, d_listCnt + (1 - curIdx), sizeof(unsigned)));
+        PG_TRY(read_back_on(ctx, rs, hCnt, d_listCnt + nxtIdx, sizeof(unsigned)));
         active = hCnt[0];
-        unsigned *t = cur; cur = nxt; nxt = t;
-        curIdx = 1 - curIdx;
+        cur = nxt; curIdx = nxtIdx;
+        if (cur == listB) { nxt = listC; nxtIdx = 3; } else { nxt = listB; nxtIdx = 1; }
         if (trace && round < 3) lap("  round");
     }
     if (rs != s) {
