@@ -382,12 +382,23 @@ class Context:
 
     # ---- multi-GPU data plane in C++ over NCCL (plass_b200/csrc/pg_shard.cu) ----
     @staticmethod
+    def _torch_nccl_first():
+        """libplassgpu.so loads NCCL at run time by soname.  In a Python process that will also import PyTorch, PyTorch's own
+        (newer) libnccl.so.2 has to be the copy in the process: import torch before the first NCCL call if it is installed."""
+        try:
+            import torch  # noqa: F401
+        except ImportError:
+            pass
+
+    @staticmethod
     def comm_unique_id():
+        Context._torch_nccl_first()
         buf = (C.c_uint8 * COMM_ID_BYTES)()
         _check(load_library().pg_comm_unique_id(buf), "pg_comm_unique_id")
         return bytes(buf)
 
     def comm_init(self, rank, world, comm_id):
+        Context._torch_nccl_first()
         buf = (C.c_uint8 * COMM_ID_BYTES)(*comm_id)
         _check(load_library().pg_comm_init(self.handle, C.c_int(rank), C.c_int(world), buf), "pg_comm_init")
 

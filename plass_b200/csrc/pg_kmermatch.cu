@@ -2216,27 +2216,32 @@ static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, 
     PG_TRY(radix_sort(pairs, tmp, nPairs, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches));
     cudaEventRecord(ctx->ev[EV_SORT2_END], s);
     Rec *other = (sorted == pairs) ? tmp : pairs;
+    // per-representative tables: only the owned key range [keyLo, keyHi) (multi-GPU: 1 / world of the keys), addressed by the
+    // key itself through pointers shifted by keyLo
+    const size_t nT = keyHi > keyLo ? (size_t) (keyHi - keyLo) : 0;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t) 15; return r; };
-    const size_t oStart = take(sizeof(unsigned long long) * nKeys), oEnd = take(sizeof(unsigned long long) * nKeys);
-    const size_t oCnt = take(sizeof(unsigned) * ((size_t) nKeys + 1));
-    const size_t oOff = take(sizeof(unsigned long long) * ((size_t) nKeys + 2)), oBig = take(sizeof(unsigned) * ((size_t) nKeys + 1));
-    const size_t oMid = take(sizeof(unsigned) * ((size_t) nKeys + 1));
-    const size_t oHuge = take(sizeof(unsigned) * ((size_t) nKeys + 1));
-    const size_t oScan = take(scan_workspace_bytes(nKeys));
-    const size_t oMinT = take(sizeof(unsigned) * ((size_t) nKeys + 1));
+    const size_t oStart = take(sizeof(unsigned long long) * (nT + 1)), oEnd = take(sizeof(unsigned long long) * (nT + 1));
+    const size_t oCnt = take(sizeof(unsigned) * (nT + 1));
+    const size_t oOff = take(sizeof(unsigned long long) * (nT + 2)), oBig = take(sizeof(unsigned) * (nT + 1));
+    const size_t oMid = take(sizeof(unsigned) * (nT + 1));
+    const size_t oHuge = take(sizeof(unsigned) * (nT + 1));
+    const size_t oScan = take(scan_workspace_bytes(nT));
+    const size_t oMinT = take(sizeof(unsigned) * (nT + 1));
     PG_TRY(ctx->buckets2.reserve(o));
     unsigned char *bb = ctx->buckets2.as<unsigned char>();
-    unsigned long long *d_start = (unsigned long long *) (bb + oStart), *d_end = (unsigned long long *) (bb + oEnd);
-    unsigned *d_hcnt = (unsigned *) (bb + oCnt), *d_big = (unsigned *) (bb + oBig), *d_minT = (unsigned *) (bb + oMinT), *d_mid = (unsigned *) (bb + oMid);
-    unsigned long long *d_hoff = (unsigned long long *) (bb + oOff);
+    unsigned long long *d_start0 = (unsigned long long *) (bb + oStart), *d_end0 = (unsigned long long *) (bb + oEnd);
+    unsigned *d_hcnt0 = (unsigned *) (bb + oCnt), *d_big = (unsigned *) (bb + oBig), *d_minT0 = (unsigned *) (bb + oMinT), *d_mid = (unsigned *) (bb + oMid);
+    unsigned long long *d_hoff0 = (unsigned long long *) (bb + oOff);
+    unsigned long long *d_start = d_start0 - keyLo, *d_end = d_end0 - keyLo, *d_hoff = d_hoff0 - keyLo;
+    unsigned *d_hcnt = d_hcnt0 - keyLo, *d_minT = d_minT0 - keyLo;
     unsigned *d_over = (unsigned *) (ctx->small.as<unsigned long long>() + 32);     // [32] overflow flag, big count, mid count; [34] total hits
     unsigned *d_bigCnt = d_over + 1, *d_midCnt = d_over + 2, *d_hugeCnt = d_over + 3;
     unsigned *d_huge = (unsigned *) (bb + oHuge);
     unsigned long long *d_total = ctx->small.as<unsigned long long>() + 34;
-    PG_CUDA(cudaMemsetAsync(d_start, 0, oOff, s));   // start, end, hit counts
+    PG_CUDA(cudaMemsetAsync(d_start0, 0, oOff, s));   // start, end, hit counts
     PG_CUDA(cudaMemsetAsync(d_over, 0, 4 * sizeof(unsigned), s));
-    PG_CUDA(cudaMemsetAsync(d_minT, 0xFF, sizeof(unsigned) * ((size_t) nKeys + 1), s));
+    PG_CUDA(cudaMemsetAsync(d_minT0, 0xFF, sizeof(unsigned) * (nT + 1), s));
     seg_bounds_kernel<<<NUM_SMS * 16, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT);
     pg_hit *tmpHits = reinterpret_cast<pg_hit *>(other);   // a hit is 16 bytes like a record, at most one per pair
     reduce_rep_warp_kernel<0><<<NUM_SMS * 32, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT, keyLo, keyHi, tmpHits, d_hcnt, d_big, d_bigCnt, d_mid, d_midCnt, d_over);
@@ -2247,7 +2252,7 @@ static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, 
     PG_CUDA(cudaFuncSetAttribute(reduce_rep_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_BLOCK_MAX * (int) sizeof(unsigned long long)));
     reduce_rep_block_kernel<<<NUM_SMS, 256, SEG_BLOCK_MAX * sizeof(unsigned long long), s>>>(sorted, nPairs, d_start, d_end, d_minT, d_huge, d_hugeCnt, tmpHits, d_hcnt, d_over);
     ctx->launches += 5;
-    PG_TRY(exclusive_scan_u32(d_hcnt, d_hoff, nKeys, d_total, bb + oScan, scan_workspace_bytes(nKeys), s, &ctx->launches));
+    PG_TRY(exclusive_scan_u32(d_hcnt0, d_hoff0, nT, d_total, bb + oScan, scan_workspace_bytes(nT), s, &ctx->launches));
     unsigned long long h = 0; unsigned over = 0;
     {
         unsigned long long hb[3];                      // small[32]: overflow flag (low word) ... small[34]: total hits

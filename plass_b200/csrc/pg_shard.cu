@@ -49,8 +49,10 @@ NcclApi g_nccl;
 
 int load_nccl() {
     if (g_nccl.handle) return 0;
-    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    // a copy the process already holds (PyTorch's) first; otherwise the system library, kept local
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
     PG_CHECK(h != nullptr, std::string("multi-GPU: cannot load libnccl.so.2 (") + (dlerror() ? dlerror() : "?") + ")");
     auto sym = [&](const char *name) { return dlsym(h, name); };
     g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId)) sym("ncclGetUniqueId");

@@ -1,11 +1,11 @@
-"""Parity at scale (-m gpu): >= 1 M synthetic reads through the GPU drop-in commands against the UNMODIFIED reference
+"""Parity at scale (-m gpu): >= 2 M synthetic reads through the GPU drop-in commands against the UNMODIFIED reference
 binaries (oracle/_ref/bin/plass, penguin) run on the same box on the same DB.  The golden fixtures hold a few thousand
 sequences; these inputs exercise what they cannot: multi-tile look-back chains, ~10^5 buckets, bucket spill lists,
 representatives with hundreds of pairs, 10^7-record sorts.
 
-  aa   1 M reads -> aa_6f_start_long (GPU six-frame pipeline) -> kmermatcher / rescorediagonal / assembleresults, two
+  aa   2 M reads -> aa_6f_start_long (GPU six-frame pipeline) -> kmermatcher / rescorediagonal / assembleresults, two
        chained iterations (hash shift 67 then 68, --include-only-extendable 0 then 1, as Assembler.cpp:99-110)
-  nt   1 M reads, penguin's k = 22 path, two chained iterations with cyclecheck's input (the assembly) compared too
+  nt   2 M reads, penguin's k = 22 path, two chained iterations with cyclecheck's input (the assembly) compared too
 
 Comparison = plass_b200_cli dbdiff (key -> entry bytes).  aa: zero mismatching entries (E-value column: last printed digit).
 nt: prefilter lines may differ in the SIGN of the score only for targets of the single k-mer group whose strand the reference
@@ -25,7 +25,7 @@ pytestmark = pytest.mark.gpu
 
 CLI = os.path.join(ROOT, "plass_b200", "plass_b200_cli")
 REF = os.path.join(ROOT, "oracle", "_ref", "bin")
-N_READS = int(os.environ.get("PLASS_SCALE_READS", "1000000"))
+N_READS = int(os.environ.get("PLASS_SCALE_READS", "2000000"))
 THREADS = str(os.cpu_count() or 1)
 
 
@@ -113,6 +113,25 @@ def test_million_reads_two_iterations_match_the_reference_binary(nucl, tmp_path)
             assert d_pref["tolerated"] == 0
         # E-values: the fp64 exp / erfc of CUDA vs glibc may flip the last printed digit of a few values
         assert d_aln["tolerated_lines"] <= max(10, d_aln["entries_b"] // 10000), d_aln
+    if not nucl:
+        # Repeated iterations in ONE context must keep giving the reference's assembly.  (The one-kernel extension runs next
+        # to the rounds of the large queries on a second stream; a list recycled too early made later runs of a process lose
+        # extensions from a few million reads on, while a fresh process -- every CLI call above -- was right.)
+        from plass_b200 import mmseqsdb
+        import bench
+        ctx = api.Context(0)
+        try:
+            ddb = ctx.upload(mmseqsdb.read_db(w("in_0")))
+            kp = api.default_km_params(False); rp = api.default_rs_params(False); ep = api.default_ex_params(False)
+            for rep_i in range(3):
+                out, hits, alns = ctx.assemble_iteration(ddb, kp, rp, ep, want_intermediates=True)
+                bench.write_db_fast(w("api_asm_%d" % rep_i), out.download())
+                out.free()
+                d = dbdiff(w("api_asm_%d" % rep_i), w("in_1"), "exact")
+                assert d["mismatching"] == 0 and d["only_in_a"] == 0 and d["only_in_b"] == 0, (rep_i, d)
+            ddb.free()
+        finally:
+            ctx.close()
     # the fused command on iteration 0's input reproduces all three DBs as well
     union = km_flags(nucl, 0) + ["--rescore-mode", "3", "--wrapped-scoring", "0", "--filter-hits", "0", "-e", "1e-05", "-a", "0", "--min-aln-len", "0",
                                   "--seq-id-mode", "0", "--add-self-matches", "0", "--sort-results", "0", "--db-load-mode", "0", "--keep-target", "1"]
