@@ -66,6 +66,11 @@ struct pg_context {
     pg::DevBuf commWs;                         // counts matrix, histogram, bounds
     unsigned long long firstKmerOverride = 0;  // nt: the job-wide smallest k-mer (all-reduced), see hash_group_kernel
     bool useFirstKmerOverride = false;
+    // fused partition + exchange over peer memory (CUDA IPC): this rank's two receive buffers (k-mer records, pair records) and
+    // every rank's mapping of them
+    pg::DevBuf xr[2];
+    void *peer[2][16] = {};
+    bool p2pDisabled = false;
     float lastExchangeMs[2] = {0, 0};
     uint64_t lastExchangeBytes[2] = {0, 0};
     uint32_t lastBounds[257];
@@ -80,6 +85,8 @@ int km_run(Context *ctx, const pg_seqdb *db, const pg_km_params *p, pg_hit **d_h
 int km_shard_pairs(Context *ctx, const pg_seqdb *db, const pg_km_params *p, int world, uint64_t *counts);
 int km_shard_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, int rank, int world, uint64_t *counts);
 int km_shard_group(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const void *d_records, uint64_t nRecords, uint64_t *hist);
+int km_shard_extract_only(Context *ctx, const pg_seqdb *db, const pg_km_params *p, int rank, int world, uint64_t *nRecords);
+void km_shard_pairs_location(Context *ctx, Rec **pairs, uint64_t *n);
 int km_shard_route(Context *ctx, int world, const unsigned *bounds, uint64_t *counts);
 void km_equal_key_bounds(unsigned max_key, int world, unsigned *bounds);
 int km_shard_reduce(Context *ctx, const pg_seqdb *db, const void *d_pairs, uint64_t nPairs, pg_hit **d_hits, uint64_t *nHits);

@@ -2598,6 +2598,32 @@ int km_shard_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, in
     return 0;
 }
 
+// phase 0 without the partition pass: the records of this rank's slice of the sequences, unordered, in recA (the fused
+// partition + exchange of pg_shard.cu takes them from there)
+int km_shard_extract_only(Context *ctx, const pg_seqdb *db, const pg_km_params *p, int rank, int world, uint64_t *nRecords) {
+    PG_CHECK(world >= 1 && world <= 256 && rank >= 0 && rank < world, "pg_shard_extract: bad rank / world size");
+    PG_CHECK(!km_is_wide(db), "multi-GPU kmermatcher: sequences >= 32765 residues (wide T=int records) are single-GPU only for now");
+    KmConst c;
+    cudaStream_t s = ctx->stream;
+    PG_TRY(km_setup_constants(db, p, c, s));
+    cudaEventRecord(ctx->ev[EV_KM_BEGIN], s);
+    uint64_t nRec = 0;
+    ctx->seqLo = (unsigned) ((unsigned long long) db->n * (unsigned) rank / (unsigned) world);
+    ctx->seqHi = (unsigned) ((unsigned long long) db->n * (unsigned) (rank + 1) / (unsigned) world);
+    const int rc = km_extract(ctx, db, p, c, &nRec);
+    ctx->seqLo = 0; ctx->seqHi = 0xFFFFFFFFu;
+    if (rc) return rc;
+    cudaEventRecord(ctx->ev[EV_EXTRACT_END], s);
+    ctx->shardPairs = ctx->recA.as<Rec>(); ctx->shardPairCount = nRec;
+    ctx->timings.n_kmer_records = nRec;
+    ctx->tExtract = true;
+    *nRecords = nRec;
+    return 0;
+}
+
+// after km_shard_group: where the pair records are
+void km_shard_pairs_location(Context *ctx, Rec **pairs, uint64_t *n) { *pairs = ctx->shardPairs; *n = ctx->shardPairCount; }
+
 // phase 1: the k-mer records this rank received (every record of the k-mers it owns) -> sort #1 + group -> pair
 // records (left on the device for pg_shard_route) and their histogram over the representative key space
 int km_shard_group(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const void *d_records, uint64_t nRec, uint64_t *hist) {

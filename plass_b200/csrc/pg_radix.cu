@@ -76,11 +76,16 @@ __global__ void radix_scan_kernel(const unsigned long long *__restrict__ ghist, 
 // ---- one pass over one portion ------------------------------------------------------------------
 constexpr unsigned FLAG_AGG = 1u, FLAG_INC = 2u;
 
-template <int ITEMS, int MINBLOCKS, bool EXT, bool BOUNDS>
+// PEER: the digit runs do not go to one output array but to dstBase[digit] (a byte address per digit, possibly in ANOTHER GPU's
+// memory, mapped through CUDA IPC over NVLink) + the record's rank within the digit.  This is the partition pass and the
+// all-to-all of the multi-GPU exchanges in one kernel: the 16-byte stores of a run leave the SM as NVLink writes to the owner's
+// receive buffer instead of HBM writes followed by a separate send.  gbase0 = the digit bases of portion 0 (rank 0 of a digit).
+template <int ITEMS, int MINBLOCKS, bool EXT, bool BOUNDS, bool PEER = false>
 __global__ void __launch_bounds__(RADIX_THREADS, MINBLOCKS) radix_scatter_kernel(
     const Rec *__restrict__ in, Rec *__restrict__ out, unsigned long long portionStart, unsigned long long portionEnd,
     DigitPass dp, const unsigned long long *__restrict__ gbase, unsigned long long *__restrict__ gbaseNext,
-    unsigned *status, unsigned *ticket, unsigned numTiles, RadixBounds bo) {
+    unsigned *status, unsigned *ticket, unsigned numTiles, RadixBounds bo,
+    const unsigned long long *__restrict__ dstBase = nullptr, const unsigned long long *__restrict__ gbase0 = nullptr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Rec *tileRecs = reinterpret_cast<Rec *>(smem_raw);
     __shared__ unsigned short warpCnt[RADIX_THREADS / 32][256];
@@ -198,11 +203,20 @@ __global__ void __launch_bounds__(RADIX_THREADS, MINBLOCKS) radix_scatter_kernel
             st_volatile_u32(&status[(size_t) tile * 256 + tid], ((unsigned) (prev + cnt) << 2) | FLAG_INC);
         }
         const unsigned long long base = gbase[tid];
-        goff[tid] = (long long) (base + prev) - (long long) digitStart[tid];
+        if (PEER) goff[tid] = (long long) dstBase[tid] + ((long long) (base - gbase0[tid] + prev) - (long long) digitStart[tid]) * (long long) sizeof(Rec);
+        else goff[tid] = (long long) (base + prev) - (long long) digitStart[tid];
         if (tile == numTiles - 1) gbaseNext[tid] = base + prev + cnt;
     }
     __syncthreads();
-    if (!BOUNDS) {
+    if (PEER) {
+        for (unsigned j = tid; j < count; j += RADIX_THREADS) {
+            const Rec r = tileRecs[j];
+            const unsigned d = digit_of_t<EXT>(r, dp);
+            uint4 raw;
+            raw.x = (unsigned) r.w0; raw.y = (unsigned) (r.w0 >> 32); raw.z = (unsigned) r.w1; raw.w = (unsigned) (r.w1 >> 32);
+            *reinterpret_cast<uint4 *>(goff[d] + (long long) j * (long long) sizeof(Rec)) = raw;
+        }
+    } else if (!BOUNDS) {
         for (unsigned j = tid; j < count; j += RADIX_THREADS) {
             const Rec r = tileRecs[j];
             const unsigned d = digit_of_t<EXT>(r, dp);
@@ -765,6 +779,66 @@ size_t radix_workspace_bytes(uint64_t n, int maxDigitBits) {
     const size_t bases = sizeof(unsigned long long) * RADIX_MAX_PASSES * (num_portions(n) + 1) * stride;
     const size_t status = sizeof(unsigned) * (max_tiles(n) * stride + 64);
     return hist + bases + status + 1024;
+}
+
+// ---- one pass whose output goes to per-digit destinations (fused partition + exchange, see the PEER kernel) ---------------
+static void peer_ws_layout(void *workspace, uint64_t n, unsigned long long **ghist, unsigned long long **bases, unsigned **status, size_t *statusWords) {
+    unsigned char *ws = (unsigned char *) workspace;
+    *ghist = (unsigned long long *) ws;
+    *bases = *ghist + (size_t) RADIX_MAX_PASSES * 256;
+    *status = (unsigned *) (*bases + (size_t) RADIX_MAX_PASSES * (num_portions(n) + 1) * 256);
+    *statusWords = max_tiles(n) * (size_t) 256 + 64;
+}
+
+int radix_pass_histogram(const Rec *a, uint64_t n, const DigitPass &pass, void *workspace, size_t workspace_bytes, cudaStream_t stream,
+                         unsigned long long *hostHist, uint64_t *launches) {
+    PG_CHECK(workspace_bytes >= radix_workspace_bytes(n, 8) && pass.mask <= 255u, "radix_pass_histogram: workspace too small / digit wider than 8 bits");
+    unsigned long long *ghist, *bases; unsigned *status; size_t statusWords;
+    peer_ws_layout(workspace, n, &ghist, &bases, &status, &statusWords);
+    PG_CUDA(cudaMemsetAsync(ghist, 0, sizeof(unsigned long long) * 256, stream));
+    RadixPlan plan; plan.npasses = 1; plan.pass[0] = pass;
+    if (n) {
+        int histBlocks = (int) std::min<unsigned long long>((n + 512ull * 16 - 1) / (512ull * 16), (unsigned long long) NUM_SMS * 4);
+        if (pass.hashed >= 2) radix_hist_kernel<true><<<histBlocks, 512, 256 * sizeof(unsigned), stream>>>(a, n, plan, ghist, 256);
+        else radix_hist_kernel<false><<<histBlocks, 512, 256 * sizeof(unsigned), stream>>>(a, n, plan, ghist, 256);
+    }
+    radix_scan_kernel<<<1, 256, 0, stream>>>(ghist, bases, (int) (num_portions(n) + 1), 256);
+    if (launches) *launches += 2;
+    PG_CUDA(cudaMemcpyAsync(hostHist, ghist, sizeof(unsigned long long) * 256, cudaMemcpyDeviceToHost, stream));
+    PG_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+int radix_scatter_peer(const Rec *a, uint64_t n, const DigitPass &pass, void *workspace, size_t workspace_bytes, cudaStream_t stream,
+                       const unsigned long long *d_dstBase, uint64_t *launches) {
+    if (n == 0) return 0;
+    PG_CHECK(workspace_bytes >= radix_workspace_bytes(n, 8) && pass.mask <= 255u, "radix_scatter_peer: workspace too small / digit wider than 8 bits");
+    unsigned long long *ghist, *bases; unsigned *status; size_t statusWords;
+    peer_ws_layout(workspace, n, &ghist, &bases, &status, &statusWords);
+    static bool attr = false;
+    const int dynSmem = 3072 * (int) sizeof(Rec);
+    if (!attr) {
+        PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<12, 3, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dynSmem));
+        PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<12, 3, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dynSmem));
+        attr = true;
+    }
+    const unsigned long long portions = num_portions(n);
+    for (unsigned long long q = 0; q < portions; q++) {
+        const unsigned long long ps = q * PORTION_RECORDS;
+        const unsigned long long pe = (ps + PORTION_RECORDS < n) ? ps + PORTION_RECORDS : n;
+        const unsigned tiles = (unsigned) ((pe - ps + 3072 - 1) / 3072);
+        PG_CUDA(cudaMemsetAsync(status, 0, sizeof(unsigned) * ((size_t) tiles * 256 + 64), stream));
+        unsigned *ticket = status + statusWords - 32;
+        PG_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), stream));
+        unsigned long long *gb = bases + q * 256;
+        if (pass.hashed >= 2)
+            radix_scatter_kernel<12, 3, true, false, true><<<tiles, RADIX_THREADS, dynSmem, stream>>>(a, nullptr, ps, pe, pass, gb, gb + 256, status, ticket, tiles, RadixBounds(), d_dstBase, bases);
+        else
+            radix_scatter_kernel<12, 3, false, false, true><<<tiles, RADIX_THREADS, dynSmem, stream>>>(a, nullptr, ps, pe, pass, gb, gb + 256, status, ticket, tiles, RadixBounds(), d_dstBase, bases);
+        if (launches) *launches += 1;
+    }
+    PG_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspace, size_t workspace_bytes,

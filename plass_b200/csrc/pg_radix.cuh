@@ -73,6 +73,14 @@ bool radix_emits_bounds(const RadixPlan &plan);
 void radix_set_mode(int mode);
 int radix_get_mode();
 
+// Fused partition + exchange (multi-GPU): one pass over `a` whose digit runs are written to dstBase[digit] + rank-within-digit
+// x 16 bytes -- dstBase = device array of 256 byte addresses, local or in a peer GPU's memory (CUDA IPC mapping, NVLink stores).
+// radix_pass_histogram first (device histogram -> host, bases left in the workspace), then radix_scatter_peer.
+int radix_pass_histogram(const Rec *a, uint64_t n, const DigitPass &pass, void *workspace, size_t workspace_bytes, cudaStream_t stream,
+                         unsigned long long *hostHist /* [256] */, uint64_t *launches);
+int radix_scatter_peer(const Rec *a, uint64_t n, const DigitPass &pass, void *workspace, size_t workspace_bytes, cudaStream_t stream,
+                       const unsigned long long *d_dstBase, uint64_t *launches);
+
 // Helper to build a plan over bit ranges: appends 8-bit digits covering bits [lo, hi) of word w.
 void plan_add_bits(RadixPlan &plan, int word, int lo, int hi);
 // same over bits [lo, hi) of mix64(w0 & hashMask)

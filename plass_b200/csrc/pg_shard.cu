@@ -162,6 +162,116 @@ __global__ void rebase_offsets_kernel(unsigned long long *__restrict__ offsets, 
 
 }  // namespace
 
+// ---- fused partition + exchange over peer memory -------------------------------------------------------------------
+// Every rank owns two receive buffers (xr[0]: k-mer records of exchange #1, xr[1]: pair records of exchange #2) that all other
+// ranks map through CUDA IPC.  A sender's partition pass (radix_scatter_peer) writes each digit run straight into the owner's
+// buffer over NVLink; a stream-ordered barrier (a one-word all-reduce) tells the owner that every sender's pass has finished.
+// Growth is decided from the all-gathered count matrix, which every rank holds identically, so all ranks re-allocate and
+// re-exchange handles in the same iteration.
+static int stream_barrier(Context *ctx) {
+    unsigned long long *d = ctx->commWs.as<unsigned long long>() + 7000;
+    PG_NCCL(g_nccl.AllReduce(d, d, 1, ncclUint64, ncclSum, comm_of(ctx), ctx->stream));
+    return 0;
+}
+
+static void close_peer_mappings(Context *ctx, int which) {
+    for (int r = 0; r < ctx->world; r++) {
+        if (r != ctx->rank && ctx->peer[which][r]) cudaIpcCloseMemHandle(ctx->peer[which][r]);
+        ctx->peer[which][r] = nullptr;
+    }
+}
+
+// returns 0 and *ok = true when every rank's buffer `which` holds at least needBytes and is mapped everywhere
+static int ensure_peer_buffers(Context *ctx, int which, size_t needBytes, bool *ok) {
+    *ok = false;
+    cudaStream_t s = ctx->stream;
+    const int W = ctx->world, me = ctx->rank;
+    if (ctx->xr[which].cap >= needBytes && ctx->peer[which][me] == ctx->xr[which].p) { *ok = true; return 0; }
+    // (re)allocate: nobody may still be writing into the old buffer -- the previous exchange ended with a barrier, and the
+    // owner's own consumers run on this stream
+    PG_CUDA(cudaStreamSynchronize(s));
+    PG_TRY(stream_barrier(ctx));
+    PG_CUDA(cudaStreamSynchronize(s));
+    close_peer_mappings(ctx, which);
+    ctx->xr[which].release();
+    PG_TRY(ctx->xr[which].reserve(needBytes + needBytes / 4));
+    cudaIpcMemHandle_t mine;
+    PG_CUDA(cudaIpcGetMemHandle(&mine, ctx->xr[which].p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    unsigned char *d_mine = ctx->commWs.as<unsigned char>() + 8 * 8000;          // 64 B, then W x 64 B (past the histogram area)
+    unsigned char *d_all = d_mine + 64;
+    std::vector<unsigned char> all((size_t) 64 * W);
+    PG_CUDA(cudaMemcpyAsync(d_mine, &mine, 64, cudaMemcpyHostToDevice, s));
+    PG_NCCL(g_nccl.AllGather(d_mine, d_all, 64, ncclUint8, comm_of(ctx), s));
+    PG_CUDA(cudaMemcpyAsync(all.data(), d_all, (size_t) 64 * W, cudaMemcpyDeviceToHost, s));
+    PG_CUDA(cudaStreamSynchronize(s));
+    unsigned long long good = 1;
+    for (int r = 0; r < W; r++) {
+        if (r == me) { ctx->peer[which][r] = ctx->xr[which].p; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all.data() + (size_t) 64 * r, 64);
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = 0; p = nullptr; }
+        ctx->peer[which][r] = p;
+    }
+    // all ranks or none
+    unsigned long long *d_flag = ctx->commWs.as<unsigned long long>() + 7001;
+    PG_CUDA(cudaMemcpyAsync(d_flag, &good, sizeof(good), cudaMemcpyHostToDevice, s));
+    PG_NCCL(g_nccl.AllReduce(d_flag, d_flag, 1, ncclUint64, ncclMin, comm_of(ctx), s));
+    PG_TRY(read_back(ctx, &good, d_flag, sizeof(good)));
+    if (!good) { close_peer_mappings(ctx, which); ctx->xr[which].release(); return 0; }
+    *ok = true;
+    return 0;
+}
+
+// One fused partition + exchange: the n records at `src` are partitioned by `pass` (digit -> owner through ownerOfDigit) and
+// written into the owners' receive buffers `which`.  On return (stream-ordered) this rank's buffer holds *nRecv records.
+// *done = false if peer memory is not available (the caller falls back to NCCL send / recv).
+static int exchange_fused(Context *ctx, const Rec *src, uint64_t n, const DigitPass &pass, int nDigits, const int *ownerOfDigit, int which,
+                          uint64_t *nRecv, bool *done) {
+    *done = false;
+    cudaStream_t s = ctx->stream;
+    const int W = ctx->world, me = ctx->rank;
+    PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(n)));
+    PG_TRY(ctx->commWs.reserve(sizeof(unsigned long long) * 16384));
+    unsigned long long h[256];
+    PG_TRY(radix_pass_histogram(src, n, pass, ctx->radixWs.p, ctx->radixWs.cap, s, h, &ctx->launches));
+    std::vector<unsigned long long> mine((size_t) W, 0), all((size_t) W * W), gbase(257, 0);
+    for (int b = 0; b < nDigits; b++) { mine[(size_t) ownerOfDigit[b]] += h[b]; gbase[(size_t) b + 1] = gbase[b] + h[b]; }
+    unsigned long long *d_mine = ctx->commWs.as<unsigned long long>();
+    unsigned long long *d_all = d_mine + W;
+    PG_CUDA(cudaMemcpyAsync(d_mine, mine.data(), sizeof(unsigned long long) * W, cudaMemcpyHostToDevice, s));
+    PG_NCCL(g_nccl.AllGather(d_mine, d_all, (size_t) W, ncclUint64, comm_of(ctx), s));
+    PG_TRY(read_back_big(ctx, all.data(), d_all, sizeof(unsigned long long) * (size_t) W * W));
+    unsigned long long maxRecv = 0;
+    std::vector<unsigned long long> recvTotal((size_t) W, 0);
+    for (int d = 0; d < W; d++) { for (int r = 0; r < W; r++) recvTotal[d] += all[(size_t) r * W + d]; maxRecv = std::max(maxRecv, recvTotal[d]); }
+    bool ok = false;
+    PG_TRY(ensure_peer_buffers(ctx, which, sizeof(Rec) * (maxRecv + 1), &ok));
+    if (!ok) return 0;
+    // destination of every digit: owner's buffer + what the lower ranks send there + this rank's digits below it for that owner
+    unsigned long long dst[256];
+    std::vector<unsigned long long> firstBase((size_t) W, ~0ull);
+    for (int b = 0; b < nDigits; b++) if (firstBase[(size_t) ownerOfDigit[b]] == ~0ull) firstBase[(size_t) ownerOfDigit[b]] = gbase[b];
+    for (int b = 0; b < 256; b++) {
+        if (b >= nDigits) { dst[b] = 0; continue; }
+        const int d = ownerOfDigit[b];
+        unsigned long long before = 0;
+        for (int r = 0; r < me; r++) before += all[(size_t) r * W + d];
+        dst[b] = (unsigned long long) ctx->peer[which][d] + (before + gbase[b] - firstBase[(size_t) d]) * sizeof(Rec);
+    }
+    unsigned long long *d_dst = ctx->commWs.as<unsigned long long>() + 6000;
+    PG_CUDA(cudaMemcpyAsync(d_dst, dst, sizeof(dst), cudaMemcpyHostToDevice, s));
+    cudaEventRecord(ctx->evXchg[2 * which], s);
+    PG_TRY(radix_scatter_peer(src, n, pass, ctx->radixWs.p, ctx->radixWs.cap, s, d_dst, &ctx->launches));
+    PG_TRY(stream_barrier(ctx));
+    cudaEventRecord(ctx->evXchg[2 * which + 1], s);
+    ctx->lastExchangeBytes[which] = (n - mine[(size_t) me]) * sizeof(Rec);
+    *nRecv = recvTotal[(size_t) me];
+    *done = true;
+    return 0;
+}
+
 // the received records of exchange #1 -> the job-wide smallest k-mer (nt: assignGroup's first-group quirk, kmermatcher.cpp:463,
 // belongs to exactly one group of the whole job, not to one group per rank)
 static int shard_global_min_kmer(Context *ctx, const Rec *recs, uint64_t n, bool nt) {
@@ -209,6 +319,7 @@ int pg_comm_init(pg_context *ctx, int rank, int world, const void *id) {
     ncclComm_t c = nullptr;
     PG_NCCL(g_nccl.CommInitRank(&c, world, u, rank));
     ctx->comm = c; ctx->rank = rank; ctx->world = world;
+    if (const char *e = getenv("PLASS_B200_SHARD_P2P")) ctx->p2pDisabled = atoi(e) == 0;     // 0: NCCL send / recv exchanges
     for (int i = 0; i < 4; i++) PG_CUDA(cudaEventCreate(&ctx->evXchg[i]));
     return 0;
 }
@@ -218,6 +329,7 @@ int pg_comm_destroy(pg_context *ctx) {
     if (!ctx->comm) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (int w = 0; w < 2; w++) { close_peer_mappings(ctx, w); ctx->xr[w].release(); }
     g_nccl.CommDestroy(comm_of(ctx));
     ctx->comm = nullptr; ctx->world = 1; ctx->rank = 0;
     for (int i = 0; i < 4; i++) { if (ctx->evXchg[i]) cudaEventDestroy(ctx->evXchg[i]); ctx->evXchg[i] = nullptr; }
@@ -305,6 +417,99 @@ int pg_shard_allgather_db(pg_context *ctx, const pg_seqdb *slice, pg_seqdb **out
     return 0;
 }
 
+}  // extern "C"
+
+// pg_shard_iteration with the two exchanges fused into their partition passes (peer memory).  *done = false (nothing changed
+// that matters) if peer mappings cannot be had; the caller then runs the NCCL send / recv variant.
+static int shard_iteration_fused(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, const pg_rs_params *rp, const pg_ex_params *ep,
+                                 pg_seqdb **out_slice, uint32_t *own_lo, uint32_t *own_hi, pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns,
+                                 bool *done) {
+    *done = false;
+    cudaStream_t s = ctx->stream;
+    const int W = ctx->world, me = ctx->rank;
+    const bool nt = db->dbtype == PG_DBTYPE_NUCLEOTIDES;
+    // phase 0: k-mer records of this rank's slice of the sequences; partition by k-mer owner + exchange #1 in one pass
+    begin_call(ctx);
+    uint64_t nRec = 0, nRecv = 0;
+    PG_TRY(km_shard_extract_only(ctx, db, kp, me, W, &nRec));
+    end_shard_phase(ctx, true);
+    begin_call(ctx);
+    {
+        RadixPlan plan; plan.npasses = 0;
+        plan_add_hash_bits(plan, nt ? ~(1ULL << 63) : ~0ULL, 56, 64);      // the same owner function as km_shard_extract: top byte of mix64
+        int owner[256];
+        for (int b = 0; b < 256; b++) owner[b] = (int) ((unsigned) b * (unsigned) W / 256u);
+        bool ok = false;
+        PG_TRY(exchange_fused(ctx, ctx->recA.as<Rec>(), nRec, plan.pass[0], 256, owner, 0, &nRecv, &ok));
+        if (!ok) { end_shard_phase(ctx, false); return 0; }
+    }
+    // phase 1 on the received records: the receive buffer stands in for the first record buffer (no copy)
+    std::swap(ctx->recA, ctx->xr[0]);
+    int rc = shard_global_min_kmer(ctx, ctx->recA.as<Rec>(), nRecv, nt);
+    std::vector<uint64_t> hist(PG_SHARD_HIST_BINS);
+    if (rc == 0) rc = km_shard_group(ctx, db, kp, ctx->recA.p, nRecv, hist.data());
+    ctx->useFirstKmerOverride = false;
+    uint64_t nRecv2 = 0;
+    if (rc == 0) {
+        unsigned long long *d_hist = ctx->commWs.as<unsigned long long>() + 1024;
+        cudaMemcpyAsync(d_hist, hist.data(), sizeof(unsigned long long) * PG_SHARD_HIST_BINS, cudaMemcpyHostToDevice, s);
+        rc = (g_nccl.AllReduce(d_hist, d_hist, PG_SHARD_HIST_BINS, ncclUint64, ncclSum, comm_of(ctx), s) == ncclSuccess) ? 0 : 1;
+        cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned long long) * PG_SHARD_HIST_BINS, cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+    }
+    if (rc == 0) {
+        balanced_bounds((const unsigned long long *) hist.data(), PG_SHARD_HIST_BINS, db->max_key, W, 4.0, ctx->lastBounds);
+        // partition by the representative's owner + exchange #2 in one pass
+        Rec *pairs = nullptr; uint64_t nPairs = 0;
+        km_shard_pairs_location(ctx, &pairs, &nPairs);
+        unsigned *d_bounds = (unsigned *) (ctx->small.as<unsigned long long>() + 64);
+        cudaMemcpyAsync(d_bounds, ctx->lastBounds, sizeof(unsigned) * (W + 1), cudaMemcpyHostToDevice, s);
+        RadixPlan plan; plan.npasses = 0;
+        plan_add_interval(plan, d_bounds, (unsigned) W);
+        int owner[256];
+        for (int b = 0; b < 256; b++) owner[b] = b < W ? b : W - 1;
+        bool ok = false;
+        rc = exchange_fused(ctx, pairs, nPairs, plan.pass[0], W, owner, 1, &nRecv2, &ok);
+        if (rc == 0 && !ok) rc = 1, pg::set_error("multi-GPU: peer memory became unavailable between the two exchanges of a step");
+    }
+    std::swap(ctx->recA, ctx->xr[0]);
+    if (rc) return rc;
+    end_shard_phase(ctx, false);
+    // phase 2: sort #2 + best diagonal + rescore + extension of the owned queries, the pair buffer standing in for recA
+    begin_call(ctx);
+    const uint32_t lo = ctx->lastBounds[me], hi = ctx->lastBounds[me + 1];
+    std::swap(ctx->recA, ctx->xr[1]);
+    ctx->ownLo = lo; ctx->ownHi = hi;
+    pg_hit *dHits = nullptr; uint64_t nH = 0;
+    rc = km_shard_reduce(ctx, db, ctx->recA.p, nRecv2, &dHits, &nH);
+    if (rc == 0 && hits && n_hits) { rc = hits_to_host_overlapped(ctx, dHits, nH, hits); *n_hits = nH; }
+    pg_aln *dAlns = nullptr; uint64_t nA = 0;
+    unsigned char *dExt = nullptr;
+    if (rc == 0) rc = rs_run(ctx, db, dHits, nH, rp, &dAlns, &nA);
+    if (rc == 0 && alns && n_alns) { rc = alns_to_host_overlapped(ctx, dAlns, nA, alns); *n_alns = nA; }
+    if (rc == 0) rc = ex_run(ctx, db, dAlns, nA, ep, out_slice, &dExt);
+    ctx->ownLo = 0; ctx->ownHi = 0xFFFFFFFFu;
+    std::swap(ctx->recA, ctx->xr[1]);
+    if (rc != 0) { cudaStreamSynchronize(ctx->copyStream); return rc; }
+    cudaFreeAsync(dExt, s);
+    end_shard_phase(ctx, false);
+    {
+        float ms = 0;
+        ctx->timings.exchange_ms = 0;
+        for (int w = 0; w < 2; w++) {
+            if (cudaEventElapsedTime(&ms, ctx->evXchg[2 * w], ctx->evXchg[2 * w + 1]) == cudaSuccess) { ctx->lastExchangeMs[w] = ms; ctx->timings.exchange_ms += ms; }
+            else cudaGetLastError();
+        }
+    }
+    if (!ctx->asyncResults) PG_CUDA(cudaStreamSynchronize(ctx->copyStream));
+    if (own_lo) *own_lo = lo;
+    if (own_hi) *own_hi = hi;
+    *done = true;
+    return 0;
+}
+
+extern "C" {
+
 // One whole assemble iteration over `world` GPUs.  `db` is the replicated sequence DB; out_slice receives the new entries
 // of the keys this rank owns ([own_lo, own_hi), ascending with the rank; pg_shard_allgather_db rebuilds the replicated DB
 // for the next iteration); hits / alns (optional, pinned host) are this rank's share of pref_N / aln_N.
@@ -317,6 +522,12 @@ int pg_shard_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_params *
     const int W = ctx->world, me = ctx->rank;
     const bool nt = db->dbtype == PG_DBTYPE_NUCLEOTIDES;
     std::vector<uint64_t> counts((size_t) W);
+    if (!ctx->p2pDisabled) {
+        bool done = false;
+        PG_TRY(shard_iteration_fused(ctx, db, kp, rp, ep, out_slice, own_lo, own_hi, hits, n_hits, alns, n_alns, &done));
+        if (done) return 0;
+        ctx->p2pDisabled = true;          // peer memory is not available between these devices / processes: NCCL send / recv from now on
+    }
     // phase 0: k-mer records of this rank's slice of the sequences, partitioned by the rank owning the k-mer
     begin_call(ctx);
     PG_TRY(km_shard_extract(ctx, db, kp, me, W, counts.data()));
