@@ -270,10 +270,13 @@ int pg_shard_finish(pg_context *ctx, const pg_seqdb *db, const void *device_pair
  *   pg_shard_iteration                 extraction of this rank's slice -> exchange #1 (k-mer records to the k-mer owner)
  *                                      -> sort #1 + assignGroup -> all-reduced work histogram -> equal-work key ranges ->
  *                                      exchange #2 (candidate pairs to the owner of the representative) -> sort #2 + best
- *                                      diagonal -> rescorediagonal -> extension of the owned queries.  Exchanges are
- *                                      grouped ncclSend / ncclRecv between the stages' record buffers; the only host
- *                                      round trips are the W x W count matrix and the work histogram.  out_slice = the
- *                                      new entries of the keys in [*own_lo, *own_hi).
+ *                                      diagonal -> rescorediagonal -> extension of the owned queries.  Each exchange is
+ *                                      FUSED into the partition pass in front of it: the pass stores every digit run
+ *                                      straight into the owner's receive buffer over NVLink (CUDA IPC peer mappings,
+ *                                      stream-ordered barrier); where peer memory cannot be mapped, or with
+ *                                      PLASS_B200_SHARD_P2P=0, the partition pass is followed by grouped ncclSend / ncclRecv.
+ *                                      The only host round trips are the W x W count matrices and the work histogram.
+ *                                      out_slice = the new entries of the keys in [*own_lo, *own_hi).
  *   pg_shard_allgather_db              concatenates the ranks' slices (ascending key ranges in rank order) into a replicated
  *                                      DB: the next iteration's input (data/assemble.sh:153), or the upload of a host DB of
  *                                      which every rank copied only its slice over PCIe. */
@@ -288,6 +291,8 @@ int pg_shard_allgather_db(pg_context *ctx, const pg_seqdb *slice, pg_seqdb **out
 int pg_shard_iteration(pg_context *ctx, const pg_seqdb *db, const pg_km_params *kp, const pg_rs_params *rp, const pg_ex_params *ep,
                        pg_seqdb **out_slice, uint32_t *own_lo, uint32_t *own_hi, pg_hit **hits, uint64_t *n_hits, pg_aln **alns, uint64_t *n_alns);
 int pg_shard_exchange_stats(const pg_context *ctx, float *ms /* [2] */, uint64_t *bytes /* [2] */);
+/* collective: releases the peer-mapped receive buffers of the fused exchanges (re-created by the next pg_shard_iteration) */
+int pg_shard_release_buffers(pg_context *ctx);
 /* the equal-work cut of the representative key space pg_shard_iteration uses (host arithmetic only) */
 int pg_shard_balanced_bounds(const uint64_t *hist, int bins, uint32_t max_key, int world, double per_key_weight, uint32_t *bounds /* world + 1 */);
 

@@ -71,6 +71,7 @@ struct pg_context {
     pg::DevBuf xr[2];
     void *peer[2][16] = {};
     bool p2pDisabled = false;
+    bool extractOnly = false;                  // km_extract: do not reserve the sort's second record buffer
     float lastExchangeMs[2] = {0, 0};
     uint64_t lastExchangeBytes[2] = {0, 0};
     uint32_t lastBounds[257];

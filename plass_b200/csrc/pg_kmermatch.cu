@@ -2036,7 +2036,7 @@ int km_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const Km
     // overflows that, the caller doubles the number of splits (rc 2)
     const unsigned long long cap = ctx->splitDiv > 1 ? h_total / ctx->splitDiv + h_total / (8ull * ctx->splitDiv) + 65536ull : h_total + 1;
     PG_TRY(ctx->recA.reserve(sizeof(Rec) * cap));
-    PG_TRY(ctx->recB.reserve(sizeof(Rec) * cap));
+    if (!ctx->extractOnly) PG_TRY(ctx->recB.reserve(sizeof(Rec) * cap));       // the sort's second buffer (not for the fused multi-GPU exchange)
     Rec *out = ctx->recA.as<Rec>();
     PG_TRY(launch_extract_warp<64>(*db, lists + 0 * (size_t) n, d_clsCount + 0, h_cls[0], c, out, d_outCount, cap, s, &ctx->launches));
     PG_TRY(launch_extract_warp<256>(*db, lists + 1 * (size_t) n, d_clsCount + 1, h_cls[1], c, out, d_outCount, cap, s, &ctx->launches));
@@ -2610,7 +2610,9 @@ int km_shard_extract_only(Context *ctx, const pg_seqdb *db, const pg_km_params *
     uint64_t nRec = 0;
     ctx->seqLo = (unsigned) ((unsigned long long) db->n * (unsigned) rank / (unsigned) world);
     ctx->seqHi = (unsigned) ((unsigned long long) db->n * (unsigned) (rank + 1) / (unsigned) world);
+    ctx->extractOnly = true;
     const int rc = km_extract(ctx, db, p, c, &nRec);
+    ctx->extractOnly = false;
     ctx->seqLo = 0; ctx->seqHi = 0xFFFFFFFFu;
     if (rc) return rc;
     cudaEventRecord(ctx->ev[EV_EXTRACT_END], s);

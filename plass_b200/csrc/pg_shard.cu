@@ -337,6 +337,21 @@ int pg_comm_destroy(pg_context *ctx) {
     return 0;
 }
 
+// Collective: gives the peer-mapped receive buffers of the fused exchanges back (they are re-created by the next
+// pg_shard_iteration).  For callers that need the memory in between, e.g. a single-GPU run of the whole job on one rank.
+int pg_shard_release_buffers(pg_context *ctx) {
+    PG_CHECK(ctx && ctx->comm, "pg_shard_release_buffers: null argument / no communicator");
+    cudaSetDevice(ctx->device);
+    PG_TRY(ctx->commWs.reserve(sizeof(unsigned long long) * 16384));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    PG_TRY(stream_barrier(ctx));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int w = 0; w < 2; w++) { close_peer_mappings(ctx, w); ctx->xr[w].release(); }
+    PG_TRY(stream_barrier(ctx));
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int pg_comm_rank(const pg_context *ctx) { return ctx ? ctx->rank : 0; }
 int pg_comm_world(const pg_context *ctx) { return ctx ? ctx->world : 1; }
 
@@ -443,8 +458,11 @@ static int shard_iteration_fused(pg_context *ctx, const pg_seqdb *db, const pg_k
         PG_TRY(exchange_fused(ctx, ctx->recA.as<Rec>(), nRec, plan.pass[0], 256, owner, 0, &nRecv, &ok));
         if (!ok) { end_shard_phase(ctx, false); return 0; }
     }
-    // phase 1 on the received records: the receive buffer stands in for the first record buffer (no copy)
-    std::swap(ctx->recA, ctx->xr[0]);
+    // phase 1 on the received records: the receive buffer stands in for the first record buffer (no copy) and the extraction's
+    // buffer, dead after the scatter, for the second -- the fused path needs three record-sized buffers, not four
+    DevBuf bufA = ctx->recA, bufB = ctx->recB;
+    void *const r1 = ctx->xr[0].p;
+    ctx->recA = ctx->xr[0]; ctx->recB = bufA;
     int rc = shard_global_min_kmer(ctx, ctx->recA.as<Rec>(), nRecv, nt);
     std::vector<uint64_t> hist(PG_SHARD_HIST_BINS);
     if (rc == 0) rc = km_shard_group(ctx, db, kp, ctx->recA.p, nRecv, hist.data());
@@ -472,13 +490,17 @@ static int shard_iteration_fused(pg_context *ctx, const pg_seqdb *db, const pg_k
         rc = exchange_fused(ctx, pairs, nPairs, plan.pass[0], W, owner, 1, &nRecv2, &ok);
         if (rc == 0 && !ok) rc = 1, pg::set_error("multi-GPU: peer memory became unavailable between the two exchanges of a step");
     }
-    std::swap(ctx->recA, ctx->xr[0]);
+    ctx->xr[0] = ctx->recA; bufA = ctx->recB;                 // (the scratch side may have been re-allocated)
+    ctx->recA = bufA; ctx->recB = bufB;
+    if (rc == 0 && ctx->xr[0].p != r1) { rc = 1; pg::set_error("multi-GPU: the mapped receive buffer of exchange #1 was re-allocated inside the step"); }
     if (rc) return rc;
     end_shard_phase(ctx, false);
-    // phase 2: sort #2 + best diagonal + rescore + extension of the owned queries, the pair buffer standing in for recA
+    // phase 2: sort #2 + best diagonal + rescore + extension of the owned queries, the pair buffer standing in for recA, the
+    // extraction's buffer for recB
     begin_call(ctx);
     const uint32_t lo = ctx->lastBounds[me], hi = ctx->lastBounds[me + 1];
-    std::swap(ctx->recA, ctx->xr[1]);
+    void *const r2 = ctx->xr[1].p;
+    ctx->recA = ctx->xr[1]; ctx->recB = bufA;
     ctx->ownLo = lo; ctx->ownHi = hi;
     pg_hit *dHits = nullptr; uint64_t nH = 0;
     rc = km_shard_reduce(ctx, db, ctx->recA.p, nRecv2, &dHits, &nH);
@@ -489,7 +511,9 @@ static int shard_iteration_fused(pg_context *ctx, const pg_seqdb *db, const pg_k
     if (rc == 0 && alns && n_alns) { rc = alns_to_host_overlapped(ctx, dAlns, nA, alns); *n_alns = nA; }
     if (rc == 0) rc = ex_run(ctx, db, dAlns, nA, ep, out_slice, &dExt);
     ctx->ownLo = 0; ctx->ownHi = 0xFFFFFFFFu;
-    std::swap(ctx->recA, ctx->xr[1]);
+    ctx->xr[1] = ctx->recA; bufA = ctx->recB;
+    ctx->recA = bufA; ctx->recB = bufB;
+    if (rc == 0 && ctx->xr[1].p != r2) { rc = 1; pg::set_error("multi-GPU: the mapped receive buffer of exchange #2 was re-allocated inside the step"); }
     if (rc != 0) { cudaStreamSynchronize(ctx->copyStream); return rc; }
     cudaFreeAsync(dExt, s);
     end_shard_phase(ctx, false);

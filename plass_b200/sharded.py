@@ -202,6 +202,7 @@ class ShardedIteration:
         dist.all_reduce(t)                       # int64 sums wrap like uint64 sums
         tot = t.cpu().numpy().view(np.uint64)
         del hits, alns
+        ctx.shard_release_buffers()              # collective: rank 0 needs the memory for the whole job on one GPU
         res = None
         if self.rank == 0:
             g = full.download()
