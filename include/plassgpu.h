@@ -119,6 +119,8 @@ int pg_device_count(void);
 int pg_init(int device, pg_context **ctx);
 void pg_destroy(pg_context *ctx);
 int pg_get_timings(const pg_context *ctx, pg_timings *out);
+/* frees the context's cached device buffers (re-created on demand) */
+int pg_release_workspace(pg_context *ctx);
 
 int pg_seqdb_upload(pg_context *ctx, const pg_seqdb_view *view, pg_seqdb **db);
 /* Same, but only ENQUEUES the copies on the context's upload stream and returns: the transfer of the next input runs

@@ -22,7 +22,7 @@ EXPORTS = ["pg_last_error", "pg_device_count", "pg_init", "pg_destroy", "pg_get_
            "pg_shard_pairs", "pg_shard_extract", "pg_shard_group", "pg_shard_route", "pg_shard_export", "pg_shard_finish", "pg_shard_owner_range", "pg_seqdb_max_key",
            "pg_seqdb_upload_async", "pg_findassemblystart", "pg_assemble_step0", "pg_cyclecheck", "pg_extractorfs", "pg_translatenucs",
            "pg_seqdb_concat", "pg_set_split_memory_limit", "pg_comm_unique_id", "pg_comm_init", "pg_comm_destroy", "pg_comm_rank", "pg_comm_world",
-           "pg_shard_broadcast_db", "pg_shard_allgather_db", "pg_shard_iteration", "pg_shard_exchange_stats", "pg_shard_balanced_bounds", "pg_shard_release_buffers"]
+           "pg_shard_broadcast_db", "pg_shard_allgather_db", "pg_shard_iteration", "pg_shard_exchange_stats", "pg_shard_balanced_bounds", "pg_shard_release_buffers", "pg_release_workspace"]
 
 
 SHARD_HIST_BINS = 4096   # PG_SHARD_HIST_BINS
@@ -218,6 +218,9 @@ class Context:
 
     def debug_force_splits(self, n):
         _check(load_library().pg_debug_force_splits(self.handle, C.c_uint(int(n))), "pg_debug_force_splits")
+
+    def release_workspace(self):
+        _check(load_library().pg_release_workspace(self.handle), "pg_release_workspace")
 
     def timings(self):
         t = Timings()

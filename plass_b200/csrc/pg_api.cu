@@ -325,6 +325,22 @@ void pg_destroy(pg_context *ctx) {
     delete ctx;
 }
 
+// Gives the context's cached device buffers (record buffers, scratch, result staging) back to the driver; they are
+// re-created on demand.  For callers that alternate between very different problem sizes on one context.
+int pg_release_workspace(pg_context *ctx) {
+    PG_CHECK(ctx, "pg_release_workspace: null argument");
+    cudaSetDevice(ctx->device);
+    PG_CUDA(cudaStreamSynchronize(ctx->stream));
+    PG_CUDA(cudaStreamSynchronize(ctx->copyStream));
+    PG_CUDA(cudaStreamSynchronize(ctx->auxStream));
+    DevBuf *bufs[] = {&ctx->lists, &ctx->recA, &ctx->recB, &ctx->radixWs, &ctx->scratch, &ctx->blockCounts, &ctx->hits,
+                      &ctx->alnAll, &ctx->alns, &ctx->flags, &ctx->exWork, &ctx->exSegs, &ctx->exMeta, &ctx->exLists, &ctx->buckets, &ctx->buckets2, &ctx->wideTabs,
+                      &ctx->nextWork, &ctx->orfInfo, &ctx->pairAcc, &ctx->spill};
+    for (DevBuf *b : bufs) b->release();
+    ctx->rsOut = nullptr; ctx->rsCnt = nullptr; ctx->rsOff = nullptr; ctx->shardPairs = nullptr; ctx->shardPairCount = 0;
+    return 0;
+}
+
 int pg_get_timings(const pg_context *ctx, pg_timings *out) {
     PG_CHECK(ctx && out, "pg_get_timings: null argument");
     *out = ctx->timings;

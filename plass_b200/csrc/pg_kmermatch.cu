@@ -2213,9 +2213,6 @@ static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, 
     else plan_add_bits(plan, 0, 32, 32 + keyBits);
     PG_TRY(ctx->radixWs.reserve(radix_workspace_bytes(nPairs, ctx->digitBits)));
     Rec *sorted = pairs;
-    PG_TRY(radix_sort(pairs, tmp, nPairs, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches));
-    cudaEventRecord(ctx->ev[EV_SORT2_END], s);
-    Rec *other = (sorted == pairs) ? tmp : pairs;
     // per-representative tables: only the owned key range [keyLo, keyHi) (multi-GPU: 1 / world of the keys), addressed by the
     // key itself through pointers shifted by keyLo
     const size_t nT = keyHi > keyLo ? (size_t) (keyHi - keyLo) : 0;
@@ -2242,7 +2239,16 @@ static int km_reduce_segmented(Context *ctx, const pg_seqdb *db, Rec **pairsIO, 
     PG_CUDA(cudaMemsetAsync(d_start0, 0, oOff, s));   // start, end, hit counts
     PG_CUDA(cudaMemsetAsync(d_over, 0, 4 * sizeof(unsigned), s));
     PG_CUDA(cudaMemsetAsync(d_minT0, 0xFF, sizeof(unsigned) * (nT + 1), s));
-    seg_bounds_kernel<<<NUM_SMS * 16, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT);
+    // the last pass of the sort knows every pair's final position: it also leaves the per-representative segment bounds and
+    // smallest targets (otherwise seg_bounds_kernel sweeps the sorted pairs once more)
+    const bool fusedSegments = radix_emits_segments(plan);
+    RadixBounds rb;
+    rb.kind = 1; rb.start = d_start; rb.end = d_end; rb.minLow = d_minT;
+    if (fusedSegments) PG_CUDA(cudaMemsetAsync(d_start0, 0xFF, sizeof(unsigned long long) * (nT + 1), s));
+    PG_TRY(radix_sort(pairs, tmp, nPairs, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches, nullptr, nullptr, fusedSegments ? &rb : nullptr));
+    cudaEventRecord(ctx->ev[EV_SORT2_END], s);
+    Rec *other = (sorted == pairs) ? tmp : pairs;
+    if (!fusedSegments) seg_bounds_kernel<<<NUM_SMS * 16, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT);
     pg_hit *tmpHits = reinterpret_cast<pg_hit *>(other);   // a hit is 16 bytes like a record, at most one per pair
     reduce_rep_warp_kernel<0><<<NUM_SMS * 32, 256, 0, s>>>(sorted, nPairs, d_start, d_end, d_minT, keyLo, keyHi, tmpHits, d_hcnt, d_big, d_bigCnt, d_mid, d_midCnt, d_over);
     // 129 .. 512 pairs: warp per representative, > 512: CTA per representative, both aggregating by (target, diagonal)

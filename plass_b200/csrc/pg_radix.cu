@@ -231,6 +231,37 @@ __global__ void __launch_bounds__(RADIX_THREADS, MINBLOCKS) radix_scatter_kernel
         // contains the digit.
         const int lane = tid & 31;
         unsigned long long localMin = ~0ULL;
+        if (bo.kind == 1) {
+            // segments by the high half of w0 (sort #2: the representative): first / one-past-last output index of every value and
+            // the smallest low half (target) per value, the latter combined per warp before it touches memory
+            for (unsigned j0 = 0; j0 < count; j0 += RADIX_THREADS) {
+                const unsigned j = j0 + tid;
+                const bool valid = j < count;
+                unsigned key = 0xFFFFFFFFu, low = 0xFFFFFFFFu;
+                Rec r; r.w0 = 0; r.w1 = 0;
+                if (valid) { r = tileRecs[j]; key = (unsigned) (r.w0 >> 32); low = (unsigned) r.w0; }
+                unsigned kp = __shfl_up_sync(0xFFFFFFFFu, key, 1), kn = __shfl_down_sync(0xFFFFFFFFu, key, 1);
+                const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+                const unsigned mt = __reduce_min_sync(peers, low);
+                if (valid) {
+                    if (lane == 0) kp = j > 0 ? (unsigned) (tileRecs[j - 1].w0 >> 32) : 0xFFFFFFFFu;
+                    if (lane == 31) kn = j + 1 < count ? (unsigned) (tileRecs[j + 1].w0 >> 32) : 0xFFFFFFFFu;
+                    if (j + 1 >= count) kn = 0xFFFFFFFFu;
+                    const unsigned d = digit_of_t<EXT>(r, dp);
+                    // neighbours with the same key share the digit; a key change inside the tile is a segment boundary only if the
+                    // neighbour is also adjacent in the output, which an equal digit guarantees -- and a differing digit implies a
+                    // differing key anyway
+                    const unsigned long long g = (unsigned long long) (goff[d] + (long long) j);
+                    uint4 raw;
+                    raw.x = (unsigned) r.w0; raw.y = (unsigned) (r.w0 >> 32); raw.z = (unsigned) r.w1; raw.w = (unsigned) (r.w1 >> 32);
+                    reinterpret_cast<uint4 *>(out)[g] = raw;
+                    if (kp != key) atomicMin(&bo.start[key], g);
+                    if (kn != key) atomicMax(&bo.end[key], g + 1ULL);
+                    if (lane == __ffs(peers) - 1) atomicMin(&bo.minLow[key], mt);
+                }
+            }
+            return;
+        }
         for (unsigned j0 = 0; j0 < count; j0 += RADIX_THREADS) {
             const unsigned j = j0 + tid;
             const bool valid = j < count;
@@ -693,6 +724,12 @@ bool radix_emits_bounds(const RadixPlan &plan) {
     return true;
 }
 
+bool radix_emits_segments(const RadixPlan &plan) {
+    if (plan.npasses == 0 || radix_get_mode() != 0 || g_items != 12) return false;
+    for (int p = 0; p < plan.npasses; p++) if (plan.pass[p].mask > 255u || plan.pass[p].hashed == 1 || plan.pass[p].hashed == 2 || plan.pass[p].word != 0) return false;
+    return true;
+}
+
 template <int THREADS, int MINB, int ITEMS, int STAGES>
 static int launch_tma(const Rec *src, Rec *dst, unsigned long long ps, unsigned long long pe, const DigitPass &dp, const unsigned long long *gb,
                       unsigned long long *gbNext, unsigned *status, unsigned *ticket, const RadixBounds *bounds, cudaStream_t stream) {
@@ -857,6 +894,7 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<12, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) sizeof(Rec)));
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<12, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) sizeof(Rec)));
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<12, 3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) sizeof(Rec)));
+        PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<12, 3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) sizeof(Rec)));
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<8, 4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * (int) sizeof(Rec)));
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_wide_kernel<16, 2, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int) (sizeof(Rec) + 2)));
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_wide_kernel<12, 3, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) (sizeof(Rec) + 2)));
@@ -897,7 +935,7 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
             PG_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), stream));
             unsigned long long *gb = bases + ((size_t) p * (portions + 1) + q) * stride;
             if (bins == 256 && mode != 0) {
-                const RadixBounds *bp = (bounds && p == plan.npasses - 1 && radix_emits_bounds(plan)) ? bounds : nullptr;
+                const RadixBounds *bp = (bounds && bounds->kind == 0 && p == plan.npasses - 1 && radix_emits_bounds(plan)) ? bounds : nullptr;
                 if (mode == 2) PG_TRY((launch_tma<256, 3, 8, 2>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, bp, stream)));
                 else if (mode == 3) PG_TRY((launch_tma<512, 2, 4, 3>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, bp, stream)));
                 else PG_TRY((launch_tma<512, 2, 6, 2>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, bp, stream)));
@@ -909,8 +947,13 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
                 else { PG_CHECK(g_items == 12, "radix_sort: wide digits need 12 or 16 records per thread"); radix_scatter_wide_kernel<12, 3, 10><<<tiles, RADIX_THREADS, dynSmemWide, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles); }
             } else if (plan.pass[p].hashed >= 2) {
                 PG_CHECK(g_items == 12, "radix_sort: interval / rebased digits need 12 records per thread");
-                radix_scatter_kernel<12, 3, true, false><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles, RadixBounds());
-            } else if (bounds && p == plan.npasses - 1 && radix_emits_bounds(plan) && g_items == 12) {
+                if (bounds && bounds->kind == 1 && p == plan.npasses - 1 && radix_emits_segments(plan))
+                    radix_scatter_kernel<12, 3, true, true><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles, *bounds);
+                else
+                    radix_scatter_kernel<12, 3, true, false><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles, RadixBounds());
+            } else if (bounds && bounds->kind == 1 && p == plan.npasses - 1 && radix_emits_segments(plan)) {
+                radix_scatter_kernel<12, 3, false, true><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles, *bounds);
+            } else if (bounds && bounds->kind == 0 && p == plan.npasses - 1 && radix_emits_bounds(plan) && g_items == 12) {
                 radix_scatter_kernel<12, 3, false, true><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles, *bounds);
             } else if (g_items == 16) radix_scatter_kernel<16, 2, false, false><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles, RadixBounds());
             else if (g_items == 12) radix_scatter_kernel<12, 3, false, false><<<tiles, RADIX_THREADS, dynSmem, stream>>>(src, dst, ps, pe, plan.pass[p], gb, gb + stride, status, ticket, tiles, RadixBounds());

@@ -51,12 +51,16 @@ struct RadixPlan {
 // w0 & hashMask of the input.  The last pass knows every record's final position, so the separate sweep over the sorted
 // records that used to find the bucket boundaries (one more read of every record) is not needed.  start[] must be preset
 // to 0xFF.., end[] to 0, *minKey to 0xFF.. by the caller.
+// kind 1 (sort #2): the segments are the values of the high half of w0 (the representative); start / end are indexed by it
+// (start preset to 0xFF.., end to 0) and minLow[value] (preset to 0xFF..) receives the smallest low half of w0 (the smallest target).
 struct RadixBounds {
     unsigned long long *start = nullptr;
     unsigned long long *end = nullptr;
     unsigned long long *minKey = nullptr;
     unsigned long long hashMask = 0;
     unsigned bucketMask = 0;
+    int kind = 0;
+    unsigned *minLow = nullptr;
 };
 
 // Workspace owned by the caller (sized by radix_workspace_bytes); maxDigitBits = the widest digit of the plan (8..10).
@@ -67,8 +71,10 @@ size_t radix_workspace_bytes(uint64_t n, int maxDigitBits = 8);
 int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspace, size_t workspace_bytes,
                cudaStream_t stream, Rec **sorted, uint64_t *launches,
                cudaEvent_t evScatterBegin = nullptr, cudaEvent_t evScatterEnd = nullptr, const RadixBounds *bounds = nullptr);
-// true if radix_sort would honour `bounds` for this plan (256-bin digits through the bulk-copy kernel)
+// true if radix_sort would honour `bounds` (kind 0) for this plan
 bool radix_emits_bounds(const RadixPlan &plan);
+// true if radix_sort would honour kind-1 bounds (segments by the high half of w0) for this plan
+bool radix_emits_segments(const RadixPlan &plan);
 // 0: register-tile kernel (round 1), 1: persistent bulk-copy (TMA) kernel, 2 records-per-thread / stage variants; see pg_radix.cu
 void radix_set_mode(int mode);
 int radix_get_mode();

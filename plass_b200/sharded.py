@@ -210,6 +210,7 @@ class ShardedIteration:
             one, h1, a1 = ctx.assemble_iteration(ddb, kp, rp, ep, want_intermediates=True)
             o = one.download()
             one.free()
+            ctx.release_workspace()              # the whole job's record buffers: the sharded steps that follow need the room
             want = np.array([len(h1), len(a1), record_checksum(h1), record_checksum(a1)], dtype=np.uint64)
             eq = {f: bool(np.array_equal(getattr(g, f), getattr(o, f))) for f in ("keys", "lens", "offsets", "data")}
             same_db = all(eq.values())
