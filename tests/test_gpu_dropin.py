@@ -102,7 +102,7 @@ def test_workflow_dropin_matches_reference(tool, wf, iters, tmp_path):
                 assert ca[0] == cb[0] and ca[2] == cb[2] and abs(int(ca[1])) == abs(int(cb[1])), (i, k, a, b)
                 flips += ca[1] != cb[1]
             affected.add(k)
-        assert flips <= max(3, len(want) // 200), (i, flips)
+        assert len(affected) <= 1, (i, flips, sorted(affected)[:4])    # hazard 6: the first k-mer group's representative only
         for name in ("aln_%d" % i, "assembly_%d" % i):
             g = mmseqsdb.read_db(os.path.join(tg, name)).entries_by_key()
             w = mmseqsdb.read_db(os.path.join(tr, name)).entries_by_key()

@@ -359,7 +359,7 @@ def test_kmermatcher_param_sweep_matches_oracle(case, over, golden_root, ctx):
             assert np.array_equal(got[fld], want[fld]), (case, over, fld)
         # the strand sign is only defined up to the documented tie hazard (nt); magnitudes must agree
         assert np.array_equal(np.abs(got["score"]), np.abs(want["score"])), (case, over)
-        assert (got["score"] != want["score"]).sum() <= max(2, len(want) // 500), (case, over)
+        assert len(np.unique(got["rep"][got["score"] != want["score"]])) <= 1, (case, over)   # first k-mer group only
 
 
 @pytest.mark.parametrize("coverage,n_reads", [(20, 4000), (60, 4000), (120, 4000), (500, 3000), (2500, 2500)])

@@ -40,8 +40,10 @@ def test_wide_kmermatcher_matches_oracle_and_golden(golden_root, ctx):
         for f in ("rep", "target", "diag"):
             assert np.array_equal(got[f], want[f]), (s["dbs"][1], f)
         assert np.array_equal(np.abs(got["score"]), np.abs(want["score"])), (s["dbs"][1], "score")
-        flips = int((np.sign(got["score"]) != np.sign(want["score"])).sum())
-        assert flips <= max(3, len(want) // 500), (s["dbs"][1], "strand flips", flips, len(want))
+        flipped = np.sign(got["score"]) != np.sign(want["score"])
+        flips = int(flipped.sum())
+        # hazard 6 concerns the first k-mer group only: every sign-only difference sits under that one representative
+        assert len(np.unique(got["rep"][flipped])) <= 1, (s["dbs"][1], "strand flips under several representatives", flips)
         if flips == 0:
             golden = mmseqsdb.read_db(os.path.join(d, s["dbs"][1]))
             assert_same_entries(ob.format_hits_by_rep(seq.keys, got), golden.entries_by_key(), "%s/%s" % (CASE, s["dbs"][1]))
