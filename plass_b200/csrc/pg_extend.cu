@@ -1039,8 +1039,14 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
         }
         extend_rescore_kernel<<<NUM_SMS * 8, 256, 0, rs>>>(*db, alnStart, c, work, d_cnt, states, parkBuf, segBuf);
         ctx->launches += 1;
-        PG_TRY(read_back_on(ctx, rs, hCnt, d_listCnt + nxtIdx, sizeof(unsigned)));
-        active = hCnt[0];
+        // The list only shrinks from round to round and every kernel reads its length on the device, so the host needs the
+        // length only to stop: it is read back after round 0 (the list drops from all queries to the large ones) and then every
+        // 8th round -- up to 7 empty rounds at the end instead of one host round trip per round (the chain of rounds is as long
+        // as the largest query's alignment list, whatever the number of GPUs).
+        if (round == 0 || (round & 7) == 0) {
+            PG_TRY(read_back_on(ctx, rs, hCnt, d_listCnt + nxtIdx, sizeof(unsigned)));
+            active = hCnt[0];
+        }
         cur = nxt; curIdx = nxtIdx;
         if (cur == listB) { nxt = listC; nxtIdx = 3; } else { nxt = listB; nxtIdx = 1; }
         if (trace && round < 3) lap("  round");

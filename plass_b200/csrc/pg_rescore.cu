@@ -132,7 +132,7 @@ __device__ DiagAln align_by_diagonal(const QView &q, const char *t, unsigned tLe
 // warp striding ~50 columns is mostly idle.  Both sequences are streamed as aligned 32-bit words (funnel-shifted
 // to the byte offset), four columns per pair of loads.  Integer sums: the result equals the warp version's.
 __device__ DiagAln align_by_diagonal_thread(const char *qs, unsigned qLen, const char *t, unsigned tLen, int diagonal, int alph,
-                                            const unsigned char *sA2n, const signed char *sMat) {
+                                            const unsigned char *sA2n, const signed char *sMat, const signed char *sPair) {
     const unsigned dist = (unsigned) abs(diagonal);
     DiagAln r; r.start = -1; r.end = -1; r.score = 0; r.diagLen = 0; r.dist = dist; r.diagonal = diagonal; r.idCnt = 0;
     unsigned qOff, tOff, len;
@@ -155,14 +155,22 @@ __device__ DiagAln align_by_diagonal_thread(const char *qs, unsigned qLen, const
         unsigned qPrev = __ldg(qw), tPrev = __ldg(tw);
         for (unsigned i = 0; i < n; i += 4) {
             const unsigned qNext = __ldg(qw + (i >> 2) + 1), tNext = __ldg(tw + (i >> 2) + 1);   // at most 7 bytes past the column range: inside the DB's tail slack
-            const unsigned q4 = __funnelshift_r(qPrev, qNext, qsh), t4 = __funnelshift_r(tPrev, tNext, tsh);
+            unsigned q4 = __funnelshift_r(qPrev, qNext, qsh), t4 = __funnelshift_r(tPrev, tNext, tsh);
             qPrev = qNext; tPrev = tNext;
+            if (n - i < 4) {                                  // last word: the bytes past the range differ and send the word to the checked path
+                const unsigned keep = 0xFFFFFFFFu >> (8 * (4 - (n - i)));
+                q4 = (q4 & keep) | (0xFFFFFFFFu & ~keep); t4 = (t4 & keep) | (0xFEFEFEFEu & ~keep);
+            }
+            // identities of four columns at once, case-folded (rescorediagonal.cpp:277-282)
+            ids += __popc(__vcmpeq4(q4 & 0xDFDFDFDFu, t4 & 0xDFDFDFDFu)) >> 3;
+            if (((q4 | t4) & 0x80808080u) == 0) {             // plain ASCII: one look-up per column in the pair table
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                if (i + b < n) {
+                for (int b = 0; b < 4; b++) sum += sPair[((q4 >> (8 * b)) & 0x7Fu) * 128u + ((t4 >> (8 * b)) & 0x7Fu)];
+            } else {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
                     const unsigned qc = (q4 >> (8 * b)) & 0xFFu, tc = (t4 >> (8 * b)) & 0xFFu;
-                    sum += sMat[sA2n[qc] * alph + sA2n[tc]];
-                    ids += ((qc & 0xDFu) == (tc & 0xDFu)) ? 1 : 0;
+                    if (i + b < n) sum += sMat[sA2n[qc] * alph + sA2n[tc]];
                 }
             }
         }
@@ -184,8 +192,11 @@ __global__ void __launch_bounds__(256) rescore_kernel(const pg_seqdb db, const p
     __shared__ unsigned char sA2n[256];
     __shared__ unsigned char sRev[256];
     __shared__ signed char sMat[21 * 21];
+    __shared__ signed char sPair[128 * 128];        // score of an ASCII pair in one look-up (the reference's createAsciiSubMat, SubstitutionMatrix.h:56-73)
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { sA2n[i] = c_rs_a2n[i]; sRev[i] = c_rs_rev[i]; }
     for (int i = threadIdx.x; i < 21 * 21; i += blockDim.x) sMat[i] = c_rs_mat[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x) sPair[i] = sMat[sA2n[i >> 7] * c.alph + sA2n[i & 127]];
     __syncthreads();
     const unsigned lane = threadIdx.x & 31;
     const unsigned long long nItems = nHits + c.nSelf;
@@ -228,13 +239,13 @@ __global__ void __launch_bounds__(256) rescore_kernel(const pg_seqdb db, const p
                 for (unsigned d = 1; d <= 1 + tl / 32768; d++) {
                     const int real = (int) (0u - d * 65536u + diag16);
                     if (!(real < 0 && (unsigned) (-real) < tl) && !(real >= 0 && (unsigned) real < (unsigned) qLen)) continue;
-                    const DiagAln tmp = align_by_diagonal_thread(qPtr, (unsigned) qLen, tPtr, tl, real, c.alph, sA2n, sMat);
+                    const DiagAln tmp = align_by_diagonal_thread(qPtr, (unsigned) qLen, tPtr, tl, real, c.alph, sA2n, sMat, sPair);
                     if (tmp.score > mine.score) mine = tmp;
                 }
                 for (unsigned d = 0; d <= (unsigned) qLen / 65536; d++) {
                     const int real = (int) (d * 65536u + diag16);
                     if (!(real < 0 && (unsigned) (-real) < tl) && !(real >= 0 && (unsigned) real < (unsigned) qLen)) continue;
-                    const DiagAln tmp = align_by_diagonal_thread(qPtr, (unsigned) qLen, tPtr, tl, real, c.alph, sA2n, sMat);
+                    const DiagAln tmp = align_by_diagonal_thread(qPtr, (unsigned) qLen, tPtr, tl, real, c.alph, sA2n, sMat, sPair);
                     if (tmp.score > mine.score) mine = tmp;
                 }
             }

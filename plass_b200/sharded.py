@@ -154,7 +154,8 @@ class ShardedIteration:
         if download:
             host = out.download()
             self.last_d2h_bytes = int(hits.nbytes + alns.nbytes + host.data.nbytes + host.offsets.nbytes + host.lens.nbytes + host.keys.nbytes)
-            self.last_host = (hits, alns, host)
+            # the host copies live in pinned blocks of the library's pool: dropped here, so that the next step reuses them
+            del hits, alns, host
         return out
 
     def timings(self):
