@@ -295,6 +295,7 @@ int pg_init(int device, pg_context **out) {
     for (int i = 0; i < EV_COUNT; i++) PG_CUDA(cudaEventCreate(&ctx->ev[i]));
     memset(&ctx->timings, 0, sizeof(ctx->timings));
     if (const char *e = getenv("PLASS_B200_NO_SCRATCH_ALIAS")) ctx->noScratchAlias = atoi(e) != 0;
+    if (const char *e = getenv("PLASS_B200_NO_PREHIST")) ctx->noPreHist = atoi(e) != 0;     // A/B: histogram sweep in front of sort #1
     if (const char *e = getenv("PLASS_B200_BUCKET_TARGET")) { const int b = atoi(e); if (b >= 64 && b <= 1200) ctx->bucketTarget = (unsigned) b; }
     if (const char *e = getenv("PLASS_B200_DIGIT_BITS")) { const int b = atoi(e); if (b >= 8 && b <= 10) ctx->digitBits = b; }
     *out = ctx;

@@ -72,6 +72,12 @@ struct pg_context {
     void *peer[2][16] = {};
     bool p2pDisabled = false;
     bool extractOnly = false;                  // km_extract: do not reserve the sort's second record buffer
+    // histograms of sort #1's partition digits, counted by the extraction kernels (3 x 256 bins); valid for the km_group call
+    // that follows the extraction directly
+    pg::DevBuf preHist;
+    bool preHistValid = false;
+    uint64_t preHistRecords = 0;
+    bool noPreHist = false;                    // debugging / tests: always run the histogram sweep
     float lastExchangeMs[2] = {0, 0};
     uint64_t lastExchangeBytes[2] = {0, 0};
     uint32_t lastBounds[257];

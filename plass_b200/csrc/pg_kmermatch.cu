@@ -224,12 +224,28 @@ __device__ int select_sequential_packed(const PCand *sorted, int cnt, unsigned l
     return nOut;
 }
 
+// By-product of the extraction: the 256-bin histograms of the first three 8-bit digits of mix64(k-mer) -- the digits sort #1's
+// partition passes use (plan_add_hash_bits: shifts 0, 8, 16; the last pass's narrower digit is a fold of its 256 bins).  The
+// records are in shared memory when they leave, so counting them here saves the separate histogram sweep (one more read of
+// every record) in front of the partition.
+constexpr int EXTRACT_HIST_BINS = 3 * 256;
+__device__ __forceinline__ void hist_partition_digits(unsigned *sHist, unsigned long long maskedKmer) {
+    const unsigned long long h = mix64(maskedKmer);
+    atomicAdd(&sHist[(unsigned) h & 255u], 1u);
+    atomicAdd(&sHist[256u + ((unsigned) (h >> 8) & 255u)], 1u);
+    atomicAdd(&sHist[512u + ((unsigned) (h >> 16) & 255u)], 1u);
+}
+
 template <int NMAX, int KT, int NTM>
 __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, const unsigned *__restrict__ list,
                                                            const unsigned *__restrict__ listCount, const KmConst c,
                                                            Rec *__restrict__ out, unsigned long long *__restrict__ outCount,
-                                                           unsigned long long outCap) {
+                                                           unsigned long long outCap, unsigned long long *__restrict__ partHist) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned sHist[EXTRACT_HIST_BINS];
+    for (int i = threadIdx.x; i < EXTRACT_HIST_BINS; i += blockDim.x) sHist[i] = 0;
+    __syncthreads();
+    const unsigned long long histMask = c.nt ? ~(1ULL << 63) : ~0ULL;
     constexpr int WARPS = 4;
     constexpr int CODES = NMAX + 40;   // k <= 32
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -366,7 +382,7 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
                     if (lane == 0) baseF = atomicAdd(outCount, (unsigned long long) nOutF);
                     baseF = __shfl_sync(0xFFFFFFFFu, baseF, 0);
                     if (baseF + nOutF <= outCap)
-                        for (int i = lane; i < nOutF; i += 32) out[baseF + i] = outRecs[i];
+                        for (int i = lane; i < nOutF; i += 32) { const Rec r = outRecs[i]; out[baseF + i] = r; hist_partition_digits(sHist, r.w0 & histMask); }
                     __syncwarp();
                     continue;
                 }
@@ -632,9 +648,12 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
         if (lane == 0 && nOut) base = atomicAdd(outCount, (unsigned long long) nOut);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base + nOut <= outCap)
-            for (int i = lane; i < nOut; i += 32) out[base + i] = outRecs[i];
+            for (int i = lane; i < nOut; i += 32) { const Rec r = outRecs[i]; out[base + i] = r; hist_partition_digits(sHist, r.w0 & histMask); }
         __syncwarp();
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < EXTRACT_HIST_BINS; i += blockDim.x)
+        if (sHist[i]) atomicAdd(partHist + i, (unsigned long long) sHist[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -644,7 +663,11 @@ __global__ void __launch_bounds__(256) extract_block_kernel(const pg_seqdb db, c
                                                             const unsigned *__restrict__ listCount, const KmConst c,
                                                             Rec *__restrict__ out, unsigned long long *__restrict__ outCount,
                                                             unsigned long long outCap, unsigned char *__restrict__ scratch,
-                                                            size_t scratchPerBlock) {
+                                                            size_t scratchPerBlock, unsigned long long *__restrict__ partHist) {
+    __shared__ unsigned sHist[EXTRACT_HIST_BINS];
+    for (int i = threadIdx.x; i < EXTRACT_HIST_BINS; i += 256) sHist[i] = 0;
+    __syncthreads();
+    const unsigned long long histMask = c.nt ? ~(1ULL << 63) : ~0ULL;
     __shared__ unsigned hier[128];
     __shared__ unsigned fine[512];
     __shared__ unsigned sCnt;
@@ -781,9 +804,12 @@ __global__ void __launch_bounds__(256) extract_block_kernel(const pg_seqdb db, c
         const int nOut = sNOut;
         const unsigned long long base = sBase;
         if (base + nOut <= outCap)
-            for (int i = tid; i < nOut; i += 256) out[base + i] = outRecs[i];
+            for (int i = tid; i < nOut; i += 256) { const Rec r = outRecs[i]; out[base + i] = r; hist_partition_digits(sHist, r.w0 & histMask); }
         __syncthreads();
     }
+    __syncthreads();
+    for (int i = tid; i < EXTRACT_HIST_BINS; i += 256)
+        if (sHist[i]) atomicAdd(partHist + i, (unsigned long long) sHist[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1984,13 +2010,14 @@ static __global__ void kmer_count_kernel(const unsigned *__restrict__ lens, unsi
 
 template <int NMAX, int KT, int NTM>
 static int launch_extract_warp_t(const pg_seqdb &db, const unsigned *list, const unsigned *listCount, unsigned hostCount, const KmConst &c,
-                                 Rec *out, unsigned long long *outCount, unsigned long long outCap, cudaStream_t stream, uint64_t *launches) {
+                                 Rec *out, unsigned long long *outCount, unsigned long long outCap, unsigned long long *partHist,
+                                 cudaStream_t stream, uint64_t *launches) {
     const size_t smem = 4 * ((size_t) NMAX * sizeof(PCand) + (size_t) (NMAX + 1) * sizeof(Rec) + (NMAX + 40));
     PG_CUDA(cudaFuncSetAttribute(extract_warp_kernel<NMAX, KT, NTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     unsigned blocks = (hostCount + 3) / 4;
     const unsigned maxBlocks = NUM_SMS * 32;
     if (blocks > maxBlocks) blocks = maxBlocks;
-    extract_warp_kernel<NMAX, KT, NTM><<<blocks, 128, smem, stream>>>(db, list, listCount, c, out, outCount, outCap);
+    extract_warp_kernel<NMAX, KT, NTM><<<blocks, 128, smem, stream>>>(db, list, listCount, c, out, outCount, outCap, partHist);
     if (launches) (*launches)++;
     return 0;
 }
@@ -1998,11 +2025,12 @@ static int launch_extract_warp_t(const pg_seqdb &db, const unsigned *list, const
 // the workflow defaults (aa k = 14, nt k = 22) get fully unrolled instances, anything else the generic one
 template <int NMAX>
 static int launch_extract_warp(const pg_seqdb &db, const unsigned *list, const unsigned *listCount, unsigned hostCount, const KmConst &c,
-                               Rec *out, unsigned long long *outCount, unsigned long long outCap, cudaStream_t stream, uint64_t *launches) {
+                               Rec *out, unsigned long long *outCount, unsigned long long outCap, unsigned long long *partHist,
+                               cudaStream_t stream, uint64_t *launches) {
     if (hostCount == 0) return 0;
-    if (!c.nt && c.k == 14) return launch_extract_warp_t<NMAX, 14, 0>(db, list, listCount, hostCount, c, out, outCount, outCap, stream, launches);
-    if (c.nt && c.k == 22) return launch_extract_warp_t<NMAX, 22, 1>(db, list, listCount, hostCount, c, out, outCount, outCap, stream, launches);
-    return launch_extract_warp_t<NMAX, 0, -1>(db, list, listCount, hostCount, c, out, outCount, outCap, stream, launches);
+    if (!c.nt && c.k == 14) return launch_extract_warp_t<NMAX, 14, 0>(db, list, listCount, hostCount, c, out, outCount, outCap, partHist, stream, launches);
+    if (c.nt && c.k == 22) return launch_extract_warp_t<NMAX, 22, 1>(db, list, listCount, hostCount, c, out, outCount, outCap, partHist, stream, launches);
+    return launch_extract_warp_t<NMAX, 0, -1>(db, list, listCount, hostCount, c, out, outCount, outCap, partHist, stream, launches);
 }
 
 // Stage 1: extraction.  Leaves the records in ws.recA, returns their count.
@@ -2038,9 +2066,14 @@ int km_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const Km
     PG_TRY(ctx->recA.reserve(sizeof(Rec) * cap));
     if (!ctx->extractOnly) PG_TRY(ctx->recB.reserve(sizeof(Rec) * cap));       // the sort's second buffer (not for the fused multi-GPU exchange)
     Rec *out = ctx->recA.as<Rec>();
-    PG_TRY(launch_extract_warp<64>(*db, lists + 0 * (size_t) n, d_clsCount + 0, h_cls[0], c, out, d_outCount, cap, s, &ctx->launches));
-    PG_TRY(launch_extract_warp<256>(*db, lists + 1 * (size_t) n, d_clsCount + 1, h_cls[1], c, out, d_outCount, cap, s, &ctx->launches));
-    PG_TRY(launch_extract_warp<1024>(*db, lists + 2 * (size_t) n, d_clsCount + 2, h_cls[2], c, out, d_outCount, cap, s, &ctx->launches));
+    // histograms of the partition digits, counted while the records leave shared memory (consumed by km_group_bucketed)
+    ctx->preHistValid = false;
+    PG_TRY(ctx->preHist.reserve(sizeof(unsigned long long) * EXTRACT_HIST_BINS));
+    unsigned long long *d_partHist = ctx->preHist.as<unsigned long long>();
+    PG_CUDA(cudaMemsetAsync(d_partHist, 0, sizeof(unsigned long long) * EXTRACT_HIST_BINS, s));
+    PG_TRY(launch_extract_warp<64>(*db, lists + 0 * (size_t) n, d_clsCount + 0, h_cls[0], c, out, d_outCount, cap, d_partHist, s, &ctx->launches));
+    PG_TRY(launch_extract_warp<256>(*db, lists + 1 * (size_t) n, d_clsCount + 1, h_cls[1], c, out, d_outCount, cap, d_partHist, s, &ctx->launches));
+    PG_TRY(launch_extract_warp<1024>(*db, lists + 2 * (size_t) n, d_clsCount + 2, h_cls[2], c, out, d_outCount, cap, d_partHist, s, &ctx->launches));
     if (h_cls[3]) {
         const unsigned maxL = db->max_seq_len;
         size_t n2 = 1;
@@ -2050,7 +2083,7 @@ int km_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const Km
         unsigned blocks = h_cls[3] < (unsigned) NUM_SMS * 2 ? h_cls[3] : NUM_SMS * 2;
         PG_TRY(ctx->scratch.reserve(perBlock * blocks));
         extract_block_kernel<<<blocks, 256, 0, s>>>(*db, lists + 3 * (size_t) n, d_clsCount + 3, c, out, d_outCount, cap,
-                                                    ctx->scratch.as<unsigned char>(), perBlock);
+                                                    ctx->scratch.as<unsigned char>(), perBlock, d_partHist);
         ctx->launches++;
     }
     unsigned long long h_out = 0;
@@ -2059,13 +2092,14 @@ int km_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, const Km
     if (h_out > cap && ctx->splitDiv > 1) { *nRecords = h_out; return 2; }
     PG_CHECK(h_out <= cap, "kmermatcher: k-mer array overflow");
     *nRecords = h_out;
+    ctx->preHistValid = true; ctx->preHistRecords = h_out;
     (void) p;
     return 0;
 }
 
 // Stage 2: sort #1 + group.  Input records in recA (n), output pair records in recA (count returned).
 // fast path of stage 2 (see hash_group_kernel); returns *ok = false if a bucket overflowed the shared-memory table
-static int km_group_bucketed(Context *ctx, const KmConst &c, uint64_t nRecords, uint64_t *nPairs, bool *ok) {
+static int km_group_bucketed(Context *ctx, const KmConst &c, uint64_t nRecords, uint64_t *nPairs, bool *ok, bool preHist) {
     cudaStream_t s = ctx->stream;
     *ok = false;
     int B = 1;
@@ -2097,7 +2131,8 @@ static int km_group_bucketed(Context *ctx, const KmConst &c, uint64_t nRecords, 
         PG_CUDA(cudaMemsetAsync(d_end, 0, sizeof(unsigned long long) * (size_t) nBuckets, s));
     }
     PG_TRY(radix_sort(ctx->recA.as<Rec>(), ctx->recB.as<Rec>(), nRecords, plan, ctx->radixWs.p, ctx->radixWs.cap, s, &sorted, &ctx->launches,
-                      ctx->ev[EV_SCATTER1_BEGIN], ctx->ev[EV_SCATTER1_END], fusedBounds ? &rb : nullptr));
+                      ctx->ev[EV_SCATTER1_BEGIN], ctx->ev[EV_SCATTER1_END], fusedBounds ? &rb : nullptr,
+                      preHist ? ctx->preHist.as<unsigned long long>() : nullptr));
     ctx->timings.sort1_passes = (uint32_t) plan.npasses;
     cudaEventRecord(ctx->ev[EV_SORT1_END], s);
     if (!fusedBounds) {
@@ -2167,10 +2202,14 @@ static int km_group_bucketed(Context *ctx, const KmConst &c, uint64_t nRecords, 
 int km_group(Context *ctx, const pg_seqdb *db, const KmConst &c, uint64_t nRecords, uint64_t *nPairs) {
     cudaStream_t s = ctx->stream;
     *nPairs = 0;
+    // the extraction's digit histograms describe exactly the records it has just left in recA: valid for the call that follows
+    // it directly, never for records that arrived from other ranks
+    const bool preHist = ctx->preHistValid && ctx->preHistRecords == nRecords && !ctx->noPreHist;
+    ctx->preHistValid = false;
     if (nRecords == 0) return 0;
     if (!ctx->forceFullSort && !c.wide) {
         bool ok = false;
-        PG_TRY(km_group_bucketed(ctx, c, nRecords, nPairs, &ok));
+        PG_TRY(km_group_bucketed(ctx, c, nRecords, nPairs, &ok, preHist));
         if (ok) return 0;
     }
     RadixPlan plan; plan.npasses = 0;
@@ -2584,6 +2623,7 @@ int km_shard_extract(Context *ctx, const pg_seqdb *db, const pg_km_params *p, in
     ctx->seqHi = (unsigned) ((unsigned long long) db->n * (unsigned) (rank + 1) / (unsigned) world);
     const int rc = km_extract(ctx, db, p, c, &nRec);
     ctx->seqLo = 0; ctx->seqHi = 0xFFFFFFFFu;
+    ctx->preHistValid = false;                    // these records are exchanged before they are grouped
     if (rc) return rc;
     for (int r = 0; r < world; r++) counts[r] = 0;
     ctx->shardPairs = ctx->recA.as<Rec>(); ctx->shardPairCount = nRec;
@@ -2620,6 +2660,7 @@ int km_shard_extract_only(Context *ctx, const pg_seqdb *db, const pg_km_params *
     const int rc = km_extract(ctx, db, p, c, &nRec);
     ctx->extractOnly = false;
     ctx->seqLo = 0; ctx->seqHi = 0xFFFFFFFFu;
+    ctx->preHistValid = false;                    // these records are exchanged before they are grouped
     if (rc) return rc;
     cudaEventRecord(ctx->ev[EV_EXTRACT_END], s);
     ctx->shardPairs = ctx->recA.as<Rec>(); ctx->shardPairCount = nRec;
@@ -2643,6 +2684,7 @@ int km_shard_group(Context *ctx, const pg_seqdb *db, const pg_km_params *p, cons
     PG_TRY(ctx->recB.reserve(sizeof(Rec) * (nRec + 1)));
     if (nRec && d_records != ctx->recA.p) PG_CUDA(cudaMemcpyAsync(ctx->recA.p, d_records, sizeof(Rec) * nRec, cudaMemcpyDeviceToDevice, s));
     uint64_t nPairs = 0;
+    ctx->preHistValid = false;                    // records received from the other ranks
     PG_TRY(km_group(ctx, db, c, nRec, &nPairs));
     if (nRec == 0) record_empty_group_events(ctx);
     ctx->timings.n_kmer_records = nRec; ctx->timings.n_pair_records = nPairs;
@@ -2675,6 +2717,7 @@ extern "C" int pg_debug_extract(pg_context *ctx, const pg_seqdb *db, const pg_km
     PG_TRY(km_setup_constants(db, p, c, ctx->stream));
     uint64_t nRec = 0;
     PG_TRY(km_extract(ctx, db, p, c, &nRec));
+    ctx->preHistValid = false;
     uint64_t *h = nullptr;
     PG_TRY(alloc_pinned(sizeof(Rec) * (nRec + 1), (void **) &h));
     PG_CUDA(cudaMemcpyAsync(h, ctx->recA.p, sizeof(Rec) * nRec, cudaMemcpyDeviceToHost, ctx->stream));

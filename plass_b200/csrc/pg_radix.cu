@@ -58,6 +58,16 @@ __global__ void __launch_bounds__(512) radix_hist_kernel(const Rec *__restrict__
         if (sh[i]) atomicAdd(&ghist[i], (unsigned long long) sh[i]);
 }
 
+// histograms counted by the producer of the records (256 bins per pass): digit d of a pass with a narrower mask collects the
+// bins congruent to d
+__global__ void radix_fold_hist_kernel(const unsigned long long *__restrict__ pre, unsigned long long *__restrict__ ghist, RadixPlan plan) {
+    const int p = blockIdx.x, d = threadIdx.x;
+    const unsigned mask = plan.pass[p].mask;
+    unsigned long long c = 0;
+    if ((unsigned) d <= mask) for (unsigned b = (unsigned) d; b < 256u; b += mask + 1u) c += pre[p * 256 + b];
+    ghist[p * 256 + d] = c;
+}
+
 // exclusive scan of each pass's bins -> bases[p][portion 0][stride]
 __global__ void radix_scan_kernel(const unsigned long long *__restrict__ ghist, unsigned long long *__restrict__ bases,
                                   int portionsPlus1, int stride) {
@@ -879,7 +889,8 @@ int radix_scatter_peer(const Rec *a, uint64_t n, const DigitPass &pass, void *wo
 }
 
 int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspace, size_t workspace_bytes,
-               cudaStream_t stream, Rec **sorted, uint64_t *launches, cudaEvent_t evScatterBegin, cudaEvent_t evScatterEnd, const RadixBounds *bounds) {
+               cudaStream_t stream, Rec **sorted, uint64_t *launches, cudaEvent_t evScatterBegin, cudaEvent_t evScatterEnd, const RadixBounds *bounds,
+               const unsigned long long *preHist) {
     *sorted = a;
     if (n == 0 || plan.npasses == 0) return 0;
     PG_CHECK(plan.npasses <= RADIX_MAX_PASSES, "radix_sort: too many passes");
@@ -915,7 +926,13 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
     if (histBlocks < 1) histBlocks = 1;
     bool ext = false;
     for (int p = 0; p < plan.npasses; p++) ext = ext || plan.pass[p].hashed >= 2;
-    if (ext) radix_hist_kernel<true><<<histBlocks, 512, (size_t) plan.npasses * stride * sizeof(unsigned), stream>>>(a, n, plan, ghist, stride);
+    bool usePre = preHist != nullptr && stride == 256 && plan.npasses <= 3;
+    for (int p = 0; p < plan.npasses && usePre; p++) {
+        const DigitPass &dp = plan.pass[p];
+        usePre = dp.hashed == 1 && dp.word == 0 && dp.shift == 8 * p && dp.mask <= 255u && ((dp.mask + 1u) & dp.mask) == 0u;
+    }
+    if (usePre) radix_fold_hist_kernel<<<plan.npasses, 256, 0, stream>>>(preHist, ghist, plan);
+    else if (ext) radix_hist_kernel<true><<<histBlocks, 512, (size_t) plan.npasses * stride * sizeof(unsigned), stream>>>(a, n, plan, ghist, stride);
     else radix_hist_kernel<false><<<histBlocks, 512, (size_t) plan.npasses * stride * sizeof(unsigned), stream>>>(a, n, plan, ghist, stride);
     radix_scan_kernel<<<plan.npasses, 256, 0, stream>>>(ghist, bases, (int) (portions + 1), stride);
     if (launches) *launches += 2;

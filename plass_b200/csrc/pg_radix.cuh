@@ -70,7 +70,11 @@ size_t radix_workspace_bytes(uint64_t n, int maxDigitBits = 8);
 // scratch buffer of the same size; *sorted points to whichever of the two holds the result.
 int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspace, size_t workspace_bytes,
                cudaStream_t stream, Rec **sorted, uint64_t *launches,
-               cudaEvent_t evScatterBegin = nullptr, cudaEvent_t evScatterEnd = nullptr, const RadixBounds *bounds = nullptr);
+               cudaEvent_t evScatterBegin = nullptr, cudaEvent_t evScatterEnd = nullptr, const RadixBounds *bounds = nullptr,
+               const unsigned long long *preHist = nullptr);
+// preHist (device, 3 x 256 counters): the histograms of the 8-bit digits of mix64(w0 & hashMask) at shifts 0, 8, 16 over exactly
+// these n records, counted by the producer of the records.  If the plan consists of such digits (plan_add_hash_bits from bit 0,
+// at most three passes; a narrower last digit is folded) the histogram sweep over the records is skipped.
 // true if radix_sort would honour `bounds` (kind 0) for this plan
 bool radix_emits_bounds(const RadixPlan &plan);
 // true if radix_sort would honour kind-1 bounds (segments by the high half of w0) for this plan

@@ -71,6 +71,34 @@ def test_radix_pass_variants(mode, golden_root, ctx):
         lib.pg_debug_set_radix_mode(before)
 
 
+def test_partition_histograms_counted_by_the_extraction(ctx, monkeypatch):
+    """Sort #1's digit histograms are a by-product of the extraction kernels (no histogram sweep over the records).  A context
+    that runs the sweep instead (PLASS_B200_NO_PREHIST=1) must give the same hits, aa and nt, at record counts that need one,
+    two and three partition passes (the last pass's narrower digit is a fold of its 256 counted bins)."""
+    from plass_b200 import synth
+    cases = []
+    for n_reads, seed in ((1500, 11), (40000, 12), (700000, 13)):      # 1, 2 and 3 partition passes
+        cases.append((synth.protein_fragments(synth.make_reads(n_reads, seed=seed)), api.default_km_params(False)))
+    cases.append((synth.nucleotide_db(synth.make_reads(60000, seed=14)), api.default_km_params(True)))
+    got = []
+    for db, kp in cases:
+        ddb = ctx.upload(db)
+        got.append(ctx.kmermatcher(ddb, kp).copy())
+        ddb.free()
+    monkeypatch.setenv("PLASS_B200_NO_PREHIST", "1")
+    other = api.Context(0)
+    try:
+        for (db, kp), g in zip(cases, got):
+            ddb = other.upload(db)
+            want = other.kmermatcher(ddb, kp)
+            ddb.free()
+            assert len(g) == len(want) and len(want) > 0
+            for f in ("rep", "target", "score", "diag"):
+                assert np.array_equal(g[f], want[f]), f
+    finally:
+        other.close()
+
+
 def test_spill_list_of_oversized_buckets_matches_oracle(ctx):
     """A k-mer that occurs in thousands of sequences (here: 1500x coverage of a 300 nt region inside a 20x data set) makes
     its bucket larger than the shared-memory hash join takes.  Only those buckets go through the spill list (copied out,
