@@ -174,7 +174,7 @@ struct ExState {
 
 __global__ void aln_ranges_kernel(const pg_seqdb db, const pg_aln *__restrict__ alns, unsigned long long nAlns,
                                   unsigned long long *__restrict__ alnStart, unsigned *__restrict__ alnCount,
-                                  unsigned *__restrict__ activeList, unsigned *__restrict__ activeCount) {
+                                  unsigned *__restrict__ activeList, unsigned *__restrict__ activeCount, unsigned *__restrict__ bigList) {
     const unsigned long long j = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nAlns) return;
     const unsigned qk = alns[j].query;
@@ -185,12 +185,12 @@ __global__ void aln_ranges_kernel(const pg_seqdb db, const pg_aln *__restrict__ 
     alnStart[qi] = j;
     alnCount[qi] = (unsigned) (k - j);
     if (k - j >= 2) activeList[atomicAdd(activeCount, 1u)] = qi;   // only the self alignment: nothing can be popped for extension
-    if (k - j > EX_WARP_MAX_ALNS) atomicAdd(activeCount + 2, 1u);  // queries that need the heap path even for amino acids
+    if (k - j > EX_WARP_MAX_ALNS) bigList[atomicAdd(activeCount + 2, 1u)] = qi;   // queries that need the heap path even for amino acids
 }
 
 // the same from the per-sequence alignment counts rescorediagonal left behind (fused iteration): only the work lists
 __global__ void active_from_counts_kernel(const unsigned *__restrict__ alnCount, unsigned long long n,
-                                          unsigned *__restrict__ activeList, unsigned *__restrict__ activeCount) {
+                                          unsigned *__restrict__ activeList, unsigned *__restrict__ activeCount, unsigned *__restrict__ bigList) {
     const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned c = i < n ? alnCount[i] : 0u;
     const unsigned lane = threadIdx.x & 31;
@@ -199,7 +199,10 @@ __global__ void active_from_counts_kernel(const unsigned *__restrict__ alnCount,
     if (lane == 0 && m) base = atomicAdd(activeCount, (unsigned) __popc(m));
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (c >= 2) activeList[base + __popc(m & ((1u << lane) - 1u))] = (unsigned) i;
-    if (lane == 0 && big) atomicAdd(activeCount + 2, (unsigned) __popc(big));
+    unsigned base2 = 0;
+    if (lane == 0 && big) base2 = atomicAdd(activeCount + 2, (unsigned) __popc(big));
+    base2 = __shfl_sync(0xFFFFFFFFu, base2, 0);
+    if (c > EX_WARP_MAX_ALNS) bigList[base2 + __popc(big & ((1u << lane) - 1u))] = (unsigned) i;
 }
 
 __global__ void init_out_kernel(const pg_seqdb db, unsigned *__restrict__ outLen) {
@@ -861,28 +864,53 @@ __global__ void __launch_bounds__(256) materialize_kernel(const pg_seqdb db, con
             if (nseg == 0) src = db.data + db.offsets[qi];
             else segs = segBuf + alnStart[qi] + qi;
         }
-        unsigned todo = __ballot_sync(0xFFFFFFFFu, live);
+        // unchanged sequences (the majority): four at a time, the loads of all four in flight before the first store -- one
+        // sequence per step is one exposed memory latency per ~50 bytes
+        unsigned plain = __ballot_sync(0xFFFFFFFFu, live && nseg == 0);
+        while (plain) {
+            const char *sp[4]; char *dp[4]; unsigned ll[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                sp[k] = nullptr; dp[k] = nullptr; ll[k] = 0;
+                if (plain) {
+                    const int j = __ffs(plain) - 1;
+                    plain &= plain - 1;
+                    sp[k] = (const char *) __shfl_sync(0xFFFFFFFFu, (unsigned long long) src, j);
+                    dp[k] = outData + __shfl_sync(0xFFFFFFFFu, o, j);
+                    ll[k] = __shfl_sync(0xFFFFFFFFu, len, j);
+                }
+            }
+            char a[4], b[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                a[k] = 0; b[k] = 0;
+                if (lane < ll[k]) a[k] = sp[k][lane];
+                if (lane + 32 < ll[k]) b[k] = sp[k][lane + 32];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (lane < ll[k]) dp[k][lane] = a[k];
+                if (lane + 32 < ll[k]) dp[k][lane + 32] = b[k];
+                for (unsigned i = lane + 64; i < ll[k]; i += 32) dp[k][i] = sp[k][i];
+            }
+        }
+        // new contigs: the rope segments one after the other
+        unsigned todo = __ballot_sync(0xFFFFFFFFu, live && nseg != 0);
         while (todo) {
             const int j = __ffs(todo) - 1;
             todo &= todo - 1;
             char *dst = outData + __shfl_sync(0xFFFFFFFFu, o, j);
             const unsigned ns = __shfl_sync(0xFFFFFFFFu, nseg, j);
-            if (ns == 0) {
-                const char *sp = (const char *) __shfl_sync(0xFFFFFFFFu, (unsigned long long) src, j);
-                const unsigned l = __shfl_sync(0xFFFFFFFFu, len, j);
-                for (unsigned i = lane; i < l; i += 32) dst[i] = sp[i];
-            } else {
-                const ExSeg *sg = (const ExSeg *) __shfl_sync(0xFFFFFFFFu, (unsigned long long) segs, j);
-                unsigned w = 0;
-                for (unsigned s = 0; s < ns; s++) {
-                    const ExSeg g = sg[s];
-                    const char *sp = db.data + db.offsets[g.src];
-                    for (unsigned i = lane; i < g.len; i += 32)
-                        dst[w + i] = g.rev ? (char) c_ex_revN[(unsigned char) sp[g.start + g.len - 1 - i]] : sp[g.start + i];
-                    w += g.len;
-                }
-                if (lane == 0) { dst[w] = '\n'; dst[w + 1] = '\0'; }
+            const ExSeg *sg = (const ExSeg *) __shfl_sync(0xFFFFFFFFu, (unsigned long long) segs, j);
+            unsigned w = 0;
+            for (unsigned s = 0; s < ns; s++) {
+                const ExSeg g = sg[s];
+                const char *sp = db.data + db.offsets[g.src];
+                for (unsigned i = lane; i < g.len; i += 32)
+                    dst[w + i] = g.rev ? (char) c_ex_revN[(unsigned char) sp[g.start + g.len - 1 - i]] : sp[g.start + i];
+                w += g.len;
             }
+            if (lane == 0) { dst[w] = '\n'; dst[w + 1] = '\0'; }
         }
     }
 }
@@ -985,8 +1013,8 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
     if (nAlns && d_alns == ctx->rsOut && ctx->rsCnt) {
         alnStart = const_cast<unsigned long long *>(ctx->rsOff);      // read-only from here on
         alnCount = const_cast<unsigned *>(ctx->rsCnt);
-        active_from_counts_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(alnCount, n, listA, d_listCnt);
-    } else if (nAlns) aln_ranges_kernel<<<(unsigned) ((nAlns + 255) / 256), 256, 0, s>>>(*db, d_alns, nAlns, alnStart, alnCount, listA, d_listCnt);
+        active_from_counts_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(alnCount, n, listA, d_listCnt, listC);
+    } else if (nAlns) aln_ranges_kernel<<<(unsigned) ((nAlns + 255) / 256), 256, 0, s>>>(*db, d_alns, nAlns, alnStart, alnCount, listA, d_listCnt, listC);
     ctx->launches += 2;
     unsigned hCnt[3] = {0, 0, 0};
     PG_TRY(read_back(ctx, hCnt, d_listCnt, 3 * sizeof(unsigned)));
@@ -1017,6 +1045,9 @@ int ex_run(Context *ctx, const pg_seqdb *db, const pg_aln *d_alns, uint64_t nAln
             *db, d_alns, alnStart, alnCount, c, cur, d_listCnt + curIdx, segBuf, segCount, outLen, ext, used);
         ctx->launches++;
         if (!needHeap) active = 0;
+        // the rounds start from the list of the large queries (listC, count [2]) that the setup kernel left, not from a sweep
+        // over all active queries
+        else { cur = listC; curIdx = 2; active = hCnt[2]; }
         lap("extend_query_warp");
     }
     for (int round = 0; active > 0; round++) {
