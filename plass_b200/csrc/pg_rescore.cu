@@ -157,13 +157,14 @@ __device__ DiagAln align_by_diagonal_thread(const char *qs, unsigned qLen, const
             const unsigned qNext = __ldg(qw + (i >> 2) + 1), tNext = __ldg(tw + (i >> 2) + 1);   // at most 7 bytes past the column range: inside the DB's tail slack
             unsigned q4 = __funnelshift_r(qPrev, qNext, qsh), t4 = __funnelshift_r(tPrev, tNext, tsh);
             qPrev = qNext; tPrev = tNext;
-            if (n - i < 4) {                                  // last word: the bytes past the range differ and send the word to the checked path
-                const unsigned keep = 0xFFFFFFFFu >> (8 * (4 - (n - i)));
-                q4 = (q4 & keep) | (0xFFFFFFFFu & ~keep); t4 = (t4 & keep) | (0xFEFEFEFEu & ~keep);
-            }
+            const unsigned keep = (n - i < 4) ? 0xFFFFFFFFu >> (8 * (4 - (n - i))) : 0xFFFFFFFFu;     // the columns of this word inside the range
+            // bytes >= 0x7E (never in a sequence DB; 0x7F / 0x7E is the padding pair below) take the checked path
+            const bool plainAscii = (((q4 | t4 | (q4 + 0x02020202u) | (t4 + 0x02020202u)) & 0x80808080u) & keep) == 0;
+            // last word: the columns past the range become the padding pair, which scores 0 and is not an identity
+            q4 = (q4 & keep) | (0x7F7F7F7Fu & ~keep); t4 = (t4 & keep) | (0x7E7E7E7Eu & ~keep);
             // identities of four columns at once, case-folded (rescorediagonal.cpp:277-282)
             ids += __popc(__vcmpeq4(q4 & 0xDFDFDFDFu, t4 & 0xDFDFDFDFu)) >> 3;
-            if (((q4 | t4) & 0x80808080u) == 0) {             // plain ASCII: one look-up per column in the pair table
+            if (plainAscii) {                                 // one look-up per column in the pair table
 #pragma unroll
                 for (int b = 0; b < 4; b++) sum += sPair[((q4 >> (8 * b)) & 0x7Fu) * 128u + ((t4 >> (8 * b)) & 0x7Fu)];
             } else {
@@ -196,7 +197,9 @@ __global__ void __launch_bounds__(256) rescore_kernel(const pg_seqdb db, const p
     for (int i = threadIdx.x; i < 256; i += blockDim.x) { sA2n[i] = c_rs_a2n[i]; sRev[i] = c_rs_rev[i]; }
     for (int i = threadIdx.x; i < 21 * 21; i += blockDim.x) sMat[i] = c_rs_mat[i];
     __syncthreads();
-    for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x) sPair[i] = sMat[sA2n[i >> 7] * c.alph + sA2n[i & 127]];
+    // (0x7F, 0x7E) is the padding pair of a partial last word: score 0
+    for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x)
+        sPair[i] = (i == 0x7F * 128 + 0x7E) ? (signed char) 0 : sMat[sA2n[i >> 7] * c.alph + sA2n[i & 127]];
     __syncthreads();
     const unsigned lane = threadIdx.x & 31;
     const unsigned long long nItems = nHits + c.nSelf;
