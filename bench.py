@@ -618,6 +618,12 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes / max(passes, 1), "launch_ms": scatter_ms / max(passes, 1), "peak_source": peak_src}
     stage_keys = ("extract_ms", "sort1_ms", "group_ms", "sort2_ms", "reduce_ms", "rescore_ms", "extend_ms", "exchange_ms", "total_ms")
     stage_ms = {k: float(np.mean([t[k] for t in tim])) for k in stage_keys}
+    if runner is not None and "exchange1_ms" in tim[-1]:
+        # rank 0's two fused partition + exchange kernels (stream-ordered barrier included) and the bytes it sent over NVLink
+        for k in ("exchange1_ms", "exchange2_ms"):
+            stage_ms[k] = float(np.mean([t[k] for t in tim]))
+        stage_ms["exchange1_bytes_sent"] = int(tim[-1]["exchange1_bytes_sent"])
+        stage_ms["exchange2_bytes_sent"] = int(tim[-1]["exchange2_bytes_sent"])
     # per-stage position against the HBM roofline: algorithmic bytes of DESIGN.md section 3 / stage time / peak
     npair, nhit, naln = int(tim[-1]["n_pair_records"]), int(tim[-1]["n_hits"]), int(tim[-1]["n_alns"])
     stage_frac = None
