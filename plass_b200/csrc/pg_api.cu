@@ -47,14 +47,17 @@ __global__ void count_nonzero_kernel(const unsigned char *__restrict__ v, unsign
 }
 
 // max length, residue count, max key, key density -- one small reduction kernel
-__global__ void seqdb_stats_kernel(const unsigned *__restrict__ lens, const unsigned *__restrict__ keys, unsigned long long n,
-                                   unsigned long long *__restrict__ out /* [0] sum(len), [1] maxLen, [2] maxKey, [3] nonDense, [4] not ascending */) {
-    unsigned long long sum = 0, mx = 0, mk = 0, nd = 0, na = 0;
+__global__ void seqdb_stats_kernel(const unsigned *__restrict__ lens, const unsigned *__restrict__ keys, const unsigned long long *__restrict__ offsets,
+                                   unsigned long long n,
+                                   unsigned long long *__restrict__ out /* [0] sum(len), [1] maxLen, [2] maxKey, [3] nonDense, [4] not ascending, [5] gaps */) {
+    unsigned long long sum = 0, mx = 0, mk = 0, nd = 0, na = 0, gaps = 0;
     for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long) gridDim.x * blockDim.x) {
         const unsigned l = lens[i], k = keys[i];
         sum += l; mx = max(mx, (unsigned long long) l); mk = max(mk, (unsigned long long) k); nd += (k != (unsigned) i);
         if (i > 0 && keys[i - 1] >= k) na++;
+        if (i + 1 < n && offsets[i] + l != offsets[i + 1]) gaps++;
     }
+    gaps = __reduce_add_sync(0xFFFFFFFFu, (unsigned) min(gaps, 0xFFFFFFFFull));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
@@ -63,7 +66,11 @@ __global__ void seqdb_stats_kernel(const unsigned *__restrict__ lens, const unsi
         mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
         mk = max(mk, __shfl_xor_sync(0xFFFFFFFFu, mk, o));
     }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], sum); atomicMax(&out[1], mx); atomicMax(&out[2], mk); atomicAdd(&out[3], nd); if (na) atomicAdd(&out[4], na); }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[0], sum); atomicMax(&out[1], mx); atomicMax(&out[2], mk); atomicAdd(&out[3], nd);
+        if (na) atomicAdd(&out[4], na);
+        if (gaps) atomicAdd(&out[5], gaps);
+    }
 }
 
 // Host-supplied prefilter hits / alignments name sequences by key: every key must exist in the DB before a kernel uses
@@ -97,14 +104,15 @@ static int validate_keys(Context *ctx, const pg_seqdb *db, const T *d_items, uin
 int seqdb_finalize(Context *ctx, pg_seqdb *db) {
     PG_TRY(ctx->small.reserve(4096));
     unsigned long long *d = ctx->small.as<unsigned long long>() + 16;
-    PG_CUDA(cudaMemsetAsync(d, 0, 40, ctx->stream));
-    if (db->n) seqdb_stats_kernel<<<NUM_SMS * 2, 256, 0, ctx->stream>>>(db->lens, db->keys, db->n, d);
-    unsigned long long h[5];
+    PG_CUDA(cudaMemsetAsync(d, 0, 48, ctx->stream));
+    if (db->n) seqdb_stats_kernel<<<NUM_SMS * 2, 256, 0, ctx->stream>>>(db->lens, db->keys, db->offsets, db->n, d);
+    unsigned long long h[6];
     PG_TRY(read_back(ctx, h, d, sizeof(h)));
     db->residues = (double) h[0] - 2.0 * (double) db->n;        // DBReader::getAminoAcidDBSize (DBReader.cpp:537-546)
     db->max_seq_len = h[1] >= 2 ? (unsigned) (h[1] - 2) : 0;
     db->max_key = (unsigned) h[2];
     db->dense_keys = (h[3] == 0);
+    db->contiguous = (h[5] == 0);
     PG_CHECK(h[4] == 0, "sequence DB: keys must be strictly ascending (index order of a sequence DB)");
     PG_CHECK(db->max_key < 0xFFFFFFF0u, "sequence DB: keys >= 2^32 - 16 are reserved");
     return 0;

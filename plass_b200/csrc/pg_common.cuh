@@ -110,6 +110,7 @@ struct pg_seqdb {
     unsigned max_key = 0;
     double residues = 0;                  // getAminoAcidDBSize = sum(len) - 2n
     bool dense_keys = false;
+    bool contiguous = false;              // offsets[i] + lens[i] == offsets[i + 1] for every i < n - 1 (entries back to back in index order)
     bool borrowed = false;                // pg_seqdb_adopt: the arrays belong to the caller
     bool downloadPending = false;         // an asynchronous pg_seqdb_download is (or was) in flight on the copy stream
     // pg_seqdb_upload_async: the host -> device copies run on the context's upload stream; evReady marks their end and the
@@ -117,3 +118,21 @@ struct pg_seqdb {
     cudaEvent_t evReady = nullptr;
     bool uploadPending = false;
 };
+
+namespace pg {
+// key -> index with the DB's own shortcuts: a dense DB (key == index everywhere, the usual sequence DB) needs no look at the
+// keys array at all -- one 32-byte sector less per random look-up
+__device__ __forceinline__ unsigned find_id_db(const pg_seqdb &db, unsigned key) {
+    if (db.dense_keys) return key < (unsigned) db.n ? key : 0xFFFFFFFFu;
+    return find_id(db.keys, (unsigned) db.n, key);
+}
+// entry i: first byte and entry length (residues + 2).  Entries that lie back to back give their length as the difference of
+// two neighbouring offsets (the same sector three times out of four) instead of a load from a third array.
+__device__ __forceinline__ const char *seq_entry(const pg_seqdb &db, unsigned i, unsigned *entryLen) {
+    const unsigned long long o = db.offsets[i];
+    if (db.contiguous && (unsigned long long) i + 1 < db.n) *entryLen = (unsigned) (db.offsets[i + 1] - o);
+    else *entryLen = db.lens[i];
+    return db.data + o;
+}
+}  // namespace pg
+

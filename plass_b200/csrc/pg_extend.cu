@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(128) extend_round_kernel(const pg_seqdb db, co
                 if ((rightStart || leftStart) && notRightStartAndLeftStart && isNotIdentity) { best = res; got = true; break; }
             }
             if (!got) break;
-            const unsigned targetId = find_id(db.keys, (unsigned) db.n, best.dbKey);
+            const unsigned targetId = find_id_db(db, best.dbKey);
             const unsigned targetSeqLen = db.lens[targetId] - 2;
             if (best.dbStartPos == 0) {
                 if ((targetSeqLen - (unsigned) (best.dbEndPos + 1)) <= rightOff) continue;
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(256) extend_round_warp_kernel(const pg_seqdb d
         const bool entered = alive;                           // this element is in the queue of this round
         // every lane resolves ITS target once (index + length): the pops below then need no dependent global loads
         unsigned myTargetId = 0, myTargetLen = 0;
-        if (alive) { myTargetId = find_id(db.keys, (unsigned) db.n, r.dbKey); myTargetLen = db.lens[myTargetId] - 2; }
+        if (alive) { myTargetId = find_id_db(db, r.dbKey); myTargetLen = db.lens[myTargetId] - 2; }
         // selectFragmentToExtend's predicate (assembleresult.cpp:40-57): failing elements are popped and dropped
         if (alive) {
             const bool notRightStartAndLeftStart = !(r.dbStartPos == 0 && r.qStartPos == 0);
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(256) extend_query_warp_kernel(const pg_seqdb d
                 alive = (rightStart || leftStart) && notRightStartAndLeftStart && (r.dbKey != queryKey);
             }
             if (alive && myTargetId == 0xFFFFFFFFu) {
-                myTargetId = find_id(db.keys, (unsigned) db.n, r.dbKey);
+                myTargetId = find_id_db(db, r.dbKey);
                 myTargetSeq = db.data + db.offsets[myTargetId];
             }
             // packed priority: (score, alnLength, smaller dbKey)
@@ -763,9 +763,10 @@ __global__ void __launch_bounds__(256) extend_rescore_kernel(const pg_seqdb db, 
             rope.segs = segBuf + a0 + qi; rope.n = st.ropeN; rope.len = st.ropeLen;
             slot = a0 + it.y;
             r = parkBuf[slot];
-            const unsigned tId = find_id(db.keys, (unsigned) db.n, r.dbKey);
-            tLen = db.lens[tId] - 2;
-            tSeq = db.data + db.offsets[tId];
+            const unsigned tId = find_id_db(db, r.dbKey);
+            unsigned tEntry;
+            tSeq = seq_entry(db, tId, &tEntry);
+            tLen = tEntry - 2;
             diag = (int) ((unsigned) r.qStartPos + st.leftOff) - r.dbStartPos;
             const unsigned dist = (unsigned) abs(diag);
             if (diag >= 0 && dist < rope.len) { len = min(tLen, rope.len - dist); qOff = dist; valid = len > 0; }

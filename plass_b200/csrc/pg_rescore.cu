@@ -214,8 +214,8 @@ __global__ void __launch_bounds__(256) rescore_kernel(const pg_seqdb db, const p
             if (item < nHits) {
                 const pg_hit h = hits[item];
                 qKey = h.rep; tKey = h.target; prefScore = h.score; diag16 = (unsigned short) (short) h.diag;
-                qi = find_id(db.keys, (unsigned) db.n, qKey);
-                ti = find_id(db.keys, (unsigned) db.n, tKey);
+                qi = find_id_db(db, qKey);
+                ti = find_id_db(db, tKey);
             } else {
                 qi = ti = c.selfLo + (unsigned) (item - nHits);
                 qKey = tKey = db.keys[qi];
@@ -224,8 +224,9 @@ __global__ void __launch_bounds__(256) rescore_kernel(const pg_seqdb db, const p
         const char *qPtr = nullptr, *tPtr = nullptr; int qLen = 0, dbLen = 0;
         bool scoreIt = false;
         if (live) {
-            qPtr = db.data + db.offsets[qi]; qLen = (int) db.lens[qi] - 2;
-            tPtr = db.data + db.offsets[ti]; dbLen = (int) db.lens[ti] - 2;
+            unsigned ql, tl;
+            qPtr = seq_entry(db, qi, &ql); qLen = (int) ql - 2;
+            tPtr = seq_entry(db, ti, &tl); dbLen = (int) tl - 2;
             scoreIt = rs_can_be_covered(c.covThr, c.covMode, (float) qLen, (float) dbLen);
             if (!scoreIt) acc[item] = 0;                       // `continue` at rescorediagonal.cpp:214-216
         }
