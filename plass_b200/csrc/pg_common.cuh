@@ -1,5 +1,6 @@
 // pg_common.cuh -- shared device/host helpers of the B200 hot path (sm_100a only).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -62,6 +63,15 @@ __host__ __device__ __forceinline__ unsigned long long xxh64_u64(unsigned long l
     h *= P3;
     h ^= h >> 32;
     return h;
+}
+
+// cudaFuncSetAttribute is a per-DEVICE setting: call sites remember the devices they have configured, not a process-wide flag
+// (contexts on several GPUs in one process).  True the first time the site runs on the calling thread's current device.
+inline bool first_use_on_device(std::atomic<unsigned long long> &seen) {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ULL << (d & 63);
+    return (seen.fetch_or(bit) & bit) == 0;
 }
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }

@@ -397,11 +397,10 @@ int cc_run(Context *ctx, const pg_seqdb *db, int maxSeqLen, int k, unsigned **d_
     PG_CUDA(cudaMemsetAsync(split, 0, sizeof(unsigned) * ((size_t) n + 1), s));
     PG_CUDA(cudaMemsetAsync(cnt, 0, 64, s));
     if (n) {
-        static bool attr = false;
-        if (!attr) {
+        static std::atomic<unsigned long long> attrDev{0};
+        if (first_use_on_device(attrDev)) {
             PG_CUDA(cudaFuncSetAttribute(cc_warp_kernel<256, W0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (S0::PER_WARP * W0)));
             PG_CUDA(cudaFuncSetAttribute(cc_warp_kernel<1024, W1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (S1::PER_WARP * W1)));
-            attr = true;
         }
         const unsigned blocks0 = std::min<unsigned>((n + W0 - 1) / W0, NUM_SMS * 16);
         cc_warp_kernel<256, W0><<<blocks0, W0 * 32, S0::PER_WARP * W0, s>>>(*db, 0u, (unsigned) S0::MAX_LEN, (unsigned) maxSeqLen, k, split);

@@ -390,11 +390,10 @@ int orf_run(Context *ctx, const pg_seqdb *db, const pg_orf_params *p, int transl
     const unsigned blocks = std::max(1u, std::min<unsigned>((n + 127) / 128, NUM_SMS * 16));
     constexpr size_t ORF_SMEM_BYTES = 4112 + 1024;
     {
-        static bool attr = false;
-        if (!attr) {
+        static std::atomic<unsigned long long> attrDev{0};
+        if (first_use_on_device(attrDev)) {
             PG_CUDA(cudaFuncSetAttribute(orf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ORF_SMEM_BYTES));
             PG_CUDA(cudaFuncSetAttribute(orf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ORF_SMEM_BYTES));
-            attr = true;
         }
     }
     if (n) {

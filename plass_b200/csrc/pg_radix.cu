@@ -745,7 +745,7 @@ static int launch_tma(const Rec *src, Rec *dst, unsigned long long ps, unsigned 
                       unsigned long long *gbNext, unsigned *status, unsigned *ticket, const RadixBounds *bounds, cudaStream_t stream) {
     constexpr int TILE = THREADS * ITEMS;
     const int smem = STAGES * TILE * (int) sizeof(Rec);
-    static bool attr[2] = {false, false};
+    static std::atomic<unsigned long long> attrDev[2];
     const unsigned tiles = (unsigned) ((pe - ps + TILE - 1) / TILE);
     const unsigned grid = std::min<unsigned>(tiles, (unsigned) NUM_SMS * (unsigned) MINB);
     // one tile period: 2 x TILE x 16 B per CTA at this SM's share of ~5 TB/s (read + write), in SM cycles at ~1.9 GHz
@@ -753,10 +753,10 @@ static int launch_tma(const Rec *src, Rec *dst, unsigned long long ps, unsigned 
     if (stagger < 0) { stagger = 11000; if (const char *e = getenv("PLASS_B200_RADIX_STAGGER")) stagger = std::max(0, atoi(e)); }
     const unsigned staggerCycles = tiles > grid ? (unsigned) stagger : 0u;
     if (bounds) {
-        if (!attr[1]) { PG_CUDA(cudaFuncSetAttribute(radix_scatter_tma_kernel<THREADS, MINB, ITEMS, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[1] = true; }
+        if (first_use_on_device(attrDev[1])) PG_CUDA(cudaFuncSetAttribute(radix_scatter_tma_kernel<THREADS, MINB, ITEMS, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         radix_scatter_tma_kernel<THREADS, MINB, ITEMS, STAGES, true><<<grid, THREADS, smem, stream>>>(src, dst, ps, pe, dp, gb, gbNext, status, ticket, tiles, *bounds, staggerCycles);
     } else {
-        if (!attr[0]) { PG_CUDA(cudaFuncSetAttribute(radix_scatter_tma_kernel<THREADS, MINB, ITEMS, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr[0] = true; }
+        if (first_use_on_device(attrDev[0])) PG_CUDA(cudaFuncSetAttribute(radix_scatter_tma_kernel<THREADS, MINB, ITEMS, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         radix_scatter_tma_kernel<THREADS, MINB, ITEMS, STAGES, false><<<grid, THREADS, smem, stream>>>(src, dst, ps, pe, dp, gb, gbNext, status, ticket, tiles, RadixBounds(), staggerCycles);
     }
     return 0;
@@ -862,12 +862,11 @@ int radix_scatter_peer(const Rec *a, uint64_t n, const DigitPass &pass, void *wo
     PG_CHECK(workspace_bytes >= radix_workspace_bytes(n, 8) && pass.mask <= 255u, "radix_scatter_peer: workspace too small / digit wider than 8 bits");
     unsigned long long *ghist, *bases; unsigned *status; size_t statusWords;
     peer_ws_layout(workspace, n, &ghist, &bases, &status, &statusWords);
-    static bool attr = false;
+    static std::atomic<unsigned long long> attrDev{0};
     const int dynSmem = 3072 * (int) sizeof(Rec);
-    if (!attr) {
+    if (first_use_on_device(attrDev)) {
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<12, 3, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dynSmem));
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<12, 3, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dynSmem));
-        attr = true;
     }
     const unsigned long long portions = num_portions(n);
     for (unsigned long long q = 0; q < portions; q++) {
@@ -897,10 +896,10 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
     const int stride = plan_stride(plan);
     PG_CHECK(workspace_bytes >= radix_workspace_bytes(n, stride == 1024 ? 10 : (stride == 512 ? 9 : 8)), "radix_sort: workspace too small");
     PG_CHECK((size_t) plan.npasses * stride * sizeof(unsigned) <= 48 * 1024, "radix_sort: too many wide passes for one histogram launch");
-    static bool attrSet = false;
+    static std::atomic<unsigned long long> attrDev{0};
     const int dynSmem = (int) (tile_records() * sizeof(Rec));
     const int dynSmemWide = (int) (tile_records() * (sizeof(Rec) + 2));    // wide digits: two bytes
-    if (!attrSet) {
+    if (first_use_on_device(attrDev)) {
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<16, 2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int) sizeof(Rec)));
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<12, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) sizeof(Rec)));
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<12, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) sizeof(Rec)));
@@ -911,7 +910,6 @@ int radix_sort(Rec *a, Rec *b, uint64_t n, const RadixPlan &plan, void *workspac
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_wide_kernel<12, 3, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) (sizeof(Rec) + 2)));
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_wide_kernel<16, 2, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int) (sizeof(Rec) + 2)));
         PG_CUDA(cudaFuncSetAttribute(radix_scatter_wide_kernel<12, 3, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3072 * (int) (sizeof(Rec) + 2)));
-        attrSet = true;
     }
     const unsigned long long portions = num_portions(n);
     unsigned char *ws = (unsigned char *) workspace;
