@@ -666,9 +666,12 @@ __global__ void __launch_bounds__(256) extend_query_warp_kernel(const pg_seqdb d
                 if (diag >= 0 && dist < ropeLen) { len = min(myTargetLen, ropeLen - dist); qOff = dist; valid = len > 0; }
                 else if (diag < 0 && dist < myTargetLen) { len = min(myTargetLen - dist, ropeLen); tOff = dist; valid = len > 0; }
                 if (valid) {
-                    first = (rope.at(qOff) == '*' || (unsigned char) myTargetSeq[tOff] == '*') ? 1u : 0u;
+                    // the four end residues are fetched together (a short-circuited `||` would expose their latencies one by one)
+                    const unsigned char q0 = rope.at(qOff), t0 = (unsigned char) myTargetSeq[tOff];
+                    const unsigned char qE = rope.at(qOff + len - 1), tE = (unsigned char) myTargetSeq[tOff + len - 1];
+                    first = (q0 == '*' || t0 == '*') ? 1u : 0u;
                     last = len - 1;
-                    if (last > 0 && (rope.at(qOff + len - 1) == '*' || (unsigned char) myTargetSeq[tOff + len - 1] == '*')) last--;
+                    if (last > 0 && (qE == '*' || tE == '*')) last--;
                 }
             }
             long long mySum = 0; int myIds = 0;
@@ -772,9 +775,11 @@ __global__ void __launch_bounds__(256) extend_rescore_kernel(const pg_seqdb db, 
             if (diag >= 0 && dist < rope.len) { len = min(tLen, rope.len - dist); qOff = dist; valid = len > 0; }
             else if (diag < 0 && dist < tLen) { len = min(tLen - dist, rope.len); tOff = dist; valid = len > 0; }
             if (valid) {
-                first = (rope.at(qOff) == '*' || target_at(tSeq, tLen, r.rev, tOff) == '*') ? 1u : 0u;
+                const unsigned char q0 = rope.at(qOff), t0 = target_at(tSeq, tLen, r.rev, tOff);
+                const unsigned char qE = rope.at(qOff + len - 1), tE = target_at(tSeq, tLen, r.rev, tOff + len - 1);
+                first = (q0 == '*' || t0 == '*') ? 1u : 0u;
                 last = len - 1;
-                if (last > 0 && (rope.at(qOff + len - 1) == '*' || target_at(tSeq, tLen, r.rev, tOff + len - 1) == '*')) last--;
+                if (last > 0 && (qE == '*' || tE == '*')) last--;
             }
         }
         // ---- phase 2: the warp sums the diagonals one by one

@@ -237,7 +237,7 @@ __device__ __forceinline__ void hist_partition_digits(unsigned *sHist, unsigned 
 }
 
 template <int NMAX, int KT, int NTM>
-__global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, const unsigned *__restrict__ list,
+__global__ void __launch_bounds__(128, 8) extract_warp_kernel(const pg_seqdb db, const unsigned *__restrict__ list,
                                                            const unsigned *__restrict__ listCount, const KmConst c,
                                                            Rec *__restrict__ out, unsigned long long *__restrict__ outCount,
                                                            unsigned long long outCap, unsigned long long *__restrict__ partHist) {
@@ -261,13 +261,43 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
         __syncthreads();
     }
     const unsigned nList = *listCount;
-    for (unsigned li = blockIdx.x * WARPS + w; li < nList; li += gridDim.x * WARPS) {
-        const unsigned si = list[li];
-        const char *seq = db.data + db.offsets[si];
-        const int entryLen = (int) db.lens[si] - 2;
+    // Software pipeline over the warp's sequences, three stages deep: while sequence li is processed, the first 64 residues of
+    // li + s, the index entry (offset / length / key) of li + 2s and the list entry of li + 3s are in flight -- every load of an
+    // iteration depends only on values requested an iteration earlier.  (Straight code sits through three dependent memory
+    // latencies -- list -> offset / length -> residues -- per ~50-residue sequence.)
+    const unsigned liStride = gridDim.x * WARPS;
+    unsigned li = blockIdx.x * WARPS + w;
+    unsigned si0 = 0, si1 = 0, si2 = 0; unsigned long long off0 = 0, off1 = 0; int len0 = 0, len1 = 0;
+    unsigned char pre0 = 0, pre1 = 0;
+    if (li < nList) {
+        si0 = list[li]; off0 = db.offsets[si0]; len0 = (int) db.lens[si0] - 2;
+        if (lane < len0) pre0 = (unsigned char) db.data[off0 + lane];
+        if (lane + 32 < len0) pre1 = (unsigned char) db.data[off0 + lane + 32];
+    }
+    if ((unsigned long long) li + liStride < nList) { si1 = list[li + liStride]; off1 = db.offsets[si1]; len1 = (int) db.lens[si1] - 2; }
+    if ((unsigned long long) li + 2ull * liStride < nList) si2 = list[li + 2 * liStride];
+    for (; li < nList; li += liStride) {
+        const unsigned si = si0;
+        const char *seq = db.data + off0;
+        const int entryLen = len0;
+        const unsigned char cur0 = pre0, cur1 = pre1;
+        const unsigned long long rest = (unsigned long long) nList - li;      // > 0; sequence li + a*s exists iff a * s < rest
+        // stage 1 -> 0: the next sequence's residues are requested (its index entry arrived during the last iteration)
+        si0 = si1; off0 = off1; len0 = len1;
+        pre0 = 0; pre1 = 0;
+        if (liStride < rest) {
+            if (lane < len0) pre0 = (unsigned char) db.data[off0 + lane];
+            if (lane + 32 < len0) pre1 = (unsigned char) db.data[off0 + lane + 32];
+        }
+        // stage 2 -> 1: index entry of the sequence after next; stage 3 -> 2: list entry of the one after that
+        if (2ull * liStride < rest) { si1 = si2; off1 = db.offsets[si1]; len1 = (int) db.lens[si1] - 2; }
+        if (3ull * liStride < rest) si2 = list[li + 3 * liStride];
+        const unsigned id = db.keys[si];         // needed only when the records are written
         // Sequence::mapSequence (Sequence.cpp:476-489): map until '\n' / '\0'
         int L = entryLen;
-        for (int i = lane; i < entryLen; i += 32) {
+        if (lane < entryLen) { codes[lane] = c_aa2num[cur0]; if (cur0 == '\n' || cur0 == 0) L = min(L, (int) lane); }
+        if (lane + 32 < entryLen) { codes[lane + 32] = c_aa2num[cur1]; if (cur1 == '\n' || cur1 == 0) L = min(L, (int) lane + 32); }
+        for (int i = lane + 64; i < entryLen; i += 32) {
             const unsigned char ch = (unsigned char) seq[i];
             codes[i] = c_aa2num[ch];
             if (ch == '\n' || ch == 0) L = min(L, i);
@@ -275,7 +305,6 @@ __global__ void __launch_bounds__(128) extract_warp_kernel(const pg_seqdb db, co
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) L = min(L, __shfl_xor_sync(0xFFFFFFFFu, L, o));
         __syncwarp();
-        const unsigned id = db.keys[si];
         // whole-sequence hash: Util::hash (poly 31) then XXH64 (kmermatcher.cpp:133-138).  Each lane hashes a
         // chunk; H(AB) = H(A) * 31^|B| + H(B) is associative, so the chunks fold in log2(32) shuffle steps.
         unsigned long long seqHash;
