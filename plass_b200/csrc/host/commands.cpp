@@ -149,6 +149,7 @@ void applyThreads(const Flags &f) {
 
 pg_seqdb *uploadSeqDb(const mmdb::Reader &r) {
     if (r.dbtype != mmdb::DBTYPE_AMINO_ACIDS && r.dbtype != mmdb::DBTYPE_NUCLEOTIDES) die("input is not a sequence database");
+    if (r.segmented()) die("internal error: a sequence database must be opened as one contiguous buffer");
     pg_seqdb_view v;
     v.data = r.data(); v.data_bytes = r.dataBytes();
     v.offsets = r.offsets.data(); v.lens = r.lens.data(); v.keys = r.keys.data(); v.n = r.size(); v.dbtype = r.dbtype;
@@ -332,7 +333,7 @@ std::vector<uint64_t> runStarts(const std::vector<uint32_t> &keys, const T *recs
 void writePrefDb(const std::string &path, bool nucl, const std::vector<uint32_t> &keys, const pg_hit *hits, uint64_t nHits) {
     std::string err;
     mmdb::Writer w;
-    if (!w.open(path, nucl ? mmdb::DBTYPE_PREFILTER_REV_RES : mmdb::DBTYPE_PREFILTER_RES, err)) die(err);
+    if (!w.open(path, nucl ? mmdb::DBTYPE_PREFILTER_REV_RES : mmdb::DBTYPE_PREFILTER_RES, err, true)) die(err);     // a data file per thread
     const std::vector<uint64_t> start = runStarts(keys, hits, nHits, [](const pg_hit &h) { return h.rep; });
     w.writeAll(keys.size(), [&](size_t i) { return keys[i]; }, [&](size_t i, std::string &buf) {
         char line[64];
@@ -372,7 +373,7 @@ struct EvalueText {
 void writeAlnDb(const std::string &path, const std::vector<uint32_t> &keys, const pg_aln *alns, uint64_t nAlns) {
     std::string err;
     mmdb::Writer w;
-    if (!w.open(path, mmdb::DBTYPE_ALIGNMENT_RES, err)) die(err);
+    if (!w.open(path, mmdb::DBTYPE_ALIGNMENT_RES, err, true)) die(err);     // a data file per thread, as rescorediagonal's DBWriter leaves them
     const std::vector<uint64_t> start = runStarts(keys, alns, nAlns, [](const pg_aln &a) { return a.query; });
     w.writeAll(keys.size(), [&](size_t i) { return keys[i]; }, [&](size_t i, std::string &buf) {
         static thread_local EvalueText evText;
@@ -392,14 +393,29 @@ void writeAlnDb(const std::string &path, const std::vector<uint32_t> &keys, cons
     if (!w.close()) die("write error");
 }
 
-void writeSeqDb(pg_seqdb *out, const std::string &path, int dbtype) {
-    char *data; uint64_t bytes, *offs, n; uint32_t *lens, *keys;
-    if (pg_seqdb_download(gpu(), out, &data, &bytes, &offs, &lens, &keys, &n) != 0) die(pg_last_error());
+// sequence DB from host arrays (entry i = data[offs[i] .. offs[i] + lens[i]), its last byte the '\0')
+void writeSeqArrays(const std::string &path, int dbtype, const char *data, uint64_t bytes, const uint64_t *offs, const uint32_t *lens,
+                    const uint32_t *keys, size_t n) {
     mmdb::Writer w;
     std::string err;
     if (!w.open(path, dbtype, err)) die(err);
-    w.writeAll(n, [&](size_t i) { return keys[i]; }, [&](size_t i, std::string &buf) { buf.append(data + offs[i], lens[i] - 1); });
+    // the buffer is the data file already when the entries lie back to back and end with their '\0' (every DB the kernels build)
+    unsigned long long gaps = 0;
+    const int nT = mmdb::hostThreads();
+#pragma omp parallel for num_threads(nT) schedule(static) reduction(+ : gaps)
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t next = i + 1 < n ? offs[i + 1] : bytes;
+        if (lens[i] == 0 || offs[i] + lens[i] != next || data[offs[i] + lens[i] - 1] != '\0') gaps++;
+    }
+    if (n && gaps == 0 && offs[0] == 0) w.writeContiguous(data, bytes, n, keys, offs, lens);
+    else w.writeAll(n, [&](size_t i) { return keys[i]; }, [&](size_t i, std::string &buf) { buf.append(data + offs[i], lens[i] - 1); });
     if (!w.close()) die("write error");
+}
+
+void writeSeqDb(pg_seqdb *out, const std::string &path, int dbtype) {
+    char *data; uint64_t bytes, *offs, n; uint32_t *lens, *keys;
+    if (pg_seqdb_download(gpu(), out, &data, &bytes, &offs, &lens, &keys, &n) != 0) die(pg_last_error());
+    writeSeqArrays(path, dbtype, data, bytes, offs, lens, keys, (size_t) n);
     pg_free_host(data); pg_free_host(offs); pg_free_host(lens); pg_free_host(keys);
 }
 
@@ -502,7 +518,7 @@ int extendCommand(int argc, const char **argv, bool nuclCommand) {
     checkSubMat(f);
     std::string err;
     mmdb::Reader seq, aln;
-    if (!seq.open(f.positional[0], err) || !aln.open(f.positional[1], err)) die(err);
+    if (!seq.open(f.positional[0], err) || !aln.open(f.positional[1], err, false)) die(err);
     const bool nucl = seq.dbtype == mmdb::DBTYPE_NUCLEOTIDES;
     (void) nuclCommand;   // like the reference, the comparator follows the command, the letters follow the DB type
     const pg_ex_params p = exParams(f, nuclCommand);
@@ -566,7 +582,7 @@ int rescorediagonal(int argc, const char **argv) {
     if (f.positional[0] != f.positional[1]) die("rescorediagonal on the GPU path requires query DB == target DB (as in assemble.sh / nuclassemble.sh)");
     std::string err;
     mmdb::Reader seq, pref;
-    if (!seq.open(f.positional[0], err) || !pref.open(f.positional[2], err)) die(err);
+    if (!seq.open(f.positional[0], err) || !pref.open(f.positional[2], err, false)) die(err);
     const bool nucl = seq.dbtype == mmdb::DBTYPE_NUCLEOTIDES;
     if (pref.dbtype != (nucl ? mmdb::DBTYPE_PREFILTER_REV_RES : mmdb::DBTYPE_PREFILTER_RES)) die("prefilter DB type does not match the sequence DB");
     if (pref.size() != seq.size() || !std::equal(pref.keys.begin(), pref.keys.end(), seq.keys.begin()))
@@ -600,7 +616,7 @@ int findassemblystart(int argc, const char **argv) {
     requireValue(f, "--compressed", "0", "uncompressed DBs only");
     std::string err;
     mmdb::Reader seq, aln;
-    if (!seq.open(f.positional[0], err) || !aln.open(f.positional[1], err)) die(err);
+    if (!seq.open(f.positional[0], err) || !aln.open(f.positional[1], err, false)) die(err);
     if (seq.dbtype != mmdb::DBTYPE_AMINO_ACIDS) die("findassemblystart expects an amino-acid sequence DB");
     const PodArray<pg_aln> alns = parseAlnDb(aln);
     pg_seqdb *db = uploadSeqDb(seq), *out = nullptr;
@@ -804,7 +820,7 @@ int dbdiff(int argc, const char **argv) {
     if (mode != "exact" && mode != "aln" && mode != "pref") die("dbdiff --mode must be exact, aln or pref");
     std::string err;
     mmdb::Reader a, b;
-    if (!a.open(f.positional[0], err) || !b.open(f.positional[1], err)) die(err);
+    if (!a.open(f.positional[0], err, false) || !b.open(f.positional[1], err, false)) die(err);
     // keys of b looked up in a (both ascending)
     unsigned long long missing = 0, mismatching = 0, tolerated = 0, toleratedLines = 0, same = 0;
     long long firstBad = -1;
@@ -872,7 +888,7 @@ int dbdiff(int argc, const char **argv) {
     return (mismatching == 0 && missing == 0 && onlyA == 0 && a.dbtype == b.dbtype) ? EXIT_SUCCESS : EXIT_FAILURE;
 }
 
-// iotest <pref|aln> <i:DB> <o:DB>: the text layer alone -- parse a prefilter / alignment DB into the records the kernels
+// iotest <pref|aln|seq> <i:DB> <o:DB>: the text layer alone -- parse a prefilter / alignment DB into the records the kernels
 // consume and write them back (no GPU involved).  The round trip must reproduce the input (dbdiff); the printed phase
 // times are the host-side cost of a drop-in step.
 int iotest(int argc, const char **argv) {
@@ -882,7 +898,7 @@ int iotest(int argc, const char **argv) {
     applyThreads(f);
     std::string err;
     mmdb::Reader in;
-    if (!in.open(f.positional[1], err)) die(err);
+    if (!in.open(f.positional[1], err, false)) die(err);
     ph.lap("open + index parse");
     if (f.positional[0] == "pref") {
         const PodArray<pg_hit> hits = parsePrefDb(in);
@@ -892,7 +908,13 @@ int iotest(int argc, const char **argv) {
         const PodArray<pg_aln> alns = parseAlnDb(in);
         ph.lap("parse alignments");
         writeAlnDb(f.positional[2], in.keys, alns.data(), alns.size());
-    } else die("iotest: first argument must be pref or aln");
+    } else if (f.positional[0] == "seq") {
+        // a sequence DB through the writer of the GPU commands' results (contiguous fast path or entry by entry)
+        mmdb::Reader seq;
+        if (!seq.open(f.positional[1], err)) die(err);
+        ph.lap("open sequence DB");
+        writeSeqArrays(f.positional[2], seq.dbtype, seq.data(), seq.dataBytes(), seq.offsets.data(), seq.lens.data(), seq.keys.data(), seq.size());
+    } else die("iotest: first argument must be pref, aln or seq");
     ph.lap("format + write");
     ph.report();
     timer.report();

@@ -40,13 +40,17 @@ static bool slurp(const std::string &p, std::vector<char> &out, size_t at) {
     return got == (size_t) sz;
 }
 
-Reader::~Reader() {
-    if (mapped) munmap(mapped, mappedBytes);
+void Reader::unmapAll() {
+    if (mapped) { munmap(mapped, mappedBytes); mapped = nullptr; }
+    for (const Seg &sg : segs) if (sg.p && sg.len) munmap(const_cast<char *>(sg.p), sg.len);
+    segs.clear();
 }
 
-bool Reader::open(const std::string &path, std::string &err) {
-    if (mapped) { munmap(mapped, mappedBytes); mapped = nullptr; }
-    owned.clear(); base = nullptr; bytes = 0;
+Reader::~Reader() { unmapAll(); }
+
+bool Reader::open(const std::string &path, std::string &err, bool contiguous) {
+    unmapAll();
+    base = nullptr; bytes = 0;
     if (fileExists(path)) {
         const int fd = ::open(path.c_str(), O_RDONLY);
         struct stat st;
@@ -72,7 +76,22 @@ bool Reader::open(const std::string &path, std::string &err) {
         }
         if (files.empty()) { err = "database " + path + " not found"; return false; }
         bytes = at.back();
-        if (bytes) {
+        if (bytes && !contiguous) {
+            // result DBs are only read entry by entry: map every file where it is, no copy
+            for (size_t f = 0; f < files.size(); f++) {
+                const size_t len = at[f + 1] - at[f];
+                Seg sg{nullptr, (uint64_t) at[f], len};
+                if (len) {
+                    const int fd = ::open(files[f].c_str(), O_RDONLY);
+                    void *m = fd < 0 ? MAP_FAILED : mmap(nullptr, len, PROT_READ, MAP_PRIVATE, fd, 0);
+                    if (fd >= 0) ::close(fd);
+                    if (m == MAP_FAILED) { err = "cannot map " + files[f]; return false; }
+                    madvise(m, len, MADV_WILLNEED);
+                    sg.p = (const char *) m;
+                }
+                if (len) segs.push_back(sg);
+            }
+        } else if (bytes) {
             mapped = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
             if (mapped == MAP_FAILED) { mapped = nullptr; err = "cannot allocate " + std::to_string(bytes) + " bytes for " + path; return false; }
             mappedBytes = bytes;
@@ -178,11 +197,26 @@ bool Reader::open(const std::string &path, std::string &err) {
     return true;
 }
 
-bool Writer::open(const std::string &p, int dbtype, std::string &err) {
+bool Writer::open(const std::string &p, int dbtype, std::string &err, bool splitData) {
     path = p;
-    fd = ::open(p.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    split = splitData;
+    // data files of an earlier DB of this name (either layout) must not survive next to the new one
+    ::unlink(p.c_str());
+    for (int k = 0; fileExists(p + "." + std::to_string(k)); k++) ::unlink((p + "." + std::to_string(k)).c_str());
+    fds.clear(); fileBytes.clear(); ents.clear();
+    if (split) {
+        fds.assign((size_t) hostThreads(), -1);
+        fileBytes.assign(fds.size(), 0);
+        for (size_t k = 0; k < fds.size(); k++) {
+            fds[k] = ::open((p + "." + std::to_string(k)).c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+            if (fds[k] < 0) { err = "cannot open " + p + "." + std::to_string(k) + " for writing"; return false; }
+        }
+        fd = -1;
+    } else {
+        fd = ::open(p.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    }
     fi = ::open((p + ".index").c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
-    if (fd < 0 || fi < 0) { err = "cannot open " + p + " for writing"; return false; }
+    if ((!split && fd < 0) || fi < 0) { err = "cannot open " + p + " for writing"; return false; }
     FILE *ft = fopen((p + ".dbtype").c_str(), "wb");
     if (!ft) { err = "cannot write dbtype"; return false; }
     const int32_t t = dbtype;
@@ -219,7 +253,10 @@ static inline void indexLine(std::string &out, uint32_t key, uint64_t off, uint6
 
 static void flushPending(Writer &w) {
     if (!w.pendData.empty()) {
-        if (!pwriteAll(w.fd, w.pendData.data(), w.pendData.size(), w.offset - w.pendData.size())) w.failed = true;
+        if (w.split) {
+            if (!pwriteAll(w.fds[0], w.pendData.data(), w.pendData.size(), w.fileBytes[0])) w.failed = true;
+            w.fileBytes[0] += w.pendData.size();
+        } else if (!pwriteAll(w.fd, w.pendData.data(), w.pendData.size(), w.offset - w.pendData.size())) w.failed = true;
         w.pendData.clear();
     }
     if (!w.pendIndex.empty()) {
@@ -230,9 +267,10 @@ static void flushPending(Writer &w) {
 }
 
 void Writer::write(uint32_t key, const char *bytes, size_t n) {
+    if (split) ents.push_back({key, (uint32_t) (n + 1), 0u, fileBytes[0] + pendData.size()});
+    else indexLine(pendIndex, key, offset, n + 1);
     pendData.append(bytes, n);
     pendData.push_back('\0');
-    indexLine(pendIndex, key, offset, n + 1);
     offset += n + 1;
     if (pendData.size() > (8u << 20)) flushPending(*this);
 }
@@ -244,6 +282,42 @@ void Writer::writeAll(size_t n, const std::function<uint32_t(size_t)> &keyOf, co
     const int T = hostThreads();
     size_t chunk = n / ((size_t) T * 8) + 1;
     chunk = std::max<size_t>(1024, std::min<size_t>(chunk, 65536));
+    if (split) {
+        // a data file per thread: every thread formats its chunks and appends them to ITS file -- no shared offsets, no barriers,
+        // no two threads on one inode.  The index is written by close().
+        const size_t entBase = ents.size();
+        ents.resize(entBase + n);
+        const size_t nChunks = (n + chunk - 1) / chunk;
+        bool badS = false;
+#pragma omp parallel num_threads(std::min<int>(T, (int) fds.size()))
+        {
+            const size_t t = (size_t) omp_get_thread_num();
+            std::string d;
+#pragma omp for schedule(static, 1)
+            for (size_t c = 0; c < nChunks; c++) {
+                d.clear();
+                const size_t lo = c * chunk, hi = std::min(n, lo + chunk);
+                uint64_t o = fileBytes[t];
+                for (size_t i = lo; i < hi; i++) {
+                    Ent &e = ents[entBase + i];
+                    if (skip && skip(i)) { e.len = 0xFFFFFFFFu; continue; }
+                    const size_t before = d.size();
+                    format(i, d);
+                    d.push_back('\0');
+                    e.key = keyOf(i); e.len = (uint32_t) (d.size() - before); e.file = (uint32_t) t; e.off = o + before;
+                }
+                if (!d.empty()) {
+                    if (!pwriteAll(fds[t], d.data(), d.size(), o)) {
+#pragma omp atomic write
+                        badS = true;
+                    }
+                    fileBytes[t] = o + d.size();
+                }
+            }
+        }
+        if (badS) failed = true;
+        return;
+    }
     const size_t wave = chunk * (size_t) T;
     std::vector<std::string> dbuf((size_t) T), ibuf((size_t) T);
     std::vector<std::vector<uint32_t>> elen((size_t) T);
@@ -309,9 +383,96 @@ void Writer::writeAll(size_t n, const std::function<uint32_t(size_t)> &keyOf, co
     if (bad) failed = true;
 }
 
+void Writer::writeContiguous(const char *data, uint64_t bytes, size_t n, const uint32_t *keys, const uint64_t *offsets, const uint32_t *lens) {
+    flushPending(*this);
+    if (split || offset != 0 || indexOffset != 0) { failed = true; return; }
+    const int T = hostThreads();
+    std::vector<std::string> ibuf((size_t) T);
+    bool bad = false;
+#pragma omp parallel num_threads(T)
+    {
+        const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+        if (t == 0) {
+            for (uint64_t o = 0; o < bytes; o += (64u << 20)) {
+                if (!pwriteAll(fd, data + o, (size_t) std::min<uint64_t>(64u << 20, bytes - o), o)) {
+#pragma omp atomic write
+                    bad = true;
+                }
+            }
+        }
+        // the index: every thread but the writer takes an equal share (all of it when there is only one thread)
+        const int workers = nt > 1 ? nt - 1 : 1, me = nt > 1 ? t - 1 : 0;
+        if (me >= 0) {
+            std::string &ix = ibuf[(size_t) (nt > 1 ? t : 0)];
+            const size_t lo = n * (size_t) me / (size_t) workers, hi = n * ((size_t) me + 1) / (size_t) workers;
+            ix.reserve((hi - lo) * 24);
+            for (size_t i = lo; i < hi; i++) indexLine(ix, keys[i], offsets[i], lens[i]);
+        }
+    }
+    uint64_t at = 0;
+    for (int t = 0; t < T; t++) {
+        const std::string &ix = ibuf[(size_t) t];
+        if (!ix.empty() && !pwriteAll(fi, ix.data(), ix.size(), at)) bad = true;
+        at += ix.size();
+    }
+    offset = bytes; indexOffset = at;
+    if (bad) failed = true;
+}
+
 bool Writer::close() {
     flushPending(*this);
     bool ok = !failed;
+    if (split) {
+        // files without data disappear, the others keep their order under consecutive numbers (a single one is named X);
+        // index offsets count through the files in that order
+        std::vector<uint64_t> base(fds.size(), 0);
+        std::vector<int> newIdx(fds.size(), -1);
+        int kept = 0;
+        uint64_t run = 0;
+        for (size_t k = 0; k < fds.size(); k++) {
+            if (fds[k] >= 0) ok &= ::close(fds[k]) == 0;
+            if (fileBytes[k]) { newIdx[k] = kept++; base[k] = run; run += fileBytes[k]; }
+        }
+        for (size_t k = 0; k < fds.size(); k++) {
+            const std::string from = path + "." + std::to_string(k);
+            if (newIdx[k] < 0) { ::unlink(from.c_str()); continue; }
+            const std::string to = kept == 1 ? path : path + "." + std::to_string(newIdx[k]);
+            if (to != from) ok &= ::rename(from.c_str(), to.c_str()) == 0;
+        }
+        if (kept == 0) {
+            const int e = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);      // an empty DB is an empty data file
+            if (e >= 0) ::close(e); else ok = false;
+        }
+        fds.clear();
+        // the index, in the order the entries were handed over (ascending keys)
+        const int T = hostThreads();
+        const size_t n = ents.size();
+        std::vector<std::string> ibuf((size_t) T);
+        std::vector<uint64_t> at((size_t) T + 1, 0);
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+        for (int t = 0; t < T; t++) {
+            std::string &ix = ibuf[(size_t) t];
+            const size_t lo = n * (size_t) t / (size_t) T, hi = n * ((size_t) t + 1) / (size_t) T;
+            ix.reserve((hi - lo) * 24);
+            for (size_t i = lo; i < hi; i++) {
+                const Ent &e = ents[i];
+                if (e.len == 0xFFFFFFFFu) continue;
+                indexLine(ix, e.key, base[e.file] + e.off, e.len);
+            }
+        }
+        for (int t = 0; t < T; t++) at[(size_t) t + 1] = at[(size_t) t] + ibuf[(size_t) t].size();
+        bool badI = false;
+#pragma omp parallel for num_threads(T) schedule(static, 1)
+        for (int t = 0; t < T; t++) {
+            const std::string &ix = ibuf[(size_t) t];
+            if (!ix.empty() && !pwriteAll(fi, ix.data(), ix.size(), indexOffset + at[(size_t) t])) {
+#pragma omp atomic write
+                badI = true;
+            }
+        }
+        if (badI) ok = false;
+        ents.clear(); ents.shrink_to_fit();
+    }
     if (fd >= 0) ok &= ::close(fd) == 0;
     if (fi >= 0) ok &= ::close(fi) == 0;
     fd = fi = -1;

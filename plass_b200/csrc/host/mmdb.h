@@ -29,33 +29,58 @@ struct Reader {
     Reader(const Reader &) = delete;
     Reader &operator=(const Reader &) = delete;
     ~Reader();
-    bool open(const std::string &path, std::string &err);
+    // contiguous = false: split data files X.0 .. X.k are mapped one by one (no copy) and only entry(i) may be used --
+    // enough for result DBs, which are parsed entry by entry; sequence DBs are uploaded as one buffer and need data().
+    bool open(const std::string &path, std::string &err, bool contiguous = true);
     size_t size() const { return keys.size(); }
-    const char *data() const { return base; }
+    const char *data() const { return base; }            // nullptr for a segmented reader
     size_t dataBytes() const { return bytes; }
-    const char *entry(size_t i) const { return base + offsets[i]; }
+    bool segmented() const { return !segs.empty(); }
+    const char *entry(size_t i) const {
+        const uint64_t o = offsets[i];
+        if (segs.empty()) return base + o;
+        size_t k = 0;
+        while (k + 1 < segs.size() && o >= segs[k + 1].start) k++;      // at most one file per writer thread
+        return segs[k].p + (o - segs[k].start);
+    }
 
 private:
-    const char *base = nullptr;      // mmap of the single data file, or `owned` (split data files X.0 .. X.k)
+    struct Seg { const char *p; uint64_t start; size_t len; };
+    const char *base = nullptr;      // mmap of the single data file, or one anonymous mapping filled from the split files
     size_t bytes = 0;
     void *mapped = nullptr;
     size_t mappedBytes = 0;
-    std::vector<char> owned;
+    std::vector<Seg> segs;           // split data files mapped one by one
+    void unmapAll();
 };
 
-// Writes entries (in ascending key order) as one data file + index + dbtype.
+// Writes entries (in ascending key order) as data file(s) + index + dbtype.
+// splitData = false: one data file X (DBWriter::close(merge = true): what the assembler leaves).
+// splitData = true:  one data file per host thread, X.0 .. X.k, index offsets into their concatenation (DBWriter::close without
+//   merge: what rescorediagonal leaves) -- buffered writes to ONE file serialise on its inode lock, so a single data file caps the
+//   writer at one core's page-cache copy rate however many threads format; with a file per thread the writes run in parallel.
+//   Files that received no data are not left behind, and a single non-empty file is named X.
 struct Writer {
     std::string path;
     int fd = -1, fi = -1;
     uint64_t offset = 0, indexOffset = 0;
     std::string pendData, pendIndex;     // sequential interface: buffered
     bool failed = false;
-    bool open(const std::string &path, int dbtype, std::string &err);
+    bool split = false;
+    std::vector<int> fds;                // split mode: the per-thread data files
+    std::vector<uint64_t> fileBytes;
+    struct Ent { uint32_t key; uint32_t len; uint32_t file; uint64_t off; };
+    std::vector<Ent> ents;               // split mode: the index is written at close(), once the files' final sizes are known
+    bool open(const std::string &path, int dbtype, std::string &err, bool splitData = false);
     void write(uint32_t key, const char *bytes, size_t n);   // appends '\0'
     // Entries i = 0 .. n-1 with key keyOf(i): format(i, out) APPENDS the entry's bytes (without the trailing '\0') to out and
     // may be called from any host thread, for any i, in any order; an entry for which `skip(i)` holds is not written.
     void writeAll(size_t n, const std::function<uint32_t(size_t)> &keyOf, const std::function<void(size_t, std::string &)> &format,
                   const std::function<bool(size_t)> &skip = nullptr);
+    // The entries already lie back to back, each with its trailing '\0', in `data` (offsets[i] + lens[i] == offsets[i + 1],
+    // offsets[0] == 0): the data file is that buffer, written by one thread in large pieces (one writer per inode is the fast
+    // way to fill a file through the page cache) while the others format the index.  Single-file mode, nothing written before.
+    void writeContiguous(const char *data, uint64_t bytes, size_t n, const uint32_t *keys, const uint64_t *offsets, const uint32_t *lens);
     bool close();
 };
 
