@@ -264,17 +264,44 @@ static inline const char *getI(const char *s, int32_t &v) {
     return s;
 }
 
-// Matcher::parseAlignmentRecord over a whole alignment DB (Matcher.cpp:190-320), entries in key order
-PodArray<pg_aln> parseAlnDb(const mmdb::Reader &aln) {
+// The sequence identity column as Util::fastSeqIdToBuffer prints it (Util.cpp:278-307): "1.00" or "0." + three digits.  For
+// these texts (float) (digits / 10^decimals) IS the correctly rounded float strtof returns -- checked for all 1001 + 101 values by
+// tests/test_host_cpu.py -- so the common case needs no strtof; anything else (exponent, more digits) goes to strtof.
+static inline const char *getSeqId(const char *s, float &v) {
+    while (*s == ' ' || *s == '\t') s++;
+    const char *p = s;
+    uint32_t num = 0; int ip = 0, dec = 0;
+    while (*p >= '0' && *p <= '9' && ip < 2) { num = num * 10 + (uint32_t) (*p - '0'); p++; ip++; }
+    if (ip == 1 && *p == '.') {
+        p++;
+        while (*p >= '0' && *p <= '9' && dec < 4) { num = num * 10 + (uint32_t) (*p - '0'); p++; dec++; }
+        if (dec >= 1 && dec <= 3 && (*p == '\t' || *p == ' ')) {
+            static const double den[4] = {1.0, 10.0, 100.0, 1000.0};
+            v = (float) ((double) num / den[dec]);
+            return p;
+        }
+    }
+    char *e;
+    v = strtof(s, &e);
+    return e;
+}
+
+// Matcher::parseAlignmentRecord over a whole alignment DB (Matcher.cpp:190-320), entries in key order.  withEvalue = false: the
+// E-value column is skipped (evalue = 0): neither the extension nor findassemblystart reads it, and strtod is most of a line's cost.
+PodArray<pg_aln> parseAlnDb(const mmdb::Reader &aln, bool withEvalue) {
     return parseParallel<pg_aln>(aln, 0, [&](size_t i, pg_aln *out) {
         const char *s = aln.entry(i);
         while (*s) {
             pg_aln a; a.query = aln.keys[i];
-            char *e;
             s = getU(s, a.target);
             s = getI(s, a.bits);
-            a.seq_id = strtof(s, &e);              // fastSeqIdToBuffer prints at most three decimals: float parsing is exact for them
-            a.evalue = strtod(e, &e);
+            const char *e = getSeqId(s, a.seq_id);
+            if (withEvalue) { char *e2; a.evalue = strtod(e, &e2); e = e2; }
+            else {
+                a.evalue = 0.0;
+                while (*e == ' ' || *e == '\t') e++;
+                while (*e && *e != '\t' && *e != ' ' && *e != '\n') e++;
+            }
             s = getI(e, a.q_start); s = getI(s, a.q_end); s = getI(s, a.q_len);
             s = getI(s, a.db_start); s = getI(s, a.db_end); s = getI(s, a.db_len);
             *out++ = a;
@@ -524,7 +551,7 @@ int extendCommand(int argc, const char **argv, bool nuclCommand) {
     const pg_ex_params p = exParams(f, nuclCommand);
     if (nuclCommand != nucl) die("sequence DB type does not match the command (assembleresults = amino acids, nuclassembleresults = nucleotides)");
     ph.lap("open + index parse");
-    const PodArray<pg_aln> alns = parseAlnDb(aln);
+    const PodArray<pg_aln> alns = parseAlnDb(aln, false);
     ph.lap("parse alignments");
     gpu();
     ph.lap("CUDA init");
@@ -618,7 +645,7 @@ int findassemblystart(int argc, const char **argv) {
     mmdb::Reader seq, aln;
     if (!seq.open(f.positional[0], err) || !aln.open(f.positional[1], err, false)) die(err);
     if (seq.dbtype != mmdb::DBTYPE_AMINO_ACIDS) die("findassemblystart expects an amino-acid sequence DB");
-    const PodArray<pg_aln> alns = parseAlnDb(aln);
+    const PodArray<pg_aln> alns = parseAlnDb(aln, false);
     pg_seqdb *db = uploadSeqDb(seq), *out = nullptr;
     if (pg_findassemblystart(gpu(), db, alns.data(), alns.size(), &out, nullptr) != 0) die(pg_last_error());
     writeSeqDb(out, f.positional[2], mmdb::DBTYPE_AMINO_ACIDS);
@@ -905,8 +932,22 @@ int iotest(int argc, const char **argv) {
         ph.lap("parse prefilter hits");
         writePrefDb(f.positional[2], in.dbtype == mmdb::DBTYPE_PREFILTER_REV_RES, in.keys, hits.data(), hits.size());
     } else if (f.positional[0] == "aln") {
-        const PodArray<pg_aln> alns = parseAlnDb(in);
+        const PodArray<pg_aln> alns = parseAlnDb(in, true);
         ph.lap("parse alignments");
+        {
+            // the parse the extension commands use (E-value column skipped) must agree in every other field
+            const PodArray<pg_aln> lean = parseAlnDb(in, false);
+            if (lean.size() != alns.size()) die("iotest: the two alignment parsers disagree on the number of lines");
+            for (size_t i = 0; i < alns.size(); i++) {
+                pg_aln a = alns.data()[i];
+                a.evalue = 0.0;
+                if (memcmp(&a, lean.data() + i, sizeof(pg_aln)) != 0 && !(a.query == lean.data()[i].query && a.target == lean.data()[i].target && a.bits == lean.data()[i].bits &&
+                        a.seq_id == lean.data()[i].seq_id && a.q_start == lean.data()[i].q_start && a.q_end == lean.data()[i].q_end && a.q_len == lean.data()[i].q_len &&
+                        a.db_start == lean.data()[i].db_start && a.db_end == lean.data()[i].db_end && a.db_len == lean.data()[i].db_len))
+                    die("iotest: the two alignment parsers disagree");
+            }
+            ph.lap("parse without E-values + compare");
+        }
         writeAlnDb(f.positional[2], in.keys, alns.data(), alns.size());
     } else if (f.positional[0] == "seq") {
         // a sequence DB through the writer of the GPU commands' results (contiguous fast path or entry by entry)
