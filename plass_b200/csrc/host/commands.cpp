@@ -288,7 +288,7 @@ static inline const char *getSeqId(const char *s, float &v) {
 
 // Matcher::parseAlignmentRecord over a whole alignment DB (Matcher.cpp:190-320), entries in key order.  withEvalue = false: the
 // E-value column is skipped (evalue = 0): neither the extension nor findassemblystart reads it, and strtod is most of a line's cost.
-PodArray<pg_aln> parseAlnDb(const mmdb::Reader &aln, bool withEvalue) {
+PodArray<pg_aln> parseAlnDb(const mmdb::Reader &aln, bool withEvalue, bool checkSeqId = false) {
     return parseParallel<pg_aln>(aln, 0, [&](size_t i, pg_aln *out) {
         const char *s = aln.entry(i);
         while (*s) {
@@ -296,6 +296,7 @@ PodArray<pg_aln> parseAlnDb(const mmdb::Reader &aln, bool withEvalue) {
             s = getU(s, a.target);
             s = getI(s, a.bits);
             const char *e = getSeqId(s, a.seq_id);
+            if (checkSeqId && a.seq_id != strtof(s, nullptr)) die("iotest: the sequence-identity parser disagrees with strtof");
             if (withEvalue) { char *e2; a.evalue = strtod(e, &e2); e = e2; }
             else {
                 a.evalue = 0.0;
@@ -932,7 +933,7 @@ int iotest(int argc, const char **argv) {
         ph.lap("parse prefilter hits");
         writePrefDb(f.positional[2], in.dbtype == mmdb::DBTYPE_PREFILTER_REV_RES, in.keys, hits.data(), hits.size());
     } else if (f.positional[0] == "aln") {
-        const PodArray<pg_aln> alns = parseAlnDb(in, true);
+        const PodArray<pg_aln> alns = parseAlnDb(in, true, true);      // every identity column cross-checked against strtof
         ph.lap("parse alignments");
         {
             // the parse the extension commands use (E-value column skipped) must agree in every other field
