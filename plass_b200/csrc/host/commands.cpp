@@ -352,14 +352,23 @@ template <class T, class KeyOf>
 std::vector<uint64_t> runStarts(const std::vector<uint32_t> &keys, const T *recs, uint64_t n, KeyOf keyOf) {
     std::vector<uint64_t> start(keys.size() + 1);
     const int nT = mmdb::hostThreads();
-#pragma omp parallel for num_threads(nT) schedule(static)
-    for (size_t i = 0; i < keys.size(); i++) {
+    // keys and records are both ascending: every thread finds the first record of its share of the keys by one binary search
+    // and walks on from there (a binary search per key is 20 cache misses per key)
+    const size_t nk = keys.size();
+#pragma omp parallel for num_threads(nT) schedule(static, 1)
+    for (int t = 0; t < nT; t++) {
+        const size_t a = nk * (size_t) t / (size_t) nT, b = nk * ((size_t) t + 1) / (size_t) nT;
+        if (a >= b) continue;
         uint64_t lo = 0, hi = n;
-        const uint32_t k = keys[i];
-        while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (keyOf(recs[mid]) < k) lo = mid + 1; else hi = mid; }
-        start[i] = lo;
+        while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (keyOf(recs[mid]) < keys[a]) lo = mid + 1; else hi = mid; }
+        uint64_t pos = lo;
+        for (size_t i = a; i < b; i++) {
+            const uint32_t k = keys[i];
+            while (pos < n && keyOf(recs[pos]) < k) pos++;
+            start[i] = pos;
+        }
     }
-    start[keys.size()] = n;
+    start[nk] = n;
     return start;
 }
 
