@@ -2149,7 +2149,7 @@ static int km_group_bucketed(Context *ctx, const KmConst &c, uint64_t nRecords, 
     Rec *sorted = nullptr;
     cudaEventRecord(ctx->ev[EV_SORT1_BEGIN], s);
     // the last partition pass knows every record's final position: it also leaves the bucket boundaries and the smallest
-    // k-mer (bulk-copy kernel); otherwise a sweep over the partitioned records finds them
+    // k-mer; otherwise (wide digits) a sweep over the partitioned records finds them
     const bool fusedBounds = radix_emits_bounds(plan);
     RadixBounds rb;
     rb.start = d_start; rb.end = d_end; rb.minKey = d_min; rb.hashMask = hashMask; rb.bucketMask = nBuckets - 1;

@@ -4,15 +4,20 @@
 // used at kmermatcher.cpp:408-412 (sort #1) and :427-431 (sort #2).
 //
 // Design (HBM-bound: every pass is one coalesced read + one coalesced write of the records):
-//   * one histogram kernel computes the 256-bin histograms of ALL passes in a single read,
-//   * per pass one "onesweep" kernel: a tile of 4096 records is ranked in registers with
+//   * one histogram kernel computes the 256-bin histograms of ALL passes in a single read -- or none at all when the producer of
+//     the records counted them on the way out (preHist: the extraction kernels do, for sort #1),
+//   * per pass one "onesweep" kernel: a tile of 3072 records is ranked in registers with
 //     warp match_any + warp-private counters, reordered through shared memory so that every digit
 //     run leaves the SM as contiguous 16-byte stores, and the tile's global offsets come from a
 //     decoupled look-back over per-tile status words (single pass, no second read of the data),
 //   * stable, so passes compose into a multi-word key sort.
-// Round 2: the 256-bin pass is a PERSISTENT kernel whose tiles arrive by bulk asynchronous copy (cp.async.bulk global ->
-// shared, completion on an mbarrier; SASS UBLKCP.S.G): tile i+1 travels while tile i is ranked, and every digit run leaves
-// the SM as one bulk shared -> global copy (UBLKCP.G.S) issued by the thread that owns the digit.
+//   * the last pass can leave by-products of the final order it alone knows: bucket bounds + smallest key (sort #1), segment
+//     bounds + smallest target per representative (sort #2) -- RadixBounds,
+//   * a pass can scatter straight into OTHER GPUs' memory (radix_scatter_peer: the multi-GPU exchanges).
+// Round 2 also built the pass as a PERSISTENT kernel whose tiles arrive by bulk asynchronous copy (cp.async.bulk global -> shared,
+// completion on an mbarrier; SASS UBLKCP.S.G) and whose digit runs leave as bulk shared -> global copies (UBLKCP.G.S).  Measured
+// slower than the register-tile kernel inside the iteration (3.5 vs 2.75 ms per pass): it stays selectable
+// (radix_set_mode 1..3 / PLASS_B200_RADIX_MODE) and parity-tested, the default is mode 0.
 #pragma once
 #include "pg_common.cuh"
 
