@@ -38,7 +38,10 @@ struct Flags {
 
 [[noreturn]] void die(const std::string &msg) {
     fprintf(stderr, "Error: %s\n", msg.c_str());
-    exit(EXIT_FAILURE);
+    fflush(stdout); fflush(stderr);
+    // EXIT() of the reference: the process ends here with EXIT_FAILURE.  Not exit(): the CUDA start-up may still be running in
+    // its helper thread, and static destructors (a joinable std::thread) would turn the error into an abort.
+    _exit(EXIT_FAILURE);
 }
 
 Flags parseFlags(int argc, const char **argv, size_t nPositional, const std::set<std::string> &known) {

@@ -73,6 +73,28 @@ def test_no_cpu_fallback():
     assert "no CUDA device" in str(e.value)
 
 
+def test_cli_errors_are_clean_failures(golden_root, tmp_path):
+    """The reference ends a command with EXIT_FAILURE and a message (EXIT(), Application.cpp); so does the drop-in: an unknown flag
+    or a flag value the GPU path does not implement is a hard error with exit status 1 -- not a fallback, and not an abort of
+    the process although the CUDA start-up is already running in its helper thread -- and so is a machine without a GPU."""
+    import subprocess
+    cli = os.path.join(ROOT, "plass_b200", "plass_b200_cli")
+    from common import golden_case
+    d, man = golden_case("synth_aa", golden_root)
+    seq = os.path.join(d, [x for x in man["steps"] if x["cmd"] == "kmermatcher"][0]["dbs"][0])
+    out = str(tmp_path / "x")
+    for args, needle in ((["kmermatcher", seq, out, "--bogus", "1"], "unknown parameter"),
+                         (["kmermatcher", seq, out, "--spaced-kmer-mode", "1"], "not supported"),
+                         (["rescorediagonal", seq, seq, out, out, "--rescore-mode", "1"], "not supported"),
+                         (["kmermatcher", str(tmp_path / "missing"), out], "")):
+        r = subprocess.run([cli] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 1 and "Error:" in r.stdout and needle in r.stdout, (args, r.returncode, r.stdout[-500:])
+    from plass_b200 import api
+    if api.load_library().pg_device_count() == 0:
+        r = subprocess.run([cli, "kmermatcher", seq, out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stdout, (r.returncode, r.stdout[-500:])
+
+
 def test_product_never_touches_the_oracle():
     pat = re.compile(r"oracle", re.I)
     for dirpath, _, files in os.walk(os.path.join(ROOT, "plass_b200")):
